@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- ISF+S(q) evaluations/s on BASELINE.json's C2 workload (N=256 He-4, M=170, 64 q), 3-D.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run)
+    python bench.py --impl reference ...                     (the CPU restatement of the reference estimators)
+
+A step = one pass of the hot path (rho_q build, tau-correlation, bin accumulation) over one batch of B synthetic
+walker configurations per GPU.  `value` = configurations evaluated per second over all ranks with beads resident
+in HBM; `e2e` = the same through the C ABI from pinned HOST buffers (H2D of every batch and D2H of the bin inside
+the timed region).  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from pimc_b200 import synth  # noqa: E402
+
+METRIC = "ISF+S(q) evaluations/sec (N=256 He-4, M=170, 64 q)"
+UNIT = "evaluations/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="walker configurations per GPU per step")
+    ap.add_argument("--workload", default="C2", choices=sorted(synth.SHAPES))
+    ap.add_argument("--rho-mode", type=int, default=-1, help="-1 library default, 0 generic sincos, 1 lattice recurrence")
+    ap.add_argument("--unique", type=int, default=16, help="distinct synthetic configurations generated per slot")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU work budget (core-seconds) of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def host_cores() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def workload_q(shape):
+    if shape.name == "C3":
+        n = np.stack(np.meshgrid(np.arange(-8, 9), np.arange(-8, 9), indexing="ij"), axis=-1).reshape(-1, 2)
+        return (2.0 * np.pi / shape.side) * n          # max_int "8 8": odometer order, last dim fastest
+    return synth.commensurate_q(shape.nq, shape.side)
+
+
+def algorithmic_flops(shape, nq):
+    """rho_q build and tau-correlation flop per evaluated configuration."""
+    rho = nq * shape.N * shape.M * (2 * shape.ndim + 40 + 2)
+    corr = nq * shape.M * (shape.M // 2 + 1) * 4
+    return rho, corr
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's estimators on the host cores (bounded sample, linear extrapolation)
+# --------------------------------------------------------------------------------------------------------------
+class CpuArm:
+    def __init__(self, shape, q, budget_core_s):
+        from oracle import oracle
+        self.orc = oracle.get(fast=True)
+        self.shape, self.q = shape, q
+        self.cores = host_cores()
+        self.beads = synth.gen_config(shape.N, shape.M, shape.ndim, shape.rho, shape.T)
+        # per-element cost estimates (ns per pair term, measured on the container's Xeon) only size the sample
+        isf_elem_s = shape.M * shape.N**2 * 25e-9
+        ssf_q_s = shape.M * shape.N * (shape.N - 1) / 2 * 40e-9
+        c = self.cores
+        self.n_elem = int(min(len(q) * shape.M, max(1, round(0.6 * budget_core_s / isf_elem_s / c)) * c))   # whole rounds of threads
+        n_ssf = 0.4 * budget_core_s / ssf_q_s
+        self.n_ssf = int(min(len(q), max(1, round(n_ssf / c)) * c if n_ssf >= c else max(1, round(n_ssf))))
+
+    def step(self):
+        """One bounded sample; returns (extrapolated seconds per full evaluation, wall seconds of the sample)."""
+        s, q = self.shape, self.q
+        t0 = time.perf_counter()
+        self.orc.isf_range(self.beads, s.N, q, 0, self.n_elem, nthreads=self.cores)
+        t1 = time.perf_counter()
+        self.orc.ssf(s.side, self.beads, s.N, q[:self.n_ssf], nthreads=min(self.cores, self.n_ssf))
+        t2 = time.perf_counter()
+        full = (t1 - t0) * (len(q) * s.M / self.n_elem) + (t2 - t1) * (len(q) / self.n_ssf)
+        return full, t2 - t0
+
+    def sample_text(self):
+        s = self.shape
+        return (f"1 configuration: {self.n_elem} of {len(self.q) * s.M} F(q,tau) elements (direct O(M N^2) loop each) + "
+                f"S(q) for {self.n_ssf} of {len(self.q)} q, {self.cores} threads, extrapolated linearly to the full q-set")
+
+
+def run_reference(args, shape, q):
+    """--impl reference: the reference's CPU algorithm (oracle port; the upstream sources need Boost/<mdspan> and do
+    not compile here) with all host threads.  Under torchrun only rank 0 works."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    total_steps = max(1, args.steps + args.warmup)
+    budget = min(args.cpu_seconds, 150.0 * host_cores() / total_steps)       # keep the whole run within minutes
+    arm = CpuArm(shape, q, budget)
+    for _ in range(args.warmup):
+        arm.step()
+    evals, wall = [], []
+    for _ in range(args.steps):
+        f, w = arm.step()
+        evals.append(f)
+        wall.append(w)
+    value = 1.0 / float(np.mean(evals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(wall)), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{shape.name}: N={shape.N} M={shape.M} nq={len(q)} ndim={shape.ndim}, CPU estimators"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": arm.sample_text()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+class DevPtr:
+    """CUDA array interface holder so torch can view the library's bin buffer without a copy."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------------------
+def run_ours(args, shape, q):
+    import torch
+    import torch.distributed as dist
+
+    from pimc_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B, K, W = args.batch, args.steps, args.warmup
+    ctx = api.Context(local, shape.ndim)
+    ctx.set_box(shape.side)
+    ctx.set_qvecs(q)
+    if args.rho_mode >= 0:
+        ctx.set_rho_mode(args.rho_mode)
+    nq = len(q)
+
+    # synthetic batches: `unique` distinct configurations per slot, cycled to B, different seeds per rank and slot
+    nslots = ctx.num_slots()
+    batch_bytes = B * shape.M * (shape.N + 3) * shape.ndim * 8
+    use_slots = nslots if nslots * batch_bytes > 140e6 else nslots        # rotate all slots; total footprint below
+    pinned = []
+    for sl in range(use_slots):
+        uniq = synth.gen_batch(shape, min(args.unique, B), first=1000 * rank + 100 * sl)
+        pa = api.PinnedArray((B,) + uniq.shape[1:])
+        for b in range(B):
+            pa.array[b] = uniq[b % len(uniq)]
+        pinned.append(pa)
+    for sl, pa in enumerate(pinned):
+        ctx.stage(pa.array, shape.N, slot=sl)
+    ctx.sync()
+    footprint_mb = use_slots * B * shape.M * 16 * ((shape.N + 15) // 16) * shape.ndim * 8 / 1e6
+
+    ext = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+    peak_tflops = ctx.fp64_peak_tflops(0.5)
+
+    def device_step(k):
+        ctx.select_slot(k % use_slots)
+        ctx.measure()
+
+    # ---- value: device-resident --------------------------------------------------------------------------
+    ctx.set_profiling(True)
+    for k in range(W):
+        device_step(k)
+    ctx.kernel_times(reset=True)
+    ctx.reset_bins()
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for k in range(K):
+        device_step(k)
+    if world > 1:
+        # the one collective of the path: sum the per-GPU bins onto rank 0 over NVLink (once per bin, not per step)
+        ptr, count = ctx.bins_device_ptr()
+        bins = torch.as_tensor(DevPtr(ptr, count), device=torch.device("cuda", local))
+        with torch.cuda.stream(ext):
+            dist.reduce(bins, dst=0, op=dist.ReduceOp.SUM)
+    e1.record(ext)
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    launches = ctx.launch_count() - launches0
+    ktimes = ctx.kernel_times(reset=True)
+    ctx.set_profiling(False)
+    value = world * B * K / (ms_total * 1e-3)
+    _, _, n_acc = ctx.read_bins()
+    assert n_acc == B * K, (n_acc, B, K)
+
+    # ---- e2e: host AoS buffers through the C ABI, H2D + D2H inside the timed region -------------------------
+    e2e = None
+    if not args.no_e2e:
+        Ke = max(4, min(K, 60))
+        ctx.reset_bins()
+        ctx.stage(pinned[0].array, shape.N)
+        for k in range(3):                               # warm-up of the pipelined loop
+            ctx.measure()
+            ctx.stage(pinned[(k + 1) % use_slots].array, shape.N)
+            ctx.read_bins()
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(Ke):
+            ctx.measure()                                               # async: kernels on batch k
+            ctx.stage(pinned[(k + 1) % use_slots].array, shape.N)       # H2D of batch k+1 overlaps them
+            ssf_bin, isf_bin, _ = ctx.read_bins()                       # D2H of the step's result (syncs)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * Ke / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(batch_bytes), "d2h_bytes_per_step": int((nq + nq * shape.M) * 8),
+               "steps": Ke, "path": "pimcb_stage_batch(pinned host AoS) + pimcb_measure + pimcb_read_bins, double-buffered"}
+
+    # ---- roofline of the dominant kernel (rho_q build) -------------------------------------------------------
+    rho_flop, corr_flop = algorithmic_flops(shape, nq)
+    rho_ms, rho_n = ktimes["rho"]
+    corr_ms, corr_n = ktimes["corr"]
+    bins_ms, _ = ktimes["bins"]
+    rho_avg_s = rho_ms * 1e-3 / max(1, rho_n)
+    achieved = B * rho_flop / rho_avg_s / 1e12 if rho_n else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("rho_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    alg_bytes = B * (8 * shape.ndim * shape.N * shape.M + 2 * 8 * nq * shape.M)
+    roofline = {
+        "kernel": "rho_lattice_kernel" if (args.rho_mode != 0) else "rho_generic_kernel",
+        "bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+        "frac": (achieved / peak_tflops) if achieved else None, "traffic": traffic,
+        "peak_source": "measured in this run: register-resident DFMA chains on all SMs (pimcb_measure_fp64_peak); "
+                       "MEASURED_PEAKS.json has no FP64 figure",
+        "flop_per_launch": B * rho_flop, "avg_launch_ms": rho_avg_s * 1e3, "launches_timed": rho_n,
+        "share_of_step": rho_ms / max(1e-12, rho_ms + corr_ms + bins_ms),
+        "hbm": {"achieved_gbs": alg_bytes / rho_avg_s / 1e9 if rho_n else None, "peak_gbs": hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"},
+        "corr_kernel": {"avg_launch_ms": corr_ms / max(1, corr_n), "achieved_tflops": B * corr_flop / (corr_ms * 1e-3 / max(1, corr_n)) / 1e12 if corr_n else None},
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{shape.name}: N={shape.N} M={shape.M} nq={nq} ndim={shape.ndim}, He-4 SVP density, "
+                               f"commensurate q, {B} walker configurations per GPU per step",
+                   "batch_per_gpu": B, "parallelism": f"walker-configuration sharding x{world}, one NCCL reduce of the bin",
+                   "l2": f"{use_slots} resident batches rotated ({footprint_mb:.0f} MB > 126 MB L2)",
+                   "rho_mode": args.rho_mode},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        arm = CpuArm(shape, q, args.cpu_seconds)
+        full_s, _ = arm.step()
+        line["cpu_baseline"] = {"value": 1.0 / full_s, "unit": UNIT, "cores": arm.cores, "kind": "port",
+                                "sample": arm.sample_text()}
+    else:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    for pa in pinned:
+        pa.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    shape = synth.SHAPES[args.workload]
+    q = workload_q(shape)
+    if args.impl == "reference":
+        run_reference(args, shape, q)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torch.distributed.run, one rank per GPU
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args, shape, q)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,142 @@
+/* pimc_b200.h -- C ABI of libpimc_b200.so, the B200 (sm_100a) implementation of the
+ * DelMaestroGroup/pimc measurement hot path: S(q), F(q,tau) and the per-slice pair-potential sums.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types, no exceptions, no
+ * exit()/assert across it.  Every entry point returns 0 on success or a negative PIMCB_E* code;
+ * pimcb_last_error() returns the message of the calling thread's last failure.
+ *
+ * Reference interfaces each entry point replaces are cited as file:line relative to the upstream
+ * tree.  The reference-side binding (EstimatorBase / LocalAction subclasses) is shown in
+ * INTEGRATION.md and implemented in pimc_b200/host/.
+ *
+ * Call pattern (one measurement, reference `EstimatorBase::accumulate()`, src/estimator.cpp:245-252):
+ *     pimcb_stage_beads(ctx, path.get_beads_data_pointer(), M, N, N_ext);   // snapshot, async H2D
+ *     pimcb_ssf(ctx, sf);  pimcb_isf(ctx, isf);                             // estimator += sf, isf
+ * A ctx is not thread-safe; distinct ctxs (one per device / process) are independent.
+ */
+#ifndef PIMC_B200_H
+#define PIMC_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pimcb_ctx pimcb_ctx;
+
+enum {
+    PIMCB_OK = 0,
+    PIMCB_EINVAL = -1,   /* bad argument / call order                                  */
+    PIMCB_ECUDA = -2,    /* a CUDA runtime call failed (message has the CUDA error)    */
+    PIMCB_ENOMEM = -3,   /* host or device allocation failed                           */
+    PIMCB_ESTATE = -4    /* required state missing (no box / q-vectors / beads / table) */
+};
+
+#define PIMCB_NPCFSEP 50 /* include/common.h:85, length of ActionBase::sepHist */
+
+/* ---- lifetime --------------------------------------------------------------------------------
+ * Replaces the ctor/dtor device bookkeeping of the shipped GPU estimator classes
+ * (src/estimator.cpp:3751-3817, 3976-4049): streams, cudaMallocAsync'd d_beads/d_qvecs/d_out. */
+int pimcb_create(pimcb_ctx** ctx, int device, int ndim);
+int pimcb_destroy(pimcb_ctx* ctx);
+const char* pimcb_last_error(void);
+/* Library/ABI version: major*10000 + minor*100 + patch. */
+int pimcb_version(void);
+
+/* ---- geometry and wave-vectors ----------------------------------------------------------------
+ * Container::side / periodic (include/container.h:24-59, src/container.cpp:84-144). */
+int pimcb_set_box(pimcb_ctx* ctx, const double* side /*[ndim]*/, const unsigned* periodic /*[ndim] or NULL = all 1*/);
+
+/* q-vectors in the AoS order produced by EstimatorBase::getQVectors (src/estimator.cpp:439-570),
+ * i.e. `qValues` / `qValues_dVec` (src/estimator.cpp:3668, 3886-3892).  Each q is classified as
+ * commensurate with the periodic box (q_i*side_i/2pi integer to 1e-9 in every periodic dimension,
+ * zero component in non-periodic ones) or not; commensurate q take the factorised path for S(q),
+ * the others the direct minimum-image pair sum. */
+int pimcb_set_qvecs(pimcb_ctx* ctx, const double* q_aos /*[nq][ndim]*/, int nq);
+/* Number of q-vectors classified commensurate (for diagnostics / tests). */
+int pimcb_num_commensurate(const pimcb_ctx* ctx);
+/* 0 = generic sincos-per-(q,bead) kernel, 1 = lattice-recurrence kernel when every q is commensurate
+ * (default 1).  Results agree to rounding; the switch exists for A/B measurement. */
+int pimcb_set_rho_mode(pimcb_ctx* ctx, int mode);
+
+/* ---- bead staging ------------------------------------------------------------------------------
+ * Replaces the per-call H2D of the whole padded AoS array + full sync
+ * (src/estimator.cpp:3833-3842, 4074-4085).  `beads_aos` is Path::get_beads_data_pointer()
+ * (include/path.h:208-210): row-major double[M][N_ext][ndim], active beads of every slice in columns
+ * [0,N) (diagonal configuration, src/estimator.cpp:228).  The call snapshots the beads (the caller may
+ * mutate them as soon as it returns) into the next pinned SoA buffer and enqueues the H2D copy on
+ * the ctx stream; staging is shared by every estimator using the ctx. */
+int pimcb_stage_beads(pimcb_ctx* ctx, const double* beads_aos, int M, int N, int N_ext);
+/* B independent configurations, contiguous double[B][M][N_ext][ndim] (walker batch). */
+int pimcb_stage_batch(pimcb_ctx* ctx, const double* beads_aos, int B, int M, int N, int N_ext);
+/* Same, into device slot `slot` (0 <= slot < pimcb_num_slots) without making it current; used to keep
+ * several batches resident.  pimcb_select_slot makes a staged slot the current input. */
+int pimcb_num_slots(const pimcb_ctx* ctx);
+int pimcb_stage_batch_slot(pimcb_ctx* ctx, int slot, const double* beads_aos, int B, int M, int N, int N_ext);
+int pimcb_select_slot(pimcb_ctx* ctx, int slot);
+/* Pinned host memory for callers that want zero-bounce staging (beads allocated here, or an existing
+ * allocation registered in place, are DMA'd directly as AoS and transposed on the device). */
+int pimcb_host_alloc(void** ptr, size_t bytes);
+int pimcb_host_free(void* ptr);
+int pimcb_host_register(void* ptr, size_t bytes);
+int pimcb_host_unregister(void* ptr);
+
+/* ---- estimators (per staged configuration) -------------------------------------------------------
+ * pimcb_ssf: replaces StaticStructureFactorEstimator::accumulate (src/estimator.cpp:3705-3737) and
+ *   StaticStructureFactorGpuEstimator::accumulate (:3822-3861).  out[b][q] = sf(q)/N, the value the
+ *   reference adds to `estimator` (CPU convention; norm 1/M is applied by EstimatorBase::output).
+ * pimcb_isf: replaces IntermediateScatteringFunctionEstimator::accumulate (:3923-3961) and the GPU
+ *   class (:4063-4100).  out[b][q*M + tau] = isf/N for tau = 0..M-1 (CPU column layout, norm 1/M).
+ * Both synchronise the ctx stream before returning. */
+int pimcb_ssf(pimcb_ctx* ctx, double* out /*[B][nq]*/);
+int pimcb_isf(pimcb_ctx* ctx, double* out /*[B][nq*M]*/);
+/* Both from one pass (rho_q is built once): either pointer may be NULL. */
+int pimcb_ssf_isf(pimcb_ctx* ctx, double* ssf_out, double* isf_out);
+
+/* ---- device-resident accumulation (bins) -----------------------------------------------------------
+ * `estimator += sf/N` / `estimator += isf/N` kept on the device across measurements so that only one
+ * D2H (and, multi-GPU, one reduce) happens per output bin (EstimatorBase::output, src/estimator.cpp:348-362).
+ * pimcb_measure enqueues rho_q build + tau-correlation (+ direct S(q) for non-commensurate q) + bin
+ * accumulation of all staged configurations on the ctx stream and returns without synchronising. */
+int pimcb_measure(pimcb_ctx* ctx);
+int pimcb_reset_bins(pimcb_ctx* ctx);
+/* Copies bins to the host (synchronises): ssf[nq], isf[nq*M] sums over accumulated configurations;
+ * *num_accumulated = configurations in the bin. */
+int pimcb_read_bins(pimcb_ctx* ctx, double* ssf /*[nq] or NULL*/, double* isf /*[nq*M] or NULL*/, long* num_accumulated);
+/* Device address of the contiguous bin buffer double[nq + nq*M] (ssf then isf), for a caller-side
+ * NCCL reduce over NVLink (one collective per bin).  *count = nq + nq*M. */
+int pimcb_bins_device_ptr(pimcb_ctx* ctx, void** dptr, size_t* count);
+int pimcb_sync(pimcb_ctx* ctx);
+/* The ctx's CUDA stream (cudaStream_t as void*) so that callers can order their own work after it. */
+int pimcb_stream(pimcb_ctx* ctx, void** stream);
+
+/* ---- pair potential -------------------------------------------------------------------------------
+ * Flat view of a TabulatedPotential (include/potential.h:148-157): lookupV / lookupdVdr, tableLength,
+ * dr, extV, extdVdr.  Tables are copied to the device once. */
+int pimcb_set_pair_table(pimcb_ctx* ctx, const double* V, const double* dVdr /*or NULL*/, int len, double dr,
+                         const double* extV /*[2]*/, const double* extdVdr /*[2] or NULL*/);
+/* All slices of all staged configurations in one pass.  Replaces M calls each of
+ * LocalAction::V(slice) (src/action.cpp:902-947; interaction part, worm factor 1) incl. its sepHist
+ * side effect (:216-224, bin = int(r/dSep)), and LocalAction::gradVSquared(slice) (:1188-1223;
+ * interaction part).  vint[b][M]; f2[b][M] or NULL; sephist[b][M][50] or NULL.
+ * `f2_parity`: -1 = every slice, 0/1 = only slices with slice%2 == f2_parity (others get 0). */
+int pimcb_pair_sums(pimcb_ctx* ctx, double* vint, double* f2, int* sephist, double dSep, int f2_parity);
+
+/* ---- measurement helpers (bench) --------------------------------------------------------------------
+ * Sustained FP64 DFMA throughput of the device in TFLOP/s (register-resident FMA chains on every SM,
+ * timed with CUDA events).  MEASURED_PEAKS.json carries no FP64 figure. */
+int pimcb_measure_fp64_peak(pimcb_ctx* ctx, double* tflops, double seconds_target);
+/* Per-kernel device time.  With profiling on, every kernel launch is bracketed by CUDA events on the stream it is
+ * launched on; pimcb_kernel_times synchronises, folds the pending event pairs into running totals and returns, per
+ * kernel id, the summed duration in ms and the number of launches since the last reset:
+ * [0]=rho_q build, [1]=tau-correlation, [2]=direct S(q), [3]=bin accumulate, [4]=pair sums, [5]=AoS->SoA transpose. */
+int pimcb_set_profiling(pimcb_ctx* ctx, int on);
+int pimcb_kernel_times(pimcb_ctx* ctx, double* ms_total /*[8]*/, long* count /*[8]*/, int reset);
+/* Number of kernel launches issued by this ctx since creation. */
+long pimcb_launch_count(const pimcb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIMC_B200_H */

@@ -1,0 +1,239 @@
+"""ctypes loader for the CPU oracle (oracle/pimc_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY.  Importable from tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py; the product package pimc_b200 never
+imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_up = C.POINTER(C.c_uint)
+
+NPCFSEP = 50
+
+
+def build(force: bool = False) -> None:
+    """Compile liboracle.so / liboracle_fast.so with oracle/Makefile (g++ only)."""
+    need = force or not all(os.path.exists(os.path.join(_HERE, n)) for n in ("liboracle.so", "liboracle_fast.so"))
+    if need:
+        subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True,
+                       stdout=subprocess.DEVNULL)
+
+
+def _dptr(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def _iptr(a):
+    return a.ctypes.data_as(_ip) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Oracle:
+    """Thin wrapper over one build of the oracle library (`fast=True` = reference optimisation flags)."""
+
+    def __init__(self, fast: bool = False):
+        build()
+        self.lib = C.CDLL(os.path.join(_HERE, "liboracle_fast.so" if fast else "liboracle.so"))
+        L = self.lib
+        L.orc_max_sep.restype = C.c_double
+        L.orc_max_sep.argtypes = [C.c_int, _dp, _up]
+        L.orc_aziz_rm.restype = C.c_double
+        L.orc_aziz_rm.argtypes = [C.c_int]
+        L.orc_potential_action.restype = C.c_double
+        L.orc_potential_action.argtypes = [_dp, _dp, C.c_int, _dp, _dp, C.c_double, C.c_double]
+        L.orc_deriv_potential_action_tau.restype = C.c_double
+        L.orc_deriv_potential_action_tau.argtypes = [C.c_double, C.c_double, C.c_int, _dp, _dp, C.c_double, C.c_double]
+        L.orc_deriv_potential_action_lambda.restype = C.c_double
+        L.orc_deriv_potential_action_lambda.argtypes = [C.c_double, C.c_int, _dp, C.c_double]
+        L.orc_time_slices.restype = C.c_int
+        L.orc_time_slices.argtypes = [C.c_double, C.c_double, C.c_int, _dp]
+        L.orc_qvectors.argtypes = [C.c_int, C.c_char_p, C.c_char_p, _dp, _dp, C.c_int]
+        L.orc_ssf.argtypes = [C.c_int, _dp, _up, _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp]
+        L.orc_ssf_mt.argtypes = L.orc_ssf.argtypes + [C.c_int]
+        L.orc_isf.argtypes = [C.c_int, _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int]
+        L.orc_isf_range.argtypes = [C.c_int, _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_long, C.c_long, C.c_int]
+        L.orc_isf_factorised.argtypes = [C.c_int, _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp]
+        L.orc_aziz_values.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int]
+        L.orc_aziz_table.argtypes = [C.c_int, C.c_double, _dp, _dp, _dp, C.c_int, _dp]
+        L.orc_table_V.argtypes = [C.c_int, _dp, C.c_int, C.c_double, _dp, _dp, _dp, C.c_int]
+        L.orc_pair_sums.argtypes = [C.c_int, _dp, _up, _dp, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int,
+                                    C.c_double, _dp, _dp, C.c_double, _dp, _dp, _ip, C.c_int]
+        L.orc_put_in_bc.argtypes = [C.c_int, _dp, _up, _dp, C.c_int]
+        L.orc_format_row.argtypes = [_dp, _dp, C.c_int, C.c_uint, C.c_char_p, C.c_int]
+        L.orc_dvec_to_string.argtypes = [C.c_int, _dp, C.c_char_p, C.c_int]
+
+    # -- geometry ------------------------------------------------------------------
+    @staticmethod
+    def _box(side, periodic):
+        side = _f64(side)
+        per = np.ascontiguousarray(periodic if periodic is not None else np.ones(len(side)), dtype=np.uint32)
+        return side, per
+
+    def max_sep(self, side, periodic=None) -> float:
+        side, per = self._box(side, periodic)
+        return self.lib.orc_max_sep(len(side), _dptr(side), per.ctypes.data_as(_up))
+
+    def put_in_bc(self, side, r, periodic=None):
+        side, per = self._box(side, periodic)
+        r = _f64(r).copy()
+        rc = self.lib.orc_put_in_bc(len(side), _dptr(side), per.ctypes.data_as(_up), _dptr(r), r.size // len(side))
+        assert rc == 0
+        return r
+
+    def time_slices(self, T, tau=0.0, P=0):
+        t = C.c_double(0.0)
+        M = self.lib.orc_time_slices(T, tau, P, C.byref(t))
+        return M, t.value
+
+    # -- wave-vectors --------------------------------------------------------------
+    def qvectors(self, qtype: str, text: str, side) -> np.ndarray:
+        side = _f64(side)
+        nd = len(side)
+        n = self.lib.orc_qvectors(nd, qtype.encode(), text.encode(), _dptr(side), None, 0)
+        if n < 0:
+            raise ValueError(f"orc_qvectors failed with {n}")
+        out = np.zeros((n, nd))
+        n2 = self.lib.orc_qvectors(nd, qtype.encode(), text.encode(), _dptr(side), _dptr(out), n)
+        assert n2 == n
+        return out
+
+    # -- estimators ----------------------------------------------------------------
+    @staticmethod
+    def _beads(beads):
+        beads = _f64(beads)
+        M, Next, nd = beads.shape
+        return beads, M, Next, nd
+
+    def ssf(self, side, beads, N, q, periodic=None, nthreads=1) -> np.ndarray:
+        """sf(q)/N as added to the estimator by one accumulate() call."""
+        beads, M, Next, nd = self._beads(beads)
+        side, per = self._box(side, periodic)
+        q = _f64(q)
+        out = np.zeros(len(q))
+        rc = self.lib.orc_ssf_mt(nd, _dptr(side), per.ctypes.data_as(_up), _dptr(beads), M, N, Next, _dptr(q),
+                                 len(q), _dptr(out), nthreads)
+        assert rc == 0
+        return out
+
+    def isf(self, beads, N, q, nthreads=1) -> np.ndarray:
+        """isf[q, tau]/N by the reference's direct O(Nq M^2 N^2) loop."""
+        beads, M, Next, nd = self._beads(beads)
+        q = _f64(q)
+        out = np.zeros((len(q), M))
+        rc = self.lib.orc_isf(nd, _dptr(beads), M, N, Next, _dptr(q), len(q), _dptr(out), nthreads)
+        assert rc == 0
+        return out
+
+    def isf_range(self, beads, N, q, e0, e1, nthreads=1) -> np.ndarray:
+        """Flattened elements [e0,e1) of isf[q*M+tau]/N (others left 0); bounded samples for CPU timing."""
+        beads, M, Next, nd = self._beads(beads)
+        q = _f64(q)
+        out = np.zeros(len(q) * M)
+        rc = self.lib.orc_isf_range(nd, _dptr(beads), M, N, Next, _dptr(q), len(q), _dptr(out), e0, e1, nthreads)
+        assert rc == 0
+        return out
+
+    def isf_factorised(self, beads, N, q) -> np.ndarray:
+        beads, M, Next, nd = self._beads(beads)
+        q = _f64(q)
+        out = np.zeros((len(q), M))
+        rc = self.lib.orc_isf_factorised(nd, _dptr(beads), M, N, Next, _dptr(q), len(q), _dptr(out))
+        assert rc == 0
+        return out
+
+    # -- pair potential --------------------------------------------------------------
+    def aziz_rm(self, year=1979) -> float:
+        return self.lib.orc_aziz_rm(year)
+
+    def aziz_values(self, r, which=0, year=1979) -> np.ndarray:
+        r = _f64(r)
+        out = np.zeros_like(r)
+        self.lib.orc_aziz_values(year, which, _dptr(r), _dptr(out), r.size)
+        return out
+
+    def aziz_table(self, max_sep, year=1979, second=False):
+        """(V, dVdr[, d2Vdr2], dr) lookup tables exactly as TabulatedPotential::initLookupTable builds them."""
+        dr = C.c_double(0.0)
+        n = self.lib.orc_aziz_table(year, max_sep, None, None, None, 0, C.byref(dr))
+        V = np.zeros(n)
+        dV = np.zeros(n)
+        d2V = np.zeros(n) if second else None
+        n2 = self.lib.orc_aziz_table(year, max_sep, _dptr(V), _dptr(dV), _dptr(d2V), n, C.byref(dr))
+        assert n2 == n
+        return (V, dV, d2V, dr.value) if second else (V, dV, dr.value)
+
+    def table_V(self, table, dr, sep, ext=(0.0, 0.0)) -> np.ndarray:
+        sep = _f64(sep)
+        nd = sep.shape[-1]
+        table = _f64(table)
+        ext = _f64(ext)
+        out = np.zeros(sep.shape[0])
+        rc = self.lib.orc_table_V(nd, _dptr(table), len(table), dr, _dptr(ext), _dptr(sep), _dptr(out), len(out))
+        assert rc == 0
+        return out
+
+    def pair_sums(self, side, beads, N, V, dVdr, dr, dSep, periodic=None, want_f2=True, want_hist=True,
+                  nthreads=1):
+        """Per-slice (Vint[M], gradVSquared[M] | None, sepHist[M,50] | None)."""
+        beads, M, Next, nd = self._beads(beads)
+        side, per = self._box(side, periodic)
+        V = _f64(V)
+        dVdr = _f64(dVdr) if dVdr is not None else None
+        ext = np.zeros(2)
+        vint = np.zeros(M)
+        f2 = np.zeros(M) if (want_f2 and dVdr is not None) else None
+        hist = np.zeros((M, NPCFSEP), dtype=np.int32) if want_hist else None
+        rc = self.lib.orc_pair_sums(nd, _dptr(side), per.ctypes.data_as(_up), _dptr(beads), M, N, Next, _dptr(V),
+                                    _dptr(dVdr), len(V), dr, _dptr(ext), _dptr(ext), dSep, _dptr(vint), _dptr(f2),
+                                    _iptr(hist), nthreads)
+        assert rc == 0
+        return vint, f2, hist
+
+    def potential_action(self, vint, f2, VFactor, gradVFactor, tau, lam) -> float:
+        vint = _f64(vint)
+        f2 = _f64(f2) if f2 is not None else np.zeros_like(vint)
+        vf, gf = _f64(VFactor), _f64(gradVFactor)
+        return self.lib.orc_potential_action(_dptr(vint), _dptr(f2), len(vint), _dptr(vf), _dptr(gf), tau, lam)
+
+    def deriv_potential_action_tau(self, vint_s, f2_s, slice_, VFactor, gradVFactor, tau, lam) -> float:
+        vf, gf = _f64(VFactor), _f64(gradVFactor)
+        return self.lib.orc_deriv_potential_action_tau(vint_s, f2_s, slice_, _dptr(vf), _dptr(gf), tau, lam)
+
+    def deriv_potential_action_lambda(self, f2_s, slice_, gradVFactor, tau) -> float:
+        gf = _f64(gradVFactor)
+        return self.lib.orc_deriv_potential_action_lambda(f2_s, slice_, _dptr(gf), tau)
+
+    # -- output formatting -----------------------------------------------------------
+    def format_row(self, estimator, norm, num_accumulated) -> str:
+        est, nrm = _f64(estimator), _f64(norm)
+        buf = C.create_string_buffer(16 * len(est) + 8)
+        n = self.lib.orc_format_row(_dptr(est), _dptr(nrm), len(est), num_accumulated, buf, len(buf))
+        assert n >= 0
+        return buf.value.decode()
+
+    def dvec_to_string(self, v) -> str:
+        v = _f64(v)
+        buf = C.create_string_buffer(64 * len(v))
+        self.lib.orc_dvec_to_string(len(v), _dptr(v), buf, len(buf))
+        return buf.value.decode()
+
+
+_cache = {}
+
+
+def get(fast: bool = False) -> Oracle:
+    if fast not in _cache:
+        _cache[fast] = Oracle(fast)
+    return _cache[fast]

@@ -1,0 +1,686 @@
+// pimc_oracle.cpp -- CPU ORACLE (test infrastructure, NOT product code).
+//
+// A from-scratch CPU restatement of the DelMaestroGroup/pimc measurement hot path,
+// used only as the checker for the CUDA library (tests/, __graft_entry__.smoke(),
+// bench.py's cpu_baseline / --impl reference legs).  The product library
+// (pimc_b200/csrc) never links, loads or calls anything in this file.
+//
+// PARITY STATUS: "parity unpinned" by reference fixtures -- the reference ships no
+// golden vectors, known-answer tests or fixtures for S(q), F(q,tau) or the pair
+// action, and its sources cannot be compiled here (Boost and
+// <mdspan> are absent).  The restatement is pinned instead by closed-form
+// known-answer tests (tests/test_oracle_kat.py) and by the reference's own
+// batched-vs-scalar 1e-9 rule reproduced on its sampleVector inputs.
+//
+// Every function cites the reference file:line (relative to the upstream tree) whose
+// arithmetic it follows.  Floating-point semantics: this file is compiled with
+// -ffp-contract=off so that each source-level operation is individually rounded
+// ("as written" IEEE semantics); the integer table index int(r/dr) of the pair
+// potential is compared bit-exactly against the GPU.
+//
+// Build: see oracle/Makefile  (g++ -O2 -ffp-contract=off -shared -fPIC).
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iterator>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+constexpr double kEPS = 1.0e-7;   // include/common.h:89
+constexpr int kNPCFSEP = 50;      // include/common.h:85
+
+// ---------------------------------------------------------------------------------
+// Periodic cell.  include/container.h:50-59 (putInBC), src/container.cpp:84-109, 117-144.
+// ---------------------------------------------------------------------------------
+struct Box {
+    int ndim;
+    double side[3], sideInv[3], pSide[3];
+    unsigned periodic[3];
+    double maxSep;
+};
+
+Box make_box(int ndim, const double* side, const unsigned* periodic) {
+    Box b{};
+    b.ndim = ndim;
+    double acc = 0.0;
+    for (int i = 0; i < ndim; ++i) {
+        b.side[i] = side[i];
+        b.sideInv[i] = 1.0 / side[i];                       // container.cpp:122
+        b.periodic[i] = periodic ? periodic[i] : 1u;
+        b.pSide[i] = b.periodic[i] * side[i];               // container.cpp:129
+        const double h = side[i] / (b.periodic[i] + 1u);    // container.cpp:136
+        acc += h * h;
+    }
+    b.maxSep = std::sqrt(acc);
+    return b;
+}
+
+template <int ND>
+inline void put_in_bc(const Box& b, double* r) {
+    // container.h:50-53: r[i] -= pSide[i] * floor(r[i]*sideInv[i] + 0.5)
+    for (int i = 0; i < ND; ++i)
+        r[i] -= b.pSide[i] * std::floor(r[i] * b.sideInv[i] + 0.5);
+}
+
+template <int ND>
+inline double dot(const double* a, const double* b) {
+    // include/array_math.h:210-216: result = T(); result += a[i]*b[i]
+    double result = 0.0;
+    for (int i = 0; i < ND; ++i) result += a[i] * b[i];
+    return result;
+}
+
+// AoS bead accessor: DynamicArray<dVec,2> beads(slice,ptcl), row-major, padded to
+// N_ext columns.  include/path.h:57-71,164; include/dynamic_array.h:55-386.
+template <int ND>
+inline const double* bead(const double* beads, int Next, int slice, int ptcl) {
+    return beads + (static_cast<size_t>(slice) * Next + ptcl) * ND;
+}
+
+// include/path.h:179-184 getSeparation(bead1,bead2) = putInBC(r(bead1) - r(bead2))
+template <int ND>
+inline void separation(const Box& b, const double* r1, const double* r2, double* sep) {
+    for (int i = 0; i < ND; ++i) sep[i] = r1[i] - r2[i];
+    put_in_bc<ND>(b, sep);
+}
+
+// ---------------------------------------------------------------------------------
+// Static structure factor.  src/estimator.cpp:3705-3737.
+// out[q] = sf(q)/numParticles  (the increment "estimator += sf/numParticles").
+// ---------------------------------------------------------------------------------
+template <int ND>
+void ssf_impl(const Box& box, const double* beads, int M, int N, int Next,
+              const double* q, int nq, double* out) {
+    for (int iq = 0; iq < nq; ++iq) {
+        const double* cq = q + static_cast<size_t>(iq) * ND;
+        double sf = 0.0;
+        for (int t = 0; t < M; ++t) {
+            for (int i = 0; i < N; ++i) {
+                sf += 1.0;                                   // :3726 bead1 == bead2 part
+                const double* r1 = bead<ND>(beads, Next, t, i);
+                for (int j = i + 1; j < N; ++j) {
+                    double sep[ND];
+                    separation<ND>(box, r1, bead<ND>(beads, Next, t, j), sep);
+                    sf += 2 * std::cos(dot<ND>(sep, cq));    // :3729
+                }
+            }
+        }
+        out[iq] = sf / N;                                    // :3736
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Intermediate scattering function, the reference's direct O(Nq M^2 N^2) loop.
+// src/estimator.cpp:3923-3961.  out[q*M + tau] = isf/numParticles.
+// Threading is over (q, tau) output elements only, so every output element is
+// accumulated in exactly the reference's order (t0 ascending, then i, then j).
+// ---------------------------------------------------------------------------------
+template <int ND>
+void isf_element_range(const double* beads, int M, int N, int Next, const double* q,
+                       int nq, double* out, long e0, long e1) {
+    (void)nq;
+    for (long e = e0; e < e1; ++e) {
+        const int iq = static_cast<int>(e / M);
+        const int tausep = static_cast<int>(e % M);
+        const double* cq = q + static_cast<size_t>(iq) * ND;
+        double acc = 0.0;
+        for (int t0 = 0; t0 < M; ++t0) {
+            const int t1 = (t0 + tausep) % M;                 // :3941
+            for (int i = 0; i < N; ++i) {
+                const double lq1 = dot<ND>(cq, bead<ND>(beads, Next, t0, i));   // :3946
+                const double c1 = std::cos(lq1), s1 = std::sin(lq1);
+                for (int j = 0; j < N; ++j) {
+                    const double lq2 = dot<ND>(cq, bead<ND>(beads, Next, t1, j)); // :3951
+                    acc += (c1 * std::cos(lq2) + s1 * std::sin(lq2));             // :3953
+                }
+            }
+        }
+        out[e] = acc / N;                                     // :3960
+    }
+}
+
+template <int ND>
+void isf_impl(const double* beads, int M, int N, int Next, const double* q, int nq,
+              double* out, int nthreads) {
+    const long total = static_cast<long>(nq) * M;
+    if (nthreads <= 1) {
+        isf_element_range<ND>(beads, M, N, Next, q, nq, out, 0, total);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int w = 0; w < nthreads; ++w) {
+        const long e0 = total * w / nthreads, e1 = total * (w + 1) / nthreads;
+        pool.emplace_back([=] { isf_element_range<ND>(beads, M, N, Next, q, nq, out, e0, e1); });
+    }
+    for (auto& th : pool) th.join();
+}
+
+// Factorised CPU variant: rho_q(t) = sum_i exp(i q.r_i(t)); F(q,tau) = sum_t0 Re[rho(t0) conj rho(t0+tau)].
+// Algebraically identical to the loop above (cos a cos b + sin a sin b summed over i,j
+// factorises exactly); validated against isf_impl in tests at small sizes and used
+// as the checker at sizes where the O(M^2 N^2) loop would take hours.
+template <int ND>
+void isf_fact_impl(const double* beads, int M, int N, int Next, const double* q, int nq,
+                   double* out) {
+    std::vector<double> C(M), S(M);
+    for (int iq = 0; iq < nq; ++iq) {
+        const double* cq = q + static_cast<size_t>(iq) * ND;
+        for (int t = 0; t < M; ++t) {
+            double c = 0.0, s = 0.0;
+            for (int i = 0; i < N; ++i) {
+                const double lq = dot<ND>(cq, bead<ND>(beads, Next, t, i));
+                c += std::cos(lq);
+                s += std::sin(lq);
+            }
+            C[t] = c; S[t] = s;
+        }
+        for (int tau = 0; tau < M; ++tau) {
+            double acc = 0.0;
+            for (int t0 = 0; t0 < M; ++t0) {
+                const int t1 = (t0 + tau) % M;
+                acc += C[t0] * C[t1] + S[t0] * S[t1];
+            }
+            out[static_cast<size_t>(iq) * M + tau] = acc / N;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Aziz HFDHE2 potential.  src/potential.cpp:1741-1909; include/potential.h:958-977.
+// ---------------------------------------------------------------------------------
+struct Aziz {
+    double rm, A, epsilon, alpha, beta, D, C6, C8, C10;
+
+    explicit Aziz(int year) {
+        if (year == 1987) {          // potential.cpp:1764-1774
+            epsilon = 10.948; rm = 2.9673; D = 1.4826; alpha = 10.43329537; beta = -2.27965105;
+            C6 = 1.36745214; C8 = 0.42123807; C10 = 0.17473318; A = 1.8443101E5;
+        } else if (year == 1995) {   // potential.cpp:1777-1787
+            epsilon = 10.956; rm = 2.9683; D = 1.438; alpha = 10.5717543; beta = -2.07758779;
+            C6 = 1.35186623; C8 = 0.4149514; C10 = 0.17151143; A = 1.86924404E5;
+        } else {                     // 1979 default, potential.cpp:1750-1760
+            epsilon = 10.8; rm = 2.9673; D = 1.241314; alpha = 13.353384; beta = 0.0;
+            C6 = 1.3732412; C8 = 0.4253785; C10 = 0.1781; A = 0.5448504E6;
+        }
+    }
+    // include/potential.h:962-964
+    double F(double x) const { return (x < D ? std::exp(-(D / x - 1.0) * (D / x - 1.0)) : 1.0); }
+    // include/potential.h:967-971
+    double dF(double x) const {
+        const double ix = 1.0 / x;
+        const double r = 2.0 * D * ix * ix * (D * ix - 1.0) * std::exp(-(D * ix - 1.0) * (D * ix - 1.0));
+        return (x < D ? r : 0.0);
+    }
+    // include/potential.h:975-980
+    double d2F(double x) const {
+        const double ix = 1.0 / x;
+        const double r = 2.0 * D * ix * ix * ix * (2.0 * D * D * D * ix * ix * ix - 4.0 * D * D * ix * ix - D * ix + 2.0)
+                         * std::exp(-(D * ix - 1.0) * (D * ix - 1.0));
+        return (x < D ? r : 0.0);
+    }
+    // src/potential.cpp:1822-1842
+    double valueV(double r) const {
+        const double x = r / rm;
+        const double Urep = A * std::exp(-alpha * x + beta * x * x);
+        if (x < kEPS) return 0.0;
+        else if (x < 0.01) return (epsilon * Urep);
+        else {
+            const double ix2 = 1.0 / (x * x);
+            const double ix6 = ix2 * ix2 * ix2;
+            const double ix8 = ix6 * ix2;
+            const double ix10 = ix8 * ix2;
+            const double Uatt = -(C6 * ix6 + C8 * ix8 + C10 * ix10) * F(x);
+            return (epsilon * (Urep + Uatt));
+        }
+    }
+    // src/potential.cpp:1849-1875
+    double valuedVdr(double r) const {
+        const double x = r / rm;
+        const double T1 = A * (-alpha + 2.0 * beta * x) * std::exp(-alpha * x + beta * x * x);
+        if (x < kEPS) return 0.0;
+        else if (x < 0.01) return ((epsilon / rm) * T1);
+        else {
+            const double ix = 1.0 / x;
+            const double ix2 = ix * ix;
+            const double ix6 = ix2 * ix2 * ix2;
+            const double ix7 = ix6 * ix;
+            const double ix8 = ix6 * ix2;
+            const double ix9 = ix8 * ix;
+            const double ix10 = ix8 * ix2;
+            const double ix11 = ix10 * ix;
+            const double T2 = (6.0 * C6 * ix7 + 8.0 * C8 * ix9 + 10.0 * C10 * ix11) * F(x);
+            const double T3 = -(C6 * ix6 + C8 * ix8 + C10 * ix10) * dF(x);
+            return ((epsilon / rm) * (T1 + T2 + T3));
+        }
+    }
+    // src/potential.cpp:1882-1909
+    double valued2Vdr2(double r) const {
+        const double x = r / rm;
+        const double abFactor2 = (alpha - 2.0 * beta * x) * (alpha - 2.0 * beta * x);
+        const double T1 = A * (2 * beta + abFactor2) * std::exp(-alpha * x + beta * x * x);
+        if (x < kEPS) return 0.0;
+        else if (x < 0.01) return ((epsilon / rm) * T1);
+        else {
+            const double ix = 1.0 / x;
+            const double ix2 = ix * ix;
+            const double ix6 = ix2 * ix2 * ix2;
+            const double ix7 = ix6 * ix;
+            const double ix8 = ix6 * ix2;
+            const double ix9 = ix8 * ix;
+            const double ix10 = ix8 * ix2;
+            const double ix11 = ix10 * ix;
+            const double ix12 = ix11 * ix;
+            const double T2 = -(42.0 * C6 * ix8 + 72.0 * C8 * ix10 + 110.0 * C10 * ix12) * F(x);
+            const double T3 = 2.0 * (6.0 * C6 * ix7 + 8.0 * C8 * ix9 + 10.0 * C10 * ix11) * dF(x);
+            const double T4 = -(C6 * ix6 + C8 * ix8 + C10 * ix10) * d2F(x);
+            return ((epsilon / (rm * rm)) * (T1 + T2 + T3 + T4));
+        }
+    }
+};
+
+// include/potential.h:249-260 TabulatedPotential::direct
+inline double table_direct(const double* table, int tableLength, double dr, const double* extVal, double r) {
+    const int k = int(r / dr);
+    if (k <= 0) return extVal[0];
+    if (k >= tableLength) return extVal[1];
+    return table[k];
+}
+
+struct PairTable {
+    const double* V; const double* dVdr; int len; double dr; double extV[2]; double extdVdr[2];
+};
+
+// LocalAction::V(slice), interaction part + sepHist side effect.
+// src/action.cpp:902-947 (+216-224 updateSepHist); worm factor == 1 on diagonal configurations
+// (include/worm.h:50, src/worm.cpp:108-118).  Separation is getSeparation(bead2,bead1), :934.
+template <int ND>
+double vint_slice(const Box& box, const PairTable& tab, const double* beads, int N, int Next,
+                  int slice, double dSep, int* sepHist) {
+    double totVint = 0.0;
+    if (sepHist) std::fill(sepHist, sepHist + kNPCFSEP, 0);    // :918
+    for (int i = 0; i < N; ++i) {
+        const double* r1 = bead<ND>(beads, Next, slice, i);
+        for (int j = i + 1; j < N; ++j) {
+            double sep[ND];
+            separation<ND>(box, bead<ND>(beads, Next, slice, j), r1, sep);
+            const double rnorm = std::sqrt(dot<ND>(sep, sep));
+            if (sepHist) {                                       // action.cpp:221-223
+                const int nR = int(rnorm / dSep);
+                if (nR >= 0 && nR < kNPCFSEP) ++sepHist[nR];
+            }
+            totVint += 1.0 * table_direct(tab.V, tab.len, tab.dr, tab.extV, rnorm);   // potential.h:985-989
+        }
+    }
+    return totVint;
+}
+
+// LocalAction::gradVSquared(slice), interaction part (external "free" potential has zero gradient).
+// src/action.cpp:1188-1223; AzizPotential::gradV include/potential.h:997-1003.
+template <int ND>
+double grad_v_squared_slice(const Box& box, const PairTable& tab, const double* beads, int N, int Next, int slice) {
+    double totF2 = 0.0;
+    for (int i = 0; i < N; ++i) {
+        double F[ND];
+        for (int d = 0; d < ND; ++d) F[d] = 0.0;
+        const double* r1 = bead<ND>(beads, Next, slice, i);
+        for (int j = 0; j < N; ++j) {
+            if (j == i) continue;                               // :1208
+            double sep[ND];
+            separation<ND>(box, r1, bead<ND>(beads, Next, slice, j), sep);   // :1211 getSeparation(bead1,bead2)
+            const double rnorm = std::sqrt(dot<ND>(sep, sep));
+            const double g = table_direct(tab.dVdr, tab.len, tab.dr, tab.extdVdr, rnorm) / rnorm;
+            for (int d = 0; d < ND; ++d) F[d] += g * sep[d];
+        }
+        totF2 += dot<ND>(F, F);                                 // :1219
+    }
+    return totF2;
+}
+
+// q-vector generation.  src/estimator.cpp:439-570.
+template <int ND>
+int qvectors_impl(const char* type_c, const char* input_c, const double* side, double* out, int max_out) {
+    const std::string inputType(type_c), input(input_c);
+    std::vector<std::array<double, ND>> qValues;
+    std::array<double, ND> q{};
+
+    std::istringstream iss(input);
+    std::vector<std::string> tokens{std::istream_iterator<std::string>{iss}, std::istream_iterator<std::string>{}};
+    if (tokens.size() < 1) return -1;                           // :450-455 (reference exits)
+
+    if ((inputType == "int") || (inputType == "float")) {       // :458-472
+        if (tokens.size() % ND != 0) return -2;
+        for (size_t i = 0; i < tokens.size(); i += ND) {
+            for (int j = 0; j < ND; ++j) {
+                if (inputType == "int") q[j] = (2.0 * M_PI / side[j]) * std::stoi(tokens[i + j]);
+                else q[j] = std::stof(tokens[i + j]);           // float precision, :466
+            }
+            qValues.push_back(q);
+        }
+    }
+    if ((inputType == "max_int") || (inputType == "max_float")) {   // :475-537
+        if (static_cast<int>(tokens.size()) < ND) return -2;
+        std::array<int, ND> q_max_int{}, _q_int{};
+        std::array<double, ND> q_max{};
+        for (int i = 0; i < ND; ++i) {
+            if (inputType == "max_int") {
+                q_max_int[i] = std::abs(std::stoi(tokens[i]));
+                q_max[i] = q_max_int[i] * 2.0 * M_PI / side[i];
+            } else {
+                q_max[i] = std::stof(tokens[i]);
+            }
+        }
+        const double q_mag_max = std::sqrt(dot<ND>(q_max.data(), q_max.data()));
+        double q_mag;
+        if (inputType == "max_float")
+            for (int i = 0; i < ND; ++i)
+                q_max_int[i] = 1 + static_cast<int>(q_mag_max * side[i] / 2.0 / M_PI);
+        int n_q = 1;
+        for (int i = 0; i < ND; ++i) {
+            n_q *= 2 * q_max_int[i] + 1;
+            _q_int[i] = -q_max_int[i];
+            q[i] = _q_int[i] * 2.0 * M_PI / side[i];
+        }
+        q_mag = std::sqrt(dot<ND>(q.data(), q.data()));
+        if (q_mag <= q_mag_max) qValues.push_back(q);
+        int pos = ND - 1;
+        int count = 0;
+        while (count < n_q - 1) {
+            if (_q_int[pos] == q_max_int[pos]) {
+                _q_int[pos] = -q_max_int[pos];
+                pos -= 1;
+            } else {
+                _q_int[pos] += 1;
+                for (int i = 0; i < ND; ++i) q[i] = _q_int[i] * 2.0 * M_PI / side[i];
+                q_mag = std::sqrt(dot<ND>(q.data(), q.data()));
+                if (q_mag <= q_mag_max) qValues.push_back(q);
+                count += 1;
+                pos = ND - 1;
+            }
+        }
+    }
+    if (inputType == "file_int") {                              // :540-553
+        std::ifstream file(input);
+        if (!file) return -3;
+        std::string line;
+        while (std::getline(file, line)) {
+            std::istringstream ls(line);
+            std::vector<int> d((std::istream_iterator<int>(ls)), std::istream_iterator<int>());
+            if (static_cast<int>(d.size()) != ND) return -2;
+            for (int i = 0; i < ND; ++i) q[i] = (2.0 * M_PI / side[i]) * d[i];
+            qValues.push_back(q);
+        }
+    }
+    if (inputType == "file_float") {                            // :556-569
+        std::ifstream file(input);
+        if (!file) return -3;
+        std::string line;
+        while (std::getline(file, line)) {
+            std::istringstream ls(line);
+            std::vector<float> d((std::istream_iterator<float>(ls)), std::istream_iterator<float>());
+            if (static_cast<int>(d.size()) != ND) return -2;
+            for (int i = 0; i < ND; ++i) q[i] = d[i];
+            qValues.push_back(q);
+        }
+    }
+    const int n = static_cast<int>(qValues.size());
+    if (out) {
+        if (n > max_out) return -4;
+        for (int k = 0; k < n; ++k)
+            for (int d = 0; d < ND; ++d) out[static_cast<size_t>(k) * ND + d] = qValues[k][d];
+    }
+    return n;
+}
+
+}  // namespace
+
+#define ORC_DISPATCH(ndim, CALL)                 \
+    switch (ndim) {                              \
+        case 1: { constexpr int ND = 1; CALL; } break; \
+        case 2: { constexpr int ND = 2; CALL; } break; \
+        case 3: { constexpr int ND = 3; CALL; } break; \
+        default: return -100;                    \
+    }
+
+extern "C" {
+
+// Returns maxSep (src/container.cpp:100,136).
+double orc_max_sep(int ndim, const double* side, const unsigned* periodic) {
+    return make_box(ndim, side, periodic).maxSep;
+}
+
+int orc_put_in_bc(int ndim, const double* side, const unsigned* periodic, double* r, int count) {
+    const Box b = make_box(ndim, side, periodic);
+    ORC_DISPATCH(ndim, for (int k = 0; k < count; ++k) put_in_bc<ND>(b, r + static_cast<size_t>(k) * ND));
+    return 0;
+}
+
+int orc_qvectors(int ndim, const char* type, const char* input, const double* side, double* out, int max_out) {
+    int n = -100;
+    ORC_DISPATCH(ndim, n = qvectors_impl<ND>(type, input, side, out, max_out));
+    return n;
+}
+
+int orc_ssf(int ndim, const double* side, const unsigned* periodic, const double* beads, int M, int N,
+            int Next, const double* q, int nq, double* out) {
+    const Box b = make_box(ndim, side, periodic);
+    ORC_DISPATCH(ndim, ssf_impl<ND>(b, beads, M, N, Next, q, nq, out));
+    return 0;
+}
+
+// Threaded over q for the all-host-cores CPU baseline (q is the outermost independent loop,
+// src/estimator.cpp:3715); each q's accumulation order is the reference's.
+int orc_ssf_mt(int ndim, const double* side, const unsigned* periodic, const double* beads, int M, int N,
+               int Next, const double* q, int nq, double* out, int nthreads) {
+    const Box b = make_box(ndim, side, periodic);
+    if (nthreads < 1) nthreads = 1;
+    std::vector<std::thread> pool;
+    for (int w = 0; w < nthreads; ++w) {
+        const int q0 = static_cast<int>(static_cast<long>(nq) * w / nthreads);
+        const int q1 = static_cast<int>(static_cast<long>(nq) * (w + 1) / nthreads);
+        if (q1 <= q0) continue;
+        pool.emplace_back([=, &b] {
+            switch (ndim) {
+                case 1: ssf_impl<1>(b, beads, M, N, Next, q + q0 * 1, q1 - q0, out + q0); break;
+                case 2: ssf_impl<2>(b, beads, M, N, Next, q + q0 * 2, q1 - q0, out + q0); break;
+                default: ssf_impl<3>(b, beads, M, N, Next, q + q0 * 3, q1 - q0, out + q0); break;
+            }
+        });
+    }
+    for (auto& th : pool) th.join();
+    return 0;
+}
+
+int orc_isf(int ndim, const double* beads, int M, int N, int Next, const double* q, int nq, double* out,
+            int nthreads) {
+    ORC_DISPATCH(ndim, isf_impl<ND>(beads, M, N, Next, q, nq, out, nthreads));
+    return 0;
+}
+
+// Elements [e0,e1) of the flattened isf[q*M + tau] array only (bounded CPU-baseline samples: every element
+// costs the same M*N^2 terms, so a sample extrapolates linearly to the full Nq*M set).
+int orc_isf_range(int ndim, const double* beads, int M, int N, int Next, const double* q, int nq, double* out,
+                  long e0, long e1, int nthreads) {
+    if (e0 < 0 || e1 > static_cast<long>(nq) * M || e0 > e1) return -5;
+    if (nthreads < 1) nthreads = 1;
+    std::vector<std::thread> pool;
+    for (int w = 0; w < nthreads; ++w) {
+        const long a = e0 + (e1 - e0) * w / nthreads, b = e0 + (e1 - e0) * (w + 1) / nthreads;
+        if (b <= a) continue;
+        pool.emplace_back([=] {
+            switch (ndim) {
+                case 1: isf_element_range<1>(beads, M, N, Next, q, nq, out, a, b); break;
+                case 2: isf_element_range<2>(beads, M, N, Next, q, nq, out, a, b); break;
+                default: isf_element_range<3>(beads, M, N, Next, q, nq, out, a, b); break;
+            }
+        });
+    }
+    for (auto& th : pool) th.join();
+    return (ndim < 1 || ndim > 3) ? -100 : 0;
+}
+
+int orc_isf_factorised(int ndim, const double* beads, int M, int N, int Next, const double* q, int nq,
+                       double* out) {
+    ORC_DISPATCH(ndim, isf_fact_impl<ND>(beads, M, N, Next, q, nq, out));
+    return 0;
+}
+
+// Aziz scalar functions (which: 0=V, 1=dV/dr, 2=d2V/dr2).
+int orc_aziz_values(int year, int which, const double* r, double* out, int count) {
+    const Aziz az(year);
+    for (int k = 0; k < count; ++k)
+        out[k] = which == 0 ? az.valueV(r[k]) : which == 1 ? az.valuedVdr(r[k]) : az.valued2Vdr2(r[k]);
+    return 0;
+}
+
+double orc_aziz_rm(int year) { return Aziz(year).rm; }
+
+// TabulatedPotential::initLookupTable, include/potential.h:163-183: dr = 1e-6*rm
+// (src/potential.cpp:1796), tableLength = int(maxSep/dr), r accumulated by r += dr.
+// Call with V == NULL to get the table length.
+int orc_aziz_table(int year, double maxSep, double* V, double* dVdr, double* d2Vdr2, int len_in, double* dr_out) {
+    const Aziz az(year);
+    const double dr = (1.0E-6) * az.rm;
+    const int tableLength = int(maxSep / dr);
+    if (dr_out) *dr_out = dr;
+    if (!V) return tableLength;
+    if (len_in < tableLength) return -4;
+    double r = 0;
+    for (int n = 0; n < tableLength; ++n) {
+        V[n] = az.valueV(r);
+        if (dVdr) dVdr[n] = az.valuedVdr(r);
+        if (d2Vdr2) d2Vdr2[n] = az.valued2Vdr2(r);
+        r += dr;
+    }
+    return tableLength;
+}
+
+// Tabulated potential evaluated on explicit separation vectors: the scalar V(dVec) path and the
+// batched V(const dVec*, double*, int) default (src/potential.cpp:127-132) are the same loop.
+int orc_table_V(int ndim, const double* table, int len, double dr, const double* ext, const double* sep,
+                double* out, int count) {
+    if (count < 0) return -5;   // reference throws std::runtime_error on negative count
+    ORC_DISPATCH(ndim, for (int k = 0; k < count; ++k) {
+        const double* s = sep + static_cast<size_t>(k) * ND;
+        out[k] = table_direct(table, len, dr, ext, std::sqrt(dot<ND>(s, s)));
+    });
+    return 0;
+}
+
+// Per-slice pair sums for all slices: vint[M], f2[M] (may be NULL), sephist[M][50] (may be NULL).
+int orc_pair_sums(int ndim, const double* side, const unsigned* periodic, const double* beads, int M, int N,
+                  int Next, const double* V, const double* dVdr, int len, double dr, const double* extV,
+                  const double* extdVdr, double dSep, double* vint, double* f2, int* sephist, int nthreads) {
+    const Box b = make_box(ndim, side, periodic);
+    PairTable tab{V, dVdr, len, dr, {extV[0], extV[1]}, {extdVdr ? extdVdr[0] : 0.0, extdVdr ? extdVdr[1] : 0.0}};
+    if (nthreads < 1) nthreads = 1;
+    auto work = [&](int s0, int s1) {
+        for (int s = s0; s < s1; ++s) {
+            int* h = sephist ? sephist + static_cast<size_t>(s) * kNPCFSEP : nullptr;
+            if (vint) {
+                if (ndim == 1) vint[s] = vint_slice<1>(b, tab, beads, N, Next, s, dSep, h);
+                else if (ndim == 2) vint[s] = vint_slice<2>(b, tab, beads, N, Next, s, dSep, h);
+                else vint[s] = vint_slice<3>(b, tab, beads, N, Next, s, dSep, h);
+            }
+            if (f2) {
+                if (ndim == 1) f2[s] = grad_v_squared_slice<1>(b, tab, beads, N, Next, s);
+                else if (ndim == 2) f2[s] = grad_v_squared_slice<2>(b, tab, beads, N, Next, s);
+                else f2[s] = grad_v_squared_slice<3>(b, tab, beads, N, Next, s);
+            }
+        }
+    };
+    if (ndim < 1 || ndim > 3) return -100;
+    if (nthreads == 1) { work(0, M); return 0; }
+    std::vector<std::thread> pool;
+    for (int w = 0; w < nthreads; ++w) {
+        const int s0 = static_cast<int>(static_cast<long>(M) * w / nthreads);
+        const int s1 = static_cast<int>(static_cast<long>(M) * (w + 1) / nthreads);
+        if (s1 > s0) pool.emplace_back(work, s0, s1);
+    }
+    for (auto& th : pool) th.join();
+    return 0;
+}
+
+// LocalAction::potentialAction(), src/action.cpp:456-472, from per-slice sums (Vext == 0 for the
+// "free" external potential): totU += VFactor[eo]*tau*(Vext+Vint); if gradVFactor[eo] > EPS
+// totU += gradVFactor[eo]*tau^3*lambda*gradVSquared(slice).
+double orc_potential_action(const double* vint, const double* f2, int M, const double* VFactor,
+                            const double* gradVFactor, double tau, double lambda) {
+    double totU = 0.0;
+    for (int slice = 0; slice < M; ++slice) {
+        const int eo = slice % 2;
+        totU += VFactor[eo] * tau * (0.0 + vint[slice]);
+        if (gradVFactor[eo] > kEPS)
+            totU += gradVFactor[eo] * tau * tau * tau * lambda * f2[slice];
+    }
+    return totU;
+}
+
+// LocalAction::derivPotentialActionTau(slice), src/action.cpp:751-765.
+double orc_deriv_potential_action_tau(double vint_s, double f2_s, int slice, const double* VFactor,
+                                      const double* gradVFactor, double tau, double lambda) {
+    const int eo = slice % 2;
+    double dU = VFactor[eo] * (0.0 + vint_s);
+    if (gradVFactor[eo] > kEPS) dU += 3.0 * gradVFactor[eo] * tau * tau * lambda * f2_s;
+    return dU;
+}
+
+// LocalAction::derivPotentialActionLambda(slice), src/action.cpp:798-806.
+double orc_deriv_potential_action_lambda(double f2_s, int slice, const double* gradVFactor, double tau) {
+    const int eo = slice % 2;
+    if (gradVFactor[eo] > kEPS) return gradVFactor[eo] * tau * tau * tau * f2_s;
+    return 0.0;
+}
+
+// EstimatorBase::output(), src/estimator.cpp:348-362: estimator *= norm/numAccumulated, then
+// boost::format("%16.8E") per column.  Writes the formatted row (no newline) into buf.
+int orc_format_row(const double* estimator, const double* norm, int numEst, unsigned numAccumulated,
+                   char* buf, int buflen) {
+    int off = 0;
+    for (int n = 0; n < numEst; ++n) {
+        const double v = estimator[n] * (norm[n] / (1.0 * numAccumulated));
+        const int w = std::snprintf(buf + off, buflen - off, "%16.8E", v);
+        if (w < 0 || off + w >= buflen) return -4;
+        off += w;
+    }
+    return off;
+}
+
+// EstimatorBase::dVecToString, src/estimator.cpp:421-429.
+int orc_dvec_to_string(int ndim, const double* v, char* buf, int buflen) {
+    int off = std::snprintf(buf, buflen, "(");
+    for (int i = 0; i < ndim; ++i) {
+        off += std::snprintf(buf + off, buflen - off, "%+15.8E", v[i]);
+        if (i < ndim - 1) off += std::snprintf(buf + off, buflen - off, ",");
+    }
+    off += std::snprintf(buf + off, buflen - off, ")");
+    return off;
+}
+
+// Number of time slices from (T, tau) or explicit P: src/setup.cpp:998-1012.  Returns M, writes tau.
+int orc_time_slices(double T, double tau_in, int P_in, double* tau_out) {
+    int numTimeSlices;
+    double tau;
+    if (P_in <= 0) {
+        tau = tau_in;
+        numTimeSlices = static_cast<int>(1.0 / (T * tau) + kEPS);
+        if ((numTimeSlices % 2) != 0) numTimeSlices--;
+    } else {
+        numTimeSlices = P_in;
+        if ((numTimeSlices % 2) != 0) numTimeSlices--;
+        tau = 1.0 / (T * numTimeSlices);
+    }
+    if (tau_out) *tau_out = tau;
+    return numTimeSlices;
+}
+
+}  // extern "C"

@@ -1,0 +1,283 @@
+"""ctypes binding of libpimc_b200.so (include/pimc_b200.h).
+
+Thin by design: one Python method per C entry point, numpy arrays in and out, errors raised as
+`PimcbError` carrying pimcb_last_error().  There is no CPU fallback: if the library or a CUDA device is
+missing the constructor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_up = C.POINTER(C.c_uint)
+NPCFSEP = 50
+
+# every symbol include/pimc_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "pimcb_create", "pimcb_destroy", "pimcb_last_error", "pimcb_version", "pimcb_set_box", "pimcb_set_qvecs",
+    "pimcb_num_commensurate", "pimcb_set_rho_mode", "pimcb_stage_beads", "pimcb_stage_batch", "pimcb_num_slots",
+    "pimcb_stage_batch_slot", "pimcb_select_slot", "pimcb_host_alloc", "pimcb_host_free", "pimcb_host_register",
+    "pimcb_host_unregister", "pimcb_ssf", "pimcb_isf", "pimcb_ssf_isf", "pimcb_measure", "pimcb_reset_bins",
+    "pimcb_read_bins", "pimcb_bins_device_ptr", "pimcb_sync", "pimcb_stream", "pimcb_set_pair_table",
+    "pimcb_pair_sums", "pimcb_measure_fp64_peak", "pimcb_set_profiling", "pimcb_kernel_times",
+    "pimcb_launch_count",
+]
+
+
+class PimcbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    """dlopen the in-tree library (never builds implicitly on import; build via __graft_entry__.build())."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or _build.LIB
+    if not os.path.exists(path):
+        raise PimcbError(f"{path} is missing: run `python -m pimc_b200.build` (nvcc, sm_100a) first")
+    lib = C.CDLL(path)
+    vp = C.c_void_p
+    lib.pimcb_last_error.restype = C.c_char_p
+    lib.pimcb_launch_count.restype = C.c_long
+    lib.pimcb_launch_count.argtypes = [vp]
+    lib.pimcb_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int]
+    lib.pimcb_destroy.argtypes = [vp]
+    lib.pimcb_set_box.argtypes = [vp, _dp, _up]
+    lib.pimcb_set_qvecs.argtypes = [vp, _dp, C.c_int]
+    lib.pimcb_num_commensurate.argtypes = [vp]
+    lib.pimcb_set_rho_mode.argtypes = [vp, C.c_int]
+    lib.pimcb_stage_beads.argtypes = [vp, _dp, C.c_int, C.c_int, C.c_int]
+    lib.pimcb_stage_batch.argtypes = [vp, _dp, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.pimcb_num_slots.argtypes = [vp]
+    lib.pimcb_stage_batch_slot.argtypes = [vp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.pimcb_select_slot.argtypes = [vp, C.c_int]
+    lib.pimcb_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    lib.pimcb_host_free.argtypes = [vp]
+    lib.pimcb_host_register.argtypes = [vp, C.c_size_t]
+    lib.pimcb_host_unregister.argtypes = [vp]
+    lib.pimcb_ssf.argtypes = [vp, _dp]
+    lib.pimcb_isf.argtypes = [vp, _dp]
+    lib.pimcb_ssf_isf.argtypes = [vp, _dp, _dp]
+    lib.pimcb_measure.argtypes = [vp]
+    lib.pimcb_reset_bins.argtypes = [vp]
+    lib.pimcb_read_bins.argtypes = [vp, _dp, _dp, C.POINTER(C.c_long)]
+    lib.pimcb_bins_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    lib.pimcb_sync.argtypes = [vp]
+    lib.pimcb_stream.argtypes = [vp, C.POINTER(vp)]
+    lib.pimcb_set_pair_table.argtypes = [vp, _dp, _dp, C.c_int, C.c_double, _dp, _dp]
+    lib.pimcb_pair_sums.argtypes = [vp, _dp, _dp, _ip, C.c_double, C.c_int]
+    lib.pimcb_measure_fp64_peak.argtypes = [vp, _dp, C.c_double]
+    lib.pimcb_set_profiling.argtypes = [vp, C.c_int]
+    lib.pimcb_kernel_times.argtypes = [vp, _dp, C.POINTER(C.c_long), C.c_int]
+    if path == _build.LIB:
+        _lib = lib
+    return lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+class PinnedArray:
+    """A numpy view over pimcb_host_alloc'd (page-locked) memory."""
+
+    def __init__(self, shape, lib=None):
+        self._lib = lib or load_library()
+        n = int(np.prod(shape))
+        self._p = C.c_void_p()
+        rc = self._lib.pimcb_host_alloc(C.byref(self._p), n * 8)
+        if rc:
+            raise PimcbError(self._lib.pimcb_last_error().decode())
+        buf = (C.c_double * n).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=np.float64).reshape(shape)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            self._lib.pimcb_host_free(self._p)
+            self._p = None
+
+
+class Context:
+    """One pimcb_ctx: one device, one spatial dimension, one box + q-set."""
+
+    KERNELS = ("rho", "corr", "ssf_direct", "bins", "pair", "transpose")
+
+    def __init__(self, device: int = 0, ndim: int = 3):
+        self.lib = load_library()
+        self.ndim = ndim
+        self._h = C.c_void_p()
+        self._chk(self.lib.pimcb_create(C.byref(self._h), device, ndim))
+        self.nq = 0
+        self.shape = None   # (B, M, N) of the current slot
+        self._slot_shapes = {}
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _chk(self, rc):
+        if rc != 0:
+            raise PimcbError(f"pimcb error {rc}: {self.lib.pimcb_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.pimcb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- configuration -------------------------------------------------------------------------
+    def set_box(self, side, periodic=None):
+        side = _f64(side)
+        assert side.shape == (self.ndim,)
+        per = None
+        if periodic is not None:
+            per = np.ascontiguousarray(periodic, dtype=np.uint32)
+        self._chk(self.lib.pimcb_set_box(self._h, _ptr(side), per.ctypes.data_as(_up) if per is not None else None))
+
+    def set_qvecs(self, q):
+        q = _f64(q)
+        assert q.ndim == 2 and q.shape[1] == self.ndim
+        self._chk(self.lib.pimcb_set_qvecs(self._h, _ptr(q), len(q)))
+        self.nq = len(q)
+
+    def num_commensurate(self) -> int:
+        return self.lib.pimcb_num_commensurate(self._h)
+
+    def set_rho_mode(self, mode: int):
+        self._chk(self.lib.pimcb_set_rho_mode(self._h, mode))
+
+    # -- staging -----------------------------------------------------------------------------------
+    @staticmethod
+    def _batch(beads, N):
+        beads = np.asarray(beads)
+        if beads.dtype != np.float64 or not beads.flags.c_contiguous:
+            beads = _f64(beads)
+        if beads.ndim == 3:
+            beads = beads[None]
+        B, M, Next, nd = beads.shape
+        return beads, B, M, Next, nd
+
+    def stage(self, beads, N: int, slot: int | None = None):
+        """beads: [M][N_ext][ndim] or [B][M][N_ext][ndim] float64 (reference AoS layout)."""
+        beads, B, M, Next, nd = self._batch(beads, N)
+        assert nd == self.ndim
+        if slot is None:
+            self._chk(self.lib.pimcb_stage_batch(self._h, _ptr(beads), B, M, N, Next))
+            self.shape = (B, M, N)
+        else:
+            self._chk(self.lib.pimcb_stage_batch_slot(self._h, slot, _ptr(beads), B, M, N, Next))
+            self._slot_shapes[slot] = (B, M, N)
+        return self
+
+    def select_slot(self, slot: int):
+        self._chk(self.lib.pimcb_select_slot(self._h, slot))
+        self.shape = self._slot_shapes.get(slot, self.shape)
+
+    def num_slots(self) -> int:
+        return self.lib.pimcb_num_slots(self._h)
+
+    # -- estimators ------------------------------------------------------------------------------------
+    def ssf_isf(self, want_ssf=True, want_isf=True):
+        B, M, _ = self.shape
+        ssf = np.zeros((B, self.nq)) if want_ssf else None
+        isf = np.zeros((B, self.nq, M)) if want_isf else None
+        self._chk(self.lib.pimcb_ssf_isf(self._h, _ptr(ssf), _ptr(isf)))
+        return ssf, isf
+
+    def ssf(self):
+        B, _, _ = self.shape
+        out = np.zeros((B, self.nq))
+        self._chk(self.lib.pimcb_ssf(self._h, _ptr(out)))
+        return out
+
+    def isf(self):
+        B, M, _ = self.shape
+        out = np.zeros((B, self.nq, M))
+        self._chk(self.lib.pimcb_isf(self._h, _ptr(out)))
+        return out
+
+    def measure(self):
+        self._chk(self.lib.pimcb_measure(self._h))
+
+    def reset_bins(self):
+        self._chk(self.lib.pimcb_reset_bins(self._h))
+
+    def read_bins(self):
+        _, M, _ = self.shape
+        ssf = np.zeros(self.nq)
+        isf = np.zeros((self.nq, M))
+        n = C.c_long(0)
+        self._chk(self.lib.pimcb_read_bins(self._h, _ptr(ssf), _ptr(isf), C.byref(n)))
+        return ssf, isf, n.value
+
+    def bins_device_ptr(self):
+        p, n = C.c_void_p(), C.c_size_t(0)
+        self._chk(self.lib.pimcb_bins_device_ptr(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def sync(self):
+        self._chk(self.lib.pimcb_sync(self._h))
+
+    def stream(self) -> int:
+        p = C.c_void_p()
+        self._chk(self.lib.pimcb_stream(self._h, C.byref(p)))
+        return p.value or 0
+
+    # -- pair potential --------------------------------------------------------------------------------
+    def set_pair_table(self, V, dVdr, dr, extV=(0.0, 0.0), extdVdr=(0.0, 0.0)):
+        V = _f64(V)
+        dV = _f64(dVdr) if dVdr is not None else None
+        e0, e1 = _f64(extV), _f64(extdVdr)
+        self._chk(self.lib.pimcb_set_pair_table(self._h, _ptr(V), _ptr(dV), len(V), dr, _ptr(e0), _ptr(e1)))
+
+    def pair_sums(self, dSep=None, want_f2=True, want_hist=True, f2_parity=-1):
+        B, M, _ = self.shape
+        vint = np.zeros((B, M))
+        f2 = np.zeros((B, M)) if want_f2 else None
+        hist = np.zeros((B, M, NPCFSEP), dtype=np.int32) if want_hist else None
+        self._chk(self.lib.pimcb_pair_sums(self._h, _ptr(vint), _ptr(f2),
+                                           hist.ctypes.data_as(_ip) if hist is not None else None,
+                                           float(dSep) if dSep else 0.0, f2_parity))
+        return vint, f2, hist
+
+    # -- measurement helpers ----------------------------------------------------------------------------
+    def fp64_peak_tflops(self, seconds=0.5) -> float:
+        v = C.c_double(0.0)
+        self._chk(self.lib.pimcb_measure_fp64_peak(self._h, C.byref(v), seconds))
+        return v.value
+
+    def set_profiling(self, on: bool):
+        self._chk(self.lib.pimcb_set_profiling(self._h, int(on)))
+
+    def kernel_times(self, reset: bool = True) -> dict:
+        """{kernel: (total_ms, launches)} since the last reset (needs set_profiling(True))."""
+        ms = (C.c_double * 8)()
+        cnt = (C.c_long * 8)()
+        self._chk(self.lib.pimcb_kernel_times(self._h, ms, cnt, int(reset)))
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(self.KERNELS)}
+
+    def launch_count(self) -> int:
+        return self.lib.pimcb_launch_count(self._h)

@@ -1,0 +1,495 @@
+// kernels.cuh -- sm_100a device code for the pimc measurement hot path (FP64, CUDA cores).
+//
+// Device bead layout ("slice-major SoA"):  pos[b][t][d][Npad]  (double), Npad = N rounded up to 16,
+// so that the ND coordinate rows of one time slice are one contiguous, 128-byte aligned chunk that a
+// CTA pulls into shared memory with coalesced 16-byte loads.
+//
+// Kernels
+//   rho_generic_kernel   rho_q(t) = sum_i exp(i q.r_i(t)), one sincos per (q, bead)      [FP64-pipe bound]
+//   rho_lattice_kernel   same for commensurate q = 2 pi n / L by per-dimension phase powers [FP64-pipe bound]
+//   isf_corr_kernel      F(q,tau) = (1/N) sum_t0 Re[rho(t0) conj rho(t0+tau)], S(q) = F(q,0)
+//   ssf_direct_kernel    sum_{i<j} cos(q.minimage(r_i-r_j)) for non-commensurate q
+//   pair_kernel          per-slice Vint, sum_i |F_i|^2, separation histogram (table gathers)
+//   bins_accumulate_kernel, ssf_direct_finalize_kernel, aos_to_soa_kernel, fp64_peak_kernel
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pimcb {
+
+constexpr int kNPCFSEP = 50;   // include/common.h:85 (upstream)
+
+struct BoxDev {
+    double sideInv[3];
+    double pSide[3];
+};
+
+// ---------------------------------------------------------------------------------------------
+// sincos for moderate arguments (|x| < ~1e5): 3-term Cody-Waite reduction by pi/2 with FMAs and the
+// classic minimax kernels on [-pi/4, pi/4] (< 1 ulp each).  21 FP64 instructions, no slow path,
+// no local memory.  The host refuses q-sets whose max |q.r| leaves the validity range.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sincos_fast(double x, double& s, double& c) {
+    const double kMagic = 6755399441055744.0;            // 1.5 * 2^52: rint() by add/sub
+    const double t = fma(x, 0.63661977236758134308, kMagic);
+    const int n = __double2loint(t);                     // quadrant = low bits of rint(x*2/pi)
+    const double kd = t - kMagic;
+    double r = fma(kd, -1.5707963267948965580e+00, x);   // pi/2 split in three doubles
+    r = fma(kd, -6.1232339957367660359e-17, r);
+    r = fma(kd, 1.4973849048591698330e-33, r);
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double sr = fma(r * z, ps, r);                                   // sin(r)
+    const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));                   // cos(r)
+    double sv = (n & 1) ? cr : sr;
+    double cv = (n & 1) ? sr : cr;
+    // sign: sin negative in quadrants 2,3; cos negative in quadrants 1,2
+    const int shi = __double2hiint(sv) ^ ((n & 2) << 30);
+    const int chi = __double2hiint(cv) ^ (((n + 1) & 2) << 30);
+    s = __hiloint2double(shi, __double2loint(sv));
+    c = __hiloint2double(chi, __double2loint(cv));
+}
+
+// Coalesced load of one slice (ND rows of Npad doubles, contiguous, 16-byte aligned) into shared memory.
+__device__ __forceinline__ void load_slice(double* __restrict__ sm, const double* __restrict__ src, int count) {
+    const double2* s2 = reinterpret_cast<const double2*>(src);
+    double2* d2 = reinterpret_cast<double2*>(sm);
+    for (int k = threadIdx.x; k < (count >> 1); k += blockDim.x) d2[k] = __ldg(s2 + k);
+}
+
+// ---------------------------------------------------------------------------------------------
+// rho_q build, generic q.  One CTA per (config, slice) (grid-stride); work item = (q, particle chunk p).
+// All lanes of a warp normally share the chunk, so coordinate reads are shared-memory broadcasts and
+// every lane runs an independent dot + sincos + 2 accumulates per particle with no cross-lane traffic.
+// rho layout: rho[slice_global][0][q] = sum cos, rho[slice_global][1][q] = sum sin.
+// ---------------------------------------------------------------------------------------------
+template <int ND>
+__global__ void __launch_bounds__(256) rho_generic_kernel(const double* __restrict__ pos, const double* __restrict__ qsoa,
+                                                           double* __restrict__ rho, int nslices, int N, int Npad, int nq,
+                                                           int P, int chunk) {
+    extern __shared__ __align__(16) double sm[];
+    double* xs = sm;                          // [ND][Npad]
+    double* part = sm + ND * Npad;            // [2][P][nq]  (only when P > 1)
+    const int items = nq * P;
+    for (int sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
+        load_slice(xs, pos + static_cast<size_t>(sl) * ND * Npad, ND * Npad);
+        __syncthreads();
+        for (int item = threadIdx.x; item < items; item += blockDim.x) {
+            const int p = item / nq;
+            const int iq = item - p * nq;
+            double qv[ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) qv[d] = __ldg(qsoa + d * nq + iq);
+            const int i0 = p * chunk;
+            const int i1 = min(N, i0 + chunk);
+            double ac = 0.0, as = 0.0;
+#pragma unroll 2
+            for (int i = i0; i < i1; ++i) {
+                double ph = qv[0] * xs[i];
+#pragma unroll
+                for (int d = 1; d < ND; ++d) ph = fma(qv[d], xs[d * Npad + i], ph);
+                double s, c;
+                sincos_fast(ph, s, c);
+                ac += c;
+                as += s;
+            }
+            if (P == 1) {
+                rho[(static_cast<size_t>(sl) * 2 + 0) * nq + iq] = ac;
+                rho[(static_cast<size_t>(sl) * 2 + 1) * nq + iq] = as;
+            } else {
+                part[p * nq + iq] = ac;
+                part[(P + p) * nq + iq] = as;
+            }
+        }
+        if (P > 1) {
+            __syncthreads();
+            for (int k = threadIdx.x; k < 2 * nq; k += blockDim.x) {
+                const int cs = k / nq, iq = k - cs * nq;
+                double acc = 0.0;
+                for (int p = 0; p < P; ++p) acc += part[(cs * P + p) * nq + iq];   // fixed order: deterministic
+                rho[(static_cast<size_t>(sl) * 2 + cs) * nq + iq] = acc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rho_q build for commensurate q = 2 pi n / L.  exp(i q.r) = prod_d e_d^{n_d}, e_d = exp(2 pi i x_d / L_d):
+// phase 1 tabulates the powers e_d^m, m = 0..nmax_d, of every particle of the slice in shared memory
+// (ND sincos + nmax complex multiplies per particle instead of nq sincos); phase 2 is one work item per
+// (q, particle chunk): ND-1 complex multiplies + 2 accumulates per (q, bead).  Negative n_d use the
+// conjugate.  Power table layout: tab[row][i] as double2 (re, im), row = rowoff[d] + m, row stride
+// N + 1 double2 so that lanes reading different rows hit different banks.
+// qn: int[nq][ND] lattice indices; kphase[d] = 2 pi / L_d.
+// ---------------------------------------------------------------------------------------------
+template <int ND>
+__global__ void __launch_bounds__(256) rho_lattice_kernel(const double* __restrict__ pos, const int* __restrict__ qn,
+                                                           double* __restrict__ rho, int nslices, int N, int Npad, int nq,
+                                                           int P, int chunk, int3 nmax, double3 kphase) {
+    extern __shared__ __align__(16) double sm[];
+    const int nmx[3] = {nmax.x, nmax.y, nmax.z};
+    const double kph[3] = {kphase.x, kphase.y, kphase.z};
+    int rowoff[ND + 1];
+    rowoff[0] = 0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) rowoff[d + 1] = rowoff[d] + nmx[d] + 1;
+    const int stride = N + 1;                                  // in double2 units
+    double2* tab = reinterpret_cast<double2*>(sm);             // [rows][stride]
+    double* xs = sm + 2 * static_cast<size_t>(rowoff[ND]) * stride;   // [ND][Npad] staging of raw coordinates
+    double* part = xs + ND * Npad;                             // [2][P][nq]
+    const int items = nq * P;
+    for (int sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
+        load_slice(xs, pos + static_cast<size_t>(sl) * ND * Npad, ND * Npad);
+        __syncthreads();
+        // phase 1: powers of the base phases
+        for (int w = threadIdx.x; w < ND * N; w += blockDim.x) {
+            const int d = w / N, i = w - d * N;
+            double s, c;
+            sincos_fast(kph[d] * xs[d * Npad + i], s, c);
+            double2* col = tab + static_cast<size_t>(rowoff[d]) * stride + i;
+            col[0] = make_double2(1.0, 0.0);
+            double pr = c, pi = s;
+            for (int m = 1; m <= nmx[d]; ++m) {
+                col[static_cast<size_t>(m) * stride] = make_double2(pr, pi);
+                const double nr = fma(pr, c, -pi * s);
+                pi = fma(pr, s, pi * c);
+                pr = nr;
+            }
+        }
+        __syncthreads();
+        // phase 2
+        for (int item = threadIdx.x; item < items; item += blockDim.x) {
+            const int p = item / nq;
+            const int iq = item - p * nq;
+            const double2* rowp[ND];
+            double sg[ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                const int n = __ldg(qn + iq * ND + d);
+                rowp[d] = tab + static_cast<size_t>(rowoff[d] + abs(n)) * stride;
+                sg[d] = n < 0 ? -1.0 : 1.0;
+            }
+            const int i0 = p * chunk;
+            const int i1 = min(N, i0 + chunk);
+            double ac = 0.0, as = 0.0;
+#pragma unroll 2
+            for (int i = i0; i < i1; ++i) {
+                const double2 a = rowp[0][i];
+                double re = a.x, im = sg[0] * a.y;
+#pragma unroll
+                for (int d = 1; d < ND; ++d) {
+                    const double2 b = rowp[d][i];
+                    const double bi = sg[d] * b.y;
+                    const double nr = fma(re, b.x, -im * bi);
+                    im = fma(re, bi, im * b.x);
+                    re = nr;
+                }
+                ac += re;
+                as += im;
+            }
+            if (P == 1) {
+                rho[(static_cast<size_t>(sl) * 2 + 0) * nq + iq] = ac;
+                rho[(static_cast<size_t>(sl) * 2 + 1) * nq + iq] = as;
+            } else {
+                part[p * nq + iq] = ac;
+                part[(P + p) * nq + iq] = as;
+            }
+        }
+        if (P > 1) {
+            __syncthreads();
+            for (int k = threadIdx.x; k < 2 * nq; k += blockDim.x) {
+                const int cs = k / nq, iq = k - cs * nq;
+                double acc = 0.0;
+                for (int p = 0; p < P; ++p) acc += part[(cs * P + p) * nq + iq];
+                rho[(static_cast<size_t>(sl) * 2 + cs) * nq + iq] = acc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tau-correlation.  One CTA per (config, q).  C(t), S(t) of that q are staged twice back to back in shared
+// memory so that t0+tau needs no modulo.  Thread tau <= M/2 accumulates over t0 in ascending order and the
+// value is mirrored to M - tau (F(q,tau) = F(q,M-tau) identically).  Output per config:
+//   cfg[b][q]               = F(q,0)            (S(q) increment sf/N, commensurate q)
+//   cfg[b][nq + q*M + tau]  = F(q,tau)          (isf/N, reference CPU column layout)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) isf_corr_kernel(const double* __restrict__ rho, double* __restrict__ cfg, int M, int nq,
+                                                        double invN, const unsigned char* __restrict__ commensurate) {
+    extern __shared__ __align__(16) double sm[];
+    double* C = sm;            // [2M]
+    double* S = sm + 2 * M;    // [2M]
+    const int b = blockIdx.x / nq, iq = blockIdx.x - b * nq;
+    const size_t cfg_stride = static_cast<size_t>(nq) + static_cast<size_t>(nq) * M;
+    for (int t = threadIdx.x; t < M; t += blockDim.x) {
+        const size_t sl = static_cast<size_t>(b) * M + t;
+        const double c = rho[(sl * 2 + 0) * nq + iq];
+        const double s = rho[(sl * 2 + 1) * nq + iq];
+        C[t] = c; C[t + M] = c;
+        S[t] = s; S[t + M] = s;
+    }
+    __syncthreads();
+    double* out = cfg + static_cast<size_t>(b) * cfg_stride;
+    const int half = M / 2;
+    for (int tau = threadIdx.x; tau <= half; tau += blockDim.x) {
+        double a0 = 0.0, a1 = 0.0;
+        int t0 = 0;
+        for (; t0 + 1 < M; t0 += 2) {
+            a0 = fma(C[t0], C[t0 + tau], a0);
+            a0 = fma(S[t0], S[t0 + tau], a0);
+            a1 = fma(C[t0 + 1], C[t0 + 1 + tau], a1);
+            a1 = fma(S[t0 + 1], S[t0 + 1 + tau], a1);
+        }
+        if (t0 < M) {
+            a0 = fma(C[t0], C[t0 + tau], a0);
+            a0 = fma(S[t0], S[t0 + tau], a0);
+        }
+        const double v = (a0 + a1) * invN;
+        out[nq + static_cast<size_t>(iq) * M + tau] = v;
+        if (tau > 0 && tau < M - tau) out[nq + static_cast<size_t>(iq) * M + (M - tau)] = v;
+        if (tau == 0 && commensurate[iq]) out[iq] = v;
+    }
+    // odd M never occurs upstream (setup.cpp:1001-1008 forces M even) but stay correct: tau in (M/2, M) mirrors.
+}
+
+// ---------------------------------------------------------------------------------------------
+// Direct minimum-image S(q) for the non-commensurate q (reference CPU semantics,
+// src/estimator.cpp:3715-3734 + include/path.h:179-184).  One CTA per (config, slice); pairs (i, i+k mod N)
+// k = 1..N/2 are spread over threads; the min-image separation is computed once per pair and reused for a
+// register tile of QT wave-vectors.  partial[sl][k] = sum_{i<j} cos(q_k . sep_ij).
+// ---------------------------------------------------------------------------------------------
+template <int ND, int QT>
+__global__ void __launch_bounds__(256) ssf_direct_kernel(const double* __restrict__ pos, const double* __restrict__ qsoa,
+                                                          const int* __restrict__ qidx, int nsel, int nq, double* __restrict__ partial,
+                                                          int nslices, int N, int Npad, BoxDev box) {
+    extern __shared__ __align__(16) double sm[];
+    double* xs = sm;                       // [ND][Npad]
+    __shared__ double red[QT][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
+        load_slice(xs, pos + static_cast<size_t>(sl) * ND * Npad, ND * Npad);
+        __syncthreads();
+        for (int q0 = 0; q0 < nsel; q0 += QT) {
+            double qv[QT][ND];
+#pragma unroll
+            for (int k = 0; k < QT; ++k) {
+                const int iq = (q0 + k < nsel) ? __ldg(qidx + q0 + k) : -1;
+#pragma unroll
+                for (int d = 0; d < ND; ++d) qv[k][d] = iq >= 0 ? __ldg(qsoa + d * nq + iq) : 0.0;
+            }
+            double acc[QT];
+#pragma unroll
+            for (int k = 0; k < QT; ++k) acc[k] = 0.0;
+            const int kmax = N / 2;
+            for (int kk = 1; kk <= kmax; ++kk) {
+                const int ilim = ((N & 1) == 0 && kk == kmax) ? N / 2 : N;
+                for (int i = threadIdx.x; i < ilim; i += blockDim.x) {
+                    int j = i + kk;
+                    if (j >= N) j -= N;
+                    double sep[ND];
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) {
+                        const double s = xs[d * Npad + i] - xs[d * Npad + j];
+                        sep[d] = s - box.pSide[d] * floor(fma(s, box.sideInv[d], 0.5));
+                    }
+#pragma unroll
+                    for (int k = 0; k < QT; ++k) {
+                        double ph = qv[k][0] * sep[0];
+#pragma unroll
+                        for (int d = 1; d < ND; ++d) ph = fma(qv[k][d], sep[d], ph);
+                        double s, c;
+                        sincos_fast(ph, s, c);
+                        acc[k] += c;
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < QT; ++k) {
+                double v = acc[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) red[k][warp] = v;
+            }
+            __syncthreads();
+            if (threadIdx.x < QT && q0 + threadIdx.x < nsel) {
+                double v = 0.0;
+                for (int w = 0; w < (blockDim.x >> 5); ++w) v += red[threadIdx.x][w];
+                partial[static_cast<size_t>(sl) * nsel + q0 + threadIdx.x] = v;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// cfg[b][qidx[k]] = (M*N + 2 * sum_t partial[b*M+t][k]) / N     (sf/N, src/estimator.cpp:3726-3736)
+__global__ void ssf_direct_finalize_kernel(const double* __restrict__ partial, const int* __restrict__ qidx, int nsel,
+                                           double* __restrict__ cfg, int B, int M, int N, int nq) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * nsel) return;
+    const int b = idx / nsel, k = idx - b * nsel;
+    double acc = 0.0;
+    for (int t = 0; t < M; ++t) acc += partial[(static_cast<size_t>(b) * M + t) * nsel + k];
+    const size_t cfg_stride = static_cast<size_t>(nq) + static_cast<size_t>(nq) * M;
+    cfg[b * cfg_stride + qidx[k]] = (static_cast<double>(M) * N + 2.0 * acc) / N;
+}
+
+// bins[j] += sum_b cfg[b][j], b ascending (deterministic).
+__global__ void bins_accumulate_kernel(const double* __restrict__ cfg, double* __restrict__ bins, int B, size_t len) {
+    const size_t j = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= len) return;
+    double acc = bins[j];
+    for (int b = 0; b < B; ++b) acc += cfg[static_cast<size_t>(b) * len + j];
+    bins[j] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pair potential.  One CTA per (config, slice).  Thread i walks partners j = i+k mod N.  The table index
+// k = int(|sep|/dr) follows the reference's operation order with individually rounded IEEE operations
+// (__d*_rn intrinsics are never contracted into FMAs) so that it is bit-identical to the CPU:
+//   sep_d = r_a,d - r_b,d ; sep_d -= pSide_d*floor(sep_d*sideInv_d + 0.5)   (include/container.h:50-53)
+//   r = sqrt(((0 + s0*s0) + s1*s1) + s2*s2) ; k = int(r/dr)                   (include/potential.h:249-260, 985-1003)
+// WANT_F2: full j != i loop accumulating F_i = sum_j (dVdr[k]/r) sep_ij, then sum_i |F_i|^2
+//          (src/action.cpp:1188-1223); V is accumulated on the k <= N/2 half so each pair counts once.
+// Without WANT_F2 only the N(N-1)/2 half is visited.
+// ---------------------------------------------------------------------------------------------
+template <int ND>
+__device__ __forceinline__ double minimage_norm(const double* __restrict__ xs, int Npad, int a, int b, const BoxDev& box, double* sep) {
+    double r2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        double s = __dsub_rn(xs[d * Npad + a], xs[d * Npad + b]);
+        const double f = floor(__dadd_rn(__dmul_rn(s, box.sideInv[d]), 0.5));
+        s = __dsub_rn(s, __dmul_rn(box.pSide[d], f));
+        sep[d] = s;
+        r2 = __dadd_rn(r2, __dmul_rn(s, s));
+    }
+    return __dsqrt_rn(r2);
+}
+
+__device__ __forceinline__ double table_direct(const double* __restrict__ tab, int len, double dr, double ext0, double ext1, double r) {
+    const int k = __double2int_rz(__ddiv_rn(r, dr));
+    if (k <= 0) return ext0;
+    if (k >= len) return ext1;
+    return __ldg(tab + k);
+}
+
+struct PairParams {
+    const double* V; const double* dVdr; int len; double dr; double extV[2]; double extdV[2];
+    double dSep; int want_hist; int f2_parity; int M;
+};
+
+template <int ND, bool WANT_F2>
+__global__ void __launch_bounds__(256) pair_kernel(const double* __restrict__ pos, int nslices, int N, int Npad, BoxDev box,
+                                                    PairParams pp, double* __restrict__ vint, double* __restrict__ f2,
+                                                    int* __restrict__ hist) {
+    extern __shared__ __align__(16) double sm[];
+    double* xs = sm;
+    __shared__ double redV[8], redF[8];
+    __shared__ int shist[kNPCFSEP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
+        const int t = sl % pp.M;
+        const bool do_f2 = WANT_F2 && (pp.f2_parity < 0 || (t & 1) == pp.f2_parity);
+        load_slice(xs, pos + static_cast<size_t>(sl) * ND * Npad, ND * Npad);
+        if (threadIdx.x < kNPCFSEP) shist[threadIdx.x] = 0;
+        __syncthreads();
+        double vsum = 0.0, fsum = 0.0;
+        const int khalf = N / 2;
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            double F[ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) F[d] = 0.0;
+            const int klast = do_f2 ? N - 1 : khalf;
+            for (int kk = 1; kk <= klast; ++kk) {
+                int j = i + kk;
+                if (j >= N) j -= N;
+                // V-half: pairs (i, i+kk), kk <= N/2, (for even N and kk == N/2 only i < N/2)
+                const bool vhalf = (kk < khalf) || (kk == khalf && ((N & 1) || i < khalf));
+                if (!do_f2 && !vhalf) continue;
+                double sep[ND];
+                double r;
+                if (do_f2) {
+                    r = minimage_norm<ND>(xs, Npad, i, j, box, sep);            // getSeparation(bead1,bead2), action.cpp:1211
+                } else {
+                    const int lo = min(i, j), hi = max(i, j);
+                    r = minimage_norm<ND>(xs, Npad, hi, lo, box, sep);          // getSeparation(bead2,bead1), action.cpp:934
+                }
+                if (vhalf) {
+                    vsum += table_direct(pp.V, pp.len, pp.dr, pp.extV[0], pp.extV[1], r);
+                    if (pp.want_hist) {
+                        const int nR = __double2int_rz(__ddiv_rn(r, pp.dSep));  // action.cpp:221
+                        if (nR >= 0 && nR < kNPCFSEP) atomicAdd(&shist[nR], 1);
+                    }
+                }
+                if (do_f2) {
+                    const double g = __ddiv_rn(table_direct(pp.dVdr, pp.len, pp.dr, pp.extdV[0], pp.extdV[1], r), r);
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) F[d] = fma(g, sep[d], F[d]);
+                }
+            }
+            if (do_f2) {
+#pragma unroll
+                for (int d = 0; d < ND; ++d) fsum = fma(F[d], F[d], fsum);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+            fsum += __shfl_xor_sync(0xffffffffu, fsum, o);
+        }
+        if (lane == 0) { redV[warp] = vsum; redF[warp] = fsum; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double v = 0.0, f = 0.0;
+            for (int w = 0; w < (blockDim.x >> 5); ++w) { v += redV[w]; f += redF[w]; }
+            vint[sl] = v;
+            if (WANT_F2 && f2) f2[sl] = f;
+        }
+        if (pp.want_hist && threadIdx.x < kNPCFSEP) hist[static_cast<size_t>(sl) * kNPCFSEP + threadIdx.x] = shist[threadIdx.x];
+        __syncthreads();
+    }
+}
+
+// AoS double[nslices][Next][ND] (the reference's beads array, DMA'd as-is) -> pos[sl][d][Npad].
+template <int ND>
+__global__ void aos_to_soa_kernel(const double* __restrict__ aos, double* __restrict__ pos, int nslices, int N, int Next, int Npad) {
+    extern __shared__ __align__(16) double sm[];
+    for (int sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
+        const double* src = aos + static_cast<size_t>(sl) * Next * ND;
+        for (int k = threadIdx.x; k < N * ND; k += blockDim.x) sm[k] = src[k];
+        __syncthreads();
+        double* dst = pos + static_cast<size_t>(sl) * ND * Npad;
+        for (int k = threadIdx.x; k < ND * Npad; k += blockDim.x) {
+            const int d = k / Npad, i = k - d * Npad;
+            dst[k] = i < N ? sm[i * ND + d] : 0.0;
+        }
+        __syncthreads();
+    }
+}
+
+// Register-resident DFMA chains: 8 independent accumulators per thread, `iters` x 8 x 4 FMAs.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    const double v = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (v == 123.456) out[0] = v;   // never true; keeps the chains live
+}
+
+}  // namespace pimcb

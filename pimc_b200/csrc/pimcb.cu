@@ -1,0 +1,748 @@
+// pimcb.cu -- host side of libpimc_b200.so: context, staging, launch logic and the C ABI declared in
+// include/pimc_b200.h.  Single backend: CUDA, sm_100a.  There is no CPU fallback anywhere in this file;
+// every entry point fails with PIMCB_ECUDA when no device is usable.
+#include "../../include/pimc_b200.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace pimcb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(PIMCB_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int kSlots = 4;
+constexpr int kKernels = 8;
+enum { K_RHO = 0, K_CORR = 1, K_DIRECT = 2, K_BINS = 3, K_PAIR = 4, K_TRANSPOSE = 5 };
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return fail(PIMCB_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        cap = bytes;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaEvent_t done = nullptr;   // recorded after the last H2D that read this buffer
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e != cudaSuccess) return fail(PIMCB_ENOMEM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        cap = bytes;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Slot {
+    DevBuf pos;            // pos[b][t][d][Npad]
+    int B = 0, M = 0, N = 0, Npad = 0;
+    bool staged = false;
+    cudaEvent_t ready = nullptr;      // H2D (+ transpose) complete
+    cudaEvent_t consumed = nullptr;   // last kernel reading this slot has been enqueued before this event
+};
+
+}  // namespace
+
+struct pimcb_ctx {
+    int device = 0, ndim = 3, sm_count = 148;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    bool have_box = false;
+    double side[3] = {0, 0, 0};
+    unsigned periodic[3] = {1, 1, 1};
+    BoxDev box{};
+    // wave-vectors
+    int nq = 0, ncomm = 0, nsel = 0;
+    std::vector<double> q_host;            // AoS
+    std::vector<unsigned char> comm;
+    std::vector<int> qn;                   // lattice indices [nq][ndim] (valid when commensurate)
+    int nmax[3] = {0, 0, 0};
+    double max_phase = 0.0;
+    DevBuf d_q, d_comm, d_qn, d_qidx;
+    int rho_mode = 1;
+    // beads
+    Slot slots[kSlots];
+    int cur = -1;
+    PinBuf pin[2];
+    int pin_next = 0;
+    DevBuf d_aos;                          // device AoS scratch for the zero-bounce path
+    // work buffers
+    DevBuf d_rho, d_cfg, d_bins, d_partial;
+    long n_acc = 0;
+    size_t bins_len = 0;
+    PinBuf h_out;
+    // pair potential
+    DevBuf d_V, d_dV, d_vint, d_f2, d_hist;
+    int tab_len = 0;
+    bool have_dV = false;
+    double dr = 0, extV[2] = {0, 0}, extdV[2] = {0, 0};
+    // profiling: (kernel id, start, stop) event records, resolved lazily by pimcb_kernel_times
+    bool profiling = false;
+    cudaEvent_t ev0[kKernels] = {}, ev1[kKernels] = {};      // scratch events (fences, fp64 peak)
+    struct Rec { int k; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> ev_pool;
+    double k_ms[kKernels] = {};
+    long k_count[kKernels] = {};
+    long launches = 0;
+    DevBuf d_scratch;
+};
+
+namespace {
+
+cudaEvent_t pool_event(pimcb_ctx* c) {
+    if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+// Brackets one kernel launch on `stream` with CUDA events when profiling is on; always counts the launch.
+struct KTimer {
+    pimcb_ctx* c; int k; cudaStream_t st; cudaEvent_t a = nullptr;
+    KTimer(pimcb_ctx* c_, int k_, cudaStream_t st_ = nullptr) : c(c_), k(k_), st(st_ ? st_ : c_->stream) {
+        if (c->profiling && (a = pool_event(c))) cudaEventRecord(a, st);
+    }
+    ~KTimer() {
+        if (a) {
+            cudaEvent_t b = pool_event(c);
+            if (b) { cudaEventRecord(b, st); c->recs.push_back({k, a, b}); }
+        }
+        c->launches++;
+    }
+};
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// Choose the particle split P (chunks per q) for the rho kernels: maximise lane utilisation of a
+// 256-thread CTA subject to the partial-sum shared-memory budget.
+void choose_split(int nq, int N, int threads, size_t smem_fixed, size_t smem_limit, int* P_out, int* chunk_out) {
+    int bestP = 1;
+    double best = -1.0;
+    for (int P = 1; P <= 64 && P <= N; ++P) {
+        const int chunk = (N + P - 1) / P;
+        if (static_cast<long>(chunk) * (P - 1) >= N) continue;                       // empty trailing chunk
+        const size_t smem = smem_fixed + (P > 1 ? sizeof(double) * 2 * P * nq : 0);
+        if (smem > smem_limit) break;
+        const long items = static_cast<long>(nq) * P;
+        const long passes = (items + threads - 1) / threads;
+        double eff = static_cast<double>(nq) * N / (static_cast<double>(passes) * threads * chunk);
+        if (items < threads) eff *= 0.999;                                           // prefer full CTAs on ties
+        eff -= 1e-4 * P;                                                             // prefer fewer partials on ties
+        if (eff > best) { best = eff; bestP = P; }
+    }
+    *P_out = bestP;
+    *chunk_out = (N + bestP - 1) / bestP;
+}
+
+int grid_for(const pimcb_ctx* c, int nslices, int ctas_per_sm) {
+    return std::max(1, std::min(nslices, c->sm_count * ctas_per_sm));
+}
+
+template <class K>
+int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    return 0;
+}
+
+int need_cur(pimcb_ctx* c, Slot** s) {
+    if (!c) return fail(PIMCB_EINVAL, "null ctx");
+    if (c->cur < 0 || !c->slots[c->cur].staged) return fail(PIMCB_ESTATE, "no beads staged");
+    *s = &c->slots[c->cur];
+    return 0;
+}
+
+// ---- rho_q build + correlation + direct S(q) into d_cfg (per configuration results) ------------
+int launch_rho(pimcb_ctx* c, const Slot& s) {
+    const int nd = c->ndim, nq = c->nq;
+    const int nsl = s.B * s.M;
+    const size_t limit = 200 * 1024;
+    int rows = 0;
+    for (int d = 0; d < nd; ++d) rows += c->nmax[d] + 1;
+    const size_t lattice_fixed = sizeof(double) * (2 * static_cast<size_t>(rows) * (s.N + 1) + static_cast<size_t>(nd) * s.Npad);
+    // lattice path only when every q is commensurate and the phase-power table leaves room for >= 2 CTAs per SM
+    const bool lattice = c->rho_mode == 1 && c->ncomm == nq && nq > 0 && lattice_fixed <= 100 * 1024;
+    int rc = c->d_rho.ensure(sizeof(double) * 2 * static_cast<size_t>(nsl) * nq);
+    if (rc) return rc;
+    int P, chunk;
+    KTimer kt(c, K_RHO);
+    if (!lattice) {
+        const size_t fixed = sizeof(double) * nd * s.Npad;
+        choose_split(nq, s.N, 256, fixed, limit, &P, &chunk);
+        const size_t smem = fixed + (P > 1 ? sizeof(double) * 2 * P * nq : 0);
+        const int grid = grid_for(c, nsl, 8);
+#define LAUNCH_GENERIC(ND)                                                                                        \
+        rc = set_smem(rho_generic_kernel<ND>, smem); if (rc) return rc;                                            \
+        rho_generic_kernel<ND><<<grid, 256, smem, c->stream>>>(s.pos.as<double>(), c->d_q.as<double>(),           \
+                                                               c->d_rho.as<double>(), nsl, s.N, s.Npad, nq, P, chunk)
+        if (nd == 1) { LAUNCH_GENERIC(1); } else if (nd == 2) { LAUNCH_GENERIC(2); } else { LAUNCH_GENERIC(3); }
+#undef LAUNCH_GENERIC
+    } else {
+        const size_t fixed = lattice_fixed;
+        choose_split(nq, s.N, 256, fixed, limit, &P, &chunk);
+        const size_t smem = fixed + (P > 1 ? sizeof(double) * 2 * P * nq : 0);
+        const int grid = grid_for(c, nsl, 8);
+        const int3 nmax = make_int3(c->nmax[0], c->nmax[1], c->nmax[2]);
+        const double twopi = 2.0 * M_PI;
+        const double3 kph = make_double3(twopi / c->side[0], nd > 1 ? twopi / c->side[1] : 0.0, nd > 2 ? twopi / c->side[2] : 0.0);
+#define LAUNCH_LATTICE(ND)                                                                                        \
+        rc = set_smem(rho_lattice_kernel<ND>, smem); if (rc) return rc;                                            \
+        rho_lattice_kernel<ND><<<grid, 256, smem, c->stream>>>(s.pos.as<double>(), c->d_qn.as<int>(),             \
+                                                               c->d_rho.as<double>(), nsl, s.N, s.Npad, nq, P, chunk, nmax, kph)
+        if (nd == 1) { LAUNCH_LATTICE(1); } else if (nd == 2) { LAUNCH_LATTICE(2); } else { LAUNCH_LATTICE(3); }
+#undef LAUNCH_LATTICE
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int launch_corr(pimcb_ctx* c, const Slot& s) {
+    KTimer kt(c, K_CORR);
+    const size_t smem = sizeof(double) * 4 * s.M;
+    int rc = set_smem(isf_corr_kernel, smem);
+    if (rc) return rc;
+    isf_corr_kernel<<<s.B * c->nq, 128, smem, c->stream>>>(c->d_rho.as<double>(), c->d_cfg.as<double>(), s.M, c->nq,
+                                                           1.0 / s.N, c->d_comm.as<unsigned char>());
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int launch_direct(pimcb_ctx* c, const Slot& s) {
+    if (c->nsel == 0) return 0;
+    const int nd = c->ndim, nsl = s.B * s.M;
+    int rc = c->d_partial.ensure(sizeof(double) * static_cast<size_t>(nsl) * c->nsel);
+    if (rc) return rc;
+    KTimer kt(c, K_DIRECT);
+    const size_t smem = sizeof(double) * nd * s.Npad;
+    const int grid = grid_for(c, nsl, 8);
+#define LAUNCH_DIRECT(ND)                                                                                          \
+    rc = set_smem(ssf_direct_kernel<ND, 4>, smem); if (rc) return rc;                                              \
+    ssf_direct_kernel<ND, 4><<<grid, 256, smem, c->stream>>>(s.pos.as<double>(), c->d_q.as<double>(), c->d_qidx.as<int>(), \
+                                                             c->nsel, c->nq, c->d_partial.as<double>(), nsl, s.N, s.Npad, c->box)
+    if (nd == 1) { LAUNCH_DIRECT(1); } else if (nd == 2) { LAUNCH_DIRECT(2); } else { LAUNCH_DIRECT(3); }
+#undef LAUNCH_DIRECT
+    CU(cudaGetLastError());
+    const int tot = s.B * c->nsel;
+    ssf_direct_finalize_kernel<<<(tot + 127) / 128, 128, 0, c->stream>>>(c->d_partial.as<double>(), c->d_qidx.as<int>(), c->nsel,
+                                                                         c->d_cfg.as<double>(), s.B, s.M, s.N, c->nq);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int run_estimators(pimcb_ctx* c, Slot** sp) {
+    Slot* s;
+    int rc = need_cur(c, &s);
+    if (rc) return rc;
+    if (c->nq <= 0) return fail(PIMCB_ESTATE, "no q-vectors set");
+    if (!c->have_box) return fail(PIMCB_ESTATE, "no box set");
+    if (c->max_phase > 1.0e5) return fail(PIMCB_EINVAL, "max |q.r| = %g exceeds the sincos validity range 1e5", c->max_phase);
+    const size_t len = static_cast<size_t>(c->nq) * (1 + s->M);
+    if (c->bins_len != len) {
+        rc = c->d_bins.ensure(sizeof(double) * len);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(c->d_bins.p, 0, sizeof(double) * len, c->stream));
+        c->bins_len = len;
+        c->n_acc = 0;
+    }
+    rc = c->d_cfg.ensure(sizeof(double) * len * s->B);
+    if (rc) return rc;
+    CU(cudaStreamWaitEvent(c->stream, s->ready, 0));
+    if ((rc = launch_rho(c, *s))) return rc;
+    if ((rc = launch_corr(c, *s))) return rc;
+    if ((rc = launch_direct(c, *s))) return rc;
+    CU(cudaEventRecord(s->consumed, c->stream));
+    *sp = s;
+    return 0;
+}
+
+int copy_out(pimcb_ctx* c, const Slot& s, double* ssf_out, double* isf_out) {
+    const size_t len = static_cast<size_t>(c->nq) * (1 + s.M);
+    const size_t bytes = sizeof(double) * len * s.B;
+    int rc = c->h_out.ensure(bytes);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->h_out.p, c->d_cfg.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const double* h = static_cast<const double*>(c->h_out.p);
+    for (int b = 0; b < s.B; ++b) {
+        if (ssf_out) std::memcpy(ssf_out + static_cast<size_t>(b) * c->nq, h + b * len, sizeof(double) * c->nq);
+        if (isf_out) std::memcpy(isf_out + static_cast<size_t>(b) * c->nq * s.M, h + b * len + c->nq, sizeof(double) * c->nq * s.M);
+    }
+    return 0;
+}
+
+int stage_into(pimcb_ctx* c, int slot, const double* beads, int B, int M, int N, int Next) {
+    if (!c) return fail(PIMCB_EINVAL, "null ctx");
+    if (!beads || B < 1 || M < 1 || N < 1 || Next < N) return fail(PIMCB_EINVAL, "bad staging arguments (B=%d M=%d N=%d N_ext=%d)", B, M, N, Next);
+    if (slot < 0 || slot >= kSlots) return fail(PIMCB_EINVAL, "slot %d out of range", slot);
+    CU(cudaSetDevice(c->device));
+    const int nd = c->ndim;
+    Slot& s = c->slots[slot];
+    const int Npad = round_up(N, 16);
+    const size_t nsl = static_cast<size_t>(B) * M;
+    const size_t soa_bytes = sizeof(double) * nsl * nd * Npad;
+    // kernels already enqueued on the compute stream may still read THIS slot: order the copy after them
+    // (other slots are untouched, so H2D into slot k+1 overlaps the kernels working on slot k)
+    CU(cudaStreamWaitEvent(c->copy_stream, s.consumed, 0));
+    int rc = s.pos.ensure(soa_bytes);
+    if (rc) return rc;
+    s.B = B; s.M = M; s.N = N; s.Npad = Npad;
+
+    cudaPointerAttributes attr{};
+    const bool pinned = cudaPointerGetAttributes(&attr, beads) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {
+        // zero-bounce path: DMA the reference AoS array as-is, transpose on the device
+        const size_t aos_bytes = sizeof(double) * nsl * Next * nd;
+        rc = c->d_aos.ensure(aos_bytes);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(c->d_aos.p, beads, aos_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        const size_t smem = sizeof(double) * N * nd;
+        const int grid = static_cast<int>(std::min<size_t>(nsl, static_cast<size_t>(c->sm_count) * 8));
+#define LAUNCH_T(ND)                                                                                  \
+        rc = set_smem(aos_to_soa_kernel<ND>, smem); if (rc) return rc;                                 \
+        aos_to_soa_kernel<ND><<<grid, 256, smem, c->copy_stream>>>(c->d_aos.as<double>(), s.pos.as<double>(), static_cast<int>(nsl), N, Next, Npad)
+        {
+            KTimer kt(c, K_TRANSPOSE, c->copy_stream);
+            if (nd == 1) { LAUNCH_T(1); } else if (nd == 2) { LAUNCH_T(2); } else { LAUNCH_T(3); }
+        }
+#undef LAUNCH_T
+        CU(cudaGetLastError());
+        // the caller may mutate its buffer when we return: the DMA must have consumed it
+        CU(cudaEventRecord(s.ready, c->copy_stream));
+        CU(cudaEventSynchronize(s.ready));
+    } else {
+        // pageable source: pack AoS -> SoA into the next pinned bounce buffer, then one H2D
+        PinBuf& pb = c->pin[c->pin_next];
+        c->pin_next ^= 1;
+        CU(cudaEventSynchronize(pb.done));
+        rc = pb.ensure(soa_bytes);
+        if (rc) return rc;
+        double* dst = static_cast<double*>(pb.p);
+        for (size_t sl = 0; sl < nsl; ++sl) {
+            const double* src = beads + sl * Next * nd;
+            double* row = dst + sl * nd * Npad;
+            for (int d = 0; d < nd; ++d) {
+                double* o = row + static_cast<size_t>(d) * Npad;
+                for (int i = 0; i < N; ++i) o[i] = src[static_cast<size_t>(i) * nd + d];
+                for (int i = N; i < Npad; ++i) o[i] = 0.0;
+            }
+        }
+        CU(cudaMemcpyAsync(s.pos.p, pb.p, soa_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaEventRecord(pb.done, c->copy_stream));
+        CU(cudaEventRecord(s.ready, c->copy_stream));
+    }
+    s.staged = true;
+    return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char* pimcb_last_error(void) { return g_err.c_str(); }
+int pimcb_version(void) { return 100; }
+
+int pimcb_create(pimcb_ctx** out, int device, int ndim) {
+    if (!out) return fail(PIMCB_EINVAL, "null out pointer");
+    *out = nullptr;
+    if (ndim < 1 || ndim > 3) return fail(PIMCB_EINVAL, "ndim must be 1, 2 or 3 (got %d)", ndim);
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(PIMCB_ECUDA, "device %d not available (%d CUDA devices visible)", device, ndev);
+    CU(cudaSetDevice(device));
+    pimcb_ctx* c = new (std::nothrow) pimcb_ctx();
+    if (!c) return fail(PIMCB_ENOMEM, "out of host memory");
+    c->device = device;
+    c->ndim = ndim;
+    cudaDeviceProp prop{};
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < kKernels; ++k) {
+        CU(cudaEventCreate(&c->ev0[k]));
+        CU(cudaEventCreate(&c->ev1[k]));
+    }
+    for (auto& s : c->slots) {
+        CU(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
+    }
+    for (auto& p : c->pin) {
+        CU(cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming));
+        CU(cudaEventRecord(p.done, c->copy_stream));
+    }
+    *out = c;
+    return 0;
+}
+
+int pimcb_destroy(pimcb_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->copy_stream);
+    for (auto& s : c->slots) {
+        s.pos.release();
+        if (s.ready) cudaEventDestroy(s.ready);
+        if (s.consumed) cudaEventDestroy(s.consumed);
+    }
+    for (auto& p : c->pin) { p.release(); if (p.done) cudaEventDestroy(p.done); }
+    c->h_out.release();
+    for (DevBuf* b : {&c->d_q, &c->d_comm, &c->d_qn, &c->d_qidx, &c->d_aos, &c->d_rho, &c->d_cfg, &c->d_bins, &c->d_partial,
+                      &c->d_V, &c->d_dV, &c->d_vint, &c->d_f2, &c->d_hist, &c->d_scratch})
+        b->release();
+    for (int k = 0; k < kKernels; ++k) { cudaEventDestroy(c->ev0[k]); cudaEventDestroy(c->ev1[k]); }
+    for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->copy_stream);
+    delete c;
+    return 0;
+}
+
+int pimcb_set_box(pimcb_ctx* c, const double* side, const unsigned* periodic) {
+    if (!c || !side) return fail(PIMCB_EINVAL, "null argument");
+    for (int d = 0; d < c->ndim; ++d) {
+        if (!(side[d] > 0.0)) return fail(PIMCB_EINVAL, "side[%d] = %g must be positive", d, side[d]);
+        c->side[d] = side[d];
+        c->periodic[d] = periodic ? periodic[d] : 1u;
+        c->box.sideInv[d] = 1.0 / side[d];                  // src/container.cpp:122
+        c->box.pSide[d] = c->periodic[d] * side[d];         // src/container.cpp:129
+    }
+    c->have_box = true;
+    if (c->nq > 0) {   // re-classify against the new box
+        std::vector<double> q = c->q_host;
+        return pimcb_set_qvecs(c, q.data(), c->nq);
+    }
+    return 0;
+}
+
+int pimcb_set_qvecs(pimcb_ctx* c, const double* q, int nq) {
+    if (!c || !q || nq < 1) return fail(PIMCB_EINVAL, "bad q-vector arguments");
+    if (!c->have_box) return fail(PIMCB_ESTATE, "pimcb_set_box must precede pimcb_set_qvecs");
+    CU(cudaSetDevice(c->device));
+    const int nd = c->ndim;
+    c->nq = nq;
+    c->q_host.assign(q, q + static_cast<size_t>(nq) * nd);
+    c->comm.assign(nq, 0);
+    c->qn.assign(static_cast<size_t>(nq) * nd, 0);
+    std::vector<int> sel;
+    std::vector<double> qsoa(static_cast<size_t>(nq) * nd);
+    c->ncomm = 0;
+    c->max_phase = 0.0;
+    for (int d = 0; d < 3; ++d) c->nmax[d] = 0;
+    for (int k = 0; k < nq; ++k) {
+        bool ok = true;
+        double phase = 0.0;
+        for (int d = 0; d < nd; ++d) {
+            const double v = q[static_cast<size_t>(k) * nd + d];
+            if (!std::isfinite(v)) return fail(PIMCB_EINVAL, "q[%d][%d] is not finite", k, d);
+            qsoa[static_cast<size_t>(d) * nq + k] = v;
+            phase += std::fabs(v) * c->side[d];             // |x_d| may reach a few box lengths for unwrapped beads
+            if (c->periodic[d]) {
+                const double n = v * c->side[d] / (2.0 * M_PI);
+                const double rn = std::nearbyint(n);
+                if (std::fabs(n - rn) > 1e-9 * std::max(1.0, std::fabs(rn)) || std::fabs(rn) > 4096.0) ok = false;
+                c->qn[static_cast<size_t>(k) * nd + d] = static_cast<int>(rn);
+            } else if (v != 0.0) {
+                ok = false;
+            }
+        }
+        c->max_phase = std::max(c->max_phase, 4.0 * phase);
+        c->comm[k] = ok;
+        if (ok) c->ncomm++; else sel.push_back(k);
+    }
+    if (c->ncomm == nq)
+        for (int k = 0; k < nq; ++k)
+            for (int d = 0; d < nd; ++d) c->nmax[d] = std::max(c->nmax[d], std::abs(c->qn[static_cast<size_t>(k) * nd + d]));
+    c->nsel = static_cast<int>(sel.size());
+    int rc;
+    if ((rc = c->d_q.ensure(sizeof(double) * qsoa.size()))) return rc;
+    if ((rc = c->d_comm.ensure(nq))) return rc;
+    if ((rc = c->d_qn.ensure(sizeof(int) * c->qn.size()))) return rc;
+    if ((rc = c->d_qidx.ensure(sizeof(int) * std::max<size_t>(1, sel.size())))) return rc;
+    CU(cudaMemcpyAsync(c->d_q.p, qsoa.data(), sizeof(double) * qsoa.size(), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_comm.p, c->comm.data(), nq, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_qn.p, c->qn.data(), sizeof(int) * c->qn.size(), cudaMemcpyHostToDevice, c->stream));
+    if (!sel.empty()) CU(cudaMemcpyAsync(c->d_qidx.p, sel.data(), sizeof(int) * sel.size(), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->bins_len = 0;   // layout changed: bins are re-created on the next measurement
+    return 0;
+}
+
+int pimcb_num_commensurate(const pimcb_ctx* c) { return c ? c->ncomm : PIMCB_EINVAL; }
+
+int pimcb_set_rho_mode(pimcb_ctx* c, int mode) {
+    if (!c || (mode != 0 && mode != 1)) return fail(PIMCB_EINVAL, "rho mode must be 0 or 1");
+    c->rho_mode = mode;
+    return 0;
+}
+
+int pimcb_num_slots(const pimcb_ctx*) { return kSlots; }
+
+int pimcb_stage_batch_slot(pimcb_ctx* c, int slot, const double* beads, int B, int M, int N, int Next) {
+    return stage_into(c, slot, beads, B, M, N, Next);
+}
+
+int pimcb_select_slot(pimcb_ctx* c, int slot) {
+    if (!c || slot < 0 || slot >= kSlots) return fail(PIMCB_EINVAL, "slot out of range");
+    if (!c->slots[slot].staged) return fail(PIMCB_ESTATE, "slot %d has no staged beads", slot);
+    c->cur = slot;
+    return 0;
+}
+
+int pimcb_stage_batch(pimcb_ctx* c, const double* beads, int B, int M, int N, int Next) {
+    if (!c) return fail(PIMCB_EINVAL, "null ctx");
+    const int slot = (c->cur + 1 + kSlots) % kSlots;
+    int rc = stage_into(c, slot, beads, B, M, N, Next);
+    if (rc) return rc;
+    c->cur = slot;
+    return 0;
+}
+
+int pimcb_stage_beads(pimcb_ctx* c, const double* beads, int M, int N, int Next) {
+    return pimcb_stage_batch(c, beads, 1, M, N, Next);
+}
+
+int pimcb_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(PIMCB_EINVAL, "null pointer");
+    CU(cudaMallocHost(ptr, bytes));
+    return 0;
+}
+int pimcb_host_free(void* ptr) { CU(cudaFreeHost(ptr)); return 0; }
+int pimcb_host_register(void* ptr, size_t bytes) { CU(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault)); return 0; }
+int pimcb_host_unregister(void* ptr) { CU(cudaHostUnregister(ptr)); return 0; }
+
+int pimcb_ssf_isf(pimcb_ctx* c, double* ssf_out, double* isf_out) {
+    if (!c) return fail(PIMCB_EINVAL, "null ctx");
+    CU(cudaSetDevice(c->device));
+    Slot* s;
+    int rc = run_estimators(c, &s);
+    if (rc) return rc;
+    return copy_out(c, *s, ssf_out, isf_out);
+}
+int pimcb_ssf(pimcb_ctx* c, double* out) { return pimcb_ssf_isf(c, out, nullptr); }
+int pimcb_isf(pimcb_ctx* c, double* out) { return pimcb_ssf_isf(c, nullptr, out); }
+
+int pimcb_measure(pimcb_ctx* c) {
+    if (!c) return fail(PIMCB_EINVAL, "null ctx");
+    CU(cudaSetDevice(c->device));
+    Slot* s;
+    int rc = run_estimators(c, &s);
+    if (rc) return rc;
+    {
+        KTimer kt(c, K_BINS);
+        const size_t len = c->bins_len;
+        bins_accumulate_kernel<<<static_cast<unsigned>((len + 255) / 256), 256, 0, c->stream>>>(c->d_cfg.as<double>(), c->d_bins.as<double>(), s->B, len);
+        CU(cudaGetLastError());
+    }
+    c->n_acc += s->B;
+    return 0;
+}
+
+int pimcb_reset_bins(pimcb_ctx* c) {
+    if (!c) return fail(PIMCB_EINVAL, "null ctx");
+    if (c->bins_len) CU(cudaMemsetAsync(c->d_bins.p, 0, sizeof(double) * c->bins_len, c->stream));
+    c->n_acc = 0;
+    return 0;
+}
+
+int pimcb_read_bins(pimcb_ctx* c, double* ssf, double* isf, long* num_acc) {
+    if (!c) return fail(PIMCB_EINVAL, "null ctx");
+    if (!c->bins_len) return fail(PIMCB_ESTATE, "no measurement accumulated yet");
+    CU(cudaSetDevice(c->device));
+    const size_t bytes = sizeof(double) * c->bins_len;
+    int rc = c->h_out.ensure(bytes);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->h_out.p, c->d_bins.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const double* h = static_cast<const double*>(c->h_out.p);
+    if (ssf) std::memcpy(ssf, h, sizeof(double) * c->nq);
+    if (isf) std::memcpy(isf, h + c->nq, bytes - sizeof(double) * c->nq);
+    if (num_acc) *num_acc = c->n_acc;
+    return 0;
+}
+
+int pimcb_bins_device_ptr(pimcb_ctx* c, void** dptr, size_t* count) {
+    if (!c || !dptr) return fail(PIMCB_EINVAL, "null argument");
+    if (!c->bins_len) return fail(PIMCB_ESTATE, "no measurement accumulated yet");
+    *dptr = c->d_bins.p;
+    if (count) *count = c->bins_len;
+    return 0;
+}
+
+int pimcb_sync(pimcb_ctx* c) {
+    if (!c) return fail(PIMCB_EINVAL, "null ctx");
+    CU(cudaStreamSynchronize(c->copy_stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int pimcb_stream(pimcb_ctx* c, void** stream) {
+    if (!c || !stream) return fail(PIMCB_EINVAL, "null argument");
+    *stream = c->stream;
+    return 0;
+}
+
+int pimcb_set_pair_table(pimcb_ctx* c, const double* V, const double* dVdr, int len, double dr, const double* extV, const double* extdVdr) {
+    if (!c || !V || len < 1 || !(dr > 0.0)) return fail(PIMCB_EINVAL, "bad pair-table arguments");
+    CU(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = c->d_V.ensure(sizeof(double) * len))) return rc;
+    CU(cudaMemcpyAsync(c->d_V.p, V, sizeof(double) * len, cudaMemcpyHostToDevice, c->stream));
+    c->have_dV = dVdr != nullptr;
+    if (dVdr) {
+        if ((rc = c->d_dV.ensure(sizeof(double) * len))) return rc;
+        CU(cudaMemcpyAsync(c->d_dV.p, dVdr, sizeof(double) * len, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    c->tab_len = len;
+    c->dr = dr;
+    c->extV[0] = extV ? extV[0] : 0.0; c->extV[1] = extV ? extV[1] : 0.0;
+    c->extdV[0] = extdVdr ? extdVdr[0] : 0.0; c->extdV[1] = extdVdr ? extdVdr[1] : 0.0;
+    return 0;
+}
+
+int pimcb_pair_sums(pimcb_ctx* c, double* vint, double* f2, int* sephist, double dSep, int f2_parity) {
+    if (!c || !vint) return fail(PIMCB_EINVAL, "null argument");
+    CU(cudaSetDevice(c->device));
+    Slot* s;
+    int rc = need_cur(c, &s);
+    if (rc) return rc;
+    if (!c->have_box) return fail(PIMCB_ESTATE, "no box set");
+    if (!c->tab_len) return fail(PIMCB_ESTATE, "no pair table set");
+    if (f2 && !c->have_dV) return fail(PIMCB_ESTATE, "gradVSquared requested but no dV/dr table set");
+    if (sephist && !(dSep > 0.0)) return fail(PIMCB_EINVAL, "dSep must be positive");
+    if (f2_parity < -1 || f2_parity > 1) return fail(PIMCB_EINVAL, "f2_parity must be -1, 0 or 1");
+    const int nsl = s->B * s->M, nd = c->ndim;
+    if ((rc = c->d_vint.ensure(sizeof(double) * nsl))) return rc;
+    if (f2 && (rc = c->d_f2.ensure(sizeof(double) * nsl))) return rc;
+    if (sephist && (rc = c->d_hist.ensure(sizeof(int) * static_cast<size_t>(nsl) * kNPCFSEP))) return rc;
+    PairParams pp{c->d_V.as<double>(), c->d_dV.as<double>(), c->tab_len, c->dr, {c->extV[0], c->extV[1]}, {c->extdV[0], c->extdV[1]},
+                  sephist ? dSep : 1.0, sephist ? 1 : 0, f2_parity, s->M};
+    CU(cudaStreamWaitEvent(c->stream, s->ready, 0));
+    {
+        KTimer kt(c, K_PAIR);
+        const size_t smem = sizeof(double) * nd * s->Npad;
+        const int grid = grid_for(c, nsl, 8);
+#define LAUNCH_PAIR(ND, F2)                                                                                       \
+        rc = set_smem(pair_kernel<ND, F2>, smem); if (rc) return rc;                                               \
+        pair_kernel<ND, F2><<<grid, 256, smem, c->stream>>>(s->pos.as<double>(), nsl, s->N, s->Npad, c->box, pp,  \
+                                                            c->d_vint.as<double>(), c->d_f2.as<double>(), c->d_hist.as<int>())
+        if (f2) {
+            if (nd == 1) { LAUNCH_PAIR(1, true); } else if (nd == 2) { LAUNCH_PAIR(2, true); } else { LAUNCH_PAIR(3, true); }
+        } else {
+            if (nd == 1) { LAUNCH_PAIR(1, false); } else if (nd == 2) { LAUNCH_PAIR(2, false); } else { LAUNCH_PAIR(3, false); }
+        }
+#undef LAUNCH_PAIR
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(s->consumed, c->stream));
+    CU(cudaMemcpyAsync(vint, c->d_vint.p, sizeof(double) * nsl, cudaMemcpyDeviceToHost, c->stream));
+    if (f2) CU(cudaMemcpyAsync(f2, c->d_f2.p, sizeof(double) * nsl, cudaMemcpyDeviceToHost, c->stream));
+    if (sephist) CU(cudaMemcpyAsync(sephist, c->d_hist.p, sizeof(int) * static_cast<size_t>(nsl) * kNPCFSEP, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int pimcb_measure_fp64_peak(pimcb_ctx* c, double* tflops, double seconds_target) {
+    if (!c || !tflops) return fail(PIMCB_EINVAL, "null argument");
+    CU(cudaSetDevice(c->device));
+    int rc = c->d_scratch.ensure(64);
+    if (rc) return rc;
+    const int grid = c->sm_count * 8, threads = 256, iters = 4096;
+    const double flop_per_launch = 2.0 * 32.0 * iters * static_cast<double>(grid) * threads;
+    cudaEvent_t e0 = c->ev0[kKernels - 2], e1 = c->ev1[kKernels - 2];
+    for (int w = 0; w < 3; ++w) fp64_peak_kernel<<<grid, threads, 0, c->stream>>>(c->d_scratch.as<double>(), iters, 1.0000001, 1e-9);
+    CU(cudaStreamSynchronize(c->stream));
+    double best = 0.0, elapsed = 0.0;
+    int reps = 0;
+    while (elapsed < seconds_target || reps < 3) {
+        CU(cudaEventRecord(e0, c->stream));
+        for (int k = 0; k < 4; ++k) fp64_peak_kernel<<<grid, threads, 0, c->stream>>>(c->d_scratch.as<double>(), iters, 1.0000001, 1e-9);
+        CU(cudaEventRecord(e1, c->stream));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::max(best, 4.0 * flop_per_launch / (ms * 1e-3) / 1e12);
+        elapsed += ms * 1e-3;
+        c->launches += 4;
+        if (++reps > 10000) break;
+    }
+    CU(cudaGetLastError());
+    *tflops = best;
+    return 0;
+}
+
+int pimcb_set_profiling(pimcb_ctx* c, int on) {
+    if (!c) return fail(PIMCB_EINVAL, "null ctx");
+    c->profiling = on != 0;
+    return 0;
+}
+
+int pimcb_kernel_times(pimcb_ctx* c, double* ms_total, long* count, int reset) {
+    if (!c) return fail(PIMCB_EINVAL, "null ctx");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (auto& r : c->recs) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, r.a, r.b));
+        c->k_ms[r.k] += ms;
+        c->k_count[r.k]++;
+        c->ev_pool.push_back(r.a);
+        c->ev_pool.push_back(r.b);
+    }
+    c->recs.clear();
+    for (int k = 0; k < kKernels; ++k) {
+        if (ms_total) ms_total[k] = c->k_ms[k];
+        if (count) count[k] = c->k_count[k];
+        if (reset) { c->k_ms[k] = 0.0; c->k_count[k] = 0; }
+    }
+    return 0;
+}
+
+long pimcb_launch_count(const pimcb_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+"""Synthetic He-4 worldline configurations and wave-vector sets.
+
+Inputs for tests and bench.py.  Layout mirrors the reference's bead storage: a row-major AoS
+`double[M][N_ext][NDIM]` (`DynamicArray<dVec,2> beads`, include/path.h:164) whose first N columns
+of every slice are the active beads of a diagonal configuration and whose `N_ext - N` trailing
+columns are padding (src/path.cpp:274-294 grows the extent and never shrinks it).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+LAMBDA_HE4 = 24.24 / 4.0030      # constants.cpp:128 lambda = 24.24/m, m = 4.0030 amu
+BASE_SEED = 139853               # src/pdrive.cpp:41 base RNG seed of the reference
+
+
+@dataclass(frozen=True)
+class Shape:
+    """One of BASELINE.json's named configurations."""
+    name: str
+    ndim: int
+    N: int
+    M: int
+    T: float
+    rho: float
+    nq: int
+
+    @property
+    def side(self) -> np.ndarray:
+        return np.full(self.ndim, (self.N / self.rho) ** (1.0 / self.ndim))   # src/container.cpp:88
+
+    @property
+    def tau(self) -> float:
+        return 1.0 / (self.T * self.M)                                        # src/setup.cpp:1009
+
+
+# C1..C4 of BASELINE.json (C5 = 64 x C2).  C3's 2-D density is not given upstream; 0.0432 A^-2.
+C1 = Shape("C1", 3, 16, 124, 2.0, 0.02198, 64)
+C2 = Shape("C2", 3, 256, 170, 1.5, 0.02198, 64)
+C3 = Shape("C3", 2, 128, 250, 1.0, 0.0432, 289)
+C4 = Shape("C4", 3, 1024, 320, 1.5, 0.02198, 256)
+SHAPES = {s.name: s for s in (C1, C2, C3, C4)}
+
+
+def put_in_bc(r: np.ndarray, side: np.ndarray) -> np.ndarray:
+    """include/container.h:50-53 on an array of vectors."""
+    return r - side * np.floor(r * (1.0 / side) + 0.5)
+
+
+def gen_config(N: int, M: int, ndim: int, rho: float, T: float, seed: int = BASE_SEED, pad: int = 3) -> np.ndarray:
+    """Lattice + jitter start, periodic Brownian-bridge worldlines; AoS [M][N+pad][ndim], padding zeroed."""
+    rng = np.random.default_rng(seed)
+    L = (N / rho) ** (1.0 / ndim)
+    side = np.full(ndim, L)
+    n_side = int(math.ceil(N ** (1.0 / ndim) - 1e-12))
+    a = L / n_side
+    grid = np.stack(np.meshgrid(*([np.arange(n_side)] * ndim), indexing="ij"), axis=-1).reshape(-1, ndim)[:N]
+    base = (grid + 0.5) * a - 0.5 * L + rng.uniform(-0.15 * a, 0.15 * a, size=(N, ndim))
+    tau = 1.0 / (T * M)
+    steps = rng.normal(0.0, math.sqrt(2.0 * LAMBDA_HE4 * tau), size=(M, N, ndim))
+    steps -= steps.mean(axis=0, keepdims=True)            # closed (periodic in imaginary time) paths
+    walk = np.cumsum(steps, axis=0) - steps[0]
+    pos = put_in_bc(base[None, :, :] + walk, side)
+    beads = np.zeros((M, N + pad, ndim))
+    beads[:, :N, :] = pos
+    return beads
+
+
+def gen_batch(shape: Shape, B: int, first: int = 0, pad: int = 3) -> np.ndarray:
+    """[B][M][N+pad][ndim]; configuration k uses seed BASE_SEED + first + k."""
+    return np.stack([gen_config(shape.N, shape.M, shape.ndim, shape.rho, shape.T, BASE_SEED + first + k, pad)
+                     for k in range(B)])
+
+
+def lattice_indices(nq: int, ndim: int, include_zero: bool = False) -> np.ndarray:
+    """First nq integer vectors n sorted by (|n|^2, lexicographic)."""
+    r = int(math.ceil((nq + 1) ** (1.0 / ndim))) + 2   # cube of half-width r contains the first nq shells
+    g = np.stack(np.meshgrid(*([np.arange(-r, r + 1)] * ndim), indexing="ij"), axis=-1).reshape(-1, ndim)
+    if not include_zero:
+        g = g[np.any(g != 0, axis=1)]
+    key = [g[:, d] for d in reversed(range(ndim))] + [np.sum(g * g, axis=1)]
+    order = np.lexsort(key)
+    return g[order][:nq]
+
+
+def commensurate_q(nq: int, side: np.ndarray, include_zero: bool = False) -> np.ndarray:
+    """q = (2 pi / side_j) * n_j as `--wavevector_type int` produces them (src/estimator.cpp:463)."""
+    n = lattice_indices(nq, len(side), include_zero)
+    return (2.0 * math.pi / np.asarray(side)) * n
+
+
+def int_wavevector_text(nq: int, ndim: int) -> str:
+    """The `--wavevector "..."` string whose `int` parse gives commensurate_q(nq, .)."""
+    return " ".join(str(int(v)) for v in lattice_indices(nq, ndim).reshape(-1))
+
+
+def float_q(nq: int, ndim: int, seed: int = 7, qmax: float = 2.5) -> np.ndarray:
+    """Non-commensurate wave-vectors, rounded through float like `--wavevector_type float` (std::stof)."""
+    rng = np.random.default_rng(seed)
+    q = rng.uniform(-qmax, qmax, size=(nq, ndim))
+    return q.astype(np.float32).astype(np.float64)

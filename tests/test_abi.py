@@ -1,0 +1,53 @@
+"""The C-ABI library loads and exports every symbol include/pimc_b200.h declares (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from pimc_b200 import build
+    return ctypes.CDLL(build.build_lib())
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pimc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pimcb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(lib):
+    syms = declared_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/pimc_b200.h but not exported"
+
+
+def test_binding_covers_header():
+    from pimc_b200 import api
+    assert sorted(api.SYMBOLS) == declared_symbols()
+
+
+def test_no_device_fails_loudly_not_silently(lib):
+    """Without a CUDA device the library must refuse to create a context (there is no CPU fallback)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = ctypes.c_void_p()
+    rc = lib.pimcb_create(ctypes.byref(h), 0, 3)
+    assert rc < 0 and not h.value
+    lib.pimcb_last_error.restype = ctypes.c_char_p
+    assert lib.pimcb_last_error()
+
+
+def test_product_never_imports_oracle():
+    """oracle/ is test infrastructure: nothing under pimc_b200/ may reference it."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "pimc_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.lower(), f"{f} mentions the oracle"

@@ -1,0 +1,222 @@
+"""GPU parity: CUDA path (through the C ABI) vs the CPU oracle on identical seeded inputs."""
+import math
+
+import numpy as np
+import pytest
+
+from parity import assert_parity
+from pimc_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from pimc_b200 import api as _api
+    return _api
+
+
+def make_ctx(api, shape, q, periodic=None):
+    ctx = api.Context(0, shape.ndim)
+    ctx.set_box(shape.side, periodic)
+    ctx.set_qvecs(q)
+    return ctx
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_c1_full_direct_oracle(api, orc, nthreads, mode):
+    """C1 (N=16, M=124, 64 q): every q, every tau against the reference's O(Nq M^2 N^2) loop."""
+    s = synth.C1
+    beads = synth.gen_config(s.N, s.M, s.ndim, s.rho, s.T)
+    q = orc.qvectors("int", synth.int_wavevector_text(s.nq, 3), s.side)
+    with make_ctx(api, s, q) as ctx:
+        assert ctx.num_commensurate() == s.nq
+        ctx.set_rho_mode(mode)
+        ssf, isf = ctx.stage(beads, s.N).ssf_isf()
+    assert_parity(ssf[0], orc.ssf(s.side, beads, s.N, q, nthreads=nthreads), "C1 ssf")
+    assert_parity(isf[0], orc.isf(beads, s.N, q, nthreads=nthreads), "C1 isf")
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_c2_shape(api, orc, nthreads, mode):
+    """C2 (N=256, M=170, 64 q): S(q) for all q against the min-image CPU loop; F(q,tau) for all q against the
+    factorised CPU variant and for 1 q against the direct reference loop (1.9e9 terms)."""
+    s = synth.C2
+    beads = synth.gen_config(s.N, s.M, s.ndim, s.rho, s.T, seed=synth.BASE_SEED + 1)
+    q = synth.commensurate_q(s.nq, s.side)
+    with make_ctx(api, s, q) as ctx:
+        ctx.set_rho_mode(mode)
+        ssf, isf = ctx.stage(beads, s.N).ssf_isf()
+        ssf_only = ctx.ssf()
+        isf_only = ctx.isf()
+    assert np.array_equal(ssf, ssf_only) and np.array_equal(isf, isf_only)
+    assert_parity(ssf[0], orc.ssf(s.side, beads, s.N, q, nthreads=nthreads), "C2 ssf")
+    assert_parity(isf[0], orc.isf_factorised(beads, s.N, q), "C2 isf (factorised oracle)")
+    k = 37
+    assert_parity(isf[0, k:k + 1], orc.isf(beads, s.N, q[k:k + 1], nthreads=nthreads), "C2 isf (direct oracle, 1 q)")
+
+
+def test_c3_2d_full_grid(api, orc, nthreads):
+    """C3: NDIM=2, N=128, M=250, max_int "8 8" -> 289 q incl. q=0, odometer order."""
+    s = synth.C3
+    beads = synth.gen_config(s.N, s.M, s.ndim, s.rho, s.T, seed=synth.BASE_SEED + 2)
+    q = orc.qvectors("max_int", "8 8", s.side)
+    assert len(q) == 289
+    for mode in (0, 1):
+        with make_ctx(api, s, q) as ctx:
+            ctx.set_rho_mode(mode)
+            ssf, isf = ctx.stage(beads, s.N).ssf_isf()
+        assert_parity(ssf[0], orc.ssf(s.side, beads, s.N, q, nthreads=nthreads), f"C3 ssf mode {mode}")
+        assert_parity(isf[0], orc.isf_factorised(beads, s.N, q), f"C3 isf mode {mode}")
+    zero = np.flatnonzero(np.all(q == 0, axis=1))[0]
+    np.testing.assert_allclose(ssf[0, zero], s.M * s.N, rtol=1e-14)
+
+
+def test_non_commensurate_q_uses_direct_min_image(api, orc, nthreads):
+    """`float` wave-vectors: S(q) must follow the CPU min-image pair sum, F(q,tau) raw positions."""
+    s = synth.Shape("mix", 3, 64, 40, 2.0, 0.02198, 0)
+    beads = synth.gen_config(s.N, s.M, 3, s.rho, s.T, seed=11)
+    q = np.vstack([synth.float_q(9, 3), synth.commensurate_q(5, s.side), synth.float_q(2, 3, seed=9)])
+    with make_ctx(api, s, q) as ctx:
+        assert ctx.num_commensurate() == 5
+        ssf, isf = ctx.stage(beads, s.N).ssf_isf()
+    assert_parity(ssf[0], orc.ssf(s.side, beads, s.N, q, nthreads=nthreads), "mixed ssf")
+    assert_parity(isf[0], orc.isf(beads, s.N, q, nthreads=nthreads), "mixed isf")
+
+
+@pytest.mark.parametrize("ndim,N,M,pad", [(1, 7, 6, 0), (2, 33, 10, 5), (3, 1, 4, 2), (3, 2, 2, 0), (3, 257, 8, 1)])
+def test_ragged_sizes(api, orc, ndim, N, M, pad):
+    """Odd particle counts, N=1, N_ext == N, N not a multiple of the CTA width."""
+    rho = {1: 0.2, 2: 0.0432, 3: 0.02198}[ndim]
+    s = synth.Shape("r", ndim, N, M, 2.0, rho, 0)
+    beads = synth.gen_config(N, M, ndim, rho, 2.0, seed=5, pad=pad)
+    if pad:
+        beads[:, N:, :] = 7777.0          # padding columns must never contribute
+    q = np.vstack([synth.commensurate_q(6, s.side, include_zero=True), synth.float_q(3, ndim)])
+    for mode in (0, 1):
+        with make_ctx(api, s, q) as ctx:
+            ctx.set_rho_mode(mode)
+            ssf, isf = ctx.stage(beads, N).ssf_isf()
+        assert_parity(ssf[0], orc.ssf(s.side, beads, N, q), f"ragged ssf {ndim}D N={N}")
+        assert_parity(isf[0], orc.isf(beads, N, q, nthreads=4), f"ragged isf {ndim}D N={N}")
+
+
+def test_batch_bins_and_slots(api, orc):
+    """A walker batch: per-configuration outputs, device-resident bin accumulation, slot rotation."""
+    s = synth.Shape("b", 3, 32, 16, 2.0, 0.02198, 0)
+    q = synth.commensurate_q(10, s.side)
+    batch = synth.gen_batch(s, 5)
+    with make_ctx(api, s, q) as ctx:
+        ssf, isf = ctx.stage(batch, s.N).ssf_isf()
+        for b in range(5):
+            assert_parity(ssf[b], orc.ssf(s.side, batch[b], s.N, q), f"batch ssf {b}")
+            assert_parity(isf[b], orc.isf(batch[b], s.N, q), f"batch isf {b}")
+        ctx.reset_bins()
+        ctx.measure()
+        ctx.stage(batch[:2], s.N, slot=2)
+        ctx.select_slot(2)
+        ctx.measure()
+        bs, bi, n = ctx.read_bins()
+        assert n == 7
+        assert_parity(bs, ssf.sum(axis=0) + ssf[:2].sum(axis=0), "bins ssf")
+        assert_parity(bi, isf.sum(axis=0) + isf[:2].sum(axis=0), "bins isf")
+        ctx.reset_bins()
+        ctx.measure()
+        assert ctx.read_bins()[2] == 2
+        assert ctx.launch_count() > 0
+
+
+def test_pinned_source_takes_device_transpose_path(api, orc):
+    s = synth.Shape("p", 3, 48, 12, 2.0, 0.02198, 0)
+    q = synth.commensurate_q(8, s.side)
+    batch = synth.gen_batch(s, 3, pad=5)
+    pin = api.PinnedArray(batch.shape)
+    pin.array[...] = batch
+    with make_ctx(api, s, q) as ctx:
+        a = ctx.stage(batch, s.N).ssf_isf()
+        b = ctx.stage(pin.array, s.N).ssf_isf()
+    pin.free()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("shape", [synth.C1, synth.C2])
+def test_pair_sums(api, orc, nthreads, shape):
+    """Vint[M] (+ sepHist, bit-exact) and gradVSquared[M] against LocalAction::V / gradVSquared restated on the CPU,
+    with the host-built Aziz table; total potentialAction for the gsf factors."""
+    s = shape
+    beads = synth.gen_config(s.N, s.M, s.ndim, s.rho, s.T, seed=synth.BASE_SEED + 3)
+    V, dV, dr = orc.aziz_table(orc.max_sep(s.side))
+    dSep = 0.5 * math.sqrt(3) * s.side[2] / 50
+    cv, cf, ch = orc.pair_sums(s.side, beads, s.N, V, dV, dr, dSep, nthreads=nthreads)
+    with api.Context(0, 3) as ctx:
+        ctx.set_box(s.side)
+        ctx.set_pair_table(V, dV, dr)
+        ctx.stage(beads, s.N)
+        gv, gf, gh = ctx.pair_sums(dSep)
+        gv2, _, gh2 = ctx.pair_sums(dSep, want_f2=False)
+        gv3, gf3, _ = ctx.pair_sums(dSep, want_hist=False, f2_parity=1)
+    assert np.array_equal(gh[0], ch), "sepHist must be bit-exact"
+    assert np.array_equal(gh2[0], ch)
+    assert_parity(gv[0], cv, "Vint")
+    assert_parity(gv2[0], cv, "Vint (V-only kernel)")
+    assert_parity(gf[0], cf, "gradVSquared")
+    assert_parity(gv3[0], cv, "Vint (odd-slice f2)")
+    assert_parity(gf3[0, 1::2], cf[1::2], "gradVSquared odd slices")
+    assert np.all(gf3[0, 0::2] == 0.0)
+    VF, GF = [2 / 3, 4 / 3], [0.0, 2 / 9]
+    Ug = orc.potential_action(gv3[0], gf3[0], VF, GF, s.tau, synth.LAMBDA_HE4)
+    Uc = orc.potential_action(cv, cf, VF, GF, s.tau, synth.LAMBDA_HE4)
+    assert abs(Ug - Uc) <= 1e-10 * abs(Uc)
+
+
+def test_pair_table_edges(api, orc):
+    """Separations below dr (k <= 0 -> extV[0]) and beyond the table (k >= len -> extV[1])."""
+    side = np.array([30.0, 30.0, 30.0])
+    M, N = 2, 4
+    beads = np.zeros((M, N, 3))
+    beads[:, 0] = [0.0, 0.0, 0.0]
+    beads[:, 1] = [1e-7, 0.0, 0.0]           # r < dr
+    beads[:, 2] = [14.0, 14.0, 14.0]         # r ~ 24 A, beyond a short table
+    beads[:, 3] = [3.0, 0.1, -0.2]
+    V, dV, dr = orc.aziz_table(12.0)
+    ext = (5.0, -7.0)
+    import numpy as _np
+    cv = _np.zeros(M)
+    with api.Context(0, 3) as ctx:
+        ctx.set_box(side)
+        ctx.set_pair_table(V, dV, dr, extV=ext, extdVdr=(0.0, 0.0))
+        ctx.stage(beads, N)
+        gv, _, gh = ctx.pair_sums(0.5 * math.sqrt(3) * 30.0 / 50, want_f2=False)
+    # oracle with the same extremal values
+    from oracle import oracle as _o
+    lib = _o.get().lib
+    import ctypes as C
+    sidec, per = _np.ascontiguousarray(side), _np.ones(3, dtype=_np.uint32)
+    extc = _np.array(ext)
+    hist = _np.zeros((M, 50), dtype=_np.int32)
+    dp = C.POINTER(C.c_double)
+    rc = lib.orc_pair_sums(3, sidec.ctypes.data_as(dp), per.ctypes.data_as(C.POINTER(C.c_uint)),
+                           beads.ctypes.data_as(dp), M, N, N, V.ctypes.data_as(dp), dV.ctypes.data_as(dp), len(V), dr,
+                           extc.ctypes.data_as(dp), extc.ctypes.data_as(dp), 0.5 * math.sqrt(3) * 30.0 / 50,
+                           cv.ctypes.data_as(dp), None, hist.ctypes.data_as(C.POINTER(C.c_int)), 1)
+    assert rc == 0
+    assert_parity(gv[0], cv, "edge Vint")
+    assert np.array_equal(gh[0], hist)
+
+
+def test_error_paths(api):
+    with pytest.raises(api.PimcbError):
+        api.Context(0, 4)
+    with api.Context(0, 3) as ctx:
+        with pytest.raises(api.PimcbError):
+            ctx.set_qvecs(np.zeros((2, 3)))          # box first
+        ctx.set_box([5.0, 5.0, 5.0])
+        ctx.set_qvecs(np.ones((2, 3)))
+        with pytest.raises(api.PimcbError):
+            ctx.shape = (1, 4, 2)
+            ctx.ssf()                                 # nothing staged
+        with pytest.raises(api.PimcbError):
+            ctx.stage(np.zeros((4, 2, 3)), 3)         # N > N_ext
+        ctx.stage(np.zeros((4, 2, 3)), 2)
+        with pytest.raises(api.PimcbError):
+            ctx.pair_sums(1.0)                        # no table
