@@ -6,7 +6,7 @@
 //
 // Kernels
 //   rho_generic_kernel   rho_q(t) = sum_i exp(i q.r_i(t)), one sincos per (q, bead)      [FP64-pipe bound]
-//   rho_lattice_kernel   same for commensurate q = 2 pi n / L by per-dimension phase powers [FP64-pipe bound]
+//   rho_lattice_kernel   same for commensurate q = 2 pi n / L: phase-power tables + sign-symmetry groups [smem-bandwidth bound]
 //   isf_corr_kernel      F(q,tau) = (1/N) sum_t0 Re[rho(t0) conj rho(t0+tau)], S(q) = F(q,0)
 //   ssf_direct_kernel    sum_{i<j} cos(q.minimage(r_i-r_j)) for non-commensurate q
 //   pair_kernel          per-slice Vint, sum_i |F_i|^2, separation histogram (table gathers)
@@ -124,42 +124,55 @@ __global__ void __launch_bounds__(256) rho_generic_kernel(const double* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
-// rho_q build for commensurate q = 2 pi n / L.  exp(i q.r) = prod_d e_d^{n_d}, e_d = exp(2 pi i x_d / L_d):
-// phase 1 tabulates the powers e_d^m, m = 0..nmax_d, of every particle of the slice in shared memory
-// (ND sincos + nmax complex multiplies per particle instead of nq sincos); phase 2 is one work item per
-// (q, particle chunk): ND-1 complex multiplies + 2 accumulates per (q, bead).  Negative n_d use the
-// conjugate.  Power table layout: tab[row][i] as double2 (re, im), row = rowoff[d] + m, row stride
-// N + 1 double2 so that lanes reading different rows hit different banks.
-// qn: int[nq][ND] lattice indices; kphase[d] = 2 pi / L_d.
+// rho_q build for commensurate q = 2 pi n / L ("lattice" path).
+//   exp(i q.r) = prod_d e_d^{n_d},  e_d = exp(2 pi i x_d / L_d).
+// Phase 1 tabulates the powers e_d^m, m = 0..nmax_d, of every particle of the slice in shared memory (ND sincos
+// + nmax complex multiplies per particle instead of nq sincos).  Phase 2 works on sign-symmetry GROUPS of
+// wave-vectors: all q that share (|n_0|,..,|n_{ND-1}|) -- up to 2^ND of them -- are produced from ONE pass over
+// the particles, because flipping the sign of a component only conjugates that factor:
+//   3-D:  P+- = X Y^(+-),  K[sb][0..3] = sum_i (P_re Z_re, P_im Z_im, P_re Z_im, P_im Z_re)       (16 FP64 / particle)
+//         rho(+a, sb b, sc c) = (K0 - sc K1) + i (sc K2 + K3),  rho(-a,..) = conj rho(+a, -sb b, -sc c)
+//   2-D:  K[0..3] = sum_i (X_re Y_re, X_im Y_im, X_re Y_im, X_im Y_re);   1-D:  K[0..1] = sum_i X.
+// Work item = (group, particle chunk).  The kernel is shared-memory-bandwidth bound (ND 16-byte table reads per
+// (group, particle)), not FP64 bound.
+// gkey: int[G][ND] = |n_d|;  gout: int[G][2^ND] = q index for sign pattern (bit d set = component d negative) or -1.
+// Power table layout: tab[row][i] as double2 (re, im), row = rowoff_d + m, row stride N + 1 double2 so that
+// lanes reading different rows / chunks hit different banks.
 // ---------------------------------------------------------------------------------------------
 template <int ND>
-__global__ void __launch_bounds__(256) rho_lattice_kernel(const double* __restrict__ pos, const int* __restrict__ qn,
-                                                           double* __restrict__ rho, int nslices, int N, int Npad, int nq,
-                                                           int P, int chunk, int3 nmax, double3 kphase) {
+struct LatticeK { static constexpr int NK = ND == 3 ? 8 : (ND == 2 ? 4 : 2); static constexpr int NPAT = 1 << ND; };
+
+template <int ND>
+__global__ void __launch_bounds__(256) rho_lattice_kernel(const double* __restrict__ pos, const int* __restrict__ gkey,
+                                                           const int* __restrict__ gout, double* __restrict__ rho, int nslices,
+                                                           int N, int Npad, int nq, int G, int P, int chunk, int3 nmax,
+                                                           double3 kphase) {
+    constexpr int NK = LatticeK<ND>::NK;
+    constexpr int NPAT = LatticeK<ND>::NPAT;
     extern __shared__ __align__(16) double sm[];
-    const int nmx[3] = {nmax.x, nmax.y, nmax.z};
-    const double kph[3] = {kphase.x, kphase.y, kphase.z};
-    int rowoff[ND + 1];
-    rowoff[0] = 0;
-#pragma unroll
-    for (int d = 0; d < ND; ++d) rowoff[d + 1] = rowoff[d] + nmx[d] + 1;
+    const int rowoff1 = nmax.x + 1;
+    const int rowoff2 = rowoff1 + (ND > 1 ? nmax.y + 1 : 0);
+    const int rows = rowoff2 + (ND > 2 ? nmax.z + 1 : 0);
     const int stride = N + 1;                                  // in double2 units
     double2* tab = reinterpret_cast<double2*>(sm);             // [rows][stride]
-    double* xs = sm + 2 * static_cast<size_t>(rowoff[ND]) * stride;   // [ND][Npad] staging of raw coordinates
-    double* part = xs + ND * Npad;                             // [2][P][nq]
-    const int items = nq * P;
+    double* xs = sm + 2 * static_cast<size_t>(rows) * stride;  // [ND][Npad] raw coordinates
+    double* part = xs + ND * Npad;                             // [P][G][NK]
+    const int items = G * P;
     for (int sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
         load_slice(xs, pos + static_cast<size_t>(sl) * ND * Npad, ND * Npad);
         __syncthreads();
         // phase 1: powers of the base phases
         for (int w = threadIdx.x; w < ND * N; w += blockDim.x) {
             const int d = w / N, i = w - d * N;
+            const double kp = d == 0 ? kphase.x : (d == 1 ? kphase.y : kphase.z);
+            const int nm = d == 0 ? nmax.x : (d == 1 ? nmax.y : nmax.z);
+            const int ro = d == 0 ? 0 : (d == 1 ? rowoff1 : rowoff2);
             double s, c;
-            sincos_fast(kph[d] * xs[d * Npad + i], s, c);
-            double2* col = tab + static_cast<size_t>(rowoff[d]) * stride + i;
+            sincos_fast(kp * xs[d * Npad + i], s, c);
+            double2* col = tab + static_cast<size_t>(ro) * stride + i;
             col[0] = make_double2(1.0, 0.0);
             double pr = c, pi = s;
-            for (int m = 1; m <= nmx[d]; ++m) {
+            for (int m = 1; m <= nm; ++m) {
                 col[static_cast<size_t>(m) * stride] = make_double2(pr, pi);
                 const double nr = fma(pr, c, -pi * s);
                 pi = fma(pr, s, pi * c);
@@ -167,100 +180,188 @@ __global__ void __launch_bounds__(256) rho_lattice_kernel(const double* __restri
             }
         }
         __syncthreads();
-        // phase 2
+        // phase 2: one (group, particle chunk) per work item
         for (int item = threadIdx.x; item < items; item += blockDim.x) {
-            const int p = item / nq;
-            const int iq = item - p * nq;
-            const double2* rowp[ND];
-            double sg[ND];
-#pragma unroll
-            for (int d = 0; d < ND; ++d) {
-                const int n = __ldg(qn + iq * ND + d);
-                rowp[d] = tab + static_cast<size_t>(rowoff[d] + abs(n)) * stride;
-                sg[d] = n < 0 ? -1.0 : 1.0;
-            }
+            const int p = item / G;
+            const int g = item - p * G;
             const int i0 = p * chunk;
             const int i1 = min(N, i0 + chunk);
-            double ac = 0.0, as = 0.0;
-#pragma unroll 2
-            for (int i = i0; i < i1; ++i) {
-                const double2 a = rowp[0][i];
-                double re = a.x, im = sg[0] * a.y;
+            const double2* X = tab + static_cast<size_t>(__ldg(gkey + g * ND)) * stride;
+            double K[NK];
 #pragma unroll
-                for (int d = 1; d < ND; ++d) {
-                    const double2 b = rowp[d][i];
-                    const double bi = sg[d] * b.y;
-                    const double nr = fma(re, b.x, -im * bi);
-                    im = fma(re, bi, im * b.x);
-                    re = nr;
+            for (int k = 0; k < NK; ++k) K[k] = 0.0;
+            if constexpr (ND == 1) {
+#pragma unroll 4
+                for (int i = i0; i < i1; ++i) {
+                    const double2 x = X[i];
+                    K[0] += x.x;
+                    K[1] += x.y;
                 }
-                ac += re;
-                as += im;
-            }
-            if (P == 1) {
-                rho[(static_cast<size_t>(sl) * 2 + 0) * nq + iq] = ac;
-                rho[(static_cast<size_t>(sl) * 2 + 1) * nq + iq] = as;
+            } else if constexpr (ND == 2) {
+                const double2* Y = tab + static_cast<size_t>(rowoff1 + __ldg(gkey + g * ND + 1)) * stride;
+#pragma unroll 4
+                for (int i = i0; i < i1; ++i) {
+                    const double2 x = X[i], y = Y[i];
+                    K[0] = fma(x.x, y.x, K[0]);
+                    K[1] = fma(x.y, y.y, K[1]);
+                    K[2] = fma(x.x, y.y, K[2]);
+                    K[3] = fma(x.y, y.x, K[3]);
+                }
             } else {
-                part[p * nq + iq] = ac;
-                part[(P + p) * nq + iq] = as;
+                const double2* Y = tab + static_cast<size_t>(rowoff1 + __ldg(gkey + g * ND + 1)) * stride;
+                const double2* Z = tab + static_cast<size_t>(rowoff2 + __ldg(gkey + g * ND + 2)) * stride;
+#pragma unroll 2
+                for (int i = i0; i < i1; ++i) {
+                    const double2 x = X[i], y = Y[i], z = Z[i];
+                    const double m1 = x.x * y.x, m2 = x.y * y.y, m3 = x.x * y.y, m4 = x.y * y.x;
+                    const double ppr = m1 - m2, ppi = m3 + m4;     // X * Y
+                    const double pmr = m1 + m2, pmi = m4 - m3;     // X * conj(Y)
+                    K[0] = fma(ppr, z.x, K[0]);
+                    K[1] = fma(ppi, z.y, K[1]);
+                    K[2] = fma(ppr, z.y, K[2]);
+                    K[3] = fma(ppi, z.x, K[3]);
+                    K[4] = fma(pmr, z.x, K[4]);
+                    K[5] = fma(pmi, z.y, K[5]);
+                    K[6] = fma(pmr, z.y, K[6]);
+                    K[7] = fma(pmi, z.x, K[7]);
+                }
             }
+            double* dst = part + static_cast<size_t>(item) * NK;
+#pragma unroll
+            for (int k = 0; k < NK; ++k) dst[k] = K[k];
         }
-        if (P > 1) {
-            __syncthreads();
-            for (int k = threadIdx.x; k < 2 * nq; k += blockDim.x) {
-                const int cs = k / nq, iq = k - cs * nq;
-                double acc = 0.0;
-                for (int p = 0; p < P; ++p) acc += part[(cs * P + p) * nq + iq];
-                rho[(static_cast<size_t>(sl) * 2 + cs) * nq + iq] = acc;
+        __syncthreads();
+        // phase 3: fold the chunks (fixed order) and unfold the sign patterns into rho
+        for (int w = threadIdx.x; w < G * NPAT; w += blockDim.x) {
+            const int g = w / NPAT, pat = w - g * NPAT;
+            const int iq = __ldg(gout + w);
+            if (iq < 0) continue;
+            const int sa = pat & 1;                                // conj of the pattern with all signs flipped
+            const int sb = ND > 1 ? (((pat >> 1) & 1) ^ sa) : 0;
+            const int sc = ND > 2 ? (((pat >> 2) & 1) ^ sa) : 0;
+            double k0 = 0.0, k1 = 0.0, k2 = 0.0, k3 = 0.0;
+            const int base = ND == 3 ? 4 * sb : 0;
+            for (int p = 0; p < P; ++p) {
+                const double* src = part + (static_cast<size_t>(p) * G + g) * NK + base;
+                k0 += src[0];
+                k1 += src[1];
+                if (ND > 1) { k2 += src[2]; k3 += src[3]; }
             }
+            double re, im;
+            if (ND == 1) { re = k0; im = k1; }
+            else {
+                const int sl_ = ND == 3 ? sc : sb;                 // sign of the last multiplied factor
+                re = sl_ ? k0 + k1 : k0 - k1;
+                im = sl_ ? k3 - k2 : k3 + k2;
+            }
+            rho[(static_cast<size_t>(sl) * 2 + 0) * nq + iq] = re;
+            rho[(static_cast<size_t>(sl) * 2 + 1) * nq + iq] = sa ? -im : im;
         }
         __syncthreads();
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// tau-correlation.  One CTA per (config, q).  C(t), S(t) of that q are staged twice back to back in shared
-// memory so that t0+tau needs no modulo.  Thread tau <= M/2 accumulates over t0 in ascending order and the
-// value is mirrored to M - tau (F(q,tau) = F(q,M-tau) identically).  Output per config:
-//   cfg[b][q]               = F(q,0)            (S(q) increment sf/N, commensurate q)
-//   cfg[b][nq + q*M + tau]  = F(q,tau)          (isf/N, reference CPU column layout)
+// tau-correlation:  F(q,tau) = (1/N) sum_t0 [C(t0) C(t0+tau) + S(t0) S(t0+tau)],  tau = 0..M/2, mirrored to M-tau
+// (F(q,tau) = F(q,M-tau) identically), S(q) = F(q,0) for commensurate q.
+// Register-tiled so that the FP64 pipe, not shared memory, is the limit: `lpq` lanes (8/16/32) share one (config,q)
+// pair; a lane owns 8 consecutive tau and sweeps t0 in blocks of 8 -- per block 8 broadcast values a(t0..t0+7) and a
+// 16-value window w(t0+tau0 .. +15) are pulled with 16-byte loads and feed 8x8x2 = 128 DFMAs.
+// C and S of a pair are staged periodically extended (index i -> value at i mod M, length 2M+16) with 2 doubles of
+// padding after every 8 so that the lanes' 64-byte-strided windows fall in different banks.
+// Output per config:  cfg[b][q] = F(q,0)  (sf/N, commensurate q);  cfg[b][nq + q*M + tau] = F(q,tau)  (isf/N).
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int corr_idx(int i) { return i + 2 * (i >> 3); }
+
 __global__ void __launch_bounds__(128) isf_corr_kernel(const double* __restrict__ rho, double* __restrict__ cfg, int M, int nq,
-                                                        double invN, const unsigned char* __restrict__ commensurate) {
+                                                        int npairs, int lpq, double invN,
+                                                        const unsigned char* __restrict__ commensurate) {
     extern __shared__ __align__(16) double sm[];
-    double* C = sm;            // [2M]
-    double* S = sm + 2 * M;    // [2M]
-    const int b = blockIdx.x / nq, iq = blockIdx.x - b * nq;
-    const size_t cfg_stride = static_cast<size_t>(nq) + static_cast<size_t>(nq) * M;
-    for (int t = threadIdx.x; t < M; t += blockDim.x) {
+    const int len = 2 * M + 16;
+    const int plen = corr_idx(len) + 2;                      // padded length of one array (even -> 16-byte aligned)
+    const int ppw = 32 / lpq;                                // pairs per warp
+    const int ppc = ppw * (blockDim.x >> 5);                 // pairs per CTA
+    const int pair0 = blockIdx.x * ppc;
+    // stage: consecutive threads take consecutive q of one slice (contiguous in rho), each value is written to
+    // every periodic image i = t, t+M, t+2M < len
+    for (int w = threadIdx.x; w < ppc * M; w += blockDim.x) {
+        const int t = w / ppc, lp = w - t * ppc;
+        const int pair = pair0 + lp;
+        if (pair >= npairs) continue;
+        const int b = pair / nq, iq = pair - b * nq;
         const size_t sl = static_cast<size_t>(b) * M + t;
         const double c = rho[(sl * 2 + 0) * nq + iq];
-        const double s = rho[(sl * 2 + 1) * nq + iq];
-        C[t] = c; C[t + M] = c;
-        S[t] = s; S[t + M] = s;
+        const double sn = rho[(sl * 2 + 1) * nq + iq];
+        for (int i = t; i < len; i += M) {
+            sm[(2 * lp + 0) * plen + corr_idx(i)] = c;
+            sm[(2 * lp + 1) * plen + corr_idx(i)] = sn;
+        }
     }
     __syncthreads();
-    double* out = cfg + static_cast<size_t>(b) * cfg_stride;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lp = warp * ppw + lane / lpq;
+    const int pair = pair0 + lp;
+    if (pair >= npairs) return;
+    const int b = pair / nq, iq = pair - b * nq;
+    const double* WC = sm + (2 * lp + 0) * plen;
+    const double* WS = sm + (2 * lp + 1) * plen;
+    const size_t cfg_stride = static_cast<size_t>(nq) + static_cast<size_t>(nq) * M;
+    double* out = cfg + static_cast<size_t>(b) * cfg_stride + nq + static_cast<size_t>(iq) * M;
     const int half = M / 2;
-    for (int tau = threadIdx.x; tau <= half; tau += blockDim.x) {
-        double a0 = 0.0, a1 = 0.0;
-        int t0 = 0;
-        for (; t0 + 1 < M; t0 += 2) {
-            a0 = fma(C[t0], C[t0 + tau], a0);
-            a0 = fma(S[t0], S[t0 + tau], a0);
-            a1 = fma(C[t0 + 1], C[t0 + 1 + tau], a1);
-            a1 = fma(S[t0 + 1], S[t0 + 1 + tau], a1);
+    const int nblk = (half + 1 + 7) / 8;                     // tau blocks of 8
+    for (int tb = lane % lpq; tb < nblk; tb += lpq) {
+        const int tau0 = 8 * tb;
+        double acc[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) acc[v] = 0.0;
+        for (int t0 = 0; t0 < M; t0 += 8) {
+            double aC[8], aS[8], wC[16], wS[16];
+            {
+                const double2* pa = reinterpret_cast<const double2*>(WC + corr_idx(t0));
+                const double2* pb = reinterpret_cast<const double2*>(WS + corr_idx(t0));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double2 x = pa[k], y = pb[k];
+                    aC[2 * k] = x.x; aC[2 * k + 1] = x.y;
+                    aS[2 * k] = y.x; aS[2 * k + 1] = y.y;
+                }
+            }
+            if (t0 + 8 > M) {                                // last block of a non-multiple-of-8 M: drop t0 >= M
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (t0 + u >= M) { aC[u] = 0.0; aS[u] = 0.0; }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double2* pc = reinterpret_cast<const double2*>(WC + corr_idx(t0 + tau0 + 8 * h));
+                const double2* ps = reinterpret_cast<const double2*>(WS + corr_idx(t0 + tau0 + 8 * h));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double2 x = pc[k], y = ps[k];
+                    wC[8 * h + 2 * k] = x.x; wC[8 * h + 2 * k + 1] = x.y;
+                    wS[8 * h + 2 * k] = y.x; wS[8 * h + 2 * k + 1] = y.y;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    acc[v] = fma(aC[u], wC[u + v], acc[v]);
+                    acc[v] = fma(aS[u], wS[u + v], acc[v]);
+                }
+            }
         }
-        if (t0 < M) {
-            a0 = fma(C[t0], C[t0 + tau], a0);
-            a0 = fma(S[t0], S[t0 + tau], a0);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            const int tau = tau0 + v;
+            if (tau > half) continue;
+            const double val = acc[v] * invN;
+            out[tau] = val;
+            if (tau > 0 && tau < M - tau) out[M - tau] = val;
+            if (tau == 0 && commensurate[iq]) cfg[static_cast<size_t>(b) * cfg_stride + iq] = val;
         }
-        const double v = (a0 + a1) * invN;
-        out[nq + static_cast<size_t>(iq) * M + tau] = v;
-        if (tau > 0 && tau < M - tau) out[nq + static_cast<size_t>(iq) * M + (M - tau)] = v;
-        if (tau == 0 && commensurate[iq]) out[iq] = v;
     }
-    // odd M never occurs upstream (setup.cpp:1001-1008 forces M even) but stay correct: tau in (M/2, M) mirrors.
+    // odd M never occurs upstream (setup.cpp:1001-1008 forces M even); for odd M, tau = (M+1)/2.. mirror as well.
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -95,8 +95,9 @@ struct pimcb_ctx {
     std::vector<unsigned char> comm;
     std::vector<int> qn;                   // lattice indices [nq][ndim] (valid when commensurate)
     int nmax[3] = {0, 0, 0};
+    int ngroups = 0;                       // sign-symmetry groups of the lattice path (0 = path unavailable)
     double max_phase = 0.0;
-    DevBuf d_q, d_comm, d_qn, d_qidx;
+    DevBuf d_q, d_comm, d_qn, d_qidx, d_gkey, d_gout;
     int rho_mode = 1;
     // beads
     Slot slots[kSlots];
@@ -154,17 +155,18 @@ int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // Choose the particle split P (chunks per q) for the rho kernels: maximise lane utilisation of a
 // 256-thread CTA subject to the partial-sum shared-memory budget.
-void choose_split(int nq, int N, int threads, size_t smem_fixed, size_t smem_limit, int* P_out, int* chunk_out) {
+void choose_split(int nitems, int N, int threads, size_t smem_fixed, size_t part_bytes_per_item, size_t smem_limit,
+                  int* P_out, int* chunk_out) {
     int bestP = 1;
     double best = -1.0;
     for (int P = 1; P <= 64 && P <= N; ++P) {
         const int chunk = (N + P - 1) / P;
         if (static_cast<long>(chunk) * (P - 1) >= N) continue;                       // empty trailing chunk
-        const size_t smem = smem_fixed + (P > 1 ? sizeof(double) * 2 * P * nq : 0);
-        if (smem > smem_limit) break;
-        const long items = static_cast<long>(nq) * P;
+        const size_t smem = smem_fixed + part_bytes_per_item * P * nitems;
+        if (P > 1 && smem > smem_limit) break;
+        const long items = static_cast<long>(nitems) * P;
         const long passes = (items + threads - 1) / threads;
-        double eff = static_cast<double>(nq) * N / (static_cast<double>(passes) * threads * chunk);
+        double eff = static_cast<double>(nitems) * N / (static_cast<double>(passes) * threads * chunk);
         if (items < threads) eff *= 0.999;                                           // prefer full CTAs on ties
         eff -= 1e-4 * P;                                                             // prefer fewer partials on ties
         if (eff > best) { best = eff; bestP = P; }
@@ -173,8 +175,10 @@ void choose_split(int nq, int N, int threads, size_t smem_fixed, size_t smem_lim
     *chunk_out = (N + bestP - 1) / bestP;
 }
 
-int grid_for(const pimcb_ctx* c, int nslices, int ctas_per_sm) {
-    return std::max(1, std::min(nslices, c->sm_count * ctas_per_sm));
+// One CTA per (configuration, slice): the hardware CTA scheduler hands slices out dynamically, so SMs never
+// idle behind a static partition (a fixed grid of k CTAs/SM with fewer than k resident serialises the excess).
+int grid_for(const pimcb_ctx*, int nslices, int /*ctas_per_sm*/) {
+    return std::max(1, nslices);
 }
 
 template <class K>
@@ -199,16 +203,16 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
     for (int d = 0; d < nd; ++d) rows += c->nmax[d] + 1;
     const size_t lattice_fixed = sizeof(double) * (2 * static_cast<size_t>(rows) * (s.N + 1) + static_cast<size_t>(nd) * s.Npad);
     // lattice path only when every q is commensurate and the phase-power table leaves room for >= 2 CTAs per SM
-    const bool lattice = c->rho_mode == 1 && c->ncomm == nq && nq > 0 && lattice_fixed <= 100 * 1024;
+    const bool lattice = c->rho_mode == 1 && c->ngroups > 0 && lattice_fixed <= 100 * 1024;
     int rc = c->d_rho.ensure(sizeof(double) * 2 * static_cast<size_t>(nsl) * nq);
     if (rc) return rc;
     int P, chunk;
     KTimer kt(c, K_RHO);
+    const int grid = grid_for(c, nsl, 8);
     if (!lattice) {
         const size_t fixed = sizeof(double) * nd * s.Npad;
-        choose_split(nq, s.N, 256, fixed, limit, &P, &chunk);
+        choose_split(nq, s.N, 256, fixed, sizeof(double) * 2, limit, &P, &chunk);
         const size_t smem = fixed + (P > 1 ? sizeof(double) * 2 * P * nq : 0);
-        const int grid = grid_for(c, nsl, 8);
 #define LAUNCH_GENERIC(ND)                                                                                        \
         rc = set_smem(rho_generic_kernel<ND>, smem); if (rc) return rc;                                            \
         rho_generic_kernel<ND><<<grid, 256, smem, c->stream>>>(s.pos.as<double>(), c->d_q.as<double>(),           \
@@ -216,17 +220,17 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
         if (nd == 1) { LAUNCH_GENERIC(1); } else if (nd == 2) { LAUNCH_GENERIC(2); } else { LAUNCH_GENERIC(3); }
 #undef LAUNCH_GENERIC
     } else {
-        const size_t fixed = lattice_fixed;
-        choose_split(nq, s.N, 256, fixed, limit, &P, &chunk);
-        const size_t smem = fixed + (P > 1 ? sizeof(double) * 2 * P * nq : 0);
-        const int grid = grid_for(c, nsl, 8);
+        const int G = c->ngroups;
+        const int nk = nd == 3 ? 8 : (nd == 2 ? 4 : 2);
+        choose_split(G, s.N, 256, lattice_fixed, sizeof(double) * nk, 110 * 1024, &P, &chunk);
+        const size_t smem = lattice_fixed + sizeof(double) * nk * P * G;
         const int3 nmax = make_int3(c->nmax[0], c->nmax[1], c->nmax[2]);
         const double twopi = 2.0 * M_PI;
         const double3 kph = make_double3(twopi / c->side[0], nd > 1 ? twopi / c->side[1] : 0.0, nd > 2 ? twopi / c->side[2] : 0.0);
 #define LAUNCH_LATTICE(ND)                                                                                        \
         rc = set_smem(rho_lattice_kernel<ND>, smem); if (rc) return rc;                                            \
-        rho_lattice_kernel<ND><<<grid, 256, smem, c->stream>>>(s.pos.as<double>(), c->d_qn.as<int>(),             \
-                                                               c->d_rho.as<double>(), nsl, s.N, s.Npad, nq, P, chunk, nmax, kph)
+        rho_lattice_kernel<ND><<<grid, 256, smem, c->stream>>>(s.pos.as<double>(), c->d_gkey.as<int>(), c->d_gout.as<int>(), \
+                                                               c->d_rho.as<double>(), nsl, s.N, s.Npad, nq, G, P, chunk, nmax, kph)
         if (nd == 1) { LAUNCH_LATTICE(1); } else if (nd == 2) { LAUNCH_LATTICE(2); } else { LAUNCH_LATTICE(3); }
 #undef LAUNCH_LATTICE
     }
@@ -236,11 +240,18 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
 
 int launch_corr(pimcb_ctx* c, const Slot& s) {
     KTimer kt(c, K_CORR);
-    const size_t smem = sizeof(double) * 4 * s.M;
+    const int nblk = (s.M / 2 + 1 + 7) / 8;                       // tau blocks of 8 per (config, q) pair
+    const int lpq = nblk <= 8 ? 8 : (nblk <= 16 ? 16 : 32);       // lanes sharing one pair
+    const int ppc = (32 / lpq) * 4;                               // pairs per 128-thread CTA
+    const int len = 2 * s.M + 16;
+    const int plen = len + 2 * (len >> 3) + 2;
+    const size_t smem = sizeof(double) * 2 * static_cast<size_t>(plen) * ppc;
+    if (smem > 200 * 1024) return fail(PIMCB_EINVAL, "M = %d too large for the correlation kernel's shared-memory staging", s.M);
     int rc = set_smem(isf_corr_kernel, smem);
     if (rc) return rc;
-    isf_corr_kernel<<<s.B * c->nq, 128, smem, c->stream>>>(c->d_rho.as<double>(), c->d_cfg.as<double>(), s.M, c->nq,
-                                                           1.0 / s.N, c->d_comm.as<unsigned char>());
+    const int npairs = s.B * c->nq;
+    isf_corr_kernel<<<(npairs + ppc - 1) / ppc, 128, smem, c->stream>>>(c->d_rho.as<double>(), c->d_cfg.as<double>(), s.M, c->nq,
+                                                                          npairs, lpq, 1.0 / s.N, c->d_comm.as<unsigned char>());
     CU(cudaGetLastError());
     return 0;
 }
@@ -429,7 +440,7 @@ int pimcb_destroy(pimcb_ctx* c) {
     }
     for (auto& p : c->pin) { p.release(); if (p.done) cudaEventDestroy(p.done); }
     c->h_out.release();
-    for (DevBuf* b : {&c->d_q, &c->d_comm, &c->d_qn, &c->d_qidx, &c->d_aos, &c->d_rho, &c->d_cfg, &c->d_bins, &c->d_partial,
+    for (DevBuf* b : {&c->d_q, &c->d_comm, &c->d_qn, &c->d_qidx, &c->d_gkey, &c->d_gout, &c->d_aos, &c->d_rho, &c->d_cfg, &c->d_bins, &c->d_partial,
                       &c->d_V, &c->d_dV, &c->d_vint, &c->d_f2, &c->d_hist, &c->d_scratch})
         b->release();
     for (int k = 0; k < kKernels; ++k) { cudaEventDestroy(c->ev0[k]); cudaEventDestroy(c->ev1[k]); }
@@ -498,6 +509,39 @@ int pimcb_set_qvecs(pimcb_ctx* c, const double* q, int nq) {
             for (int d = 0; d < nd; ++d) c->nmax[d] = std::max(c->nmax[d], std::abs(c->qn[static_cast<size_t>(k) * nd + d]));
     c->nsel = static_cast<int>(sel.size());
     int rc;
+    // sign-symmetry groups for the lattice path: key = (|n_0|,..,|n_{nd-1}|), member slot = sign pattern
+    c->ngroups = 0;
+    if (c->ncomm == nq) {
+        const int npat = 1 << nd;
+        std::vector<int> gkey, gout;
+        for (int k = 0; k < nq; ++k) {
+            int key[3] = {0, 0, 0}, pat = 0;
+            for (int d = 0; d < nd; ++d) {
+                const int n = c->qn[static_cast<size_t>(k) * nd + d];
+                key[d] = std::abs(n);
+                if (n < 0) pat |= 1 << d;
+            }
+            int g = -1;
+            const int ng = static_cast<int>(gkey.size()) / nd;
+            for (int j = 0; j < ng && g < 0; ++j) {
+                bool same = true;
+                for (int d = 0; d < nd; ++d) same = same && gkey[static_cast<size_t>(j) * nd + d] == key[d];
+                if (same && gout[static_cast<size_t>(j) * npat + pat] < 0) g = j;   // a repeated q opens a new group
+            }
+            if (g < 0) {
+                g = ng;
+                for (int d = 0; d < nd; ++d) gkey.push_back(key[d]);
+                gout.insert(gout.end(), npat, -1);
+            }
+            gout[static_cast<size_t>(g) * npat + pat] = k;
+        }
+        c->ngroups = static_cast<int>(gkey.size()) / nd;
+        if ((rc = c->d_gkey.ensure(sizeof(int) * gkey.size()))) return rc;
+        if ((rc = c->d_gout.ensure(sizeof(int) * gout.size()))) return rc;
+        CU(cudaMemcpyAsync(c->d_gkey.p, gkey.data(), sizeof(int) * gkey.size(), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->d_gout.p, gout.data(), sizeof(int) * gout.size(), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));   // gkey/gout are locals
+    }
     if ((rc = c->d_q.ensure(sizeof(double) * qsoa.size()))) return rc;
     if ((rc = c->d_comm.ensure(nq))) return rc;
     if ((rc = c->d_qn.ensure(sizeof(int) * c->qn.size()))) return rc;
