@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--unique", type=int, default=16, help="distinct synthetic configurations generated per slot")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--peak-seconds", type=float, default=0.5, help="duration of the in-run FP64 DFMA peak measurement")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU work budget (core-seconds) of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -233,7 +234,7 @@ def run_ours(args, shape, q):
     footprint_mb = use_slots * B * shape.M * 16 * ((shape.N + 15) // 16) * shape.ndim * 8 / 1e6
 
     ext = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
-    peak_tflops = ctx.fp64_peak_tflops(0.5)
+    peak_tflops = ctx.fp64_peak_tflops(args.peak_seconds)
 
     def device_step(k):
         ctx.select_slot(k % use_slots)

@@ -29,27 +29,48 @@ struct BoxDev {
 // classic minimax kernels on [-pi/4, pi/4] (< 1 ulp each).  21 FP64 instructions, no slow path,
 // no local memory.  The host refuses q-sets whose max |q.r| leaves the validity range.
 // ---------------------------------------------------------------------------------------------
+// Coefficients live in the constant bank so that every DFMA takes them as a c[bank][offset] operand; written as
+// literals ptxas re-materialises all of them into uniform registers (30 UMOVs) on every loop iteration.
+__constant__ double kSC[20] = {
+    0.63661977236758134308,        // [0]  2/pi
+    6755399441055744.0,            // [1]  1.5 * 2^52: rint() by add/sub
+    -1.5707963267948965580e+00,    // [2]  -pi/2 split in three doubles
+    -6.1232339957367660359e-17,    // [3]
+    1.4973849048591698330e-33,     // [4]
+    1.58969099521155010221e-10,    // [5]  sin: S6..S1
+    -2.50507602534068634195e-08,   // [6]
+    2.75573137070700676789e-06,    // [7]
+    -1.98412698298579493134e-04,   // [8]
+    8.33333333332248946124e-03,    // [9]
+    -1.66666666666666324348e-01,   // [10]
+    -1.13596475577881948265e-11,   // [11] cos: C6..C1
+    2.08757232129817482790e-09,    // [12]
+    -2.75573143513906633035e-07,   // [13]
+    2.48015872894767294178e-05,    // [14]
+    -1.38888888888741095749e-03,   // [15]
+    4.16666666666666019037e-02,    // [16]
+    -0.5, 1.0, 0.0};
+
 __device__ __forceinline__ void sincos_fast(double x, double& s, double& c) {
-    const double kMagic = 6755399441055744.0;            // 1.5 * 2^52: rint() by add/sub
-    const double t = fma(x, 0.63661977236758134308, kMagic);
+    const double t = fma(x, kSC[0], kSC[1]);
     const int n = __double2loint(t);                     // quadrant = low bits of rint(x*2/pi)
-    const double kd = t - kMagic;
-    double r = fma(kd, -1.5707963267948965580e+00, x);   // pi/2 split in three doubles
-    r = fma(kd, -6.1232339957367660359e-17, r);
-    r = fma(kd, 1.4973849048591698330e-33, r);
+    const double kd = t - kSC[1];
+    double r = fma(kd, kSC[2], x);
+    r = fma(kd, kSC[3], r);
+    r = fma(kd, kSC[4], r);
     const double z = r * r;
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    ps = fma(z, ps, 2.75573137070700676789e-06);
-    pc = fma(z, pc, -2.75573143513906633035e-07);
-    ps = fma(z, ps, -1.98412698298579493134e-04);
-    pc = fma(z, pc, 2.48015872894767294178e-05);
-    ps = fma(z, ps, 8.33333333332248946124e-03);
-    pc = fma(z, pc, -1.38888888888741095749e-03);
-    ps = fma(z, ps, -1.66666666666666324348e-01);
-    pc = fma(z, pc, 4.16666666666666019037e-02);
+    double ps = fma(z, kSC[5], kSC[6]);
+    double pc = fma(z, kSC[11], kSC[12]);
+    ps = fma(z, ps, kSC[7]);
+    pc = fma(z, pc, kSC[13]);
+    ps = fma(z, ps, kSC[8]);
+    pc = fma(z, pc, kSC[14]);
+    ps = fma(z, ps, kSC[9]);
+    pc = fma(z, pc, kSC[15]);
+    ps = fma(z, ps, kSC[10]);
+    pc = fma(z, pc, kSC[16]);
     const double sr = fma(r * z, ps, r);                                   // sin(r)
-    const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));                   // cos(r)
+    const double cr = fma(z * z, pc, fma(z, kSC[17], kSC[18]));            // cos(r)
     double sv = (n & 1) ? cr : sr;
     double cv = (n & 1) ? sr : cr;
     // sign: sin negative in quadrants 2,3; cos negative in quadrants 1,2
@@ -92,7 +113,7 @@ __global__ void __launch_bounds__(256) rho_generic_kernel(const double* __restri
             const int i0 = p * chunk;
             const int i1 = min(N, i0 + chunk);
             double ac = 0.0, as = 0.0;
-#pragma unroll 2
+#pragma unroll 4
             for (int i = i0; i < i1; ++i) {
                 double ph = qv[0] * xs[i];
 #pragma unroll
@@ -156,7 +177,7 @@ __global__ void __launch_bounds__(256) rho_lattice_kernel(const double* __restri
     const int stride = N + 1;                                  // in double2 units
     double2* tab = reinterpret_cast<double2*>(sm);             // [rows][stride]
     double* xs = sm + 2 * static_cast<size_t>(rows) * stride;  // [ND][Npad] raw coordinates
-    double* part = xs + ND * Npad;                             // [P][G][NK]
+    double* part = xs + ND * Npad;                             // [NK][P*G]  (k-major: conflict-free stores and loads)
     const int items = G * P;
     for (int sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
         load_slice(xs, pos + static_cast<size_t>(sl) * ND * Npad, ND * Npad);
@@ -226,9 +247,8 @@ __global__ void __launch_bounds__(256) rho_lattice_kernel(const double* __restri
                     K[7] = fma(pmi, z.x, K[7]);
                 }
             }
-            double* dst = part + static_cast<size_t>(item) * NK;
 #pragma unroll
-            for (int k = 0; k < NK; ++k) dst[k] = K[k];
+            for (int k = 0; k < NK; ++k) part[k * items + item] = K[k];
         }
         __syncthreads();
         // phase 3: fold the chunks (fixed order) and unfold the sign patterns into rho
@@ -242,10 +262,10 @@ __global__ void __launch_bounds__(256) rho_lattice_kernel(const double* __restri
             double k0 = 0.0, k1 = 0.0, k2 = 0.0, k3 = 0.0;
             const int base = ND == 3 ? 4 * sb : 0;
             for (int p = 0; p < P; ++p) {
-                const double* src = part + (static_cast<size_t>(p) * G + g) * NK + base;
+                const double* src = part + base * items + p * G + g;
                 k0 += src[0];
-                k1 += src[1];
-                if (ND > 1) { k2 += src[2]; k3 += src[3]; }
+                k1 += src[items];
+                if (ND > 1) { k2 += src[2 * items]; k3 += src[3 * items]; }
             }
             double re, im;
             if (ND == 1) { re = k0; im = k1; }
