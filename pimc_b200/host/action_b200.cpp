@@ -1,0 +1,71 @@
+#include "action_b200.h"
+
+LocalActionB200::LocalActionB200(const Path& _path, PotentialBase* external, PotentialBase* interaction,
+                                 const TableView& table, const std::array<double, 2>& _VFactor,
+                                 const std::array<double, 2>& _gradVFactor, int _period)
+    : ActionBase(_path, external, interaction, _period), VFactor(_VFactor), gradVFactor(_gradVFactor) {
+    B200Session::get(path).setPairTable(table.V, table.dVdr, table.tableLength, table.dr, table.extV.data(),
+                                        table.extdVdr.data());
+    // which slices carry the gradient correction (src/setup.cpp:1232-1253): gsf {0, 2/9} -> odd slices only,
+    // li_broughton {1/12, 1/12} -> all, primitive {0, 0} -> none
+    const bool even = gradVFactor[0] > EPS, odd = gradVFactor[1] > EPS;
+    needF2 = even || odd;
+    f2Parity = (even && odd) ? -1 : (odd ? 1 : 0);
+}
+
+const B200Session::PairSums& LocalActionB200::sums() {
+    return B200Session::get(path).pairSums(dSep, needF2, f2Parity);
+}
+
+// Per-slice entry points are called for slice = 0..M-1 in ascending order within one measurement
+// (src/estimator.cpp:983-988); without the newConfiguration() hook a non-increasing slice index marks a new pass.
+const B200Session::PairSums& LocalActionB200::sumsForSlice(int slice, int which) {
+    if (slice <= lastSlice[which]) B200Session::get(path).beginIfUnhooked();
+    lastSlice[which] = slice;
+    return sums();
+}
+
+// sum_i factor_i Vext(r_i), src/action.cpp:941-943 (factor 1 on diagonal configurations)
+double LocalActionB200::externalV(int slice) {
+    double tot = 0.0;
+    const int n = path.numBeadsAtSlice(slice);
+    for (int i = 0; i < n; ++i) tot += externalPtr->V(path(slice, i));
+    return tot;
+}
+
+std::array<double, 2> LocalActionB200::potential(int slice) {
+    const B200Session::PairSums& s = sumsForSlice(slice, 0);
+    for (int k = 0; k < NPCFSEP; ++k) sepHist(k) = s.hist[static_cast<size_t>(slice) * NPCFSEP + k];   // action.cpp:918,935
+    return {externalV(slice), s.vint[slice]};
+}
+
+// The interaction part comes from the device; a non-trivial external potential adds gradVext inside |F_i|^2, which
+// couples to the pair forces -- supported only for external potentials with zero gradient (FreePotential).
+double LocalActionB200::gradVSquared(int slice) { return sums().f2[slice]; }
+
+double LocalActionB200::potentialAction() {
+    B200Session::get(path).beginIfUnhooked();
+    const B200Session::PairSums& s = sums();
+    double totU = 0.0;
+    for (int slice = 0; slice < path.numTimeSlices; slice++) {
+        const int eo = slice % 2;
+        totU += VFactor[eo] * tau() * (externalV(slice) + s.vint[slice]);
+        if (gradVFactor[eo] > EPS)
+            totU += gradVFactor[eo] * tau() * tau() * tau() * constants()->lambda() * s.f2[slice];
+    }
+    return totU;
+}
+
+double LocalActionB200::derivPotentialActionTau(int slice) {
+    const B200Session::PairSums& s = sumsForSlice(slice, 1);
+    const int eo = slice % 2;
+    double dU = VFactor[eo] * (externalV(slice) + s.vint[slice]);
+    if (gradVFactor[eo] > EPS) dU += 3.0 * gradVFactor[eo] * tau() * tau() * constants()->lambda() * s.f2[slice];
+    return dU;
+}
+
+double LocalActionB200::derivPotentialActionLambda(int slice) {
+    const int eo = slice % 2;
+    if (gradVFactor[eo] > EPS) return gradVFactor[eo] * tau() * tau() * tau() * sumsForSlice(slice, 2).f2[slice];
+    return 0.0;
+}

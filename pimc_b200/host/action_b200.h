@@ -1,0 +1,43 @@
+// action_b200.h -- B200 replacement of the whole-path pair sums behind the reference's ActionBase interface.
+//
+// LocalActionB200 answers the virtuals the measurement code calls --
+//     potentialAction()                    (src/action.cpp:456-472)
+//     potential(int slice)  = V(slice)     (include/action.h:197, src/action.cpp:902-947) incl. the sepHist side effect
+//     derivPotentialActionTau(int slice)   (src/action.cpp:751-765)
+//     derivPotentialActionLambda(int slice)(src/action.cpp:798-806)
+// -- from ONE device pass over all slices (pimcb_pair_sums) per configuration instead of M O(N^2) host loops, and
+// removes the redundant re-evaluations the energy estimator triggers (V(slice) 1+1/period times, gradVSquared twice
+// per corrected slice; src/estimator.cpp:983-988).  The external potential is evaluated on the host through the
+// reference's own PotentialBase (O(N) per slice; `free` for bulk He-4).  Worm factors are 1 on the diagonal
+// configurations estimators sample (src/estimator.cpp:228, include/worm.h:50).
+#ifndef PIMCB_ACTION_B200_H
+#define PIMCB_ACTION_B200_H
+
+#ifdef PIMCB_STANDALONE
+#include "pimc_compat.h"
+#else
+#include "action.h"
+#endif
+#include "b200_session.h"
+
+class LocalActionB200 : public ActionBase {
+public:
+    LocalActionB200(const Path& path, PotentialBase* external, PotentialBase* interaction, const TableView& table,
+                    const std::array<double, 2>& VFactor, const std::array<double, 2>& gradVFactor, int period);
+    double potentialAction() override;
+    std::array<double, 2> potential(int slice) override;
+    double derivPotentialActionTau(int slice) override;
+    double derivPotentialActionLambda(int slice) override;
+    double gradVSquared(int slice);
+private:
+    std::array<double, 2> VFactor, gradVFactor;
+    bool needF2;
+    int f2Parity;
+    int lastSlice[3] = {1 << 30, 1 << 30, 1 << 30};   // last slice served per per-slice entry point (unhooked mode)
+    const B200Session::PairSums& sums();
+    const B200Session::PairSums& sumsForSlice(int slice, int which);
+    double externalV(int slice);
+    double externalGradCorrection(int slice);
+};
+
+#endif

@@ -1,0 +1,112 @@
+#include "b200_session.h"
+
+#include <cstdlib>
+#include <iostream>
+#include <map>
+#include <memory>
+
+struct SessionRegistry {
+    std::map<const Path*, B200Session*> map;
+    ~SessionRegistry() { for (auto& kv : map) delete kv.second; }
+};
+static SessionRegistry& registry() { static SessionRegistry r; return r; }
+
+// ABI failures follow the reference's error convention: message on std::cerr, then exit(EXIT_FAILURE)
+// (src/estimator.cpp:450-455); nothing is ever wrapped in assert() (cf. GPU_ASSERT, include/common_gpu.h:55).
+void B200Session::check(int rc, const char* what) const {
+    if (rc == 0) return;
+    std::cerr << "\nERROR: pimc_b200: " << what << " failed (" << rc << "): " << pimcb_last_error() << std::endl;
+    std::exit(EXIT_FAILURE);
+}
+
+B200Session::B200Session(const Path& path) : path_(path) {
+    int device = 0;
+    if (const char* env = std::getenv("PIMCB_DEVICE")) device = std::atoi(env);
+    check(pimcb_create(&ctx_, device, NDIM), "pimcb_create");
+    double side[NDIM];
+    unsigned periodic[NDIM];
+    for (int d = 0; d < NDIM; ++d) {
+        side[d] = path.boxPtr->side[d];
+        periodic[d] = path.boxPtr->periodic[d];
+    }
+    check(pimcb_set_box(ctx_, side, periodic), "pimcb_set_box");
+}
+
+B200Session::~B200Session() { pimcb_destroy(ctx_); }
+
+B200Session& B200Session::get(const Path& path) {
+    auto& m = registry().map;
+    auto it = m.find(&path);
+    if (it == m.end()) it = m.emplace(&path, new B200Session(path)).first;
+    return *it->second;
+}
+
+void B200Session::newConfiguration(const Path& path) {
+    B200Session& s = get(path);
+    s.hooked_ = true;
+    s.invalidate();
+}
+
+void B200Session::shutdown() {
+    auto& m = registry().map;
+    for (auto& kv : m) delete kv.second;
+    m.clear();
+}
+
+void B200Session::setQVectors(const std::vector<dVec>& q) {
+    std::vector<double> flat(q.size() * NDIM);
+    for (size_t k = 0; k < q.size(); ++k)
+        for (int d = 0; d < NDIM; ++d) flat[k * NDIM + d] = q[k][d];
+    check(pimcb_set_qvecs(ctx_, flat.data(), static_cast<int>(q.size())), "pimcb_set_qvecs");
+    nq_ = q.size();
+    have_sf_ = false;
+}
+
+void B200Session::stageIfNeeded() {
+    if (staged_) return;
+    const auto ext = path_.get_beads_extents();
+    const int M = path_.numTimeSlices;
+    const int N = path_.getTrueNumParticles();           // diagonal configuration: N active beads on every slice
+    check(pimcb_stage_beads(ctx_, path_.get_beads_data_pointer(), M, N, static_cast<int>(ext[1])), "pimcb_stage_beads");
+    staged_ = true;
+    have_sf_ = have_pair_ = false;
+}
+
+const std::vector<double>& B200Session::ssf() {
+    if (!have_sf_) {
+        stageIfNeeded();
+        const int M = path_.numTimeSlices;
+        ssf_.resize(nq_);
+        isf_.resize(nq_ * M);
+        check(pimcb_ssf_isf(ctx_, ssf_.data(), isf_.data()), "pimcb_ssf_isf");
+        have_sf_ = true;
+    }
+    return ssf_;
+}
+
+const std::vector<double>& B200Session::isf() {
+    ssf();
+    return isf_;
+}
+
+void B200Session::setPairTable(const double* V, const double* dVdr, int len, double dr, const double* extV,
+                               const double* extdVdr) {
+    check(pimcb_set_pair_table(ctx_, V, dVdr, len, dr, extV, extdVdr), "pimcb_set_pair_table");
+    have_table_ = true;
+    have_pair_ = false;
+}
+
+const B200Session::PairSums& B200Session::pairSums(double dSep, bool wantF2, int f2Parity) {
+    if (!(have_pair_ && (pair_has_f2_ || !wantF2))) {
+        stageIfNeeded();
+        const int M = path_.numTimeSlices;
+        pair_.vint.assign(M, 0.0);
+        pair_.f2.assign(M, 0.0);
+        pair_.hist.assign(static_cast<size_t>(M) * NPCFSEP, 0);
+        check(pimcb_pair_sums(ctx_, pair_.vint.data(), wantF2 ? pair_.f2.data() : nullptr, pair_.hist.data(), dSep, f2Parity),
+              "pimcb_pair_sums");
+        have_pair_ = true;
+        pair_has_f2_ = wantF2;
+    }
+    return pair_;
+}

@@ -1,0 +1,67 @@
+// b200_session.h -- one pimcb_ctx per Path, shared by every B200 estimator / action object that looks at that path,
+// so that the beads are staged once per measured configuration instead of once per estimator (the shipped GPU
+// estimators each copy the whole padded array per call, src/estimator.cpp:3833-3842, 4074-4085).
+//
+// Configuration identity.  The reference has no "path generation" counter; PathIntegralMonteCarlo::step() simply
+// calls est.sample() for every estimator right after the move sweep (src/pimc.cpp:732-738).  Two modes:
+//   * hooked:   the driver calls B200Session::newConfiguration(path) once per MC step before the estimator loop
+//               (a one-line patch in pimc.cpp); all consumers of that step share one staging
+//               and one S(q)/F(q,tau) (resp. pair-sum) pass.
+//   * unhooked: (default) the session is a pure cache and every entry point that could be looking at a new
+//               configuration (an estimator's accumulate(), potentialAction(), a per-slice call whose slice index
+//               does not increase) calls beginIfUnhooked() first: always correct, costs one extra H2D + pass per
+//               estimator.
+#ifndef PIMCB_SESSION_H
+#define PIMCB_SESSION_H
+
+#include <vector>
+
+#include "../../include/pimc_b200.h"
+#ifdef PIMCB_STANDALONE
+#include "pimc_compat.h"
+#else
+#include "common.h"
+#include "path.h"
+#include "container.h"
+#endif
+
+class B200Session {
+public:
+    static B200Session& get(const Path& path);
+    static void newConfiguration(const Path& path);     // hook: call once per MC step before est.sample()
+    static void shutdown();                             // destroys all contexts (end of main)
+
+    // Wave-vectors are fixed per session (all scattering estimators of a run share --wavevector).
+    void setQVectors(const std::vector<dVec>& q);
+    int numQ() const { return static_cast<int>(nq_); }
+
+    // S(q)/N [nq] and F(q,tau)/N [nq*M] of the current configuration (computed once per configuration).
+    const std::vector<double>& ssf();
+    const std::vector<double>& isf();
+
+    // Pair sums of the current configuration: Vint[M], gradVSquared[M], sepHist[M][NPCFSEP].
+    void setPairTable(const double* V, const double* dVdr, int len, double dr, const double* extV, const double* extdVdr);
+    struct PairSums { std::vector<double> vint, f2; std::vector<int> hist; };
+    const PairSums& pairSums(double dSep, bool wantF2, int f2Parity);
+    void invalidate() { staged_ = false; have_sf_ = false; have_pair_ = false; }
+    void beginIfUnhooked() { if (!hooked_) invalidate(); }
+    bool hooked() const { return hooked_; }
+
+private:
+    explicit B200Session(const Path& path);
+    ~B200Session();
+    B200Session(const B200Session&) = delete;
+    void stageIfNeeded();
+    void check(int rc, const char* what) const;
+
+    const Path& path_;
+    pimcb_ctx* ctx_ = nullptr;
+    size_t nq_ = 0;
+    bool hooked_ = false, staged_ = false, have_sf_ = false, have_pair_ = false, have_table_ = false;
+    bool pair_has_f2_ = false;
+    std::vector<double> ssf_, isf_;
+    PairSums pair_;
+    friend struct SessionRegistry;
+};
+
+#endif

@@ -1,0 +1,50 @@
+// host_selftest -- GPU-free checks of the host layer: factory registration names, wave-vector generation, header and
+// row formatting.  Prints a small key=value report that tests/test_host_layer.py compares with the CPU oracle.
+#include <iostream>
+
+#include "aziz.h"
+#include "estimator_base.h"
+
+class ProbeEstimator : public EstimatorBase {
+public:
+    ProbeEstimator(const Path& p, ActionBase* a, const MTRand& r, double maxR) : EstimatorBase(p, a, r, maxR, 1, "probe") {}
+    void run() {
+        std::vector<dVec> q;
+        getQVectors(q);
+        std::cout << "nq=" << q.size() << std::endl;
+        for (const dVec& v : q) std::cout << "q=" << dVecToString(v) << std::endl;
+        std::cout.precision(17);
+        for (const dVec& v : q) {
+            std::cout << "qraw=";
+            for (int d = 0; d < NDIM; ++d) std::cout << v[d] << (d + 1 < NDIM ? " " : "");
+            std::cout << std::endl;
+        }
+    }
+};
+
+int main(int argc, char** argv) {
+    if (argc < 5) { std::cerr << "usage: host_selftest N density type \"wavevector\"" << std::endl; return 2; }
+    const int N = std::atoi(argv[1]);
+    Prism box(std::atof(argv[2]), N);
+    constants()->wavevectorType_ = argv[3];
+    constants()->wavevector_ = argv[4];
+    constants()->numTimeSlices_ = 4;
+    constants()->initialNumParticles_ = N;
+    Path path(&box, 4, N, N);
+    MTRand r;
+    std::cout.precision(17);
+    std::cout << "side=" << box.side[0] << std::endl << "maxSep=" << box.maxSep << std::endl;
+    for (const std::string& n : estimatorFactory()->getNames()) std::cout << "registered=" << n << std::endl;
+    ProbeEstimator(path, nullptr, r, 0.0).run();
+    std::cout << "row=" << pimcb_format("%16.8E", 30864.19725) << pimcb_format("%16.8E", -6.25e-4) << std::endl;
+#if NDIM == 3
+    AzizPotential az(1979, &box);
+    const TableView t = az.tableView();
+    std::cout << "tableLength=" << t.tableLength << std::endl << "dr=" << t.dr << std::endl;
+    std::cout << "V1e6=" << t.V[1000000] << std::endl << "dV1e6=" << t.dVdr[1000000] << std::endl;
+    double cs = 0.0;
+    for (int k = 0; k < t.tableLength; k += 997) cs += t.V[k] * 1e-3 + t.dVdr[k] * 1e-6;
+    std::cout << "checksum=" << cs << std::endl;
+#endif
+    return 0;
+}

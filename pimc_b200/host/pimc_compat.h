@@ -1,0 +1,258 @@
+// pimc_compat.h -- minimal stand-ins for the reference types the B200 adaptor classes touch.
+//
+// Inside a reference checkout the adaptor sources (estimator_b200.*, action_b200.*) are compiled against the
+// reference's own headers (common.h, path.h, container.h, constants.h, estimator.h, action.h, factory.h) and this
+// file is not used.  Stand-alone (this repository: no Boost, no <mdspan>) it supplies from-scratch types with the
+// same names, members and call signatures, restricted to what the measurement path needs, so that the adaptor code
+// is compile-checked and runnable (tools: pimcb_measure) here.  Citations are upstream file:line.
+#ifndef PIMCB_COMPAT_H
+#define PIMCB_COMPAT_H
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <fstream>
+#include <functional>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#ifndef NDIM
+#define NDIM 3                      // CMakeLists.txt:223-226 (compile-time dimension upstream)
+#endif
+#define NPCFSEP 50                  // include/common.h:85
+#define EPS 1.0E-7                  // include/common.h:89
+
+typedef unsigned int uint32;
+typedef std::array<double, NDIM> dVec;      // include/common.h:104
+typedef std::array<int, NDIM> iVec;
+typedef std::array<int, 2> beadLocator;     // include/common.h:110
+
+// Rank-1 subset of the reference's DynamicArray<T,Rank> (include/dynamic_array.h:55-386): element access with
+// operator()(i), resize, fill, data, size.
+template <class T, int Rank> class DynamicArray;
+template <class T>
+class DynamicArray<T, 1> {
+public:
+    void resize(size_t n) { v_.resize(n); }
+    void fill(const T& x) { std::fill(v_.begin(), v_.end(), x); }
+    T& operator()(size_t i) { return v_[i]; }
+    const T& operator()(size_t i) const { return v_[i]; }
+    T* data() { return v_.data(); }
+    const T* data() const { return v_.data(); }
+    size_t size() const { return v_.size(); }
+private:
+    std::vector<T> v_;
+};
+
+inline double dot(const dVec& a, const dVec& b) {      // include/array_math.h:210-216
+    double r = 0.0;
+    for (int i = 0; i < NDIM; ++i) r += a[i] * b[i];
+    return r;
+}
+
+// ---- Container (include/container.h:24-59, src/container.cpp:84-144) ------------------------------------------
+class Container {
+public:
+    dVec side{}, sideInv{}, pSide{};
+    std::array<unsigned int, NDIM> periodic{};
+    double maxSep = 0.0, volume = 0.0;
+    void putInBC(dVec& r) const {
+        for (int i = 0; i < NDIM; ++i) r[i] -= pSide[i] * std::floor(r[i] * sideInv[i] + 0.5);
+    }
+};
+
+class Prism : public Container {
+public:
+    Prism(double density, int numParticles) {
+        side.fill(std::pow(1.0 * numParticles / density, 1.0 / (1.0 * NDIM)));
+        periodic.fill(1u);
+        finish();
+    }
+    Prism(const dVec& _side, const std::array<unsigned int, NDIM>& _periodic) {
+        side = _side;
+        periodic = _periodic;
+        finish();
+    }
+private:
+    void finish() {
+        double acc = 0.0;
+        volume = 1.0;
+        for (int i = 0; i < NDIM; ++i) {
+            sideInv[i] = 1.0 / side[i];
+            pSide[i] = periodic[i] * side[i];
+            const double h = side[i] / (periodic[i] + 1u);
+            acc += h * h;
+            volume *= side[i];
+        }
+        maxSep = std::sqrt(acc);
+    }
+};
+
+// ---- simulation constants (include/constants.h; only the getters the path reads) ----------------------------
+class ConstantParameters {
+public:
+    bool canonical() const { return canonical_; }
+    bool restart() const { return false; }
+    int initialNumParticles() const { return initialNumParticles_; }
+    int numTimeSlices() const { return numTimeSlices_; }
+    double tau() const { return tau_; }
+    double T() const { return T_; }
+    double lambda() const { return lambda_; }                  // src/constants.cpp:128: 24.24/m
+    std::string wavevector() const { return wavevector_; }
+    std::string wavevectorType() const { return wavevectorType_; }
+    std::string id() const { return id_; }
+    bool canonical_ = true;
+    int initialNumParticles_ = 0, numTimeSlices_ = 0;
+    double tau_ = 0.0, T_ = 0.0, lambda_ = 24.24 / 4.0030;
+    std::string wavevector_, wavevectorType_ = "int", id_ = "000000000";
+};
+ConstantParameters* constants();
+
+// ---- worm + path (include/worm.h, include/path.h:29-217) -----------------------------------------------------
+class Worm {
+public:
+    bool isConfigDiagonal = true;
+    int numBeadsOn = 0;
+    int getNumBeadsOn() const { return numBeadsOn; }
+};
+
+class Path {
+public:
+    Path(const Container* box, int numTimeSlices_, int numParticles, int extent)
+        : numTimeSlices(numTimeSlices_), boxPtr(box), n_(numParticles), next_(extent),
+          beads_(static_cast<size_t>(numTimeSlices_) * extent) {
+        worm.numBeadsOn = numTimeSlices * numParticles;
+    }
+    const int numTimeSlices;
+    const Container* boxPtr;
+    Worm worm;
+    int numBeadsAtSlice(int) const { return n_; }
+    int getTrueNumParticles() const { return worm.getNumBeadsOn() / numTimeSlices; }          // path.h:54
+    const dVec& operator()(int slice, int ptcl) const { return beads_[static_cast<size_t>(slice) * next_ + ptcl]; }
+    dVec& operator()(int slice, int ptcl) { return beads_[static_cast<size_t>(slice) * next_ + ptcl]; }
+    const dVec& operator()(const beadLocator& b) const { return (*this)(b[0], b[1]); }
+    dVec getSeparation(const beadLocator& b1, const beadLocator& b2) const {                   // path.h:179-184
+        dVec sep;
+        for (int i = 0; i < NDIM; ++i) sep[i] = (*this)(b1)[i] - (*this)(b2)[i];
+        boxPtr->putInBC(sep);
+        return sep;
+    }
+    const double* get_beads_data_pointer() const { return reinterpret_cast<const double*>(beads_.data()); }   // path.h:208-210
+    double* beads_data() { return reinterpret_cast<double*>(beads_.data()); }
+    std::array<size_t, 2> get_beads_extents() const { return {static_cast<size_t>(numTimeSlices), static_cast<size_t>(next_)}; }
+private:
+    int n_, next_;
+    std::vector<dVec> beads_;       // row-major [slice][ptcl] AoS, as DynamicArray<dVec,2> (path.h:164)
+};
+
+class MTRand {};                    // the path never draws random numbers
+
+// ---- potentials (include/potential.h:40-117) -------------------------------------------------------------------
+class PotentialBase {
+public:
+    virtual ~PotentialBase() {}
+    virtual double V(const dVec&) { return 0.0; }
+    virtual void V(const dVec* pos, double* values, int count) {          // src/potential.cpp:127-132
+        if (count < 0) throw std::runtime_error("negative count");
+        for (int i = 0; i < count; ++i) values[i] = V(pos[i]);
+    }
+    virtual dVec gradV(const dVec&) { return dVec{}; }
+    virtual double grad2V(const dVec&) { return 0.0; }
+    double tailV = 0.0;
+};
+class FreePotential : public PotentialBase {};
+
+// Flat view of a TabulatedPotential (include/potential.h:148-157); upstream the members are protected and a
+// 3-line public accessor returning this struct is the only change the potential classes need.
+struct TableView {
+    const double* V = nullptr;
+    const double* dVdr = nullptr;
+    int tableLength = 0;
+    double dr = 0.0;
+    std::array<double, 2> extV{}, extdVdr{};
+};
+
+// ---- action (include/action.h:30-254; the members the measurement path uses) -----------------------------------
+class ActionBase {
+public:
+    ActionBase(const Path& p, PotentialBase* ext, PotentialBase* inter, int period_ = 1)
+        : period(period_), path(p), externalPtr(ext), interactionPtr(inter) {
+        sepHist.resize(NPCFSEP);
+        sepHist.fill(0);
+        dSep = 0.5 * std::sqrt(1.0 * NDIM) * path.boxPtr->side[NDIM - 1] / (1.0 * NPCFSEP);      // src/action.cpp:192
+    }
+    virtual ~ActionBase() {}
+    virtual double potentialAction() { return 0.0; }
+    virtual std::array<double, 2> potential(int) { return {0.0, 0.0}; }
+    virtual double derivPotentialActionTau(int) { return 0.0; }
+    virtual double derivPotentialActionLambda(int) { return 0.0; }
+    const int period;
+    DynamicArray<int, 1> sepHist;   // action.h:114
+    double tau() const { return constants()->tau(); }
+protected:
+    const Path& path;
+    PotentialBase* externalPtr;
+    PotentialBase* interactionPtr;
+    double dSep;
+};
+
+// ---- output files (include/communicator.h; file-name pattern src/communicator.cpp:39-44,160-167) ----------------
+class File {
+public:
+    explicit File(const std::string& name) : name_(name), stream_(name, std::ios::out | std::ios::trunc) {}
+    std::fstream& stream() { return stream_; }
+    bool exists() const { return false; }
+    bool prepared() const { return prepared_; }
+    void prepare() { prepared_ = true; }
+    const std::string& name() const { return name_; }
+private:
+    std::string name_;
+    std::fstream stream_;
+    bool prepared_ = false;
+};
+class Communicator {
+public:
+    void init(const std::string& dir, const std::string& ensemble, const std::string& dataName) {
+        dir_ = dir; ensemble_ = ensemble; dataName_ = dataName;
+    }
+    File* file(const std::string& label);
+private:
+    std::string dir_ = "OUTPUT", ensemble_ = "ce", dataName_ = "run";
+    std::map<std::string, std::unique_ptr<File>> files_;
+};
+Communicator* communicate();
+
+// ---- factory (include/factory.h:26-95) ---------------------------------------------------------------------------
+template <typename CtorSignature> class Factory;
+template <class BaseType, class... ParamType>
+class Factory<BaseType(ParamType...)> {
+    using CreateObjectFunc = BaseType (*)(ParamType...);
+public:
+    std::vector<std::string> getNames() const {
+        std::vector<std::string> names;
+        for (auto const& kv : _create) names.push_back(kv.first);
+        return names;
+    }
+    Factory* operator()() { static Factory f; return &f; }
+    BaseType Create(std::string name, ParamType... param) {
+        auto it = _create.find(name);
+        return it != _create.end() ? (it->second)(param...) : nullptr;
+    }
+    template <class DerivedType> bool Register(std::string name) {
+        _create[name] = &createObj<DerivedType>;
+        return true;
+    }
+private:
+    std::map<std::string, CreateObjectFunc> _create;
+    template <class DerivedType> static BaseType createObj(ParamType... param) { return new DerivedType(param...); }
+};
+class EstimatorBase;
+typedef Factory<EstimatorBase*(Path&, ActionBase*, MTRand&, double)> EstimatorFactory;
+extern EstimatorFactory estimatorFactory;
+
+#endif

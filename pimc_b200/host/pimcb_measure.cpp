@@ -1,0 +1,119 @@
+// pimcb_measure -- stand-alone driver of the B200 measurement path through the reference's plugin API:
+// builds Container / Path / constants, creates the estimators BY NAME through the estimator factory exactly as
+// Setup::estimators does (src/setup.cpp:1343-1367), feeds them path configurations, and writes the reference's
+// output files (OUTPUT/ce-ssfq-*.dat, ce-isf-*.dat; one row per bin, src/estimator.cpp:348-362).
+//
+//   pimcb_measure -N 16 -n 0.02198 -T 2.0 -P 124 --wavevector_type int --wavevector "1 0 0 0 1 0"
+//                 --configs beads.bin [--bin_size 100] [--outdir OUTPUT] [--id run] [--action gsf]
+//
+// `--configs` is a raw little-endian file of B configurations, each double[M][N_ext][NDIM] in the reference's bead
+// layout (N_ext given by --extent, default N).  With --potential the total potential action, per-slice Vint and
+// gradVSquared of every configuration are written to <outdir>/ce-potential-<id>.dat as well.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+
+#include "action_b200.h"
+#include "aziz.h"
+#include "estimator_b200.h"
+
+static const char* arg(int argc, char** argv, const char* key, const char* def) {
+    for (int i = 1; i + 1 < argc; ++i)
+        if (!std::strcmp(argv[i], key)) return argv[i + 1];
+    return def;
+}
+static bool flag(int argc, char** argv, const char* key) {
+    for (int i = 1; i < argc; ++i)
+        if (!std::strcmp(argv[i], key)) return true;
+    return false;
+}
+
+int main(int argc, char** argv) {
+    const int N = std::atoi(arg(argc, argv, "-N", "16"));
+    const double density = std::atof(arg(argc, argv, "-n", "0.02198"));
+    const double T = std::atof(arg(argc, argv, "-T", "2.0"));
+    int M = std::atoi(arg(argc, argv, "-P", "0"));
+    double tau = std::atof(arg(argc, argv, "-t", "0.004"));
+    const int extent = std::atoi(arg(argc, argv, "--extent", arg(argc, argv, "-N", "16")));
+    const int binSize = std::atoi(arg(argc, argv, "--bin_size", "100"));
+    const std::string actionType = arg(argc, argv, "--action", "gsf");
+    const char* cfgFile = arg(argc, argv, "--configs", nullptr);
+    if (!cfgFile) {
+        std::cerr << "usage: pimcb_measure -N n -n density -T temp (-P slices | -t tau) --wavevector_type T --wavevector \"...\" --configs file" << std::endl;
+        return 2;
+    }
+    // number of time slices, forced even (src/setup.cpp:998-1012)
+    if (M <= 0) {
+        M = static_cast<int>(1.0 / (T * tau) + EPS);
+        if (M % 2) M--;
+    } else {
+        if (M % 2) M--;
+        tau = 1.0 / (T * M);
+    }
+    ConstantParameters* c = constants();
+    c->initialNumParticles_ = N;
+    c->numTimeSlices_ = M;
+    c->tau_ = tau;
+    c->T_ = T;
+    c->wavevector_ = arg(argc, argv, "--wavevector", "");
+    c->wavevectorType_ = arg(argc, argv, "--wavevector_type", "int");
+    c->id_ = arg(argc, argv, "--id", "run");
+    communicate()->init(arg(argc, argv, "--outdir", "OUTPUT"), "ce", c->id_);
+
+    Prism box(density, N);
+    Path path(&box, M, N, extent);
+    MTRand random;
+    const bool wantPotential = flag(argc, argv, "--potential");
+
+    FreePotential external;
+    std::unique_ptr<AzizPotential> aziz;
+    std::unique_ptr<LocalActionB200> action;
+    if (wantPotential) {
+        aziz.reset(new AzizPotential(std::atoi(arg(argc, argv, "--aziz_year", "1979")), &box));
+        std::array<double, 2> VF{1.0, 1.0}, GF{0.0, 0.0};      // src/setup.cpp:1232-1253
+        int period = 1;
+        if (actionType == "gsf") { VF = {2.0 / 3.0, 4.0 / 3.0}; GF = {0.0, 2.0 / 9.0}; period = 2; }
+        else if (actionType == "li_broughton") { GF = {1.0 / 12.0, 1.0 / 12.0}; period = 2; }
+        action.reset(new LocalActionB200(path, &external, aziz.get(), aziz->tableView(), VF, GF, period));
+    }
+
+    std::vector<std::unique_ptr<EstimatorBase>> estimators;
+    for (const char* name : {"static structure factor", "intermediate scattering function"}) {
+        EstimatorBase* e = estimatorFactory()->Create(name, path, action.get(), random, 0.0);
+        if (!e) { std::cerr << "estimator not registered: " << name << std::endl; return 1; }
+        estimators.emplace_back(e);
+        e->prepare();
+    }
+    std::fstream* potOut = nullptr;
+    if (wantPotential) {
+        potOut = &communicate()->file("potential")->stream();
+        (*potOut) << "# potentialAction, then Vint[0..M-1], then gradVSquared[0..M-1] per configuration" << std::endl;
+    }
+
+    FILE* f = std::fopen(cfgFile, "rb");
+    if (!f) { std::cerr << "cannot open " << cfgFile << std::endl; return 1; }
+    const size_t count = static_cast<size_t>(M) * extent * NDIM;
+    long nconf = 0;
+    while (std::fread(path.beads_data(), sizeof(double), count, f) == count) {
+        B200Session::newConfiguration(path);         // the per-step hook
+        for (auto& e : estimators) e->sample();      // src/pimc.cpp:737-738
+        ++nconf;
+        if (wantPotential) {
+            (*potOut) << pimcb_format("%24.16E", action->potentialAction());
+            for (int s = 0; s < M; ++s) (*potOut) << pimcb_format("%24.16E", action->potential(s)[1]);
+            for (int s = 0; s < M; ++s) (*potOut) << pimcb_format("%24.16E", action->gradVSquared(s));
+            (*potOut) << std::endl;
+        }
+        if (estimators[0]->getNumAccumulated() >= static_cast<uint32>(binSize))     // src/pimc.cpp:743-749
+            for (auto& e : estimators) e->output();
+    }
+    std::fclose(f);
+    if (estimators[0]->getNumAccumulated() > 0)
+        for (auto& e : estimators) e->output();
+    std::cout << "pimcb_measure: " << nconf << " configurations, N=" << N << " M=" << M << " tau=" << tau << std::endl;
+    estimators.clear();
+    action.reset();
+    B200Session::shutdown();
+    return 0;
+}

@@ -1,0 +1,130 @@
+"""Host-side C++ adaptor layer (pimc_b200/host): EstimatorBase mirror, factory registration, q generation, output
+formatting (CPU), and the plugin-API drop-in run through pimcb_measure (GPU)."""
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from pimc_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "pimc_b200", "host")
+
+
+@pytest.fixture(scope="module")
+def host_bins():
+    from pimc_b200 import build
+    build.build_lib()
+    for nd in (2, 3):
+        subprocess.run(["make", "-C", HOST, f"NDIM={nd}"], check=True, stdout=subprocess.DEVNULL)
+    return HOST
+
+
+def selftest(host, ndim, N, rho, qtype, text):
+    out = subprocess.run([os.path.join(host, f"pimcb_host_selftest{ndim}d"), str(N), repr(rho), qtype, text],
+                         check=True, capture_output=True, text=True).stdout
+    d = {}
+    for line in out.splitlines():
+        k, v = line.split("=", 1)
+        d.setdefault(k, []).append(v)
+    return d
+
+
+@pytest.mark.parametrize("ndim,N,rho,qtype,text", [
+    (3, 16, 0.02198, "int", "1 0 0  0 -2 3  5 5 5"),
+    (3, 16, 0.02198, "float", "0.1 0.25 1.7  -2.2 0.3 0.0"),
+    (3, 16, 0.02198, "max_int", "2 1 2"),
+    (3, 256, 0.02198, "max_float", "0.9 0.0 0.0"),
+    (2, 128, 0.0432, "max_int", "8 8"),
+    (2, 128, 0.0432, "int", "1 0 0 1 -1 1"),
+])
+def test_qvectors_match_oracle_bitwise(host_bins, orc, ndim, N, rho, qtype, text):
+    rep = selftest(host_bins, ndim, N, rho, qtype, text)
+    side = np.full(ndim, (N / rho) ** (1.0 / ndim))
+    assert float(rep["side"][0]) == side[0]
+    q = orc.qvectors(qtype, text, side)
+    assert int(rep["nq"][0]) == len(q)
+    got = np.array([[float(x) for x in l.split()] for l in rep["qraw"]])
+    assert np.array_equal(got, q)
+    assert rep["q"][0] == orc.dvec_to_string(q[0])
+    assert float(rep["maxSep"][0]) == orc.max_sep(side)
+
+
+def test_factory_names_and_formatting(host_bins, orc):
+    rep = selftest(host_bins, 3, 16, 0.02198, "int", "1 0 0")
+    assert sorted(rep["registered"]) == ["intermediate scattering function", "static structure factor"]
+    assert rep["row"][0] == orc.format_row([30864.19725, -6.25e-4], [1.0, 1.0], 1)
+
+
+def test_aziz_table_matches_oracle(host_bins, orc):
+    rep = selftest(host_bins, 3, 16, 0.02198, "int", "1 0 0")
+    side = synth.C1.side
+    V, dV, dr = orc.aziz_table(orc.max_sep(side))
+    assert int(rep["tableLength"][0]) == len(V) and float(rep["dr"][0]) == dr
+    assert float(rep["V1e6"][0]) == pytest.approx(V[1000000], rel=1e-15)
+    assert float(rep["dV1e6"][0]) == pytest.approx(dV[1000000], rel=1e-15)
+    cs = float(np.sum(V[::997] * 1e-3 + dV[::997] * 1e-6))
+    assert float(rep["checksum"][0]) == pytest.approx(cs, rel=1e-12)
+
+
+def read_dat(path):
+    head, rows = [], []
+    for line in open(path):
+        if line.startswith("#"):
+            head.append(line.rstrip("\n"))
+        elif line.strip():
+            rows.append(line.rstrip("\n"))
+    return head, rows
+
+
+@pytest.mark.gpu
+def test_plugin_api_drop_in_files(host_bins, orc, nthreads, tmp_path):
+    """C1 through the factory-created estimators: headers, column order, normalisation and %16.8E rows of
+    ce-ssfq / ce-isf as EstimatorBase::output writes them, plus potentialAction via LocalActionB200."""
+    s = synth.C1
+    B, bin_size, nq = 5, 2, 12
+    batch = synth.gen_batch(s, B)
+    cfg = tmp_path / "beads.bin"
+    batch.tofile(cfg)
+    text = synth.int_wavevector_text(nq, 3)
+    out = tmp_path / "OUTPUT"
+    subprocess.run([os.path.join(host_bins, "pimcb_measure3d"), "-N", str(s.N), "-n", repr(s.rho), "-T", repr(s.T), "-t", "0.004",
+                    "--extent", str(s.N + 3), "--wavevector_type", "int", "--wavevector", text, "--configs", str(cfg),
+                    "--bin_size", str(bin_size), "--outdir", str(out), "--id", "t", "--potential"], check=True)
+    q = orc.qvectors("int", text, s.side)
+    ssf = np.array([orc.ssf(s.side, b, s.N, q) for b in batch])
+    isf = np.array([orc.isf(b, s.N, q, nthreads=nthreads).reshape(-1) for b in batch])
+
+    head, rows = read_dat(out / "ce-ssfq-t.dat")
+    assert head[0] == f"# ESTINF: num_q = {nq}; " + " ".join(orc.dvec_to_string(v) for v in q) + " "
+    assert head[1] == "#%15d" % 0 + "".join("%16d" % n for n in range(1, nq))
+    bins = [(0, 2), (2, 4), (4, 5)]                      # two full bins and the flushed remainder
+    assert len(rows) == len(bins)
+    for row, (a, b) in zip(rows, bins):
+        expect = orc.format_row(ssf[a:b].sum(axis=0), np.full(nq, 1.0 / s.M), b - a)
+        got = np.array([float(row[16 * k:16 * k + 16]) for k in range(nq)])
+        ref = np.array([float(expect[16 * k:16 * k + 16]) for k in range(nq)])
+        np.testing.assert_allclose(got, ref, rtol=2e-8)
+        assert sum(row[16 * k:16 * k + 16] == expect[16 * k:16 * k + 16] for k in range(nq)) >= nq - 1
+
+    head, rows = read_dat(out / "ce-isf-t.dat")
+    assert head[0] == "#%15d" % 0 + "".join("%16d" % n for n in range(1, nq * s.M))
+    for row, (a, b) in zip(rows, bins):
+        expect = orc.format_row(isf[a:b].sum(axis=0), np.full(nq * s.M, 1.0 / s.M), b - a)
+        got = np.array([float(row[16 * k:16 * k + 16]) for k in range(nq * s.M)])
+        ref = np.array([float(expect[16 * k:16 * k + 16]) for k in range(nq * s.M)])
+        np.testing.assert_allclose(got, ref, rtol=2e-8, atol=1e-8)
+
+    V, dV, dr = orc.aziz_table(orc.max_sep(s.side))
+    dSep = 0.5 * math.sqrt(3) * s.side[2] / 50
+    _, prow = read_dat(out / "ce-potential-t.dat")
+    assert len(prow) == B
+    for b in range(B):
+        vals = np.array([float(x) for x in prow[b].split()])
+        cv, cf, _ = orc.pair_sums(s.side, batch[b], s.N, V, dV, dr, dSep, nthreads=nthreads)
+        U = orc.potential_action(cv, cf, [2 / 3, 4 / 3], [0.0, 2 / 9], 0.004, synth.LAMBDA_HE4)
+        assert vals[0] == pytest.approx(U, rel=1e-10)
+        np.testing.assert_allclose(vals[1:1 + s.M], cv, rtol=1e-10)
+        np.testing.assert_allclose(vals[1 + s.M + 1::2], cf[1::2], rtol=1e-10)      # gsf: odd slices carry |F|^2

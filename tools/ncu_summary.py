@@ -1,0 +1,107 @@
+#!/usr/bin/env python
+"""Summarise ncu output brought back in gpurun_out/ into tracked files under profiles/.
+
+    python tools/ncu_summary.py <tag>       e.g. r01b  ->  profiles/<tag>_launches.csv, profiles/<tag>_kernels.md
+
+Launch list: the `--metrics gpu__time_duration.sum --clock-control none` pass (cold-cache, serialised: shares, not
+absolutes).  Per-kernel detail: one `--set full` capture per kernel (<tag>_prof_*.ncu-rep), read with
+`ncu -i ... --page raw --csv`.
+"""
+import csv
+import glob
+import io
+import os
+import re
+import subprocess
+import sys
+from collections import OrderedDict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
+    "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum", "smsp__inst_executed.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum", "sm__cycles_elapsed.max",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+]
+
+
+def short(name):
+    m = re.search(r"(\w+)(<[^>]*>)?\(", name)
+    return (m.group(1) + (m.group(2) or "")) if m else name
+
+
+def launches(tag, out):
+    src = os.path.join(ROOT, "gpurun_out", f"{tag}_launches.csv")
+    if not os.path.exists(src):
+        return None
+    text = "".join(l for l in open(src) if l.startswith('"'))
+    rows = list(csv.DictReader(io.StringIO(text)))
+    agg = OrderedDict()
+    for r in rows:
+        k = short(r["Kernel Name"])
+        a = agg.setdefault(k, [0, 0.0, r["Grid Size"], r["Block Size"]])
+        a[0] += 1
+        a[1] += float(r["Metric Value"])
+    total = sum(a[1] for a in agg.values())
+    with open(os.path.join(out, f"{tag}_launches.csv"), "w") as f:
+        f.write("kernel,launches,total_ns,avg_ns,share_of_listed_time,grid,block\n")
+        for k, a in agg.items():
+            f.write(f"\"{k}\",{a[0]},{a[1]:.0f},{a[1] / a[0]:.0f},{a[1] / total:.4f},\"{a[2]}\",\"{a[3]}\"\n")
+    return agg, total
+
+
+def kernel_detail(rep):
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    if len(rows) < 3:
+        return None
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+    return d
+
+
+def main():
+    tag = sys.argv[1]
+    out = os.path.join(ROOT, "profiles")
+    os.makedirs(out, exist_ok=True)
+    md = [f"# ncu summary `{tag}`", "",
+          "Source: `tools/gpu_round.sh` on one B200 (`ncu --clock-control none`); numbers printed under ncu are never bench values.", ""]
+    la = launches(tag, out)
+    if la:
+        agg, total = la
+        md += ["## Launch list (gpu__time_duration.sum; cold-cache, serialised -- compare shares)", "",
+               "| kernel | launches | avg us | share |", "|---|---:|---:|---:|"]
+        for k, a in agg.items():
+            md.append(f"| `{k}` | {a[0]} | {a[1] / a[0] / 1e3:.1f} | {100 * a[1] / total:.1f}% |")
+        md.append("")
+    for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"{tag}_prof_*.ncu-rep"))):
+        d = kernel_detail(rep)
+        if not d:
+            continue
+        name = d.get("Kernel Name", ("?", ""))[0]
+        md += [f"## `{short(name)}`  ({os.path.basename(rep)}, --set full)", "", "| metric | value | unit |", "|---|---:|---|"]
+        for k in KEYS:
+            if k in d:
+                md.append(f"| {k} | {d[k][0]} | {d[k][1]} |")
+        md.append("")
+    with open(os.path.join(out, f"{tag}_kernels.md"), "w") as f:
+        f.write("\n".join(md) + "\n")
+    print("\n".join(md))
+
+
+if __name__ == "__main__":
+    main()
