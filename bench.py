@@ -39,6 +39,9 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=64, help="walker configurations per GPU per step")
     ap.add_argument("--workload", default="C2", choices=sorted(synth.SHAPES))
     ap.add_argument("--rho-mode", type=int, default=-1, help="-1 library default, 0 generic sincos, 1 lattice recurrence")
+    ap.add_argument("--shard", default="config", choices=["config", "q"],
+                    help="multi-GPU axis: independent walker configurations (weak scaling, one reduce) or q-vectors "
+                         "(strong scaling, every rank sees every configuration, one all-gather)")
     ap.add_argument("--unique", type=int, default=16, help="distinct synthetic configurations generated per slot")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -179,13 +182,6 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-class DevPtr:
-    """CUDA array interface holder so torch can view the library's bin buffer without a copy."""
-
-    def __init__(self, ptr, count):
-        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
-
-
 # --------------------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------------------
@@ -209,7 +205,12 @@ def run_ours(args, shape, q):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from pimc_b200 import multi
     B, K, W = args.batch, args.steps, args.warmup
+    q_all = q
+    if args.shard == "q" and world > 1:
+        lo, hi = multi.shard_range(len(q_all), world, rank)
+        q = q_all[lo:hi]
     ctx = api.Context(local, shape.ndim)
     ctx.set_box(shape.side)
     ctx.set_qvecs(q)
@@ -223,7 +224,8 @@ def run_ours(args, shape, q):
     use_slots = nslots if nslots * batch_bytes > 140e6 else nslots        # rotate all slots; total footprint below
     pinned = []
     for sl in range(use_slots):
-        uniq = synth.gen_batch(shape, min(args.unique, B), first=1000 * rank + 100 * sl)
+        seed_rank = 0 if args.shard == "q" else rank          # q-sharding: every rank measures the same walkers
+        uniq = synth.gen_batch(shape, min(args.unique, B), first=1000 * seed_rank + 100 * sl)
         pa = api.PinnedArray((B,) + uniq.shape[1:])
         for b in range(B):
             pa.array[b] = uniq[b % len(uniq)]
@@ -255,11 +257,15 @@ def run_ours(args, shape, q):
     for k in range(K):
         device_step(k)
     if world > 1:
-        # the one collective of the path: sum the per-GPU bins onto rank 0 over NVLink (once per bin, not per step)
-        ptr, count = ctx.bins_device_ptr()
-        bins = torch.as_tensor(DevPtr(ptr, count), device=torch.device("cuda", local))
+        # the one collective of the path, once per bin (not per step), on the library's own device buffer
+        bins = multi.bins_tensor(ctx, torch.device("cuda", local))
         with torch.cuda.stream(ext):
-            dist.reduce(bins, dst=0, op=dist.ReduceOp.SUM)
+            if args.shard == "config":
+                dist.reduce(bins, dst=0, op=dist.ReduceOp.SUM)            # sum of per-GPU bins over NVLink
+            else:
+                loc = torch.cat([bins[:nq, None], bins[nq:].view(nq, shape.M)], dim=1)
+                gathered = multi.gather_q_shards(loc, len(q_all))         # concatenate the q-shards
+                assert gathered.shape == (len(q_all), 1 + shape.M)
     e1.record(ext)
     barrier()
     clocks = sampler.stop()
@@ -270,7 +276,8 @@ def run_ours(args, shape, q):
     launches = ctx.launch_count() - launches0
     ktimes = ctx.kernel_times(reset=True)
     ctx.set_profiling(False)
-    value = world * B * K / (ms_total * 1e-3)
+    evals_per_step = world * B if args.shard == "config" else B    # q-sharding: all ranks work on the same B walkers
+    value = evals_per_step * K / (ms_total * 1e-3)
     _, _, n_acc = ctx.read_bins()
     assert n_acc == B * K, (n_acc, B, K)
 
@@ -294,7 +301,7 @@ def run_ours(args, shape, q):
         dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B * Ke / float(dt.item()), "unit": UNIT,
+        e2e = {"value": evals_per_step * Ke / float(dt.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(batch_bytes), "d2h_bytes_per_step": int((nq + nq * shape.M) * 8),
                "steps": Ke, "path": "pimcb_stage_batch(pinned host AoS) + pimcb_measure + pimcb_read_bins, double-buffered"}
 
@@ -334,11 +341,14 @@ def run_ours(args, shape, q):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak" if args.shard == "config" else "strong",
+        "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{shape.name}: N={shape.N} M={shape.M} nq={nq} ndim={shape.ndim}, He-4 SVP density, "
                                f"commensurate q, {B} walker configurations per GPU per step",
-                   "batch_per_gpu": B, "parallelism": f"walker-configuration sharding x{world}, one NCCL reduce of the bin",
+                   "batch_per_gpu": B,
+                   "parallelism": (f"walker-configuration sharding x{world}, one NCCL reduce of the bin" if args.shard == "config"
+                                   else f"q-vector sharding x{world} ({nq} of {len(q_all)} q per GPU), one NCCL all-gather of the bin"),
                    "l2": f"{use_slots} resident batches rotated ({footprint_mb:.0f} MB > 126 MB L2)",
                    "rho_mode": args.rho_mode},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
