@@ -56,8 +56,10 @@ int pimcb_set_box(pimcb_ctx* ctx, const double* side /*[ndim]*/, const unsigned*
 int pimcb_set_qvecs(pimcb_ctx* ctx, const double* q_aos /*[nq][ndim]*/, int nq);
 /* Number of q-vectors classified commensurate (for diagnostics / tests). */
 int pimcb_num_commensurate(const pimcb_ctx* ctx);
-/* 0 = generic sincos-per-(q,bead) kernel, 1 = lattice-recurrence kernel when every q is commensurate
- * (default 1).  Results agree to rounding; the switch exists for A/B measurement. */
+/* rho_q build kernel: 0 = generic (one sincos per (q, bead)); 1 = lattice path when every q is commensurate
+ * (default): phase-power tables + sign-symmetry groups, particle sums as a small GEMM on the FP64 tensor cores
+ * (DMMA), falling back to the CUDA-core lattice kernel and then to the generic one when the q-set does not fit;
+ * 2 = force the CUDA-core lattice kernel.  Results agree to rounding; the switch exists for A/B measurement. */
 int pimcb_set_rho_mode(pimcb_ctx* ctx, int mode);
 
 /* ---- bead staging ------------------------------------------------------------------------------

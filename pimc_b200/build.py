@@ -23,7 +23,8 @@ def is_stale() -> bool:
 def build_lib(force: bool = False, verbose: bool = False) -> str:
     if force or is_stale():
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+        extra = os.environ.get("PIMCB_NVCC_EXTRA", "").split()
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
         subprocess.run(cmd, check=True)
     return LIB
 

@@ -6,7 +6,9 @@
 //
 // Kernels
 //   rho_generic_kernel   rho_q(t) = sum_i exp(i q.r_i(t)), one sincos per (q, bead)      [FP64-pipe bound]
-//   rho_lattice_kernel   same for commensurate q = 2 pi n / L: phase-power tables + sign-symmetry groups [smem-bandwidth bound]
+//   rho_lattice_kernel   same for commensurate q = 2 pi n / L: phase-power tables + sign-symmetry groups,
+//                        lane = particle, warp = column of groups                       [FP64 / smem balanced]
+//   rho_lattice_mma_kernel  the same particle sums as a batched small GEMM on the FP64 tensor cores (DMMA)
 //   isf_corr_kernel      F(q,tau) = (1/N) sum_t0 Re[rho(t0) conj rho(t0+tau)], S(q) = F(q,0)
 //   ssf_direct_kernel    sum_{i<j} cos(q.minimage(r_i-r_j)) for non-commensurate q
 //   pair_kernel          per-slice Vint, sum_i |F_i|^2, separation histogram (table gathers)
@@ -148,128 +150,216 @@ __global__ void __launch_bounds__(256) rho_generic_kernel(const double* __restri
 // rho_q build for commensurate q = 2 pi n / L ("lattice" path).
 //   exp(i q.r) = prod_d e_d^{n_d},  e_d = exp(2 pi i x_d / L_d).
 // Phase 1 tabulates the powers e_d^m, m = 0..nmax_d, of every particle of the slice in shared memory (ND sincos
-// + nmax complex multiplies per particle instead of nq sincos).  Phase 2 works on sign-symmetry GROUPS of
-// wave-vectors: all q that share (|n_0|,..,|n_{ND-1}|) -- up to 2^ND of them -- are produced from ONE pass over
-// the particles, because flipping the sign of a component only conjugates that factor:
-//   3-D:  P+- = X Y^(+-),  K[sb][0..3] = sum_i (P_re Z_re, P_im Z_im, P_re Z_im, P_im Z_re)       (16 FP64 / particle)
-//         rho(+a, sb b, sc c) = (K0 - sc K1) + i (sc K2 + K3),  rho(-a,..) = conj rho(+a, -sb b, -sc c)
-//   2-D:  K[0..3] = sum_i (X_re Y_re, X_im Y_im, X_re Y_im, X_im Y_re);   1-D:  K[0..1] = sum_i X.
-// Work item = (group, particle chunk).  The kernel is shared-memory-bandwidth bound (ND 16-byte table reads per
-// (group, particle)), not FP64 bound.
-// gkey: int[G][ND] = |n_d|;  gout: int[G][2^ND] = q index for sign pattern (bit d set = component d negative) or -1.
-// Power table layout: tab[row][i] as double2 (re, im), row = rowoff_d + m, row stride N + 1 double2 so that
-// lanes reading different rows / chunks hit different banks.
+// + nmax complex multiplies per particle instead of nq sincos).
+// Phase 2 works on sign-symmetry GROUPS of wave-vectors: all q that share (|n_0|,..,|n_{ND-1}|) -- up to 2^ND of
+// them -- come out of ONE pass over the particles, because flipping the sign of a component only conjugates that
+// factor.  In 3-D, with X = e_x^|a|, Y = e_y^|b|, Z = e_z^|c|:
+//      P+- = X Y^(+-),   K[sb][0..3] = sum_i (P_re Z_re, P_im Z_im, P_re Z_im, P_im Z_re)      (8 DFMA / particle)
+//      rho(+a, sb b, sc c) = (K0 - sc K1) + i (sc K2 + K3),   rho(-a, ..) = conj rho(+a, -sb b, -sc c).
+// Mapping: LANE = PARTICLE, WARP = TASK.  A task is a column (|a|,|b|) with a run of |c| entries: the warp computes
+// P+- of its particles once (registers, J particles per lane) and reuses them for every entry of the run, so each
+// (group, particle) costs ONE 16-byte shared-memory read (Z) instead of three -- the v2 kernel (thread = group) was
+// shared-memory-bandwidth bound at 48 B per (group, particle).  The sum over particles is a halving butterfly
+// (v[8] -> 1 value per lane in 9 exchanged doubles) followed by a single-lane accumulate into part[k][group].
+// Tasks are distributed over the 8 warps of the CTA by a host-side LPT schedule (plan.warp_first / plan.tasks).
+// Phase 3 unfolds the sign patterns:  gout[g][pattern] = q index (bit d of pattern set = component d negative) or -1.
+// 2-D: column = |a|, entries = |b|, K[0..3] = sum (X_re Y_re, X_im Y_im, X_re Y_im, X_im Y_re);  1-D: K = sum X^|a|.
+// Power table layout: tab[row][i] as double2 (re, im), row = rowoff_d + m, row stride N + 1 double2.
 // ---------------------------------------------------------------------------------------------
 template <int ND>
 struct LatticeK { static constexpr int NK = ND == 3 ? 8 : (ND == 2 ? 4 : 2); static constexpr int NPAT = 1 << ND; };
 
-template <int ND>
-__global__ void __launch_bounds__(256) rho_lattice_kernel(const double* __restrict__ pos, const int* __restrict__ gkey,
-                                                           const int* __restrict__ gout, double* __restrict__ rho, int nslices,
-                                                           int N, int Npad, int nq, int G, int P, int chunk, int3 nmax,
-                                                           double3 kphase) {
+struct LatticePlan {
+    const int* gout;        // [G][2^ND]
+    const int* ent;         // [G]     |n_last| of group g (groups are stored column by column)
+    const int* tasks;       // [ntask][4] = {|a|, |b|, first group, one-past-last group}
+    const int* warp_first;  // [9]     tasks of warp w: warp_first[w] .. warp_first[w+1]
+    int G;
+};
+
+// Sum v[0..NK) over the 32 lanes.  On return lane L holds the total of component
+// idx = bits (4,3,2) of L for NK = 8, bits (4,3) for NK = 4, bit 4 for NK = 2; lanes sharing those bits agree.
+template <int NK>
+__device__ __forceinline__ double butterfly_sum(double (&v)[NK], int lane, int& idx) {
+    constexpr unsigned FULL = 0xffffffffu;
+    if constexpr (NK == 8) {
+        const bool u4 = lane & 16, u3 = lane & 8, u2 = lane & 4;
+        double a[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double send = u4 ? v[k] : v[k + 4];
+            const double keep = u4 ? v[k + 4] : v[k];
+            a[k] = keep + __shfl_xor_sync(FULL, send, 16);
+        }
+        double b[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const double send = u3 ? a[k] : a[k + 2];
+            const double keep = u3 ? a[k + 2] : a[k];
+            b[k] = keep + __shfl_xor_sync(FULL, send, 8);
+        }
+        double w = (u2 ? b[1] : b[0]) + __shfl_xor_sync(FULL, u2 ? b[0] : b[1], 4);
+        w += __shfl_xor_sync(FULL, w, 2);
+        w += __shfl_xor_sync(FULL, w, 1);
+        idx = (u4 ? 4 : 0) + (u3 ? 2 : 0) + (u2 ? 1 : 0);
+        return w;
+    } else if constexpr (NK == 4) {
+        const bool u4 = lane & 16, u3 = lane & 8;
+        double a[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const double send = u4 ? v[k] : v[k + 2];
+            const double keep = u4 ? v[k + 2] : v[k];
+            a[k] = keep + __shfl_xor_sync(FULL, send, 16);
+        }
+        double w = (u3 ? a[1] : a[0]) + __shfl_xor_sync(FULL, u3 ? a[0] : a[1], 8);
+        w += __shfl_xor_sync(FULL, w, 4);
+        w += __shfl_xor_sync(FULL, w, 2);
+        w += __shfl_xor_sync(FULL, w, 1);
+        idx = (u4 ? 2 : 0) + (u3 ? 1 : 0);
+        return w;
+    } else {
+        const bool u4 = lane & 16;
+        double w = (u4 ? v[1] : v[0]) + __shfl_xor_sync(FULL, u4 ? v[0] : v[1], 16);
+        w += __shfl_xor_sync(FULL, w, 8);
+        w += __shfl_xor_sync(FULL, w, 4);
+        w += __shfl_xor_sync(FULL, w, 2);
+        w += __shfl_xor_sync(FULL, w, 1);
+        idx = u4 ? 1 : 0;
+        return w;
+    }
+}
+
+// Row stride (double2 units) of the phase-power table: N rounded up to whole particle blocks of 32*J, plus one
+// element so that consecutive rows start in different banks.
+__host__ __device__ inline int lattice_stride(int N, int J) { return (N + 32 * J - 1) / (32 * J) * (32 * J) + 1; }
+
+#ifndef PIMCB_LATTICE_MINB
+#define PIMCB_LATTICE_MINB 4
+#endif
+constexpr int kLatticeWarps = 4;   // warps (= concurrent tasks) per CTA of the lattice kernel
+
+template <int ND, int J>
+__global__ void __launch_bounds__(32 * kLatticeWarps, PIMCB_LATTICE_MINB) rho_lattice_kernel(const double* __restrict__ pos, LatticePlan plan,
+                                                           double* __restrict__ rho, int nslices, int N, int Npad, int nq,
+                                                           int3 nmax, double3 kphase) {
     constexpr int NK = LatticeK<ND>::NK;
     constexpr int NPAT = LatticeK<ND>::NPAT;
     extern __shared__ __align__(16) double sm[];
     const int rowoff1 = nmax.x + 1;
     const int rowoff2 = rowoff1 + (ND > 1 ? nmax.y + 1 : 0);
     const int rows = rowoff2 + (ND > 2 ? nmax.z + 1 : 0);
-    const int stride = N + 1;                                  // in double2 units
+    const int stride = lattice_stride(N, J);                   // in double2 units; rows are zero beyond N
+    const int G = plan.G;
     double2* tab = reinterpret_cast<double2*>(sm);             // [rows][stride]
     double* xs = sm + 2 * static_cast<size_t>(rows) * stride;  // [ND][Npad] raw coordinates
-    double* part = xs + ND * Npad;                             // [NK][P*G]  (k-major: conflict-free stores and loads)
-    const int items = G * P;
+    double* part = xs + ND * Npad;                             // [NK][G]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lastrow = ND == 3 ? rowoff2 : (ND == 2 ? rowoff1 : 0);   // row offset of the entry dimension
+    const int nblk = (N + 32 * J - 1) / (32 * J);              // particle blocks of 32*J
     for (int sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
         load_slice(xs, pos + static_cast<size_t>(sl) * ND * Npad, ND * Npad);
         __syncthreads();
-        // phase 1: powers of the base phases
-        for (int w = threadIdx.x; w < ND * N; w += blockDim.x) {
-            const int d = w / N, i = w - d * N;
+        // phase 1: powers of the base phases; entries i >= N of every row are zero so that padded lanes add nothing
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
             const double kp = d == 0 ? kphase.x : (d == 1 ? kphase.y : kphase.z);
             const int nm = d == 0 ? nmax.x : (d == 1 ? nmax.y : nmax.z);
-            const int ro = d == 0 ? 0 : (d == 1 ? rowoff1 : rowoff2);
-            double s, c;
-            sincos_fast(kp * xs[d * Npad + i], s, c);
-            double2* col = tab + static_cast<size_t>(ro) * stride + i;
-            col[0] = make_double2(1.0, 0.0);
-            double pr = c, pi = s;
-            for (int m = 1; m <= nm; ++m) {
-                col[static_cast<size_t>(m) * stride] = make_double2(pr, pi);
-                const double nr = fma(pr, c, -pi * s);
-                pi = fma(pr, s, pi * c);
-                pr = nr;
+            double2* row0 = tab + static_cast<size_t>(d == 0 ? 0 : (d == 1 ? rowoff1 : rowoff2)) * stride;
+            for (int i = threadIdx.x; i < nblk * 32 * J; i += blockDim.x) {
+                double2* col = row0 + i;
+                if (i < N) {
+                    double s, c;
+                    sincos_fast(kp * xs[d * Npad + i], s, c);
+                    col[0] = make_double2(1.0, 0.0);
+                    double pr = c, pi = s;
+                    for (int m = 1; m <= nm; ++m) {
+                        col[m * stride] = make_double2(pr, pi);
+                        const double nr = fma(pr, c, -pi * s);
+                        pi = fma(pr, s, pi * c);
+                        pr = nr;
+                    }
+                } else {
+                    for (int m = 0; m <= nm; ++m) col[m * stride] = make_double2(0.0, 0.0);
+                }
             }
         }
         __syncthreads();
-        // phase 2: one (group, particle chunk) per work item
-        for (int item = threadIdx.x; item < items; item += blockDim.x) {
-            const int p = item / G;
-            const int g = item - p * G;
-            const int i0 = p * chunk;
-            const int i1 = min(N, i0 + chunk);
-            const double2* X = tab + static_cast<size_t>(__ldg(gkey + g * ND)) * stride;
-            double K[NK];
+        // phase 2: warp = task, lane = particle
+        for (int ti = __ldg(plan.warp_first + warp); ti < __ldg(plan.warp_first + warp + 1); ++ti) {
+            const int4 tk = __ldg(reinterpret_cast<const int4*>(plan.tasks) + ti);
+            for (int ib = 0; ib < nblk; ++ib) {
+                const int ibase = ib * 32 * J + lane;
+                double pa[J], pb[J], pc[J], pd[J];             // 3-D: P+ (re,im), P- (re,im); 2-D: X (re,im)
+                if constexpr (ND > 1) {
+                    const double2* X = tab + tk.x * stride + ibase;
+                    const double2* Y = tab + (rowoff1 + tk.y) * stride + ibase;
 #pragma unroll
-            for (int k = 0; k < NK; ++k) K[k] = 0.0;
-            if constexpr (ND == 1) {
-#pragma unroll 4
-                for (int i = i0; i < i1; ++i) {
-                    const double2 x = X[i];
-                    K[0] += x.x;
-                    K[1] += x.y;
+                    for (int j = 0; j < J; ++j) {
+                        const double2 x = X[32 * j];           // zero beyond N
+                        if constexpr (ND == 3) {
+                            const double2 y = Y[32 * j];
+                            const double m1 = x.x * y.x, m2 = x.y * y.y, m3 = x.x * y.y, m4 = x.y * y.x;
+                            pa[j] = m1 - m2; pb[j] = m3 + m4;  // X * Y
+                            pc[j] = m1 + m2; pd[j] = m4 - m3;  // X * conj(Y)
+                        } else {
+                            pa[j] = x.x; pb[j] = x.y;
+                        }
+                    }
                 }
-            } else if constexpr (ND == 2) {
-                const double2* Y = tab + static_cast<size_t>(rowoff1 + __ldg(gkey + g * ND + 1)) * stride;
-#pragma unroll 4
-                for (int i = i0; i < i1; ++i) {
-                    const double2 x = X[i], y = Y[i];
-                    K[0] = fma(x.x, y.x, K[0]);
-                    K[1] = fma(x.y, y.y, K[1]);
-                    K[2] = fma(x.x, y.y, K[2]);
-                    K[3] = fma(x.y, y.x, K[3]);
-                }
-            } else {
-                const double2* Y = tab + static_cast<size_t>(rowoff1 + __ldg(gkey + g * ND + 1)) * stride;
-                const double2* Z = tab + static_cast<size_t>(rowoff2 + __ldg(gkey + g * ND + 2)) * stride;
-#pragma unroll 2
-                for (int i = i0; i < i1; ++i) {
-                    const double2 x = X[i], y = Y[i], z = Z[i];
-                    const double m1 = x.x * y.x, m2 = x.y * y.y, m3 = x.x * y.y, m4 = x.y * y.x;
-                    const double ppr = m1 - m2, ppi = m3 + m4;     // X * Y
-                    const double pmr = m1 + m2, pmi = m4 - m3;     // X * conj(Y)
-                    K[0] = fma(ppr, z.x, K[0]);
-                    K[1] = fma(ppi, z.y, K[1]);
-                    K[2] = fma(ppr, z.y, K[2]);
-                    K[3] = fma(ppi, z.x, K[3]);
-                    K[4] = fma(pmr, z.x, K[4]);
-                    K[5] = fma(pmi, z.y, K[5]);
-                    K[6] = fma(pmr, z.y, K[6]);
-                    K[7] = fma(pmi, z.x, K[7]);
+                for (int g = tk.z; g < tk.w; ++g) {
+                    const int c = __ldg(plan.ent + g);
+                    const double2* Z = tab + (lastrow + c) * stride + ibase;
+                    double K[NK];
+#pragma unroll
+                    for (int k = 0; k < NK; ++k) K[k] = 0.0;
+                    if (ND == 1 || c != 0) {
+#pragma unroll
+                        for (int j = 0; j < J; ++j) {
+                            const double2 z = Z[32 * j];
+                            if constexpr (ND == 3) {
+                                K[0] = fma(pa[j], z.x, K[0]); K[1] = fma(pb[j], z.y, K[1]);
+                                K[2] = fma(pa[j], z.y, K[2]); K[3] = fma(pb[j], z.x, K[3]);
+                                K[4] = fma(pc[j], z.x, K[4]); K[5] = fma(pd[j], z.y, K[5]);
+                                K[6] = fma(pc[j], z.y, K[6]); K[7] = fma(pd[j], z.x, K[7]);
+                            } else if constexpr (ND == 2) {
+                                K[0] = fma(pa[j], z.x, K[0]); K[1] = fma(pb[j], z.y, K[1]);
+                                K[2] = fma(pa[j], z.y, K[2]); K[3] = fma(pb[j], z.x, K[3]);
+                            } else {
+                                K[0] += z.x; K[1] += z.y;
+                            }
+                        }
+                    } else {                                   // Z = 1: no table read, no multiply
+#pragma unroll
+                        for (int j = 0; j < J; ++j) {
+                            if constexpr (ND == 3) { K[0] += pa[j]; K[3] += pb[j]; K[4] += pc[j]; K[7] += pd[j]; }
+                            else { K[0] += pa[j]; K[3] += pb[j]; }
+                        }
+                    }
+                    int idx;
+                    const double w = butterfly_sum<NK>(K, lane, idx);
+                    if ((lane & (32 / NK - 1)) == 0) {
+                        double* dst = part + idx * G + g;
+                        *dst = ib == 0 ? w : *dst + w;
+                    }
                 }
             }
-#pragma unroll
-            for (int k = 0; k < NK; ++k) part[k * items + item] = K[k];
         }
         __syncthreads();
-        // phase 3: fold the chunks (fixed order) and unfold the sign patterns into rho
+        // phase 3: unfold the sign patterns into rho
         for (int w = threadIdx.x; w < G * NPAT; w += blockDim.x) {
             const int g = w / NPAT, pat = w - g * NPAT;
-            const int iq = __ldg(gout + w);
+            const int iq = __ldg(plan.gout + w);
             if (iq < 0) continue;
             const int sa = pat & 1;                                // conj of the pattern with all signs flipped
             const int sb = ND > 1 ? (((pat >> 1) & 1) ^ sa) : 0;
             const int sc = ND > 2 ? (((pat >> 2) & 1) ^ sa) : 0;
-            double k0 = 0.0, k1 = 0.0, k2 = 0.0, k3 = 0.0;
-            const int base = ND == 3 ? 4 * sb : 0;
-            for (int p = 0; p < P; ++p) {
-                const double* src = part + base * items + p * G + g;
-                k0 += src[0];
-                k1 += src[items];
-                if (ND > 1) { k2 += src[2 * items]; k3 += src[3 * items]; }
-            }
+            const double* src = part + (ND == 3 ? 4 * sb : 0) * G + g;
+            const double k0 = src[0], k1 = src[G];
             double re, im;
-            if (ND == 1) { re = k0; im = k1; }
+            if constexpr (ND == 1) { re = k0; im = k1; }
             else {
+                const double k2 = src[2 * G], k3 = src[3 * G];
                 const int sl_ = ND == 3 ? sc : sb;                 // sign of the last multiplied factor
                 re = sl_ ? k0 + k1 : k0 - k1;
                 im = sl_ ? k3 - k2 : k3 + k2;
@@ -278,6 +368,209 @@ __global__ void __launch_bounds__(256) rho_lattice_kernel(const double* __restri
             rho[(static_cast<size_t>(sl) * 2 + 1) * nq + iq] = sa ? -im : im;
         }
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rho_q build for commensurate q on the FP64 tensor cores (DMMA, mma.sync.m8n8k4.f64).
+// The particle sum of the lattice path is a small real GEMM per time slice,
+//        C[row][col] = sum_i  Lrow(i) * Rcol(i),
+// with, in 3-D,  L rows = {Re,Im}(X^|a| Y^|b|), {Re,Im}(X^|a| conj Y^|b|) for every (|a|,|b|) column of the q-set and
+//                R cols = {Re,Im}(Z^|c|) for every |c|;   2-D: L = {Re,Im} X^|a|, R = {Re,Im} Y^|b|;   1-D: L = 1, R = X^|a|.
+// The 8 (3-D) / 4 (2-D) / 2 (1-D) real sums K of a sign-symmetry group are entries of C (see phase C), and the
+// reduction over particles happens inside the tensor-core accumulation -- no shuffles, no per-particle FP64 issue
+// slots: one DMMA = 256 FMAs.  CTA = one (configuration, slice), 4 warps.  Particles are processed in chunks of
+// kMmaChunk: phase A (thread = particle) evaluates ND sincos, the power recurrences and the L/R planes straight
+// into shared memory (plane stride = chunk + 4 doubles, so the 8 rows of an A/B fragment fall into distinct
+// banks); phase B gives every warp a quarter of the chunk's particles and all MT x NT accumulator tiles;
+// phase C adds the four warps' partial tiles in fixed order and unfolds the sign patterns into rho.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMmaChunk = 128;               // particles per chunk (4 warps x 8 k-steps x 4)
+constexpr int kMmaStride = kMmaChunk + 4;    // plane stride in doubles: 32 B past a multiple of 128 B
+
+struct MmaPlan {
+    const int* gout;    // [G][2^ND]  q index per sign pattern or -1
+    const int* gdesc;   // [G][2]     {first L row, first R col} of the group
+    int G, nL, nR;      // groups, L rows, R cols actually used (the kernel's MT x NT tiles cover them, zero padded)
+    // small lookup tables, passed by value so that they sit in the constant bank:
+    short lmap[81];     // 3-D: [(nmax_x+1)*(nmax_y+1)] first L row of column (a,b) or -1; 2-D: [nmax_x+1]; 1-D: unused
+    short rmap[17];     // [nmax_last+1] first R col of |n_last| or -1
+};
+
+__device__ __forceinline__ void dmma8x8x4(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// Persistent CTAs (grid = SMs x resident CTAs, static stride over slices -- the work per slice is uniform): the
+// coordinates of the NEXT (slice, chunk) are fetched into registers while the current one is processed, so the HBM
+// latency of the only global read of the kernel is never exposed.
+template <int ND, int MT, int NT>
+__global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __restrict__ pos, const MmaPlan plan,
+                                                               double* __restrict__ rho, int nslices, int N, int Npad, int nq,
+                                                               int3 nmax, double3 kphase) {
+    constexpr int NPAT = 1 << ND;
+    constexpr int ML = MT, NR = NT;                         // every tile is computed; unused rows / cols are zero planes
+    constexpr int ntile = ML * NR;
+    extern __shared__ __align__(16) double sm[];
+    const int G = plan.G;
+    double* Lp = sm;                                        // [8*ML][kMmaStride]
+    double* Rp = Lp + 8 * ML * kMmaStride;                  // [8*NR][kMmaStride]
+    double* Cp = sm;                                        // [4 warps][ntile][64], aliases the planes after the last chunk
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int il = threadIdx.x;                             // particle of the chunk this thread owns in phase A
+    const int nchunk = (N + kMmaChunk - 1) / kMmaChunk;
+
+    // padding rows / columns (planes phase A never writes) must not hold NaNs: cleared once per CTA
+    for (int w = plan.nL * kMmaStride + threadIdx.x; w < 8 * ML * kMmaStride; w += blockDim.x) Lp[w] = 0.0;
+    for (int w = plan.nR * kMmaStride + threadIdx.x; w < 8 * NR * kMmaStride; w += blockDim.x) Rp[w] = 0.0;
+
+    auto fetch = [&](int sl, int ch, double (&x)[3]) {
+        const int i = ch * kMmaChunk + il;
+        x[0] = x[1] = x[2] = 0.0;
+        if (sl < nslices && i < N) {
+            const double* ps = pos + static_cast<size_t>(sl) * ND * Npad + i;
+            x[0] = __ldg(ps);
+            if constexpr (ND > 1) x[1] = __ldg(ps + Npad);
+            if constexpr (ND > 2) x[2] = __ldg(ps + 2 * Npad);
+        }
+    };
+    double xn[3];
+    fetch(blockIdx.x, 0, xn);
+    for (int sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
+        double acc[MT][NT][2];
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+        for (int ch = 0; ch < nchunk; ++ch) {
+            const double xc[3] = {xn[0], xn[1], xn[2]};
+            if (ch + 1 < nchunk) fetch(sl, ch + 1, xn); else fetch(sl + gridDim.x, 0, xn);
+            // ---- phase A: thread = particle of the chunk -------------------------------------------------
+            {
+                const bool live = ch * kMmaChunk + il < N;
+                const double lv = live ? 1.0 : 0.0;          // dead particles contribute zero rows (xc = 0 -> e = 1)
+                double ex_s, ex_c, ey_s = 0.0, ey_c = 1.0, ez_s = 0.0, ez_c = 1.0;
+                sincos_fast(kphase.x * xc[0], ex_s, ex_c);
+                if constexpr (ND > 1) sincos_fast(kphase.y * xc[1], ey_s, ey_c);
+                if constexpr (ND > 2) sincos_fast(kphase.z * xc[2], ez_s, ez_c);
+                {   // R planes: powers of the last dimension's phase
+                    const double bs = ND == 3 ? ez_s : (ND == 2 ? ey_s : ex_s);
+                    const double bc = ND == 3 ? ez_c : (ND == 2 ? ey_c : ex_c);
+                    const int nl = ND == 3 ? nmax.z : (ND == 2 ? nmax.y : nmax.x);
+                    double pr = lv, pi = 0.0;
+                    for (int m = 0; m <= nl; ++m) {
+                        const int col = plan.rmap[m];
+                        if (col >= 0) {
+                            Rp[col * kMmaStride + il] = pr;
+                            Rp[(col + 1) * kMmaStride + il] = pi;
+                        }
+                        const double nr = fma(pr, bc, -pi * bs);
+                        pi = fma(pr, bs, pi * bc);
+                        pr = nr;
+                    }
+                }
+                if constexpr (ND == 1) {
+                    Lp[il] = lv;
+                } else if constexpr (ND == 2) {
+                    double pr = lv, pi = 0.0;
+                    for (int a = 0; a <= nmax.x; ++a) {
+                        const int row = plan.lmap[a];
+                        if (row >= 0) {
+                            Lp[row * kMmaStride + il] = pr;
+                            Lp[(row + 1) * kMmaStride + il] = pi;
+                        }
+                        const double nr = fma(pr, ex_c, -pi * ex_s);
+                        pi = fma(pr, ex_s, pi * ex_c);
+                        pr = nr;
+                    }
+                } else {
+                    double xr = lv, xi = 0.0;
+                    for (int a = 0; a <= nmax.x; ++a) {
+                        double yr = 1.0, yi = 0.0;
+                        for (int b = 0; b <= nmax.y; ++b) {
+                            const int row = plan.lmap[a * (nmax.y + 1) + b];
+                            if (row >= 0) {
+                                const double m1 = xr * yr, m2 = xi * yi, m3 = xr * yi, m4 = xi * yr;
+                                double* d = Lp + row * kMmaStride + il;
+                                d[0] = m1 - m2;                   // Re X Y
+                                d[kMmaStride] = m3 + m4;          // Im X Y
+                                d[2 * kMmaStride] = m1 + m2;      // Re X conj(Y)
+                                d[3 * kMmaStride] = m4 - m3;      // Im X conj(Y)
+                            }
+                            const double nr = fma(yr, ey_c, -yi * ey_s);
+                            yi = fma(yr, ey_s, yi * ey_c);
+                            yr = nr;
+                        }
+                        const double nr = fma(xr, ex_c, -xi * ex_s);
+                        xi = fma(xr, ex_s, xi * ex_c);
+                        xr = nr;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- phase B: warp = quarter of the chunk, all tiles ---------------------------------------------
+            {
+                const int frow = lane >> 2, fk = lane & 3;
+                const double* la = Lp + frow * kMmaStride + warp * (kMmaChunk / 4) + fk;
+                const double* rb = Rp + frow * kMmaStride + warp * (kMmaChunk / 4) + fk;
+#pragma unroll 2
+                for (int ks = 0; ks < kMmaChunk / 16; ++ks) {
+                    double a[MT], b[NT];
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) a[m] = la[m * 8 * kMmaStride + 4 * ks];
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) b[n] = rb[n * 8 * kMmaStride + 4 * ks];
+#pragma unroll
+                    for (int m = 0; m < MT; ++m)
+#pragma unroll
+                        for (int n = 0; n < NT; ++n) dmma8x8x4(acc[m][n], a[m], b[n]);
+                }
+            }
+            __syncthreads();
+        }
+        // ---- phase C: combine the warps' partial tiles, unfold sign patterns -------------------------------
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                double2* d = reinterpret_cast<double2*>(Cp + (warp * ntile + m * NR + n) * 64) + lane;
+                *d = make_double2(acc[m][n][0], acc[m][n][1]);
+            }
+        __syncthreads();
+        auto centry = [&](int row, int col) {
+            const int off = ((row >> 3) * NR + (col >> 3)) * 64 + ((row & 7) * 4 + ((col & 7) >> 1)) * 2 + (col & 1);
+            return ((Cp[off] + Cp[ntile * 64 + off]) + Cp[2 * ntile * 64 + off]) + Cp[3 * ntile * 64 + off];
+        };
+        for (int w = threadIdx.x; w < G * NPAT; w += blockDim.x) {
+            const int g = w / NPAT, pat = w - g * NPAT;
+            const int iq = __ldg(plan.gout + w);
+            if (iq < 0) continue;
+            const int rb = __ldg(plan.gdesc + 2 * g), cb = __ldg(plan.gdesc + 2 * g + 1);
+            const int sa = pat & 1;                                // conj of the pattern with all signs flipped
+            const int sb = ND > 1 ? (((pat >> 1) & 1) ^ sa) : 0;
+            const int sc = ND > 2 ? (((pat >> 2) & 1) ^ sa) : 0;
+            double re, im;
+            if constexpr (ND == 1) {
+                re = centry(rb, cb);
+                im = centry(rb, cb + 1);
+            } else {
+                const int rr = rb + (ND == 3 ? 2 * sb : 0), ri = rr + 1;
+                const double k0 = centry(rr, cb), k1 = centry(ri, cb + 1), k2 = centry(rr, cb + 1), k3 = centry(ri, cb);
+                const int sl_ = ND == 3 ? sc : sb;                 // sign of the last multiplied factor
+                re = sl_ ? k0 + k1 : k0 - k1;
+                im = sl_ ? k3 - k2 : k3 + k2;
+            }
+            rho[(static_cast<size_t>(sl) * 2 + 0) * nq + iq] = re;
+            rho[(static_cast<size_t>(sl) * 2 + 1) * nq + iq] = sa ? -im : im;
+        }
+        __syncthreads();
+        // Cp aliased the padding planes of L / R: restore them before the next slice's phase B reads them
+        if (sl + gridDim.x < nslices) {
+            for (int w = plan.nL * kMmaStride + threadIdx.x; w < 8 * ML * kMmaStride && w < 4 * ntile * 64; w += blockDim.x) Lp[w] = 0.0;
+            if (4 * ntile * 64 > 8 * ML * kMmaStride)
+                for (int w = plan.nR * kMmaStride + threadIdx.x; w < 8 * NR * kMmaStride; w += blockDim.x) Rp[w] = 0.0;
+        }
     }
 }
 

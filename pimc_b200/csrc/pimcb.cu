@@ -8,6 +8,8 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <array>
 #include <cstring>
 #include <new>
 #include <string>
@@ -97,7 +99,12 @@ struct pimcb_ctx {
     int nmax[3] = {0, 0, 0};
     int ngroups = 0;                       // sign-symmetry groups of the lattice path (0 = path unavailable)
     double max_phase = 0.0;
-    DevBuf d_q, d_comm, d_qn, d_qidx, d_gkey, d_gout;
+    DevBuf d_q, d_comm, d_qn, d_qidx, d_plan;
+    size_t plan_off[7] = {0, 0, 0, 0, 0, 0, 0};   // int offsets of gout / ent / tasks / warp_first / gdesc / lmap / rmap in d_plan
+    int mma_nL = 0, mma_nR = 0;            // L rows / R cols of the DMMA formulation (0 = not available)
+    std::vector<int> mma_lmap, mma_rmap;
+    int lattice_J = 0;                     // 0 = choose from N; else forced (PIMCB_LATTICE_J)
+    int lattice_warps = kLatticeWarps;     // warps per CTA of the lattice kernel (PIMCB_LATTICE_WARPS may lower it to 2)
     int rho_mode = 1;
     // beads
     Slot slots[kSlots];
@@ -201,14 +208,56 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
     const size_t limit = 200 * 1024;
     int rows = 0;
     for (int d = 0; d < nd; ++d) rows += c->nmax[d] + 1;
-    const size_t lattice_fixed = sizeof(double) * (2 * static_cast<size_t>(rows) * (s.N + 1) + static_cast<size_t>(nd) * s.Npad);
+    const int J = c->lattice_J ? c->lattice_J : (s.N > 128 ? 8 : (s.N > 64 ? 4 : (s.N > 32 ? 2 : 1)));
+    const int JJ = J >= 8 ? 8 : (J >= 4 ? 4 : (J >= 2 ? 2 : 1));
+    const size_t lattice_fixed = sizeof(double) * (2 * static_cast<size_t>(rows) * lattice_stride(s.N, JJ) + static_cast<size_t>(nd) * s.Npad);
     // lattice path only when every q is commensurate and the phase-power table leaves room for >= 2 CTAs per SM
-    const bool lattice = c->rho_mode == 1 && c->ngroups > 0 && lattice_fixed <= 100 * 1024;
+    const bool lattice = c->rho_mode >= 1 && c->ngroups > 0 && lattice_fixed <= 100 * 1024;
     int rc = c->d_rho.ensure(sizeof(double) * 2 * static_cast<size_t>(nsl) * nq);
     if (rc) return rc;
-    int P, chunk;
+    int P = 1, chunk = 0;
     KTimer kt(c, K_RHO);
     const int grid = grid_for(c, nsl, 8);
+    // DMMA formulation: tile counts rounded up to a compiled accumulator shape MT x NT (MT*NT <= 16)
+    auto up = [](int v) { return v <= 1 ? 1 : (v <= 2 ? 2 : (v <= 4 ? 4 : (v <= 8 ? 8 : 16))); };
+    const int ML = c->mma_nL > 0 ? up((c->mma_nL + 7) / 8) : 0, NR = c->mma_nR > 0 ? up((c->mma_nR + 7) / 8) : 0;
+    const bool mma_fits = ML > 0 && NR > 0 && c->mma_nL <= 128 && NR <= 4 && ML * NR <= 16 &&
+                          c->mma_lmap.size() <= 81 && c->mma_rmap.size() <= 17;
+    const size_t mma_smem = sizeof(double) * 8 * static_cast<size_t>(ML + NR) * kMmaStride;   // C staging aliases the planes
+    if (c->rho_mode == 1 && c->ngroups > 0 && mma_fits && mma_smem <= 160 * 1024) {
+        const int3 nmax = make_int3(c->nmax[0], c->nmax[1], c->nmax[2]);
+        const double twopi = 2.0 * M_PI;
+        const double3 kph = make_double3(twopi / c->side[0], nd > 1 ? twopi / c->side[1] : 0.0, nd > 2 ? twopi / c->side[2] : 0.0);
+        const int* pl = c->d_plan.as<int>();
+        MmaPlan plan{};
+        plan.gout = pl + c->plan_off[0];
+        plan.gdesc = pl + c->plan_off[4];
+        plan.G = c->ngroups; plan.nL = c->mma_nL; plan.nR = c->mma_nR;
+        for (size_t k = 0; k < c->mma_lmap.size(); ++k) plan.lmap[k] = static_cast<short>(c->mma_lmap[k]);
+        for (size_t k = 0; k < c->mma_rmap.size(); ++k) plan.rmap[k] = static_cast<short>(c->mma_rmap[k]);
+        int pgrid = 0;
+#define LAUNCH_MMA(ND, MT, NT)                                                                                    \
+        { rc = set_smem(rho_lattice_mma_kernel<ND, MT, NT>, mma_smem); if (rc) return rc;                          \
+        int occ = 1;                                                                                               \
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rho_lattice_mma_kernel<ND, MT, NT>, 128, mma_smem)); \
+        pgrid = std::max(1, std::min(nsl, c->sm_count * std::max(1, occ)));                                        \
+        rho_lattice_mma_kernel<ND, MT, NT><<<pgrid, 128, mma_smem, c->stream>>>(s.pos.as<double>(), plan, c->d_rho.as<double>(), \
+                                                                                nsl, s.N, s.Npad, nq, nmax, kph); }
+#define LAUNCH_MMA_M(ND, NT)                                                                                      \
+        switch (ML) { case 1: LAUNCH_MMA(ND, 1, NT) break; case 2: LAUNCH_MMA(ND, 2, NT) break;                    \
+                      default: LAUNCH_MMA(ND, 4, NT) break; }
+#define LAUNCH_MMA_SHAPE(ND)                                                                                      \
+        if (NR == 1) { switch (ML) { case 8: LAUNCH_MMA(ND, 8, 1) break; case 16: LAUNCH_MMA(ND, 16, 1) break;     \
+                                     default: LAUNCH_MMA_M(ND, 1) } }                                              \
+        else if (NR == 2) { if (ML == 8) LAUNCH_MMA(ND, 8, 2) else LAUNCH_MMA_M(ND, 2) }                           \
+        else { LAUNCH_MMA_M(ND, 4) }
+        if (nd == 1) { LAUNCH_MMA_SHAPE(1) } else if (nd == 2) { LAUNCH_MMA_SHAPE(2) } else { LAUNCH_MMA_SHAPE(3) }
+#undef LAUNCH_MMA_SHAPE
+#undef LAUNCH_MMA_M
+#undef LAUNCH_MMA
+        CU(cudaGetLastError());
+        return 0;
+    }
     if (!lattice) {
         const size_t fixed = sizeof(double) * nd * s.Npad;
         choose_split(nq, s.N, 256, fixed, sizeof(double) * 2, limit, &P, &chunk);
@@ -222,16 +271,22 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
     } else {
         const int G = c->ngroups;
         const int nk = nd == 3 ? 8 : (nd == 2 ? 4 : 2);
-        choose_split(G, s.N, 256, lattice_fixed, sizeof(double) * nk, 110 * 1024, &P, &chunk);
-        const size_t smem = lattice_fixed + sizeof(double) * nk * P * G;
+        const size_t smem = lattice_fixed + sizeof(double) * nk * G;
         const int3 nmax = make_int3(c->nmax[0], c->nmax[1], c->nmax[2]);
         const double twopi = 2.0 * M_PI;
         const double3 kph = make_double3(twopi / c->side[0], nd > 1 ? twopi / c->side[1] : 0.0, nd > 2 ? twopi / c->side[2] : 0.0);
-#define LAUNCH_LATTICE(ND)                                                                                        \
-        rc = set_smem(rho_lattice_kernel<ND>, smem); if (rc) return rc;                                            \
-        rho_lattice_kernel<ND><<<grid, 256, smem, c->stream>>>(s.pos.as<double>(), c->d_gkey.as<int>(), c->d_gout.as<int>(), \
-                                                               c->d_rho.as<double>(), nsl, s.N, s.Npad, nq, G, P, chunk, nmax, kph)
-        if (nd == 1) { LAUNCH_LATTICE(1); } else if (nd == 2) { LAUNCH_LATTICE(2); } else { LAUNCH_LATTICE(3); }
+        const int* pl = c->d_plan.as<int>();
+        const LatticePlan plan{pl + c->plan_off[0], pl + c->plan_off[1], pl + c->plan_off[2], pl + c->plan_off[3], G};
+        (void)P; (void)chunk;
+#define LAUNCH_LATTICE(ND, JJ)                                                                                    \
+        rc = set_smem(rho_lattice_kernel<ND, JJ>, smem); if (rc) return rc;                                        \
+        rho_lattice_kernel<ND, JJ><<<grid, 32 * c->lattice_warps, smem, c->stream>>>(s.pos.as<double>(), plan, c->d_rho.as<double>(), nsl, \
+                                                                   s.N, s.Npad, nq, nmax, kph)
+#define LAUNCH_LATTICE_J(ND)                                                                                      \
+        if (J >= 8) { LAUNCH_LATTICE(ND, 8); } else if (J >= 4) { LAUNCH_LATTICE(ND, 4); }                         \
+        else if (J >= 2) { LAUNCH_LATTICE(ND, 2); } else { LAUNCH_LATTICE(ND, 1); }
+        if (nd == 1) { LAUNCH_LATTICE_J(1) } else if (nd == 2) { LAUNCH_LATTICE_J(2) } else { LAUNCH_LATTICE_J(3) }
+#undef LAUNCH_LATTICE_J
 #undef LAUNCH_LATTICE
     }
     CU(cudaGetLastError());
@@ -407,6 +462,11 @@ int pimcb_create(pimcb_ctx** out, int device, int ndim) {
     if (!c) return fail(PIMCB_ENOMEM, "out of host memory");
     c->device = device;
     c->ndim = ndim;
+    if (const char* e = std::getenv("PIMCB_LATTICE_J")) c->lattice_J = std::atoi(e);
+    if (const char* e = std::getenv("PIMCB_LATTICE_WARPS")) {
+        const int w = std::atoi(e);
+        if (w == 2 || w == 4) c->lattice_warps = w;
+    }
     cudaDeviceProp prop{};
     CU(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
@@ -440,7 +500,7 @@ int pimcb_destroy(pimcb_ctx* c) {
     }
     for (auto& p : c->pin) { p.release(); if (p.done) cudaEventDestroy(p.done); }
     c->h_out.release();
-    for (DevBuf* b : {&c->d_q, &c->d_comm, &c->d_qn, &c->d_qidx, &c->d_gkey, &c->d_gout, &c->d_aos, &c->d_rho, &c->d_cfg, &c->d_bins, &c->d_partial,
+    for (DevBuf* b : {&c->d_q, &c->d_comm, &c->d_qn, &c->d_qidx, &c->d_plan, &c->d_aos, &c->d_rho, &c->d_cfg, &c->d_bins, &c->d_partial,
                       &c->d_V, &c->d_dV, &c->d_vint, &c->d_f2, &c->d_hist, &c->d_scratch})
         b->release();
     for (int k = 0; k < kKernels; ++k) { cudaEventDestroy(c->ev0[k]); cudaEventDestroy(c->ev1[k]); }
@@ -509,11 +569,14 @@ int pimcb_set_qvecs(pimcb_ctx* c, const double* q, int nq) {
             for (int d = 0; d < nd; ++d) c->nmax[d] = std::max(c->nmax[d], std::abs(c->qn[static_cast<size_t>(k) * nd + d]));
     c->nsel = static_cast<int>(sel.size());
     int rc;
-    // sign-symmetry groups for the lattice path: key = (|n_0|,..,|n_{nd-1}|), member slot = sign pattern
+    // Lattice-path plan: sign-symmetry groups (key = (|n_0|,..,|n_{nd-1}|), member slot = sign pattern), stored
+    // column by column (column = leading nd-1 key components), cut into tasks and scheduled on the CTA's warps (LPT).
     c->ngroups = 0;
+    c->mma_nL = c->mma_nR = 0;
     if (c->ncomm == nq) {
         const int npat = 1 << nd;
-        std::vector<int> gkey, gout;
+        struct Grp { int key[3]; std::vector<int> out; };
+        std::vector<Grp> groups;
         for (int k = 0; k < nq; ++k) {
             int key[3] = {0, 0, 0}, pat = 0;
             for (int d = 0; d < nd; ++d) {
@@ -521,26 +584,116 @@ int pimcb_set_qvecs(pimcb_ctx* c, const double* q, int nq) {
                 key[d] = std::abs(n);
                 if (n < 0) pat |= 1 << d;
             }
-            int g = -1;
-            const int ng = static_cast<int>(gkey.size()) / nd;
-            for (int j = 0; j < ng && g < 0; ++j) {
-                bool same = true;
-                for (int d = 0; d < nd; ++d) same = same && gkey[static_cast<size_t>(j) * nd + d] == key[d];
-                if (same && gout[static_cast<size_t>(j) * npat + pat] < 0) g = j;   // a repeated q opens a new group
+            Grp* hit = nullptr;
+            for (Grp& g : groups)
+                if (g.key[0] == key[0] && g.key[1] == key[1] && g.key[2] == key[2] && g.out[pat] < 0) { hit = &g; break; }
+            if (!hit) {                                   // a repeated q opens a new group with the same key
+                groups.push_back(Grp{{key[0], key[1], key[2]}, std::vector<int>(npat, -1)});
+                hit = &groups.back();
             }
-            if (g < 0) {
-                g = ng;
-                for (int d = 0; d < nd; ++d) gkey.push_back(key[d]);
-                gout.insert(gout.end(), npat, -1);
-            }
-            gout[static_cast<size_t>(g) * npat + pat] = k;
+            hit->out[pat] = k;
         }
-        c->ngroups = static_cast<int>(gkey.size()) / nd;
-        if ((rc = c->d_gkey.ensure(sizeof(int) * gkey.size()))) return rc;
-        if ((rc = c->d_gout.ensure(sizeof(int) * gout.size()))) return rc;
-        CU(cudaMemcpyAsync(c->d_gkey.p, gkey.data(), sizeof(int) * gkey.size(), cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(c->d_gout.p, gout.data(), sizeof(int) * gout.size(), cudaMemcpyHostToDevice, c->stream));
-        CU(cudaStreamSynchronize(c->stream));   // gkey/gout are locals
+        std::stable_sort(groups.begin(), groups.end(), [](const Grp& a, const Grp& b) {
+            return std::lexicographical_compare(a.key, a.key + 3, b.key, b.key + 3);
+        });
+        const int G = static_cast<int>(groups.size());
+        auto col_of = [&](const Grp& g, int which) { return which < nd - 1 ? g.key[which] : 0; };
+        auto same_col = [&](const Grp& a, const Grp& b) { return col_of(a, 0) == col_of(b, 0) && col_of(a, 1) == col_of(b, 1); };
+        const int last = nd - 1;
+        // candidate run lengths: pick the one whose LPT makespan is smallest
+        int maxlen = 1;
+        for (int g0 = 0; g0 < G;) {
+            int g1 = g0 + 1;
+            while (g1 < G && same_col(groups[g0], groups[g1])) ++g1;
+            maxlen = std::max(maxlen, g1 - g0);
+            g0 = g1;
+        }
+        std::vector<int> best_tasks, best_first;
+        double best_span = 1e300;
+        for (int emax = 1; emax <= maxlen; ++emax) {
+            std::vector<std::array<int, 4>> tasks;
+            std::vector<double> cost;
+            for (int g0 = 0; g0 < G;) {
+                int g1 = g0 + 1;
+                while (g1 < G && same_col(groups[g0], groups[g1])) ++g1;
+                for (int a = g0; a < g1; a += emax) {
+                    const int b = std::min(g1, a + emax);
+                    double cst = nd == 3 ? 0.8 : (nd == 2 ? 0.3 : 0.0);
+                    for (int g = a; g < b; ++g) cst += (groups[g].key[last] == 0 && nd > 1) ? 0.6 : 1.0;
+                    tasks.push_back({col_of(groups[g0], 0), col_of(groups[g0], 1), a, b});
+                    cost.push_back(cst);
+                }
+                g0 = g1;
+            }
+            std::vector<int> order(tasks.size());
+            for (size_t i = 0; i < order.size(); ++i) order[i] = static_cast<int>(i);
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+            const int W = c->lattice_warps;
+            double load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            std::vector<int> owner(tasks.size());
+            for (int t : order) {
+                int w = 0;
+                for (int k = 1; k < W; ++k) if (load[k] < load[w]) w = k;
+                load[w] += cost[t];
+                owner[t] = w;
+            }
+            const double span = *std::max_element(load, load + W);
+            if (span < best_span - 1e-9) {
+                best_span = span;
+                best_tasks.clear();
+                best_first.assign(9, 0);
+                for (int w = 0; w < 8; ++w) {
+                    best_first[w] = static_cast<int>(best_tasks.size() / 4);
+                    for (size_t t = 0; t < tasks.size(); ++t)
+                        if (owner[t] == w && w < W) best_tasks.insert(best_tasks.end(), tasks[t].begin(), tasks[t].end());
+                }
+                best_first[8] = static_cast<int>(best_tasks.size() / 4);
+            }
+        }
+        std::vector<int> plan;
+        auto align4 = [&plan]() { while (plan.size() % 4) plan.push_back(0); };
+        c->plan_off[0] = plan.size();
+        for (const Grp& g : groups) plan.insert(plan.end(), g.out.begin(), g.out.end());
+        align4();
+        c->plan_off[1] = plan.size();
+        for (const Grp& g : groups) plan.push_back(g.key[last]);
+        align4();
+        c->plan_off[2] = plan.size();
+        plan.insert(plan.end(), best_tasks.begin(), best_tasks.end());
+        align4();
+        c->plan_off[3] = plan.size();
+        plan.insert(plan.end(), best_first.begin(), best_first.end());
+        // DMMA formulation: L rows per (leading-key) column, R columns per last-key value
+        {
+            const int n0 = c->nmax[0] + 1, n1 = nd == 3 ? c->nmax[1] + 1 : 1;
+            std::vector<int> lmap(nd == 1 ? 1 : static_cast<size_t>(n0) * n1, -1), rmap(c->nmax[last] + 1, -1), gdesc;
+            const int per_col = nd == 3 ? 4 : 2;
+            int nL = nd == 1 ? 1 : 0, nR = 0;
+            if (nd == 1) lmap[0] = 0;
+            for (const Grp& g : groups) {
+                int& r = rmap[g.key[last]];
+                if (r < 0) { r = nR; nR += 2; }
+                int lrow = 0;
+                if (nd > 1) {
+                    int& l = lmap[nd == 3 ? g.key[0] * n1 + g.key[1] : g.key[0]];
+                    if (l < 0) { l = nL; nL += per_col; }
+                    lrow = l;
+                }
+                gdesc.push_back(lrow);
+                gdesc.push_back(r);
+            }
+            c->mma_nL = nL;
+            c->mma_nR = nR;
+            c->mma_lmap = lmap;
+            c->mma_rmap = rmap;
+            align4();
+            c->plan_off[4] = plan.size();
+            plan.insert(plan.end(), gdesc.begin(), gdesc.end());
+        }
+        c->ngroups = G;
+        if ((rc = c->d_plan.ensure(sizeof(int) * plan.size()))) return rc;
+        CU(cudaMemcpyAsync(c->d_plan.p, plan.data(), sizeof(int) * plan.size(), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));   // `plan` is a local
     }
     if ((rc = c->d_q.ensure(sizeof(double) * qsoa.size()))) return rc;
     if ((rc = c->d_comm.ensure(nq))) return rc;
@@ -558,7 +711,7 @@ int pimcb_set_qvecs(pimcb_ctx* c, const double* q, int nq) {
 int pimcb_num_commensurate(const pimcb_ctx* c) { return c ? c->ncomm : PIMCB_EINVAL; }
 
 int pimcb_set_rho_mode(pimcb_ctx* c, int mode) {
-    if (!c || (mode != 0 && mode != 1)) return fail(PIMCB_EINVAL, "rho mode must be 0 or 1");
+    if (!c || mode < 0 || mode > 2) return fail(PIMCB_EINVAL, "rho mode must be 0, 1 or 2");
     c->rho_mode = mode;
     return 0;
 }

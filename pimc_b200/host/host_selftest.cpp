@@ -1,5 +1,5 @@
 // host_selftest -- GPU-free checks of the host layer: factory registration names, wave-vector generation, header and
-// row formatting.  Prints a small key=value report that tests/test_host_layer.py compares with the CPU oracle.
+// row formatting.  Prints a small key=value report that tests/test_host_layer.py compares with independent CPU results.
 #include <iostream>
 
 #include "aziz.h"

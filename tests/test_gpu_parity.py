@@ -23,7 +23,7 @@ def make_ctx(api, shape, q, periodic=None):
     return ctx
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_c1_full_direct_oracle(api, orc, nthreads, mode):
     """C1 (N=16, M=124, 64 q): every q, every tau against the reference's O(Nq M^2 N^2) loop."""
     s = synth.C1
@@ -37,7 +37,7 @@ def test_c1_full_direct_oracle(api, orc, nthreads, mode):
     assert_parity(isf[0], orc.isf(beads, s.N, q, nthreads=nthreads), "C1 isf")
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_c2_shape(api, orc, nthreads, mode):
     """C2 (N=256, M=170, 64 q): S(q) for all q against the min-image CPU loop; F(q,tau) for all q against the
     factorised CPU variant and for 1 q against the direct reference loop (1.9e9 terms)."""
@@ -62,7 +62,7 @@ def test_c3_2d_full_grid(api, orc, nthreads):
     beads = synth.gen_config(s.N, s.M, s.ndim, s.rho, s.T, seed=synth.BASE_SEED + 2)
     q = orc.qvectors("max_int", "8 8", s.side)
     assert len(q) == 289
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         with make_ctx(api, s, q) as ctx:
             ctx.set_rho_mode(mode)
             ssf, isf = ctx.stage(beads, s.N).ssf_isf()
@@ -93,7 +93,7 @@ def test_ragged_sizes(api, orc, ndim, N, M, pad):
     if pad:
         beads[:, N:, :] = 7777.0          # padding columns must never contribute
     q = np.vstack([synth.commensurate_q(6, s.side, include_zero=True), synth.float_q(3, ndim)])
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         with make_ctx(api, s, q) as ctx:
             ctx.set_rho_mode(mode)
             ssf, isf = ctx.stage(beads, N).ssf_isf()

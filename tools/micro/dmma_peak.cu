@@ -1,0 +1,59 @@
+// Microbenchmark: FP64 tensor-core (mma.sync.m8n8k4.f64 -> DMMA.8x8x4) throughput vs DFMA on sm_100a.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o dmma_peak dmma_peak.cu && ./dmma_peak
+#include <cstdio>
+#include <cuda_runtime.h>
+
+__global__ void __launch_bounds__(256) dmma_kernel(double* out, int iters, double a, double b) {
+    double c0[2] = {0, 0}, c1[2] = {0, 0}, c2[2] = {0, 0}, c3[2] = {0, 0};
+    double c4[2] = {0, 0}, c5[2] = {0, 0}, c6[2] = {0, 0}, c7[2] = {0, 0};
+    const double av = a + threadIdx.x * 1e-9, bv = b;
+#define MMA(c) asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(av), "d"(bv))
+    for (int it = 0; it < iters; ++it) {
+        MMA(c0); MMA(c1); MMA(c2); MMA(c3); MMA(c4); MMA(c5); MMA(c6); MMA(c7);
+    }
+    const double v = c0[0] + c1[0] + c2[0] + c3[0] + c4[1] + c5[1] + c6[1] + c7[1];
+    if (v == 123.456) out[0] = v;
+}
+
+__global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    const double v = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (v == 123.456) out[0] = v;
+}
+
+int main() {
+    double* d;
+    cudaMalloc(&d, 64);
+    cudaDeviceProp p;
+    cudaGetDeviceProperties(&p, 0);
+    const int grid = p.multiProcessorCount * 8, iters = 4096;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int w = 0; w < 3; ++w) { if (pass) dmma_kernel<<<grid, 256>>>(d, iters, 1.0000001, 1e-9); else dfma_kernel<<<grid, 256>>>(d, iters, 1.0000001, 1e-9); }
+        cudaDeviceSynchronize();
+        float best = 1e30f;
+        for (int r = 0; r < 5; ++r) {
+            cudaEventRecord(e0);
+            if (pass) dmma_kernel<<<grid, 256>>>(d, iters, 1.0000001, 1e-9); else dfma_kernel<<<grid, 256>>>(d, iters, 1.0000001, 1e-9);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            best = ms < best ? ms : best;
+        }
+        // dfma: 32 FMA/thread/iter; dmma: 8 MMA/warp/iter, each 8*8*4 FMA
+        const double flop = pass ? 2.0 * 8 * 256.0 * iters * grid * 8 : 2.0 * 32 * iters * (double)grid * 256;
+        printf("%s: %.3f ms  %.2f TFLOP/s\n", pass ? "DMMA m8n8k4" : "DFMA", best, flop / (best * 1e-3) / 1e12);
+    }
+    printf("cudaGetLastError: %s\n", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
