@@ -390,12 +390,16 @@ constexpr int kMmaStride = kMmaChunk + 4;    // plane stride in doubles: 32 B pa
 
 struct MmaPlan {
     const int* gout;    // [G][2^ND]  q index per sign pattern or -1
-    const int* gdesc;   // [G][2]     {first L row, first R col} of the group
-    int G, nL, nR;      // groups, L rows, R cols actually used (the kernel's MT x NT tiles cover them, zero padded)
+    const int* gdesc;   // [G][8]     {rowRe+, rowIm+, rowRe-, rowIm-, signIm-, colRe, colIm, 0}: where the group's factors live
+    int G, nL, nR;      // groups; L rows / R cols in use INCLUDING the reserved zero plane (index nL-1 / nR-1);
+                        // the kernel's MT x NT tiles cover them, everything from the zero plane on is cleared
     // small lookup tables, passed by value so that they sit in the constant bank:
     short lmap[81];     // 3-D: [(nmax_x+1)*(nmax_y+1)] first L row of column (a,b) or -1; 2-D: [nmax_x+1]; 1-D: unused
     short rmap[17];     // [nmax_last+1] first R col of |n_last| or -1
 };
+// Rows are stored only once when factors coincide (3-D):  b = 0: X conj(Y) = X Y (2 rows: Re, Im of X^a);
+// a = 0: X conj(Y) = conj(Y^b) (2 rows: Re, Im of Y^b, Im- = -Im+);  a = b = 0: one row of ones (Im = the zero row).
+// Likewise c = 0 stores the single column of ones (Im = the zero column).  Row nL-1 / column nR-1 are all zero.
 
 __device__ __forceinline__ void dmma8x8x4(double (&c)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -422,8 +426,8 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
     const int nchunk = (N + kMmaChunk - 1) / kMmaChunk;
 
     // padding rows / columns (planes phase A never writes) must not hold NaNs: cleared once per CTA
-    for (int w = plan.nL * kMmaStride + threadIdx.x; w < 8 * ML * kMmaStride; w += blockDim.x) Lp[w] = 0.0;
-    for (int w = plan.nR * kMmaStride + threadIdx.x; w < 8 * NR * kMmaStride; w += blockDim.x) Rp[w] = 0.0;
+    for (int w = (plan.nL - 1) * kMmaStride + threadIdx.x; w < 8 * ML * kMmaStride; w += blockDim.x) Lp[w] = 0.0;
+    for (int w = (plan.nR - 1) * kMmaStride + threadIdx.x; w < 8 * NR * kMmaStride; w += blockDim.x) Rp[w] = 0.0;
 
     auto fetch = [&](int sl, int ch, double (&x)[3]) {
         const int i = ch * kMmaChunk + il;
@@ -438,11 +442,13 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
     double xn[3];
     fetch(blockIdx.x, 0, xn);
     for (int sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
-        double acc[MT][NT][2];
+        double acc[2][MT][NT][2];                           // two accumulator sets (even / odd k-steps) for DMMA ILP
 #pragma unroll
-        for (int m = 0; m < MT; ++m)
+        for (int e = 0; e < 2; ++e)
 #pragma unroll
-            for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int n = 0; n < NT; ++n) acc[e][m][n][0] = acc[e][m][n][1] = 0.0;
         for (int ch = 0; ch < nchunk; ++ch) {
             const double xc[3] = {xn[0], xn[1], xn[2]};
             if (ch + 1 < nchunk) fetch(sl, ch + 1, xn); else fetch(sl + gridDim.x, 0, xn);
@@ -463,7 +469,7 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                         const int col = plan.rmap[m];
                         if (col >= 0) {
                             Rp[col * kMmaStride + il] = pr;
-                            Rp[(col + 1) * kMmaStride + il] = pi;
+                            if (m > 0 || ND == 1) Rp[(col + 1) * kMmaStride + il] = pi;
                         }
                         const double nr = fma(pr, bc, -pi * bs);
                         pi = fma(pr, bs, pi * bc);
@@ -478,7 +484,7 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                         const int row = plan.lmap[a];
                         if (row >= 0) {
                             Lp[row * kMmaStride + il] = pr;
-                            Lp[(row + 1) * kMmaStride + il] = pi;
+                            if (a > 0) Lp[(row + 1) * kMmaStride + il] = pi;
                         }
                         const double nr = fma(pr, ex_c, -pi * ex_s);
                         pi = fma(pr, ex_s, pi * ex_c);
@@ -491,12 +497,22 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                         for (int b = 0; b <= nmax.y; ++b) {
                             const int row = plan.lmap[a * (nmax.y + 1) + b];
                             if (row >= 0) {
-                                const double m1 = xr * yr, m2 = xi * yi, m3 = xr * yi, m4 = xi * yr;
                                 double* d = Lp + row * kMmaStride + il;
-                                d[0] = m1 - m2;                   // Re X Y
-                                d[kMmaStride] = m3 + m4;          // Im X Y
-                                d[2 * kMmaStride] = m1 + m2;      // Re X conj(Y)
-                                d[3 * kMmaStride] = m4 - m3;      // Im X conj(Y)
+                                if (a > 0 && b > 0) {
+                                    const double m1 = xr * yr, m2 = xi * yi, m3 = xr * yi, m4 = xi * yr;
+                                    d[0] = m1 - m2;                   // Re X Y
+                                    d[kMmaStride] = m3 + m4;          // Im X Y
+                                    d[2 * kMmaStride] = m1 + m2;      // Re X conj(Y)
+                                    d[3 * kMmaStride] = m4 - m3;      // Im X conj(Y)
+                                } else if (a > 0) {                   // Y = 1
+                                    d[0] = xr;
+                                    d[kMmaStride] = xi;
+                                } else if (b > 0) {                   // X = 1 (times the live mask)
+                                    d[0] = lv * yr;
+                                    d[kMmaStride] = lv * yi;
+                                } else {
+                                    d[0] = lv;
+                                }
                             }
                             const double nr = fma(yr, ey_c, -yi * ey_s);
                             yi = fma(yr, ey_s, yi * ey_c);
@@ -514,7 +530,7 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                 const int frow = lane >> 2, fk = lane & 3;
                 const double* la = Lp + frow * kMmaStride + warp * (kMmaChunk / 4) + fk;
                 const double* rb = Rp + frow * kMmaStride + warp * (kMmaChunk / 4) + fk;
-#pragma unroll 2
+#pragma unroll
                 for (int ks = 0; ks < kMmaChunk / 16; ++ks) {
                     double a[MT], b[NT];
 #pragma unroll
@@ -524,7 +540,7 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
 #pragma unroll
                     for (int m = 0; m < MT; ++m)
 #pragma unroll
-                        for (int n = 0; n < NT; ++n) dmma8x8x4(acc[m][n], a[m], b[n]);
+                        for (int n = 0; n < NT; ++n) dmma8x8x4(acc[ks & 1][m][n], a[m], b[n]);
                 }
             }
             __syncthreads();
@@ -535,7 +551,7 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
 #pragma unroll
             for (int n = 0; n < NT; ++n) {
                 double2* d = reinterpret_cast<double2*>(Cp + (warp * ntile + m * NR + n) * 64) + lane;
-                *d = make_double2(acc[m][n][0], acc[m][n][1]);
+                *d = make_double2(acc[0][m][n][0] + acc[1][m][n][0], acc[0][m][n][1] + acc[1][m][n][1]);
             }
         __syncthreads();
         auto centry = [&](int row, int col) {
@@ -546,17 +562,21 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
             const int g = w / NPAT, pat = w - g * NPAT;
             const int iq = __ldg(plan.gout + w);
             if (iq < 0) continue;
-            const int rb = __ldg(plan.gdesc + 2 * g), cb = __ldg(plan.gdesc + 2 * g + 1);
+            const int4 d0 = __ldg(reinterpret_cast<const int4*>(plan.gdesc) + 2 * g);
+            const int4 d1 = __ldg(reinterpret_cast<const int4*>(plan.gdesc) + 2 * g + 1);
             const int sa = pat & 1;                                // conj of the pattern with all signs flipped
             const int sb = ND > 1 ? (((pat >> 1) & 1) ^ sa) : 0;
             const int sc = ND > 2 ? (((pat >> 2) & 1) ^ sa) : 0;
+            const int cr = d1.y, ci = d1.z;                        // columns of Re / Im of the last factor
             double re, im;
             if constexpr (ND == 1) {
-                re = centry(rb, cb);
-                im = centry(rb, cb + 1);
+                re = centry(d0.x, cr);
+                im = centry(d0.x, ci);
             } else {
-                const int rr = rb + (ND == 3 ? 2 * sb : 0), ri = rr + 1;
-                const double k0 = centry(rr, cb), k1 = centry(ri, cb + 1), k2 = centry(rr, cb + 1), k3 = centry(ri, cb);
+                const int side = ND == 3 ? sb : 0;                 // 3-D: which of X Y / X conj(Y)
+                const int rr = side ? d0.z : d0.x, ri = side ? d0.w : d0.y;
+                const double sg = (side && d1.x < 0) ? -1.0 : 1.0;
+                const double k0 = centry(rr, cr), k1 = sg * centry(ri, ci), k2 = centry(rr, ci), k3 = sg * centry(ri, cr);
                 const int sl_ = ND == 3 ? sc : sb;                 // sign of the last multiplied factor
                 re = sl_ ? k0 + k1 : k0 - k1;
                 im = sl_ ? k3 - k2 : k3 + k2;
@@ -567,9 +587,9 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
         __syncthreads();
         // Cp aliased the padding planes of L / R: restore them before the next slice's phase B reads them
         if (sl + gridDim.x < nslices) {
-            for (int w = plan.nL * kMmaStride + threadIdx.x; w < 8 * ML * kMmaStride && w < 4 * ntile * 64; w += blockDim.x) Lp[w] = 0.0;
+            for (int w = (plan.nL - 1) * kMmaStride + threadIdx.x; w < 8 * ML * kMmaStride && w < 4 * ntile * 64; w += blockDim.x) Lp[w] = 0.0;
             if (4 * ntile * 64 > 8 * ML * kMmaStride)
-                for (int w = plan.nR * kMmaStride + threadIdx.x; w < 8 * NR * kMmaStride; w += blockDim.x) Rp[w] = 0.0;
+                for (int w = (plan.nR - 1) * kMmaStride + threadIdx.x; w < 8 * NR * kMmaStride; w += blockDim.x) Rp[w] = 0.0;
         }
     }
 }

@@ -220,7 +220,9 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
     const int grid = grid_for(c, nsl, 8);
     // DMMA formulation: tile counts rounded up to a compiled accumulator shape MT x NT (MT*NT <= 16)
     auto up = [](int v) { return v <= 1 ? 1 : (v <= 2 ? 2 : (v <= 4 ? 4 : (v <= 8 ? 8 : 16))); };
-    const int ML = c->mma_nL > 0 ? up((c->mma_nL + 7) / 8) : 0, NR = c->mma_nR > 0 ? up((c->mma_nR + 7) / 8) : 0;
+    const int mlx = (c->mma_nL + 7) / 8, nrx = (c->mma_nR + 7) / 8;        // exact tile counts
+    const int NR = c->mma_nR > 0 ? up(nrx) : 0;
+    const int ML = c->mma_nL > 0 ? ((NR <= 2 && mlx <= 8) ? mlx : up(mlx)) : 0;   // MT = 1..8 compiled exactly for NT <= 2
     const bool mma_fits = ML > 0 && NR > 0 && c->mma_nL <= 128 && NR <= 4 && ML * NR <= 16 &&
                           c->mma_lmap.size() <= 81 && c->mma_rmap.size() <= 17;
     const size_t mma_smem = sizeof(double) * 8 * static_cast<size_t>(ML + NR) * kMmaStride;   // C staging aliases the planes
@@ -243,17 +245,19 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
         pgrid = std::max(1, std::min(nsl, c->sm_count * std::max(1, occ)));                                        \
         rho_lattice_mma_kernel<ND, MT, NT><<<pgrid, 128, mma_smem, c->stream>>>(s.pos.as<double>(), plan, c->d_rho.as<double>(), \
                                                                                 nsl, s.N, s.Npad, nq, nmax, kph); }
-#define LAUNCH_MMA_M(ND, NT)                                                                                      \
+#define LAUNCH_MMA_M8(ND, NT)                                                                                     \
         switch (ML) { case 1: LAUNCH_MMA(ND, 1, NT) break; case 2: LAUNCH_MMA(ND, 2, NT) break;                    \
-                      default: LAUNCH_MMA(ND, 4, NT) break; }
+                      case 3: LAUNCH_MMA(ND, 3, NT) break; case 4: LAUNCH_MMA(ND, 4, NT) break;                    \
+                      case 5: LAUNCH_MMA(ND, 5, NT) break; case 6: LAUNCH_MMA(ND, 6, NT) break;                    \
+                      case 7: LAUNCH_MMA(ND, 7, NT) break; default: LAUNCH_MMA(ND, 8, NT) break; }
 #define LAUNCH_MMA_SHAPE(ND)                                                                                      \
-        if (NR == 1) { switch (ML) { case 8: LAUNCH_MMA(ND, 8, 1) break; case 16: LAUNCH_MMA(ND, 16, 1) break;     \
-                                     default: LAUNCH_MMA_M(ND, 1) } }                                              \
-        else if (NR == 2) { if (ML == 8) LAUNCH_MMA(ND, 8, 2) else LAUNCH_MMA_M(ND, 2) }                           \
-        else { LAUNCH_MMA_M(ND, 4) }
+        if (NR == 1) { if (ML == 16) LAUNCH_MMA(ND, 16, 1) else LAUNCH_MMA_M8(ND, 1) }                             \
+        else if (NR == 2) { LAUNCH_MMA_M8(ND, 2) }                                                                 \
+        else { switch (ML) { case 1: LAUNCH_MMA(ND, 1, 4) break; case 2: LAUNCH_MMA(ND, 2, 4) break;               \
+                             default: LAUNCH_MMA(ND, 4, 4) break; } }
         if (nd == 1) { LAUNCH_MMA_SHAPE(1) } else if (nd == 2) { LAUNCH_MMA_SHAPE(2) } else { LAUNCH_MMA_SHAPE(3) }
 #undef LAUNCH_MMA_SHAPE
-#undef LAUNCH_MMA_M
+#undef LAUNCH_MMA_M8
 #undef LAUNCH_MMA
         CU(cudaGetLastError());
         return 0;
@@ -663,24 +667,46 @@ int pimcb_set_qvecs(pimcb_ctx* c, const double* q, int nq) {
         align4();
         c->plan_off[3] = plan.size();
         plan.insert(plan.end(), best_first.begin(), best_first.end());
-        // DMMA formulation: L rows per (leading-key) column, R columns per last-key value
+        // DMMA formulation: L rows per (leading-key) column, R columns per last-key value; coinciding factors are
+        // stored once (see kernels.cuh, MmaPlan) and one all-zero row / column is reserved at the end
         {
             const int n0 = c->nmax[0] + 1, n1 = nd == 3 ? c->nmax[1] + 1 : 1;
-            std::vector<int> lmap(nd == 1 ? 1 : static_cast<size_t>(n0) * n1, -1), rmap(c->nmax[last] + 1, -1), gdesc;
-            const int per_col = nd == 3 ? 4 : 2;
+            std::vector<int> lmap(nd == 1 ? 1 : static_cast<size_t>(n0) * n1, -1), rmap(c->nmax[last] + 1, -1);
             int nL = nd == 1 ? 1 : 0, nR = 0;
             if (nd == 1) lmap[0] = 0;
             for (const Grp& g : groups) {
                 int& r = rmap[g.key[last]];
-                if (r < 0) { r = nR; nR += 2; }
-                int lrow = 0;
+                if (r < 0) { r = nR; nR += (g.key[last] > 0 || nd == 1) ? 2 : 1; }
                 if (nd > 1) {
                     int& l = lmap[nd == 3 ? g.key[0] * n1 + g.key[1] : g.key[0]];
-                    if (l < 0) { l = nL; nL += per_col; }
-                    lrow = l;
+                    if (l < 0) {
+                        l = nL;
+                        if (nd == 3) nL += (g.key[0] > 0 && g.key[1] > 0) ? 4 : ((g.key[0] > 0 || g.key[1] > 0) ? 2 : 1);
+                        else nL += g.key[0] > 0 ? 2 : 1;
+                    }
                 }
-                gdesc.push_back(lrow);
-                gdesc.push_back(r);
+            }
+            const int zrow = nL++, zcol = nR++;              // reserved zero planes
+            std::vector<int> gdesc;
+            for (const Grp& g : groups) {
+                const int c0 = rmap[g.key[last]];
+                const bool czero = g.key[last] == 0 && nd > 1;
+                int rrp = 0, rip = zrow, rrm = 0, rim = zrow, sgn = 1;
+                if (nd == 3) {
+                    const int a = g.key[0], b = g.key[1], l = lmap[a * n1 + b];
+                    if (a > 0 && b > 0) { rrp = l; rip = l + 1; rrm = l + 2; rim = l + 3; }
+                    else if (a > 0) { rrp = rrm = l; rip = rim = l + 1; }
+                    else if (b > 0) { rrp = rrm = l; rip = rim = l + 1; sgn = -1; }       // X conj(Y) = conj(Y^b)
+                    else { rrp = rrm = l; rip = rim = zrow; }
+                } else if (nd == 2) {
+                    const int a = g.key[0], l = lmap[a];
+                    rrp = rrm = l;
+                    rip = rim = a > 0 ? l + 1 : zrow;
+                } else {
+                    rrp = rrm = 0;                            // the row of ones
+                }
+                const int e[8] = {rrp, rip, rrm, rim, sgn, c0, czero ? zcol : c0 + 1, 0};
+                gdesc.insert(gdesc.end(), e, e + 8);
             }
             c->mma_nL = nL;
             c->mma_nR = nR;
