@@ -394,7 +394,7 @@ struct MmaPlan {
     int G, nL, nR;      // groups; L rows / R cols in use INCLUDING the reserved zero plane (index nL-1 / nR-1);
                         // the kernel's MT x NT tiles cover them, everything from the zero plane on is cleared
     // small lookup tables, passed by value so that they sit in the constant bank:
-    short lmap[81];     // 3-D: [(nmax_x+1)*(nmax_y+1)] first L row of column (a,b) or -1; 2-D: [nmax_x+1]; 1-D: unused
+    short lmap[81];     // 3-D: lmap[a*9 + b] first L row of column (a,b) or -1 (fixed stride 9); 2-D: lmap[a]; 1-D: unused
     short rmap[17];     // [nmax_last+1] first R col of |n_last| or -1
 };
 // Rows are stored only once when factors coincide (3-D):  b = 0: X conj(Y) = X Y (2 rows: Re, Im of X^a);
@@ -409,7 +409,9 @@ __device__ __forceinline__ void dmma8x8x4(double (&c)[2], double a, double b) {
 // Persistent CTAs (grid = SMs x resident CTAs, static stride over slices -- the work per slice is uniform): the
 // coordinates of the NEXT (slice, chunk) are fetched into registers while the current one is processed, so the HBM
 // latency of the only global read of the kernel is never exposed.
-template <int ND, int MT, int NT>
+// NM > 0 (3-D only): every |n_d| <= NM, the power recurrences and the (a,b) column loop are fully unrolled with the
+// powers held in registers; NM = 0: run-time loop bounds.
+template <int ND, int MT, int NT, int NM>
 __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __restrict__ pos, const MmaPlan plan,
                                                                double* __restrict__ rho, int nslices, int N, int Npad, int nq,
                                                                int3 nmax, double3 kphase) {
@@ -460,6 +462,56 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                 sincos_fast(kphase.x * xc[0], ex_s, ex_c);
                 if constexpr (ND > 1) sincos_fast(kphase.y * xc[1], ey_s, ey_c);
                 if constexpr (ND > 2) sincos_fast(kphase.z * xc[2], ez_s, ez_c);
+                if constexpr (ND == 3 && NM > 0) {
+                    // compile-time bounds: powers of the three phases in registers, (a,b) columns unrolled
+                    double xr[NM + 1], xi[NM + 1], yr[NM + 1], yi[NM + 1], zr = lv, zi = 0.0;
+                    xr[0] = lv; xi[0] = 0.0; yr[0] = 1.0; yi[0] = 0.0;
+#pragma unroll
+                    for (int m = 1; m <= NM; ++m) {
+                        xr[m] = fma(xr[m - 1], ex_c, -xi[m - 1] * ex_s);
+                        xi[m] = fma(xr[m - 1], ex_s, xi[m - 1] * ex_c);
+                        yr[m] = fma(yr[m - 1], ey_c, -yi[m - 1] * ey_s);
+                        yi[m] = fma(yr[m - 1], ey_s, yi[m - 1] * ey_c);
+                    }
+#pragma unroll
+                    for (int m = 0; m <= NM; ++m) {
+                        const int col = plan.rmap[m];
+                        if (col >= 0) {
+                            Rp[col * kMmaStride + il] = zr;
+                            if (m > 0) Rp[(col + 1) * kMmaStride + il] = zi;
+                        }
+                        if (m < NM) {
+                            const double nr = fma(zr, ez_c, -zi * ez_s);
+                            zi = fma(zr, ez_s, zi * ez_c);
+                            zr = nr;
+                        }
+                    }
+#pragma unroll
+                    for (int a = 0; a <= NM; ++a) {
+#pragma unroll
+                        for (int b = 0; b <= NM; ++b) {
+                            const int row = plan.lmap[a * 9 + b];
+                            if (row >= 0) {
+                                double* d = Lp + row * kMmaStride + il;
+                                if (a > 0 && b > 0) {
+                                    const double m1 = xr[a] * yr[b], m2 = xi[a] * yi[b], m3 = xr[a] * yi[b], m4 = xi[a] * yr[b];
+                                    d[0] = m1 - m2;                   // Re X Y
+                                    d[kMmaStride] = m3 + m4;          // Im X Y
+                                    d[2 * kMmaStride] = m1 + m2;      // Re X conj(Y)
+                                    d[3 * kMmaStride] = m4 - m3;      // Im X conj(Y)
+                                } else if (a > 0) {
+                                    d[0] = xr[a];
+                                    d[kMmaStride] = xi[a];
+                                } else if (b > 0) {
+                                    d[0] = lv * yr[b];
+                                    d[kMmaStride] = lv * yi[b];
+                                } else {
+                                    d[0] = lv;
+                                }
+                            }
+                        }
+                    }
+                } else {
                 {   // R planes: powers of the last dimension's phase
                     const double bs = ND == 3 ? ez_s : (ND == 2 ? ey_s : ex_s);
                     const double bc = ND == 3 ? ez_c : (ND == 2 ? ey_c : ex_c);
@@ -495,7 +547,7 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                     for (int a = 0; a <= nmax.x; ++a) {
                         double yr = 1.0, yi = 0.0;
                         for (int b = 0; b <= nmax.y; ++b) {
-                            const int row = plan.lmap[a * (nmax.y + 1) + b];
+                            const int row = plan.lmap[a * 9 + b];
                             if (row >= 0) {
                                 double* d = Lp + row * kMmaStride + il;
                                 if (a > 0 && b > 0) {
@@ -523,6 +575,7 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                         xr = nr;
                     }
                 }
+                }   // run-time loop bounds
             }
             __syncthreads();
             // ---- phase B: warp = quarter of the chunk, all tiles ---------------------------------------------
@@ -606,92 +659,118 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int corr_idx(int i) { return i + 2 * (i >> 3); }
 
-__global__ void __launch_bounds__(128) isf_corr_kernel(const double* __restrict__ rho, double* __restrict__ cfg, int M, int nq,
-                                                        int npairs, int lpq, double invN,
+__global__ void __launch_bounds__(128, 7) isf_corr_kernel(const double* __restrict__ rho, double* __restrict__ cfg, int M, int nq,
+                                                        int npairs, int lpq, int tsplit, double invN,
                                                         const unsigned char* __restrict__ commensurate) {
+    // lpq lanes own the tau blocks of one pair; tsplit (1 or 2) such lane groups share the pair and split the t0
+    // range, their partial sums are added with one shuffle.  Lanes per pair = lpq * tsplit.
     extern __shared__ __align__(16) double sm[];
     const int len = 2 * M + 16;
     const int plen = corr_idx(len) + 2;                      // padded length of one array (even -> 16-byte aligned)
-    const int ppw = 32 / lpq;                                // pairs per warp
+    const int lpp = lpq * tsplit;                            // lanes per pair
+    const int ppw = 32 / lpp;                                // pairs per warp
     const int ppc = ppw * (blockDim.x >> 5);                 // pairs per CTA
     const int pair0 = blockIdx.x * ppc;
-    // stage: consecutive threads take consecutive q of one slice (contiguous in rho), each value is written to
-    // every periodic image i = t, t+M, t+2M < len
-    for (int w = threadIdx.x; w < ppc * M; w += blockDim.x) {
-        const int t = w / ppc, lp = w - t * ppc;
+    // stage: consecutive threads take consecutive q of one slice (contiguous in rho); ppc divides the CTA size, so a
+    // thread keeps its pair and walks t.  Each value goes to every periodic image i = t, t+M, t+2M < len.
+    {
+        const int lp = threadIdx.x % ppc, tstep = blockDim.x / ppc;
         const int pair = pair0 + lp;
-        if (pair >= npairs) continue;
-        const int b = pair / nq, iq = pair - b * nq;
-        const size_t sl = static_cast<size_t>(b) * M + t;
-        const double c = rho[(sl * 2 + 0) * nq + iq];
-        const double sn = rho[(sl * 2 + 1) * nq + iq];
-        for (int i = t; i < len; i += M) {
-            sm[(2 * lp + 0) * plen + corr_idx(i)] = c;
-            sm[(2 * lp + 1) * plen + corr_idx(i)] = sn;
+        if (pair < npairs) {
+            const int b = pair / nq, iq = pair - b * nq;
+            const double* src = rho + (static_cast<size_t>(b) * M * 2) * nq + iq;
+            double* dc = sm + (2 * lp + 0) * plen;
+            double* ds = sm + (2 * lp + 1) * plen;
+            int t = threadIdx.x / ppc;
+            for (; t + 3 * tstep < M; t += 4 * tstep) {      // 8 independent loads in flight
+                double c[4], sn[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    c[u] = __ldg(src + static_cast<size_t>(t + u * tstep) * 2 * nq);
+                    sn[u] = __ldg(src + (static_cast<size_t>(t + u * tstep) * 2 + 1) * nq);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    for (int i = t + u * tstep; i < len; i += M) { dc[corr_idx(i)] = c[u]; ds[corr_idx(i)] = sn[u]; }
+            }
+            for (; t < M; t += tstep) {
+                const double c = __ldg(src + static_cast<size_t>(t) * 2 * nq);
+                const double sn = __ldg(src + (static_cast<size_t>(t) * 2 + 1) * nq);
+                for (int i = t; i < len; i += M) { dc[corr_idx(i)] = c; ds[corr_idx(i)] = sn; }
+            }
         }
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int lp = warp * ppw + lane / lpq;
-    const int pair = pair0 + lp;
-    if (pair >= npairs) return;
+    const int lp = warp * ppw + lane / lpp;
+    const int pair = min(pair0 + lp, npairs - 1);            // surplus lanes recompute the last pair (no divergent exit before shuffles)
+    const bool owner = pair0 + lp < npairs;
     const int b = pair / nq, iq = pair - b * nq;
-    const double* WC = sm + (2 * lp + 0) * plen;
-    const double* WS = sm + (2 * lp + 1) * plen;
+    const double* WC = sm + (2 * (pair - pair0)) * plen;
+    const double* WS = WC + plen;
     const size_t cfg_stride = static_cast<size_t>(nq) + static_cast<size_t>(nq) * M;
     double* out = cfg + static_cast<size_t>(b) * cfg_stride + nq + static_cast<size_t>(iq) * M;
     const int half = M / 2;
     const int nblk = (half + 1 + 7) / 8;                     // tau blocks of 8
-    for (int tb = lane % lpq; tb < nblk; tb += lpq) {
-        const int tau0 = 8 * tb;
+    const int lin = lane % lpp;                              // lane within the pair
+    const int seg = lin / lpq;                               // which part of the t0 range
+    const int nt8 = (M + 7) / 8;                             // t0 blocks of 8
+    const int tb0 = (nt8 * seg) / tsplit, tb1 = (nt8 * (seg + 1)) / tsplit;
+    const int rounds = (nblk + lpq - 1) / lpq;
+    for (int r = 0; r < rounds; ++r) {
+        const int tb = r * lpq + (lin % lpq);
+        const int tau0 = 8 * min(tb, nblk - 1);
         double acc[8];
 #pragma unroll
         for (int v = 0; v < 8; ++v) acc[v] = 0.0;
-        for (int t0 = 0; t0 < M; t0 += 8) {
-            double aC[8], aS[8], wC[16], wS[16];
-            {
-                const double2* pa = reinterpret_cast<const double2*>(WC + corr_idx(t0));
-                const double2* pb = reinterpret_cast<const double2*>(WS + corr_idx(t0));
+        for (int t8 = tb0; t8 < tb1; ++t8) {
+            const int t0 = 8 * t8;
+            // cos part, then sin part: one 8-value broadcast block a(t0..t0+7) and one 16-value window per part
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                const double* W = part ? WS : WC;
+                double a[8], w[16];
+                const double2* pa = reinterpret_cast<const double2*>(W + corr_idx(t0));
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const double2 x = pa[k], y = pb[k];
-                    aC[2 * k] = x.x; aC[2 * k + 1] = x.y;
-                    aS[2 * k] = y.x; aS[2 * k + 1] = y.y;
+                    const double2 x = pa[k];
+                    a[2 * k] = x.x; a[2 * k + 1] = x.y;
                 }
-            }
-            if (t0 + 8 > M) {                                // last block of a non-multiple-of-8 M: drop t0 >= M
+                if (t0 + 8 > M) {                            // last block of a non-multiple-of-8 M: drop t0 >= M
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (t0 + u >= M) { aC[u] = 0.0; aS[u] = 0.0; }
-            }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const double2* pc = reinterpret_cast<const double2*>(WC + corr_idx(t0 + tau0 + 8 * h));
-                const double2* ps = reinterpret_cast<const double2*>(WS + corr_idx(t0 + tau0 + 8 * h));
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const double2 x = pc[k], y = ps[k];
-                    wC[8 * h + 2 * k] = x.x; wC[8 * h + 2 * k + 1] = x.y;
-                    wS[8 * h + 2 * k] = y.x; wS[8 * h + 2 * k + 1] = y.y;
+                    for (int u = 0; u < 8; ++u)
+                        if (t0 + u >= M) a[u] = 0.0;
                 }
-            }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+                for (int h = 0; h < 2; ++h) {
+                    const double2* pw = reinterpret_cast<const double2*>(W + corr_idx(t0 + tau0 + 8 * h));
 #pragma unroll
-                for (int v = 0; v < 8; ++v) {
-                    acc[v] = fma(aC[u], wC[u + v], acc[v]);
-                    acc[v] = fma(aS[u], wS[u + v], acc[v]);
+                    for (int k = 0; k < 4; ++k) {
+                        const double2 x = pw[k];
+                        w[8 * h + 2 * k] = x.x; w[8 * h + 2 * k + 1] = x.y;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) acc[v] = fma(a[u], w[u + v], acc[v]);
                 }
             }
         }
+        if (tsplit == 2) {
 #pragma unroll
-        for (int v = 0; v < 8; ++v) {
-            const int tau = tau0 + v;
-            if (tau > half) continue;
-            const double val = acc[v] * invN;
-            out[tau] = val;
-            if (tau > 0 && tau < M - tau) out[M - tau] = val;
-            if (tau == 0 && commensurate[iq]) cfg[static_cast<size_t>(b) * cfg_stride + iq] = val;
+            for (int v = 0; v < 8; ++v) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], lpq);
+        }
+        if (owner && seg == 0 && tb < nblk) {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                const int tau = tau0 + v;
+                if (tau > half) continue;
+                const double val = acc[v] * invN;
+                out[tau] = val;
+                if (tau > 0 && tau < M - tau) out[M - tau] = val;
+                if (tau == 0 && commensurate[iq]) cfg[static_cast<size_t>(b) * cfg_stride + iq] = val;
+            }
         }
     }
     // odd M never occurs upstream (setup.cpp:1001-1008 forces M even); for odd M, tau = (M+1)/2.. mirror as well.
@@ -778,13 +857,25 @@ __global__ void ssf_direct_finalize_kernel(const double* __restrict__ partial, c
     cfg[b * cfg_stride + qidx[k]] = (static_cast<double>(M) * N + 2.0 * acc) / N;
 }
 
-// bins[j] += sum_b cfg[b][j], b ascending (deterministic).
-__global__ void bins_accumulate_kernel(const double* __restrict__ cfg, double* __restrict__ bins, int B, size_t len) {
-    const size_t j = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (j >= len) return;
-    double acc = bins[j];
-    for (int b = 0; b < B; ++b) acc += cfg[static_cast<size_t>(b) * len + j];
-    bins[j] = acc;
+// bins[j] += sum_b cfg[b][j].  Four adjacent lanes share one element j and sum a contiguous quarter of the
+// configurations each (b ascending); the quarters are combined in fixed order, so the result is deterministic.
+__global__ void __launch_bounds__(256) bins_accumulate_kernel(const double* __restrict__ cfg, double* __restrict__ bins, int B, size_t len) {
+    const size_t gid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t j = min(gid >> 2, len - 1);
+    const int part = static_cast<int>(gid & 3);
+    const int b0 = (B * part) / 4, b1 = (B * (part + 1)) / 4;
+    double a0 = 0.0, a1 = 0.0;
+    int b = b0;
+    for (; b + 1 < b1; b += 2) {
+        a0 += cfg[static_cast<size_t>(b) * len + j];
+        a1 += cfg[static_cast<size_t>(b + 1) * len + j];
+    }
+    if (b < b1) a0 += cfg[static_cast<size_t>(b) * len + j];
+    double acc = a0 + a1;
+    const double p1 = __shfl_down_sync(0xffffffffu, acc, 1);
+    const double p2 = __shfl_down_sync(0xffffffffu, acc, 2);
+    const double p3 = __shfl_down_sync(0xffffffffu, acc, 3);
+    if (part == 0 && (gid >> 2) < len) bins[j] += ((acc + p1) + p2) + p3;
 }
 
 // ---------------------------------------------------------------------------------------------

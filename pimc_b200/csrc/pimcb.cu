@@ -224,7 +224,7 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
     const int NR = c->mma_nR > 0 ? up(nrx) : 0;
     const int ML = c->mma_nL > 0 ? ((NR <= 2 && mlx <= 8) ? mlx : up(mlx)) : 0;   // MT = 1..8 compiled exactly for NT <= 2
     const bool mma_fits = ML > 0 && NR > 0 && c->mma_nL <= 128 && NR <= 4 && ML * NR <= 16 &&
-                          c->mma_lmap.size() <= 81 && c->mma_rmap.size() <= 17;
+                          c->mma_lmap.size() <= 81 && c->mma_rmap.size() <= 17 && (nd < 3 || c->nmax[1] <= 8);
     const size_t mma_smem = sizeof(double) * 8 * static_cast<size_t>(ML + NR) * kMmaStride;   // C staging aliases the planes
     if (c->rho_mode == 1 && c->ngroups > 0 && mma_fits && mma_smem <= 160 * 1024) {
         const int3 nmax = make_int3(c->nmax[0], c->nmax[1], c->nmax[2]);
@@ -235,16 +235,24 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
         plan.gout = pl + c->plan_off[0];
         plan.gdesc = pl + c->plan_off[4];
         plan.G = c->ngroups; plan.nL = c->mma_nL; plan.nR = c->mma_nR;
+        for (short& v : plan.lmap) v = -1;      // the unrolled kernels probe entries beyond this q-set's nmax
+        for (short& v : plan.rmap) v = -1;
         for (size_t k = 0; k < c->mma_lmap.size(); ++k) plan.lmap[k] = static_cast<short>(c->mma_lmap[k]);
         for (size_t k = 0; k < c->mma_rmap.size(); ++k) plan.rmap[k] = static_cast<short>(c->mma_rmap[k]);
         int pgrid = 0;
-#define LAUNCH_MMA(ND, MT, NT)                                                                                    \
-        { rc = set_smem(rho_lattice_mma_kernel<ND, MT, NT>, mma_smem); if (rc) return rc;                          \
+        const int nm3 = std::max(c->nmax[0], std::max(c->nmax[1], c->nmax[2]));
+#define LAUNCH_MMA_NM(ND, MT, NT, NM)                                                                             \
+        { rc = set_smem(rho_lattice_mma_kernel<ND, MT, NT, NM>, mma_smem); if (rc) return rc;                      \
         int occ = 1;                                                                                               \
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rho_lattice_mma_kernel<ND, MT, NT>, 128, mma_smem)); \
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rho_lattice_mma_kernel<ND, MT, NT, NM>, 128, mma_smem)); \
         pgrid = std::max(1, std::min(nsl, c->sm_count * std::max(1, occ)));                                        \
-        rho_lattice_mma_kernel<ND, MT, NT><<<pgrid, 128, mma_smem, c->stream>>>(s.pos.as<double>(), plan, c->d_rho.as<double>(), \
-                                                                                nsl, s.N, s.Npad, nq, nmax, kph); }
+        rho_lattice_mma_kernel<ND, MT, NT, NM><<<pgrid, 128, mma_smem, c->stream>>>(s.pos.as<double>(), plan, c->d_rho.as<double>(), \
+                                                                                    nsl, s.N, s.Npad, nq, nmax, kph); }
+        // 3-D with every |n_d| <= 2 (or 3): phase A fully unrolled; the R columns then fit one N tile
+#define LAUNCH_MMA(ND, MT, NT)                                                                                    \
+        if (ND == 3 && NT == 1 && nm3 <= 2) LAUNCH_MMA_NM(ND, MT, NT, (ND == 3 && NT == 1 ? 2 : 0))                \
+        else if (ND == 3 && NT == 1 && nm3 <= 3) LAUNCH_MMA_NM(ND, MT, NT, (ND == 3 && NT == 1 ? 3 : 0))           \
+        else LAUNCH_MMA_NM(ND, MT, NT, 0)
 #define LAUNCH_MMA_M8(ND, NT)                                                                                     \
         switch (ML) { case 1: LAUNCH_MMA(ND, 1, NT) break; case 2: LAUNCH_MMA(ND, 2, NT) break;                    \
                       case 3: LAUNCH_MMA(ND, 3, NT) break; case 4: LAUNCH_MMA(ND, 4, NT) break;                    \
@@ -259,6 +267,7 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
 #undef LAUNCH_MMA_SHAPE
 #undef LAUNCH_MMA_M8
 #undef LAUNCH_MMA
+#undef LAUNCH_MMA_NM
         CU(cudaGetLastError());
         return 0;
     }
@@ -300,8 +309,9 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
 int launch_corr(pimcb_ctx* c, const Slot& s) {
     KTimer kt(c, K_CORR);
     const int nblk = (s.M / 2 + 1 + 7) / 8;                       // tau blocks of 8 per (config, q) pair
-    const int lpq = nblk <= 8 ? 8 : (nblk <= 16 ? 16 : 32);       // lanes sharing one pair
-    const int ppc = (32 / lpq) * 4;                               // pairs per 128-thread CTA
+    const int lpq = nblk <= 8 ? 8 : (nblk <= 16 ? 16 : 32);       // lanes owning the tau blocks of one pair
+    const int tsplit = lpq <= 16 ? 2 : 1;                         // lane groups splitting the t0 range of the pair
+    const int ppc = (32 / (lpq * tsplit)) * 4;                    // pairs per 128-thread CTA
     const int len = 2 * s.M + 16;
     const int plen = len + 2 * (len >> 3) + 2;
     const size_t smem = sizeof(double) * 2 * static_cast<size_t>(plen) * ppc;
@@ -310,7 +320,7 @@ int launch_corr(pimcb_ctx* c, const Slot& s) {
     if (rc) return rc;
     const int npairs = s.B * c->nq;
     isf_corr_kernel<<<(npairs + ppc - 1) / ppc, 128, smem, c->stream>>>(c->d_rho.as<double>(), c->d_cfg.as<double>(), s.M, c->nq,
-                                                                          npairs, lpq, 1.0 / s.N, c->d_comm.as<unsigned char>());
+                                                                          npairs, lpq, tsplit, 1.0 / s.N, c->d_comm.as<unsigned char>());
     CU(cudaGetLastError());
     return 0;
 }
@@ -670,7 +680,7 @@ int pimcb_set_qvecs(pimcb_ctx* c, const double* q, int nq) {
         // DMMA formulation: L rows per (leading-key) column, R columns per last-key value; coinciding factors are
         // stored once (see kernels.cuh, MmaPlan) and one all-zero row / column is reserved at the end
         {
-            const int n0 = c->nmax[0] + 1, n1 = nd == 3 ? c->nmax[1] + 1 : 1;
+            const int n0 = c->nmax[0] + 1, n1 = nd == 3 ? 9 : 1;   // 3-D lmap has the fixed stride 9 the kernel indexes with
             std::vector<int> lmap(nd == 1 ? 1 : static_cast<size_t>(n0) * n1, -1), rmap(c->nmax[last] + 1, -1);
             int nL = nd == 1 ? 1 : 0, nR = 0;
             if (nd == 1) lmap[0] = 0;
@@ -797,7 +807,7 @@ int pimcb_measure(pimcb_ctx* c) {
     {
         KTimer kt(c, K_BINS);
         const size_t len = c->bins_len;
-        bins_accumulate_kernel<<<static_cast<unsigned>((len + 255) / 256), 256, 0, c->stream>>>(c->d_cfg.as<double>(), c->d_bins.as<double>(), s->B, len);
+        bins_accumulate_kernel<<<static_cast<unsigned>((4 * len + 255) / 256), 256, 0, c->stream>>>(c->d_cfg.as<double>(), c->d_bins.as<double>(), s->B, len);
         CU(cudaGetLastError());
     }
     c->n_acc += s->B;

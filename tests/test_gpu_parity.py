@@ -101,6 +101,32 @@ def test_ragged_sizes(api, orc, ndim, N, M, pad):
         assert_parity(isf[0], orc.isf(beads, N, q, nthreads=4), f"ragged isf {ndim}D N={N}")
 
 
+@pytest.mark.parametrize("ndim,nvec", [
+    (3, [[1, 0, 0], [0, 0, 1]]),                                   # nmax = (1,0,1): columns with b = 0 only
+    (3, [[0, 3, 0], [0, -3, 0], [2, 3, -1], [-2, -3, 1], [2, -3, 1]]),   # anisotropic, nmax = (2,3,1)
+    (3, [[4, 1, 0], [0, 0, 4], [1, 1, 1], [-1, 1, 1], [1, -1, 1], [1, 1, -1], [0, 0, 0]]),   # nmax 4: run-time-bound kernel
+    (3, [[1, 2, 3], [1, 2, 3], [-1, -2, -3]]),                      # a repeated q opens a second group
+    (2, [[0, 5], [5, 0], [-5, 0], [3, -4], [0, 0]]),
+    (1, [[1], [-1], [3], [0]]),
+])
+def test_lattice_qsets(api, orc, ndim, nvec):
+    """Hand-picked lattice q-sets that exercise every branch of the lattice plans (zero components, anisotropic
+    nmax, repeated q, q = 0) in the DMMA (1) and CUDA-core (2) lattice kernels against the generic kernel and oracle."""
+    rho = {1: 0.2, 2: 0.0432, 3: 0.02198}[ndim]
+    N, M = 40, 6
+    s = synth.Shape("l", ndim, N, M, 2.0, rho, 0)
+    beads = synth.gen_config(N, M, ndim, rho, 2.0, seed=17)
+    q = (2.0 * math.pi / s.side) * np.array(nvec, dtype=float)
+    ref_s, ref_f = orc.ssf(s.side, beads, N, q), orc.isf(beads, N, q, nthreads=4)
+    for mode in (0, 1, 2):
+        with make_ctx(api, s, q) as ctx:
+            assert ctx.num_commensurate() == len(q)
+            ctx.set_rho_mode(mode)
+            ssf, isf = ctx.stage(beads, N).ssf_isf()
+        assert_parity(ssf[0], ref_s, f"qset ssf mode {mode}")
+        assert_parity(isf[0], ref_f, f"qset isf mode {mode}")
+
+
 def test_batch_bins_and_slots(api, orc):
     """A walker batch: per-configuration outputs, device-resident bin accumulation, slot rotation."""
     s = synth.Shape("b", 3, 32, 16, 2.0, 0.02198, 0)
