@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--unique", type=int, default=16, help="distinct synthetic configurations generated per slot")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ab", action="store_true", help="skip the generic-kernel A/B leg")
+    ap.add_argument("--no-pair", action="store_true", help="skip the pair-potential secondary measurement")
     ap.add_argument("--peak-seconds", type=float, default=0.5, help="duration of the in-run FP64 DFMA peak measurement")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU work budget (core-seconds) of the cpu_baseline sample")
     return ap.parse_args()
@@ -62,6 +64,21 @@ def workload_q(shape):
         n = np.stack(np.meshgrid(np.arange(-8, 9), np.arange(-8, 9), indexing="ij"), axis=-1).reshape(-1, 2)
         return (2.0 * np.pi / shape.side) * n          # max_int "8 8": odometer order, last dim fastest
     return synth.commensurate_q(shape.nq, shape.side)
+
+
+def kernel_algorithmic_flops(shape, nq, plan):
+    """Useful flop per evaluated configuration of the rho_q kernel that actually ran.
+    generic: SURVEY 8d convention.  lattice (DMMA or CUDA-core): per bead ND*(1 + 40) for the base phases, 6 per extra
+    power, 8 per (a>0,b>0) column product pair; per (group, bead) 2 flop per real sum K (8 in 3-D, 4 in 2-D, 2 in 1-D)."""
+    if plan["path"] == 0:
+        return algorithmic_flops(shape, nq)[0]
+    nd = shape.ndim
+    nmax = [plan["nmax_x"], plan["nmax_y"], plan["nmax_z"]][:nd]
+    per_bead = nd * 41 + 6 * sum(max(n - 1, 0) for n in nmax)
+    if nd == 3:
+        per_bead += 8 * max(0, (plan["L_rows"] - 1) // 4)            # rough: one X*Y / X*conj(Y) pair per 4 L rows
+    nk = {3: 8, 2: 4, 1: 2}[nd]
+    return shape.N * shape.M * (per_bead + 2 * nk * plan["groups"])
 
 
 def algorithmic_flops(shape, nq):
@@ -311,12 +328,14 @@ def run_ours(args, shape, q):
     corr_ms, corr_n = ktimes["corr"]
     bins_ms, _ = ktimes["bins"]
     rho_avg_s = rho_ms * 1e-3 / max(1, rho_n)
-    achieved = B * rho_flop / rho_avg_s / 1e12 if rho_n else None
+    plan = ctx.rho_plan_info()
+    kernel_flop = kernel_algorithmic_flops(shape, nq, plan)          # useful flop of the kernel that actually ran
+    achieved = B * kernel_flop / rho_avg_s / 1e12 if rho_n else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("rho_dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get(plan["path_name"] + "_dram_bytes_per_launch")
         except Exception:
             traffic = None
     peaks = {}
@@ -327,17 +346,75 @@ def run_ours(args, shape, q):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     alg_bytes = B * (8 * shape.ndim * shape.N * shape.M + 2 * 8 * nq * shape.M)
     roofline = {
-        "kernel": "rho_lattice_kernel" if (args.rho_mode != 0) else "rho_generic_kernel",
-        "bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+        "kernel": plan["path_name"],
+        "bound": "fp64" if plan["path"] != 1 else "fp64 (DFMA phase A + DMMA tensor phase B share the FP64 units)",
+        "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
         "frac": (achieved / peak_tflops) if achieved else None, "traffic": traffic,
         "peak_source": "measured in this run: register-resident DFMA chains on all SMs (pimcb_measure_fp64_peak); "
-                       "MEASURED_PEAKS.json has no FP64 figure",
-        "flop_per_launch": B * rho_flop, "avg_launch_ms": rho_avg_s * 1e3, "launches_timed": rho_n,
+                       "MEASURED_PEAKS.json has no FP64 figure (DMMA m8n8k4 measures 37.0 TFLOP/s, tools/micro/dmma_peak.cu)",
+        "flop_per_launch": B * kernel_flop, "flop_basis": "useful flop of the kernel that ran (DESIGN.md section 5)",
+        "avg_launch_ms": rho_avg_s * 1e3, "launches_timed": rho_n,
         "share_of_step": rho_ms / max(1e-12, rho_ms + corr_ms + bins_ms),
+        "plan": plan,
+        # the same launch expressed in SURVEY.md section 8d's convention (one 40-flop sincos per (q, bead)): what a
+        # generic kernel would have to sustain to finish in the same time
+        "survey_convention": {"flop_per_launch": B * rho_flop, "equivalent_tflops": B * rho_flop / rho_avg_s / 1e12 if rho_n else None},
         "hbm": {"achieved_gbs": alg_bytes / rho_avg_s / 1e9 if rho_n else None, "peak_gbs": hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"},
         "corr_kernel": {"avg_launch_ms": corr_ms / max(1, corr_n), "achieved_tflops": B * corr_flop / (corr_ms * 1e-3 / max(1, corr_n)) / 1e12 if corr_n else None},
     }
+    # ---- A/B: the generic kernel (one sincos per (q, bead)) on the same batches, SURVEY 8d flop convention --------
+    if plan["path"] != 0 and not args.no_ab:
+        ctx.set_rho_mode(0)
+        ctx.set_profiling(True)
+        for k in range(3):
+            device_step(k)
+        ctx.kernel_times(reset=True)
+        nab = max(5, min(K, 40))
+        for k in range(nab):
+            device_step(k)
+        kt0 = ctx.kernel_times(reset=True)
+        ctx.set_profiling(False)
+        ctx.set_rho_mode(1 if args.rho_mode < 0 else args.rho_mode)
+        g_s = kt0["rho"][0] * 1e-3 / max(1, kt0["rho"][1])
+        g_ach = B * rho_flop / g_s / 1e12
+        roofline["generic_kernel_ab"] = {"kernel": "rho_generic_kernel", "avg_launch_ms": g_s * 1e3, "launches_timed": kt0["rho"][1],
+                                         "flop_per_launch": B * rho_flop, "achieved": g_ach, "peak": peak_tflops,
+                                         "frac": g_ach / peak_tflops, "bound": "fp64",
+                                         "note": "not part of the timed region; same inputs, same outputs to rounding"}
+        ctx.reset_bins()
+
+    # ---- secondary metric: per-slice pair-potential sums (Vint, gradVSquared on odd slices, sepHist) -------------
+    pair = None
+    if shape.ndim == 3 and not args.no_pair:
+        import math
+        max_sep = math.sqrt(sum((L / 2.0) ** 2 for L in shape.side))
+        Vt, dVt, drt = synth.aziz_table_numpy(max_sep)
+        ctx.set_pair_table(Vt, dVt, drt)
+        ctx.select_slot(0)
+        dSep = 0.5 * math.sqrt(3.0) * shape.side[2] / 50.0
+        ctx.set_profiling(True)
+        for _ in range(2):
+            ctx.pair_sums(dSep, want_f2=True, want_hist=True, f2_parity=1)
+        ctx.kernel_times(reset=True)
+        npair = 5
+        for k in range(npair):
+            ctx.select_slot(k % use_slots)
+            ctx.pair_sums(dSep, want_f2=True, want_hist=True, f2_parity=1)
+        pms, pn = ctx.kernel_times(reset=True)["pair"]
+        ctx.set_profiling(False)
+        p_s = pms * 1e-3 / max(1, pn)
+        pairs = shape.N * (shape.N - 1) // 2               # pairs per slice
+        # gsf action: even slices read V once per pair; odd slices walk the full j != i loop (2 visits per pair, each
+        # reads dV/dr, half of them also read V): 3 table reads per pair
+        gathers = B * ((shape.M - shape.M // 2) * pairs + (shape.M // 2) * 3 * pairs)
+        pair = {"metric": "pair-potential action sums/s (Vint[M] + gradVSquared[odd slices] + sepHist[M][50] per configuration)",
+                "value": B / p_s, "unit": "configurations/s", "avg_launch_ms": p_s * 1e3, "launches_timed": pn,
+                "table_entries": len(Vt), "table_mb": 2 * 8 * len(Vt) / 1e6,
+                "gathers_per_launch": gathers, "gather_rate_g_per_s": gathers / p_s / 1e9,
+                "sector_traffic_tbs": 32.0 * gathers / p_s / 1e12,
+                "bound": "L2/HBM gather: 8-byte table reads move 32-byte sectors; the 106 MB of tables exceed what one L2 "
+                         "partition keeps, ncu shows 6.3 GB of DRAM reads per launch (profiles/traffic.json)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -351,7 +428,7 @@ def run_ours(args, shape, q):
                                    else f"q-vector sharding x{world} ({nq} of {len(q_all)} q per GPU), one NCCL all-gather of the bin"),
                    "l2": f"{use_slots} resident batches rotated ({footprint_mb:.0f} MB > 126 MB L2)",
                    "rho_mode": args.rho_mode},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "pair_sums": pair,
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

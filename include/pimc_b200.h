@@ -135,6 +135,10 @@ int pimcb_measure_fp64_peak(pimcb_ctx* ctx, double* tflops, double seconds_targe
  * [0]=rho_q build, [1]=tau-correlation, [2]=direct S(q), [3]=bin accumulate, [4]=pair sums, [5]=AoS->SoA transpose. */
 int pimcb_set_profiling(pimcb_ctx* ctx, int on);
 int pimcb_kernel_times(pimcb_ctx* ctx, double* ms_total /*[8]*/, long* count /*[8]*/, int reset);
+/* Description of the rho_q build the last measurement used, for flop accounting: info[12] = {path (0 generic
+ * sincos kernel, 1 DMMA lattice kernel, 2 CUDA-core lattice kernel), sign-symmetry groups, L rows, R cols, M tiles,
+ * N tiles, nmax_x, nmax_y, nmax_z, commensurate q, non-commensurate q, nq}. */
+int pimcb_rho_plan_info(const pimcb_ctx* ctx, int* info /*[12]*/);
 /* Number of kernel launches issued by this ctx since creation. */
 long pimcb_launch_count(const pimcb_ctx* ctx);
 

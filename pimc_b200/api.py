@@ -26,7 +26,7 @@ SYMBOLS = [
     "pimcb_host_unregister", "pimcb_ssf", "pimcb_isf", "pimcb_ssf_isf", "pimcb_measure", "pimcb_reset_bins",
     "pimcb_read_bins", "pimcb_bins_device_ptr", "pimcb_sync", "pimcb_stream", "pimcb_set_pair_table",
     "pimcb_pair_sums", "pimcb_measure_fp64_peak", "pimcb_set_profiling", "pimcb_kernel_times",
-    "pimcb_launch_count",
+    "pimcb_launch_count", "pimcb_rho_plan_info",
 ]
 
 
@@ -79,6 +79,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.pimcb_measure_fp64_peak.argtypes = [vp, _dp, C.c_double]
     lib.pimcb_set_profiling.argtypes = [vp, C.c_int]
     lib.pimcb_kernel_times.argtypes = [vp, _dp, C.POINTER(C.c_long), C.c_int]
+    lib.pimcb_rho_plan_info.argtypes = [vp, _ip]
     if path == _build.LIB:
         _lib = lib
     return lib
@@ -278,6 +279,15 @@ class Context:
         cnt = (C.c_long * 8)()
         self._chk(self.lib.pimcb_kernel_times(self._h, ms, cnt, int(reset)))
         return {k: (ms[i], cnt[i]) for i, k in enumerate(self.KERNELS)}
+
+    def rho_plan_info(self) -> dict:
+        v = (C.c_int * 12)()
+        self._chk(self.lib.pimcb_rho_plan_info(self._h, v))
+        keys = ("path", "groups", "L_rows", "R_cols", "M_tiles", "N_tiles", "nmax_x", "nmax_y", "nmax_z", "commensurate",
+                "non_commensurate", "nq")
+        d = dict(zip(keys, list(v)))
+        d["path_name"] = {0: "rho_generic_kernel", 1: "rho_lattice_mma_kernel", 2: "rho_lattice_kernel"}.get(d["path"], "none")
+        return d
 
     def launch_count(self) -> int:
         return self.lib.pimcb_launch_count(self._h)

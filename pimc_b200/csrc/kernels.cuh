@@ -379,14 +379,17 @@ __global__ void __launch_bounds__(32 * kLatticeWarps, PIMCB_LATTICE_MINB) rho_la
 //                R cols = {Re,Im}(Z^|c|) for every |c|;   2-D: L = {Re,Im} X^|a|, R = {Re,Im} Y^|b|;   1-D: L = 1, R = X^|a|.
 // The 8 (3-D) / 4 (2-D) / 2 (1-D) real sums K of a sign-symmetry group are entries of C (see phase C), and the
 // reduction over particles happens inside the tensor-core accumulation -- no shuffles, no per-particle FP64 issue
-// slots: one DMMA = 256 FMAs.  CTA = one (configuration, slice), 4 warps.  Particles are processed in chunks of
-// kMmaChunk: phase A (thread = particle) evaluates ND sincos, the power recurrences and the L/R planes straight
-// into shared memory (plane stride = chunk + 4 doubles, so the 8 rows of an A/B fragment fall into distinct
-// banks); phase B gives every warp a quarter of the chunk's particles and all MT x NT accumulator tiles;
-// phase C adds the four warps' partial tiles in fixed order and unfolds the sign patterns into rho.
+// slots: one DMMA = 256 FMAs.  A CTA (4 warps) works on one (configuration, slice) at a time; every warp owns a
+// quarter of the particles and PRIVATE operand planes, so the warps only meet once per slice:
+//   phase A (lane = particle, blocks of 32) evaluates ND sincos, the power recurrences and the L/R planes straight
+//           into the warp's shared-memory planes (stride 36 doubles: the 8 rows of a fragment fall into distinct banks);
+//   phase B 8 k-steps of MT x NT DMMAs on those planes (__syncwarp only, so one warp's tensor work overlaps another
+//           warp's FP64 phase A);
+//   phase C (CTA barrier) adds the four warps' partial tiles in fixed order and unfolds the sign patterns into rho.
 // ---------------------------------------------------------------------------------------------
-constexpr int kMmaChunk = 128;               // particles per chunk (4 warps x 8 k-steps x 4)
+constexpr int kMmaChunk = 32;                // particles per warp block (8 k-steps x 4)
 constexpr int kMmaStride = kMmaChunk + 4;    // plane stride in doubles: 32 B past a multiple of 128 B
+constexpr int kMmaWarps = 4;                 // warps per CTA, each with private operand planes
 
 struct MmaPlan {
     const int* gout;    // [G][2^ND]  q index per sign pattern or -1
@@ -420,16 +423,18 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
     constexpr int ntile = ML * NR;
     extern __shared__ __align__(16) double sm[];
     const int G = plan.G;
-    double* Lp = sm;                                        // [8*ML][kMmaStride]
-    double* Rp = Lp + 8 * ML * kMmaStride;                  // [8*NR][kMmaStride]
-    double* Cp = sm;                                        // [4 warps][ntile][64], aliases the planes after the last chunk
+    constexpr int region = 8 * (ML + NR) * kMmaStride;      // doubles of shared memory per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int il = threadIdx.x;                             // particle of the chunk this thread owns in phase A
-    const int nchunk = (N + kMmaChunk - 1) / kMmaChunk;
+    double* Lp = sm + warp * region;                        // [8*ML][kMmaStride]   this warp's L planes
+    double* Rp = Lp + 8 * ML * kMmaStride;                  // [8*NR][kMmaStride]   this warp's R planes
+    double* Cw = Lp;                                        // [ntile][64] C staging, aliases the planes after the last block
+    const int il = lane;                                    // particle of the block this lane owns in phase A
+    const int nchunk = (N + kMmaChunk - 1) / kMmaChunk;     // particle blocks of the slice; this warp takes warp, warp+4, ..
 
-    // padding rows / columns (planes phase A never writes) must not hold NaNs: cleared once per CTA
-    for (int w = (plan.nL - 1) * kMmaStride + threadIdx.x; w < 8 * ML * kMmaStride; w += blockDim.x) Lp[w] = 0.0;
-    for (int w = (plan.nR - 1) * kMmaStride + threadIdx.x; w < 8 * NR * kMmaStride; w += blockDim.x) Rp[w] = 0.0;
+    // the reserved zero plane and the padding rows / columns (never written by phase A) must be zero
+    for (int w = (plan.nL - 1) * kMmaStride + lane; w < 8 * ML * kMmaStride; w += 32) Lp[w] = 0.0;
+    for (int w = (plan.nR - 1) * kMmaStride + lane; w < 8 * NR * kMmaStride; w += 32) Rp[w] = 0.0;
+    __syncwarp();
 
     auto fetch = [&](int sl, int ch, double (&x)[3]) {
         const int i = ch * kMmaChunk + il;
@@ -442,7 +447,7 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
         }
     };
     double xn[3];
-    fetch(blockIdx.x, 0, xn);
+    fetch(blockIdx.x, warp, xn);
     for (int sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
         double acc[2][MT][NT][2];                           // two accumulator sets (even / odd k-steps) for DMMA ILP
 #pragma unroll
@@ -451,9 +456,9 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
             for (int m = 0; m < MT; ++m)
 #pragma unroll
                 for (int n = 0; n < NT; ++n) acc[e][m][n][0] = acc[e][m][n][1] = 0.0;
-        for (int ch = 0; ch < nchunk; ++ch) {
+        for (int ch = warp; ch < nchunk; ch += kMmaWarps) {
             const double xc[3] = {xn[0], xn[1], xn[2]};
-            if (ch + 1 < nchunk) fetch(sl, ch + 1, xn); else fetch(sl + gridDim.x, 0, xn);
+            if (ch + kMmaWarps < nchunk) fetch(sl, ch + kMmaWarps, xn); else fetch(sl + gridDim.x, warp, xn);
             // ---- phase A: thread = particle of the chunk -------------------------------------------------
             {
                 const bool live = ch * kMmaChunk + il < N;
@@ -577,14 +582,14 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                 }
                 }   // run-time loop bounds
             }
-            __syncthreads();
-            // ---- phase B: warp = quarter of the chunk, all tiles ---------------------------------------------
+            __syncwarp();
+            // ---- phase B: 8 k-steps over the warp's 32 particles, all tiles ------------------------------------
             {
                 const int frow = lane >> 2, fk = lane & 3;
-                const double* la = Lp + frow * kMmaStride + warp * (kMmaChunk / 4) + fk;
-                const double* rb = Rp + frow * kMmaStride + warp * (kMmaChunk / 4) + fk;
+                const double* la = Lp + frow * kMmaStride + fk;
+                const double* rb = Rp + frow * kMmaStride + fk;
 #pragma unroll
-                for (int ks = 0; ks < kMmaChunk / 16; ++ks) {
+                for (int ks = 0; ks < kMmaChunk / 4; ++ks) {
                     double a[MT], b[NT];
 #pragma unroll
                     for (int m = 0; m < MT; ++m) a[m] = la[m * 8 * kMmaStride + 4 * ks];
@@ -596,20 +601,20 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                         for (int n = 0; n < NT; ++n) dmma8x8x4(acc[ks & 1][m][n], a[m], b[n]);
                 }
             }
-            __syncthreads();
+            __syncwarp();
         }
         // ---- phase C: combine the warps' partial tiles, unfold sign patterns -------------------------------
 #pragma unroll
         for (int m = 0; m < MT; ++m)
 #pragma unroll
             for (int n = 0; n < NT; ++n) {
-                double2* d = reinterpret_cast<double2*>(Cp + (warp * ntile + m * NR + n) * 64) + lane;
+                double2* d = reinterpret_cast<double2*>(Cw + (m * NR + n) * 64) + lane;
                 *d = make_double2(acc[0][m][n][0] + acc[1][m][n][0], acc[0][m][n][1] + acc[1][m][n][1]);
             }
         __syncthreads();
         auto centry = [&](int row, int col) {
             const int off = ((row >> 3) * NR + (col >> 3)) * 64 + ((row & 7) * 4 + ((col & 7) >> 1)) * 2 + (col & 1);
-            return ((Cp[off] + Cp[ntile * 64 + off]) + Cp[2 * ntile * 64 + off]) + Cp[3 * ntile * 64 + off];
+            return ((sm[off] + sm[region + off]) + sm[2 * region + off]) + sm[3 * region + off];
         };
         for (int w = threadIdx.x; w < G * NPAT; w += blockDim.x) {
             const int g = w / NPAT, pat = w - g * NPAT;
@@ -638,11 +643,12 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
             rho[(static_cast<size_t>(sl) * 2 + 1) * nq + iq] = sa ? -im : im;
         }
         __syncthreads();
-        // Cp aliased the padding planes of L / R: restore them before the next slice's phase B reads them
+        // the C staging aliased the start of this warp's planes: re-zero whatever it covered of the zero / padding planes
         if (sl + gridDim.x < nslices) {
-            for (int w = (plan.nL - 1) * kMmaStride + threadIdx.x; w < 8 * ML * kMmaStride && w < 4 * ntile * 64; w += blockDim.x) Lp[w] = 0.0;
-            if (4 * ntile * 64 > 8 * ML * kMmaStride)
-                for (int w = (plan.nR - 1) * kMmaStride + threadIdx.x; w < 8 * NR * kMmaStride; w += blockDim.x) Rp[w] = 0.0;
+            for (int w = (plan.nL - 1) * kMmaStride + lane; w < 8 * ML * kMmaStride && w < ntile * 64; w += 32) Lp[w] = 0.0;
+            if (ntile * 64 > 8 * ML * kMmaStride)
+                for (int w = (plan.nR - 1) * kMmaStride + lane; w < 8 * NR * kMmaStride; w += 32) Rp[w] = 0.0;
+            __syncwarp();
         }
     }
 }
@@ -857,25 +863,26 @@ __global__ void ssf_direct_finalize_kernel(const double* __restrict__ partial, c
     cfg[b * cfg_stride + qidx[k]] = (static_cast<double>(M) * N + 2.0 * acc) / N;
 }
 
-// bins[j] += sum_b cfg[b][j].  Four adjacent lanes share one element j and sum a contiguous quarter of the
-// configurations each (b ascending); the quarters are combined in fixed order, so the result is deterministic.
+// bins[j] += sum_b cfg[b][j].  kBinLanes adjacent lanes share one element j and sum a contiguous slice of the
+// configurations each (b ascending, loads issued together); the slices are then combined by a fixed-order shuffle
+// tree, so the result is deterministic for a given batch size.
+constexpr int kBinLanes = 16;
 __global__ void __launch_bounds__(256) bins_accumulate_kernel(const double* __restrict__ cfg, double* __restrict__ bins, int B, size_t len) {
     const size_t gid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const size_t j = min(gid >> 2, len - 1);
-    const int part = static_cast<int>(gid & 3);
-    const int b0 = (B * part) / 4, b1 = (B * (part + 1)) / 4;
-    double a0 = 0.0, a1 = 0.0;
+    const size_t j = min(gid / kBinLanes, len - 1);
+    const int part = static_cast<int>(gid % kBinLanes);
+    const int b0 = (B * part) / kBinLanes, b1 = (B * (part + 1)) / kBinLanes;
+    double acc = 0.0;
     int b = b0;
-    for (; b + 1 < b1; b += 2) {
-        a0 += cfg[static_cast<size_t>(b) * len + j];
-        a1 += cfg[static_cast<size_t>(b + 1) * len + j];
+    for (; b + 3 < b1; b += 4) {
+        const double v0 = __ldg(cfg + static_cast<size_t>(b) * len + j), v1 = __ldg(cfg + static_cast<size_t>(b + 1) * len + j);
+        const double v2 = __ldg(cfg + static_cast<size_t>(b + 2) * len + j), v3 = __ldg(cfg + static_cast<size_t>(b + 3) * len + j);
+        acc += ((v0 + v1) + v2) + v3;
     }
-    if (b < b1) a0 += cfg[static_cast<size_t>(b) * len + j];
-    double acc = a0 + a1;
-    const double p1 = __shfl_down_sync(0xffffffffu, acc, 1);
-    const double p2 = __shfl_down_sync(0xffffffffu, acc, 2);
-    const double p3 = __shfl_down_sync(0xffffffffu, acc, 3);
-    if (part == 0 && (gid >> 2) < len) bins[j] += ((acc + p1) + p2) + p3;
+    for (; b < b1; ++b) acc += __ldg(cfg + static_cast<size_t>(b) * len + j);
+#pragma unroll
+    for (int o = 1; o < kBinLanes; o <<= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);   // lane 0 of the group: fixed tree
+    if (part == 0 && gid / kBinLanes < len) bins[j] += acc;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -102,6 +102,7 @@ struct pimcb_ctx {
     DevBuf d_q, d_comm, d_qn, d_qidx, d_plan;
     size_t plan_off[7] = {0, 0, 0, 0, 0, 0, 0};   // int offsets of gout / ent / tasks / warp_first / gdesc / lmap / rmap in d_plan
     int mma_nL = 0, mma_nR = 0;            // L rows / R cols of the DMMA formulation (0 = not available)
+    int last_rho_path = -1, last_ML = 0, last_NR = 0;   // what launch_rho used last: 0 generic, 1 DMMA lattice, 2 CUDA-core lattice
     std::vector<int> mma_lmap, mma_rmap;
     int lattice_J = 0;                     // 0 = choose from N; else forced (PIMCB_LATTICE_J)
     int lattice_warps = kLatticeWarps;     // warps per CTA of the lattice kernel (PIMCB_LATTICE_WARPS may lower it to 2)
@@ -225,7 +226,7 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
     const int ML = c->mma_nL > 0 ? ((NR <= 2 && mlx <= 8) ? mlx : up(mlx)) : 0;   // MT = 1..8 compiled exactly for NT <= 2
     const bool mma_fits = ML > 0 && NR > 0 && c->mma_nL <= 128 && NR <= 4 && ML * NR <= 16 &&
                           c->mma_lmap.size() <= 81 && c->mma_rmap.size() <= 17 && (nd < 3 || c->nmax[1] <= 8);
-    const size_t mma_smem = sizeof(double) * 8 * static_cast<size_t>(ML + NR) * kMmaStride;   // C staging aliases the planes
+    const size_t mma_smem = sizeof(double) * kMmaWarps * 8 * static_cast<size_t>(ML + NR) * kMmaStride;   // per-warp planes; C staging aliases them
     if (c->rho_mode == 1 && c->ngroups > 0 && mma_fits && mma_smem <= 160 * 1024) {
         const int3 nmax = make_int3(c->nmax[0], c->nmax[1], c->nmax[2]);
         const double twopi = 2.0 * M_PI;
@@ -239,6 +240,7 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
         for (short& v : plan.rmap) v = -1;
         for (size_t k = 0; k < c->mma_lmap.size(); ++k) plan.lmap[k] = static_cast<short>(c->mma_lmap[k]);
         for (size_t k = 0; k < c->mma_rmap.size(); ++k) plan.rmap[k] = static_cast<short>(c->mma_rmap[k]);
+        c->last_rho_path = 1; c->last_ML = ML; c->last_NR = NR;
         int pgrid = 0;
         const int nm3 = std::max(c->nmax[0], std::max(c->nmax[1], c->nmax[2]));
 #define LAUNCH_MMA_NM(ND, MT, NT, NM)                                                                             \
@@ -271,6 +273,7 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
         CU(cudaGetLastError());
         return 0;
     }
+    c->last_rho_path = lattice ? 2 : 0;
     if (!lattice) {
         const size_t fixed = sizeof(double) * nd * s.Npad;
         choose_split(nq, s.N, 256, fixed, sizeof(double) * 2, limit, &P, &chunk);
@@ -807,7 +810,7 @@ int pimcb_measure(pimcb_ctx* c) {
     {
         KTimer kt(c, K_BINS);
         const size_t len = c->bins_len;
-        bins_accumulate_kernel<<<static_cast<unsigned>((4 * len + 255) / 256), 256, 0, c->stream>>>(c->d_cfg.as<double>(), c->d_bins.as<double>(), s->B, len);
+        bins_accumulate_kernel<<<static_cast<unsigned>((kBinLanes * len + 255) / 256), 256, 0, c->stream>>>(c->d_cfg.as<double>(), c->d_bins.as<double>(), s->B, len);
         CU(cudaGetLastError());
     }
     c->n_acc += s->B;
@@ -977,5 +980,13 @@ int pimcb_kernel_times(pimcb_ctx* c, double* ms_total, long* count, int reset) {
 }
 
 long pimcb_launch_count(const pimcb_ctx* c) { return c ? c->launches : 0; }
+
+int pimcb_rho_plan_info(const pimcb_ctx* c, int* info) {
+    if (!c || !info) return fail(PIMCB_EINVAL, "null argument");
+    const int v[12] = {c->last_rho_path, c->ngroups, c->mma_nL, c->mma_nR, c->last_ML, c->last_NR,
+                       c->nmax[0], c->nmax[1], c->nmax[2], c->ncomm, c->nsel, c->nq};
+    for (int k = 0; k < 12; ++k) info[k] = v[k];
+    return 0;
+}
 
 }  // extern "C"
