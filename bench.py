@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=64, help="walker configurations per GPU per step")
     ap.add_argument("--workload", default="C2", choices=sorted(synth.SHAPES))
     ap.add_argument("--rho-mode", type=int, default=-1, help="-1 library default, 0 generic sincos, 1 lattice recurrence")
+    ap.add_argument("--corr-mode", type=int, default=-1, help="-1 library default, 0 CUDA-core tau-correlation, 1 DMMA")
     ap.add_argument("--shard", default="config", choices=["config", "q"],
                     help="multi-GPU axis: independent walker configurations (weak scaling, one reduce) or q-vectors "
                          "(strong scaling, every rank sees every configuration, one all-gather)")
@@ -233,6 +234,8 @@ def run_ours(args, shape, q):
     ctx.set_qvecs(q)
     if args.rho_mode >= 0:
         ctx.set_rho_mode(args.rho_mode)
+    if args.corr_mode >= 0:
+        ctx.set_corr_mode(args.corr_mode)
     nq = len(q)
 
     # synthetic batches: `unique` distinct configurations per slot, cycled to B, different seeds per rank and slot
@@ -427,7 +430,7 @@ def run_ours(args, shape, q):
                    "parallelism": (f"walker-configuration sharding x{world}, one NCCL reduce of the bin" if args.shard == "config"
                                    else f"q-vector sharding x{world} ({nq} of {len(q_all)} q per GPU), one NCCL all-gather of the bin"),
                    "l2": f"{use_slots} resident batches rotated ({footprint_mb:.0f} MB > 126 MB L2)",
-                   "rho_mode": args.rho_mode},
+                   "rho_mode": args.rho_mode, "corr_mode": args.corr_mode},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "pair_sums": pair,
     }
 

@@ -21,7 +21,7 @@ NPCFSEP = 50
 # every symbol include/pimc_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "pimcb_create", "pimcb_destroy", "pimcb_last_error", "pimcb_version", "pimcb_set_box", "pimcb_set_qvecs",
-    "pimcb_num_commensurate", "pimcb_set_rho_mode", "pimcb_stage_beads", "pimcb_stage_batch", "pimcb_num_slots",
+    "pimcb_num_commensurate", "pimcb_set_rho_mode", "pimcb_set_corr_mode", "pimcb_stage_beads", "pimcb_stage_batch", "pimcb_num_slots",
     "pimcb_stage_batch_slot", "pimcb_select_slot", "pimcb_host_alloc", "pimcb_host_free", "pimcb_host_register",
     "pimcb_host_unregister", "pimcb_ssf", "pimcb_isf", "pimcb_ssf_isf", "pimcb_measure", "pimcb_reset_bins",
     "pimcb_read_bins", "pimcb_bins_device_ptr", "pimcb_sync", "pimcb_stream", "pimcb_set_pair_table",
@@ -56,6 +56,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.pimcb_set_qvecs.argtypes = [vp, _dp, C.c_int]
     lib.pimcb_num_commensurate.argtypes = [vp]
     lib.pimcb_set_rho_mode.argtypes = [vp, C.c_int]
+    lib.pimcb_set_corr_mode.argtypes = [vp, C.c_int]
     lib.pimcb_stage_beads.argtypes = [vp, _dp, C.c_int, C.c_int, C.c_int]
     lib.pimcb_stage_batch.argtypes = [vp, _dp, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.pimcb_num_slots.argtypes = [vp]
@@ -169,6 +170,9 @@ class Context:
 
     def set_rho_mode(self, mode: int):
         self._chk(self.lib.pimcb_set_rho_mode(self._h, mode))
+
+    def set_corr_mode(self, mode: int):
+        self._chk(self.lib.pimcb_set_corr_mode(self._h, mode))
 
     # -- staging -----------------------------------------------------------------------------------
     @staticmethod

@@ -9,7 +9,8 @@
 //   rho_lattice_kernel   same for commensurate q = 2 pi n / L: phase-power tables + sign-symmetry groups,
 //                        lane = particle, warp = column of groups                       [FP64 / smem balanced]
 //   rho_lattice_mma_kernel  the same particle sums as a batched small GEMM on the FP64 tensor cores (DMMA)
-//   isf_corr_kernel      F(q,tau) = (1/N) sum_t0 Re[rho(t0) conj rho(t0+tau)], S(q) = F(q,0)
+//   isf_corr_mma_kernel  F(q,tau) = (1/N) sum_t0 Re[rho(t0) conj rho(t0+tau)], S(q) = F(q,0), as DMMA GEMMs (M <= 510)
+//   isf_corr_kernel      the same on the CUDA cores (register tiled; any M)
 //   ssf_direct_kernel    sum_{i<j} cos(q.minimage(r_i-r_j)) for non-commensurate q
 //   pair_kernel          per-slice Vint, sum_i |F_i|^2, separation histogram (table gathers)
 //   bins_accumulate_kernel, ssf_direct_finalize_kernel, aos_to_soa_kernel, fp64_peak_kernel
@@ -53,9 +54,9 @@ __constant__ double kSC[20] = {
     4.16666666666666019037e-02,    // [16]
     -0.5, 1.0, 0.0};
 
-__device__ __forceinline__ void sincos_fast(double x, double& s, double& c) {
+__device__ __forceinline__ void sincos_fast(double x, double& s, double& c, int& n) {
     const double t = fma(x, kSC[0], kSC[1]);
-    const int n = __double2loint(t);                     // quadrant = low bits of rint(x*2/pi)
+    n = __double2loint(t);                               // quadrant = low bits of rint(x*2/pi)
     const double kd = t - kSC[1];
     double r = fma(kd, kSC[2], x);
     r = fma(kd, kSC[3], r);
@@ -80,6 +81,10 @@ __device__ __forceinline__ void sincos_fast(double x, double& s, double& c) {
     const int chi = __double2hiint(cv) ^ (((n + 1) & 2) << 30);
     s = __hiloint2double(shi, __double2loint(sv));
     c = __hiloint2double(chi, __double2loint(cv));
+}
+__device__ __forceinline__ void sincos_fast(double x, double& s, double& c) {
+    int n;
+    sincos_fast(x, s, c, n);
 }
 
 // Coalesced load of one slice (ND rows of Npad doubles, contiguous, 16-byte aligned) into shared memory.
@@ -409,46 +414,85 @@ __device__ __forceinline__ void dmma8x8x4(double (&c)[2], double a, double b) {
                  : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-// Persistent CTAs (grid = SMs x resident CTAs, static stride over slices -- the work per slice is uniform): the
-// coordinates of the NEXT (slice, chunk) are fetched into registers while the current one is processed, so the HBM
-// latency of the only global read of the kernel is never exposed.
+// Persistent warps, each fully independent: a WARP owns a whole (configuration, slice) at a time -- all particle
+// blocks of the slice accumulate into the warp's register tiles, so there is no cross-warp reduction and no CTA
+// barrier after the prologue (the CTA-per-slice version of this kernel spent 10 % of its time at the two barriers of
+// phase C and serialised the unfold behind them).  Slices are handed out by a global ticket counter (`sched[0]`;
+// the last warp to retire re-arms it through `sched[1]`), which keeps the tail to one slice per warp.
+// The coordinates of the NEXT particle block are fetched into registers while the current one is processed.  The
+// prefetch address carries a (run-time zero) dependence on the quadrant integers of the current block's sincos:
+// without it ptxas issues the prefetch LDGs right before the first use of the current coordinates, on the same
+// scoreboard, and the "prefetch" waits for itself (21 % of all stall samples in profiles/r01j).
 // NM > 0 (3-D only): every |n_d| <= NM, the power recurrences and the (a,b) column loop are fully unrolled with the
 // powers held in registers; NM = 0: run-time loop bounds.
 template <int ND, int MT, int NT, int NM>
 __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __restrict__ pos, const MmaPlan plan,
                                                                double* __restrict__ rho, int nslices, int N, int Npad, int nq,
-                                                               int3 nmax, double3 kphase) {
+                                                               int3 nmax, double3 kphase, unsigned* __restrict__ sched,
+                                                               int zero_mask) {
     constexpr int NPAT = 1 << ND;
     constexpr int ML = MT, NR = NT;                         // every tile is computed; unused rows / cols are zero planes
     constexpr int ntile = ML * NR;
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) double sm[];
     const int G = plan.G;
-    constexpr int region = 8 * (ML + NR) * kMmaStride;      // doubles of shared memory per warp
+    constexpr int region = 8 * (ML + NR) * kMmaStride + ntile * 64;   // doubles of shared memory per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* Lp = sm + warp * region;                        // [8*ML][kMmaStride]   this warp's L planes
     double* Rp = Lp + 8 * ML * kMmaStride;                  // [8*NR][kMmaStride]   this warp's R planes
-    double* Cw = Lp;                                        // [ntile][64] C staging, aliases the planes after the last block
+    double* Cw = Rp + 8 * NR * kMmaStride;                  // [ntile][64]          this warp's C staging
+    int* s_gout = reinterpret_cast<int*>(sm + kMmaWarps * region);   // [G][NPAT]  CTA copy of the plan tables
+    int* s_gdesc = s_gout + ((G * NPAT + 3) & ~3);          // [G][8], 16-byte aligned
     const int il = lane;                                    // particle of the block this lane owns in phase A
-    const int nchunk = (N + kMmaChunk - 1) / kMmaChunk;     // particle blocks of the slice; this warp takes warp, warp+4, ..
+    const int nchunk = (N + kMmaChunk - 1) / kMmaChunk;     // particle blocks of a slice
 
+    for (int w = threadIdx.x; w < G * NPAT; w += blockDim.x) s_gout[w] = __ldg(plan.gout + w);
+    for (int w = threadIdx.x; w < G * 8; w += blockDim.x) s_gdesc[w] = __ldg(plan.gdesc + w);
     // the reserved zero plane and the padding rows / columns (never written by phase A) must be zero
     for (int w = (plan.nL - 1) * kMmaStride + lane; w < 8 * ML * kMmaStride; w += 32) Lp[w] = 0.0;
     for (int w = (plan.nR - 1) * kMmaStride + lane; w < 8 * NR * kMmaStride; w += 32) Rp[w] = 0.0;
-    __syncwarp();
+    __syncthreads();
 
-    auto fetch = [&](int sl, int ch, double (&x)[3]) {
+    // NM > 0: plane offsets of every (a,b) column / |c| power, resolved once (register resident) instead of a constant-bank
+    // lookup + multiply per particle block
+    int loff[NM > 0 ? (NM + 1) * (NM + 1) : 1], roff[NM > 0 ? NM + 1 : 1];
+    if constexpr (NM > 0) {
+#pragma unroll
+        for (int a = 0; a <= NM; ++a)
+#pragma unroll
+            for (int b = 0; b <= NM; ++b) {
+                const int row = plan.lmap[a * 9 + b];
+                loff[a * (NM + 1) + b] = row >= 0 ? row * kMmaStride + il : -1;
+            }
+#pragma unroll
+        for (int m = 0; m <= NM; ++m) {
+            const int col = plan.rmap[m];
+            roff[m] = col >= 0 ? col * kMmaStride + il : -1;
+        }
+    }
+    // plain atom (not atomicAdd: the compiler would warp-aggregate it and broadcast the result with a shuffle right
+    // away, stalling on the round trip); the ticket is only read when the current slice is nearly done
+    auto ticket_request = [&]() {
+        unsigned v = 0;
+        if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(v) : "l"(sched) : "memory");
+        return v;
+    };
+    auto fetch = [&](int sl, int ch, int dep, double (&x)[3]) {
         const int i = ch * kMmaChunk + il;
         x[0] = x[1] = x[2] = 0.0;
         if (sl < nslices && i < N) {
-            const double* ps = pos + static_cast<size_t>(sl) * ND * Npad + i;
+            const double* ps = pos + static_cast<size_t>(sl) * ND * Npad + (i + dep);
             x[0] = __ldg(ps);
             if constexpr (ND > 1) x[1] = __ldg(ps + Npad);
             if constexpr (ND > 2) x[2] = __ldg(ps + 2 * Npad);
         }
     };
     double xn[3];
-    fetch(blockIdx.x, warp, xn);
-    for (int sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
+    int sl = static_cast<int>(__shfl_sync(FULL, ticket_request(), 0));
+    fetch(sl, 0, 0, xn);
+    while (sl < nslices) {
+        const unsigned tk = ticket_request();               // next slice's ticket: requested now, read at the last block
+        int sl_next = nslices;
         double acc[2][MT][NT][2];                           // two accumulator sets (even / odd k-steps) for DMMA ILP
 #pragma unroll
         for (int e = 0; e < 2; ++e)
@@ -456,17 +500,22 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
             for (int m = 0; m < MT; ++m)
 #pragma unroll
                 for (int n = 0; n < NT; ++n) acc[e][m][n][0] = acc[e][m][n][1] = 0.0;
-        for (int ch = warp; ch < nchunk; ch += kMmaWarps) {
+        for (int ch = 0; ch < nchunk; ++ch) {
             const double xc[3] = {xn[0], xn[1], xn[2]};
-            if (ch + kMmaWarps < nchunk) fetch(sl, ch + kMmaWarps, xn); else fetch(sl + gridDim.x, warp, xn);
             // ---- phase A: thread = particle of the chunk -------------------------------------------------
             {
                 const bool live = ch * kMmaChunk + il < N;
                 const double lv = live ? 1.0 : 0.0;          // dead particles contribute zero rows (xc = 0 -> e = 1)
                 double ex_s, ex_c, ey_s = 0.0, ey_c = 1.0, ez_s = 0.0, ez_c = 1.0;
-                sincos_fast(kphase.x * xc[0], ex_s, ex_c);
-                if constexpr (ND > 1) sincos_fast(kphase.y * xc[1], ey_s, ey_c);
-                if constexpr (ND > 2) sincos_fast(kphase.z * xc[2], ez_s, ez_c);
+                int qx = 0, qy = 0, qz = 0;                  // quadrant integers: the prefetch below depends on them
+                sincos_fast(kphase.x * xc[0], ex_s, ex_c, qx);
+                if constexpr (ND > 1) sincos_fast(kphase.y * xc[1], ey_s, ey_c, qy);
+                if constexpr (ND > 2) sincos_fast(kphase.z * xc[2], ez_s, ez_c, qz);
+                {
+                    const int dep = (qx | qy | qz) & zero_mask;   // always 0, but only known at run time
+                    if (ch + 1 < nchunk) fetch(sl, ch + 1, dep, xn);
+                    else { sl_next = static_cast<int>(__shfl_sync(FULL, tk, 0)); fetch(sl_next, 0, dep, xn); }
+                }
                 if constexpr (ND == 3 && NM > 0) {
                     // compile-time bounds: powers of the three phases in registers, (a,b) columns unrolled
                     double xr[NM + 1], xi[NM + 1], yr[NM + 1], yi[NM + 1], zr = lv, zi = 0.0;
@@ -480,10 +529,9 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                     }
 #pragma unroll
                     for (int m = 0; m <= NM; ++m) {
-                        const int col = plan.rmap[m];
-                        if (col >= 0) {
-                            Rp[col * kMmaStride + il] = zr;
-                            if (m > 0) Rp[(col + 1) * kMmaStride + il] = zi;
+                        if (roff[m] >= 0) {
+                            Rp[roff[m]] = zr;
+                            if (m > 0) Rp[roff[m] + kMmaStride] = zi;
                         }
                         if (m < NM) {
                             const double nr = fma(zr, ez_c, -zi * ez_s);
@@ -495,9 +543,8 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                     for (int a = 0; a <= NM; ++a) {
 #pragma unroll
                         for (int b = 0; b <= NM; ++b) {
-                            const int row = plan.lmap[a * 9 + b];
-                            if (row >= 0) {
-                                double* d = Lp + row * kMmaStride + il;
+                            if (loff[a * (NM + 1) + b] >= 0) {
+                                double* d = Lp + loff[a * (NM + 1) + b];
                                 if (a > 0 && b > 0) {
                                     const double m1 = xr[a] * yr[b], m2 = xi[a] * yi[b], m3 = xr[a] * yi[b], m4 = xi[a] * yr[b];
                                     d[0] = m1 - m2;                   // Re X Y
@@ -603,7 +650,7 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
             }
             __syncwarp();
         }
-        // ---- phase C: combine the warps' partial tiles, unfold sign patterns -------------------------------
+        // ---- phase C (warp-local): stage the tiles, unfold the sign patterns into rho ---------------------------
 #pragma unroll
         for (int m = 0; m < MT; ++m)
 #pragma unroll
@@ -611,17 +658,16 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                 double2* d = reinterpret_cast<double2*>(Cw + (m * NR + n) * 64) + lane;
                 *d = make_double2(acc[0][m][n][0] + acc[1][m][n][0], acc[0][m][n][1] + acc[1][m][n][1]);
             }
-        __syncthreads();
+        __syncwarp();
         auto centry = [&](int row, int col) {
-            const int off = ((row >> 3) * NR + (col >> 3)) * 64 + ((row & 7) * 4 + ((col & 7) >> 1)) * 2 + (col & 1);
-            return ((sm[off] + sm[region + off]) + sm[2 * region + off]) + sm[3 * region + off];
+            return Cw[((row >> 3) * NR + (col >> 3)) * 64 + ((row & 7) * 4 + ((col & 7) >> 1)) * 2 + (col & 1)];
         };
-        for (int w = threadIdx.x; w < G * NPAT; w += blockDim.x) {
+        for (int w = lane; w < G * NPAT; w += 32) {
             const int g = w / NPAT, pat = w - g * NPAT;
-            const int iq = __ldg(plan.gout + w);
+            const int iq = s_gout[w];
             if (iq < 0) continue;
-            const int4 d0 = __ldg(reinterpret_cast<const int4*>(plan.gdesc) + 2 * g);
-            const int4 d1 = __ldg(reinterpret_cast<const int4*>(plan.gdesc) + 2 * g + 1);
+            const int4 d0 = reinterpret_cast<const int4*>(s_gdesc)[2 * g];
+            const int4 d1 = reinterpret_cast<const int4*>(s_gdesc)[2 * g + 1];
             const int sa = pat & 1;                                // conj of the pattern with all signs flipped
             const int sb = ND > 1 ? (((pat >> 1) & 1) ^ sa) : 0;
             const int sc = ND > 2 ? (((pat >> 2) & 1) ^ sa) : 0;
@@ -642,14 +688,14 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
             rho[(static_cast<size_t>(sl) * 2 + 0) * nq + iq] = re;
             rho[(static_cast<size_t>(sl) * 2 + 1) * nq + iq] = sa ? -im : im;
         }
-        __syncthreads();
-        // the C staging aliased the start of this warp's planes: re-zero whatever it covered of the zero / padding planes
-        if (sl + gridDim.x < nslices) {
-            for (int w = (plan.nL - 1) * kMmaStride + lane; w < 8 * ML * kMmaStride && w < ntile * 64; w += 32) Lp[w] = 0.0;
-            if (ntile * 64 > 8 * ML * kMmaStride)
-                for (int w = (plan.nR - 1) * kMmaStride + lane; w < 8 * NR * kMmaStride; w += 32) Rp[w] = 0.0;
-            __syncwarp();
-        }
+        __syncwarp();
+        sl = sl_next;
+    }
+    // re-arm the ticket counter for the next launch: every warp takes exactly one failing ticket before it retires
+    if (lane == 0) {
+        __threadfence();
+        const unsigned done = atomicAdd(sched + 1, 1u);
+        if (done == gridDim.x * kMmaWarps - 1) { sched[0] = 0u; sched[1] = 0u; }
     }
 }
 
@@ -780,6 +826,118 @@ __global__ void __launch_bounds__(128, 7) isf_corr_kernel(const double* __restri
         }
     }
     // odd M never occurs upstream (setup.cpp:1001-1008 forces M even); for odd M, tau = (M+1)/2.. mirror as well.
+}
+
+// ---------------------------------------------------------------------------------------------
+// tau-correlation on the FP64 tensor cores.  With tau = 8 i + j the circular correlation of a (config, q) pair is
+//        F[8 i + j] = sum_s a[(s - 8 i) mod M] * a[(s + j) mod M]         (a = C, then a = S, same accumulators)
+// i.e. D = A B with A[i][s] = a[s - 8 i], B[s][j] = a[s + j], contracted over s in [0, M): one DMMA m8n8k4 per four
+// s and per block of 64 tau.  One warp per pair, MTC = ceil((M/2 + 1) / 64) accumulator tiles.  The pair's C and S
+// are staged periodically extended (offset OFF = 64 MTC to the left) with 4 doubles of padding after every 8, which
+// puts the 8 rows of an A fragment (12 doubles apart) and the 11 consecutive elements of a B fragment in distinct banks.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int corrm_idx(int e) { return e + 4 * (e >> 3); }
+
+template <int MTC>
+__global__ void __launch_bounds__(128) isf_corr_mma_kernel(const double* __restrict__ rho, double* __restrict__ cfg, int M, int nq,
+                                                            int npairs, double invN, const unsigned char* __restrict__ commensurate) {
+    extern __shared__ __align__(16) double sm[];
+    constexpr int OFF = 64 * MTC;
+    constexpr int kRounds = 6;                               // t rounds (of 32 slices) whose loads are in flight together
+    const int Mpad = (M + 3) & ~3;
+    const int ext = OFF + Mpad + 8;                          // extended length in elements
+    const int plen = corrm_idx(ext) + 4;                     // padded doubles per array
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair0 = blockIdx.x * 4;                        // one pair per warp, 4 per CTA
+    {   // stage: thread = (pair lp, slice t mod 32); consecutive lanes read 4 consecutive q of one rho row (one 32-byte
+        // sector); every periodic image e = t + k M inside [-OFF, Mpad + 8) is written
+        const int lp = threadIdx.x & 3, t0 = threadIdx.x >> 2;
+        const int pair = pair0 + lp;
+        if (pair < npairs) {
+            const int b = pair / nq, iq = pair - b * nq;
+            const double* src = rho + (static_cast<size_t>(b) * M * 2) * nq + iq;
+            double* dc = sm + (2 * lp + 0) * plen;
+            double* ds = sm + (2 * lp + 1) * plen;
+            const int kneg = (OFF + M - 1) / M;              // images to the left of t
+            for (int tb = t0; tb < M; tb += 32 * kRounds) {
+                double c[kRounds], sn[kRounds];
+#pragma unroll
+                for (int u = 0; u < kRounds; ++u) {
+                    const int t = tb + 32 * u;
+                    if (t < M) {
+                        c[u] = __ldg(src + static_cast<size_t>(t) * 2 * nq);
+                        sn[u] = __ldg(src + (static_cast<size_t>(t) * 2 + 1) * nq);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kRounds; ++u) {
+                    const int t = tb + 32 * u;
+                    if (t < M)
+                        for (int e = t - kneg * M; e < Mpad + 8; e += M)
+                            if (e >= -OFF) { dc[corrm_idx(e + OFF)] = c[u]; ds[corrm_idx(e + OFF)] = sn[u]; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int pair = pair0 + warp;
+    if (pair >= npairs) return;
+    const int b = pair / nq, iq = pair - b * nq;
+    const int fi = lane >> 2, fk = lane & 3;                 // fragment row / k index of this lane
+    double acc[2][MTC][2];                                   // even / odd k-steps accumulate separately (DMMA ILP)
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int m = 0; m < MTC; ++m) acc[e][m][0] = acc[e][m][1] = 0.0;
+    // Operand addressing without per-element index arithmetic.  k-step ks covers s = 4 ks + fk; two k-steps advance the
+    // padded index by exactly 12, and OFF is a multiple of 8, so with h = ks >> 1
+    //     B[s][j = fi]           sits at  pb{0,1} + 12 h   (even / odd ks; the odd base absorbs the "+4" and any padding jump)
+    //     A[i = fi + 8 m][s]     sits at  pa + 12 h (+4 for odd ks) - 96 m   (fk + 4 never crosses a group of 8)
+    const int nfull = M >> 2;                                // k-steps with all four s < M
+    const int nks = Mpad >> 2;
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+        const double* E = sm + (2 * warp + part) * plen;
+        const double* pa = E + corrm_idx(fk - 8 * fi + OFF);
+        const double* pb0 = E + corrm_idx(fk + fi + OFF);
+        const double* pb1 = E + corrm_idx(4 + fk + fi + OFF);
+        const int hmax = nfull >> 1;
+#pragma unroll 2
+        for (int h = 0; h < hmax; ++h) {
+            const double bv0 = pb0[12 * h], bv1 = pb1[12 * h];
+            double av0[MTC], av1[MTC];
+#pragma unroll
+            for (int m = 0; m < MTC; ++m) { av0[m] = pa[12 * h - 96 * m]; av1[m] = pa[12 * h + 4 - 96 * m]; }
+#pragma unroll
+            for (int m = 0; m < MTC; ++m) dmma8x8x4(acc[0][m], av0[m], bv0);
+#pragma unroll
+            for (int m = 0; m < MTC; ++m) dmma8x8x4(acc[1][m], av1[m], bv1);
+        }
+        for (int ks = 2 * hmax; ks < nks; ++ks) {            // at most two: a full even k-step and / or the masked tail
+            const int h = ks >> 1, s = 4 * ks + fk;
+            const double bv = (ks & 1) ? pb1[12 * h] : pb0[12 * h];
+#pragma unroll
+            for (int m = 0; m < MTC; ++m) {
+                const double v = pa[12 * h + 4 * (ks & 1) - 96 * m];
+                const double vm = s < M ? v : 0.0;                // the contraction runs over s < M only
+                if (ks & 1) dmma8x8x4(acc[1][m], vm, bv); else dmma8x8x4(acc[0][m], vm, bv);
+            }
+        }
+    }
+    const size_t cfg_stride = static_cast<size_t>(nq) + static_cast<size_t>(nq) * M;
+    double* out = cfg + static_cast<size_t>(b) * cfg_stride + nq + static_cast<size_t>(iq) * M;
+    const int half = M / 2;
+#pragma unroll
+    for (int m = 0; m < MTC; ++m)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int tau = 64 * m + 8 * fi + 2 * fk + e;
+            if (tau > half) continue;
+            const double val = (acc[0][m][e] + acc[1][m][e]) * invN;
+            out[tau] = val;
+            if (tau > 0 && tau < M - tau) out[M - tau] = val;
+            if (tau == 0 && commensurate[iq]) cfg[static_cast<size_t>(b) * cfg_stride + iq] = val;
+        }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -107,6 +107,7 @@ struct pimcb_ctx {
     int lattice_J = 0;                     // 0 = choose from N; else forced (PIMCB_LATTICE_J)
     int lattice_warps = kLatticeWarps;     // warps per CTA of the lattice kernel (PIMCB_LATTICE_WARPS may lower it to 2)
     int rho_mode = 1;
+    int corr_mode = 1;                     // 1 = DMMA tau-correlation when M <= 510, 0 = CUDA-core kernel (PIMCB_CORR_MODE)
     // beads
     Slot slots[kSlots];
     int cur = -1;
@@ -133,6 +134,7 @@ struct pimcb_ctx {
     long k_count[kKernels] = {};
     long launches = 0;
     DevBuf d_scratch;
+    DevBuf d_sched;                        // ticket counter + retire counter of the persistent-warp rho kernel (self re-arming)
 };
 
 namespace {
@@ -226,7 +228,9 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
     const int ML = c->mma_nL > 0 ? ((NR <= 2 && mlx <= 8) ? mlx : up(mlx)) : 0;   // MT = 1..8 compiled exactly for NT <= 2
     const bool mma_fits = ML > 0 && NR > 0 && c->mma_nL <= 128 && NR <= 4 && ML * NR <= 16 &&
                           c->mma_lmap.size() <= 81 && c->mma_rmap.size() <= 17 && (nd < 3 || c->nmax[1] <= 8);
-    const size_t mma_smem = sizeof(double) * kMmaWarps * 8 * static_cast<size_t>(ML + NR) * kMmaStride;   // per-warp planes; C staging aliases them
+    const size_t mma_smem = sizeof(double) * kMmaWarps * (8 * static_cast<size_t>(ML + NR) * kMmaStride + static_cast<size_t>(ML) * NR * 64) +
+                            sizeof(int) * (((static_cast<size_t>(c->ngroups) << nd) + 3) / 4 * 4 + 8 * static_cast<size_t>(c->ngroups));
+                            // per-warp operand planes + C staging, CTA copy of the plan tables
     if (c->rho_mode == 1 && c->ngroups > 0 && mma_fits && mma_smem <= 160 * 1024) {
         const int3 nmax = make_int3(c->nmax[0], c->nmax[1], c->nmax[2]);
         const double twopi = 2.0 * M_PI;
@@ -247,9 +251,10 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
         { rc = set_smem(rho_lattice_mma_kernel<ND, MT, NT, NM>, mma_smem); if (rc) return rc;                      \
         int occ = 1;                                                                                               \
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rho_lattice_mma_kernel<ND, MT, NT, NM>, 128, mma_smem)); \
-        pgrid = std::max(1, std::min(nsl, c->sm_count * std::max(1, occ)));                                        \
+        pgrid = std::max(1, std::min((nsl + kMmaWarps - 1) / kMmaWarps, c->sm_count * std::max(1, occ)));          \
         rho_lattice_mma_kernel<ND, MT, NT, NM><<<pgrid, 128, mma_smem, c->stream>>>(s.pos.as<double>(), plan, c->d_rho.as<double>(), \
-                                                                                    nsl, s.N, s.Npad, nq, nmax, kph); }
+                                                                                    nsl, s.N, s.Npad, nq, nmax, kph,         \
+                                                                                    c->d_sched.as<unsigned>(), 0); }
         // 3-D with every |n_d| <= 2 (or 3): phase A fully unrolled; the R columns then fit one N tile
 #define LAUNCH_MMA(ND, MT, NT)                                                                                    \
         if (ND == 3 && NT == 1 && nm3 <= 2) LAUNCH_MMA_NM(ND, MT, NT, (ND == 3 && NT == 1 ? 2 : 0))                \
@@ -311,6 +316,22 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
 
 int launch_corr(pimcb_ctx* c, const Slot& s) {
     KTimer kt(c, K_CORR);
+    const int npairs_all = s.B * c->nq;
+    const int mtc = (s.M / 2 + 1 + 63) / 64;                      // 64-tau accumulator tiles of the DMMA formulation
+    if (c->corr_mode == 1 && mtc <= 4) {
+        const int off = 64 * mtc, mpad = (s.M + 3) & ~3, ext = off + mpad + 8;
+        const int plen = ext + 4 * (ext >> 3) + 4;
+        const size_t smem = sizeof(double) * 2 * static_cast<size_t>(plen) * 4;
+        int rc = 0;
+#define LAUNCH_CORR_MMA(MTC)                                                                                      \
+        rc = set_smem(isf_corr_mma_kernel<MTC>, smem); if (rc) return rc;                                          \
+        isf_corr_mma_kernel<MTC><<<(npairs_all + 3) / 4, 128, smem, c->stream>>>(c->d_rho.as<double>(), c->d_cfg.as<double>(), s.M, \
+                                                                                 c->nq, npairs_all, 1.0 / s.N, c->d_comm.as<unsigned char>())
+        if (mtc == 1) { LAUNCH_CORR_MMA(1); } else if (mtc == 2) { LAUNCH_CORR_MMA(2); } else if (mtc == 3) { LAUNCH_CORR_MMA(3); } else { LAUNCH_CORR_MMA(4); }
+#undef LAUNCH_CORR_MMA
+        CU(cudaGetLastError());
+        return 0;
+    }
     const int nblk = (s.M / 2 + 1 + 7) / 8;                       // tau blocks of 8 per (config, q) pair
     const int lpq = nblk <= 8 ? 8 : (nblk <= 16 ? 16 : 32);       // lanes owning the tau blocks of one pair
     const int tsplit = lpq <= 16 ? 2 : 1;                         // lane groups splitting the t0 range of the pair
@@ -480,6 +501,7 @@ int pimcb_create(pimcb_ctx** out, int device, int ndim) {
     c->device = device;
     c->ndim = ndim;
     if (const char* e = std::getenv("PIMCB_LATTICE_J")) c->lattice_J = std::atoi(e);
+    if (const char* e = std::getenv("PIMCB_CORR_MODE")) c->corr_mode = std::atoi(e) ? 1 : 0;
     if (const char* e = std::getenv("PIMCB_LATTICE_WARPS")) {
         const int w = std::atoi(e);
         if (w == 2 || w == 4) c->lattice_warps = w;
@@ -501,6 +523,8 @@ int pimcb_create(pimcb_ctx** out, int device, int ndim) {
         CU(cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming));
         CU(cudaEventRecord(p.done, c->copy_stream));
     }
+    if (int rc = c->d_sched.ensure(2 * sizeof(unsigned))) { pimcb_destroy(c); return rc; }
+    CU(cudaMemsetAsync(c->d_sched.p, 0, 2 * sizeof(unsigned), c->stream));
     *out = c;
     return 0;
 }
@@ -518,7 +542,7 @@ int pimcb_destroy(pimcb_ctx* c) {
     for (auto& p : c->pin) { p.release(); if (p.done) cudaEventDestroy(p.done); }
     c->h_out.release();
     for (DevBuf* b : {&c->d_q, &c->d_comm, &c->d_qn, &c->d_qidx, &c->d_plan, &c->d_aos, &c->d_rho, &c->d_cfg, &c->d_bins, &c->d_partial,
-                      &c->d_V, &c->d_dV, &c->d_vint, &c->d_f2, &c->d_hist, &c->d_scratch})
+                      &c->d_V, &c->d_dV, &c->d_vint, &c->d_f2, &c->d_hist, &c->d_scratch, &c->d_sched})
         b->release();
     for (int k = 0; k < kKernels; ++k) { cudaEventDestroy(c->ev0[k]); cudaEventDestroy(c->ev1[k]); }
     for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -752,6 +776,12 @@ int pimcb_num_commensurate(const pimcb_ctx* c) { return c ? c->ncomm : PIMCB_EIN
 int pimcb_set_rho_mode(pimcb_ctx* c, int mode) {
     if (!c || mode < 0 || mode > 2) return fail(PIMCB_EINVAL, "rho mode must be 0, 1 or 2");
     c->rho_mode = mode;
+    return 0;
+}
+
+int pimcb_set_corr_mode(pimcb_ctx* c, int mode) {
+    if (!c || mode < 0 || mode > 1) return fail(PIMCB_EINVAL, "corr mode must be 0 or 1");
+    c->corr_mode = mode;
     return 0;
 }
 

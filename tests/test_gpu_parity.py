@@ -127,6 +127,29 @@ def test_lattice_qsets(api, orc, ndim, nvec):
         assert_parity(isf[0], ref_f, f"qset isf mode {mode}")
 
 
+@pytest.mark.parametrize("M", [2, 4, 6, 14, 62, 126, 128, 130, 254, 258, 382, 386, 510, 512, 640])
+def test_tau_correlation_kernels(api, orc, M):
+    """Both tau-correlation kernels (1 = DMMA, up to M = 510 then falls back; 0 = CUDA cores) over time-slice counts
+    that straddle every 64-tau accumulator tile boundary of the DMMA formulation, two configurations per batch."""
+    N = 5
+    s = synth.Shape("corr", 3, N, M, 2.0, 0.02198, 0)
+    batch = np.stack([synth.gen_config(N, M, 3, s.rho, 2.0, seed=31 + b) for b in range(2)])
+    q = np.vstack([synth.commensurate_q(5, s.side, include_zero=True), synth.float_q(2, 3)])
+    out = {}
+    for mode in (0, 1):
+        with make_ctx(api, s, q) as ctx:
+            ctx.set_corr_mode(mode)
+            out[mode] = ctx.stage(batch, N).ssf_isf()
+    for b in range(2):
+        ref_f = orc.isf_factorised(batch[b], N, q)
+        ref_s = orc.ssf(s.side, batch[b], N, q)
+        for mode in (0, 1):
+            assert_parity(out[mode][1][b], ref_f, f"isf corr mode {mode} M={M}")
+            assert_parity(out[mode][0][b], ref_s, f"ssf corr mode {mode} M={M}")
+    if M <= 62:
+        assert_parity(out[1][1][0], orc.isf(batch[0], N, q, nthreads=4), f"isf direct M={M}")
+
+
 def test_batch_bins_and_slots(api, orc):
     """A walker batch: per-configuration outputs, device-resident bin accumulation, slot rotation."""
     s = synth.Shape("b", 3, 32, 16, 2.0, 0.02198, 0)
