@@ -470,11 +470,12 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
             roff[m] = col >= 0 ? col * kMmaStride + il : -1;
         }
     }
-    // plain atom (not atomicAdd: the compiler would warp-aggregate it and broadcast the result with a shuffle right
-    // away, stalling on the round trip); the ticket is only read when the current slice is nearly done
+    // requested at the start of a slice, needed at its last particle block.  (ptxas warp-aggregates every spelling of
+    // this add -- atom.add, atom.inc, run-time operand -- and broadcasts the result with a shuffle at once, so the warp
+    // does wait one atomic round trip per slice here: 3 % of the stall samples, covered by the other resident warps.)
     auto ticket_request = [&]() {
         unsigned v = 0;
-        if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(v) : "l"(sched) : "memory");
+        if (lane == 0) v = atomicAdd(sched, 1u);
         return v;
     };
     auto fetch = [&](int sl, int ch, int dep, double (&x)[3]) {
@@ -518,25 +519,24 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                 }
                 if constexpr (ND == 3 && NM > 0) {
                     // compile-time bounds: powers of the three phases in registers, (a,b) columns unrolled
-                    double xr[NM + 1], xi[NM + 1], yr[NM + 1], yi[NM + 1], zr = lv, zi = 0.0;
-                    xr[0] = lv; xi[0] = 0.0; yr[0] = 1.0; yi[0] = 0.0;
+                    // (every L row carries the live mask through X or explicitly, so the R planes need none)
+                    double xr[NM + 1], xi[NM + 1], yr[NM + 1], yi[NM + 1], zr[NM + 1], zi[NM + 1];
+                    xr[0] = lv; xi[0] = 0.0; yr[0] = 1.0; yi[0] = 0.0; zr[0] = 1.0; zi[0] = 0.0;
+                    xr[1] = lv * ex_c; xi[1] = lv * ex_s; yr[1] = ey_c; yi[1] = ey_s; zr[1] = ez_c; zi[1] = ez_s;   // no multiply by (1, 0)
 #pragma unroll
-                    for (int m = 1; m <= NM; ++m) {
+                    for (int m = 2; m <= NM; ++m) {
                         xr[m] = fma(xr[m - 1], ex_c, -xi[m - 1] * ex_s);
                         xi[m] = fma(xr[m - 1], ex_s, xi[m - 1] * ex_c);
                         yr[m] = fma(yr[m - 1], ey_c, -yi[m - 1] * ey_s);
                         yi[m] = fma(yr[m - 1], ey_s, yi[m - 1] * ey_c);
+                        zr[m] = fma(zr[m - 1], ez_c, -zi[m - 1] * ez_s);
+                        zi[m] = fma(zr[m - 1], ez_s, zi[m - 1] * ez_c);
                     }
 #pragma unroll
                     for (int m = 0; m <= NM; ++m) {
                         if (roff[m] >= 0) {
-                            Rp[roff[m]] = zr;
-                            if (m > 0) Rp[roff[m] + kMmaStride] = zi;
-                        }
-                        if (m < NM) {
-                            const double nr = fma(zr, ez_c, -zi * ez_s);
-                            zi = fma(zr, ez_s, zi * ez_c);
-                            zr = nr;
+                            Rp[roff[m]] = zr[m];
+                            if (m > 0) Rp[roff[m] + kMmaStride] = zi[m];
                         }
                     }
 #pragma unroll

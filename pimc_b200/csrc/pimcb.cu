@@ -251,6 +251,7 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
         { rc = set_smem(rho_lattice_mma_kernel<ND, MT, NT, NM>, mma_smem); if (rc) return rc;                      \
         int occ = 1;                                                                                               \
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rho_lattice_mma_kernel<ND, MT, NT, NM>, 128, mma_smem)); \
+        if (const char* e = std::getenv("PIMCB_RHO_OCC")) occ = std::max(1, std::min(occ, std::atoi(e)));          \
         pgrid = std::max(1, std::min((nsl + kMmaWarps - 1) / kMmaWarps, c->sm_count * std::max(1, occ)));          \
         rho_lattice_mma_kernel<ND, MT, NT, NM><<<pgrid, 128, mma_smem, c->stream>>>(s.pos.as<double>(), plan, c->d_rho.as<double>(), \
                                                                                     nsl, s.N, s.Npad, nq, nmax, kph,         \

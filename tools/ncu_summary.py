@@ -9,12 +9,16 @@ absolutes).  Per-kernel detail: one `--set full` capture per kernel (<tag>_prof_
 """
 import csv
 import glob
+import json
 import io
 import os
 import re
 import subprocess
 import sys
 from collections import OrderedDict
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import ncu_hot  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KEYS = [
@@ -23,6 +27,7 @@ KEYS = [
     "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active", "sm__cycles_active.avg",
     "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
     "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum", "smsp__inst_executed.sum",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
@@ -80,6 +85,7 @@ def main():
     os.makedirs(out, exist_ok=True)
     md = [f"# ncu summary `{tag}`", "",
           "Source: `tools/gpu_round.sh` on one B200 (`ncu --clock-control none`); numbers printed under ncu are never bench values.", ""]
+    traffic = {}
     la = launches(tag, out)
     if la:
         agg, total = la
@@ -93,11 +99,24 @@ def main():
         if not d:
             continue
         name = d.get("Kernel Name", ("?", ""))[0]
+        try:
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            rd, wr = d["dram__bytes_read.sum"], d["dram__bytes_write.sum"]
+            traffic[re.sub(r"<.*", "", short(name)) + "_dram_bytes_per_launch"] = float(rd[0]) * scale[rd[1]] + float(wr[0]) * scale[wr[1]]
+        except (KeyError, ValueError):
+            pass
         md += [f"## `{short(name)}`  ({os.path.basename(rep)}, --set full)", "", "| metric | value | unit |", "|---|---:|---|"]
         for k in KEYS:
             if k in d:
                 md.append(f"| {k} | {d[k][0]} | {d[k][1]} |")
         md.append("")
+        hot = ncu_hot.digest(rep)
+        if hot:
+            md += ["Hot spots (source page, SASS; `tools/ncu_hot.py`):", "", "```"] + hot + ["```", ""]
+    if traffic:
+        traffic["source"] = f"ncu --set full --clock-control none, one launch each, tools/gpu_round.sh {tag} (64 C2 configurations per launch)"
+        with open(os.path.join(out, "traffic.json"), "w") as f:
+            json.dump(traffic, f, indent=1)
     with open(os.path.join(out, f"{tag}_kernels.md"), "w") as f:
         f.write("\n".join(md) + "\n")
     print("\n".join(md))
