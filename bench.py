@@ -149,7 +149,7 @@ def run_reference(args, shape, q):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -262,10 +262,23 @@ def run_ours(args, shape, q):
         ctx.select_slot(k % use_slots)
         ctx.measure()
 
+    def bin_collective():
+        # the one collective of the path, once per bin (not per step), on the library's own device buffer
+        bins = multi.bins_tensor(ctx, torch.device("cuda", local))
+        with torch.cuda.stream(ext):
+            if args.shard == "config":
+                dist.reduce(bins, dst=0, op=dist.ReduceOp.SUM)            # sum of per-GPU bins over NVLink
+            else:
+                loc = torch.cat([bins[:nq, None], bins[nq:].view(nq, shape.M)], dim=1)
+                gathered = multi.gather_q_shards(loc, len(q_all))         # concatenate the q-shards
+                assert gathered.shape == (len(q_all), 1 + shape.M)
+
     # ---- value: device-resident --------------------------------------------------------------------------
     ctx.set_profiling(True)
     for k in range(W):
         device_step(k)
+    if world > 1:
+        bin_collective()       # warm-up of the collective too: NCCL connects its channels lazily on first use
     ctx.kernel_times(reset=True)
     ctx.reset_bins()
     launches0 = ctx.launch_count()
@@ -277,15 +290,7 @@ def run_ours(args, shape, q):
     for k in range(K):
         device_step(k)
     if world > 1:
-        # the one collective of the path, once per bin (not per step), on the library's own device buffer
-        bins = multi.bins_tensor(ctx, torch.device("cuda", local))
-        with torch.cuda.stream(ext):
-            if args.shard == "config":
-                dist.reduce(bins, dst=0, op=dist.ReduceOp.SUM)            # sum of per-GPU bins over NVLink
-            else:
-                loc = torch.cat([bins[:nq, None], bins[nq:].view(nq, shape.M)], dim=1)
-                gathered = multi.gather_q_shards(loc, len(q_all))         # concatenate the q-shards
-                assert gathered.shape == (len(q_all), 1 + shape.M)
+        bin_collective()
     e1.record(ext)
     barrier()
     clocks = sampler.stop()
@@ -324,6 +329,22 @@ def run_ours(args, shape, q):
         e2e = {"value": evals_per_step * Ke / float(dt.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(batch_bytes), "d2h_bytes_per_step": int((nq + nq * shape.M) * 8),
                "steps": Ke, "path": "pimcb_stage_batch(pinned host AoS) + pimcb_measure + pimcb_read_bins, double-buffered"}
+
+    # ---- latency: ONE configuration through the synchronous ABI calls an estimator's accumulate() makes ----------
+    latency = None
+    if not args.no_e2e:
+        one = np.ascontiguousarray(pinned[0].array[0])                   # pageable host copy, like Path::beads
+        ssf1, isf1 = ctx.stage(one, shape.N).ssf_isf()
+        for _ in range(5):
+            ctx.stage(one, shape.N).ssf_isf()
+        nlat = 50
+        t0 = time.perf_counter()
+        for _ in range(nlat):
+            ctx.stage(one, shape.N).ssf_isf()                             # pimcb_stage_beads + pimcb_ssf_isf (H2D, kernels, D2H, sync)
+        lat = (time.perf_counter() - t0) / nlat
+        latency = {"single_configuration_us": lat * 1e6, "evaluations_per_s": 1.0 / lat, "calls": nlat,
+                   "path": "pimcb_stage_beads(pageable host AoS) + pimcb_ssf_isf, synchronous, one walker"}
+        ctx.reset_bins()
 
     # ---- roofline of the dominant kernel (rho_q build) -------------------------------------------------------
     rho_flop, corr_flop = algorithmic_flops(shape, nq)
@@ -431,7 +452,7 @@ def run_ours(args, shape, q):
                                    else f"q-vector sharding x{world} ({nq} of {len(q_all)} q per GPU), one NCCL all-gather of the bin"),
                    "l2": f"{use_slots} resident batches rotated ({footprint_mb:.0f} MB > 126 MB L2)",
                    "rho_mode": args.rho_mode, "corr_mode": args.corr_mode},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "pair_sums": pair,
+        "clocks": clocks, "e2e": e2e, "latency": latency, "gpu_launches": int(launches), "roofline": roofline, "pair_sums": pair,
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -442,12 +463,34 @@ def run_ours(args, shape, q):
     else:
         line["cpu_baseline"] = None
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     for pa in pinned:
         pa.free()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Everything any library prints on fd 1 (NCCL's version banner, torchrun notices) goes to stderr; the JSON line is
+    written to the original stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -464,6 +507,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"), os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    claim_stdout()
     run_ours(args, shape, q)
 
 

@@ -429,7 +429,7 @@ template <int ND, int MT, int NT, int NM>
 __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __restrict__ pos, const MmaPlan plan,
                                                                double* __restrict__ rho, int nslices, int N, int Npad, int nq,
                                                                int3 nmax, double3 kphase, unsigned* __restrict__ sched,
-                                                               int zero_mask) {
+                                                               int zero_mask, int split, double* __restrict__ partial) {
     constexpr int NPAT = 1 << ND;
     constexpr int ML = MT, NR = NT;                         // every tile is computed; unused rows / cols are zero planes
     constexpr int ntile = ML * NR;
@@ -488,12 +488,16 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
             if constexpr (ND > 2) x[2] = __ldg(ps + 2 * Npad);
         }
     };
+    // Work item = (slice, part): `split` warps (anywhere on the GPU) share the particle blocks of a slice when there
+    // are too few slices to occupy every warp (small batches, one walker); part p takes blocks p, p + split, ...
+    const int nitems = nslices * split;
     double xn[3];
-    int sl = static_cast<int>(__shfl_sync(FULL, ticket_request(), 0));
-    fetch(sl, 0, 0, xn);
-    while (sl < nslices) {
-        const unsigned tk = ticket_request();               // next slice's ticket: requested now, read at the last block
-        int sl_next = nslices;
+    int item = static_cast<int>(__shfl_sync(FULL, ticket_request(), 0));
+    fetch(item < nitems ? item / split : nslices, item % split, 0, xn);
+    while (item < nitems) {
+        const int sl = item / split, part = item - sl * split;
+        const unsigned tk = ticket_request();               // next item's ticket: requested now, read at the last block
+        int item_next = nitems;
         double acc[2][MT][NT][2];                           // two accumulator sets (even / odd k-steps) for DMMA ILP
 #pragma unroll
         for (int e = 0; e < 2; ++e)
@@ -501,7 +505,7 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
             for (int m = 0; m < MT; ++m)
 #pragma unroll
                 for (int n = 0; n < NT; ++n) acc[e][m][n][0] = acc[e][m][n][1] = 0.0;
-        for (int ch = 0; ch < nchunk; ++ch) {
+        for (int ch = part; ch < nchunk; ch += split) {
             const double xc[3] = {xn[0], xn[1], xn[2]};
             // ---- phase A: thread = particle of the chunk -------------------------------------------------
             {
@@ -514,8 +518,11 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                 if constexpr (ND > 2) sincos_fast(kphase.z * xc[2], ez_s, ez_c, qz);
                 {
                     const int dep = (qx | qy | qz) & zero_mask;   // always 0, but only known at run time
-                    if (ch + 1 < nchunk) fetch(sl, ch + 1, dep, xn);
-                    else { sl_next = static_cast<int>(__shfl_sync(FULL, tk, 0)); fetch(sl_next, 0, dep, xn); }
+                    if (ch + split < nchunk) fetch(sl, ch + split, dep, xn);
+                    else {
+                        item_next = static_cast<int>(__shfl_sync(FULL, tk, 0));
+                        fetch(item_next < nitems ? item_next / split : nslices, item_next % split, dep, xn);
+                    }
                 }
                 if constexpr (ND == 3 && NM > 0) {
                     // compile-time bounds: powers of the three phases in registers, (a,b) columns unrolled
@@ -651,18 +658,52 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
             __syncwarp();
         }
         // ---- phase C (warp-local): stage the tiles, unfold the sign patterns into rho ---------------------------
+        bool unfold = true;
+        if (split > 1) {
+            // park this part's tiles in global scratch; the warp that completes the slice adds the parts in fixed order
+            // (deterministic) and unfolds.  slice_done[sl] is re-armed by that warp.
+            double2* mine = reinterpret_cast<double2*>(partial + (static_cast<size_t>(sl) * split + part) * (ntile * 64)) + lane;
 #pragma unroll
-        for (int m = 0; m < MT; ++m)
+            for (int m = 0; m < MT; ++m)
 #pragma unroll
-            for (int n = 0; n < NT; ++n) {
-                double2* d = reinterpret_cast<double2*>(Cw + (m * NR + n) * 64) + lane;
-                *d = make_double2(acc[0][m][n][0] + acc[1][m][n][0], acc[0][m][n][1] + acc[1][m][n][1]);
+                for (int n = 0; n < NT; ++n)
+                    __stcg(mine + (m * NR + n) * 32, make_double2(acc[0][m][n][0] + acc[1][m][n][0], acc[0][m][n][1] + acc[1][m][n][1]));
+            __threadfence();
+            __syncwarp();
+            unsigned prev = 0;
+            if (lane == 0) prev = atomicAdd(sched + 2 + sl, 1u);
+            prev = __shfl_sync(FULL, prev, 0);
+            unfold = prev == static_cast<unsigned>(split - 1);
+            if (unfold) {
+                __threadfence();
+                if (lane == 0) sched[2 + sl] = 0u;
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) {
+                        const double2* src = reinterpret_cast<const double2*>(partial + static_cast<size_t>(sl) * split * (ntile * 64)) + (m * NR + n) * 32 + lane;
+                        double2 t = __ldcg(src);
+                        for (int p = 1; p < split; ++p) {
+                            const double2 u = __ldcg(src + static_cast<size_t>(p) * (ntile * 32));
+                            t.x += u.x; t.y += u.y;
+                        }
+                        reinterpret_cast<double2*>(Cw + (m * NR + n) * 64)[lane] = t;
+                    }
             }
+        } else {
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    double2* d = reinterpret_cast<double2*>(Cw + (m * NR + n) * 64) + lane;
+                    *d = make_double2(acc[0][m][n][0] + acc[1][m][n][0], acc[0][m][n][1] + acc[1][m][n][1]);
+                }
+        }
         __syncwarp();
         auto centry = [&](int row, int col) {
             return Cw[((row >> 3) * NR + (col >> 3)) * 64 + ((row & 7) * 4 + ((col & 7) >> 1)) * 2 + (col & 1)];
         };
-        for (int w = lane; w < G * NPAT; w += 32) {
+        for (int w = lane; unfold && w < G * NPAT; w += 32) {
             const int g = w / NPAT, pat = w - g * NPAT;
             const int iq = s_gout[w];
             if (iq < 0) continue;
@@ -689,7 +730,7 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
             rho[(static_cast<size_t>(sl) * 2 + 1) * nq + iq] = sa ? -im : im;
         }
         __syncwarp();
-        sl = sl_next;
+        item = item_next;
     }
     // re-arm the ticket counter for the next launch: every warp takes exactly one failing ticket before it retires
     if (lane == 0) {

@@ -204,6 +204,17 @@ int need_cur(pimcb_ctx* c, Slot** s) {
     return 0;
 }
 
+// Scheduler words of the persistent-warp rho kernel: [0] ticket, [1] retired warps, [2 + slice] parts done (split > 1).
+// All of them are left at zero by the kernel itself; growing the buffer re-zeroes it on the compute stream.
+int ensure_sched(pimcb_ctx* c, size_t words) {
+    if (sizeof(unsigned) * words <= c->d_sched.cap) return 0;
+    CU(cudaStreamSynchronize(c->stream));
+    int rc = c->d_sched.ensure(sizeof(unsigned) * std::max<size_t>(words, 4096));
+    if (rc) return rc;
+    CU(cudaMemsetAsync(c->d_sched.p, 0, c->d_sched.cap, c->stream));
+    return 0;
+}
+
 // ---- rho_q build + correlation + direct S(q) into d_cfg (per configuration results) ------------
 int launch_rho(pimcb_ctx* c, const Slot& s) {
     const int nd = c->ndim, nq = c->nq;
@@ -246,16 +257,27 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
         for (size_t k = 0; k < c->mma_rmap.size(); ++k) plan.rmap[k] = static_cast<short>(c->mma_rmap[k]);
         c->last_rho_path = 1; c->last_ML = ML; c->last_NR = NR;
         int pgrid = 0;
+        const int nchunk = (s.N + kMmaChunk - 1) / kMmaChunk;      // 32-particle blocks per slice
         const int nm3 = std::max(c->nmax[0], std::max(c->nmax[1], c->nmax[2]));
 #define LAUNCH_MMA_NM(ND, MT, NT, NM)                                                                             \
         { rc = set_smem(rho_lattice_mma_kernel<ND, MT, NT, NM>, mma_smem); if (rc) return rc;                      \
         int occ = 1;                                                                                               \
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rho_lattice_mma_kernel<ND, MT, NT, NM>, 128, mma_smem)); \
         if (const char* e = std::getenv("PIMCB_RHO_OCC")) occ = std::max(1, std::min(occ, std::atoi(e)));          \
-        pgrid = std::max(1, std::min((nsl + kMmaWarps - 1) / kMmaWarps, c->sm_count * std::max(1, occ)));          \
+        const int wmax = c->sm_count * std::max(1, occ) * kMmaWarps;          /* resident warps of a full grid */   \
+        int split = 1;                                                         /* warps sharing one slice */         \
+        while (split < 8 && 2 * split <= nchunk && nsl * split < wmax) split *= 2;                                   \
+        if (const char* e = std::getenv("PIMCB_RHO_SPLIT")) split = std::max(1, std::min(nchunk, std::atoi(e)));   \
+        if (split > 1) {                                                                                           \
+            rc = c->d_partial.ensure(sizeof(double) * static_cast<size_t>(nsl) * split * (MT * NT * 64)); if (rc) return rc; \
+            rc = ensure_sched(c, 2 + static_cast<size_t>(nsl)); if (rc) return rc;                                 \
+        }                                                                                                          \
+        const int items = nsl * split;                                                                             \
+        pgrid = std::max(1, std::min((items + kMmaWarps - 1) / kMmaWarps, c->sm_count * std::max(1, occ)));        \
         rho_lattice_mma_kernel<ND, MT, NT, NM><<<pgrid, 128, mma_smem, c->stream>>>(s.pos.as<double>(), plan, c->d_rho.as<double>(), \
                                                                                     nsl, s.N, s.Npad, nq, nmax, kph,         \
-                                                                                    c->d_sched.as<unsigned>(), 0); }
+                                                                                    c->d_sched.as<unsigned>(), 0, split,     \
+                                                                                    c->d_partial.as<double>()); }
         // 3-D with every |n_d| <= 2 (or 3): phase A fully unrolled; the R columns then fit one N tile
 #define LAUNCH_MMA(ND, MT, NT)                                                                                    \
         if (ND == 3 && NT == 1 && nm3 <= 2) LAUNCH_MMA_NM(ND, MT, NT, (ND == 3 && NT == 1 ? 2 : 0))                \
@@ -524,8 +546,7 @@ int pimcb_create(pimcb_ctx** out, int device, int ndim) {
         CU(cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming));
         CU(cudaEventRecord(p.done, c->copy_stream));
     }
-    if (int rc = c->d_sched.ensure(2 * sizeof(unsigned))) { pimcb_destroy(c); return rc; }
-    CU(cudaMemsetAsync(c->d_sched.p, 0, 2 * sizeof(unsigned), c->stream));
+    if (int rc = ensure_sched(c, 2)) { pimcb_destroy(c); return rc; }
     *out = c;
     return 0;
 }

@@ -150,6 +150,24 @@ def test_tau_correlation_kernels(api, orc, M):
         assert_parity(out[1][1][0], orc.isf(batch[0], N, q, nthreads=4), f"isf direct M={M}")
 
 
+@pytest.mark.parametrize("split", [1, 2, 3, 5])
+def test_rho_split_slices(api, orc, split, monkeypatch):
+    """Persistent-warp rho kernel with `split` warps sharing every slice (partial tiles parked in global scratch, last
+    warp of a slice reduces in fixed order): same numbers for every split, launch after launch (self re-arming counters)."""
+    N, M = 150, 12                                     # 5 particle blocks per slice, the last one ragged
+    s = synth.Shape("split", 3, N, M, 2.0, 0.02198, 0)
+    batch = synth.gen_batch(s, 3)
+    q = synth.commensurate_q(20, s.side)
+    monkeypatch.setenv("PIMCB_RHO_SPLIT", str(split))
+    with make_ctx(api, s, q) as ctx:
+        first = ctx.stage(batch, N).ssf_isf()
+        again = ctx.stage(batch, N).ssf_isf()
+    assert np.array_equal(first[0], again[0]) and np.array_equal(first[1], again[1]), "deterministic across launches"
+    for b in range(3):
+        assert_parity(first[0][b], orc.ssf(s.side, batch[b], N, q), f"split {split} ssf")
+        assert_parity(first[1][b], orc.isf_factorised(batch[b], N, q), f"split {split} isf")
+
+
 def test_batch_bins_and_slots(api, orc):
     """A walker batch: per-configuration outputs, device-resident bin accumulation, slot rotation."""
     s = synth.Shape("b", 3, 32, 16, 2.0, 0.02198, 0)
