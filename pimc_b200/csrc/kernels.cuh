@@ -1,4 +1,4 @@
-// kernels.cuh -- sm_100a device code for the pimc measurement hot path (FP64, CUDA cores).
+// kernels.cuh -- sm_100a device code for the pimc measurement hot path (FP64: CUDA cores and DMMA tensor instructions).
 //
 // Device bead layout ("slice-major SoA"):  pos[b][t][d][Npad]  (double), Npad = N rounded up to 16,
 // so that the ND coordinate rows of one time slice are one contiguous, 128-byte aligned chunk that a
