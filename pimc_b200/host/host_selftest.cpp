@@ -4,6 +4,7 @@
 
 #include "aziz.h"
 #include "estimator_base.h"
+#include "state_file.h"
 
 class ProbeEstimator : public EstimatorBase {
 public:
@@ -22,7 +23,32 @@ public:
     }
 };
 
+// host_selftest --state <file> N density : parse a text state file and report what the loader would hold
+static int stateReport(const char* file, int N, double density) {
+    PimcState st;
+    std::string err;
+    if (!readStateFile(file, st, err)) { std::cout << "error=" << err << std::endl; return 1; }
+    Prism box(density, N);
+    std::cout.precision(17);
+    std::cout << "header=" << st.headerWorldLines << std::endl << "slices=" << st.numTimeSlices << std::endl
+              << "worldlines=" << st.numWorldLines << std::endl << "beadsOn=" << st.numBeadsOn() << std::endl
+              << "diagonal=" << st.isDiagonal() << std::endl << "leftPacked=" << st.isLeftPacked() << std::endl;
+    if (!st.isLeftPacked()) st.leftPack();
+    st.putInside(box);
+    std::cout << "perSlice=";
+    for (int n : st.numBeadsAtSlice) std::cout << n << " ";
+    std::cout << std::endl;
+    for (int s = 0; s < st.numTimeSlices; ++s)
+        for (int p = 0; p < st.numBeadsAtSlice[s]; ++p) {
+            std::cout << "bead=";
+            for (int d = 0; d < NDIM; ++d) std::cout << st.beads[st.idx(s, p)][d] << (d + 1 < NDIM ? " " : "");
+            std::cout << std::endl;
+        }
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc == 5 && std::string(argv[1]) == "--state") return stateReport(argv[2], std::atoi(argv[3]), std::atof(argv[4]));
     if (argc < 5) { std::cerr << "usage: host_selftest N density type \"wavevector\"" << std::endl; return 2; }
     const int N = std::atoi(argv[1]);
     Prism box(std::atof(argv[2]), N);

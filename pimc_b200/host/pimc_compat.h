@@ -26,6 +26,7 @@
 #endif
 #define NPCFSEP 50                  // include/common.h:85
 #define EPS 1.0E-7                  // include/common.h:89
+#define XXX -1                      // include/common.h:93 (nonsense bead index)
 
 typedef unsigned int uint32;
 typedef std::array<double, NDIM> dVec;      // include/common.h:104
@@ -63,6 +64,15 @@ public:
     double maxSep = 0.0, volume = 0.0;
     void putInBC(dVec& r) const {
         for (int i = 0; i < NDIM; ++i) r[i] -= pSide[i] * std::floor(r[i] * sideInv[i] + 0.5);
+    }
+    // Prism::putInside, include/container.h:118-135: periodic wrap, then clamp the non-periodic dimensions
+    void putInside(dVec& r) const {
+        putInBC(r);
+        for (int i = 0; i < NDIM; ++i)
+            if (!periodic[i]) {
+                if (r[i] >= 0.5 * side[i]) r[i] = 0.5 * side[i] - 2 * EPS;
+                if (r[i] < -0.5 * side[i]) r[i] = -0.5 * side[i] + 2 * EPS;
+            }
     }
 };
 

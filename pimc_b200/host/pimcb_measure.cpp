@@ -7,7 +7,9 @@
 //                 --configs beads.bin [--bin_size 100] [--outdir OUTPUT] [--id run] [--action gsf]
 //
 // `--configs` is a raw little-endian file of B configurations, each double[M][N_ext][NDIM] in the reference's bead
-// layout (N_ext given by --extent, default N).  With --potential the total potential action, per-slice Vint and
+// layout (N_ext given by --extent, default N).  `--state f1,f2,...` measures saved text state files
+// (OUTPUT/(g)ce-state-*.dat, state_file.h) instead: -N, -P and the extent are then taken from the first file, every
+// state must be diagonal with that many particles and slices, and the loader's putInside is applied (pimc.cpp:1258-1268).  With --potential the total potential action, per-slice Vint and
 // gradVSquared of every configuration are written to <outdir>/ce-potential-<id>.dat as well.
 #include <cstdio>
 #include <cstdlib>
@@ -17,6 +19,7 @@
 #include "action_b200.h"
 #include "aziz.h"
 #include "estimator_b200.h"
+#include "state_file.h"
 
 static const char* arg(int argc, char** argv, const char* key, const char* def) {
     for (int i = 1; i + 1 < argc; ++i)
@@ -30,16 +33,31 @@ static bool flag(int argc, char** argv, const char* key) {
 }
 
 int main(int argc, char** argv) {
-    const int N = std::atoi(arg(argc, argv, "-N", "16"));
+    std::vector<std::string> stateFiles;
+    if (const char* sf = arg(argc, argv, "--state", nullptr)) {
+        std::string all(sf), item;
+        for (size_t a = 0; a <= all.size(); ++a) {
+            if (a == all.size() || all[a] == ',') { if (!item.empty()) stateFiles.push_back(item); item.clear(); }
+            else item += all[a];
+        }
+    }
+    PimcState first;
+    if (!stateFiles.empty()) {
+        std::string err;
+        if (!readStateFile(stateFiles[0], first, err)) { std::cerr << stateFiles[0] << ": " << err << std::endl; return 1; }
+        if (!first.isDiagonal()) { std::cerr << stateFiles[0] << ": not a diagonal configuration" << std::endl; return 1; }
+    }
+    const bool fromStates = !stateFiles.empty();
+    const int N = fromStates ? first.numBeadsAtSlice[0] : std::atoi(arg(argc, argv, "-N", "16"));
     const double density = std::atof(arg(argc, argv, "-n", "0.02198"));
     const double T = std::atof(arg(argc, argv, "-T", "2.0"));
-    int M = std::atoi(arg(argc, argv, "-P", "0"));
+    int M = fromStates ? first.numTimeSlices : std::atoi(arg(argc, argv, "-P", "0"));
     double tau = std::atof(arg(argc, argv, "-t", "0.004"));
-    const int extent = std::atoi(arg(argc, argv, "--extent", arg(argc, argv, "-N", "16")));
+    const int extent = fromStates ? first.numWorldLines : std::atoi(arg(argc, argv, "--extent", arg(argc, argv, "-N", "16")));
     const int binSize = std::atoi(arg(argc, argv, "--bin_size", "100"));
     const std::string actionType = arg(argc, argv, "--action", "gsf");
     const char* cfgFile = arg(argc, argv, "--configs", nullptr);
-    if (!cfgFile) {
+    if (!cfgFile && !fromStates) {
         std::cerr << "usage: pimcb_measure -N n -n density -T temp (-P slices | -t tau) --wavevector_type T --wavevector \"...\" --configs file" << std::endl;
         return 2;
     }
@@ -91,11 +109,30 @@ int main(int argc, char** argv) {
         (*potOut) << "# potentialAction, then Vint[0..M-1], then gradVSquared[0..M-1] per configuration" << std::endl;
     }
 
-    FILE* f = std::fopen(cfgFile, "rb");
-    if (!f) { std::cerr << "cannot open " << cfgFile << std::endl; return 1; }
+    FILE* f = fromStates ? nullptr : std::fopen(cfgFile, "rb");
+    if (!fromStates && !f) { std::cerr << "cannot open " << cfgFile << std::endl; return 1; }
     const size_t count = static_cast<size_t>(M) * extent * NDIM;
     long nconf = 0;
-    while (std::fread(path.beads_data(), sizeof(double), count, f) == count) {
+    size_t nextState = 0;
+    // next configuration into path.beads: a raw record, or a parsed state file (left-packed, wrapped into the cell)
+    auto nextConfiguration = [&]() -> bool {
+        if (!fromStates) return std::fread(path.beads_data(), sizeof(double), count, f) == count;
+        if (nextState >= stateFiles.size()) return false;
+        PimcState st;
+        std::string err;
+        const std::string& name = stateFiles[nextState++];
+        if (!readStateFile(name, st, err)) { std::cerr << name << ": " << err << std::endl; std::exit(EXIT_FAILURE); }
+        if (!st.isDiagonal() || st.numTimeSlices != M || st.numBeadsAtSlice[0] != N || st.numWorldLines != extent) {
+            std::cerr << name << ": not a diagonal configuration of " << N << " particles x " << M << " slices (extent "
+                      << extent << ")" << std::endl;
+            std::exit(EXIT_FAILURE);
+        }
+        if (!st.isLeftPacked()) st.leftPack();
+        st.putInside(box);
+        std::memcpy(path.beads_data(), st.beads.data(), count * sizeof(double));
+        return true;
+    };
+    while (nextConfiguration()) {
         B200Session::newConfiguration(path);         // the per-step hook
         for (auto& e : estimators) e->sample();      // src/pimc.cpp:737-738
         ++nconf;
@@ -108,7 +145,7 @@ int main(int argc, char** argv) {
         if (estimators[0]->getNumAccumulated() >= static_cast<uint32>(binSize))     // src/pimc.cpp:743-749
             for (auto& e : estimators) e->output();
     }
-    std::fclose(f);
+    if (f) std::fclose(f);
     if (estimators[0]->getNumAccumulated() > 0)
         for (auto& e : estimators) e->output();
     std::cout << "pimcb_measure: " << nconf << " configurations, N=" << N << " M=" << M << " tau=" << tau << std::endl;

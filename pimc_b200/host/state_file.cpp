@@ -1,0 +1,128 @@
+#include "state_file.h"
+
+#include <fstream>
+#include <istream>
+#include <sstream>
+
+namespace {
+
+// "(r0,r1) x (c0,c1)" then everything up to '[' (include/common.h:306-372)
+bool readHeader(std::istream& is, int& rows, int& cols) {
+    int r0, r1, c0, c1;
+    char ch;
+    if (!(is >> ch) || ch != '(') return false;
+    if (!(is >> r0 >> ch) || ch != ',') return false;
+    if (!(is >> r1 >> ch) || ch != ')') return false;
+    if (!(is >> ch) || ch != 'x') return false;
+    if (!(is >> ch) || ch != '(') return false;
+    if (!(is >> c0 >> ch) || ch != ',') return false;
+    if (!(is >> c1 >> ch) || ch != ')') return false;
+    rows = r1 - r0 + 1;
+    cols = c1 - c0 + 1;
+    if (rows <= 0 || cols <= 0) return false;
+    while (is >> ch)
+        if (ch == '[') return true;
+    return false;
+}
+
+bool readFooter(std::istream& is) {
+    char ch;
+    while (is >> ch)
+        if (ch == ']') return true;
+    return false;
+}
+
+// "(a,b,...)" (include/common.h:270-300)
+template <class T, size_t K>
+bool readTuple(std::istream& is, std::array<T, K>& a) {
+    char ch;
+    if (!(is >> ch) || ch != '(') return false;
+    for (size_t i = 0; i < K; ++i) {
+        if (!(is >> a[i])) return false;
+        if (i + 1 < K && (!(is >> ch) || ch != ',')) return false;
+    }
+    return (is >> ch) && ch == ')';
+}
+
+template <class T, class Read>
+bool readArray(std::istream& is, int& rows, int& cols, std::vector<T>& out, Read readOne) {
+    if (!readHeader(is, rows, cols)) return false;
+    out.resize(static_cast<size_t>(rows) * cols);
+    for (auto& v : out)
+        if (!readOne(is, v)) return false;
+    return readFooter(is);
+}
+
+}  // namespace
+
+bool readStateText(std::istream& in, PimcState& st, std::string& err) {
+    st = PimcState();
+    if (!(in >> st.headerWorldLines)) { err = "missing world-line count on the first line"; return false; }
+    // skip the acceptance / estimator lines until a line starts with '(' (src/pimc.cpp:1136-1142)
+    std::string line;
+    std::getline(in, line);
+    while (in.good() && in.peek() != '(') std::getline(in, line);
+    if (!in.good()) { err = "no beads array found"; return false; }
+    int r = 0, c = 0;
+    if (!readArray(in, st.numTimeSlices, st.numWorldLines, st.beads,
+                   [](std::istream& is, dVec& v) { return readTuple(is, v); })) { err = "malformed beads array"; return false; }
+    if (!readArray(in, r, c, st.nextLink, [](std::istream& is, beadLocator& v) { return readTuple(is, v); }) ||
+        r != st.numTimeSlices || c != st.numWorldLines) { err = "malformed nextLink array"; return false; }
+    if (!readArray(in, r, c, st.prevLink, [](std::istream& is, beadLocator& v) { return readTuple(is, v); }) ||
+        r != st.numTimeSlices || c != st.numWorldLines) { err = "malformed prevLink array"; return false; }
+    if (!readArray(in, r, c, st.wormBeads, [](std::istream& is, unsigned& v) { return static_cast<bool>(is >> v); }) ||
+        r != st.numTimeSlices || c != st.numWorldLines) { err = "malformed worm.beads array"; return false; }
+    // empty beads are unlinked (src/pimc.cpp:1228-1239)
+    for (size_t k = 0; k < st.wormBeads.size(); ++k)
+        if (!st.wormBeads[k]) { st.nextLink[k] = {XXX, XXX}; st.prevLink[k] = {XXX, XXX}; }
+    st.numBeadsAtSlice.assign(st.numTimeSlices, 0);
+    for (int s = 0; s < st.numTimeSlices; ++s)
+        for (int p = 0; p < st.numWorldLines; ++p) st.numBeadsAtSlice[s] += st.wormBeads[st.idx(s, p)] ? 1 : 0;
+    return true;
+}
+
+bool readStateFile(const std::string& fileName, PimcState& st, std::string& err) {
+    std::ifstream f(fileName);
+    if (!f) { err = "cannot open " + fileName; return false; }
+    return readStateText(f, st, err);
+}
+
+int PimcState::numBeadsOn() const {
+    int n = 0;
+    for (unsigned b : wormBeads) n += b ? 1 : 0;
+    return n;
+}
+
+bool PimcState::isDiagonal() const {
+    if (numTimeSlices == 0) return false;
+    for (int s = 0; s < numTimeSlices; ++s)
+        if (numBeadsAtSlice[s] != numBeadsAtSlice[0]) return false;
+    for (size_t k = 0; k < wormBeads.size(); ++k)
+        if (wormBeads[k] && (nextLink[k][0] == XXX || nextLink[k][1] == XXX || prevLink[k][0] == XXX || prevLink[k][1] == XXX))
+            return false;
+    return true;
+}
+
+bool PimcState::isLeftPacked() const {
+    for (int s = 0; s < numTimeSlices; ++s)
+        for (int p = 0; p < numWorldLines; ++p)
+            if ((wormBeads[idx(s, p)] != 0) != (p < numBeadsAtSlice[s])) return false;
+    return true;
+}
+
+void PimcState::leftPack() {
+    for (int s = 0; s < numTimeSlices; ++s) {
+        int w = 0;
+        for (int p = 0; p < numWorldLines; ++p)
+            if (wormBeads[idx(s, p)]) {
+                if (w != p) { beads[idx(s, w)] = beads[idx(s, p)]; wormBeads[idx(s, w)] = 1; wormBeads[idx(s, p)] = 0; }
+                ++w;
+            }
+    }
+    nextLink.clear();
+    prevLink.clear();
+}
+
+void PimcState::putInside(const Container& box) {
+    for (auto& b : beads) box.putInside(b);
+}

@@ -79,6 +79,100 @@ def read_dat(path):
     return head, rows
 
 
+def state_report(host, ndim, fname, N, rho):
+    out = subprocess.run([os.path.join(host, f"pimcb_host_selftest{ndim}d"), "--state", str(fname), str(N), repr(rho)],
+                         check=True, capture_output=True, text=True).stdout
+    d = {}
+    for line in out.splitlines():
+        k, v = line.split("=", 1)
+        d.setdefault(k, []).append(v)
+    return d
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_state_file_parser_matches_format_restatement(host_bins, tmp_path, ndim):
+    """The C++ reader of the reference's text state files against the Python restatement of the writer/loader
+    (oracle/statefile.py): extents, active-bead bookkeeping, putInside, bit-identical coordinates, ragged (padded,
+    not left-packed, off-diagonal) files."""
+    from oracle import statefile
+    rho = {2: 0.0432, 3: 0.02198}[ndim]
+    N, M, W = 7, 6, 10
+    s = synth.Shape("st", ndim, N, M, 2.0, rho, 0)
+    rng = np.random.default_rng(5)
+    beads = rng.uniform(-1.7, 1.7, size=(M, W, ndim)) * s.side       # outside the cell on purpose: putInside must wrap
+    on = np.zeros((M, W), dtype=np.uint32)
+    on[:, :N] = 1
+    f1 = tmp_path / "ce-state-a.dat"
+    statefile.write_state(f1, beads, on)
+    rep = state_report(host_bins, ndim, f1, N, rho)
+    ref = statefile.read_state(f1, side=s.side)
+    assert rep["header"] == [str(N)] and rep["slices"] == [str(M)] and rep["worldlines"] == [str(W)]
+    assert rep["beadsOn"] == [str(N * M)] and rep["diagonal"] == ["1"] and rep["leftPacked"] == ["1"]
+    got = np.array([[float(x) for x in b.split()] for b in rep["bead"]]).reshape(M, N, ndim)
+    assert np.array_equal(got, ref["beads"][:, :N]), "strtod and float() must agree bit for bit after putInside"
+    assert np.all(np.abs(got) <= 0.5 * s.side + 1e-12)
+    # holes in the rows (not left-packed): same active beads, packed
+    on2 = np.zeros((M, W), dtype=np.uint32)
+    cols = [sorted(rng.choice(W, size=N, replace=False)) for _ in range(M)]
+    for t in range(M):
+        on2[t, cols[t]] = 1
+    f2 = tmp_path / "ce-state-b.dat"
+    statefile.write_state(f2, beads, on2)
+    rep = state_report(host_bins, ndim, f2, N, rho)
+    assert rep["leftPacked"] == ["0"] and rep["diagonal"] == ["1"]
+    got = np.array([[float(x) for x in b.split()] for b in rep["bead"]]).reshape(M, N, ndim)
+    ref = statefile.read_state(f2, side=s.side)
+    assert np.array_equal(got, np.stack([ref["beads"][t, cols[t]] for t in range(M)]))
+    # a worm (one bead missing on one slice) is not diagonal
+    on3 = on.copy()
+    on3[2, N - 1] = 0
+    f3 = tmp_path / "gce-state-c.dat"
+    statefile.write_state(f3, beads, on3)
+    rep = state_report(host_bins, ndim, f3, N, rho)
+    assert rep["diagonal"] == ["0"] and rep["perSlice"][0].split()[2] == str(N - 1)
+    # garbage
+    f4 = tmp_path / "bad.dat"
+    f4.write_text("12\n 1 2\n(0,1) x (0,1)\n[ (1,2 ]\n")
+    out = subprocess.run([os.path.join(host_bins, f"pimcb_host_selftest{ndim}d"), "--state", str(f4), "4", "0.02"],
+                         capture_output=True, text=True)
+    assert out.returncode == 1 and "error=" in out.stdout
+
+
+@pytest.mark.gpu
+def test_state_files_through_the_plugin_api(host_bins, orc, nthreads, tmp_path):
+    """Saved path configurations (text state files) re-measured by pimcb_measure --state against the oracle on the
+    same parsed positions."""
+    from oracle import statefile
+    s = synth.Shape("sf", 3, 12, 20, 2.0, 0.02198, 0)
+    W, nq, B = s.N + 4, 9, 3
+    batch = synth.gen_batch(s, B, pad=W - s.N)
+    batch[:, :, s.N:, :] = 1234.5                       # junk in the inactive columns
+    batch[:, :, :s.N, :] += s.side                      # one box length off: the loader wraps it back
+    files = []
+    for b in range(B):
+        on = np.zeros((s.M, W), dtype=np.uint32)
+        on[:, :s.N] = 1
+        f = tmp_path / f"ce-state-{b}.dat"
+        statefile.write_state(f, batch[b], on)
+        files.append(str(f))
+    text = synth.int_wavevector_text(nq, 3)
+    out = tmp_path / "OUTPUT"
+    subprocess.run([os.path.join(host_bins, "pimcb_measure3d"), "-n", repr(s.rho), "-T", repr(s.T), "--wavevector_type", "int",
+                    "--wavevector", text, "--state", ",".join(files), "--bin_size", "100", "--outdir", str(out), "--id", "s"],
+                   check=True)
+    q = orc.qvectors("int", text, s.side)
+    parsed = [statefile.read_state(f, side=s.side)["beads"] for f in files]
+    ssf = np.array([orc.ssf(s.side, p, s.N, q) for p in parsed]).sum(axis=0)
+    isf = np.array([orc.isf(p, s.N, q, nthreads=nthreads).reshape(-1) for p in parsed]).sum(axis=0)
+    _, rows = read_dat(out / "ce-ssfq-s.dat")
+    assert len(rows) == 1
+    got = np.array([float(rows[0][16 * k:16 * k + 16]) for k in range(nq)])
+    np.testing.assert_allclose(got, ssf / (s.M * B), rtol=2e-8)
+    _, rows = read_dat(out / "ce-isf-s.dat")
+    got = np.array([float(rows[0][16 * k:16 * k + 16]) for k in range(nq * s.M)])
+    np.testing.assert_allclose(got, isf / (s.M * B), rtol=2e-8, atol=1e-8)
+
+
 @pytest.mark.gpu
 def test_plugin_api_drop_in_files(host_bins, orc, nthreads, tmp_path):
     """C1 through the factory-created estimators: headers, column order, normalisation and %16.8E rows of
