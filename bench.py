@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument("--workload", default="C2", choices=sorted(synth.SHAPES))
     ap.add_argument("--rho-mode", type=int, default=-1, help="-1 library default, 0 generic sincos, 1 lattice recurrence")
     ap.add_argument("--corr-mode", type=int, default=-1, help="-1 library default, 0 CUDA-core tau-correlation, 1 DMMA")
+    ap.add_argument("--profile", default="rho", help="kernels timed with events INSIDE the timed region: all | rho | none")
+    ap.add_argument("--profile-stride", type=int, default=8, help="bracket every n-th launch of a profiled kernel")
     ap.add_argument("--shard", default="config", choices=["config", "q"],
                     help="multi-GPU axis: independent walker configurations (weak scaling, one reduce) or q-vectors "
                          "(strong scaling, every rank sees every configuration, one all-gather)")
@@ -274,7 +276,10 @@ def run_ours(args, shape, q):
                 assert gathered.shape == (len(q_all), 1 + shape.M)
 
     # ---- value: device-resident --------------------------------------------------------------------------
-    ctx.set_profiling(True)
+    # events bracket the dominant kernel (rho_q build) on every launch of the timed region; the two small kernels are
+    # timed in a separate pass below (an event between two kernels breaks their back-to-back staging)
+    ctx.set_profiling({"all": True, "none": False}.get(args.profile, ["rho"]))
+    ctx.set_profiling_stride(args.profile_stride)        # every 8th launch: an event pair costs ~3 us of stream time
     for k in range(W):
         device_step(k)
     if world > 1:
@@ -301,10 +306,22 @@ def run_ours(args, shape, q):
     launches = ctx.launch_count() - launches0
     ktimes = ctx.kernel_times(reset=True)
     ctx.set_profiling(False)
+    ctx.set_profiling_stride(1)
     evals_per_step = world * B if args.shard == "config" else B    # q-sharding: all ranks work on the same B walkers
     value = evals_per_step * K / (ms_total * 1e-3)
     _, _, n_acc = ctx.read_bins()
     assert n_acc == B * K, (n_acc, B, K)
+    if args.profile != "all":                      # untimed-region pass with every kernel bracketed: corr / bins durations
+        ctx.set_profiling(True)
+        for k in range(max(10, min(K, 50))):
+            device_step(k)
+        kall = ctx.kernel_times(reset=True)
+        for name in ("corr", "bins"):
+            ktimes[name] = kall[name]
+        if args.profile == "none":
+            ktimes["rho"] = kall["rho"]
+        ctx.reset_bins()
+        ctx.set_profiling(False)
 
     # ---- e2e: host AoS buffers through the C ABI, H2D + D2H inside the timed region -------------------------
     e2e = None
@@ -378,7 +395,9 @@ def run_ours(args, shape, q):
                        "MEASURED_PEAKS.json has no FP64 figure (DMMA m8n8k4 measures 37.0 TFLOP/s, tools/micro/dmma_peak.cu)",
         "flop_per_launch": B * kernel_flop, "flop_basis": "useful flop of the kernel that ran (DESIGN.md section 5)",
         "avg_launch_ms": rho_avg_s * 1e3, "launches_timed": rho_n,
-        "share_of_step": rho_ms / max(1e-12, rho_ms + corr_ms + bins_ms),
+        "timing": f"CUDA events around every {args.profile_stride}-th launch of this kernel inside the timed region ({rho_n} of {K} steps)",
+        "share_of_step": rho_avg_s * 1e3 / max(1e-12, rho_avg_s * 1e3 + corr_ms / max(1, corr_n) + bins_ms / max(1, ktimes["bins"][1])),
+        "bins_kernel": {"avg_launch_ms": bins_ms / max(1, ktimes["bins"][1])},
         "plan": plan,
         # the same launch expressed in SURVEY.md section 8d's convention (one 40-flop sincos per (q, bead)): what a
         # generic kernel would have to sustain to finish in the same time

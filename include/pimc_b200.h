@@ -135,8 +135,13 @@ int pimcb_measure_fp64_peak(pimcb_ctx* ctx, double* tflops, double seconds_targe
 /* Per-kernel device time.  With profiling on, every kernel launch is bracketed by CUDA events on the stream it is
  * launched on; pimcb_kernel_times synchronises, folds the pending event pairs into running totals and returns, per
  * kernel id, the summed duration in ms and the number of launches since the last reset:
- * [0]=rho_q build, [1]=tau-correlation, [2]=direct S(q), [3]=bin accumulate, [4]=pair sums, [5]=AoS->SoA transpose. */
+ * [0]=rho_q build, [1]=tau-correlation, [2]=direct S(q), [3]=bin accumulate, [4]=pair sums, [5]=AoS->SoA transpose.
+ * `on`: 0 = off, 1 = every kernel, otherwise a mask with bit (id + 1) set for each kernel id to time (an event
+ * between two kernels keeps the second from being staged behind the first, so timing all of them costs ~10 % of a
+ * step; the bench times only the dominant kernel inside its timed region). */
 int pimcb_set_profiling(pimcb_ctx* ctx, int on);
+/* Bracket only every `stride`-th launch of each profiled kernel (default 1 = every launch). */
+int pimcb_set_profiling_stride(pimcb_ctx* ctx, int stride);
 int pimcb_kernel_times(pimcb_ctx* ctx, double* ms_total /*[8]*/, long* count /*[8]*/, int reset);
 /* Description of the rho_q build the last measurement used, for flop accounting: info[12] = {path (0 generic
  * sincos kernel, 1 DMMA lattice kernel, 2 CUDA-core lattice kernel), sign-symmetry groups, L rows, R cols, M tiles,

@@ -25,7 +25,7 @@ SYMBOLS = [
     "pimcb_stage_batch_slot", "pimcb_select_slot", "pimcb_host_alloc", "pimcb_host_free", "pimcb_host_register",
     "pimcb_host_unregister", "pimcb_ssf", "pimcb_isf", "pimcb_ssf_isf", "pimcb_measure", "pimcb_reset_bins",
     "pimcb_read_bins", "pimcb_bins_device_ptr", "pimcb_sync", "pimcb_stream", "pimcb_set_pair_table",
-    "pimcb_pair_sums", "pimcb_measure_fp64_peak", "pimcb_set_profiling", "pimcb_kernel_times",
+    "pimcb_pair_sums", "pimcb_measure_fp64_peak", "pimcb_set_profiling", "pimcb_set_profiling_stride", "pimcb_kernel_times",
     "pimcb_launch_count", "pimcb_rho_plan_info",
 ]
 
@@ -79,6 +79,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.pimcb_pair_sums.argtypes = [vp, _dp, _dp, _ip, C.c_double, C.c_int]
     lib.pimcb_measure_fp64_peak.argtypes = [vp, _dp, C.c_double]
     lib.pimcb_set_profiling.argtypes = [vp, C.c_int]
+    lib.pimcb_set_profiling_stride.argtypes = [vp, C.c_int]
     lib.pimcb_kernel_times.argtypes = [vp, _dp, C.POINTER(C.c_long), C.c_int]
     lib.pimcb_rho_plan_info.argtypes = [vp, _ip]
     if path == _build.LIB:
@@ -274,8 +275,18 @@ class Context:
         self._chk(self.lib.pimcb_measure_fp64_peak(self._h, C.byref(v), seconds))
         return v.value
 
-    def set_profiling(self, on: bool):
-        self._chk(self.lib.pimcb_set_profiling(self._h, int(on)))
+    KERNEL_IDS = {"rho": 0, "corr": 1, "direct": 2, "bins": 3, "pair": 4, "transpose": 5}
+
+    def set_profiling(self, on):
+        """False / True (every kernel) or an iterable of kernel names to time."""
+        if isinstance(on, (bool, int)):
+            mode = int(bool(on))
+        else:
+            mode = sum(1 << (self.KERNEL_IDS[k] + 1) for k in on)
+        self._chk(self.lib.pimcb_set_profiling(self._h, mode))
+
+    def set_profiling_stride(self, stride: int):
+        self._chk(self.lib.pimcb_set_profiling_stride(self._h, int(stride)))
 
     def kernel_times(self, reset: bool = True) -> dict:
         """{kernel: (total_ms, launches)} since the last reset (needs set_profiling(True))."""

@@ -87,6 +87,14 @@ __device__ __forceinline__ void sincos_fast(double x, double& s, double& c) {
     sincos_fast(x, s, c, n);
 }
 
+// rho_q layout ("pair-major"): rho[((b * nq + q) * 2 + {cos,sin}) * Ms + t], Ms = M rounded up to even -- the M values
+// of one (configuration, q) pair are contiguous, which is what the tau-correlation reads; the rho kernels write one
+// 8-byte element per (q, part) and slice, neighbouring slices complete the 32-byte sectors in L2.
+__host__ __device__ inline int rho_row_stride(int M) { return (M + 1) & ~1; }
+__device__ __forceinline__ size_t rho_row(int b, int iq, int cs, int nq, int Ms) {
+    return ((static_cast<size_t>(b) * nq + iq) * 2 + cs) * Ms;
+}
+
 // Coalesced load of one slice (ND rows of Npad doubles, contiguous, 16-byte aligned) into shared memory.
 __device__ __forceinline__ void load_slice(double* __restrict__ sm, const double* __restrict__ src, int count) {
     const double2* s2 = reinterpret_cast<const double2*>(src);
@@ -103,12 +111,14 @@ __device__ __forceinline__ void load_slice(double* __restrict__ sm, const double
 template <int ND>
 __global__ void __launch_bounds__(256) rho_generic_kernel(const double* __restrict__ pos, const double* __restrict__ qsoa,
                                                            double* __restrict__ rho, int nslices, int N, int Npad, int nq,
-                                                           int P, int chunk) {
+                                                           int P, int chunk, int M) {
     extern __shared__ __align__(16) double sm[];
     double* xs = sm;                          // [ND][Npad]
     double* part = sm + ND * Npad;            // [2][P][nq]  (only when P > 1)
     const int items = nq * P;
+    const int Ms = rho_row_stride(M);
     for (int sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
+        const int cb = sl / M, ct = sl - cb * M;      // configuration and time slice of this CTA's work item
         load_slice(xs, pos + static_cast<size_t>(sl) * ND * Npad, ND * Npad);
         __syncthreads();
         for (int item = threadIdx.x; item < items; item += blockDim.x) {
@@ -131,8 +141,8 @@ __global__ void __launch_bounds__(256) rho_generic_kernel(const double* __restri
                 as += s;
             }
             if (P == 1) {
-                rho[(static_cast<size_t>(sl) * 2 + 0) * nq + iq] = ac;
-                rho[(static_cast<size_t>(sl) * 2 + 1) * nq + iq] = as;
+                rho[rho_row(cb, iq, 0, nq, Ms) + ct] = ac;
+                rho[rho_row(cb, iq, 1, nq, Ms) + ct] = as;
             } else {
                 part[p * nq + iq] = ac;
                 part[(P + p) * nq + iq] = as;
@@ -144,7 +154,7 @@ __global__ void __launch_bounds__(256) rho_generic_kernel(const double* __restri
                 const int cs = k / nq, iq = k - cs * nq;
                 double acc = 0.0;
                 for (int p = 0; p < P; ++p) acc += part[(cs * P + p) * nq + iq];   // fixed order: deterministic
-                rho[(static_cast<size_t>(sl) * 2 + cs) * nq + iq] = acc;
+                rho[rho_row(cb, iq, cs, nq, Ms) + ct] = acc;
             }
         }
         __syncthreads();
@@ -247,8 +257,9 @@ constexpr int kLatticeWarps = 4;   // warps (= concurrent tasks) per CTA of the 
 template <int ND, int J>
 __global__ void __launch_bounds__(32 * kLatticeWarps, PIMCB_LATTICE_MINB) rho_lattice_kernel(const double* __restrict__ pos, LatticePlan plan,
                                                            double* __restrict__ rho, int nslices, int N, int Npad, int nq,
-                                                           int3 nmax, double3 kphase) {
+                                                           int3 nmax, double3 kphase, int M) {
     constexpr int NK = LatticeK<ND>::NK;
+    const int Ms = rho_row_stride(M);
     constexpr int NPAT = LatticeK<ND>::NPAT;
     extern __shared__ __align__(16) double sm[];
     const int rowoff1 = nmax.x + 1;
@@ -369,8 +380,9 @@ __global__ void __launch_bounds__(32 * kLatticeWarps, PIMCB_LATTICE_MINB) rho_la
                 re = sl_ ? k0 + k1 : k0 - k1;
                 im = sl_ ? k3 - k2 : k3 + k2;
             }
-            rho[(static_cast<size_t>(sl) * 2 + 0) * nq + iq] = re;
-            rho[(static_cast<size_t>(sl) * 2 + 1) * nq + iq] = sa ? -im : im;
+            const int cb = sl / M, ct = sl - cb * M;
+            rho[rho_row(cb, iq, 0, nq, Ms) + ct] = re;
+            rho[rho_row(cb, iq, 1, nq, Ms) + ct] = sa ? -im : im;
         }
         __syncthreads();
     }
@@ -429,7 +441,7 @@ template <int ND, int MT, int NT, int NM>
 __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __restrict__ pos, const MmaPlan plan,
                                                                double* __restrict__ rho, int nslices, int N, int Npad, int nq,
                                                                int3 nmax, double3 kphase, unsigned* __restrict__ sched,
-                                                               int zero_mask, int split, double* __restrict__ partial) {
+                                                               int zero_mask, int split, double* __restrict__ partial, int M) {
     constexpr int NPAT = 1 << ND;
     constexpr int ML = MT, NR = NT;                         // every tile is computed; unused rows / cols are zero planes
     constexpr int ntile = ML * NR;
@@ -703,6 +715,9 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
         auto centry = [&](int row, int col) {
             return Cw[((row >> 3) * NR + (col >> 3)) * 64 + ((row & 7) * 4 + ((col & 7) >> 1)) * 2 + (col & 1)];
         };
+        const int cb = sl / M, ct = sl - cb * M;
+        const int Ms = rho_row_stride(M);
+        const size_t out_re = rho_row(cb, 0, 0, nq, Ms) + ct;      // + q * 2 Ms (+ Ms for the sine part)
         for (int w = lane; unfold && w < G * NPAT; w += 32) {
             const int g = w / NPAT, pat = w - g * NPAT;
             const int iq = s_gout[w];
@@ -726,8 +741,8 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                 re = sl_ ? k0 + k1 : k0 - k1;
                 im = sl_ ? k3 - k2 : k3 + k2;
             }
-            rho[(static_cast<size_t>(sl) * 2 + 0) * nq + iq] = re;
-            rho[(static_cast<size_t>(sl) * 2 + 1) * nq + iq] = sa ? -im : im;
+            rho[out_re + static_cast<size_t>(iq) * (2 * Ms)] = re;
+            rho[out_re + static_cast<size_t>(iq) * (2 * Ms) + Ms] = sa ? -im : im;
         }
         __syncwarp();
         item = item_next;
@@ -764,31 +779,33 @@ __global__ void __launch_bounds__(128, 7) isf_corr_kernel(const double* __restri
     const int ppw = 32 / lpp;                                // pairs per warp
     const int ppc = ppw * (blockDim.x >> 5);                 // pairs per CTA
     const int pair0 = blockIdx.x * ppc;
-    // stage: consecutive threads take consecutive q of one slice (contiguous in rho); ppc divides the CTA size, so a
-    // thread keeps its pair and walks t.  Each value goes to every periodic image i = t, t+M, t+2M < len.
+    // stage: the threads of a pair walk its two contiguous rho rows; each value goes to every periodic image
+    // i = t, t+M, t+2M < len.
     {
-        const int lp = threadIdx.x % ppc, tstep = blockDim.x / ppc;
+        const int tstep = blockDim.x / ppc, lp = threadIdx.x / tstep;      // tstep consecutive threads walk one pair's rows
         const int pair = pair0 + lp;
         if (pair < npairs) {
             const int b = pair / nq, iq = pair - b * nq;
-            const double* src = rho + (static_cast<size_t>(b) * M * 2) * nq + iq;
+            const int Ms = rho_row_stride(M);
+            const double* srcc = rho + rho_row(b, iq, 0, nq, Ms);
+            const double* srcs = srcc + Ms;
             double* dc = sm + (2 * lp + 0) * plen;
             double* ds = sm + (2 * lp + 1) * plen;
-            int t = threadIdx.x / ppc;
+            int t = threadIdx.x - lp * tstep;
             for (; t + 3 * tstep < M; t += 4 * tstep) {      // 8 independent loads in flight
                 double c[4], sn[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    c[u] = __ldg(src + static_cast<size_t>(t + u * tstep) * 2 * nq);
-                    sn[u] = __ldg(src + (static_cast<size_t>(t + u * tstep) * 2 + 1) * nq);
+                    c[u] = __ldg(srcc + t + u * tstep);
+                    sn[u] = __ldg(srcs + t + u * tstep);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
                     for (int i = t + u * tstep; i < len; i += M) { dc[corr_idx(i)] = c[u]; ds[corr_idx(i)] = sn[u]; }
             }
             for (; t < M; t += tstep) {
-                const double c = __ldg(src + static_cast<size_t>(t) * 2 * nq);
-                const double sn = __ldg(src + (static_cast<size_t>(t) * 2 + 1) * nq);
+                const double c = __ldg(srcc + t);
+                const double sn = __ldg(srcs + t);
                 for (int i = t; i < len; i += M) { dc[corr_idx(i)] = c; ds[corr_idx(i)] = sn; }
             }
         }
@@ -879,106 +896,151 @@ __global__ void __launch_bounds__(128, 7) isf_corr_kernel(const double* __restri
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int corrm_idx(int e) { return e + 4 * (e >> 3); }
 
-template <int MTC>
-__global__ void __launch_bounds__(128) isf_corr_mma_kernel(const double* __restrict__ rho, double* __restrict__ cfg, int M, int nq,
-                                                            int npairs, double invN, const unsigned char* __restrict__ commensurate) {
+// A CTA is four warps = the four configurations b0..b0+3 of one q (blockIdx = (b0 / 4) * nq + q); every warp stages
+// its own pair from its two contiguous rho rows and runs independently (no CTA barrier on the per-configuration path).
+// PARTIAL = false: out = cfg, one row of nq + nq*M results per configuration.
+// PARTIAL = true : the four warps' results are added in fixed order in shared memory and written as ONE row per
+//                  configuration quad (out = part[ceil(B/4)][nq + nq*M]); the bin accumulation then reads a quarter
+//                  of the data and the per-configuration rows are never written (pimcb_measure, all q commensurate).
+//                  The CTA that completes a q (counter qdone[q], re-armed by that CTA) then adds the quad rows of its q
+//                  in fixed order into the device-resident bin -- the bin accumulation costs no extra launch.
+template <int MTC, bool PARTIAL>
+__global__ void __launch_bounds__(128) isf_corr_mma_kernel(const double* __restrict__ rho, double* __restrict__ out, int M, int nq,
+                                                            int B, double invN, const unsigned char* __restrict__ commensurate,
+                                                            double* __restrict__ bins, unsigned* __restrict__ qdone) {
     extern __shared__ __align__(16) double sm[];
     constexpr int OFF = 64 * MTC;
-    constexpr int kRounds = 6;                               // t rounds (of 32 slices) whose loads are in flight together
     const int Mpad = (M + 3) & ~3;
     const int ext = OFF + Mpad + 8;                          // extended length in elements
     const int plen = corrm_idx(ext) + 4;                     // padded doubles per array
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pair0 = blockIdx.x * 4;                        // one pair per warp, 4 per CTA
-    {   // stage: thread = (pair lp, slice t mod 32); consecutive lanes read 4 consecutive q of one rho row (one 32-byte
-        // sector); every periodic image e = t + k M inside [-OFF, Mpad + 8) is written
-        const int lp = threadIdx.x & 3, t0 = threadIdx.x >> 2;
-        const int pair = pair0 + lp;
-        if (pair < npairs) {
-            const int b = pair / nq, iq = pair - b * nq;
-            const double* src = rho + (static_cast<size_t>(b) * M * 2) * nq + iq;
-            double* dc = sm + (2 * lp + 0) * plen;
-            double* ds = sm + (2 * lp + 1) * plen;
-            const int kneg = (OFF + M - 1) / M;              // images to the left of t
-            for (int tb = t0; tb < M; tb += 32 * kRounds) {
-                double c[kRounds], sn[kRounds];
-#pragma unroll
-                for (int u = 0; u < kRounds; ++u) {
-                    const int t = tb + 32 * u;
-                    if (t < M) {
-                        c[u] = __ldg(src + static_cast<size_t>(t) * 2 * nq);
-                        sn[u] = __ldg(src + (static_cast<size_t>(t) * 2 + 1) * nq);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < kRounds; ++u) {
-                    const int t = tb + 32 * u;
-                    if (t < M)
-                        for (int e = t - kneg * M; e < Mpad + 8; e += M)
-                            if (e >= -OFF) { dc[corrm_idx(e + OFF)] = c[u]; ds[corrm_idx(e + OFF)] = sn[u]; }
-                }
-            }
-        }
-    }
-    __syncthreads();
-    const int pair = pair0 + warp;
-    if (pair >= npairs) return;
-    const int b = pair / nq, iq = pair - b * nq;
+    const int bq = blockIdx.x / nq, iq = blockIdx.x - bq * nq;
+    const int b = 4 * bq + warp;
+    const bool live = b < B;
+    const int half = M / 2;
+    double* dc = sm + (2 * warp) * plen;
+    double* ds = dc + plen;
     const int fi = lane >> 2, fk = lane & 3;                 // fragment row / k index of this lane
     double acc[2][MTC][2];                                   // even / odd k-steps accumulate separately (DMMA ILP)
 #pragma unroll
     for (int e = 0; e < 2; ++e)
 #pragma unroll
         for (int m = 0; m < MTC; ++m) acc[e][m][0] = acc[e][m][1] = 0.0;
-    // Operand addressing without per-element index arithmetic.  k-step ks covers s = 4 ks + fk; two k-steps advance the
-    // padded index by exactly 12, and OFF is a multiple of 8, so with h = ks >> 1
-    //     B[s][j = fi]           sits at  pb{0,1} + 12 h   (even / odd ks; the odd base absorbs the "+4" and any padding jump)
-    //     A[i = fi + 8 m][s]     sits at  pa + 12 h (+4 for odd ks) - 96 m   (fk + 4 never crosses a group of 8)
-    const int nfull = M >> 2;                                // k-steps with all four s < M
-    const int nks = Mpad >> 2;
+    if (live) {
+        {   // stage: element e of the periodically extended arrays is rho(t = (e - OFF) mod M)
+            const int Ms = rho_row_stride(M);
+            const double* rc = rho + rho_row(b, iq, 0, nq, Ms);
+            const double* rs = rc + Ms;
+            int t = ((lane - OFF) % M + M) % M;
+            for (int e0 = lane; e0 < ext; e0 += 128) {
+                double c[4], sn[4];
 #pragma unroll
-    for (int part = 0; part < 2; ++part) {
-        const double* E = sm + (2 * warp + part) * plen;
-        const double* pa = E + corrm_idx(fk - 8 * fi + OFF);
-        const double* pb0 = E + corrm_idx(fk + fi + OFF);
-        const double* pb1 = E + corrm_idx(4 + fk + fi + OFF);
-        const int hmax = nfull >> 1;
-#pragma unroll 2
-        for (int h = 0; h < hmax; ++h) {
-            const double bv0 = pb0[12 * h], bv1 = pb1[12 * h];
-            double av0[MTC], av1[MTC];
+                for (int u = 0; u < 4; ++u) {
+                    if (e0 + 32 * u < ext) { c[u] = __ldg(rc + t); sn[u] = __ldg(rs + t); }
+                    t += 32;
+                    while (t >= M) t -= M;
+                }
 #pragma unroll
-            for (int m = 0; m < MTC; ++m) { av0[m] = pa[12 * h - 96 * m]; av1[m] = pa[12 * h + 4 - 96 * m]; }
-#pragma unroll
-            for (int m = 0; m < MTC; ++m) dmma8x8x4(acc[0][m], av0[m], bv0);
-#pragma unroll
-            for (int m = 0; m < MTC; ++m) dmma8x8x4(acc[1][m], av1[m], bv1);
+                for (int u = 0; u < 4; ++u)
+                    if (e0 + 32 * u < ext) { const int k = corrm_idx(e0 + 32 * u); dc[k] = c[u]; ds[k] = sn[u]; }
+            }
         }
-        for (int ks = 2 * hmax; ks < nks; ++ks) {            // at most two: a full even k-step and / or the masked tail
-            const int h = ks >> 1, s = 4 * ks + fk;
-            const double bv = (ks & 1) ? pb1[12 * h] : pb0[12 * h];
+        __syncwarp();
+        // Operand addressing without per-element index arithmetic.  k-step ks covers s = 4 ks + fk; two k-steps advance
+        // the padded index by exactly 12, and OFF is a multiple of 8, so with h = ks >> 1
+        //     B[s][j = fi]        sits at  pb{0,1} + 12 h   (even / odd ks; the odd base absorbs the "+4" and any padding jump)
+        //     A[i = fi + 8 m][s]  sits at  pa + 12 h (+4 for odd ks) - 96 m   (fk + 4 never crosses a group of 8)
+        const int nfull = M >> 2;                            // k-steps with all four s < M
+        const int nks = Mpad >> 2;
 #pragma unroll
-            for (int m = 0; m < MTC; ++m) {
-                const double v = pa[12 * h + 4 * (ks & 1) - 96 * m];
-                const double vm = s < M ? v : 0.0;                // the contraction runs over s < M only
-                if (ks & 1) dmma8x8x4(acc[1][m], vm, bv); else dmma8x8x4(acc[0][m], vm, bv);
+        for (int part = 0; part < 2; ++part) {
+            const double* E = part ? ds : dc;
+            const double* pa = E + corrm_idx(fk - 8 * fi + OFF);
+            const double* pb0 = E + corrm_idx(fk + fi + OFF);
+            const double* pb1 = E + corrm_idx(4 + fk + fi + OFF);
+            const int hmax = nfull >> 1;
+#pragma unroll 2
+            for (int h = 0; h < hmax; ++h) {
+                const double bv0 = pb0[12 * h], bv1 = pb1[12 * h];
+                double av0[MTC], av1[MTC];
+#pragma unroll
+                for (int m = 0; m < MTC; ++m) { av0[m] = pa[12 * h - 96 * m]; av1[m] = pa[12 * h + 4 - 96 * m]; }
+#pragma unroll
+                for (int m = 0; m < MTC; ++m) dmma8x8x4(acc[0][m], av0[m], bv0);
+#pragma unroll
+                for (int m = 0; m < MTC; ++m) dmma8x8x4(acc[1][m], av1[m], bv1);
+            }
+            for (int ks = 2 * hmax; ks < nks; ++ks) {        // at most two: a full even k-step and / or the masked tail
+                const int h = ks >> 1, sidx = 4 * ks + fk;
+                const double bv = (ks & 1) ? pb1[12 * h] : pb0[12 * h];
+#pragma unroll
+                for (int m = 0; m < MTC; ++m) {
+                    const double v = pa[12 * h + 4 * (ks & 1) - 96 * m];
+                    const double vm = sidx < M ? v : 0.0;    // the contraction runs over s < M only
+                    if (ks & 1) dmma8x8x4(acc[1][m], vm, bv); else dmma8x8x4(acc[0][m], vm, bv);
+                }
             }
         }
     }
-    const size_t cfg_stride = static_cast<size_t>(nq) + static_cast<size_t>(nq) * M;
-    double* out = cfg + static_cast<size_t>(b) * cfg_stride + nq + static_cast<size_t>(iq) * M;
-    const int half = M / 2;
+    const size_t row_len = static_cast<size_t>(nq) + static_cast<size_t>(nq) * M;
+    if constexpr (!PARTIAL) {
+        if (!live) return;
+        double* row = out + static_cast<size_t>(b) * row_len;
+        double* dst = row + nq + static_cast<size_t>(iq) * M;
 #pragma unroll
-    for (int m = 0; m < MTC; ++m)
+        for (int m = 0; m < MTC; ++m)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int tau = 64 * m + 8 * fi + 2 * fk + e;
-            if (tau > half) continue;
-            const double val = (acc[0][m][e] + acc[1][m][e]) * invN;
-            out[tau] = val;
-            if (tau > 0 && tau < M - tau) out[M - tau] = val;
-            if (tau == 0 && commensurate[iq]) cfg[static_cast<size_t>(b) * cfg_stride + iq] = val;
+            for (int e = 0; e < 2; ++e) {
+                const int tau = 64 * m + 8 * fi + 2 * fk + e;
+                if (tau > half) continue;
+                const double val = (acc[0][m][e] + acc[1][m][e]) * invN;
+                dst[tau] = val;
+                if (tau > 0 && tau < M - tau) dst[M - tau] = val;
+                if (tau == 0 && commensurate[iq]) row[iq] = val;
+            }
+    } else {
+        // park F(tau <= M/2) of this configuration at the start of the warp's own staging area, then add the four
+        // configurations in fixed order (b0, b0+1, b0+2, b0+3) -- dead warps contribute exact zeros
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < MTC; ++m)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int tau = 64 * m + 8 * fi + 2 * fk + e;
+                if (tau <= half) dc[tau] = (acc[0][m][e] + acc[1][m][e]) * invN;
+            }
+        __syncthreads();
+        double* dst = out + static_cast<size_t>(bq) * row_len + nq + static_cast<size_t>(iq) * M;   // tau <= M/2 only
+        for (int tau = threadIdx.x; tau <= half; tau += blockDim.x)
+            __stcg(dst + tau, ((sm[tau] + sm[2 * plen + tau]) + sm[4 * plen + tau]) + sm[6 * plen + tau]);
+        // last CTA of this q: add the quad rows (fixed order) into the bin, mirror tau -> M - tau, S(q) = F(q,0)
+        __shared__ unsigned s_last;
+        __threadfence();
+        __syncthreads();
+        const unsigned nquads = gridDim.x / nq;
+        if (threadIdx.x == 0) s_last = atomicAdd(qdone + iq, 1u) == nquads - 1 ? 1u : 0u;
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        const double* src = out + nq + static_cast<size_t>(iq) * M;
+        double* bq_out = bins + nq + static_cast<size_t>(iq) * M;
+        for (int tau = threadIdx.x; tau <= half; tau += blockDim.x) {
+            double tot = 0.0;
+            unsigned r = 0;
+            for (; r + 8 <= nquads; r += 8) {                        // 8 loads in flight, added in row order
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + static_cast<size_t>(r + u) * row_len + tau);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) tot += v[u];
+            }
+            for (; r < nquads; ++r) tot += __ldcg(src + static_cast<size_t>(r) * row_len + tau);
+            bq_out[tau] += tot;
+            if (tau > 0 && tau < M - tau) bq_out[M - tau] += tot;
+            if (tau == 0 && commensurate[iq]) bins[iq] += tot;
         }
+        if (threadIdx.x == 0) qdone[iq] = 0u;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -125,7 +125,9 @@ struct pimcb_ctx {
     bool have_dV = false;
     double dr = 0, extV[2] = {0, 0}, extdV[2] = {0, 0};
     // profiling: (kernel id, start, stop) event records, resolved lazily by pimcb_kernel_times
-    bool profiling = false;
+    unsigned profiling = 0;                 // bit k set: launches of kernel id k are bracketed by events
+    int prof_stride = 1;                    // ... every prof_stride-th launch of that kernel
+    long prof_seen[kKernels] = {};
     cudaEvent_t ev0[kKernels] = {}, ev1[kKernels] = {};      // scratch events (fences, fp64 peak)
     struct Rec { int k; cudaEvent_t a, b; };
     std::vector<Rec> recs;
@@ -134,6 +136,7 @@ struct pimcb_ctx {
     long k_count[kKernels] = {};
     long launches = 0;
     DevBuf d_scratch;
+    DevBuf d_qdone;                        // per-q completion counters of the fused correlation + bin accumulation
     DevBuf d_sched;                        // ticket counter + retire counter of the persistent-warp rho kernel (self re-arming)
 };
 
@@ -150,7 +153,7 @@ cudaEvent_t pool_event(pimcb_ctx* c) {
 struct KTimer {
     pimcb_ctx* c; int k; cudaStream_t st; cudaEvent_t a = nullptr;
     KTimer(pimcb_ctx* c_, int k_, cudaStream_t st_ = nullptr) : c(c_), k(k_), st(st_ ? st_ : c_->stream) {
-        if (c->profiling && (a = pool_event(c))) cudaEventRecord(a, st);
+        if (((c->profiling >> k) & 1u) && (c->prof_seen[k]++ % c->prof_stride) == 0 && (a = pool_event(c))) cudaEventRecord(a, st);
     }
     ~KTimer() {
         if (a) {
@@ -227,7 +230,7 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
     const size_t lattice_fixed = sizeof(double) * (2 * static_cast<size_t>(rows) * lattice_stride(s.N, JJ) + static_cast<size_t>(nd) * s.Npad);
     // lattice path only when every q is commensurate and the phase-power table leaves room for >= 2 CTAs per SM
     const bool lattice = c->rho_mode >= 1 && c->ngroups > 0 && lattice_fixed <= 100 * 1024;
-    int rc = c->d_rho.ensure(sizeof(double) * 2 * static_cast<size_t>(nsl) * nq);
+    int rc = c->d_rho.ensure(sizeof(double) * 2 * static_cast<size_t>(s.B) * nq * rho_row_stride(s.M));   // pair-major rows
     if (rc) return rc;
     int P = 1, chunk = 0;
     KTimer kt(c, K_RHO);
@@ -277,7 +280,7 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
         rho_lattice_mma_kernel<ND, MT, NT, NM><<<pgrid, 128, mma_smem, c->stream>>>(s.pos.as<double>(), plan, c->d_rho.as<double>(), \
                                                                                     nsl, s.N, s.Npad, nq, nmax, kph,         \
                                                                                     c->d_sched.as<unsigned>(), 0, split,     \
-                                                                                    c->d_partial.as<double>()); }
+                                                                                    c->d_partial.as<double>(), s.M); }
         // 3-D with every |n_d| <= 2 (or 3): phase A fully unrolled; the R columns then fit one N tile
 #define LAUNCH_MMA(ND, MT, NT)                                                                                    \
         if (ND == 3 && NT == 1 && nm3 <= 2) LAUNCH_MMA_NM(ND, MT, NT, (ND == 3 && NT == 1 ? 2 : 0))                \
@@ -309,7 +312,7 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
 #define LAUNCH_GENERIC(ND)                                                                                        \
         rc = set_smem(rho_generic_kernel<ND>, smem); if (rc) return rc;                                            \
         rho_generic_kernel<ND><<<grid, 256, smem, c->stream>>>(s.pos.as<double>(), c->d_q.as<double>(),           \
-                                                               c->d_rho.as<double>(), nsl, s.N, s.Npad, nq, P, chunk)
+                                                               c->d_rho.as<double>(), nsl, s.N, s.Npad, nq, P, chunk, s.M)
         if (nd == 1) { LAUNCH_GENERIC(1); } else if (nd == 2) { LAUNCH_GENERIC(2); } else { LAUNCH_GENERIC(3); }
 #undef LAUNCH_GENERIC
     } else {
@@ -325,7 +328,7 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
 #define LAUNCH_LATTICE(ND, JJ)                                                                                    \
         rc = set_smem(rho_lattice_kernel<ND, JJ>, smem); if (rc) return rc;                                        \
         rho_lattice_kernel<ND, JJ><<<grid, 32 * c->lattice_warps, smem, c->stream>>>(s.pos.as<double>(), plan, c->d_rho.as<double>(), nsl, \
-                                                                   s.N, s.Npad, nq, nmax, kph)
+                                                                   s.N, s.Npad, nq, nmax, kph, s.M)
 #define LAUNCH_LATTICE_J(ND)                                                                                      \
         if (J >= 8) { LAUNCH_LATTICE(ND, 8); } else if (J >= 4) { LAUNCH_LATTICE(ND, 4); }                         \
         else if (J >= 2) { LAUNCH_LATTICE(ND, 2); } else { LAUNCH_LATTICE(ND, 1); }
@@ -337,22 +340,35 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
     return 0;
 }
 
-int launch_corr(pimcb_ctx* c, const Slot& s) {
+// partial_rows != nullptr asks for the quad-summed form (one row per four configurations, folded into the bin by the
+// kernel itself) when the DMMA kernel can provide it; *partial_rows returns the number of rows of d_cfg that still have
+// to be accumulated into the bin (0 after the fused form, B after a per-configuration form).
+int launch_corr(pimcb_ctx* c, const Slot& s, int* partial_rows = nullptr) {
     KTimer kt(c, K_CORR);
-    const int npairs_all = s.B * c->nq;
+    if (partial_rows) *partial_rows = s.B;
     const int mtc = (s.M / 2 + 1 + 63) / 64;                      // 64-tau accumulator tiles of the DMMA formulation
     if (c->corr_mode == 1 && mtc <= 4) {
         const int off = 64 * mtc, mpad = (s.M + 3) & ~3, ext = off + mpad + 8;
         const int plen = ext + 4 * (ext >> 3) + 4;
         const size_t smem = sizeof(double) * 2 * static_cast<size_t>(plen) * 4;
+        const int quads = (s.B + 3) / 4;
+        const bool partial = partial_rows != nullptr;
         int rc = 0;
-#define LAUNCH_CORR_MMA(MTC)                                                                                      \
-        rc = set_smem(isf_corr_mma_kernel<MTC>, smem); if (rc) return rc;                                          \
-        isf_corr_mma_kernel<MTC><<<(npairs_all + 3) / 4, 128, smem, c->stream>>>(c->d_rho.as<double>(), c->d_cfg.as<double>(), s.M, \
-                                                                                 c->nq, npairs_all, 1.0 / s.N, c->d_comm.as<unsigned char>())
-        if (mtc == 1) { LAUNCH_CORR_MMA(1); } else if (mtc == 2) { LAUNCH_CORR_MMA(2); } else if (mtc == 3) { LAUNCH_CORR_MMA(3); } else { LAUNCH_CORR_MMA(4); }
+        if (partial && sizeof(unsigned) * c->nq > c->d_qdone.cap) {          // per-q completion counters, left at zero by the kernel
+            rc = c->d_qdone.ensure(sizeof(unsigned) * c->nq); if (rc) return rc;
+            CU(cudaMemsetAsync(c->d_qdone.p, 0, c->d_qdone.cap, c->stream));
+        }
+#define LAUNCH_CORR_MMA2(MTC, PART)                                                                                \
+        rc = set_smem(isf_corr_mma_kernel<MTC, PART>, smem); if (rc) return rc;                                    \
+        isf_corr_mma_kernel<MTC, PART><<<quads * c->nq, 128, smem, c->stream>>>(c->d_rho.as<double>(), c->d_cfg.as<double>(), s.M, \
+                                                                                c->nq, s.B, 1.0 / s.N, c->d_comm.as<unsigned char>(), \
+                                                                                c->d_bins.as<double>(), c->d_qdone.as<unsigned>())
+#define LAUNCH_CORR_MMA(MTC) if (partial) { LAUNCH_CORR_MMA2(MTC, true); } else { LAUNCH_CORR_MMA2(MTC, false); }
+        if (mtc == 1) { LAUNCH_CORR_MMA(1) } else if (mtc == 2) { LAUNCH_CORR_MMA(2) } else if (mtc == 3) { LAUNCH_CORR_MMA(3) } else { LAUNCH_CORR_MMA(4) }
 #undef LAUNCH_CORR_MMA
+#undef LAUNCH_CORR_MMA2
         CU(cudaGetLastError());
+        if (partial) *partial_rows = 0;         // already folded into the bin by the kernel
         return 0;
     }
     const int nblk = (s.M / 2 + 1 + 7) / 8;                       // tau blocks of 8 per (config, q) pair
@@ -395,7 +411,9 @@ int launch_direct(pimcb_ctx* c, const Slot& s) {
     return 0;
 }
 
-int run_estimators(pimcb_ctx* c, Slot** sp) {
+// rows != nullptr (pimcb_measure): only the sum over configurations is wanted, so the correlation may write
+// quad-summed rows; *rows = number of rows of d_cfg to accumulate into the bin.
+int run_estimators(pimcb_ctx* c, Slot** sp, int* rows = nullptr) {
     Slot* s;
     int rc = need_cur(c, &s);
     if (rc) return rc;
@@ -414,7 +432,10 @@ int run_estimators(pimcb_ctx* c, Slot** sp) {
     if (rc) return rc;
     CU(cudaStreamWaitEvent(c->stream, s->ready, 0));
     if ((rc = launch_rho(c, *s))) return rc;
-    if ((rc = launch_corr(c, *s))) return rc;
+    // quad-summed rows only when every S(q) comes from the correlation (no direct min-image q writes per-configuration rows)
+    const bool partial = rows != nullptr && c->nsel == 0;
+    if (rows) *rows = s->B;
+    if ((rc = launch_corr(c, *s, partial ? rows : nullptr))) return rc;
     if ((rc = launch_direct(c, *s))) return rc;
     CU(cudaEventRecord(s->consumed, c->stream));
     *sp = s;
@@ -564,7 +585,7 @@ int pimcb_destroy(pimcb_ctx* c) {
     for (auto& p : c->pin) { p.release(); if (p.done) cudaEventDestroy(p.done); }
     c->h_out.release();
     for (DevBuf* b : {&c->d_q, &c->d_comm, &c->d_qn, &c->d_qidx, &c->d_plan, &c->d_aos, &c->d_rho, &c->d_cfg, &c->d_bins, &c->d_partial,
-                      &c->d_V, &c->d_dV, &c->d_vint, &c->d_f2, &c->d_hist, &c->d_scratch, &c->d_sched})
+                      &c->d_V, &c->d_dV, &c->d_vint, &c->d_f2, &c->d_hist, &c->d_scratch, &c->d_sched, &c->d_qdone})
         b->release();
     for (int k = 0; k < kKernels; ++k) { cudaEventDestroy(c->ev0[k]); cudaEventDestroy(c->ev1[k]); }
     for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -857,12 +878,13 @@ int pimcb_measure(pimcb_ctx* c) {
     if (!c) return fail(PIMCB_EINVAL, "null ctx");
     CU(cudaSetDevice(c->device));
     Slot* s;
-    int rc = run_estimators(c, &s);
+    int rows = 0;
+    int rc = run_estimators(c, &s, &rows);
     if (rc) return rc;
-    {
+    if (rows > 0) {
         KTimer kt(c, K_BINS);
         const size_t len = c->bins_len;
-        bins_accumulate_kernel<<<static_cast<unsigned>((kBinLanes * len + 255) / 256), 256, 0, c->stream>>>(c->d_cfg.as<double>(), c->d_bins.as<double>(), s->B, len);
+        bins_accumulate_kernel<<<static_cast<unsigned>((kBinLanes * len + 255) / 256), 256, 0, c->stream>>>(c->d_cfg.as<double>(), c->d_bins.as<double>(), rows, len);
         CU(cudaGetLastError());
     }
     c->n_acc += s->B;
@@ -1003,9 +1025,16 @@ int pimcb_measure_fp64_peak(pimcb_ctx* c, double* tflops, double seconds_target)
     return 0;
 }
 
+int pimcb_set_profiling_stride(pimcb_ctx* c, int stride) {
+    if (!c || stride < 1) return fail(PIMCB_EINVAL, "profiling stride must be >= 1");
+    c->prof_stride = stride;
+    for (long& v : c->prof_seen) v = 0;
+    return 0;
+}
+
 int pimcb_set_profiling(pimcb_ctx* c, int on) {
     if (!c) return fail(PIMCB_EINVAL, "null ctx");
-    c->profiling = on != 0;
+    c->profiling = on == 1 ? ~0u : static_cast<unsigned>(on) >> 1;   // 0 off, 1 all, else mask with bit (id + 1) per kernel
     return 0;
 }
 
