@@ -87,13 +87,17 @@ __device__ __forceinline__ void sincos_fast(double x, double& s, double& c) {
     sincos_fast(x, s, c, n);
 }
 
-// rho_q layout ("pair-major"): rho[((b * nq + q) * 2 + {cos,sin}) * Ms + t], Ms = M rounded up to even -- the M values
-// of one (configuration, q) pair are contiguous, which is what the tau-correlation reads; the rho kernels write one
-// 8-byte element per (q, part) and slice, neighbouring slices complete the 32-byte sectors in L2.
-__host__ __device__ inline int rho_row_stride(int M) { return (M + 1) & ~1; }
-__device__ __forceinline__ size_t rho_row(int b, int iq, int cs, int nq, int Ms) {
-    return ((static_cast<size_t>(b) * nq + iq) * 2 + cs) * Ms;
+// rho_q layout ("blocks of four slices"):  rho[b][t / 4][q][{cos,sin}][t % 4]  (double).
+//   * a rho kernel finishing slice t writes one 8-byte element into each of 2 nq CONSECUTIVE 32-byte sectors (the
+//     warp's 32 lanes touch 8 cache lines per store; a fully pair-major layout -- M contiguous values per (b, q) --
+//     touched 32 lines per store and cost the rho kernel 6 %);
+//   * the tau-correlation reads, per (b, q) pair, whole 32-byte sectors (four consecutive slices of its pair), so no
+//     fetched byte is wasted and four configurations of the SAME q can share a CTA (quad-summed partial rows).
+__host__ __device__ inline int rho_tblocks(int M) { return (M + 3) >> 2; }
+__device__ __forceinline__ size_t rho_pair_base(int b, int iq, int cs, int nq, int nTB) {   // + rho_slice_off(t)
+    return (static_cast<size_t>(b) * nTB * nq * 2 + static_cast<size_t>(iq) * 2 + cs) * 4;
 }
+__device__ __forceinline__ size_t rho_slice_off(int t, int nq) { return static_cast<size_t>(t >> 2) * nq * 8 + (t & 3); }
 
 // Coalesced load of one slice (ND rows of Npad doubles, contiguous, 16-byte aligned) into shared memory.
 __device__ __forceinline__ void load_slice(double* __restrict__ sm, const double* __restrict__ src, int count) {
@@ -116,9 +120,10 @@ __global__ void __launch_bounds__(256) rho_generic_kernel(const double* __restri
     double* xs = sm;                          // [ND][Npad]
     double* part = sm + ND * Npad;            // [2][P][nq]  (only when P > 1)
     const int items = nq * P;
-    const int Ms = rho_row_stride(M);
+    const int nTB = rho_tblocks(M);
     for (int sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
         const int cb = sl / M, ct = sl - cb * M;      // configuration and time slice of this CTA's work item
+        const size_t so = rho_slice_off(ct, nq);
         load_slice(xs, pos + static_cast<size_t>(sl) * ND * Npad, ND * Npad);
         __syncthreads();
         for (int item = threadIdx.x; item < items; item += blockDim.x) {
@@ -141,8 +146,8 @@ __global__ void __launch_bounds__(256) rho_generic_kernel(const double* __restri
                 as += s;
             }
             if (P == 1) {
-                rho[rho_row(cb, iq, 0, nq, Ms) + ct] = ac;
-                rho[rho_row(cb, iq, 1, nq, Ms) + ct] = as;
+                rho[rho_pair_base(cb, iq, 0, nq, nTB) + so] = ac;
+                rho[rho_pair_base(cb, iq, 1, nq, nTB) + so] = as;
             } else {
                 part[p * nq + iq] = ac;
                 part[(P + p) * nq + iq] = as;
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(256) rho_generic_kernel(const double* __restri
                 const int cs = k / nq, iq = k - cs * nq;
                 double acc = 0.0;
                 for (int p = 0; p < P; ++p) acc += part[(cs * P + p) * nq + iq];   // fixed order: deterministic
-                rho[rho_row(cb, iq, cs, nq, Ms) + ct] = acc;
+                rho[rho_pair_base(cb, iq, cs, nq, nTB) + so] = acc;
             }
         }
         __syncthreads();
@@ -259,7 +264,7 @@ __global__ void __launch_bounds__(32 * kLatticeWarps, PIMCB_LATTICE_MINB) rho_la
                                                            double* __restrict__ rho, int nslices, int N, int Npad, int nq,
                                                            int3 nmax, double3 kphase, int M) {
     constexpr int NK = LatticeK<ND>::NK;
-    const int Ms = rho_row_stride(M);
+    const int nTB = rho_tblocks(M);
     constexpr int NPAT = LatticeK<ND>::NPAT;
     extern __shared__ __align__(16) double sm[];
     const int rowoff1 = nmax.x + 1;
@@ -381,8 +386,8 @@ __global__ void __launch_bounds__(32 * kLatticeWarps, PIMCB_LATTICE_MINB) rho_la
                 im = sl_ ? k3 - k2 : k3 + k2;
             }
             const int cb = sl / M, ct = sl - cb * M;
-            rho[rho_row(cb, iq, 0, nq, Ms) + ct] = re;
-            rho[rho_row(cb, iq, 1, nq, Ms) + ct] = sa ? -im : im;
+            rho[rho_pair_base(cb, iq, 0, nq, nTB) + rho_slice_off(ct, nq)] = re;
+            rho[rho_pair_base(cb, iq, 1, nq, nTB) + rho_slice_off(ct, nq)] = sa ? -im : im;
         }
         __syncthreads();
     }
@@ -716,8 +721,7 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
             return Cw[((row >> 3) * NR + (col >> 3)) * 64 + ((row & 7) * 4 + ((col & 7) >> 1)) * 2 + (col & 1)];
         };
         const int cb = sl / M, ct = sl - cb * M;
-        const int Ms = rho_row_stride(M);
-        const size_t out_re = rho_row(cb, 0, 0, nq, Ms) + ct;      // + q * 2 Ms (+ Ms for the sine part)
+        const size_t out_re = rho_pair_base(cb, 0, 0, nq, rho_tblocks(M)) + rho_slice_off(ct, nq);   // + 8 q (+ 4 for the sine part)
         for (int w = lane; unfold && w < G * NPAT; w += 32) {
             const int g = w / NPAT, pat = w - g * NPAT;
             const int iq = s_gout[w];
@@ -741,8 +745,8 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                 re = sl_ ? k0 + k1 : k0 - k1;
                 im = sl_ ? k3 - k2 : k3 + k2;
             }
-            rho[out_re + static_cast<size_t>(iq) * (2 * Ms)] = re;
-            rho[out_re + static_cast<size_t>(iq) * (2 * Ms) + Ms] = sa ? -im : im;
+            rho[out_re + 8 * iq] = re;
+            rho[out_re + 8 * iq + 4] = sa ? -im : im;
         }
         __syncwarp();
         item = item_next;
@@ -779,16 +783,15 @@ __global__ void __launch_bounds__(128, 7) isf_corr_kernel(const double* __restri
     const int ppw = 32 / lpp;                                // pairs per warp
     const int ppc = ppw * (blockDim.x >> 5);                 // pairs per CTA
     const int pair0 = blockIdx.x * ppc;
-    // stage: the threads of a pair walk its two contiguous rho rows; each value goes to every periodic image
+    // stage: the threads of a pair walk its rho values (whole 32-byte sectors per four slices); each value goes to every periodic image
     // i = t, t+M, t+2M < len.
     {
         const int tstep = blockDim.x / ppc, lp = threadIdx.x / tstep;      // tstep consecutive threads walk one pair's rows
         const int pair = pair0 + lp;
         if (pair < npairs) {
             const int b = pair / nq, iq = pair - b * nq;
-            const int Ms = rho_row_stride(M);
-            const double* srcc = rho + rho_row(b, iq, 0, nq, Ms);
-            const double* srcs = srcc + Ms;
+            const double* srcc = rho + rho_pair_base(b, iq, 0, nq, rho_tblocks(M));
+            const double* srcs = srcc + 4;
             double* dc = sm + (2 * lp + 0) * plen;
             double* ds = sm + (2 * lp + 1) * plen;
             int t = threadIdx.x - lp * tstep;
@@ -796,16 +799,16 @@ __global__ void __launch_bounds__(128, 7) isf_corr_kernel(const double* __restri
                 double c[4], sn[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    c[u] = __ldg(srcc + t + u * tstep);
-                    sn[u] = __ldg(srcs + t + u * tstep);
+                    c[u] = __ldg(srcc + rho_slice_off(t + u * tstep, nq));
+                    sn[u] = __ldg(srcs + rho_slice_off(t + u * tstep, nq));
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
                     for (int i = t + u * tstep; i < len; i += M) { dc[corr_idx(i)] = c[u]; ds[corr_idx(i)] = sn[u]; }
             }
             for (; t < M; t += tstep) {
-                const double c = __ldg(srcc + t);
-                const double sn = __ldg(srcs + t);
+                const double c = __ldg(srcc + rho_slice_off(t, nq));
+                const double sn = __ldg(srcs + rho_slice_off(t, nq));
                 for (int i = t; i < len; i += M) { dc[corr_idx(i)] = c; ds[corr_idx(i)] = sn; }
             }
         }
@@ -897,7 +900,7 @@ __global__ void __launch_bounds__(128, 7) isf_corr_kernel(const double* __restri
 __device__ __forceinline__ int corrm_idx(int e) { return e + 4 * (e >> 3); }
 
 // A CTA is four warps = the four configurations b0..b0+3 of one q (blockIdx = (b0 / 4) * nq + q); every warp stages
-// its own pair from its two contiguous rho rows and runs independently (no CTA barrier on the per-configuration path).
+// its own pair (whole 32-byte sectors of the rho buffer) and runs independently (no CTA barrier on the per-configuration path).
 // PARTIAL = false: out = cfg, one row of nq + nq*M results per configuration.
 // PARTIAL = true : the four warps' results are added in fixed order in shared memory and written as ONE row per
 //                  configuration quad (out = part[ceil(B/4)][nq + nq*M]); the bin accumulation then reads a quarter
@@ -928,15 +931,14 @@ __global__ void __launch_bounds__(128) isf_corr_mma_kernel(const double* __restr
         for (int m = 0; m < MTC; ++m) acc[e][m][0] = acc[e][m][1] = 0.0;
     if (live) {
         {   // stage: element e of the periodically extended arrays is rho(t = (e - OFF) mod M)
-            const int Ms = rho_row_stride(M);
-            const double* rc = rho + rho_row(b, iq, 0, nq, Ms);
-            const double* rs = rc + Ms;
+            const double* rc = rho + rho_pair_base(b, iq, 0, nq, rho_tblocks(M));
+            const double* rs = rc + 4;
             int t = ((lane - OFF) % M + M) % M;
             for (int e0 = lane; e0 < ext; e0 += 128) {
                 double c[4], sn[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    if (e0 + 32 * u < ext) { c[u] = __ldg(rc + t); sn[u] = __ldg(rs + t); }
+                    if (e0 + 32 * u < ext) { const size_t o = rho_slice_off(t, nq); c[u] = __ldg(rc + o); sn[u] = __ldg(rs + o); }
                     t += 32;
                     while (t >= M) t -= M;
                 }

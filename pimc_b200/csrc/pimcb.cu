@@ -230,7 +230,7 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
     const size_t lattice_fixed = sizeof(double) * (2 * static_cast<size_t>(rows) * lattice_stride(s.N, JJ) + static_cast<size_t>(nd) * s.Npad);
     // lattice path only when every q is commensurate and the phase-power table leaves room for >= 2 CTAs per SM
     const bool lattice = c->rho_mode >= 1 && c->ngroups > 0 && lattice_fixed <= 100 * 1024;
-    int rc = c->d_rho.ensure(sizeof(double) * 2 * static_cast<size_t>(s.B) * nq * rho_row_stride(s.M));   // pair-major rows
+    int rc = c->d_rho.ensure(sizeof(double) * 8 * static_cast<size_t>(s.B) * rho_tblocks(s.M) * nq);   // rho[b][t/4][q][cs][t%4]
     if (rc) return rc;
     int P = 1, chunk = 0;
     KTimer kt(c, K_RHO);

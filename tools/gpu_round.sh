@@ -9,7 +9,7 @@ python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > $OUT/${TAG}_pytest_gpu.log
 python __graft_entry__.py smoke 2>&1 | tail -2
 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; cat $OUT/${TAG}_bench.json; tail -3 $OUT/${TAG}_bench.err
 python bench.py --rho-mode 0 --no-cpu-baseline > $OUT/${TAG}_bench_generic.json 2>> $OUT/${TAG}_bench.err; cat $OUT/${TAG}_bench_generic.json
-KF='regex:rho_|isf_corr|bins_acc|aos_to|ssf_direct|pair_'
+KF="regex:rho_|isf_corr|bins_acc|aos_to|ssf_direct|pair_"
 BARGS="--steps 8 --warmup 3 --no-cpu-baseline --peak-seconds 0.02 --no-ab --no-pair"
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KF" -c 200 --csv --log-file $OUT/${TAG}_launches.csv python bench.py $BARGS > $OUT/${TAG}_ncu_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:rho_lattice_mma -s 4 -c 1 -f -o $OUT/${TAG}_prof_rho_lattice python bench.py $BARGS --no-e2e > /dev/null 2>&1
