@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--unique", type=int, default=16, help="distinct synthetic configurations generated per slot")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the single-configuration latency leg")
     ap.add_argument("--no-ab", action="store_true", help="skip the generic-kernel A/B leg")
     ap.add_argument("--no-pair", action="store_true", help="skip the pair-potential secondary measurement")
     ap.add_argument("--peak-seconds", type=float, default=0.5, help="duration of the in-run FP64 DFMA peak measurement")
@@ -349,7 +350,7 @@ def run_ours(args, shape, q):
 
     # ---- latency: ONE configuration through the synchronous ABI calls an estimator's accumulate() makes ----------
     latency = None
-    if not args.no_e2e:
+    if not args.no_e2e and not args.no_latency:
         one = np.ascontiguousarray(pinned[0].array[0])                   # pageable host copy, like Path::beads
         ssf1, isf1 = ctx.stage(one, shape.N).ssf_isf()
         for _ in range(5):
