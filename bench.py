@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--unique", type=int, default=16, help="distinct synthetic configurations generated per slot")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's local CPUs")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-configuration latency leg")
     ap.add_argument("--no-ab", action="store_true", help="skip the generic-kernel A/B leg")
     ap.add_argument("--no-pair", action="store_true", help="skip the pair-potential secondary measurement")
@@ -203,6 +204,32 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa(local: int):
+    """Pin this rank's threads (and so the first-touch placement of its pinned staging buffers) to the CPUs NVML
+    reports as local to its GPU -- what `numactl` per rank would do.  With 8 ranks on a two-socket host, buffers on
+    the wrong socket halve the aggregate host-to-device rate.  Returns the CPU list or None."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(local)
+        try:
+            bus = "%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 # --------------------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------------------
@@ -218,6 +245,8 @@ def run_ours(args, shape, q):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
+    numa_cpus = bind_to_gpu_numa(local) if not args.no_numa else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -362,6 +391,9 @@ def run_ours(args, shape, q):
         lat = (time.perf_counter() - t0) / nlat
         latency = {"single_configuration_us": lat * 1e6, "evaluations_per_s": 1.0 / lat, "calls": nlat,
                    "path": "pimcb_stage_beads(pageable host AoS) + pimcb_ssf_isf, synchronous, one walker"}
+        for sl, pa in enumerate(pinned):               # the single-walker calls cycled through the slots: restore the batches
+            ctx.stage(pa.array, shape.N, slot=sl)
+        ctx.sync()
         ctx.reset_bins()
 
     # ---- roofline of the dominant kernel (rho_q build) -------------------------------------------------------
@@ -471,11 +503,13 @@ def run_ours(args, shape, q):
                    "parallelism": (f"walker-configuration sharding x{world}, one NCCL reduce of the bin" if args.shard == "config"
                                    else f"q-vector sharding x{world} ({nq} of {len(q_all)} q per GPU), one NCCL all-gather of the bin"),
                    "l2": f"{use_slots} resident batches rotated ({footprint_mb:.0f} MB > 126 MB L2)",
-                   "rho_mode": args.rho_mode, "corr_mode": args.corr_mode},
+                   "rho_mode": args.rho_mode, "corr_mode": args.corr_mode,
+                   "host_binding": (f"rank bound to {len(numa_cpus)} GPU-local CPUs (NVML affinity)" if numa_cpus else "none")},
         "clocks": clocks, "e2e": e2e, "latency": latency, "gpu_launches": int(launches), "roofline": roofline, "pair_sums": pair,
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)             # the CPU arm gets every host core again
         arm = CpuArm(shape, q, args.cpu_seconds)
         full_s, _ = arm.step()
         line["cpu_baseline"] = {"value": 1.0 / full_s, "unit": UNIT, "cores": arm.cores, "kind": "port",
