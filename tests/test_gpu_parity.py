@@ -72,6 +72,53 @@ def test_c3_2d_full_grid(api, orc, nthreads):
     np.testing.assert_allclose(ssf[0, zero], s.M * s.N, rtol=1e-14)
 
 
+def test_c4_shape_and_q_shards(api, orc, nthreads):
+    """C4 (N=1024, M=320, 256 q): all q against the factorised CPU variant, S(q) of 2 q against the min-image CPU loop,
+    a handful of F(q,tau) elements against the direct reference loop, and the 8-way q-sharding of BASELINE config 4
+    (32 q per shard) reproducing the unsharded columns exactly."""
+    from pimc_b200 import multi
+    s = synth.C4
+    beads = synth.gen_config(s.N, s.M, s.ndim, s.rho, s.T, seed=synth.BASE_SEED + 4)
+    q = synth.commensurate_q(s.nq, s.side)
+    with make_ctx(api, s, q) as ctx:
+        ssf, isf = ctx.stage(beads, s.N).ssf_isf()
+    assert_parity(isf[0], orc.isf_factorised(beads, s.N, q), "C4 isf (factorised oracle)")
+    assert_parity(ssf[0], isf[0][:, 0], "C4 S(q) = F(q,0)")
+    pick = [3, 200]
+    assert_parity(ssf[0, pick], orc.ssf(s.side, beads, s.N, q[pick], nthreads=nthreads), "C4 ssf (min-image oracle, 2 q)")
+    e0 = 77 * s.M + 150                                  # q 77, tau 150..153: 4 elements of the O(M N^2) loop each
+    ref = orc.isf_range(beads, s.N, q, e0, e0 + 4, nthreads=nthreads)[e0:e0 + 4]
+    assert_parity(isf[0].reshape(-1)[e0:e0 + 4], ref, "C4 isf (direct oracle, 4 elements)")
+    np.testing.assert_allclose(isf[0][:, 1:], isf[0][:, :0:-1], rtol=0, atol=0)      # F(tau) = F(M - tau): mirrored, bit-equal
+    for rank in (0, 5, 7):
+        lo, hi = multi.shard_range(s.nq, 8, rank)
+        with make_ctx(api, s, q[lo:hi]) as ctx:
+            s_loc, f_loc = ctx.stage(beads, s.N).ssf_isf()
+        assert_parity(f_loc[0], isf[0, lo:hi], f"C4 q-shard {rank}")
+        assert_parity(s_loc[0], ssf[0, lo:hi], f"C4 q-shard {rank} ssf")
+
+
+def test_c5_walker_batch_bin(api, orc):
+    """C5 per GPU: a batch of C2 walkers through pimcb_measure (quad-summed correlation + in-kernel bin accumulation)
+    equals the sum of the per-configuration results; ragged batch sizes; two configurations against the oracle."""
+    s = synth.C2
+    q = synth.commensurate_q(s.nq, s.side)
+    batch = synth.gen_batch(s, 11, first=50)
+    with make_ctx(api, s, q) as ctx:
+        ssf, isf = ctx.stage(batch, s.N).ssf_isf()
+        for nb in (11, 8, 5, 1):
+            ctx.reset_bins()
+            ctx.stage(batch[:nb], s.N)
+            ctx.measure()
+            ctx.measure()                                 # twice: the kernel re-arms its own completion counters
+            bs, bi, n = ctx.read_bins()
+            assert n == 2 * nb
+            assert_parity(bs, 2 * ssf[:nb].sum(axis=0), f"bin ssf B={nb}")
+            assert_parity(bi, 2 * isf[:nb].sum(axis=0), f"bin isf B={nb}")
+    for b in (0, 10):
+        assert_parity(isf[b], orc.isf_factorised(batch[b], s.N, q), f"C5 isf config {b}")
+
+
 def test_non_commensurate_q_uses_direct_min_image(api, orc, nthreads):
     """`float` wave-vectors: S(q) must follow the CPU min-image pair sum, F(q,tau) raw positions."""
     s = synth.Shape("mix", 3, 64, 40, 2.0, 0.02198, 0)
