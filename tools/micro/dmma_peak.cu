@@ -68,6 +68,53 @@ __global__ void __launch_bounds__(256) dfma_ffma_kernel(double* out, int iters, 
     if (v == 123.456) out[0] = v;
 }
 
+// Does a DMMA keep the sub-partition's issue port busy for its 16 cycles?  4 DMMA (64 datapath cycles) next to 64
+// independent FFMAs (64 issue cycles) per iteration: ~64 cycles per iteration if they overlap, ~128 if they do not.
+__global__ void __launch_bounds__(256) dmma_ffma_kernel(double* out, int iters, double a, double b) {
+    double c0[2] = {0, 0}, c1[2] = {0, 0}, c2[2] = {0, 0}, c3[2] = {0, 0};
+    const double av = a + threadIdx.x * 1e-9, bv = b;
+    float y[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) y[k] = threadIdx.x + k;
+    const float fa = (float)a, fb = (float)b;
+    for (int it = 0; it < iters; ++it) {
+        MMA(c0);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) y[k] = fmaf(y[k], fa, fb);
+        MMA(c1);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) y[k] = fmaf(y[k], fa, fb);
+        MMA(c2);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) y[k] = fmaf(y[k], fa, fb);
+        MMA(c3);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) y[k] = fmaf(y[k], fa, fb);
+    }
+    float ys = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) ys += y[k];
+    const double v = c0[0] + c1[0] + c2[1] + c3[1] + (double)ys;
+    if (v == 123.456) out[0] = v;
+}
+
+__global__ void __launch_bounds__(256) ffma_only_kernel(double* out, int iters, double a, double b) {
+    float y[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) y[k] = threadIdx.x + k;
+    const float fa = (float)a, fb = (float)b;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) y[k] = fmaf(y[k], fa, fb);
+    }
+    float ys = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) ys += y[k];
+    if ((double)ys == 123.456) out[0] = ys;
+}
+
 int main() {
     double* d;
     cudaMalloc(&d, 64);
@@ -110,6 +157,21 @@ int main() {
         // mixed: 4 DMMA + 32 DFMA per warp-iteration; dfma_ffma: 32 DFMA (+ 32 FFMA) per thread-iteration
         const double flop = pass ? 2.0 * 32 * iters * (double)grid * 256 : 2.0 * (4 * 256.0 + 32 * 32.0) * iters * grid * 8;
         printf("%s: %.3f ms  %.2f FP64 TFLOP/s\n", pass ? "DFMA + FFMA 1:1 (FP64 flop only)" : "DMMA + DFMA mixed 1:1", best, flop / (best * 1e-3) / 1e12);
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int w = 0; w < 3; ++w) { if (pass) ffma_only_kernel<<<grid, 256>>>(d, iters, 1.0000001, 1e-9); else dmma_ffma_kernel<<<grid, 256>>>(d, iters, 1.0000001, 1e-9); }
+        cudaDeviceSynchronize();
+        float best = 1e30f;
+        for (int r = 0; r < 5; ++r) {
+            cudaEventRecord(e0);
+            if (pass) ffma_only_kernel<<<grid, 256>>>(d, iters, 1.0000001, 1e-9); else dmma_ffma_kernel<<<grid, 256>>>(d, iters, 1.0000001, 1e-9);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            best = ms < best ? ms : best;
+        }
+        printf("%s: %.3f ms\n", pass ? "64 FFMA per iteration alone" : "4 DMMA + 64 FFMA per iteration", best);
     }
     printf("cudaGetLastError: %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
