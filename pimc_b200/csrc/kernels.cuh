@@ -1184,10 +1184,26 @@ struct PairParams {
     double dSep; int want_hist; int f2_parity; int M;
 };
 
+#ifndef PIMCB_PAIR_UNROLL
+#define PIMCB_PAIR_UNROLL 2
+#endif
+#ifndef PIMCB_PAIR_MINB
+#define PIMCB_PAIR_MINB 4
+#endif
+
+// The table gathers are the long pole (46 % of the stall samples of the one-pair-at-a-time version were a warp waiting
+// for its single outstanding gather): every thread works on U partners at once -- U separations, U (or 2 U) gathers
+// in flight -- and then accumulates them in the original partner order, so the sums are bit-identical to the
+// sequential loop.  Measured on 64 C2 configurations (gsf action): U = 1: 4.35 ms, U = 2 (64 registers, 4 CTAs/SM):
+// 3.34 ms, U = 3: 3.7 ms, U = 4: 3.8 - 4.9 ms (occupancy).  At U = 2 the kernel moves 6.8 TB/s of 32-byte sectors out
+// of L2; interleaving V and dV/dr into one (V, dV/dr) table to halve the sectors of the force slices was tried and is
+// SLOWER (3.9 - 4.2 ms): it doubles the footprint of the V-only reads and the L2 hit rate (66 %) pays for it.  A
+// persisting-L2 access-policy window on either table (79 MB available) changes nothing (3.37 ms).
 template <int ND, bool WANT_F2>
-__global__ void __launch_bounds__(256) pair_kernel(const double* __restrict__ pos, int nslices, int N, int Npad, BoxDev box,
+__global__ void __launch_bounds__(256, PIMCB_PAIR_MINB) pair_kernel(const double* __restrict__ pos, int nslices, int N, int Npad, BoxDev box,
                                                     PairParams pp, double* __restrict__ vint, double* __restrict__ f2,
                                                     int* __restrict__ hist) {
+    constexpr int U = PIMCB_PAIR_UNROLL;
     extern __shared__ __align__(16) double sm[];
     double* xs = sm;
     __shared__ double redV[8], redF[8];
@@ -1205,32 +1221,50 @@ __global__ void __launch_bounds__(256) pair_kernel(const double* __restrict__ po
             double F[ND];
 #pragma unroll
             for (int d = 0; d < ND; ++d) F[d] = 0.0;
-            const int klast = do_f2 ? N - 1 : khalf;
-            for (int kk = 1; kk <= klast; ++kk) {
-                int j = i + kk;
-                if (j >= N) j -= N;
-                // V-half: pairs (i, i+kk), kk <= N/2, (for even N and kk == N/2 only i < N/2)
-                const bool vhalf = (kk < khalf) || (kk == khalf && ((N & 1) || i < khalf));
-                if (!do_f2 && !vhalf) continue;
-                double sep[ND];
-                double r;
-                if (do_f2) {
-                    r = minimage_norm<ND>(xs, Npad, i, j, box, sep);            // getSeparation(bead1,bead2), action.cpp:1211
-                } else {
-                    const int lo = min(i, j), hi = max(i, j);
-                    r = minimage_norm<ND>(xs, Npad, hi, lo, box, sep);          // getSeparation(bead2,bead1), action.cpp:934
-                }
-                if (vhalf) {
-                    vsum += table_direct(pp.V, pp.len, pp.dr, pp.extV[0], pp.extV[1], r);
-                    if (pp.want_hist) {
-                        const int nR = __double2int_rz(__ddiv_rn(r, pp.dSep));  // action.cpp:221
-                        if (nR >= 0 && nR < kNPCFSEP) atomicAdd(&shist[nR], 1);
+            // V-half: pairs (i, i+kk), kk <= N/2 (for even N and kk == N/2 only i < N/2); with forces the whole ring
+            const int kv = ((N & 1) || i < khalf) ? khalf : khalf - 1;       // last kk that contributes to V
+            const int klast = do_f2 ? N - 1 : kv;
+            for (int kk0 = 1; kk0 <= klast; kk0 += U) {
+                double r[U], sep[U][ND], vv[U], dv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int kk = min(kk0 + u, klast);                      // surplus slots recompute the last partner
+                    int j = i + kk;
+                    if (j >= N) j -= N;
+                    if (do_f2) {
+                        r[u] = minimage_norm<ND>(xs, Npad, i, j, box, sep[u]);          // getSeparation(bead1,bead2), action.cpp:1211
+                    } else {
+                        const int lo = min(i, j), hi = max(i, j);
+                        r[u] = minimage_norm<ND>(xs, Npad, hi, lo, box, sep[u]);        // getSeparation(bead2,bead1), action.cpp:934
                     }
                 }
-                if (do_f2) {
-                    const double g = __ddiv_rn(table_direct(pp.dVdr, pp.len, pp.dr, pp.extdV[0], pp.extdV[1], r), r);
 #pragma unroll
-                    for (int d = 0; d < ND; ++d) F[d] = fma(g, sep[d], F[d]);
+                for (int u = 0; u < U; ++u) {                                // all gathers of the group are issued here
+                    const int kidx = __double2int_rz(__ddiv_rn(r[u], pp.dr));
+                    const bool inside = kidx > 0 && kidx < pp.len;
+                    const bool live = kk0 + u <= klast;
+                    const bool vhalf = live && kk0 + u <= kv;
+                    vv[u] = 0.0;
+                    dv[u] = 0.0;
+                    if (vhalf) vv[u] = inside ? __ldg(pp.V + kidx) : (kidx <= 0 ? pp.extV[0] : pp.extV[1]);
+                    if (WANT_F2 && do_f2 && live) dv[u] = inside ? __ldg(pp.dVdr + kidx) : (kidx <= 0 ? pp.extdV[0] : pp.extdV[1]);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool live = kk0 + u <= klast;
+                    const bool vhalf = live && kk0 + u <= kv;
+                    if (vhalf) {
+                        vsum += vv[u];
+                        if (pp.want_hist) {
+                            const int nR = __double2int_rz(__ddiv_rn(r[u], pp.dSep));   // action.cpp:221
+                            if (nR >= 0 && nR < kNPCFSEP) atomicAdd(&shist[nR], 1);
+                        }
+                    }
+                    if (WANT_F2 && do_f2 && live) {
+                        const double g = __ddiv_rn(dv[u], r[u]);
+#pragma unroll
+                        for (int d = 0; d < ND; ++d) F[d] = fma(g, sep[u][d], F[d]);
+                    }
                 }
             }
             if (do_f2) {
