@@ -492,6 +492,33 @@ def run_ours(args, shape, q):
                 "bound": "L2/HBM gather: 8-byte table reads move 32-byte sectors; the 106 MB of tables exceed what one L2 "
                          "partition keeps, ncu shows 6.3 GB of DRAM reads per launch (profiles/traffic.json)"}
 
+    # ---- secondary: direct minimum-image S(q) for non-commensurate (`float`) wave-vectors --------
+    direct = None
+    if not args.no_pair:
+        nqd = 8
+        qd = synth.float_q(nqd, shape.ndim)
+        dctx = api.Context(local, shape.ndim)
+        dctx.set_box(shape.side)
+        dctx.set_qvecs(qd)
+        nb = min(B, 16)
+        dctx.stage(pinned[0].array[:nb], shape.N)
+        dctx.measure()
+        dctx.set_profiling(True)
+        nrep = 5
+        for _ in range(nrep):
+            dctx.measure()
+        kt = dctx.kernel_times(reset=True)
+        dctx.set_profiling(False)
+        dkey = [k for k in kt if "direct" in k][0]
+        d_s = kt[dkey][0] * 1e-3 / max(1, kt[dkey][1])
+        pairs_q = nb * nqd * shape.M * shape.N * (shape.N - 1) // 2
+        dflop = pairs_q * (shape.ndim * 8 + 20 + 1)               # 45 flop per (pair, q) in 3-D
+        direct = {"metric": "direct min-image S(q), non-commensurate q (ssf_direct_kernel)", "nq": nqd, "configurations": nb,
+                  "avg_launch_ms": d_s * 1e3, "launches_timed": kt[dkey][1], "pair_q_terms_per_launch": pairs_q,
+                  "achieved_tflops": dflop / d_s / 1e12, "peak_tflops": peak_tflops, "frac": dflop / d_s / 1e12 / peak_tflops,
+                  "terms_per_s": pairs_q / d_s, "bound": "fp64"}
+        dctx.close()
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak" if args.shard == "config" else "strong",
@@ -505,7 +532,7 @@ def run_ours(args, shape, q):
                    "l2": f"{use_slots} resident batches rotated ({footprint_mb:.0f} MB > 126 MB L2)",
                    "rho_mode": args.rho_mode, "corr_mode": args.corr_mode,
                    "host_binding": (f"rank bound to {len(numa_cpus)} GPU-local CPUs (NVML affinity)" if numa_cpus else "none")},
-        "clocks": clocks, "e2e": e2e, "latency": latency, "gpu_launches": int(launches), "roofline": roofline, "pair_sums": pair,
+        "clocks": clocks, "e2e": e2e, "latency": latency, "gpu_launches": int(launches), "roofline": roofline, "pair_sums": pair, "ssf_direct": direct,
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
