@@ -75,6 +75,12 @@ int pimcb_set_corr_mode(pimcb_ctx* ctx, int mode);
 int pimcb_stage_beads(pimcb_ctx* ctx, const double* beads_aos, int M, int N, int N_ext);
 /* B independent configurations, contiguous double[B][M][N_ext][ndim] (walker batch). */
 int pimcb_stage_batch(pimcb_ctx* ctx, const double* beads_aos, int B, int M, int N, int N_ext);
+/* Asynchronous form for page-locked sources (pimcb_host_alloc / pimcb_host_register): returns as soon as the DMA is
+ * enqueued, so a pipelined caller keeps the host link busy back to back; `beads_aos` must stay untouched until
+ * pimcb_stage_wait returns (or until results computed from it have been read).  Pageable sources are snapshotted
+ * synchronously exactly as by pimcb_stage_batch. */
+int pimcb_stage_batch_async(pimcb_ctx* ctx, const double* beads_aos, int B, int M, int N, int N_ext);
+int pimcb_stage_wait(pimcb_ctx* ctx);
 /* Same, into device slot `slot` (0 <= slot < pimcb_num_slots) without making it current; used to keep
  * several batches resident.  pimcb_select_slot makes a staged slot the current input. */
 int pimcb_num_slots(const pimcb_ctx* ctx);

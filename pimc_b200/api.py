@@ -21,7 +21,7 @@ NPCFSEP = 50
 # every symbol include/pimc_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "pimcb_create", "pimcb_destroy", "pimcb_last_error", "pimcb_version", "pimcb_set_box", "pimcb_set_qvecs",
-    "pimcb_num_commensurate", "pimcb_set_rho_mode", "pimcb_set_corr_mode", "pimcb_stage_beads", "pimcb_stage_batch", "pimcb_num_slots",
+    "pimcb_num_commensurate", "pimcb_set_rho_mode", "pimcb_set_corr_mode", "pimcb_stage_beads", "pimcb_stage_batch", "pimcb_stage_batch_async", "pimcb_stage_wait", "pimcb_num_slots",
     "pimcb_stage_batch_slot", "pimcb_select_slot", "pimcb_host_alloc", "pimcb_host_free", "pimcb_host_register",
     "pimcb_host_unregister", "pimcb_ssf", "pimcb_isf", "pimcb_ssf_isf", "pimcb_measure", "pimcb_reset_bins",
     "pimcb_read_bins", "pimcb_bins_device_ptr", "pimcb_sync", "pimcb_stream", "pimcb_set_pair_table",
@@ -59,6 +59,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.pimcb_set_corr_mode.argtypes = [vp, C.c_int]
     lib.pimcb_stage_beads.argtypes = [vp, _dp, C.c_int, C.c_int, C.c_int]
     lib.pimcb_stage_batch.argtypes = [vp, _dp, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.pimcb_stage_batch_async.argtypes = [vp, _dp, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.pimcb_stage_wait.argtypes = [vp]
     lib.pimcb_num_slots.argtypes = [vp]
     lib.pimcb_stage_batch_slot.argtypes = [vp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.pimcb_select_slot.argtypes = [vp, C.c_int]
@@ -197,6 +199,17 @@ class Context:
             self._chk(self.lib.pimcb_stage_batch_slot(self._h, slot, _ptr(beads), B, M, N, Next))
             self._slot_shapes[slot] = (B, M, N)
         return self
+
+    def stage_async(self, beads, N: int):
+        """Page-locked source: enqueue the DMA and return; keep `beads` untouched until stage_wait() / results are read."""
+        beads, B, M, Next, nd = self._batch(beads, N)
+        assert nd == self.ndim
+        self._chk(self.lib.pimcb_stage_batch_async(self._h, _ptr(beads), B, M, N, Next))
+        self.shape = (B, M, N)
+        return self
+
+    def stage_wait(self):
+        self._chk(self.lib.pimcb_stage_wait(self._h))
 
     def select_slot(self, slot: int):
         self._chk(self.lib.pimcb_select_slot(self._h, slot))

@@ -76,8 +76,10 @@ struct PinBuf {
 
 struct Slot {
     DevBuf pos;            // pos[b][t][d][Npad]
-    int B = 0, M = 0, N = 0, Npad = 0;
+    DevBuf aos;            // landing buffer of the zero-bounce path: the reference AoS array as DMA'd
+    int B = 0, M = 0, N = 0, Npad = 0, Next = 0;
     bool staged = false;
+    bool needs_transpose = false;     // aos holds the data; the first consumer transposes it on the compute stream
     cudaEvent_t ready = nullptr;      // H2D (+ transpose) complete
     cudaEvent_t consumed = nullptr;   // last kernel reading this slot has been enqueued before this event
 };
@@ -113,7 +115,6 @@ struct pimcb_ctx {
     int cur = -1;
     PinBuf pin[2];
     int pin_next = 0;
-    DevBuf d_aos;                          // device AoS scratch for the zero-bounce path
     // work buffers
     DevBuf d_rho, d_cfg, d_bins, d_partial;
     long n_acc = 0;
@@ -411,6 +412,8 @@ int launch_direct(pimcb_ctx* c, const Slot& s) {
     return 0;
 }
 
+int materialize(pimcb_ctx* c, Slot& s);
+
 // rows != nullptr (pimcb_measure): only the sum over configurations is wanted, so the correlation may write
 // quad-summed rows; *rows = number of rows of d_cfg to accumulate into the bin.
 int run_estimators(pimcb_ctx* c, Slot** sp, int* rows = nullptr) {
@@ -431,6 +434,7 @@ int run_estimators(pimcb_ctx* c, Slot** sp, int* rows = nullptr) {
     rc = c->d_cfg.ensure(sizeof(double) * len * s->B);
     if (rc) return rc;
     CU(cudaStreamWaitEvent(c->stream, s->ready, 0));
+    if ((rc = materialize(c, *s))) return rc;
     if ((rc = launch_rho(c, *s))) return rc;
     // quad-summed rows only when every S(q) comes from the correlation (no direct min-image q writes per-configuration rows)
     const bool partial = rows != nullptr && c->nsel == 0;
@@ -457,7 +461,31 @@ int copy_out(pimcb_ctx* c, const Slot& s, double* ssf_out, double* isf_out) {
     return 0;
 }
 
-int stage_into(pimcb_ctx* c, int slot, const double* beads, int B, int M, int N, int Next) {
+// Makes sure slot s is in the kernels' SoA layout: a slot staged through the zero-bounce path is transposed here, on
+// the compute stream, so that the copy stream carries nothing but back-to-back DMAs.
+int materialize(pimcb_ctx* c, Slot& s) {
+    if (!s.needs_transpose) return 0;
+    const int nd = c->ndim;
+    const size_t nsl = static_cast<size_t>(s.B) * s.M;
+    const size_t smem = sizeof(double) * s.N * nd;
+    const int grid = static_cast<int>(std::min<size_t>(nsl, static_cast<size_t>(c->sm_count) * 8));
+    int rc = 0;
+#define LAUNCH_T(ND)                                                                                  \
+    rc = set_smem(aos_to_soa_kernel<ND>, smem); if (rc) return rc;                                     \
+    aos_to_soa_kernel<ND><<<grid, 256, smem, c->stream>>>(s.aos.as<double>(), s.pos.as<double>(), static_cast<int>(nsl), s.N, s.Next, s.Npad)
+    {
+        KTimer kt(c, K_TRANSPOSE);
+        if (nd == 1) { LAUNCH_T(1); } else if (nd == 2) { LAUNCH_T(2); } else { LAUNCH_T(3); }
+    }
+#undef LAUNCH_T
+    CU(cudaGetLastError());
+    s.needs_transpose = false;
+    return 0;
+}
+
+// wait = false (pimcb_stage_batch_async): a page-locked source is NOT waited for; the caller keeps it untouched until
+// pimcb_stage_wait or any later synchronising call on this slot's data.
+int stage_into(pimcb_ctx* c, int slot, const double* beads, int B, int M, int N, int Next, bool wait = true) {
     if (!c) return fail(PIMCB_EINVAL, "null ctx");
     if (!beads || B < 1 || M < 1 || N < 1 || Next < N) return fail(PIMCB_EINVAL, "bad staging arguments (B=%d M=%d N=%d N_ext=%d)", B, M, N, Next);
     if (slot < 0 || slot >= kSlots) return fail(PIMCB_EINVAL, "slot %d out of range", slot);
@@ -478,25 +506,17 @@ int stage_into(pimcb_ctx* c, int slot, const double* beads, int B, int M, int N,
     const bool pinned = cudaPointerGetAttributes(&attr, beads) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
     if (pinned) {
-        // zero-bounce path: DMA the reference AoS array as-is, transpose on the device
+        // zero-bounce path: DMA the reference AoS array as-is into the slot's landing buffer; the transpose runs later
+        // on the compute stream (materialize), so consecutive stagings are back-to-back DMAs on the copy stream
         const size_t aos_bytes = sizeof(double) * nsl * Next * nd;
-        rc = c->d_aos.ensure(aos_bytes);
+        rc = s.aos.ensure(aos_bytes);
         if (rc) return rc;
-        CU(cudaMemcpyAsync(c->d_aos.p, beads, aos_bytes, cudaMemcpyHostToDevice, c->copy_stream));
-        const size_t smem = sizeof(double) * N * nd;
-        const int grid = static_cast<int>(std::min<size_t>(nsl, static_cast<size_t>(c->sm_count) * 8));
-#define LAUNCH_T(ND)                                                                                  \
-        rc = set_smem(aos_to_soa_kernel<ND>, smem); if (rc) return rc;                                 \
-        aos_to_soa_kernel<ND><<<grid, 256, smem, c->copy_stream>>>(c->d_aos.as<double>(), s.pos.as<double>(), static_cast<int>(nsl), N, Next, Npad)
-        {
-            KTimer kt(c, K_TRANSPOSE, c->copy_stream);
-            if (nd == 1) { LAUNCH_T(1); } else if (nd == 2) { LAUNCH_T(2); } else { LAUNCH_T(3); }
-        }
-#undef LAUNCH_T
-        CU(cudaGetLastError());
-        // the caller may mutate its buffer when we return: the DMA must have consumed it
+        CU(cudaMemcpyAsync(s.aos.p, beads, aos_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        s.Next = Next;
+        s.needs_transpose = true;
         CU(cudaEventRecord(s.ready, c->copy_stream));
-        CU(cudaEventSynchronize(s.ready));
+        // the caller may mutate its buffer when we return: the DMA must have consumed it
+        if (wait) CU(cudaEventSynchronize(s.ready));
     } else {
         // pageable source: pack AoS -> SoA into the next pinned bounce buffer, then one H2D
         PinBuf& pb = c->pin[c->pin_next];
@@ -517,6 +537,7 @@ int stage_into(pimcb_ctx* c, int slot, const double* beads, int B, int M, int N,
         CU(cudaMemcpyAsync(s.pos.p, pb.p, soa_bytes, cudaMemcpyHostToDevice, c->copy_stream));
         CU(cudaEventRecord(pb.done, c->copy_stream));
         CU(cudaEventRecord(s.ready, c->copy_stream));
+        s.needs_transpose = false;
     }
     s.staged = true;
     return 0;
@@ -579,12 +600,13 @@ int pimcb_destroy(pimcb_ctx* c) {
     cudaStreamSynchronize(c->copy_stream);
     for (auto& s : c->slots) {
         s.pos.release();
+        s.aos.release();
         if (s.ready) cudaEventDestroy(s.ready);
         if (s.consumed) cudaEventDestroy(s.consumed);
     }
     for (auto& p : c->pin) { p.release(); if (p.done) cudaEventDestroy(p.done); }
     c->h_out.release();
-    for (DevBuf* b : {&c->d_q, &c->d_comm, &c->d_qn, &c->d_qidx, &c->d_plan, &c->d_aos, &c->d_rho, &c->d_cfg, &c->d_bins, &c->d_partial,
+    for (DevBuf* b : {&c->d_q, &c->d_comm, &c->d_qn, &c->d_qidx, &c->d_plan, &c->d_rho, &c->d_cfg, &c->d_bins, &c->d_partial,
                       &c->d_V, &c->d_dV, &c->d_vint, &c->d_f2, &c->d_hist, &c->d_scratch, &c->d_sched, &c->d_qdone})
         b->release();
     for (int k = 0; k < kKernels; ++k) { cudaEventDestroy(c->ev0[k]); cudaEventDestroy(c->ev1[k]); }
@@ -850,6 +872,22 @@ int pimcb_stage_batch(pimcb_ctx* c, const double* beads, int B, int M, int N, in
     return 0;
 }
 
+int pimcb_stage_batch_async(pimcb_ctx* c, const double* beads, int B, int M, int N, int Next) {
+    if (!c) return fail(PIMCB_EINVAL, "null ctx");
+    const int slot = (c->cur + 1 + kSlots) % kSlots;
+    int rc = stage_into(c, slot, beads, B, M, N, Next, false);
+    if (rc) return rc;
+    c->cur = slot;
+    return 0;
+}
+
+int pimcb_stage_wait(pimcb_ctx* c) {
+    if (!c) return fail(PIMCB_EINVAL, "null ctx");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    return 0;
+}
+
 int pimcb_stage_beads(pimcb_ctx* c, const double* beads, int M, int N, int Next) {
     return pimcb_stage_batch(c, beads, 1, M, N, Next);
 }
@@ -972,6 +1010,7 @@ int pimcb_pair_sums(pimcb_ctx* c, double* vint, double* f2, int* sephist, double
     PairParams pp{c->d_V.as<double>(), c->d_dV.as<double>(), c->tab_len, c->dr, {c->extV[0], c->extV[1]}, {c->extdV[0], c->extdV[1]},
                   sephist ? dSep : 1.0, sephist ? 1 : 0, f2_parity, s->M};
     CU(cudaStreamWaitEvent(c->stream, s->ready, 0));
+    if ((rc = materialize(c, *s))) return rc;
     {
         KTimer kt(c, K_PAIR);
         const size_t smem = sizeof(double) * nd * s->Npad;

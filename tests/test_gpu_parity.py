@@ -249,8 +249,26 @@ def test_pinned_source_takes_device_transpose_path(api, orc):
     with make_ctx(api, s, q) as ctx:
         a = ctx.stage(batch, s.N).ssf_isf()
         b = ctx.stage(pin.array, s.N).ssf_isf()
+        # asynchronous staging of page-locked sources: two batches enqueued back to back, results read afterwards
+        pin2 = api.PinnedArray(batch.shape)
+        pin2.array[...] = batch[::-1]
+        ctx.stage_async(pin.array, s.N)
+        c1 = ctx.ssf_isf()
+        ctx.stage_async(pin2.array, s.N)
+        ctx.stage_async(pin.array, s.N)
+        ctx.stage_wait()
+        c2 = ctx.ssf_isf()
+        ctx.reset_bins()
+        ctx.stage_async(pin2.array, s.N)
+        ctx.measure()
+        bs, bi, n = ctx.read_bins()
     pin.free()
+    pin2.free()
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(a[0], c1[0]) and np.array_equal(a[1], c1[1])
+    assert np.array_equal(a[0], c2[0]) and np.array_equal(a[1], c2[1])
+    assert n == 3
+    assert_parity(bi, a[1].sum(axis=0), "bin after async staging")
 
 
 @pytest.mark.parametrize("shape", [synth.C1, synth.C2])
