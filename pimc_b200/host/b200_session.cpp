@@ -32,7 +32,10 @@ B200Session::B200Session(const Path& path) : path_(path) {
     check(pimcb_set_box(ctx_, side, periodic), "pimcb_set_box");
 }
 
-B200Session::~B200Session() { pimcb_destroy(ctx_); }
+B200Session::~B200Session() {
+    if (locked_ptr_) pimcb_host_unregister(const_cast<void*>(locked_ptr_));
+    pimcb_destroy(ctx_);
+}
 
 B200Session& B200Session::get(const Path& path) {
     auto& m = registry().map;
@@ -67,6 +70,20 @@ void B200Session::stageIfNeeded() {
     const auto ext = path_.get_beads_extents();
     const int M = path_.numTimeSlices;
     const int N = path_.getTrueNumParticles();           // diagonal configuration: N active beads on every slice
+    // Page-lock Path::beads once (again whenever the array was reallocated, i.e. after particle insertions grew it):
+    // staging is then a single DMA of the reference array as it lies, no host-side repacking.  A refused registration
+    // only means the bounce-buffer path is used.
+    const void* base = path_.get_beads_data_pointer();
+    const size_t bytes = sizeof(double) * static_cast<size_t>(M) * ext[1] * NDIM;
+    if (base != locked_ptr_ || bytes != locked_bytes_) {
+        if (locked_ptr_) pimcb_host_unregister(const_cast<void*>(locked_ptr_));
+        locked_ptr_ = nullptr;
+        locked_bytes_ = 0;
+        if (!std::getenv("PIMCB_NO_PAGE_LOCK") && pimcb_host_register(const_cast<void*>(base), bytes) == 0) {
+            locked_ptr_ = base;
+            locked_bytes_ = bytes;
+        }
+    }
     check(pimcb_stage_beads(ctx_, path_.get_beads_data_pointer(), M, N, static_cast<int>(ext[1])), "pimcb_stage_beads");
     staged_ = true;
     have_sf_ = have_pair_ = false;

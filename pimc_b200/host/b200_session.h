@@ -56,6 +56,8 @@ private:
 
     const Path& path_;
     pimcb_ctx* ctx_ = nullptr;
+    const void* locked_ptr_ = nullptr;      // Path::beads storage currently page-locked (pimcb_host_register)
+    size_t locked_bytes_ = 0;
     size_t nq_ = 0;
     bool hooked_ = false, staged_ = false, have_sf_ = false, have_pair_ = false, have_table_ = false;
     bool pair_has_f2_ = false;
