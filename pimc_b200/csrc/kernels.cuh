@@ -414,8 +414,9 @@ constexpr int kMmaStride = kMmaChunk + 4;    // plane stride in doubles: 32 B pa
 constexpr int kMmaWarps = 4;                 // warps per CTA, each with private operand planes
 
 struct MmaPlan {
-    const int* gout;    // [G][2^ND]  q index per sign pattern or -1
-    const int* gdesc;   // [G][8]     {rowRe+, rowIm+, rowRe-, rowIm-, signIm-, colRe, colIm, 0}: where the group's factors live
+    const unsigned* unfold;   // [2 nq]  output k = 2 q + {re, im}:  rho = (+-) C[o0] (+-) C[o1], packed by the host as
+                              //         o0 | o1 << 12 | neg0 << 24 | neg1 << 25 (offsets in doubles into the staged C tiles);
+                              //         the host resolves sign patterns, coinciding factors and zero planes once per q-set
     int G, nL, nR;      // groups; L rows / R cols in use INCLUDING the reserved zero plane (index nL-1 / nR-1);
                         // the kernel's MT x NT tiles cover them, everything from the zero plane on is cleared
     // small lookup tables, passed by value so that they sit in the constant bank:
@@ -446,7 +447,8 @@ template <int ND, int MT, int NT, int NM>
 __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __restrict__ pos, const MmaPlan plan,
                                                                double* __restrict__ rho, int nslices, int N, int Npad, int nq,
                                                                int3 nmax, double3 kphase, unsigned* __restrict__ sched,
-                                                               int zero_mask, int split, double* __restrict__ partial, int M) {
+                                                               int zero_mask, int split, double* __restrict__ partial, int M,
+                                                               unsigned ticket_wrap) {
     constexpr int NPAT = 1 << ND;
     constexpr int ML = MT, NR = NT;                         // every tile is computed; unused rows / cols are zero planes
     constexpr int ntile = ML * NR;
@@ -458,13 +460,11 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
     double* Lp = sm + warp * region;                        // [8*ML][kMmaStride]   this warp's L planes
     double* Rp = Lp + 8 * ML * kMmaStride;                  // [8*NR][kMmaStride]   this warp's R planes
     double* Cw = Rp + 8 * NR * kMmaStride;                  // [ntile][64]          this warp's C staging
-    int* s_gout = reinterpret_cast<int*>(sm + kMmaWarps * region);   // [G][NPAT]  CTA copy of the plan tables
-    int* s_gdesc = s_gout + ((G * NPAT + 3) & ~3);          // [G][8], 16-byte aligned
+    unsigned* s_unfold = reinterpret_cast<unsigned*>(sm + kMmaWarps * region);   // [2 nq]  CTA copy of the unfold table
     const int il = lane;                                    // particle of the block this lane owns in phase A
     const int nchunk = (N + kMmaChunk - 1) / kMmaChunk;     // particle blocks of a slice
 
-    for (int w = threadIdx.x; w < G * NPAT; w += blockDim.x) s_gout[w] = __ldg(plan.gout + w);
-    for (int w = threadIdx.x; w < G * 8; w += blockDim.x) s_gdesc[w] = __ldg(plan.gdesc + w);
+    for (int w = threadIdx.x; w < 2 * nq; w += blockDim.x) s_unfold[w] = __ldg(plan.unfold + w);
     // the reserved zero plane and the padding rows / columns (never written by phase A) must be zero
     for (int w = (plan.nL - 1) * kMmaStride + lane; w < 8 * ML * kMmaStride; w += 32) Lp[w] = 0.0;
     for (int w = (plan.nR - 1) * kMmaStride + lane; w < 8 * NR * kMmaStride; w += 32) Rp[w] = 0.0;
@@ -487,12 +487,14 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
             roff[m] = col >= 0 ? col * kMmaStride + il : -1;
         }
     }
-    // requested at the start of a slice, needed at its last particle block.  (ptxas warp-aggregates every spelling of
-    // this add -- atom.add, atom.inc, run-time operand -- and broadcasts the result with a shuffle at once, so the warp
-    // does wait one atomic round trip per slice here: 3 % of the stall samples, covered by the other resident warps.)
+    // requested at the start of a slice, needed at its last particle block.  atomicInc with a RUN-TIME wrap limit
+    // (0xffffffff, a kernel argument): ptxas warp-aggregates every form of "add 1" -- atomicAdd, atom.add, atom.inc with a
+    // literal limit -- and broadcasts the aggregated result with a shuffle right behind the atomic, which made every warp
+    // sit out one atomic round trip per slice (10 % of all stall samples); this form stays a plain ATOMG.INC whose
+    // result is first read ~7 particle blocks later.
     auto ticket_request = [&]() {
         unsigned v = 0;
-        if (lane == 0) v = atomicAdd(sched, 1u);
+        if (lane == 0) v = atomicInc(sched, ticket_wrap);
         return v;
     };
     auto fetch = [&](int sl, int ch, int dep, double (&x)[3]) {
@@ -717,36 +719,14 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                 }
         }
         __syncwarp();
-        auto centry = [&](int row, int col) {
-            return Cw[((row >> 3) * NR + (col >> 3)) * 64 + ((row & 7) * 4 + ((col & 7) >> 1)) * 2 + (col & 1)];
-        };
         const int cb = sl / M, ct = sl - cb * M;
-        const size_t out_re = rho_pair_base(cb, 0, 0, nq, rho_tblocks(M)) + rho_slice_off(ct, nq);   // + 8 q (+ 4 for the sine part)
-        for (int w = lane; unfold && w < G * NPAT; w += 32) {
-            const int g = w / NPAT, pat = w - g * NPAT;
-            const int iq = s_gout[w];
-            if (iq < 0) continue;
-            const int4 d0 = reinterpret_cast<const int4*>(s_gdesc)[2 * g];
-            const int4 d1 = reinterpret_cast<const int4*>(s_gdesc)[2 * g + 1];
-            const int sa = pat & 1;                                // conj of the pattern with all signs flipped
-            const int sb = ND > 1 ? (((pat >> 1) & 1) ^ sa) : 0;
-            const int sc = ND > 2 ? (((pat >> 2) & 1) ^ sa) : 0;
-            const int cr = d1.y, ci = d1.z;                        // columns of Re / Im of the last factor
-            double re, im;
-            if constexpr (ND == 1) {
-                re = centry(d0.x, cr);
-                im = centry(d0.x, ci);
-            } else {
-                const int side = ND == 3 ? sb : 0;                 // 3-D: which of X Y / X conj(Y)
-                const int rr = side ? d0.z : d0.x, ri = side ? d0.w : d0.y;
-                const double sg = (side && d1.x < 0) ? -1.0 : 1.0;
-                const double k0 = centry(rr, cr), k1 = sg * centry(ri, ci), k2 = centry(rr, ci), k3 = sg * centry(ri, cr);
-                const int sl_ = ND == 3 ? sc : sb;                 // sign of the last multiplied factor
-                re = sl_ ? k0 + k1 : k0 - k1;
-                im = sl_ ? k3 - k2 : k3 + k2;
-            }
-            rho[out_re + 8 * iq] = re;
-            rho[out_re + 8 * iq + 4] = sa ? -im : im;
+        const size_t out_base = rho_pair_base(cb, 0, 0, nq, rho_tblocks(M)) + rho_slice_off(ct, nq);   // + 4 (2 q + {re, im})
+        for (int k = lane; unfold && k < 2 * nq; k += 32) {
+            const unsigned d = s_unfold[k];
+            const double a = Cw[d & 0xfffu], b = Cw[(d >> 12) & 0xfffu];
+            const double sa_ = __hiloint2double(__double2hiint(a) ^ static_cast<int>((d << 7) & 0x80000000u), __double2loint(a));
+            const double sb_ = __hiloint2double(__double2hiint(b) ^ static_cast<int>((d << 6) & 0x80000000u), __double2loint(b));
+            rho[out_base + 4 * k] = sa_ + sb_;
         }
         __syncwarp();
         item = item_next;

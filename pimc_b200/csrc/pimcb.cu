@@ -105,7 +105,9 @@ struct pimcb_ctx {
     size_t plan_off[7] = {0, 0, 0, 0, 0, 0, 0};   // int offsets of gout / ent / tasks / warp_first / gdesc / lmap / rmap in d_plan
     int mma_nL = 0, mma_nR = 0;            // L rows / R cols of the DMMA formulation (0 = not available)
     int last_rho_path = -1, last_ML = 0, last_NR = 0;   // what launch_rho used last: 0 generic, 1 DMMA lattice, 2 CUDA-core lattice
-    std::vector<int> mma_lmap, mma_rmap;
+    std::vector<int> mma_lmap, mma_rmap, mma_gout, mma_gdesc;   // host copies of the DMMA plan tables
+    int unfold_NR = -1;                    // N-tile count the device unfold table (d_unfold) was built for
+    DevBuf d_unfold;
     int lattice_J = 0;                     // 0 = choose from N; else forced (PIMCB_LATTICE_J)
     int lattice_warps = kLatticeWarps;     // warps per CTA of the lattice kernel (PIMCB_LATTICE_WARPS may lower it to 2)
     int rho_mode = 1;
@@ -219,6 +221,52 @@ int ensure_sched(pimcb_ctx* c, size_t words) {
     return 0;
 }
 
+// Unfold table of the DMMA rho kernel: for every output value k = 2 q + {re, im} the two entries of the staged C tiles
+// it is made of and their signs (kernels.cuh, MmaPlan::unfold).  With K0..K3 = C(rr,cr), C(ri,ci), C(rr,ci), C(ri,cr):
+//   rho_re = K0 -+ sg K1,   rho_im = +-(sg K3 +- K2)
+// where (rr, ri) are the rows of X^a Y^b or X^a conj(Y^b) (3-D, chosen by the relative sign of the second component),
+// sg = -1 when the stored row is the conjugate of the wanted one, and the remaining signs follow the sign pattern.
+int build_unfold(pimcb_ctx* c, int NR) {
+    if (c->unfold_NR == NR) return 0;
+    const int nd = c->ndim, npat = 1 << nd, G = c->ngroups, nq = c->nq;
+    const int zrow = c->mma_nL - 1;
+    auto off = [NR](int row, int col) {
+        return static_cast<unsigned>(((row >> 3) * NR + (col >> 3)) * 64 + ((row & 7) * 4 + ((col & 7) >> 1)) * 2 + (col & 1));
+    };
+    auto pack = [](unsigned o0, bool n0, unsigned o1, bool n1) { return o0 | (o1 << 12) | (n0 ? 1u << 24 : 0u) | (n1 ? 1u << 25 : 0u); };
+    std::vector<unsigned> tab(2 * static_cast<size_t>(nq), 0u);
+    for (int g = 0; g < G; ++g) {
+        const int* e = &c->mma_gdesc[static_cast<size_t>(g) * 8];
+        for (int pat = 0; pat < npat; ++pat) {
+            const int iq = c->mma_gout[static_cast<size_t>(g) * npat + pat];
+            if (iq < 0) continue;
+            const int sa = pat & 1;                                  // the pattern with all signs flipped is the conjugate
+            const int sb = nd > 1 ? (((pat >> 1) & 1) ^ sa) : 0;
+            const int sc = nd > 2 ? (((pat >> 2) & 1) ^ sa) : 0;
+            const int cr = e[5], ci = e[6];
+            if (nd == 1) {
+                tab[2 * iq + 0] = pack(off(e[0], cr), false, off(zrow, 0), false);
+                tab[2 * iq + 1] = pack(off(e[0], ci), sa != 0, off(zrow, 0), false);
+                continue;
+            }
+            const int side = nd == 3 ? sb : 0;
+            const int rr = side ? e[2] : e[0], ri = side ? e[3] : e[1];
+            const bool sgneg = side && e[4] < 0;
+            const int sl = nd == 3 ? sc : sb;                        // sign of the last multiplied factor
+            // re = K0 + (sl ? +sg : -sg) K1
+            tab[2 * iq + 0] = pack(off(rr, cr), false, off(ri, ci), sl ? sgneg : !sgneg);
+            // im = (sa ? -1 : 1) [ sg K3 + (sl ? -1 : 1) K2 ]
+            tab[2 * iq + 1] = pack(off(ri, cr), sgneg != (sa != 0), off(rr, ci), (sl != 0) != (sa != 0));
+        }
+    }
+    int rc = c->d_unfold.ensure(sizeof(unsigned) * tab.size());
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->d_unfold.p, tab.data(), sizeof(unsigned) * tab.size(), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));        // `tab` is a local
+    c->unfold_NR = NR;
+    return 0;
+}
+
 // ---- rho_q build + correlation + direct S(q) into d_cfg (per configuration results) ------------
 int launch_rho(pimcb_ctx* c, const Slot& s) {
     const int nd = c->ndim, nq = c->nq;
@@ -244,16 +292,17 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
     const bool mma_fits = ML > 0 && NR > 0 && c->mma_nL <= 128 && NR <= 4 && ML * NR <= 16 &&
                           c->mma_lmap.size() <= 81 && c->mma_rmap.size() <= 17 && (nd < 3 || c->nmax[1] <= 8);
     const size_t mma_smem = sizeof(double) * kMmaWarps * (8 * static_cast<size_t>(ML + NR) * kMmaStride + static_cast<size_t>(ML) * NR * 64) +
-                            sizeof(int) * (((static_cast<size_t>(c->ngroups) << nd) + 3) / 4 * 4 + 8 * static_cast<size_t>(c->ngroups));
-                            // per-warp operand planes + C staging, CTA copy of the plan tables
+                            sizeof(unsigned) * 2 * static_cast<size_t>(nq);
+                            // per-warp operand planes + C staging, CTA copy of the unfold table
     if (c->rho_mode == 1 && c->ngroups > 0 && mma_fits && mma_smem <= 160 * 1024) {
         const int3 nmax = make_int3(c->nmax[0], c->nmax[1], c->nmax[2]);
         const double twopi = 2.0 * M_PI;
         const double3 kph = make_double3(twopi / c->side[0], nd > 1 ? twopi / c->side[1] : 0.0, nd > 2 ? twopi / c->side[2] : 0.0);
         const int* pl = c->d_plan.as<int>();
         MmaPlan plan{};
-        plan.gout = pl + c->plan_off[0];
-        plan.gdesc = pl + c->plan_off[4];
+        (void)pl;
+        if ((rc = build_unfold(c, NR))) return rc;
+        plan.unfold = c->d_unfold.as<unsigned>();
         plan.G = c->ngroups; plan.nL = c->mma_nL; plan.nR = c->mma_nR;
         for (short& v : plan.lmap) v = -1;      // the unrolled kernels probe entries beyond this q-set's nmax
         for (short& v : plan.rmap) v = -1;
@@ -281,7 +330,7 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
         rho_lattice_mma_kernel<ND, MT, NT, NM><<<pgrid, 128, mma_smem, c->stream>>>(s.pos.as<double>(), plan, c->d_rho.as<double>(), \
                                                                                     nsl, s.N, s.Npad, nq, nmax, kph,         \
                                                                                     c->d_sched.as<unsigned>(), 0, split,     \
-                                                                                    c->d_partial.as<double>(), s.M); }
+                                                                                    c->d_partial.as<double>(), s.M, 0xffffffffu); }
         // 3-D with every |n_d| <= 2 (or 3): phase A fully unrolled; the R columns then fit one N tile
 #define LAUNCH_MMA(ND, MT, NT)                                                                                    \
         if (ND == 3 && NT == 1 && nm3 <= 2) LAUNCH_MMA_NM(ND, MT, NT, (ND == 3 && NT == 1 ? 2 : 0))                \
@@ -607,7 +656,7 @@ int pimcb_destroy(pimcb_ctx* c) {
     for (auto& p : c->pin) { p.release(); if (p.done) cudaEventDestroy(p.done); }
     c->h_out.release();
     for (DevBuf* b : {&c->d_q, &c->d_comm, &c->d_qn, &c->d_qidx, &c->d_plan, &c->d_rho, &c->d_cfg, &c->d_bins, &c->d_partial,
-                      &c->d_V, &c->d_dV, &c->d_vint, &c->d_f2, &c->d_hist, &c->d_scratch, &c->d_sched, &c->d_qdone})
+                      &c->d_V, &c->d_dV, &c->d_vint, &c->d_f2, &c->d_hist, &c->d_scratch, &c->d_sched, &c->d_qdone, &c->d_unfold})
         b->release();
     for (int k = 0; k < kKernels; ++k) { cudaEventDestroy(c->ev0[k]); cudaEventDestroy(c->ev1[k]); }
     for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -814,6 +863,10 @@ int pimcb_set_qvecs(pimcb_ctx* c, const double* q, int nq) {
             c->mma_nR = nR;
             c->mma_lmap = lmap;
             c->mma_rmap = rmap;
+            c->mma_gdesc = gdesc;
+            c->mma_gout.clear();
+            for (const Grp& g : groups) c->mma_gout.insert(c->mma_gout.end(), g.out.begin(), g.out.end());
+            c->unfold_NR = -1;
             align4();
             c->plan_off[4] = plan.size();
             plan.insert(plan.end(), gdesc.begin(), gdesc.end());
