@@ -529,7 +529,10 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
             // ---- phase A: thread = particle of the chunk -------------------------------------------------
             {
                 const bool live = ch * kMmaChunk + il < N;
-                const double lv = live ? 1.0 : 0.0;          // dead particles contribute zero rows (xc = 0 -> e = 1)
+                // Particles beyond N (ragged last block) must add nothing: their R entries (the powers of the last
+                // dimension's phase, incl. the column of ones) are zeroed with selects, so every product L x R vanishes
+                // and the L side needs no mask -- FP64 instructions are the scarce resource here, selects are not.
+                const double lv = live ? 1.0 : 0.0;
                 double ex_s, ex_c, ey_s = 0.0, ey_c = 1.0, ez_s = 0.0, ez_c = 1.0;
                 int qx = 0, qy = 0, qz = 0;                  // quadrant integers: the prefetch below depends on them
                 sincos_fast(kphase.x * xc[0], ex_s, ex_c, qx);
@@ -545,10 +548,10 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                 }
                 if constexpr (ND == 3 && NM > 0) {
                     // compile-time bounds: powers of the three phases in registers, (a,b) columns unrolled
-                    // (every L row carries the live mask through X or explicitly, so the R planes need none)
-                    double xr[NM + 1], xi[NM + 1], yr[NM + 1], yi[NM + 1], zr[NM + 1], zi[NM + 1];
-                    xr[0] = lv; xi[0] = 0.0; yr[0] = 1.0; yi[0] = 0.0; zr[0] = 1.0; zi[0] = 0.0;
-                    xr[1] = lv * ex_c; xi[1] = lv * ex_s; yr[1] = ey_c; yi[1] = ey_s; zr[1] = ez_c; zi[1] = ez_s;   // no multiply by (1, 0)
+                                        double xr[NM + 1], xi[NM + 1], yr[NM + 1], yi[NM + 1], zr[NM + 1], zi[NM + 1];
+                    xr[0] = 1.0; xi[0] = 0.0; yr[0] = 1.0; yi[0] = 0.0; zr[0] = lv; zi[0] = 0.0;
+                    xr[1] = ex_c; xi[1] = ex_s; yr[1] = ey_c; yi[1] = ey_s;          // first powers: no multiply by (1, 0)
+                    zr[1] = live ? ez_c : 0.0; zi[1] = live ? ez_s : 0.0;
 #pragma unroll
                     for (int m = 2; m <= NM; ++m) {
                         xr[m] = fma(xr[m - 1], ex_c, -xi[m - 1] * ex_s);
@@ -581,10 +584,10 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                                     d[0] = xr[a];
                                     d[kMmaStride] = xi[a];
                                 } else if (b > 0) {
-                                    d[0] = lv * yr[b];
-                                    d[kMmaStride] = lv * yi[b];
+                                    d[0] = yr[b];
+                                    d[kMmaStride] = yi[b];
                                 } else {
-                                    d[0] = lv;
+                                    d[0] = 1.0;
                                 }
                             }
                         }
@@ -607,9 +610,9 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                     }
                 }
                 if constexpr (ND == 1) {
-                    Lp[il] = lv;
+                    Lp[il] = 1.0;
                 } else if constexpr (ND == 2) {
-                    double pr = lv, pi = 0.0;
+                    double pr = 1.0, pi = 0.0;
                     for (int a = 0; a <= nmax.x; ++a) {
                         const int row = plan.lmap[a];
                         if (row >= 0) {
@@ -621,7 +624,7 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                         pr = nr;
                     }
                 } else {
-                    double xr = lv, xi = 0.0;
+                    double xr = 1.0, xi = 0.0;
                     for (int a = 0; a <= nmax.x; ++a) {
                         double yr = 1.0, yi = 0.0;
                         for (int b = 0; b <= nmax.y; ++b) {
@@ -638,10 +641,10 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                                     d[0] = xr;
                                     d[kMmaStride] = xi;
                                 } else if (b > 0) {                   // X = 1 (times the live mask)
-                                    d[0] = lv * yr;
-                                    d[kMmaStride] = lv * yi;
+                                    d[0] = yr;
+                                    d[kMmaStride] = yi;
                                 } else {
-                                    d[0] = lv;
+                                    d[0] = 1.0;
                                 }
                             }
                             const double nr = fma(yr, ey_c, -yi * ey_s);
