@@ -449,12 +449,10 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
                                                                int3 nmax, double3 kphase, unsigned* __restrict__ sched,
                                                                int zero_mask, int split, double* __restrict__ partial, int M,
                                                                unsigned ticket_wrap) {
-    constexpr int NPAT = 1 << ND;
     constexpr int ML = MT, NR = NT;                         // every tile is computed; unused rows / cols are zero planes
     constexpr int ntile = ML * NR;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) double sm[];
-    const int G = plan.G;
     constexpr int region = 8 * (ML + NR) * kMmaStride + ntile * 64;   // doubles of shared memory per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* Lp = sm + warp * region;                        // [8*ML][kMmaStride]   this warp's L planes
