@@ -57,6 +57,10 @@ class Oracle:
         L.orc_deriv_potential_action_tau.argtypes = [C.c_double, C.c_double, C.c_int, _dp, _dp, C.c_double, C.c_double]
         L.orc_deriv_potential_action_lambda.restype = C.c_double
         L.orc_deriv_potential_action_lambda.argtypes = [C.c_double, C.c_int, _dp, C.c_double]
+        L.orc_aziz_tail.restype = C.c_double
+        L.orc_aziz_tail.argtypes = [C.c_int, C.c_double]
+        L.orc_energy.argtypes = [C.c_int, _dp, _up, _dp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), _dp, _dp, _dp, _dp,
+                                 C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _dp]
         L.orc_time_slices.restype = C.c_int
         L.orc_time_slices.argtypes = [C.c_double, C.c_double, C.c_int, _dp]
         L.orc_qvectors.argtypes = [C.c_int, C.c_char_p, C.c_char_p, _dp, _dp, C.c_int]
@@ -214,6 +218,26 @@ class Oracle:
     def deriv_potential_action_lambda(self, f2_s, slice_, gradVFactor, tau) -> float:
         gf = _f64(gradVFactor)
         return self.lib.orc_deriv_potential_action_lambda(f2_s, slice_, _dptr(gf), tau)
+
+    def aziz_tail(self, rc, year=1979) -> float:
+        return self.lib.orc_aziz_tail(year, rc)
+
+    def energy(self, side, beads, N, vint, f2, VFactor, gradVFactor, period, tau, lam, tailV, mu=0.0, next_links=None) -> np.ndarray:
+        """EnergyEstimator::accumulate for one configuration -> [K, V, V_ext, V_int, E, E_mu, K/N, V/N, E/N]."""
+        beads, M, Next, nd = self._beads(beads)
+        side = _f64(side)
+        per = np.ones(nd, dtype=np.uint32)
+        vint, f2 = _f64(vint), _f64(f2)
+        vf, gf = _f64(VFactor), _f64(gradVFactor)
+        nl = None
+        if next_links is not None:
+            nl = np.ascontiguousarray(next_links, dtype=np.int32)
+        out = np.zeros(9)
+        rc = self.lib.orc_energy(nd, _dptr(side), per.ctypes.data_as(_up), _dptr(beads), M, N, Next,
+                                 nl.ctypes.data_as(C.POINTER(C.c_int)) if nl is not None else None, _dptr(vint), _dptr(f2),
+                                 _dptr(vf), _dptr(gf), period, tau, lam, mu, tailV, _dptr(out))
+        assert rc == 0
+        return out
 
     # -- output formatting -----------------------------------------------------------
     def format_row(self, estimator, norm, num_accumulated) -> str:

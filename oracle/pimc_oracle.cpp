@@ -666,6 +666,61 @@ int orc_dvec_to_string(int ndim, const double* v, char* buf, int buflen) {
     return off;
 }
 
+// AzizPotential tail correction, src/potential.cpp:1798-1806 (rc = potential cutoff, default side[NDIM-1]).
+double orc_aziz_tail(int year, double rc) {
+    const Aziz az(year);
+    const double rmorc = az.rm / rc;
+    const double t2 = az.C6 * pow(rmorc, 3.0) / 3.0;
+    const double t3 = az.C8 * pow(rmorc, 5.0) / 5.0;
+    const double t4 = az.C10 * pow(rmorc, 7.0) / 7.0;
+    return 2.0 * M_PI * az.epsilon * (-az.rm * az.rm * az.rm * (t2 + t3 + t4));
+}
+
+// EnergyEstimator::accumulate, src/estimator.cpp:940-1029 (PIMC mode: startSlice = 0, endSlice = M, sliceFactor = 1),
+// on top of the per-slice pair sums (Vint, gradVSquared) of this file; external potential "free" (Vext = 0).
+// Kinetic term: Path::getVelocity, include/path.h:189-203, over the links `next` ([M][Next][2], NULL = straight
+// world lines).  out[9] = {K, V, V_ext, V_int, E, E_mu, K/N, V/N, E/N} of ONE configuration.
+int orc_energy(int nd, const double* side, const unsigned* periodic, const double* beads, int M, int N, int Next,
+               const int* next, const double* vint, const double* f2, const double* VFactor, const double* gradVFactor,
+               int period, double tau, double lambda, double mu, double tailV_potential, double* out) {
+    double pSide[3], sideInv[3], volume = 1.0;
+    for (int d = 0; d < nd; ++d) { pSide[d] = periodic[d] * side[d]; sideInv[d] = 1.0 / side[d]; volume *= side[d]; }
+    const int numParticles = N, numTimeSlices = M;
+    const double tailV = (1.0 * numParticles * numParticles / volume) * tailV_potential;
+    const double kinNorm = (0.25 / (lambda * tau)) / (tau * numTimeSlices);          // constants.h:82
+    const double classicalKinetic = (0.5 * nd / tau) * numParticles;
+    double totK = 0.0;
+    for (int slice = 0; slice < M; ++slice)
+        for (int ptcl = 0; ptcl < N; ++ptcl) {
+            int ns = (slice + 1) % M, np = ptcl;
+            if (next) { ns = next[(static_cast<size_t>(slice) * Next + ptcl) * 2]; np = next[(static_cast<size_t>(slice) * Next + ptcl) * 2 + 1]; }
+            if (ns < 0 || np < 0) continue;                                           // XXX links: zero velocity
+            double v2 = 0.0;
+            for (int d = 0; d < nd; ++d) {
+                double v = beads[(static_cast<size_t>(ns) * Next + np) * nd + d] - beads[(static_cast<size_t>(slice) * Next + ptcl) * nd + d];
+                v -= pSide[d] * floor(v * sideInv[d] + 0.5);
+                v2 += v * v;
+            }
+            totK -= v2;
+        }
+    totK *= kinNorm;
+    double t1 = 0.0, t2 = 0.0, vop = 0.0;
+    for (int slice = 0; slice < M; ++slice) {
+        t1 += orc_deriv_potential_action_lambda(f2 ? f2[slice] : 0.0, slice, gradVFactor, tau);
+        t2 += orc_deriv_potential_action_tau(vint[slice], f2 ? f2[slice] : 0.0, slice, VFactor, gradVFactor, tau, lambda);
+        if (!(slice % period)) vop += vint[slice];
+    }
+    t1 *= lambda / (tau * numTimeSlices);
+    t2 /= 1.0 * numTimeSlices;
+    vop /= (numTimeSlices / period);
+    totK += (classicalKinetic + t1);
+    const double totV = t2 - t1 + tailV;
+    vop += tailV;
+    out[0] = totK; out[1] = totV; out[2] = 0.0; out[3] = vop; out[4] = totK + totV; out[5] = totK + totV - mu * numParticles;
+    out[6] = totK / numParticles; out[7] = totV / numParticles; out[8] = (totK + totV) / numParticles;
+    return 0;
+}
+
 // Number of time slices from (T, tau) or explicit P: src/setup.cpp:998-1012.  Returns M, writes tau.
 int orc_time_slices(double T, double tau_in, int P_in, double* tau_out) {
     int numTimeSlices;

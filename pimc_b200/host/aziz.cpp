@@ -27,6 +27,13 @@ AzizPotential::AzizPotential(int year, const Container* box) {
         lookupdVdr[n] = valuedVdr(r);
         r += dr;
     }
+    // tail correction (potential.cpp:1798-1806); the cutoff defaults to the box side (src/setup.cpp:1128-1130)
+    const double rc = constants()->rc() > 0.0 ? constants()->rc() : box->side[NDIM - 1];
+    const double rmorc = rm / rc;
+    const double t2 = C6 * std::pow(rmorc, 3.0) / 3.0;
+    const double t3 = C8 * std::pow(rmorc, 5.0) / 5.0;
+    const double t4 = C10 * std::pow(rmorc, 7.0) / 7.0;
+    tailV = 2.0 * M_PI * epsilon * (-rm * rm * rm * (t2 + t3 + t4));
 }
 
 double AzizPotential::F(double x) const {

@@ -41,6 +41,10 @@ EstimatorBase::EstimatorBase(const Path& _path, ActionBase* _actionPtr, const MT
       numSampled(0), numAccumulated(0), totNumAccumulated(0), diagonal(true), endLine(true) {
     canonical = constants()->canonical();
     numBeads0 = constants()->initialNumParticles() * constants()->numTimeSlices();
+    sliceFactor.assign(constants()->numTimeSlices(), 1.0);      // :182, :196-199 (PIMC: every slice, weight 1)
+    startSlice = 0;
+    endSlice = path.numTimeSlices;
+    endDiagSlice = endSlice;
 }
 
 EstimatorBase::~EstimatorBase() {}
@@ -72,6 +76,18 @@ void EstimatorBase::initialize(int _numEst) {
     norm.resize(numEst);
     norm.fill(1.0);
     reset();
+}
+
+// src/estimator.cpp:274-289
+void EstimatorBase::initialize(std::vector<std::string> estLabel) {
+    for (size_t i = 0; i < estLabel.size(); ++i) estIndex[estLabel[i]] = static_cast<int>(i);
+    header = "";
+    for (const auto& l : estLabel) {
+        char buf[64];
+        std::snprintf(buf, sizeof buf, "%16s", l.c_str());
+        header += buf;
+    }
+    initialize(static_cast<int>(estLabel.size()));
 }
 
 // src/estimator.cpp:297-321

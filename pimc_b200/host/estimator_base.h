@@ -47,8 +47,13 @@ protected:
     bool diagonal, endLine, canonical;
     std::string header;
 
+    std::map<std::string, int> estIndex;            // include/estimator.h:104
+    std::vector<double> sliceFactor;                // 1.0 on every slice in PIMC mode (src/estimator.cpp:182-199)
+    int startSlice = 0, endSlice = 0, endDiagSlice = 0;
+
     virtual void accumulate() {}
     void initialize(int);
+    void initialize(std::vector<std::string> estLabel);
     void getQVectors(std::vector<dVec>&);
 };
 

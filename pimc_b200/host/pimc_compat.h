@@ -113,6 +113,12 @@ public:
     double tau() const { return tau_; }
     double T() const { return T_; }
     double lambda() const { return lambda_; }                  // src/constants.cpp:128: 24.24/m
+    double mu() const { return mu_; }
+    double rc() const { return rc_; }                          // potential cutoff; defaults to side[NDIM-1] (src/setup.cpp:1128-1130)
+    double fourLambdaTauInv() const { return 0.25 / (lambda_ * tau_); }   // include/constants.h:82
+    uint32 binSize() const { return binSize_; }
+    double mu_ = 0.0, rc_ = 0.0;
+    uint32 binSize_ = 100;
     std::string wavevector() const { return wavevector_; }
     std::string wavevectorType() const { return wavevectorType_; }
     std::string id() const { return id_; }
@@ -135,8 +141,22 @@ class Path {
 public:
     Path(const Container* box, int numTimeSlices_, int numParticles, int extent)
         : numTimeSlices(numTimeSlices_), boxPtr(box), n_(numParticles), next_(extent),
-          beads_(static_cast<size_t>(numTimeSlices_) * extent) {
+          beads_(static_cast<size_t>(numTimeSlices_) * extent), nextLink_(static_cast<size_t>(numTimeSlices_) * extent) {
         worm.numBeadsOn = numTimeSlices * numParticles;
+        for (int s = 0; s < numTimeSlices; ++s)            // straight closed world lines unless setLinks() says otherwise
+            for (int p = 0; p < extent; ++p)
+                nextLink_[static_cast<size_t>(s) * extent + p] =
+                    p < numParticles ? beadLocator{(s + 1) % numTimeSlices, p} : beadLocator{XXX, XXX};
+    }
+    void setLinks(const std::vector<beadLocator>& nextLink) { if (nextLink.size() == nextLink_.size()) nextLink_ = nextLink; }
+    const beadLocator& next(const beadLocator& b) const { return nextLink_[static_cast<size_t>(b[0]) * next_ + b[1]]; }   // path.h:92-99
+    dVec getVelocity(const beadLocator& b) const {                                              // path.h:189-203
+        dVec vel;
+        const beadLocator& n = next(b);
+        if ((b[0] == XXX && b[1] == XXX) || (n[0] == XXX && n[1] == XXX)) { vel.fill(0.0); return vel; }
+        for (int i = 0; i < NDIM; ++i) vel[i] = (*this)(n)[i] - (*this)(b)[i];
+        boxPtr->putInBC(vel);
+        return vel;
     }
     const int numTimeSlices;
     const Container* boxPtr;
@@ -158,6 +178,7 @@ public:
 private:
     int n_, next_;
     std::vector<dVec> beads_;       // row-major [slice][ptcl] AoS, as DynamicArray<dVec,2> (path.h:164)
+    std::vector<beadLocator> nextLink_;
 };
 
 class MTRand {};                    // the path never draws random numbers
@@ -191,7 +212,7 @@ struct TableView {
 class ActionBase {
 public:
     ActionBase(const Path& p, PotentialBase* ext, PotentialBase* inter, int period_ = 1)
-        : period(period_), path(p), externalPtr(ext), interactionPtr(inter) {
+        : period(period_), externalPtr(ext), interactionPtr(inter), path(p) {
         sepHist.resize(NPCFSEP);
         sepHist.fill(0);
         dSep = 0.5 * std::sqrt(1.0 * NDIM) * path.boxPtr->side[NDIM - 1] / (1.0 * NPCFSEP);      // src/action.cpp:192
@@ -203,11 +224,11 @@ public:
     virtual double derivPotentialActionLambda(int) { return 0.0; }
     const int period;
     DynamicArray<int, 1> sepHist;   // action.h:114
+    PotentialBase* externalPtr;     // public upstream as well (include/action.h:108-109)
+    PotentialBase* interactionPtr;
     double tau() const { return constants()->tau(); }
 protected:
     const Path& path;
-    PotentialBase* externalPtr;
-    PotentialBase* interactionPtr;
     double dSep;
 };
 

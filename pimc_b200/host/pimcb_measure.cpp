@@ -7,7 +7,7 @@
 //                 --configs beads.bin [--bin_size 100] [--outdir OUTPUT] [--id run] [--action gsf]
 //
 // `--configs` is a raw little-endian file of B configurations, each double[M][N_ext][NDIM] in the reference's bead
-// layout (N_ext given by --extent, default N).  `--state f1,f2,...` measures saved text state files
+// layout (N_ext given by --extent, default N).  --energy adds the thermodynamic energy estimator (ce-estimator-<id>.dat).  `--state f1,f2,...` measures saved text state files
 // (OUTPUT/(g)ce-state-*.dat, state_file.h) instead: -N, -P and the extent are then taken from the first file, every
 // state must be diagonal with that many particles and slices, and the loader's putInside is applied (pimc.cpp:1258-1268).  With --potential the total potential action, per-slice Vint and
 // gradVSquared of every configuration are written to <outdir>/ce-potential-<id>.dat as well.
@@ -18,6 +18,7 @@
 
 #include "action_b200.h"
 #include "aziz.h"
+#include "energy_estimator.h"
 #include "estimator_b200.h"
 #include "state_file.h"
 
@@ -97,10 +98,16 @@ int main(int argc, char** argv) {
     }
 
     std::vector<std::unique_ptr<EstimatorBase>> estimators;
-    for (const char* name : {"static structure factor", "intermediate scattering function"}) {
+    std::vector<const char*> names = {"static structure factor", "intermediate scattering function"};
+    const bool wantEnergy = flag(argc, argv, "--energy");          // thermodynamic energy estimator on the device pair sums
+    if (wantEnergy && !wantPotential) { std::cerr << "--energy needs --potential (the action object)" << std::endl; return 2; }
+    if (wantEnergy) names.push_back("energy");
+    c->binSize_ = static_cast<uint32>(binSize);
+    for (const char* name : names) {
         EstimatorBase* e = estimatorFactory()->Create(name, path, action.get(), random, 0.0);
         if (!e) { std::cerr << "estimator not registered: " << name << std::endl; return 1; }
         estimators.emplace_back(e);
+        if (std::string(name) == "energy") e->addEndLine();            // the only scalar estimator here closes the row (setup.cpp:1364-1366)
         e->prepare();
     }
     std::fstream* potOut = nullptr;
@@ -130,6 +137,7 @@ int main(int argc, char** argv) {
         if (!st.isLeftPacked()) st.leftPack();
         st.putInside(box);
         std::memcpy(path.beads_data(), st.beads.data(), count * sizeof(double));
+        path.setLinks(st.nextLink);                                   // world-line connectivity for the kinetic estimator
         return true;
     };
     while (nextConfiguration()) {

@@ -54,7 +54,7 @@ def test_qvectors_match_oracle_bitwise(host_bins, orc, ndim, N, rho, qtype, text
 
 def test_factory_names_and_formatting(host_bins, orc):
     rep = selftest(host_bins, 3, 16, 0.02198, "int", "1 0 0")
-    assert sorted(rep["registered"]) == ["intermediate scattering function", "static structure factor"]
+    assert sorted(rep["registered"]) == ["energy", "intermediate scattering function", "static structure factor"]
     assert rep["row"][0] == orc.format_row([30864.19725, -6.25e-4], [1.0, 1.0], 1)
 
 
@@ -136,6 +136,39 @@ def test_state_file_parser_matches_format_restatement(host_bins, tmp_path, ndim)
     out = subprocess.run([os.path.join(host_bins, f"pimcb_host_selftest{ndim}d"), "--state", str(f4), "4", "0.02"],
                          capture_output=True, text=True)
     assert out.returncode == 1 and "error=" in out.stdout
+
+
+@pytest.mark.gpu
+def test_energy_estimator_on_device_pair_sums(host_bins, orc, nthreads, tmp_path):
+    """The thermodynamic EnergyEstimator (src/estimator.cpp:940-1029) restated on top of LocalActionB200: K, V, V_int,
+    E per bin in ce-estimator-<id>.dat against the oracle's restatement on the oracle's own pair sums (gsf action)."""
+    s = synth.C1
+    B, bin_size = 5, 2
+    batch = synth.gen_batch(s, B, first=20)
+    cfg = tmp_path / "beads.bin"
+    batch.tofile(cfg)
+    out = tmp_path / "OUTPUT"
+    subprocess.run([os.path.join(host_bins, "pimcb_measure3d"), "-N", str(s.N), "-n", repr(s.rho), "-T", repr(s.T), "-t", "0.004",
+                    "--extent", str(s.N + 3), "--wavevector_type", "int", "--wavevector", "1 0 0", "--configs", str(cfg),
+                    "--bin_size", str(bin_size), "--outdir", str(out), "--id", "e", "--potential", "--energy"], check=True)
+    head, rows = read_dat(out / "ce-estimator-e.dat")
+    names = ["K", "V", "V_ext", "V_int", "E", "E_mu", "K/N", "V/N", "E/N"]
+    assert head[0] == "#" + ("%16s" % names[0])[1:] + "".join("%16s" % n for n in names[1:])
+    V, dV, dr = orc.aziz_table(orc.max_sep(s.side))
+    dSep = 0.5 * math.sqrt(3) * s.side[2] / 50
+    tail = orc.aziz_tail(s.side[2])
+    per_cfg = []
+    for b in range(B):
+        cv, cf, _ = orc.pair_sums(s.side, batch[b], s.N, V, dV, dr, dSep, nthreads=nthreads)
+        cf[0::2] = 0.0                                    # gsf: the gradient correction lives on odd slices only
+        per_cfg.append(orc.energy(s.side, batch[b], s.N, cv, cf, [2 / 3, 4 / 3], [0.0, 2 / 9], 2, 0.004, synth.LAMBDA_HE4, tail))
+    per_cfg = np.array(per_cfg)
+    bins = [(0, 2), (2, 4), (4, 5)]
+    assert len(rows) == len(bins)
+    for row, (a, b) in zip(rows, bins):
+        got = np.array([float(row[16 * k:16 * k + 16]) for k in range(9)])
+        np.testing.assert_allclose(got, per_cfg[a:b].mean(axis=0), rtol=2e-8, atol=1e-8)
+    assert abs(per_cfg[0, 0]) > 1.0 and abs(per_cfg[0, 3]) > 1.0          # not trivially zero
 
 
 @pytest.mark.gpu

@@ -235,3 +235,16 @@ def test_output_formatting(orc):
     row = orc.format_row([1.0, -2.5e-3, 123456.789], [0.5, 0.5, 0.5], 2)
     assert row == "  2.50000000E-01 -6.25000000E-04  3.08641973E+04"
     assert orc.dvec_to_string([0.5, -1.25, 3.0]) == "(+5.00000000E-01,-1.25000000E+00,+3.00000000E+00)"
+
+
+def test_energy_estimator_free_particle_closed_form(orc):
+    """One free particle hopping by +-d along x every slice: K = NDIM/(2 tau) - d^2/(4 lambda tau^2), V = tail only."""
+    M, d, tau, lam = 8, 0.01, 0.05, 6.0
+    side = np.array([10.0, 10.0, 10.0])
+    beads = np.zeros((M, 1, 3))
+    beads[:, 0, 0] = d * (np.arange(M) % 2) - 4.0         # zig-zag: every link, the closing one included, has length d
+    zeros = np.zeros(M)
+    e = orc.energy(side, beads, 1, zeros, zeros, [1.0, 1.0], [0.0, 0.0], 1, tau, lam, tailV=-2.0, mu=0.3)
+    K = 1.5 / tau - d * d / (4.0 * lam * tau * tau)
+    Vt = -2.0 / 1000.0
+    np.testing.assert_allclose(e, [K, Vt, 0.0, Vt, K + Vt, K + Vt - 0.3, K, Vt, K + Vt], rtol=1e-13, atol=1e-15)
