@@ -174,6 +174,36 @@ def test_lattice_qsets(api, orc, ndim, nvec):
         assert_parity(isf[0], ref_f, f"qset isf mode {mode}")
 
 
+@pytest.mark.parametrize("ndim,seed", [(1, 1), (2, 2), (2, 3), (3, 4), (3, 5), (3, 6), (3, 7), (3, 8)])
+def test_random_lattice_qsets_all_rho_kernels_agree(api, orc, ndim, seed):
+    """Fuzz of the lattice planner (groups, coinciding factors, zero planes, tile shapes up to 16 x 1 / 8 x 2 / 4 x 4,
+    the host-resolved unfold table): random integer q-sets with repeats and q = 0; DMMA (1), CUDA-core lattice (2) and
+    generic (0) kernels must agree with each other and with the oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    rho = {1: 0.2, 2: 0.0432, 3: 0.02198}[ndim]
+    N, M = 37, 4
+    s = synth.Shape("fz", ndim, N, M, 2.0, rho, 0)
+    beads = synth.gen_config(N, M, ndim, rho, 2.0, seed=seed)
+    nmax = rng.integers(1, {1: 12, 2: 9, 3: 5}[ndim], size=ndim)
+    if seed % 2 == 0:
+        nmax[rng.integers(0, ndim)] = 0                    # a dimension that never appears
+    nq = int(rng.integers(3, {1: 14, 2: 60, 3: 120}[ndim]))
+    n = np.stack([rng.integers(-nmax[d], nmax[d] + 1, size=nq) for d in range(ndim)], axis=1)
+    n[0] = 0                                               # q = 0
+    n[-1] = n[1]                                           # a repeated q
+    q = (2.0 * math.pi / s.side) * n
+    res = {}
+    for mode in (0, 1, 2):
+        with make_ctx(api, s, q) as ctx:
+            assert ctx.num_commensurate() == nq
+            ctx.set_rho_mode(mode)
+            res[mode] = ctx.stage(beads, N).ssf_isf()
+    ref_f = orc.isf_factorised(beads, N, q)
+    for mode in (0, 1, 2):
+        assert_parity(res[mode][1][0], ref_f, f"fuzz isf mode {mode} nmax {nmax.tolist()} nq {nq}")
+        assert_parity(res[mode][0][0], ref_f[:, 0], f"fuzz ssf mode {mode}")
+
+
 @pytest.mark.parametrize("M", [2, 4, 6, 14, 62, 126, 128, 130, 254, 258, 382, 386, 510, 512, 640])
 def test_tau_correlation_kernels(api, orc, M):
     """Both tau-correlation kernels (1 = DMMA, up to M = 510 then falls back; 0 = CUDA cores) over time-slice counts
