@@ -892,15 +892,13 @@ __device__ __forceinline__ int corrm_idx(int e) { return e + 4 * (e >> 3); }
 // A CTA is four warps = the four configurations b0..b0+3 of one q (blockIdx = (b0 / 4) * nq + q); every warp stages
 // its own pair (whole 32-byte sectors of the rho buffer) and runs independently (no CTA barrier on the per-configuration path).
 // PARTIAL = false: out = cfg, one row of nq + nq*M results per configuration.
-// PARTIAL = true : the four warps' results are added in fixed order in shared memory and written as ONE row per
-//                  configuration quad (out = part[ceil(B/4)][nq + nq*M]); the bin accumulation then reads a quarter
-//                  of the data and the per-configuration rows are never written (pimcb_measure, all q commensurate).
-//                  The CTA that completes a q (counter qdone[q], re-armed by that CTA) then adds the quad rows of its q
-//                  in fixed order into the device-resident bin -- the bin accumulation costs no extra launch.
+// PARTIAL = true : the four warps' results are added in fixed order in shared memory and ACCUMULATED into the CTA's own
+//                  persistent row segment (out = rows[ceil(B/4)][nq][M/2 + 1]); per-configuration rows are never
+//                  written and the bin accumulation costs neither a launch nor a dependency between CTAs
+//                  (pimcb_measure, all q commensurate).  bins_fold_kernel folds the rows into the bin when it is read.
 template <int MTC, bool PARTIAL>
 __global__ void __launch_bounds__(128) isf_corr_mma_kernel(const double* __restrict__ rho, double* __restrict__ out, int M, int nq,
-                                                            int B, double invN, const unsigned char* __restrict__ commensurate,
-                                                            double* __restrict__ bins, unsigned* __restrict__ qdone) {
+                                                            int B, double invN, const unsigned char* __restrict__ commensurate) {
     extern __shared__ __align__(16) double sm[];
     constexpr int OFF = 64 * MTC;
     const int Mpad = (M + 3) & ~3;
@@ -1002,37 +1000,32 @@ __global__ void __launch_bounds__(128) isf_corr_mma_kernel(const double* __restr
                 if (tau <= half) dc[tau] = (acc[0][m][e] + acc[1][m][e]) * invN;
             }
         __syncthreads();
-        double* dst = out + static_cast<size_t>(bq) * row_len + nq + static_cast<size_t>(iq) * M;   // tau <= M/2 only
+        // out = persistent quad rows [quad][q][M/2 + 1]: this CTA is the only writer of its row segment, launch after
+        // launch, so a plain read-add-write accumulates the bin without any ordering between CTAs
+        double* row = out + (static_cast<size_t>(bq) * nq + iq) * (half + 1);
         for (int tau = threadIdx.x; tau <= half; tau += blockDim.x)
-            __stcg(dst + tau, ((sm[tau] + sm[2 * plen + tau]) + sm[4 * plen + tau]) + sm[6 * plen + tau]);
-        // last CTA of this q: add the quad rows (fixed order) into the bin, mirror tau -> M - tau, S(q) = F(q,0)
-        __shared__ unsigned s_last;
-        __threadfence();
-        __syncthreads();
-        const unsigned nquads = gridDim.x / nq;
-        if (threadIdx.x == 0) s_last = atomicAdd(qdone + iq, 1u) == nquads - 1 ? 1u : 0u;
-        __syncthreads();
-        if (!s_last) return;
-        __threadfence();
-        const double* src = out + nq + static_cast<size_t>(iq) * M;
-        double* bq_out = bins + nq + static_cast<size_t>(iq) * M;
-        for (int tau = threadIdx.x; tau <= half; tau += blockDim.x) {
-            double tot = 0.0;
-            unsigned r = 0;
-            for (; r + 8 <= nquads; r += 8) {                        // 8 loads in flight, added in row order
-                double v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + static_cast<size_t>(r + u) * row_len + tau);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) tot += v[u];
-            }
-            for (; r < nquads; ++r) tot += __ldcg(src + static_cast<size_t>(r) * row_len + tau);
-            bq_out[tau] += tot;
-            if (tau > 0 && tau < M - tau) bq_out[M - tau] += tot;
-            if (tau == 0 && commensurate[iq]) bins[iq] += tot;
-        }
-        if (threadIdx.x == 0) qdone[iq] = 0u;
+            row[tau] += ((sm[tau] + sm[2 * plen + tau]) + sm[4 * plen + tau]) + sm[6 * plen + tau];
     }
+}
+
+// Folds the persistent quad rows into the bin (fixed row order), mirrors tau -> M - tau, S(q) = F(q,0) for commensurate
+// q, and clears the rows.  Runs once per bin read-out, not per measurement.
+__global__ void __launch_bounds__(128) bins_fold_kernel(double* __restrict__ rows, double* __restrict__ bins, int nrows, int nq, int M,
+                                                         const unsigned char* __restrict__ commensurate) {
+    const int half = M / 2, seg = half + 1;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nq * seg) return;
+    const int iq = idx / seg, tau = idx - iq * seg;
+    double tot = 0.0;
+    for (int r = 0; r < nrows; ++r) {
+        double* p = rows + (static_cast<size_t>(r) * nq) * seg + idx;
+        tot += *p;
+        *p = 0.0;
+    }
+    double* f = bins + nq + static_cast<size_t>(iq) * M;
+    f[tau] += tot;
+    if (tau > 0 && tau < M - tau) f[M - tau] += tot;
+    if (tau == 0 && commensurate[iq]) bins[iq] += tot;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -121,6 +121,7 @@ struct pimcb_ctx {
     DevBuf d_rho, d_cfg, d_bins, d_partial;
     long n_acc = 0;
     size_t bins_len = 0;
+    int bins_M = 0;                        // time slices of the current bin layout
     PinBuf h_out;
     // pair potential
     DevBuf d_V, d_dV, d_vint, d_f2, d_hist;
@@ -139,7 +140,9 @@ struct pimcb_ctx {
     long k_count[kKernels] = {};
     long launches = 0;
     DevBuf d_scratch;
-    DevBuf d_qdone;                        // per-q completion counters of the fused correlation + bin accumulation
+    DevBuf d_binrows;                      // persistent quad rows [rows][nq][M/2+1] of the measure path (folded into d_bins on read)
+    int binrows_n = 0;                     // rows in use since the last fold (0 = nothing pending)
+    int binrows_cap = 0;                   // rows the buffer holds for the current (nq, M)
     DevBuf d_sched;                        // ticket counter + retire counter of the persistent-warp rho kernel (self re-arming)
 };
 
@@ -390,6 +393,18 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
     return 0;
 }
 
+// Folds the pending quad rows of the measure path into d_bins (one small launch per bin read-out).
+int fold_binrows(pimcb_ctx* c, int M) {
+    if (c->binrows_n == 0) return 0;
+    const int total = c->nq * (M / 2 + 1);
+    bins_fold_kernel<<<(total + 127) / 128, 128, 0, c->stream>>>(c->d_binrows.as<double>(), c->d_bins.as<double>(), c->binrows_n, c->nq, M,
+                                                                  c->d_comm.as<unsigned char>());
+    CU(cudaGetLastError());
+    c->launches++;
+    c->binrows_n = 0;
+    return 0;
+}
+
 // partial_rows != nullptr asks for the quad-summed form (one row per four configurations, folded into the bin by the
 // kernel itself) when the DMMA kernel can provide it; *partial_rows returns the number of rows of d_cfg that still have
 // to be accumulated into the bin (0 after the fused form, B after a per-configuration form).
@@ -404,21 +419,27 @@ int launch_corr(pimcb_ctx* c, const Slot& s, int* partial_rows = nullptr) {
         const int quads = (s.B + 3) / 4;
         const bool partial = partial_rows != nullptr;
         int rc = 0;
-        if (partial && sizeof(unsigned) * c->nq > c->d_qdone.cap) {          // per-q completion counters, left at zero by the kernel
-            rc = c->d_qdone.ensure(sizeof(unsigned) * c->nq); if (rc) return rc;
-            CU(cudaMemsetAsync(c->d_qdone.p, 0, c->d_qdone.cap, c->stream));
+        if (partial) {
+            if (quads > c->binrows_cap) {                                    // grow the persistent rows (pending sums folded first)
+                if ((rc = fold_binrows(c, s.M))) return rc;
+                const size_t bytes = sizeof(double) * quads * c->nq * (s.M / 2 + 1);
+                if ((rc = c->d_binrows.ensure(bytes))) return rc;
+                CU(cudaMemsetAsync(c->d_binrows.p, 0, c->d_binrows.cap, c->stream));
+                c->binrows_cap = quads;
+            }
+            c->binrows_n = std::max(c->binrows_n, quads);
         }
 #define LAUNCH_CORR_MMA2(MTC, PART)                                                                                \
         rc = set_smem(isf_corr_mma_kernel<MTC, PART>, smem); if (rc) return rc;                                    \
-        isf_corr_mma_kernel<MTC, PART><<<quads * c->nq, 128, smem, c->stream>>>(c->d_rho.as<double>(), c->d_cfg.as<double>(), s.M, \
-                                                                                c->nq, s.B, 1.0 / s.N, c->d_comm.as<unsigned char>(), \
-                                                                                c->d_bins.as<double>(), c->d_qdone.as<unsigned>())
+        isf_corr_mma_kernel<MTC, PART><<<quads * c->nq, 128, smem, c->stream>>>(c->d_rho.as<double>(),                          \
+                                                                                PART ? c->d_binrows.as<double>() : c->d_cfg.as<double>(), \
+                                                                                s.M, c->nq, s.B, 1.0 / s.N, c->d_comm.as<unsigned char>())
 #define LAUNCH_CORR_MMA(MTC) if (partial) { LAUNCH_CORR_MMA2(MTC, true); } else { LAUNCH_CORR_MMA2(MTC, false); }
         if (mtc == 1) { LAUNCH_CORR_MMA(1) } else if (mtc == 2) { LAUNCH_CORR_MMA(2) } else if (mtc == 3) { LAUNCH_CORR_MMA(3) } else { LAUNCH_CORR_MMA(4) }
 #undef LAUNCH_CORR_MMA
 #undef LAUNCH_CORR_MMA2
         CU(cudaGetLastError());
-        if (partial) *partial_rows = 0;         // already folded into the bin by the kernel
+        if (partial) *partial_rows = 0;         // accumulated into the persistent quad rows by the kernel
         return 0;
     }
     const int nblk = (s.M / 2 + 1 + 7) / 8;                       // tau blocks of 8 per (config, q) pair
@@ -478,7 +499,10 @@ int run_estimators(pimcb_ctx* c, Slot** sp, int* rows = nullptr) {
         if (rc) return rc;
         CU(cudaMemsetAsync(c->d_bins.p, 0, sizeof(double) * len, c->stream));
         c->bins_len = len;
+        c->bins_M = s->M;
         c->n_acc = 0;
+        c->binrows_n = 0;                  // pending quad rows belonged to the old layout
+        c->binrows_cap = 0;                // re-zeroed and re-sized on the next measurement
     }
     rc = c->d_cfg.ensure(sizeof(double) * len * s->B);
     if (rc) return rc;
@@ -656,7 +680,7 @@ int pimcb_destroy(pimcb_ctx* c) {
     for (auto& p : c->pin) { p.release(); if (p.done) cudaEventDestroy(p.done); }
     c->h_out.release();
     for (DevBuf* b : {&c->d_q, &c->d_comm, &c->d_qn, &c->d_qidx, &c->d_plan, &c->d_rho, &c->d_cfg, &c->d_bins, &c->d_partial,
-                      &c->d_V, &c->d_dV, &c->d_vint, &c->d_f2, &c->d_hist, &c->d_scratch, &c->d_sched, &c->d_qdone, &c->d_unfold})
+                      &c->d_V, &c->d_dV, &c->d_vint, &c->d_f2, &c->d_hist, &c->d_scratch, &c->d_sched, &c->d_binrows, &c->d_unfold})
         b->release();
     for (int k = 0; k < kKernels; ++k) { cudaEventDestroy(c->ev0[k]); cudaEventDestroy(c->ev1[k]); }
     for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -985,6 +1009,10 @@ int pimcb_measure(pimcb_ctx* c) {
 int pimcb_reset_bins(pimcb_ctx* c) {
     if (!c) return fail(PIMCB_EINVAL, "null ctx");
     if (c->bins_len) CU(cudaMemsetAsync(c->d_bins.p, 0, sizeof(double) * c->bins_len, c->stream));
+    if (c->binrows_n > 0) {
+        CU(cudaMemsetAsync(c->d_binrows.p, 0, c->d_binrows.cap, c->stream));
+        c->binrows_n = 0;
+    }
     c->n_acc = 0;
     return 0;
 }
@@ -996,6 +1024,7 @@ int pimcb_read_bins(pimcb_ctx* c, double* ssf, double* isf, long* num_acc) {
     const size_t bytes = sizeof(double) * c->bins_len;
     int rc = c->h_out.ensure(bytes);
     if (rc) return rc;
+    if ((rc = fold_binrows(c, c->bins_M))) return rc;
     CU(cudaMemcpyAsync(c->h_out.p, c->d_bins.p, bytes, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     const double* h = static_cast<const double*>(c->h_out.p);
@@ -1008,6 +1037,8 @@ int pimcb_read_bins(pimcb_ctx* c, double* ssf, double* isf, long* num_acc) {
 int pimcb_bins_device_ptr(pimcb_ctx* c, void** dptr, size_t* count) {
     if (!c || !dptr) return fail(PIMCB_EINVAL, "null argument");
     if (!c->bins_len) return fail(PIMCB_ESTATE, "no measurement accumulated yet");
+    CU(cudaSetDevice(c->device));
+    if (int rc = fold_binrows(c, c->bins_M)) return rc;      // enqueued on the ctx stream, like every consumer of the bin
     *dptr = c->d_bins.p;
     if (count) *count = c->bins_len;
     return 0;
