@@ -148,7 +148,9 @@ def run_reference(args, shape, q):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(wall)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{shape.name}: N={shape.N} M={shape.M} nq={len(q)} ndim={shape.ndim}, CPU estimators"},
+        "config": {"workload": f"{shape.name}: N={shape.N} M={shape.M} nq={len(q)} ndim={shape.ndim}, He-4 SVP density, "
+                               f"commensurate q; reference CPU estimators (oracle port) on a bounded sample per step",
+                   "parallelism": f"{arm.cores} host threads, q-vectors / F(q,tau) elements split over threads"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": arm.sample_text()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
