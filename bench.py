@@ -393,13 +393,13 @@ def run_ours(args, shape, q):
         lat = (time.perf_counter() - t0) / nlat
         one_locked = pinned[0].array[0]                                   # page-locked, as B200Session registers Path::beads
         for _ in range(5):
-            ctx.stage(one_locked, shape.N).ssf_isf()
+            ctx.ssf_isf_beads(one_locked, shape.N)
         t0 = time.perf_counter()
         for _ in range(nlat):
-            ctx.stage(one_locked, shape.N).ssf_isf()                      # DMA of the AoS array as it lies + device transpose
+            ctx.ssf_isf_beads(one_locked, shape.N)                        # one ABI call: DMA, transpose, kernels, read-back, one sync
         lat_locked = (time.perf_counter() - t0) / nlat
         latency = {"single_configuration_us": lat_locked * 1e6, "evaluations_per_s": 1.0 / lat_locked, "calls": nlat,
-                   "path": "pimcb_stage_beads(page-locked host AoS, the adaptor's default) + pimcb_ssf_isf, synchronous, one walker",
+                   "path": "pimcb_ssf_isf_beads(page-locked host AoS), what B200Session calls: one synchronous ABI call per walker",
                    "pageable_source_us": lat * 1e6}
         for sl, pa in enumerate(pinned):               # the single-walker calls cycled through the slots: restore the batches
             ctx.stage(pa.array, shape.N, slot=sl)

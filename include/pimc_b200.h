@@ -104,6 +104,10 @@ int pimcb_ssf(pimcb_ctx* ctx, double* out /*[B][nq]*/);
 int pimcb_isf(pimcb_ctx* ctx, double* out /*[B][nq*M]*/);
 /* Both from one pass (rho_q is built once): either pointer may be NULL. */
 int pimcb_ssf_isf(pimcb_ctx* ctx, double* ssf_out, double* isf_out);
+/* pimcb_stage_beads + pimcb_ssf_isf of ONE configuration with a single synchronisation (what an estimator's
+ * accumulate() needs): `beads_aos` may be mutated as soon as the call returns. */
+int pimcb_ssf_isf_beads(pimcb_ctx* ctx, const double* beads_aos, int M, int N, int N_ext, double* ssf /*[nq] or NULL*/,
+                        double* isf /*[nq*M] or NULL*/);
 
 /* ---- device-resident accumulation (bins) -----------------------------------------------------------
  * `estimator += sf/N` / `estimator += isf/N` kept on the device across measurements so that only one

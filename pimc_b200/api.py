@@ -23,7 +23,7 @@ SYMBOLS = [
     "pimcb_create", "pimcb_destroy", "pimcb_last_error", "pimcb_version", "pimcb_set_box", "pimcb_set_qvecs",
     "pimcb_num_commensurate", "pimcb_set_rho_mode", "pimcb_set_corr_mode", "pimcb_stage_beads", "pimcb_stage_batch", "pimcb_stage_batch_async", "pimcb_stage_wait", "pimcb_num_slots",
     "pimcb_stage_batch_slot", "pimcb_select_slot", "pimcb_host_alloc", "pimcb_host_free", "pimcb_host_register",
-    "pimcb_host_unregister", "pimcb_ssf", "pimcb_isf", "pimcb_ssf_isf", "pimcb_measure", "pimcb_reset_bins",
+    "pimcb_host_unregister", "pimcb_ssf", "pimcb_isf", "pimcb_ssf_isf", "pimcb_ssf_isf_beads", "pimcb_measure", "pimcb_reset_bins",
     "pimcb_read_bins", "pimcb_bins_device_ptr", "pimcb_sync", "pimcb_stream", "pimcb_set_pair_table",
     "pimcb_pair_sums", "pimcb_measure_fp64_peak", "pimcb_set_profiling", "pimcb_set_profiling_stride", "pimcb_kernel_times",
     "pimcb_launch_count", "pimcb_rho_plan_info",
@@ -71,6 +71,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.pimcb_ssf.argtypes = [vp, _dp]
     lib.pimcb_isf.argtypes = [vp, _dp]
     lib.pimcb_ssf_isf.argtypes = [vp, _dp, _dp]
+    lib.pimcb_ssf_isf_beads.argtypes = [vp, _dp, C.c_int, C.c_int, C.c_int, _dp, _dp]
     lib.pimcb_measure.argtypes = [vp]
     lib.pimcb_reset_bins.argtypes = [vp]
     lib.pimcb_read_bins.argtypes = [vp, _dp, _dp, C.POINTER(C.c_long)]
@@ -217,6 +218,16 @@ class Context:
 
     def num_slots(self) -> int:
         return self.lib.pimcb_num_slots(self._h)
+
+    def ssf_isf_beads(self, beads, N: int):
+        """One configuration [M][N_ext][ndim]: stage + S(q) + F(q,tau) + read-back with a single synchronisation."""
+        beads, B, M, Next, nd = self._batch(beads, N)
+        assert B == 1 and nd == self.ndim
+        ssf = np.zeros((1, self.nq))
+        isf = np.zeros((1, self.nq, M))
+        self._chk(self.lib.pimcb_ssf_isf_beads(self._h, _ptr(beads), M, N, Next, _ptr(ssf), _ptr(isf)))
+        self.shape = (1, M, N)
+        return ssf, isf
 
     # -- estimators ------------------------------------------------------------------------------------
     def ssf_isf(self, want_ssf=True, want_isf=True):

@@ -986,6 +986,16 @@ int pimcb_ssf_isf(pimcb_ctx* c, double* ssf_out, double* isf_out) {
     if (rc) return rc;
     return copy_out(c, *s, ssf_out, isf_out);
 }
+// Stage + evaluate + read back with ONE synchronisation: the DMA of a page-locked source is not waited for on its own,
+// the final stream synchronisation of the read-back covers it (the compute stream waits for the slot's ready event).
+int pimcb_ssf_isf_beads(pimcb_ctx* c, const double* beads, int M, int N, int Next, double* ssf_out, double* isf_out) {
+    if (!c) return fail(PIMCB_EINVAL, "null ctx");
+    const int slot = (c->cur + 1 + kSlots) % kSlots;
+    int rc = stage_into(c, slot, beads, 1, M, N, Next, false);
+    if (rc) return rc;
+    c->cur = slot;
+    return pimcb_ssf_isf(c, ssf_out, isf_out);
+}
 int pimcb_ssf(pimcb_ctx* c, double* out) { return pimcb_ssf_isf(c, out, nullptr); }
 int pimcb_isf(pimcb_ctx* c, double* out) { return pimcb_ssf_isf(c, nullptr, out); }
 

@@ -84,18 +84,28 @@ void B200Session::stageIfNeeded() {
             locked_bytes_ = bytes;
         }
     }
-    check(pimcb_stage_beads(ctx_, path_.get_beads_data_pointer(), M, N, static_cast<int>(ext[1])), "pimcb_stage_beads");
+    if (fused_ssf_out_) {          // ssf()/isf() asked for the staging: one call, one synchronisation
+        check(pimcb_ssf_isf_beads(ctx_, path_.get_beads_data_pointer(), M, N, static_cast<int>(ext[1]), fused_ssf_out_, fused_isf_out_),
+              "pimcb_ssf_isf_beads");
+        fused_done_ = true;
+    } else {
+        check(pimcb_stage_beads(ctx_, path_.get_beads_data_pointer(), M, N, static_cast<int>(ext[1])), "pimcb_stage_beads");
+    }
     staged_ = true;
     have_sf_ = have_pair_ = false;
 }
 
 const std::vector<double>& B200Session::ssf() {
     if (!have_sf_) {
-        stageIfNeeded();
         const int M = path_.numTimeSlices;
         ssf_.resize(nq_);
         isf_.resize(nq_ * M);
-        check(pimcb_ssf_isf(ctx_, ssf_.data(), isf_.data()), "pimcb_ssf_isf");
+        fused_ssf_out_ = ssf_.data();
+        fused_isf_out_ = isf_.data();
+        fused_done_ = false;
+        stageIfNeeded();                       // not yet staged: stages and evaluates in one call
+        fused_ssf_out_ = fused_isf_out_ = nullptr;
+        if (!fused_done_) check(pimcb_ssf_isf(ctx_, ssf_.data(), isf_.data()), "pimcb_ssf_isf");
         have_sf_ = true;
     }
     return ssf_;

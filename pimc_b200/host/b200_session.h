@@ -58,6 +58,9 @@ private:
     pimcb_ctx* ctx_ = nullptr;
     const void* locked_ptr_ = nullptr;      // Path::beads storage currently page-locked (pimcb_host_register)
     size_t locked_bytes_ = 0;
+    double* fused_ssf_out_ = nullptr;       // set while ssf() drives the staging (fused stage + evaluate call)
+    double* fused_isf_out_ = nullptr;
+    bool fused_done_ = false;
     size_t nq_ = 0;
     bool hooked_ = false, staged_ = false, have_sf_ = false, have_pair_ = false, have_table_ = false;
     bool pair_has_f2_ = false;

@@ -292,6 +292,11 @@ def test_pinned_source_takes_device_transpose_path(api, orc):
         ctx.stage_async(pin2.array, s.N)
         ctx.measure()
         bs, bi, n = ctx.read_bins()
+        # fused stage + evaluate + read-back of one configuration, page-locked and pageable source
+        f1 = ctx.ssf_isf_beads(pin.array[1], s.N)
+        f2 = ctx.ssf_isf_beads(batch[1].copy(), s.N)
+        for f in (f1, f2):
+            assert np.array_equal(f[0][0], a[0][1]) and np.array_equal(f[1][0], a[1][1])
     pin.free()
     pin2.free()
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
