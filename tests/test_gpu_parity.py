@@ -204,6 +204,29 @@ def test_random_lattice_qsets_all_rho_kernels_agree(api, orc, ndim, seed):
         assert_parity(res[mode][0][0], ref_f[:, 0], f"fuzz ssf mode {mode}")
 
 
+@pytest.mark.parametrize("M", [1, 3, 7, 171])
+def test_odd_slice_counts(api, orc, M):
+    """The reference forces an even number of time slices (src/setup.cpp:1000-1008); the ABI does not: odd M through
+    both correlation kernels, the per-configuration and the bin path."""
+    N = 6
+    s = synth.Shape("odd", 3, N, M, 2.0, 0.02198, 0)
+    batch = np.stack([synth.gen_config(N, M, 3, s.rho, 2.0, seed=71 + b) for b in range(3)])
+    q = synth.commensurate_q(7, s.side, include_zero=True)
+    ref = np.array([orc.isf(batch[b], N, q, nthreads=2) for b in range(3)])
+    for mode in (0, 1):
+        with make_ctx(api, s, q) as ctx:
+            ctx.set_corr_mode(mode)
+            ssf, isf = ctx.stage(batch, N).ssf_isf()
+            ctx.reset_bins()
+            ctx.measure()
+            bs, bi, n = ctx.read_bins()
+        for b in range(3):
+            assert_parity(isf[b], ref[b], f"odd M={M} isf corr mode {mode}")
+            assert_parity(ssf[b], ref[b][:, 0], f"odd M={M} ssf corr mode {mode}")
+        assert n == 3
+        assert_parity(bi, ref.sum(axis=0), f"odd M={M} bin corr mode {mode}")
+
+
 @pytest.mark.parametrize("M", [2, 4, 6, 14, 62, 126, 128, 130, 254, 258, 382, 386, 510, 512, 640])
 def test_tau_correlation_kernels(api, orc, M):
     """Both tau-correlation kernels (1 = DMMA, up to M = 510 then falls back; 0 = CUDA cores) over time-slice counts
