@@ -5,12 +5,16 @@
 // bench.py's cpu_baseline / --impl reference legs).  The product library
 // (pimc_b200/csrc) never links, loads or calls anything in this file.
 //
-// PARITY STATUS: "parity unpinned" by reference fixtures -- the reference ships no
-// golden vectors, known-answer tests or fixtures for S(q), F(q,tau) or the pair
-// action, and its sources cannot be compiled here (Boost and
-// <mdspan> are absent).  The restatement is pinned instead by closed-form
-// known-answer tests (tests/test_oracle_kat.py) and by the reference's own
-// batched-vs-scalar 1e-9 rule reproduced on its sampleVector inputs.
+// PARITY STATUS
+//  * S(q) and F(q,tau): PINNED against the reference's own code.  The reference ships no golden vectors or
+//    fixtures for this path and its CPU estimators cannot be compiled here (Boost and <mdspan> are absent), but
+//    its shipped GPU implementation of the same two estimators, src/estimator_gpu.cu, compiles unmodified from
+//    the upstream tree (oracle/Makefile target `ref` -> oracle/_ref/librefgpu<NDIM>d.so); tests/test_reference_gpu.py
+//    holds this restatement (and the product's CUDA path) to 1e-10 against it on C1, C2, 2-D and ragged inputs.
+//  * pair-potential sums (Vint, gradVSquared, sepHist), q-vector generation, output formatting, energy:
+//    "parity unpinned" by reference outputs -- no fixture exists upstream and those sources need Boost; pinned by
+//    closed-form known-answer tests (tests/test_oracle_kat.py) and by the reference's own batched-vs-scalar 1e-9
+//    rule reproduced on its sampleVector inputs.
 //
 // Every function cites the reference file:line (relative to the upstream tree) whose
 // arithmetic it follows.  Floating-point semantics: this file is compiled with
