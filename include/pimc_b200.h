@@ -138,6 +138,36 @@ int pimcb_set_pair_table(pimcb_ctx* ctx, const double* V, const double* dVdr /*o
  * `f2_parity`: -1 = every slice, 0/1 = only slices with slice%2 == f2_parity (others get 0). */
 int pimcb_pair_sums(pimcb_ctx* ctx, double* vint, double* f2, int* sephist, double dSep, int f2_parity);
 
+/* ---- scattering variants ---------------------------------------------------
+ * pimcb_elastic: replaces ElasticScatteringEstimatorGpu::accumulate (src/estimator.cpp:4197-4235; kernel
+ *   gpu_isf<true>, src/estimator_gpu.cu:66-164, launcher :408-413).  out[b][q] = the value upstream adds to
+ *   `estimator` per measurement: 2/(N M) sum_{tau=0}^{M/2} sum_t sum_{i,j} cos(q.(r_j(t+tau) - r_i(t))) (its norm is
+ *   0.5).  Reuses the S(q)/F(q,tau) pass of the same staged batch when pimcb_ssf_isf ran just before.
+ * pimcb_ssf_cyl: replaces CylinderStaticStructureFactorEstimator::accumulate (src/estimator.cpp:5415-5456).
+ *   out[b][q] = sum_t sum_{i in} [1 + 2 sum_{j>i, j in} cos(q.minimage(r_i - r_j))] with "in" = x^2 + y^2 < maxR^2
+ *   (include(), :4309-4311), NOT yet divided by the particle count; n_inside[b] (may be NULL) = beads of slice 0
+ *   inside the radius (num1DParticles, :4318-4327), the divisor upstream uses.  The caller sums the q of one
+ *   magnitude shell (getQVectors2, :762-837).  The shipped GPU variant (gpu_ssf_cyl, src/estimator_gpu.cu:169-285)
+ *   masks with the opposite sense and overwrites instead of accumulating in its strided loop; the CPU class is the
+ *   semantics followed here. */
+int pimcb_elastic(pimcb_ctx* ctx, double* out /*[B][nq]*/);
+int pimcb_ssf_cyl(pimcb_ctx* ctx, double maxR, double* out /*[B][nq]*/, int* n_inside /*[B] or NULL*/);
+
+/* ---- virial slice sums ------------------------------------------------------
+ * Third table of the TabulatedPotential view: lookupd2Vdr2 / extd2Vdr2 (include/potential.h:148-157), same length
+ * and dr as the tables given to pimcb_set_pair_table (which must come first, with dV/dr). */
+int pimcb_set_pair_table_d2(pimcb_ctx* ctx, const double* d2Vdr2, int len, const double* extd2Vdr2 /*[2] or NULL*/);
+/* All slices of all staged configurations in one pass: the O(N^2) parts of LocalAction::rDOTgradUterm1/2
+ * (src/action.cpp:1446-1575) and deltadotgradUterm1/2 (:1588-1784), interaction potential only (external "free"):
+ *   out[b][t][0] = sum_i gV_i . r_i        out[b][t][1] = sum_i (T_i gV_i) . r_i
+ *   out[b][t][2] = sum_i gV_i . delta_i    out[b][t][3] = sum_i (T_i gV_i) . delta_i
+ * gV_i = sum_{j != i} gradV(minimage(r_i - r_j)), T_i the per-particle T-matrix of :1547-1554.  `delta_aos`
+ * ([B][M][N_ext][ndim], the beads' own AoS shape; NULL = skip, entries 2 and 3 are 0) holds each bead's deviation
+ * from the centroid of its world-line window -- it depends on the link structure, which stays on the host.
+ * `t2_parity`: slices that carry the T-matrix terms (gradVFactor[slice%2] > EPS): -1 all, 0 even, 1 odd, -2 none.
+ * The caller applies VFactor*tau and 2*gradVFactor*tau^3*lambda. */
+int pimcb_virial_sums(pimcb_ctx* ctx, const double* delta_aos, int t2_parity, double* out /*[B][M][4]*/);
+
 /* ---- measurement helpers (bench) --------------------------------------------------------------------
  * Sustained FP64 DFMA throughput of the device in TFLOP/s (register-resident FMA chains on every SM,
  * timed with CUDA events).  MEASURED_PEAKS.json carries no FP64 figure. */
@@ -145,7 +175,8 @@ int pimcb_measure_fp64_peak(pimcb_ctx* ctx, double* tflops, double seconds_targe
 /* Per-kernel device time.  With profiling on, every kernel launch is bracketed by CUDA events on the stream it is
  * launched on; pimcb_kernel_times synchronises, folds the pending event pairs into running totals and returns, per
  * kernel id, the summed duration in ms and the number of launches since the last reset:
- * [0]=rho_q build, [1]=tau-correlation, [2]=direct S(q), [3]=bin accumulate, [4]=pair sums, [5]=AoS->SoA transpose.
+ * [0]=rho_q build, [1]=tau-correlation, [2]=direct S(q), [3]=bin accumulate, [4]=pair sums, [5]=AoS->SoA transpose,
+ * [6]=scattering variants (elastic, cylinder S(q)), [7]=virial slice sums.
  * `on`: 0 = off, 1 = every kernel, otherwise a mask with bit (id + 1) set for each kernel id to time (an event
  * between two kernels keeps the second from being staged behind the first, so timing all of them costs ~10 % of a
  * step; the bench times only the dominant kernel inside its timed region). */

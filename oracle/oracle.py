@@ -77,6 +77,14 @@ class Oracle:
         L.orc_put_in_bc.argtypes = [C.c_int, _dp, _up, _dp, C.c_int]
         L.orc_format_row.argtypes = [_dp, _dp, C.c_int, C.c_uint, C.c_char_p, C.c_int]
         L.orc_dvec_to_string.argtypes = [C.c_int, _dp, C.c_char_p, C.c_int]
+        L.orc_qvectors2.argtypes = [C.c_int, C.c_double, C.c_double, C.c_char_p, _dp, C.c_int, _ip, C.c_int, _ip]
+        L.orc_ssf_cyl.argtypes = [C.c_int, _dp, _up, _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, C.c_double, _dp, _ip]
+        L.orc_elastic.argtypes = [C.c_int, _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int]
+        L.orc_virial_delta.argtypes = [C.c_int, _dp, _up, _dp, C.c_int, C.c_int, C.c_int, _ip, C.c_int, _dp]
+        L.orc_virial_sums.argtypes = [C.c_int, _dp, _up, _dp, C.c_int, C.c_int, C.c_int, _ip, C.c_int, _dp, _dp, C.c_int,
+                                      C.c_double, _dp, _dp, C.c_int, _dp, C.c_int]
+        L.orc_virial_energy.argtypes = [C.c_int, _dp, _up, _dp, C.c_int, C.c_int, C.c_int, _ip, C.c_int, _dp, _dp, _dp, _dp, _dp,
+                                        C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, _dp]
 
     # -- geometry ------------------------------------------------------------------
     @staticmethod
@@ -236,6 +244,91 @@ class Oracle:
         rc = self.lib.orc_energy(nd, _dptr(side), per.ctypes.data_as(_up), _dptr(beads), M, N, Next,
                                  nl.ctypes.data_as(C.POINTER(C.c_int)) if nl is not None else None, _dptr(vint), _dptr(f2),
                                  _dptr(vf), _dptr(gf), period, tau, lam, mu, tailV, _dptr(out))
+        assert rc == 0
+        return out
+
+    # -- scattering variants ---------------------------------------------------------
+    def qvectors2(self, ndim, dq, qmax, geometry="line"):
+        """getQVectors2: list of per-magnitude arrays [n_k][ndim] (shell 0 = the null vector)."""
+        nq = C.c_int(0)
+        r = self.lib.orc_qvectors2(ndim, dq, qmax, geometry.encode(), None, 0, None, 0, C.byref(nq))
+        if r == -1000:
+            raise ValueError("geometry must be 'line' or 'sphere'")
+        nshell = -r if r < 0 else r
+        nshell = max(nshell, 1)
+        # first pass returned -max(numq, nshell); count shells by a second sizing pass with generous capacity
+        out = np.zeros((max(nq.value, 1), ndim))
+        sizes = np.zeros(max(nq.value, 1) + 8, dtype=np.int32)
+        r = self.lib.orc_qvectors2(ndim, dq, qmax, geometry.encode(), _dptr(out), len(out), _iptr(sizes), len(sizes), C.byref(nq))
+        assert r > 0, r
+        shells, k = [], 0
+        for n in sizes[:r]:
+            shells.append(out[k:k + n].copy())
+            k += n
+        return shells
+
+    def ssf_cyl(self, side, beads, N, q, maxR, periodic=None):
+        """Cylinder S(q) raw sums per wave-vector + num1DParticles (slice 0)."""
+        beads, M, Next, nd = self._beads(beads)
+        side, per = self._box(side, periodic)
+        q = _f64(q)
+        out = np.zeros(len(q))
+        n_in = C.c_int(0)
+        rc = self.lib.orc_ssf_cyl(nd, _dptr(side), per.ctypes.data_as(_up), _dptr(beads), M, N, Next, _dptr(q), len(q),
+                                  maxR, _dptr(out), C.byref(n_in))
+        assert rc == 0
+        return out, n_in.value
+
+    def elastic(self, beads, N, q, nthreads=1) -> np.ndarray:
+        beads, M, Next, nd = self._beads(beads)
+        q = _f64(q)
+        out = np.zeros(len(q))
+        rc = self.lib.orc_elastic(nd, _dptr(beads), M, N, Next, _dptr(q), len(q), _dptr(out), nthreads)
+        assert rc == 0
+        return out
+
+    # -- virial ------------------------------------------------------------------------
+    @staticmethod
+    def _links(next_links):
+        return np.ascontiguousarray(next_links, dtype=np.int32) if next_links is not None else None
+
+    def virial_delta(self, side, beads, N, window, next_links=None, periodic=None) -> np.ndarray:
+        beads, M, Next, nd = self._beads(beads)
+        side, per = self._box(side, periodic)
+        nl = self._links(next_links)
+        out = np.zeros_like(beads)
+        rc = self.lib.orc_virial_delta(nd, _dptr(side), per.ctypes.data_as(_up), _dptr(beads), M, N, Next, _iptr(nl), window, _dptr(out))
+        assert rc == 0
+        return out
+
+    def virial_sums(self, side, beads, N, window, dVdr, d2V, dr, t2_parity=-1, next_links=None, periodic=None, nthreads=1):
+        """[M][4] = {sum gV.r, sum (gV T).r, sum gV.delta, sum (gV T).delta} per slice."""
+        beads, M, Next, nd = self._beads(beads)
+        side, per = self._box(side, periodic)
+        nl = self._links(next_links)
+        dVdr, d2V = _f64(dVdr), _f64(d2V)
+        ext = np.zeros(2)
+        out = np.zeros((M, 4))
+        rc = self.lib.orc_virial_sums(nd, _dptr(side), per.ctypes.data_as(_up), _dptr(beads), M, N, Next, _iptr(nl), window,
+                                      _dptr(dVdr), _dptr(d2V), len(dVdr), dr, _dptr(ext), _dptr(ext), t2_parity, _dptr(out), nthreads)
+        assert rc == 0
+        return out
+
+    VIRIAL_COLUMNS = ("K_op", "K_cv", "V_op", "V_cv", "E", "E_mu", "K_op/N", "K_cv/N", "V_op/N", "V_cv/N", "E/N",
+                      "EEcv*Beta^2", "Ecv*Beta", "dEdB", "CvCov1", "CvCov2", "CvCov3", "E_th", "P")
+
+    def virial_energy(self, side, beads, N, window, vir, vint, f2, VFactor, gradVFactor, tau, lam, tailV, mu=0.0,
+                      next_links=None, quirk=True) -> np.ndarray:
+        """VirialEnergyEstimator::accumulate for one configuration -> the 19 columns of VIRIAL_COLUMNS."""
+        beads, M, Next, nd = self._beads(beads)
+        side, per = self._box(side, None)
+        nl = self._links(next_links)
+        vir, vint, f2 = _f64(vir), _f64(vint), _f64(f2)
+        vf, gf = _f64(VFactor), _f64(gradVFactor)
+        out = np.zeros(19)
+        rc = self.lib.orc_virial_energy(nd, _dptr(side), per.ctypes.data_as(_up), _dptr(beads), M, N, Next, _iptr(nl), window,
+                                        _dptr(vir), _dptr(vint), _dptr(f2), _dptr(vf), _dptr(gf), tau, lam, mu, tailV,
+                                        int(quirk), _dptr(out))
         assert rc == 0
         return out
 

@@ -350,6 +350,190 @@ double grad_v_squared_slice(const Box& box, const PairTable& tab, const double* 
     return totF2;
 }
 
+// ---------------------------------------------------------------------------------
+// Scattering variants.
+// ---------------------------------------------------------------------------------
+
+// EstimatorBase::getQVectors2, src/estimator.cpp:762-837: magnitude shells cq = 0, dq, 2 dq, ... <= qMax + EPS
+// (cq accumulated by cq += dq); shell 0 is the null vector; every other shell starts with cq along the last
+// dimension; in 3-D the "sphere" geometry adds (theta, phi) points on the positive octant with
+// dtheta = (pi/2)/24, dphi = dtheta/sin(theta) (for "line" dtheta = pi, so the theta loop never runs).
+// out: flattened vectors [numq][ndim]; shell_sizes[k] = vectors in shell k.  Returns the number of shells, or the
+// negated required count when a capacity is too small; -1000 on a bad geometry string.
+int qvectors2_impl(int ndim, double dq, double qMax, const char* geom_c, double* out, int max_vecs, int* shell_sizes,
+                   int max_shells, int* numq_out) {
+    const std::string qGeometry(geom_c);
+    if (qGeometry != "line" && qGeometry != "sphere") return -1000;
+    int numq = 0, nshell = 0;
+    auto push = [&](const double* v) {
+        if (numq < max_vecs) for (int d = 0; d < ndim; ++d) out[static_cast<size_t>(numq) * ndim + d] = v[d];
+        ++numq;
+    };
+    for (double cq = 0.0; cq <= qMax + kEPS; cq += dq) {
+        const int before = numq;
+        if (std::abs(cq) < kEPS) {
+            double qd[3] = {0.0, 0.0, 0.0};
+            push(qd);
+        } else {
+            double qd[3] = {0.0, 0.0, 0.0};
+            qd[ndim - 1] = cq;
+            push(qd);
+            if (ndim == 3) {
+                const int numTheta = 24;
+                const double dtheta = (qGeometry == "line") ? M_PI : 0.5 * M_PI / numTheta;
+                for (double theta = dtheta; theta <= 0.5 * M_PI + kEPS; theta += dtheta) {
+                    const double dphi = dtheta / sin(theta);
+                    for (double phi = 0.0; phi <= 0.5 * M_PI + kEPS; phi += dphi) {
+                        double v[3];
+                        v[0] = cq * sin(theta) * cos(phi);
+                        v[1] = cq * sin(theta) * sin(phi);
+                        v[2] = cq * cos(theta);
+                        push(v);
+                    }
+                }
+            }
+        }
+        if (nshell < max_shells) shell_sizes[nshell] = numq - before;
+        ++nshell;
+    }
+    if (numq_out) *numq_out = numq;
+    if (numq > max_vecs || nshell > max_shells) return -std::max(numq, nshell);
+    return nshell;
+}
+
+// include(r, maxR), src/estimator.cpp:4309-4311
+inline bool cyl_include(const double* r, double maxR) { return (r[0] * r[0] + r[1] * r[1] < maxR * maxR); }
+
+// CylinderStaticStructureFactorEstimator::accumulate, src/estimator.cpp:5415-5456, for ONE wave-vector (the caller sums
+// the vectors of a magnitude shell and divides by num1DParticles): sum_t sum_{i in} [1 + 2 sum_{j>i, j in} cos(sep.q)].
+template <int ND>
+double ssf_cyl_one(const Box& box, const double* beads, int M, int N, int Next, const double* q, double maxR) {
+    double sf = 0.0;
+    for (int t = 0; t < M; ++t)
+        for (int i = 0; i < N; ++i) {
+            const double* r1 = bead<ND>(beads, Next, t, i);
+            if (!cyl_include(r1, maxR)) continue;
+            sf += 1.0;
+            for (int j = i + 1; j < N; ++j) {
+                const double* r2 = bead<ND>(beads, Next, t, j);
+                if (!cyl_include(r2, maxR)) continue;
+                double sep[ND];
+                separation<ND>(box, r1, r2, sep);
+                sf += 2 * cos(dot<ND>(sep, q));
+            }
+        }
+    return sf;
+}
+
+// ---------------------------------------------------------------------------------
+// Virial slice sums.  Links: next[(slice*Next + ptcl)*2 + {0,1}] = (slice, ptcl) of
+// the next bead (NULL = straight closed world lines); prev is the inverse map.
+// ---------------------------------------------------------------------------------
+struct Links {
+    const int* next; std::vector<int> prev; int M, Next;
+    Links(const int* n, int M_, int N, int Next_) : next(n), M(M_), Next(Next_) {
+        if (!next) return;
+        prev.assign(static_cast<size_t>(M) * Next * 2, -1);
+        for (int s = 0; s < M; ++s)
+            for (int p = 0; p < N; ++p) {
+                const int ns = next[(static_cast<size_t>(s) * Next + p) * 2], np = next[(static_cast<size_t>(s) * Next + p) * 2 + 1];
+                if (ns < 0 || np < 0) continue;
+                prev[(static_cast<size_t>(ns) * Next + np) * 2] = s;
+                prev[(static_cast<size_t>(ns) * Next + np) * 2 + 1] = p;
+            }
+    }
+    void fwd(int& s, int& p) const {          // Path::next(bead), include/path.h:96-98
+        if (!next) { s = (s + 1) % M; return; }
+        const size_t k = (static_cast<size_t>(s) * Next + p) * 2;
+        s = next[k]; p = next[k + 1];
+    }
+    void back(int& s, int& p) const {         // Path::prev(bead), include/path.h:105-107
+        if (!next) { s = (s + M - 1) % M; return; }
+        const size_t k = (static_cast<size_t>(s) * Next + p) * 2;
+        const int a = prev[k], b = prev[k + 1];
+        s = a; p = b;
+    }
+};
+
+// delta = putInBC(pos1 - COM) of bead (slice, ptcl) over the virial window, src/action.cpp:1620-1647 / 1742-1769:
+// path.next(bead1, gamma) / path.prev(bead1, gamma) for gamma = 0..window-1 (gamma links away from bead1, so the first
+// pair is bead1 itself), running sums of minimum-image link vectors, COM /= 2*window.
+template <int ND>
+void virial_delta(const Box& box, const double* beads, const Links& L, int slice, int ptcl, int window, double* delta) {
+    double runTotMore[ND], runTotLess[ND], COM[ND];
+    for (int d = 0; d < ND; ++d) runTotMore[d] = runTotLess[d] = COM[d] = 0.0;
+    const double* pos1 = bead<ND>(beads, L.Next, slice, ptcl);
+    int nos = slice, nop = ptcl, pos_ = slice, pop = ptcl;          // beadNextOld, beadPrevOld
+    for (int gamma = 0; gamma < window; ++gamma) {
+        int ns = slice, np = ptcl, ps = slice, pp = ptcl;
+        for (int m = 0; m < gamma; ++m) { L.fwd(ns, np); L.back(ps, pp); }
+        double sep[ND];
+        separation<ND>(box, bead<ND>(beads, L.Next, ns, np), bead<ND>(beads, L.Next, nos, nop), sep);
+        for (int d = 0; d < ND; ++d) runTotMore[d] += sep[d];
+        separation<ND>(box, bead<ND>(beads, L.Next, ps, pp), bead<ND>(beads, L.Next, pos_, pop), sep);
+        for (int d = 0; d < ND; ++d) runTotLess[d] += sep[d];
+        for (int d = 0; d < ND; ++d) COM[d] += (pos1[d] + runTotMore[d]) + (pos1[d] + runTotLess[d]);
+        nos = ns; nop = np; pos_ = ps; pop = pp;
+    }
+    for (int d = 0; d < ND; ++d) COM[d] /= (2.0 * window);
+    for (int d = 0; d < ND; ++d) delta[d] = pos1[d] - COM[d];
+    put_in_bc<ND>(box, delta);
+}
+
+struct VirialTables {
+    const double* dVdr; const double* d2V; int len; double dr; double extdVdr[2]; double extd2V[2];
+};
+
+// One slice: out[0] = sum_i gV_i.r_i (rDOTgradUterm1 without VFactor*tau, src/action.cpp:1446-1478),
+// out[1] = sum_i (gV_i T_i).r_i (rDOTgradUterm2 without 2*gradVFactor*tau^3*lambda, :1493-1575),
+// out[2], out[3] the same with delta_i in place of r_i (deltadotgradUterm1/2, :1588-1784).  External potential "free".
+template <int ND>
+void virial_slice(const Box& box, const VirialTables& tab, const double* beads, const Links& L, int N, int slice, int window,
+                  bool want_t2, double* out) {
+    const int Next = L.Next;
+    out[0] = out[1] = out[2] = out[3] = 0.0;
+    for (int i = 0; i < N; ++i) {
+        const double* r1 = bead<ND>(beads, Next, slice, i);
+        double gV[ND], tMat[ND][ND];
+        for (int a = 0; a < ND; ++a) { gV[a] = 0.0; for (int b = 0; b < ND; ++b) tMat[a][b] = 0.0; }
+        for (int j = 0; j < N; ++j) {
+            double rDiff[ND];
+            separation<ND>(box, r1, bead<ND>(beads, Next, slice, j), rDiff);
+            const double rmag = std::sqrt(dot<ND>(rDiff, rDiff));
+            if (j == i) continue;
+            double gVi[ND];
+            const double g = table_direct(tab.dVdr, tab.len, tab.dr, tab.extdVdr, rmag) / rmag;    // potential.h:997-1003
+            for (int d = 0; d < ND; ++d) gVi[d] = g * rDiff[d];
+            if (want_t2) {
+                const double dVi = std::sqrt(dot<ND>(gVi, gVi));
+                const double g2Vi = table_direct(tab.d2V, tab.len, tab.dr, tab.extd2V, rmag);      // potential.h:1010-1016
+                const double dV = dVi + 0.0, d2V = g2Vi + 0.0;
+                for (int a = 0; a < ND; ++a)
+                    for (int b = 0; b < ND; ++b) {
+                        tMat[a][b] += rDiff[a] * rDiff[b] * d2V / (rmag * rmag) - rDiff[a] * rDiff[b] * dV / pow(rmag, 3);
+                        if (a == b) tMat[a][b] += dV / rmag;
+                    }
+            }
+            for (int d = 0; d < ND; ++d) gV[d] += gVi[d];
+        }
+        double gVdotT[ND];
+        for (int row = 0; row < ND; ++row) {                                                        // common.h:187-199
+            double acc = 0.0;
+            for (int k = 0; k < ND; ++k) acc = acc + tMat[row][k] * gV[k];
+            gVdotT[row] = 0.0 + acc;
+        }
+        double delta[ND];
+        virial_delta<ND>(box, beads, L, slice, i, window, delta);
+        out[0] += dot<ND>(gV, r1);
+        out[2] += dot<ND>(gV, delta);
+        if (want_t2) {
+            out[1] += dot<ND>(gVdotT, r1);
+            out[3] += dot<ND>(gVdotT, delta);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // q-vector generation.  src/estimator.cpp:439-570.
 template <int ND>
 int qvectors_impl(const char* type_c, const char* input_c, const double* side, double* out, int max_out) {
@@ -722,6 +906,215 @@ int orc_energy(int nd, const double* side, const unsigned* periodic, const doubl
     vop += tailV;
     out[0] = totK; out[1] = totV; out[2] = 0.0; out[3] = vop; out[4] = totK + totV; out[5] = totK + totV - mu * numParticles;
     out[6] = totK / numParticles; out[7] = totV / numParticles; out[8] = (totK + totV) / numParticles;
+    return 0;
+}
+
+// ---- scattering variants -------------------------------------------------------------------------------------------
+int orc_qvectors2(int ndim, double dq, double qMax, const char* geometry, double* out, int max_vecs, int* shell_sizes,
+                  int max_shells, int* numq) {
+    return qvectors2_impl(ndim, dq, qMax, geometry, out, max_vecs, shell_sizes, max_shells, numq);
+}
+
+// Cylinder S(q) per wave-vector (raw sums, not divided) + num1DParticles (src/estimator.cpp:4318-4327, slice 0 only).
+int orc_ssf_cyl(int ndim, const double* side, const unsigned* periodic, const double* beads, int M, int N, int Next,
+                const double* q, int nq, double maxR, double* out, int* n_inside) {
+    if (ndim < 2 || ndim > 3) return -100;
+    const Box b = make_box(ndim, side, periodic);
+    for (int k = 0; k < nq; ++k)
+        out[k] = ndim == 2 ? ssf_cyl_one<2>(b, beads, M, N, Next, q + 2 * k, maxR) : ssf_cyl_one<3>(b, beads, M, N, Next, q + 3 * k, maxR);
+    if (n_inside) {
+        int tot = 0;
+        for (int p = 0; p < N; ++p) if (cyl_include(beads + static_cast<size_t>(p) * ndim, maxR)) tot++;
+        *n_inside = tot;
+    }
+    return 0;
+}
+
+// Elastic scattering: what ElasticScatteringEstimatorGpu::accumulate adds to `estimator` per measurement
+// (src/estimator.cpp:4197-4235 with gpu_isf<true>, src/estimator_gpu.cu:66-164): for each q the M/2 + 1 "blocks"
+// tau = 0..M/2 each add 2 * inorm * sum_{m1} sum_{n1,n2} cos(q.(r(m1+tau, n2) - r(m1, n1))), inorm = 1/(N M).
+// The sum order inside a block differs from the device's tree; tau ascending here.
+int orc_elastic(int ndim, const double* beads, int M, int N, int Next, const double* q, int nq, double* out, int nthreads) {
+    if (ndim < 1 || ndim > 3) return -100;
+    const double inorm = 1.0 / (static_cast<double>(N) * M);
+    auto work = [&](int k0, int k1) {
+        for (int k = k0; k < k1; ++k) {
+            double es = 0.0;
+            for (int tau = 0; tau <= M / 2; ++tau) {
+                double blk = 0.0;
+                for (int m1 = 0; m1 < M; ++m1) {
+                    const int m2 = (m1 + tau) % M;
+                    for (int n1 = 0; n1 < N; ++n1)
+                        for (int n2 = 0; n2 < N; ++n2) {
+                            double q_dot_sep = 0.0;
+                            for (int d = 0; d < ndim; ++d)
+                                q_dot_sep += q[k * ndim + d] * (beads[(static_cast<size_t>(m2) * Next + n2) * ndim + d] -
+                                                                beads[(static_cast<size_t>(m1) * Next + n1) * ndim + d]);
+                            blk += cos(q_dot_sep);
+                        }
+                }
+                es += 2.0 * blk * inorm;
+            }
+            out[k] = es;
+        }
+    };
+    if (nthreads < 1) nthreads = 1;
+    std::vector<std::thread> pool;
+    for (int w = 0; w < nthreads; ++w) {
+        const int k0 = static_cast<int>(static_cast<long>(nq) * w / nthreads), k1 = static_cast<int>(static_cast<long>(nq) * (w + 1) / nthreads);
+        if (k1 > k0) pool.emplace_back(work, k0, k1);
+    }
+    for (auto& th : pool) th.join();
+    return 0;
+}
+
+// ---- virial ----------------------------------------------------------------------------------------------------------
+// delta[M][Next][ndim] (padding columns zero) for every active bead: the host-side input of pimcb_virial_sums.
+int orc_virial_delta(int ndim, const double* side, const unsigned* periodic, const double* beads, int M, int N, int Next,
+                     const int* next, int window, double* delta) {
+    if (ndim < 1 || ndim > 3) return -100;
+    const Box b = make_box(ndim, side, periodic);
+    const Links L(next, M, N, Next);
+    std::fill(delta, delta + static_cast<size_t>(M) * Next * ndim, 0.0);
+    for (int s = 0; s < M; ++s)
+        for (int p = 0; p < N; ++p) {
+            double* d = delta + (static_cast<size_t>(s) * Next + p) * ndim;
+            if (ndim == 1) virial_delta<1>(b, beads, L, s, p, window, d);
+            else if (ndim == 2) virial_delta<2>(b, beads, L, s, p, window, d);
+            else virial_delta<3>(b, beads, L, s, p, window, d);
+        }
+    return 0;
+}
+
+// out[M][4] per slice (see virial_slice); t2_parity: -1 all slices, 0/1 slices of that parity, -2 none.
+int orc_virial_sums(int ndim, const double* side, const unsigned* periodic, const double* beads, int M, int N, int Next,
+                    const int* next, int window, const double* dVdr, const double* d2V, int len, double dr,
+                    const double* extdVdr, const double* extd2V, int t2_parity, double* out, int nthreads) {
+    if (ndim < 1 || ndim > 3) return -100;
+    const Box b = make_box(ndim, side, periodic);
+    const Links L(next, M, N, Next);
+    VirialTables tab{dVdr, d2V, len, dr, {extdVdr ? extdVdr[0] : 0.0, extdVdr ? extdVdr[1] : 0.0},
+                     {extd2V ? extd2V[0] : 0.0, extd2V ? extd2V[1] : 0.0}};
+    auto work = [&](int s0, int s1) {
+        for (int s = s0; s < s1; ++s) {
+            const bool t2 = t2_parity == -1 || (t2_parity >= 0 && (s % 2) == t2_parity);
+            double* o = out + static_cast<size_t>(s) * 4;
+            if (ndim == 1) virial_slice<1>(b, tab, beads, L, N, s, window, t2, o);
+            else if (ndim == 2) virial_slice<2>(b, tab, beads, L, N, s, window, t2, o);
+            else virial_slice<3>(b, tab, beads, L, N, s, window, t2, o);
+        }
+    };
+    if (nthreads < 1) nthreads = 1;
+    std::vector<std::thread> pool;
+    for (int w = 0; w < nthreads; ++w) {
+        const int s0 = static_cast<int>(static_cast<long>(M) * w / nthreads), s1 = static_cast<int>(static_cast<long>(M) * (w + 1) / nthreads);
+        if (s1 > s0) pool.emplace_back(work, s0, s1);
+    }
+    for (auto& th : pool) th.join();
+    return 0;
+}
+
+// VirialEnergyEstimator::accumulate, src/estimator.cpp:1086-1250, for ONE configuration on top of the per-slice sums
+// vir[M][4] (orc_virial_sums / pimcb_virial_sums), vint[M], f2[M]; external potential "free".  out[19] in the
+// estimator's column order {K_op, K_cv, V_op, V_cv, E, E_mu, K_op/N, K_cv/N, V_op/N, V_cv/N, E/N, EEcv*Beta^2,
+// Ecv*Beta, dEdB, CvCov1, CvCov2, CvCov3, E_th, P}.  Upstream accumulates "cVCov2" under a misspelt key
+// (estIndex["cVCov2"], :1239), which lands in a NEW map slot with index 0 -- i.e. it is added to K_op.  That quirk is
+// reproduced when `quirk` is non-zero (column CvCov2 stays 0, K_op gets totEcv*beta*dEdB added).
+int orc_virial_energy(int nd, const double* side, const unsigned* periodic, const double* beads, int M, int N, int Next,
+                      const int* next, int window, const double* vir, const double* vint, const double* f2,
+                      const double* VFactor, const double* gradVFactor, double tau, double lambda, double mu,
+                      double tailV_potential, int quirk, double* out) {
+    if (nd < 1 || nd > 3) return -100;
+    const Box b = make_box(nd, side, periodic);
+    const Links L(next, M, N, Next);
+    double volume = 1.0;
+    for (int d = 0; d < nd; ++d) volume *= side[d];
+    const int numParticles = N, numTimeSlices = M, virialWindow = window;
+    const double beta = 1.0 * numTimeSlices * tau;
+    const double tailV = (1.0 * numParticles * numParticles / volume) * tailV_potential;
+    const double thermTerm1 = (0.5 * nd / tau) * numParticles;
+    const double T1 = 0.5 * nd * numParticles / (1.0 * virialWindow * tau);
+    const double exchangeNorm = 1.0 / (4.0 * virialWindow * pow(tau, 2) * lambda * numTimeSlices);
+    double Pressure = nd * numParticles, P2 = 0.0, P3 = 0.0, T2 = 0.0, T3 = 0.0, T4 = 0.0, T5 = 0.0, thermE = 0.0, virKinTerm = 0.0, totVop = 0.0;
+    auto sepv = [&](int s1, int p1, int s2, int p2, double* sep) {
+        for (int d = 0; d < nd; ++d) {
+            sep[d] = beads[(static_cast<size_t>(s1) * Next + p1) * nd + d] - beads[(static_cast<size_t>(s2) * Next + p2) * nd + d];
+            sep[d] -= b.pSide[d] * std::floor(sep[d] * b.sideInv[d] + 0.5);
+        }
+    };
+    for (int slice = 0; slice < numTimeSlices; slice++)
+        for (int ptcl = 0; ptcl < N; ptcl++) {
+            double vel2[3] = {0, 0, 0}, vel1[3] = {0, 0, 0}, sep[3];
+            int ns = slice, np = ptcl;
+            L.fwd(ns, np);
+            if (ns >= 0 && np >= 0) sepv(ns, np, slice, ptcl, vel2);                                 // getVelocity, path.h:189-203
+            int os = slice, op = ptcl;
+            for (int gamma = 1; gamma <= virialWindow; gamma++) {
+                int gs = slice, gp = ptcl;
+                for (int m = 0; m < gamma; ++m) L.fwd(gs, gp);
+                sepv(gs, gp, os, op, sep);
+                for (int d = 0; d < nd; ++d) vel1[d] += sep[d];
+                os = gs; op = gp;
+            }
+            double d12 = 0.0, d22 = 0.0;
+            for (int d = 0; d < nd; ++d) { d12 += vel1[d] * vel2[d]; d22 += vel2[d] * vel2[d]; }
+            T2 -= d12;
+            thermE -= d22;
+        }
+    P2 = thermE;
+    T2 *= exchangeNorm;
+    P2 /= (2.0 * lambda * tau * numTimeSlices);
+    Pressure += P2;
+    for (int slice = 0; slice < numTimeSlices; slice++) {
+        const int eo = slice % 2;
+        const bool corr = gradVFactor[eo] > kEPS;
+        const double* v = vir + static_cast<size_t>(slice) * 4;
+        const double c2 = 2.0 * gradVFactor[eo] * pow(tau, 3) * lambda;
+        T3 += VFactor[eo] * tau * v[2];                                                              // deltaDOTgradUterm1
+        T4 += corr ? v[3] * c2 : 0.0;                                                                // deltaDOTgradUterm2
+        T5 += orc_deriv_potential_action_tau(vint[slice], f2 ? f2[slice] : 0.0, slice, VFactor, gradVFactor, tau, lambda);
+        if (corr) virKinTerm += (f2 ? f2[slice] : 0.0) * gradVFactor[eo] * pow(tau, 3) * lambda;     // virialKinCorrection, action.cpp:1786-1803
+        if (eo == 0) totVop += 0.0 + vint[slice];
+        P3 += VFactor[eo] * tau * v[0] + (corr ? v[1] * c2 : 0.0);                                   // rDOTgradUterm1 + term2
+    }
+    P3 *= (1.0 / (2.0 * numTimeSlices));
+    Pressure -= P3;
+    Pressure /= (nd * tau * volume);
+    totVop /= (0.5 * numTimeSlices);
+    totVop += tailV;
+    T3 /= (2.0 * beta);
+    T4 /= (1.0 * beta);
+    T5 /= (1.0 * numTimeSlices);
+    virKinTerm /= (0.5 * beta);
+    thermE *= (0.25 / (lambda * tau)) / (tau * numTimeSlices);
+    thermE += thermTerm1;
+    thermE += T5;
+    thermE += tailV;
+    const double totEcv = T1 + T2 + T3 + T4 + T5 + tailV;
+    const double Kcv = T1 + T2 + T3 + T4 + virKinTerm;
+    double dEdB = (-1.0 * T1 - 2.0 * T2 + 2.0 * T4) / tau;
+    for (int slice = 0; slice < numTimeSlices; slice++) {
+        const int eo = slice % 2;
+        double d2U = 0.0;
+        if (gradVFactor[eo] > kEPS) d2U += 6.0 * gradVFactor[eo] * tau * lambda * (f2 ? f2[slice] : 0.0);   // action.cpp:776-787
+        dEdB += d2U / (1.0 * numTimeSlices);
+    }
+    dEdB *= beta * beta / (1.0 * numTimeSlices);
+    for (int k = 0; k < 19; ++k) out[k] = 0.0;
+    out[0] = totEcv - totVop; out[1] = Kcv; out[2] = totVop; out[3] = totEcv - Kcv; out[4] = totEcv;
+    out[5] = totEcv - mu * numParticles;
+    if (numParticles > 0) {
+        out[6] = (totEcv - totVop) / (1.0 * numParticles); out[7] = Kcv / (1.0 * numParticles);
+        out[8] = totVop / (1.0 * numParticles); out[9] = (totEcv - Kcv) / (1.0 * numParticles); out[10] = totEcv / (1.0 * numParticles);
+    }
+    out[11] = totEcv * thermE * beta * beta;
+    out[12] = totEcv * beta;
+    out[13] = dEdB;
+    out[14] = totEcv * thermE * beta * beta * totEcv * beta;
+    if (quirk) out[0] += totEcv * beta * dEdB; else out[15] = totEcv * beta * dEdB;
+    out[16] = totEcv * thermE * beta * beta * dEdB;
+    out[17] = thermE;
+    out[18] = Pressure;
     return 0;
 }
 

@@ -30,9 +30,10 @@ def _array_text(rows, fmt) -> str:
     return "".join(out)
 
 
-def write_state(path, beads, on=None, n_moves=7, n_estimators=4, rng_words=8) -> None:
+def write_state(path, beads, on=None, n_moves=7, n_estimators=4, rng_words=8, next_link=None) -> None:
     """beads [M][W][ndim]; on [M][W] (1 = active, default all).  Links are the straight worldlines of a diagonal
-    configuration: next(s,p) = (s+1 mod M, p) for active beads, (XXX,XXX) otherwise."""
+    configuration: next(s,p) = (s+1 mod M, p) for active beads, (XXX,XXX) otherwise -- or `next_link` [M][W][2]
+    (permuted world lines), with prev its inverse."""
     beads = np.asarray(beads, dtype=np.float64)
     M, W, _ = beads.shape
     on = np.ones((M, W), dtype=np.uint32) if on is None else np.asarray(on, dtype=np.uint32)
@@ -40,6 +41,14 @@ def write_state(path, beads, on=None, n_moves=7, n_estimators=4, rng_words=8) ->
     loc = lambda v: "(%d,%d)" % (v[0], v[1])                           # noqa: E731
     nxt = [[((s + 1) % M, p) if on[s, p] else (XXX, XXX) for p in range(W)] for s in range(M)]
     prv = [[((s - 1) % M, p) if on[s, p] else (XXX, XXX) for p in range(W)] for s in range(M)]
+    if next_link is not None:
+        nxt = [[tuple(int(v) for v in next_link[s][p]) if on[s, p] else (XXX, XXX) for p in range(W)] for s in range(M)]
+        prv = [[(XXX, XXX) for p in range(W)] for s in range(M)]
+        for s in range(M):
+            for p in range(W):
+                if on[s, p]:
+                    a, b = nxt[s][p]
+                    prv[a][b] = (s, p)
     with open(path, "w") as f:
         f.write(f"{int(on.sum()) // M}\n")                            # getNumParticles()
         for k in range(1 + n_moves + n_estimators):                  # "%16d\t%16d\n" acceptance / sampling lines

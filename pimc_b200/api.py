@@ -26,7 +26,8 @@ SYMBOLS = [
     "pimcb_host_unregister", "pimcb_ssf", "pimcb_isf", "pimcb_ssf_isf", "pimcb_ssf_isf_beads", "pimcb_measure", "pimcb_reset_bins",
     "pimcb_read_bins", "pimcb_bins_device_ptr", "pimcb_sync", "pimcb_stream", "pimcb_set_pair_table",
     "pimcb_pair_sums", "pimcb_measure_fp64_peak", "pimcb_set_profiling", "pimcb_set_profiling_stride", "pimcb_kernel_times",
-    "pimcb_launch_count", "pimcb_rho_plan_info",
+    "pimcb_launch_count", "pimcb_rho_plan_info", "pimcb_elastic", "pimcb_ssf_cyl", "pimcb_set_pair_table_d2",
+    "pimcb_virial_sums",
 ]
 
 
@@ -85,6 +86,10 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.pimcb_set_profiling_stride.argtypes = [vp, C.c_int]
     lib.pimcb_kernel_times.argtypes = [vp, _dp, C.POINTER(C.c_long), C.c_int]
     lib.pimcb_rho_plan_info.argtypes = [vp, _ip]
+    lib.pimcb_elastic.argtypes = [vp, _dp]
+    lib.pimcb_ssf_cyl.argtypes = [vp, C.c_double, _dp, _ip]
+    lib.pimcb_set_pair_table_d2.argtypes = [vp, _dp, C.c_int, _dp]
+    lib.pimcb_virial_sums.argtypes = [vp, _dp, C.c_int, _dp]
     if path == _build.LIB:
         _lib = lib
     return lib
@@ -121,7 +126,7 @@ class PinnedArray:
 class Context:
     """One pimcb_ctx: one device, one spatial dimension, one box + q-set."""
 
-    KERNELS = ("rho", "corr", "ssf_direct", "bins", "pair", "transpose")
+    KERNELS = ("rho", "corr", "ssf_direct", "bins", "pair", "transpose", "variant", "virial")
 
     def __init__(self, device: int = 0, ndim: int = 3):
         self.lib = load_library()
@@ -293,13 +298,41 @@ class Context:
                                            float(dSep) if dSep else 0.0, f2_parity))
         return vint, f2, hist
 
+    # -- scattering variants / virial ---------------------------------------------------------------------
+    def elastic(self):
+        """[B][nq]: the upstream elastic-scattering estimator's per-measurement increment."""
+        B, _, _ = self.shape
+        out = np.zeros((B, self.nq))
+        self._chk(self.lib.pimcb_elastic(self._h, _ptr(out)))
+        return out
+
+    def ssf_cyl(self, maxR: float):
+        """([B][nq] raw cylinder S(q) sums, [B] beads of slice 0 inside the radius)."""
+        B, _, _ = self.shape
+        out = np.zeros((B, self.nq))
+        n_in = np.zeros(B, dtype=np.int32)
+        self._chk(self.lib.pimcb_ssf_cyl(self._h, float(maxR), _ptr(out), n_in.ctypes.data_as(_ip)))
+        return out, n_in
+
+    def set_pair_table_d2(self, d2V, ext=(0.0, 0.0)):
+        d2V, e = _f64(d2V), _f64(ext)
+        self._chk(self.lib.pimcb_set_pair_table_d2(self._h, _ptr(d2V), len(d2V), _ptr(e)))
+
+    def virial_sums(self, delta=None, t2_parity=-1):
+        """[B][M][4] = {sum gV.r, sum (T gV).r, sum gV.delta, sum (T gV).delta}; delta in the staged beads' AoS shape."""
+        B, M, _ = self.shape
+        d = _f64(delta) if delta is not None else None
+        out = np.zeros((B, M, 4))
+        self._chk(self.lib.pimcb_virial_sums(self._h, _ptr(d), t2_parity, _ptr(out)))
+        return out
+
     # -- measurement helpers ----------------------------------------------------------------------------
     def fp64_peak_tflops(self, seconds=0.5) -> float:
         v = C.c_double(0.0)
         self._chk(self.lib.pimcb_measure_fp64_peak(self._h, C.byref(v), seconds))
         return v.value
 
-    KERNEL_IDS = {"rho": 0, "corr": 1, "direct": 2, "bins": 3, "pair": 4, "transpose": 5}
+    KERNEL_IDS = {"rho": 0, "corr": 1, "direct": 2, "bins": 3, "pair": 4, "transpose": 5, "variant": 6, "virial": 7}
 
     def set_profiling(self, on):
         """False / True (every kernel) or an iterable of kernel names to time."""

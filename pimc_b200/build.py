@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libpimc_b200.so")
 SOURCES = [os.path.join(CSRC, "pimcb.cu")]
-HEADERS = [os.path.join(CSRC, "kernels.cuh"), os.path.join(_HERE, "..", "include", "pimc_b200.h")]
+HEADERS = [os.path.join(CSRC, "kernels.cuh"), os.path.join(CSRC, "kernels_ext.cuh"), os.path.join(_HERE, "..", "include", "pimc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--fmad=true", "-cudart", "shared"]
 

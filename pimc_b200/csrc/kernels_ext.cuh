@@ -1,0 +1,235 @@
+// kernels_ext.cuh -- the scattering-family variants and the virial slice sums.
+// Same conventions as kernels.cuh: FP64 throughout, one CTA per (configuration, slice), SoA slice rows
+// pos[sl][d][Npad], fixed-order reductions (results do not depend on scheduling).
+#pragma once
+
+#include "kernels.cuh"
+
+namespace pimcb {
+
+// ---------------------------------------------------------------------------------------------
+// Elastic scattering: the upstream "elastic scattering gpu" estimator launches gpu_isf<true> once per q with
+// M/2 + 1 blocks that all atomicAdd 2*inorm*sum into es[q], inorm = 1/(N M)
+// (src/estimator_gpu.cu:66-164, 408-413; src/estimator.cpp:4197-4235):
+//     es[q] = 2/(N M) sum_{tau=0}^{M/2} sum_t sum_{i,j} cos(q.(r_j(t+tau) - r_i(t))) = (2/M) sum_{tau<=M/2} cfg_isf[q][tau]
+// with cfg_isf = isf/N as left in cfg[b][nq + q*M + tau] by the tau-correlation.  One warp per (configuration, q);
+// lanes stride tau, fixed butterfly.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) elastic_kernel(const double* __restrict__ cfg, double* __restrict__ out, int B, int nq, int M) {
+    const int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (pair >= B * nq) return;
+    const int b = pair / nq, iq = pair - b * nq;
+    const size_t stride = static_cast<size_t>(nq) * (1 + M);
+    const double* f = cfg + b * stride + nq + static_cast<size_t>(iq) * M;
+    double acc = 0.0;
+    for (int tau = lane; tau <= M / 2; tau += 32) acc += f[tau];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[pair] = acc * (2.0 / M);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cylinder static structure factor (CylinderStaticStructureFactorEstimator::accumulate, src/estimator.cpp:5415-5456;
+// include(r, maxR) = r[0]^2 + r[1]^2 < maxR^2, :4309-4311):
+//     partial[sl][q] = sum_{i in} [ 1 + 2 sum_{j > i, j in} cos(q . minimage(r_i - r_j)) ]
+// q commensurate with the periodic box (the estimator's own "line" q-set: multiples of 2 pi / L_z along z):
+// |sum_{i in} exp(i q.r_i)|^2, one warp per q with lanes over particles; other q: the masked pair loop.
+// inside[b] = number of slice-0 beads inside the radius (num1DParticles, :4318-4327).
+// ---------------------------------------------------------------------------------------------
+template <int ND>
+__global__ void __launch_bounds__(256) ssf_cyl_kernel(const double* __restrict__ pos, const double* __restrict__ qsoa,
+                                                       const unsigned char* __restrict__ comm, int nq, double maxR,
+                                                       double* __restrict__ partial, int* __restrict__ inside, int nslices, int M,
+                                                       int N, int Npad, BoxDev box) {
+    extern __shared__ __align__(16) double sm[];
+    double* xs = sm;                                          // [ND][Npad]
+    unsigned char* in = reinterpret_cast<unsigned char*>(sm + ND * Npad);   // [Npad]
+    __shared__ int s_count;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const double maxR2 = maxR * maxR;
+    for (int sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
+        load_slice(xs, pos + static_cast<size_t>(sl) * ND * Npad, ND * Npad);
+        if (threadIdx.x == 0) s_count = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < Npad; i += blockDim.x) {
+            const double x = xs[i], y = xs[Npad + i];
+            const bool ok = i < N && __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)) < maxR2;
+            in[i] = ok ? 1 : 0;
+            if (ok) atomicAdd(&s_count, 1);
+        }
+        __syncthreads();
+        const int n_in = s_count;
+        if (threadIdx.x == 0 && (sl % M) == 0) inside[sl / M] = n_in;
+        for (int iq = warp; iq < nq; iq += nwarps) {
+            double qv[ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) qv[d] = __ldg(qsoa + d * nq + iq);
+            double val;
+            if (comm[iq]) {
+                double cs = 0.0, sn = 0.0;
+                for (int i = lane; i < N; i += 32) {
+                    if (!in[i]) continue;
+                    double ph = qv[0] * xs[i];
+#pragma unroll
+                    for (int d = 1; d < ND; ++d) ph = fma(qv[d], xs[d * Npad + i], ph);
+                    double s, c;
+                    sincos_fast(ph, s, c);
+                    cs += c;
+                    sn += s;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    cs += __shfl_xor_sync(0xffffffffu, cs, o);
+                    sn += __shfl_xor_sync(0xffffffffu, sn, o);
+                }
+                val = fma(cs, cs, sn * sn);
+            } else {
+                double acc = 0.0;
+                for (int i = 0; i < N; ++i) {
+                    if (!in[i]) continue;
+                    for (int j = i + 1 + lane; j < N; j += 32) {
+                        if (!in[j]) continue;
+                        double ph = 0.0;
+#pragma unroll
+                        for (int d = 0; d < ND; ++d) {
+                            const double s = xs[d * Npad + i] - xs[d * Npad + j];
+                            ph = fma(qv[d], s - box.pSide[d] * floor(fma(s, box.sideInv[d], 0.5)), ph);
+                        }
+                        double s, c;
+                        sincos_fast(ph, s, c);
+                        acc += c;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                val = fma(2.0, acc, static_cast<double>(n_in));
+            }
+            if (lane == 0) partial[static_cast<size_t>(sl) * nq + iq] = val;
+        }
+        __syncthreads();
+    }
+}
+
+// out[b][q] = sum_t partial[b*M + t][q]   (t ascending)
+__global__ void ssf_cyl_finalize_kernel(const double* __restrict__ partial, double* __restrict__ out, int B, int M, int nq) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * nq) return;
+    const int b = idx / nq, iq = idx - b * nq;
+    double acc = 0.0;
+    for (int t = 0; t < M; ++t) acc += partial[(static_cast<size_t>(b) * M + t) * nq + iq];
+    out[idx] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Virial slice sums (VirialEnergyEstimator::accumulate, src/estimator.cpp:1086-1250) -- the O(N^2) per-slice parts of
+//   LocalAction::rDOTgradUterm1 / term2        (src/action.cpp:1446-1575)   w_i = r_i            (raw position)
+//   LocalAction::deltadotgradUterm1 / term2    (src/action.cpp:1588-1784)   w_i = delta_i        (bead - centroid of its
+//                                                                            world-line window, from the host)
+// For every particle i of the slice, over all partners j != i with sep = minimage(r_i - r_j), r = |sep|,
+// k = int(r/dr) (bit-identical to the CPU, see pair_kernel):
+//   gV_i  = sum_j (dVdr[k]/r) sep                                        (AzizPotential::gradV, potential.h:997-1003)
+//   T_i   = sum_j [ sep sep^T (d2V[k]/r^2 - dV/r^3) + 1 dV/r ],  dV = |(dVdr[k]/r) sep|   (action.cpp:1547-1554, 1722-1729)
+// and out[sl] = { sum_i gV_i.r_i, sum_i (T_i gV_i).r_i, sum_i gV_i.delta_i, sum_i (T_i gV_i).delta_i }.
+// The prefactors (VFactor tau, 2 gradVFactor tau^3 lambda) are applied by the caller.  t2_parity selects the slices
+// whose gradVFactor is finite (-1 all, 0 even, 1 odd, -2 none): the T-matrix terms of the others are returned as 0,
+// as upstream skips them (action.cpp:1505, 1680).  External potential "free" (zero gradient and Laplacian).
+// ---------------------------------------------------------------------------------------------
+struct VirialParams {
+    const double* dVdr; const double* d2V; int len; double dr; double extdV[2]; double extd2V[2]; int t2_parity; int M;
+};
+
+template <int ND>
+__global__ void __launch_bounds__(256, 2) virial_kernel(const double* __restrict__ pos, const double* __restrict__ delta, int nslices,
+                                                         int N, int Npad, BoxDev box, VirialParams vp, double* __restrict__ out) {
+    constexpr int NT = ND * (ND + 1) / 2;
+    extern __shared__ __align__(16) double sm[];
+    double* xs = sm;                                  // [ND][Npad]
+    double* ds = sm + ND * Npad;                      // [ND][Npad] (delta)
+    __shared__ double red[4][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
+        const int t = sl % vp.M;
+        const bool do_t2 = vp.t2_parity == -1 || (vp.t2_parity >= 0 && (t & 1) == vp.t2_parity);
+        load_slice(xs, pos + static_cast<size_t>(sl) * ND * Npad, ND * Npad);
+        if (delta) load_slice(ds, delta + static_cast<size_t>(sl) * ND * Npad, ND * Npad);
+        __syncthreads();
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            double gV[ND], T[NT];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) gV[d] = 0.0;
+#pragma unroll
+            for (int k = 0; k < NT; ++k) T[k] = 0.0;
+            for (int kk = 1; kk < N; ++kk) {
+                int j = i + kk;
+                if (j >= N) j -= N;
+                double sep[ND];
+                const double r = minimage_norm<ND>(xs, Npad, i, j, box, sep);     // getSeparation(bead1, bead2)
+                const int kidx = __double2int_rz(__ddiv_rn(r, vp.dr));
+                const bool inside = kidx > 0 && kidx < vp.len;
+                const double dv = inside ? __ldg(vp.dVdr + kidx) : (kidx <= 0 ? vp.extdV[0] : vp.extdV[1]);
+                const double g = dv / r;
+                double gi[ND], g2 = 0.0;
+#pragma unroll
+                for (int d = 0; d < ND; ++d) {
+                    gi[d] = __dmul_rn(g, sep[d]);              // gVi as its own rounded value, then gV += gVi (action.cpp:1466, 1556)
+                    gV[d] = __dadd_rn(gV[d], gi[d]);
+                    g2 = fma(gi[d], gi[d], g2);
+                }
+                if (do_t2) {
+                    const double d2 = inside ? __ldg(vp.d2V + kidx) : (kidx <= 0 ? vp.extd2V[0] : vp.extd2V[1]);
+                    const double dV = sqrt(g2);
+                    const double rinv = 1.0 / r;
+                    const double a = d2 * rinv * rinv - dV * rinv * rinv * rinv;
+                    const double diag = dV * rinv;
+                    int k = 0;
+#pragma unroll
+                    for (int p = 0; p < ND; ++p)
+#pragma unroll
+                        for (int q = p; q < ND; ++q, ++k) T[k] = fma(sep[p] * sep[q], a, T[k]) + (p == q ? diag : 0.0);
+                }
+            }
+            double u[ND];
+#pragma unroll
+            for (int p = 0; p < ND; ++p) u[p] = 0.0;
+            {
+                int k = 0;
+#pragma unroll
+                for (int p = 0; p < ND; ++p)
+#pragma unroll
+                    for (int q = p; q < ND; ++q, ++k) {
+                        u[p] = fma(T[k], gV[q], u[p]);
+                        if (q != p) u[q] = fma(T[k], gV[p], u[q]);
+                    }
+            }
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                const double x = xs[d * Npad + i];
+                acc[0] = fma(gV[d], x, acc[0]);
+                acc[1] = fma(u[d], x, acc[1]);
+                if (delta) {
+                    const double dl = ds[d * Npad + i];
+                    acc[2] = fma(gV[d], dl, acc[2]);
+                    acc[3] = fma(u[d], dl, acc[3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double v = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red[k][warp] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            double v = 0.0;
+            for (int w = 0; w < (blockDim.x >> 5); ++w) v += red[threadIdx.x][w];
+            out[static_cast<size_t>(sl) * 4 + threadIdx.x] = v;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace pimcb

@@ -3,6 +3,7 @@
 // every entry point fails with PIMCB_ECUDA when no device is usable.
 #include "../../include/pimc_b200.h"
 #include "kernels.cuh"
+#include "kernels_ext.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -40,7 +41,7 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr int kSlots = 4;
 constexpr int kKernels = 8;
-enum { K_RHO = 0, K_CORR = 1, K_DIRECT = 2, K_BINS = 3, K_PAIR = 4, K_TRANSPOSE = 5 };
+enum { K_RHO = 0, K_CORR = 1, K_DIRECT = 2, K_BINS = 3, K_PAIR = 4, K_TRANSPOSE = 5, K_VARIANT = 6, K_VIRIAL = 7 };
 
 struct DevBuf {
     void* p = nullptr;
@@ -79,6 +80,7 @@ struct Slot {
     DevBuf aos;            // landing buffer of the zero-bounce path: the reference AoS array as DMA'd
     int B = 0, M = 0, N = 0, Npad = 0, Next = 0;
     bool staged = false;
+    unsigned long gen = 0;            // staging generation (identifies the configuration batch held by the slot)
     bool needs_transpose = false;     // aos holds the data; the first consumer transposes it on the compute stream
     cudaEvent_t ready = nullptr;      // H2D (+ transpose) complete
     cudaEvent_t consumed = nullptr;   // last kernel reading this slot has been enqueued before this event
@@ -143,6 +145,13 @@ struct pimcb_ctx {
     DevBuf d_binrows;                      // persistent quad rows [rows][nq][M/2+1] of the measure path (folded into d_bins on read)
     int binrows_n = 0;                     // rows in use since the last fold (0 = nothing pending)
     int binrows_cap = 0;                   // rows the buffer holds for the current (nq, M)
+    // per-configuration results cache: d_cfg holds S(q)/F(q,tau) of slot cfg_slot at staging generation cfg_gen
+    unsigned long gen_counter = 0, cfg_gen = 0;
+    int cfg_slot = -1;
+    // scattering variants (elastic, cylinder S(q)) and virial slice sums
+    DevBuf d_var, d_inside, d_d2V, d_delta_aos, d_delta, d_vir;
+    bool have_d2V = false;
+    double extd2V[2] = {0, 0};
     DevBuf d_sched;                        // ticket counter + retire counter of the persistent-warp rho kernel (self re-arming)
 };
 
@@ -516,6 +525,9 @@ int run_estimators(pimcb_ctx* c, Slot** sp, int* rows = nullptr) {
     if ((rc = launch_direct(c, *s))) return rc;
     CU(cudaEventRecord(s->consumed, c->stream));
     *sp = s;
+    // d_cfg holds complete per-configuration rows only on the per-configuration path (no quad-summed rows)
+    c->cfg_slot = (rows == nullptr) ? c->cur : -1;
+    c->cfg_gen = s->gen;
     return 0;
 }
 
@@ -573,7 +585,7 @@ int stage_into(pimcb_ctx* c, int slot, const double* beads, int B, int M, int N,
     CU(cudaStreamWaitEvent(c->copy_stream, s.consumed, 0));
     int rc = s.pos.ensure(soa_bytes);
     if (rc) return rc;
-    s.B = B; s.M = M; s.N = N; s.Npad = Npad;
+    s.B = B; s.M = M; s.N = N; s.Npad = Npad; s.Next = Next;
 
     cudaPointerAttributes attr{};
     const bool pinned = cudaPointerGetAttributes(&attr, beads) == cudaSuccess && attr.type == cudaMemoryTypeHost;
@@ -613,6 +625,8 @@ int stage_into(pimcb_ctx* c, int slot, const double* beads, int B, int M, int N,
         s.needs_transpose = false;
     }
     s.staged = true;
+    s.gen = ++c->gen_counter;
+    if (c->cfg_slot == slot) c->cfg_slot = -1;
     return 0;
 }
 
@@ -910,6 +924,7 @@ int pimcb_set_qvecs(pimcb_ctx* c, const double* q, int nq) {
     if (!sel.empty()) CU(cudaMemcpyAsync(c->d_qidx.p, sel.data(), sizeof(int) * sel.size(), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->bins_len = 0;   // layout changed: bins are re-created on the next measurement
+    c->cfg_slot = -1;
     return 0;
 }
 
@@ -918,12 +933,14 @@ int pimcb_num_commensurate(const pimcb_ctx* c) { return c ? c->ncomm : PIMCB_EIN
 int pimcb_set_rho_mode(pimcb_ctx* c, int mode) {
     if (!c || mode < 0 || mode > 2) return fail(PIMCB_EINVAL, "rho mode must be 0, 1 or 2");
     c->rho_mode = mode;
+    c->cfg_slot = -1;
     return 0;
 }
 
 int pimcb_set_corr_mode(pimcb_ctx* c, int mode) {
     if (!c || mode < 0 || mode > 1) return fail(PIMCB_EINVAL, "corr mode must be 0 or 1");
     c->corr_mode = mode;
+    c->cfg_slot = -1;
     return 0;
 }
 
@@ -1125,6 +1142,136 @@ int pimcb_pair_sums(pimcb_ctx* c, double* vint, double* f2, int* sephist, double
     CU(cudaMemcpyAsync(vint, c->d_vint.p, sizeof(double) * nsl, cudaMemcpyDeviceToHost, c->stream));
     if (f2) CU(cudaMemcpyAsync(f2, c->d_f2.p, sizeof(double) * nsl, cudaMemcpyDeviceToHost, c->stream));
     if (sephist) CU(cudaMemcpyAsync(sephist, c->d_hist.p, sizeof(int) * static_cast<size_t>(nsl) * kNPCFSEP, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- scattering variants ------------------------------------------------------------------------------------------
+int pimcb_elastic(pimcb_ctx* c, double* out) {
+    if (!c || !out) return fail(PIMCB_EINVAL, "null argument");
+    CU(cudaSetDevice(c->device));
+    Slot* s;
+    int rc = need_cur(c, &s);
+    if (rc) return rc;
+    // S(q)/F(q,tau) of this very configuration batch may already be in d_cfg (pimcb_ssf_isf just before): reuse it
+    if (!(c->cfg_slot == c->cur && c->cfg_gen == s->gen) && (rc = run_estimators(c, &s))) return rc;
+    const int pairs = s->B * c->nq;
+    if ((rc = c->d_var.ensure(sizeof(double) * pairs))) return rc;
+    {
+        KTimer kt(c, K_VARIANT);
+        elastic_kernel<<<(pairs + 3) / 4, 128, 0, c->stream>>>(c->d_cfg.as<double>(), c->d_var.as<double>(), s->B, c->nq, s->M);
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(out, c->d_var.p, sizeof(double) * pairs, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int pimcb_ssf_cyl(pimcb_ctx* c, double maxR, double* out, int* n_inside) {
+    if (!c || !out) return fail(PIMCB_EINVAL, "null argument");
+    if (c->ndim < 2) return fail(PIMCB_EINVAL, "the cylinder cut-off needs at least two spatial dimensions");
+    if (!(maxR > 0.0)) return fail(PIMCB_EINVAL, "maxR must be positive");
+    CU(cudaSetDevice(c->device));
+    Slot* s;
+    int rc = need_cur(c, &s);
+    if (rc) return rc;
+    if (c->nq <= 0) return fail(PIMCB_ESTATE, "no q-vectors set");
+    if (!c->have_box) return fail(PIMCB_ESTATE, "no box set");
+    if (c->max_phase > 1.0e5) return fail(PIMCB_EINVAL, "max |q.r| = %g exceeds the sincos validity range 1e5", c->max_phase);
+    const int nd = c->ndim, nsl = s->B * s->M;
+    if ((rc = c->d_partial.ensure(sizeof(double) * static_cast<size_t>(nsl) * c->nq))) return rc;
+    if ((rc = c->d_var.ensure(sizeof(double) * s->B * c->nq))) return rc;
+    if ((rc = c->d_inside.ensure(sizeof(int) * s->B))) return rc;
+    CU(cudaStreamWaitEvent(c->stream, s->ready, 0));
+    if ((rc = materialize(c, *s))) return rc;
+    {
+        KTimer kt(c, K_VARIANT);
+        const size_t smem = sizeof(double) * nd * s->Npad + static_cast<size_t>(s->Npad);
+#define LAUNCH_CYL(ND)                                                                                             \
+        rc = set_smem(ssf_cyl_kernel<ND>, smem); if (rc) return rc;                                                 \
+        ssf_cyl_kernel<ND><<<nsl, 256, smem, c->stream>>>(s->pos.as<double>(), c->d_q.as<double>(), c->d_comm.as<unsigned char>(), \
+                                                          c->nq, maxR, c->d_partial.as<double>(), c->d_inside.as<int>(), nsl, s->M, \
+                                                          s->N, s->Npad, c->box)
+        if (nd == 2) { LAUNCH_CYL(2); } else { LAUNCH_CYL(3); }
+#undef LAUNCH_CYL
+        CU(cudaGetLastError());
+    }
+    const int tot = s->B * c->nq;
+    ssf_cyl_finalize_kernel<<<(tot + 127) / 128, 128, 0, c->stream>>>(c->d_partial.as<double>(), c->d_var.as<double>(), s->B, s->M, c->nq);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(s->consumed, c->stream));
+    CU(cudaMemcpyAsync(out, c->d_var.p, sizeof(double) * tot, cudaMemcpyDeviceToHost, c->stream));
+    if (n_inside) CU(cudaMemcpyAsync(n_inside, c->d_inside.p, sizeof(int) * s->B, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- virial slice sums ----------------------------------------------------------------------------------------------
+int pimcb_set_pair_table_d2(pimcb_ctx* c, const double* d2Vdr2, int len, const double* extd2Vdr2) {
+    if (!c || !d2Vdr2) return fail(PIMCB_EINVAL, "null argument");
+    if (!c->tab_len || !c->have_dV) return fail(PIMCB_ESTATE, "pimcb_set_pair_table (with dV/dr) must precede pimcb_set_pair_table_d2");
+    if (len != c->tab_len) return fail(PIMCB_EINVAL, "d2V/dr2 table length %d differs from the V table length %d", len, c->tab_len);
+    CU(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = c->d_d2V.ensure(sizeof(double) * len))) return rc;
+    CU(cudaMemcpyAsync(c->d_d2V.p, d2Vdr2, sizeof(double) * len, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->extd2V[0] = extd2Vdr2 ? extd2Vdr2[0] : 0.0;
+    c->extd2V[1] = extd2Vdr2 ? extd2Vdr2[1] : 0.0;
+    c->have_d2V = true;
+    return 0;
+}
+
+int pimcb_virial_sums(pimcb_ctx* c, const double* delta_aos, int t2_parity, double* out) {
+    if (!c || !out) return fail(PIMCB_EINVAL, "null argument");
+    if (t2_parity < -2 || t2_parity > 1) return fail(PIMCB_EINVAL, "t2_parity must be -2, -1, 0 or 1");
+    CU(cudaSetDevice(c->device));
+    Slot* s;
+    int rc = need_cur(c, &s);
+    if (rc) return rc;
+    if (!c->have_box) return fail(PIMCB_ESTATE, "no box set");
+    if (!c->tab_len || !c->have_dV) return fail(PIMCB_ESTATE, "no dV/dr table set");
+    if (t2_parity != -2 && !c->have_d2V) return fail(PIMCB_ESTATE, "T-matrix terms requested but no d2V/dr2 table set");
+    const int nd = c->ndim, nsl = s->B * s->M;
+    if ((rc = c->d_vir.ensure(sizeof(double) * 4 * nsl))) return rc;
+    CU(cudaStreamWaitEvent(c->stream, s->ready, 0));
+    if ((rc = materialize(c, *s))) return rc;
+    const double* d_delta = nullptr;
+    if (delta_aos) {
+        // same AoS shape as the staged beads ([B][M][N_ext][ndim]); transposed on the device into the slice-row layout
+        const int Next = s->Next > 0 ? s->Next : s->N;
+        const size_t aos_bytes = sizeof(double) * static_cast<size_t>(nsl) * Next * nd;
+        if ((rc = c->d_delta_aos.ensure(aos_bytes))) return rc;
+        if ((rc = c->d_delta.ensure(sizeof(double) * static_cast<size_t>(nsl) * nd * s->Npad))) return rc;
+        CU(cudaMemcpyAsync(c->d_delta_aos.p, delta_aos, aos_bytes, cudaMemcpyHostToDevice, c->stream));
+        const size_t tsmem = sizeof(double) * s->N * nd;
+        const int tgrid = static_cast<int>(std::min<size_t>(nsl, static_cast<size_t>(c->sm_count) * 8));
+#define LAUNCH_TD(ND)                                                                                              \
+        rc = set_smem(aos_to_soa_kernel<ND>, tsmem); if (rc) return rc;                                             \
+        aos_to_soa_kernel<ND><<<tgrid, 256, tsmem, c->stream>>>(c->d_delta_aos.as<double>(), c->d_delta.as<double>(), nsl, s->N, Next, s->Npad)
+        {
+            KTimer kt(c, K_TRANSPOSE);
+            if (nd == 1) { LAUNCH_TD(1); } else if (nd == 2) { LAUNCH_TD(2); } else { LAUNCH_TD(3); }
+        }
+#undef LAUNCH_TD
+        CU(cudaGetLastError());
+        d_delta = c->d_delta.as<double>();
+    }
+    VirialParams vp{c->d_dV.as<double>(), c->d_d2V.as<double>(), c->tab_len, c->dr, {c->extdV[0], c->extdV[1]},
+                    {c->extd2V[0], c->extd2V[1]}, t2_parity, s->M};
+    {
+        KTimer kt(c, K_VIRIAL);
+        const size_t smem = sizeof(double) * 2 * nd * s->Npad;
+#define LAUNCH_VIR(ND)                                                                                             \
+        rc = set_smem(virial_kernel<ND>, smem); if (rc) return rc;                                                  \
+        virial_kernel<ND><<<nsl, 256, smem, c->stream>>>(s->pos.as<double>(), d_delta, nsl, s->N, s->Npad, c->box, vp, c->d_vir.as<double>())
+        if (nd == 1) { LAUNCH_VIR(1); } else if (nd == 2) { LAUNCH_VIR(2); } else { LAUNCH_VIR(3); }
+#undef LAUNCH_VIR
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(s->consumed, c->stream));
+    CU(cudaMemcpyAsync(out, c->d_vir.p, sizeof(double) * 4 * nsl, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return 0;
 }

@@ -11,6 +11,7 @@ LocalActionB200::LocalActionB200(const Path& _path, PotentialBase* external, Pot
     const bool even = gradVFactor[0] > EPS, odd = gradVFactor[1] > EPS;
     needF2 = even || odd;
     f2Parity = (even && odd) ? -1 : (odd ? 1 : 0);
+    if (table.d2Vdr2) B200Session::get(path).setPairTableD2(table.d2Vdr2, table.tableLength, table.extd2Vdr2.data());
 }
 
 const B200Session::PairSums& LocalActionB200::sums() {
@@ -68,4 +69,45 @@ double LocalActionB200::derivPotentialActionLambda(int slice) {
     const int eo = slice % 2;
     if (gradVFactor[eo] > EPS) return gradVFactor[eo] * tau() * tau() * tau() * sumsForSlice(slice, 2).f2[slice];
     return 0.0;
+}
+
+// ---- virial / pressure terms ----------------------------------------------------------------------------------------
+// The virial estimator walks slice = 0..M-1 calling all of these per slice (src/estimator.cpp:1160-1172); they share one
+// device pass.  Only the first of them (deltaDOTgradUterm1, the first call of that loop) marks a new configuration in
+// unhooked mode.  External potential: zero gradient / Laplacian only (FreePotential), as for gradVSquared.
+const double* LocalActionB200::virial(int slice) {
+    const int t2 = needF2 ? f2Parity : -2;
+    return &B200Session::get(path).virialSums(constants()->virialWindow(), t2)[static_cast<size_t>(slice) * 4];
+}
+
+double LocalActionB200::rDOTgradUterm1(int slice) { return VFactor[slice % 2] * tau() * virial(slice)[0]; }
+
+double LocalActionB200::rDOTgradUterm2(int slice) {
+    const int eo = slice % 2;
+    if (!(gradVFactor[eo] > EPS)) return 0.0;
+    return virial(slice)[1] * (2.0 * gradVFactor[eo] * std::pow(tau(), 3) * constants()->lambda());
+}
+
+double LocalActionB200::deltaDOTgradUterm1(int slice) {
+    if (slice <= lastSlice[3]) B200Session::get(path).beginIfUnhooked();
+    lastSlice[3] = slice;
+    return VFactor[slice % 2] * tau() * virial(slice)[2];
+}
+
+double LocalActionB200::deltaDOTgradUterm2(int slice) {
+    const int eo = slice % 2;
+    if (!(gradVFactor[eo] > EPS)) return 0.0;
+    return virial(slice)[3] * (2.0 * gradVFactor[eo] * std::pow(tau(), 3) * constants()->lambda());
+}
+
+double LocalActionB200::virKinCorr(int slice) {
+    const int eo = slice % 2;
+    if (!(gradVFactor[eo] > EPS)) return 0.0;
+    return sums().f2[slice] * gradVFactor[eo] * std::pow(tau(), 3) * constants()->lambda();
+}
+
+double LocalActionB200::secondderivPotentialActionTau(int slice) {
+    const int eo = slice % 2;
+    if (!(gradVFactor[eo] > EPS)) return 0.0;
+    return 6.0 * gradVFactor[eo] * tau() * constants()->lambda() * sums().f2[slice];
 }

@@ -5,6 +5,7 @@
 //     potential(int slice)  = V(slice)     (include/action.h:197, src/action.cpp:902-947) incl. the sepHist side effect
 //     derivPotentialActionTau(int slice)   (src/action.cpp:751-765)
 //     derivPotentialActionLambda(int slice)(src/action.cpp:798-806)
+//     rDOTgradUterm1/2, deltaDOTgradUterm1/2, virKinCorr, secondderivPotentialActionTau (virial estimator, pressure)
 // -- from ONE device pass over all slices (pimcb_pair_sums) per configuration instead of M O(N^2) host loops, and
 // removes the redundant re-evaluations the energy estimator triggers (V(slice) 1+1/period times, gradVSquared twice
 // per corrected slice; src/estimator.cpp:983-988).  The external potential is evaluated on the host through the
@@ -29,13 +30,21 @@ public:
     double derivPotentialActionTau(int slice) override;
     double derivPotentialActionLambda(int slice) override;
     double gradVSquared(int slice);
+    // virial / pressure terms: the O(N^2) sums come from one pimcb_virial_sums pass per configuration
+    double secondderivPotentialActionTau(int slice) override;   // src/action.cpp:776-787
+    double rDOTgradUterm1(int slice) override;                  // src/action.cpp:1446-1478
+    double rDOTgradUterm2(int slice) override;                  // src/action.cpp:1493-1575
+    double deltaDOTgradUterm1(int slice) override;              // src/action.cpp:1588-1652
+    double deltaDOTgradUterm2(int slice) override;              // src/action.cpp:1667-1784
+    double virKinCorr(int slice) override;                      // src/action.cpp:1786-1803
 private:
     std::array<double, 2> VFactor, gradVFactor;
     bool needF2;
     int f2Parity;
-    int lastSlice[3] = {1 << 30, 1 << 30, 1 << 30};   // last slice served per per-slice entry point (unhooked mode)
+    int lastSlice[4] = {1 << 30, 1 << 30, 1 << 30, 1 << 30};   // last slice served per per-slice entry point (unhooked mode)
     const B200Session::PairSums& sums();
     const B200Session::PairSums& sumsForSlice(int slice, int which);
+    const double* virial(int slice);        // the four sums of `slice`
     double externalV(int slice);
     double externalGradCorrection(int slice);
 };

@@ -21,10 +21,12 @@ AzizPotential::AzizPotential(int year, const Container* box) {
     tableLength = int(box->maxSep / dr);
     lookupV.resize(tableLength);
     lookupdVdr.resize(tableLength);
+    lookupd2Vdr2.resize(tableLength);
     double r = 0;
     for (int n = 0; n < tableLength; n++) {
         lookupV[n] = valueV(r);
         lookupdVdr[n] = valuedVdr(r);
+        lookupd2Vdr2[n] = valued2Vdr2(r);
         r += dr;
     }
     // tail correction (potential.cpp:1798-1806); the cutoff defaults to the box side (src/setup.cpp:1128-1130)
@@ -79,6 +81,37 @@ double AzizPotential::valuedVdr(double r) const {
     return (epsilon / rm) * (T1 + T2 + T3);
 }
 
+// second derivative of the damping function, potential.h:968-975
+double AzizPotential::d2F(double x) const {
+    if (x >= D) return 0.0;
+    const double ix = 1.0 / x;
+    const double u = D * ix - 1.0;
+    return 2.0 * D * ix * ix * ix * (2.0 * D * D * D * ix * ix * ix - 4.0 * D * D * ix * ix - D * ix + 2.0) * std::exp(-u * u);
+}
+
+double AzizPotential::valued2Vdr2(double r) const {
+    const double x = r / rm;
+    const double ab = alpha - 2.0 * beta * x;
+    const double T1 = A * (2 * beta + ab * ab) * std::exp(-alpha * x + beta * x * x);
+    if (x < EPS) return 0.0;
+    if (x < 0.01) return (epsilon / rm) * T1;                  // upstream's hard-core branch keeps the 1/rm prefactor
+    const double ix = 1.0 / x;
+    const double ix2 = ix * ix;
+    const double ix6 = ix2 * ix2 * ix2;
+    const double ix7 = ix6 * ix;
+    const double ix8 = ix6 * ix2;
+    const double ix9 = ix8 * ix;
+    const double ix10 = ix8 * ix2;
+    const double ix11 = ix10 * ix;
+    const double ix12 = ix11 * ix;
+    const double T2 = -(42.0 * C6 * ix8 + 72.0 * C8 * ix10 + 110.0 * C10 * ix12) * F(x);
+    const double T3 = 2.0 * (6.0 * C6 * ix7 + 8.0 * C8 * ix9 + 10.0 * C10 * ix11) * dF(x);
+    const double T4 = -(C6 * ix6 + C8 * ix8 + C10 * ix10) * d2F(x);
+    return (epsilon / (rm * rm)) * (T1 + T2 + T3 + T4);
+}
+
+double AzizPotential::grad2V(const dVec& r) { return direct(lookupd2Vdr2, extd2Vdr2, std::sqrt(dot(r, r))); }
+
 double AzizPotential::direct(const std::vector<double>& table, const std::array<double, 2>& ext, double r) const {
     const int k = int(r / dr);                 // potential.h:252
     if (k <= 0) return ext[0];
@@ -100,6 +133,8 @@ TableView AzizPotential::tableView() const {
     TableView v;
     v.V = lookupV.data();
     v.dVdr = lookupdVdr.data();
+    v.d2Vdr2 = lookupd2Vdr2.data();
+    v.extd2Vdr2 = extd2Vdr2;
     v.tableLength = tableLength;
     v.dr = dr;
     v.extV = extV;

@@ -14,15 +14,18 @@ public:
     dVec gradV(const dVec& r) override;        // potential.h:997-1003
     double valueV(double r) const;             // potential.cpp:1822-1842
     double valuedVdr(double r) const;          // potential.cpp:1849-1875
+    double valued2Vdr2(double r) const;        // potential.cpp:1881-1909
+    double grad2V(const dVec& r) override;     // potential.h:1010-1016 (direct lookup of d2V/dr2)
     TableView tableView() const;               // the accessor the B200 action needs (tables are protected upstream)
 private:
     double rm, A, epsilon, alpha, beta, D, C6, C8, C10;
     double dr = 0.0;
     int tableLength = 0;
-    std::vector<double> lookupV, lookupdVdr;
-    std::array<double, 2> extV{}, extdVdr{};
+    std::vector<double> lookupV, lookupdVdr, lookupd2Vdr2;
+    std::array<double, 2> extV{}, extdVdr{}, extd2Vdr2{};
     double F(double x) const;
     double dF(double x) const;
+    double d2F(double x) const;
     double direct(const std::vector<double>& table, const std::array<double, 2>& ext, double r) const;
 };
 

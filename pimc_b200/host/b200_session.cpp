@@ -63,6 +63,7 @@ void B200Session::setQVectors(const std::vector<dVec>& q) {
     check(pimcb_set_qvecs(ctx_, flat.data(), static_cast<int>(q.size())), "pimcb_set_qvecs");
     nq_ = q.size();
     have_sf_ = false;
+    have_es_ = have_cyl_ = false;
 }
 
 void B200Session::stageIfNeeded() {
@@ -93,6 +94,7 @@ void B200Session::stageIfNeeded() {
     }
     staged_ = true;
     have_sf_ = have_pair_ = false;
+    have_es_ = have_cyl_ = have_vir_ = false;
 }
 
 const std::vector<double>& B200Session::ssf() {
@@ -136,4 +138,83 @@ const B200Session::PairSums& B200Session::pairSums(double dSep, bool wantF2, int
         pair_has_f2_ = wantF2;
     }
     return pair_;
+}
+
+// ---- scattering variants ---------------------------------------------------------------------------------------------
+const std::vector<double>& B200Session::elastic() {
+    if (!have_es_) {
+        ssf();                                 // stages if needed and leaves S(q)/F(q,tau) of this configuration on the device
+        es_.resize(nq_);
+        check(pimcb_elastic(ctx_, es_.data()), "pimcb_elastic");
+        have_es_ = true;
+    }
+    return es_;
+}
+
+const std::vector<double>& B200Session::ssfCylinder(double maxR, int& numInside) {
+    if (!(have_cyl_ && cyl_maxR_ == maxR)) {
+        stageIfNeeded();
+        cyl_.resize(nq_);
+        check(pimcb_ssf_cyl(ctx_, maxR, cyl_.data(), &cyl_inside_), "pimcb_ssf_cyl");
+        cyl_maxR_ = maxR;
+        have_cyl_ = true;
+    }
+    numInside = cyl_inside_;
+    return cyl_;
+}
+
+// ---- virial slice sums -------------------------------------------------------------------------------------------------
+void B200Session::setPairTableD2(const double* d2Vdr2, int len, const double* extd2Vdr2) {
+    check(pimcb_set_pair_table_d2(ctx_, d2Vdr2, len, extd2Vdr2), "pimcb_set_pair_table_d2");
+    have_d2_ = true;
+    have_vir_ = false;
+}
+
+const std::vector<double>& B200Session::virialSums(int window, int t2Parity) {
+    if (!(have_vir_ && vir_window_ == window && vir_parity_ == t2Parity)) {
+        stageIfNeeded();
+        const auto ext = path_.get_beads_extents();
+        const int M = path_.numTimeSlices;
+        const int Next = static_cast<int>(ext[1]);
+        // deviation of every bead from the centroid of its world-line window, WITHOUT mirror image for the centroid and
+        // with putInBC on the result (src/action.cpp:1620-1647 == 1742-1769)
+        delta_.assign(static_cast<size_t>(M) * Next * NDIM, 0.0);
+        beadLocator bead1, beadNext, beadPrev, beadNextOld, beadPrevOld;
+        for (bead1[0] = 0; bead1[0] < M; bead1[0]++) {
+            const int numParticles = path_.numBeadsAtSlice(bead1[0]);
+            for (bead1[1] = 0; bead1[1] < numParticles; bead1[1]++) {
+                dVec runTotMore{}, runTotLess{}, COM{};
+                const dVec pos1 = path_(bead1);
+                beadNextOld = bead1;
+                beadPrevOld = bead1;
+                for (int gamma = 0; gamma < window; gamma++) {
+                    beadNext = path_.next(bead1, gamma);
+                    beadPrev = path_.prev(bead1, gamma);
+                    const dVec more = path_.getSeparation(beadNext, beadNextOld);
+                    const dVec less = path_.getSeparation(beadPrev, beadPrevOld);
+                    for (int d = 0; d < NDIM; ++d) {
+                        runTotMore[d] += more[d];
+                        runTotLess[d] += less[d];
+                        COM[d] += (pos1[d] + runTotMore[d]) + (pos1[d] + runTotLess[d]);
+                    }
+                    beadNextOld = beadNext;
+                    beadPrevOld = beadPrev;
+                }
+                dVec delta;
+                for (int d = 0; d < NDIM; ++d) {
+                    COM[d] /= (2.0 * window);
+                    delta[d] = pos1[d] - COM[d];
+                }
+                path_.boxPtr->putInBC(delta);
+                double* out = &delta_[(static_cast<size_t>(bead1[0]) * Next + bead1[1]) * NDIM];
+                for (int d = 0; d < NDIM; ++d) out[d] = delta[d];
+            }
+        }
+        vir_.assign(static_cast<size_t>(M) * 4, 0.0);
+        check(pimcb_virial_sums(ctx_, delta_.data(), have_d2_ ? t2Parity : -2, vir_.data()), "pimcb_virial_sums");
+        vir_window_ = window;
+        vir_parity_ = t2Parity;
+        have_vir_ = true;
+    }
+    return vir_;
 }

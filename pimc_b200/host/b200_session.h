@@ -43,7 +43,18 @@ public:
     void setPairTable(const double* V, const double* dVdr, int len, double dr, const double* extV, const double* extdVdr);
     struct PairSums { std::vector<double> vint, f2; std::vector<int> hist; };
     const PairSums& pairSums(double dSep, bool wantF2, int f2Parity);
-    void invalidate() { staged_ = false; have_sf_ = false; have_pair_ = false; }
+
+    // Scattering variants of the current configuration: the elastic-scattering increment [nq] and the
+    // cylinder S(q) raw sums [nq] + the number of slice-0 beads inside maxR.
+    const std::vector<double>& elastic();
+    const std::vector<double>& ssfCylinder(double maxR, int& numInside);
+
+    // Virial slice sums of the current configuration: [M][4] = {sum gV.r, sum (T gV).r, sum gV.delta,
+    // sum (T gV).delta}; delta (bead minus the centroid of its world-line window, src/action.cpp:1620-1647) is
+    // computed here from the path's links.  t2Parity as pimcb_virial_sums.
+    void setPairTableD2(const double* d2Vdr2, int len, const double* extd2Vdr2);
+    const std::vector<double>& virialSums(int window, int t2Parity);
+    void invalidate() { staged_ = false; have_sf_ = false; have_pair_ = false; have_es_ = have_cyl_ = have_vir_ = false; }
     void beginIfUnhooked() { if (!hooked_) invalidate(); }
     bool hooked() const { return hooked_; }
 
@@ -66,6 +77,10 @@ private:
     bool pair_has_f2_ = false;
     std::vector<double> ssf_, isf_;
     PairSums pair_;
+    bool have_es_ = false, have_cyl_ = false, have_vir_ = false, have_d2_ = false;
+    double cyl_maxR_ = 0.0;
+    int cyl_inside_ = 0, vir_window_ = 0, vir_parity_ = 0;
+    std::vector<double> es_, cyl_, vir_, delta_;
     friend struct SessionRegistry;
 };
 

@@ -216,3 +216,43 @@ void EstimatorBase::getQVectors(std::vector<dVec>& qValues) {
         }
     }
 }
+
+// src/estimator.cpp:762-837: wave-vectors grouped by magnitude.  Magnitudes 0, dq, 2 dq, ... (accumulated) up to
+// qMax + EPS; the null vector alone in shell 0; every other shell starts with the vector along the last axis and, in
+// three dimensions, continues over the positive octant in steps dtheta = pi/48 (geometry "sphere"; "line" uses
+// dtheta = pi, i.e. no further vectors), dphi = dtheta / sin(theta).
+std::vector<std::vector<dVec>> EstimatorBase::getQVectors2(double dq, double qMax, int& numq, std::string qGeometry) {
+    numq = 0;
+    std::vector<std::vector<dVec>> shells;
+    if ((qGeometry != "line") && (qGeometry != "sphere")) {
+        std::cerr << "\nERROR: A valid geometry wasn't chosen for q-space." << std::endl
+                  << "Action: choose \"line\" or \"sphere\"" << std::endl;
+        exit(1);
+    }
+    for (double cq = 0.0; cq <= qMax + EPS; cq += dq) {
+        std::vector<dVec> shell;
+        dVec axis{};
+        if (!(std::abs(cq) < EPS)) axis[NDIM - 1] = cq;
+        shell.push_back(axis);
+#if NDIM == 3
+        if (!(std::abs(cq) < EPS)) {
+            const int numTheta = 24;
+            const double dtheta = (qGeometry == "line") ? M_PI : 0.5 * M_PI / numTheta;
+            for (double theta = dtheta; theta <= 0.5 * M_PI + EPS; theta += dtheta) {
+                const double dphi = dtheta / sin(theta);
+                for (double phi = 0.0; phi <= 0.5 * M_PI + EPS; phi += dphi) {
+                    dVec qd;
+                    qd[0] = cq * sin(theta) * cos(phi);
+                    qd[1] = cq * sin(theta) * sin(phi);
+                    qd[2] = cq * cos(theta);
+                    shell.push_back(qd);
+                }
+            }
+        }
+#endif
+        numq += static_cast<int>(shell.size());
+        shells.push_back(shell);
+    }
+    std::cout << "numQ = " << numq << std::endl;
+    return shells;
+}

@@ -55,6 +55,7 @@ protected:
     void initialize(int);
     void initialize(std::vector<std::string> estLabel);
     void getQVectors(std::vector<dVec>&);
+    std::vector<std::vector<dVec>> getQVectors2(double, double, int&, std::string);   // include/estimator.h:132
 };
 
 // src/estimator.cpp:31-34

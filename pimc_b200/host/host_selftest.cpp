@@ -9,6 +9,21 @@
 class ProbeEstimator : public EstimatorBase {
 public:
     ProbeEstimator(const Path& p, ActionBase* a, const MTRand& r, double maxR) : EstimatorBase(p, a, r, maxR, 1, "probe") {}
+    // getQVectors2 report: one "shell=" line per magnitude, vectors separated by ';'
+    void shells(double dq, double qMax, const std::string& geometry) {
+        int numq = 0;
+        const auto q = getQVectors2(dq, qMax, numq, geometry);
+        std::cout.precision(17);
+        std::cout << "numq2=" << numq << std::endl;
+        for (const auto& sh : q) {
+            std::cout << "shell=";
+            for (size_t k = 0; k < sh.size(); ++k) {
+                for (int d = 0; d < NDIM; ++d) std::cout << sh[k][d] << (d + 1 < NDIM ? " " : "");
+                if (k + 1 < sh.size()) std::cout << ";";
+            }
+            std::cout << std::endl;
+        }
+    }
     void run() {
         std::vector<dVec> q;
         getQVectors(q);
@@ -49,6 +64,16 @@ static int stateReport(const char* file, int N, double density) {
 
 int main(int argc, char** argv) {
     if (argc == 5 && std::string(argv[1]) == "--state") return stateReport(argv[2], std::atoi(argv[3]), std::atof(argv[4]));
+    if (argc == 7 && std::string(argv[1]) == "--q2") {          // --q2 N density dq qMax geometry
+        const int N2 = std::atoi(argv[2]);
+        Prism box2(std::atof(argv[3]), N2);
+        constants()->numTimeSlices_ = 4;
+        constants()->initialNumParticles_ = N2;
+        Path path2(&box2, 4, N2, N2);
+        MTRand r2;
+        ProbeEstimator(path2, nullptr, r2, 0.0).shells(std::atof(argv[4]), std::atof(argv[5]), argv[6]);
+        return 0;
+    }
     if (argc < 5) { std::cerr << "usage: host_selftest N density type \"wavevector\"" << std::endl; return 2; }
     const int N = std::atoi(argv[1]);
     Prism box(std::atof(argv[2]), N);
@@ -71,6 +96,10 @@ int main(int argc, char** argv) {
     double cs = 0.0;
     for (int k = 0; k < t.tableLength; k += 997) cs += t.V[k] * 1e-3 + t.dVdr[k] * 1e-6;
     std::cout << "checksum=" << cs << std::endl;
+    std::cout << "d2V1e6=" << t.d2Vdr2[1000000] << std::endl;
+    double cs2 = 0.0;
+    for (int k = 0; k < t.tableLength; k += 997) cs2 += t.d2Vdr2[k] * 1e-9;
+    std::cout << "checksum2=" << cs2 << std::endl;
 #endif
     return 0;
 }

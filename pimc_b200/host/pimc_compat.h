@@ -117,6 +117,10 @@ public:
     double rc() const { return rc_; }                          // potential cutoff; defaults to side[NDIM-1] (src/setup.cpp:1128-1130)
     double fourLambdaTauInv() const { return 0.25 / (lambda_ * tau_); }   // include/constants.h:82
     uint32 binSize() const { return binSize_; }
+    int virialWindow() const { return virialWindow_; }         // --virial_window, default 5 (src/setup.cpp:450)
+    double V() const { return V_; }                            // cell volume (include/constants.h:70)
+    int virialWindow_ = 5;
+    double V_ = 0.0;
     double mu_ = 0.0, rc_ = 0.0;
     uint32 binSize_ = 100;
     std::string wavevector() const { return wavevector_; }
@@ -147,9 +151,25 @@ public:
             for (int p = 0; p < extent; ++p)
                 nextLink_[static_cast<size_t>(s) * extent + p] =
                     p < numParticles ? beadLocator{(s + 1) % numTimeSlices, p} : beadLocator{XXX, XXX};
+        buildPrev();
     }
-    void setLinks(const std::vector<beadLocator>& nextLink) { if (nextLink.size() == nextLink_.size()) nextLink_ = nextLink; }
+    void setLinks(const std::vector<beadLocator>& nextLink) {
+        if (nextLink.size() != nextLink_.size()) return;
+        nextLink_ = nextLink;
+        buildPrev();
+    }
     const beadLocator& next(const beadLocator& b) const { return nextLink_[static_cast<size_t>(b[0]) * next_ + b[1]]; }   // path.h:92-99
+    const beadLocator& prev(const beadLocator& b) const { return prevLink_[static_cast<size_t>(b[0]) * next_ + b[1]]; }   // path.h:101-107
+    beadLocator next(const beadLocator& b, int numLinks) const {                                 // path.h:233-240
+        beadLocator bI = b;
+        for (int m = 0; m < numLinks; m++) bI = next(bI);
+        return bI;
+    }
+    beadLocator prev(const beadLocator& b, int numLinks) const {                                 // path.h:256-263
+        beadLocator bI = b;
+        for (int m = 0; m < numLinks; m++) bI = prev(bI);
+        return bI;
+    }
     dVec getVelocity(const beadLocator& b) const {                                              // path.h:189-203
         dVec vel;
         const beadLocator& n = next(b);
@@ -178,7 +198,15 @@ public:
 private:
     int n_, next_;
     std::vector<dVec> beads_;       // row-major [slice][ptcl] AoS, as DynamicArray<dVec,2> (path.h:164)
-    std::vector<beadLocator> nextLink_;
+    std::vector<beadLocator> nextLink_, prevLink_;
+    void buildPrev() {                  // prevLink is the inverse map of nextLink on a closed configuration
+        prevLink_.assign(nextLink_.size(), beadLocator{XXX, XXX});
+        for (int s = 0; s < numTimeSlices; ++s)
+            for (int p = 0; p < next_; ++p) {
+                const beadLocator& n = nextLink_[static_cast<size_t>(s) * next_ + p];
+                if (n[0] != XXX && n[1] != XXX) prevLink_[static_cast<size_t>(n[0]) * next_ + n[1]] = beadLocator{s, p};
+            }
+    }
 };
 
 class MTRand {};                    // the path never draws random numbers
@@ -203,9 +231,10 @@ class FreePotential : public PotentialBase {};
 struct TableView {
     const double* V = nullptr;
     const double* dVdr = nullptr;
+    const double* d2Vdr2 = nullptr;
     int tableLength = 0;
     double dr = 0.0;
-    std::array<double, 2> extV{}, extdVdr{};
+    std::array<double, 2> extV{}, extdVdr{}, extd2Vdr2{};
 };
 
 // ---- action (include/action.h:30-254; the members the measurement path uses) -----------------------------------
@@ -222,6 +251,12 @@ public:
     virtual std::array<double, 2> potential(int) { return {0.0, 0.0}; }
     virtual double derivPotentialActionTau(int) { return 0.0; }
     virtual double derivPotentialActionLambda(int) { return 0.0; }
+    virtual double secondderivPotentialActionTau(int) { return 0.0; }     // include/action.h:63
+    virtual double rDOTgradUterm1(int) { return 0.0; }                    // include/action.h:75-85
+    virtual double rDOTgradUterm2(int) { return 0.0; }
+    virtual double deltaDOTgradUterm1(int) { return 0.0; }
+    virtual double deltaDOTgradUterm2(int) { return 0.0; }
+    virtual double virKinCorr(int) { return 0.0; }
     const int period;
     DynamicArray<int, 1> sepHist;   // action.h:114
     PotentialBase* externalPtr;     // public upstream as well (include/action.h:108-109)

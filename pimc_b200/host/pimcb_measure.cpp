@@ -20,6 +20,8 @@
 #include "aziz.h"
 #include "energy_estimator.h"
 #include "estimator_b200.h"
+#include "scattering_b200.h"
+#include "virial_estimator.h"
 #include "state_file.h"
 
 static const char* arg(int argc, char** argv, const char* key, const char* def) {
@@ -81,6 +83,7 @@ int main(int argc, char** argv) {
     communicate()->init(arg(argc, argv, "--outdir", "OUTPUT"), "ce", c->id_);
 
     Prism box(density, N);
+    c->V_ = box.volume;
     Path path(&box, M, N, extent);
     MTRand random;
     const bool wantPotential = flag(argc, argv, "--potential");
@@ -102,12 +105,25 @@ int main(int argc, char** argv) {
     const bool wantEnergy = flag(argc, argv, "--energy");          // thermodynamic energy estimator on the device pair sums
     if (wantEnergy && !wantPotential) { std::cerr << "--energy needs --potential (the action object)" << std::endl; return 2; }
     if (wantEnergy) names.push_back("energy");
+    // --virial [--virial_window W]: centroid-virial energy estimator (19 more scalar columns of ce-estimator-<id>.dat)
+    const bool wantVirial = flag(argc, argv, "--virial");
+    if (wantVirial && !wantPotential) { std::cerr << "--virial needs --potential (the action object)" << std::endl; return 2; }
+    if (wantVirial) names.push_back("virial");
+    c->virialWindow_ = std::atoi(arg(argc, argv, "--virial_window", "5"));
+    if (c->virialWindow_ == 0) c->virialWindow_ = M;                   // src/setup.cpp:1775-1777
+    // --elastic: elastic scattering (ce-es-<id>.dat); --cylinder R: cylinder S(q) of the beads within R of the z axis
+    // (ce-cyl_ssf-<id>.dat).  The cylinder estimator brings its own q-set, so it gets a session of its own q-vectors:
+    // combine it with the other scattering estimators only in separate runs.
+    if (flag(argc, argv, "--elastic")) names.push_back("elastic scattering");
+    const double maxR = std::atof(arg(argc, argv, "--cylinder", "0"));
+    if (maxR > 0.0) names = {"cylinder static structure factor"};
     c->binSize_ = static_cast<uint32>(binSize);
+    const char* lastScalar = wantVirial ? "virial" : "energy";
     for (const char* name : names) {
-        EstimatorBase* e = estimatorFactory()->Create(name, path, action.get(), random, 0.0);
+        EstimatorBase* e = estimatorFactory()->Create(name, path, action.get(), random, maxR);
         if (!e) { std::cerr << "estimator not registered: " << name << std::endl; return 1; }
         estimators.emplace_back(e);
-        if (std::string(name) == "energy") e->addEndLine();            // the only scalar estimator here closes the row (setup.cpp:1364-1366)
+        if (std::string(name) == lastScalar) e->addEndLine();          // the last scalar estimator closes the row (setup.cpp:1364-1366)
         e->prepare();
     }
     std::fstream* potOut = nullptr;

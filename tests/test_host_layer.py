@@ -54,8 +54,26 @@ def test_qvectors_match_oracle_bitwise(host_bins, orc, ndim, N, rho, qtype, text
 
 def test_factory_names_and_formatting(host_bins, orc):
     rep = selftest(host_bins, 3, 16, 0.02198, "int", "1 0 0")
-    assert sorted(rep["registered"]) == ["energy", "intermediate scattering function", "static structure factor"]
+    assert sorted(rep["registered"]) == ["cylinder static structure factor", "elastic scattering", "energy",
+                                         "intermediate scattering function", "static structure factor", "virial"]
     assert rep["row"][0] == orc.format_row([30864.19725, -6.25e-4], [1.0, 1.0], 1)
+
+
+@pytest.mark.parametrize("ndim,geometry,qmax", [(3, "line", 4.0), (3, "sphere", 0.8), (2, "line", 2.0)])
+def test_qvectors2_match_oracle_bitwise(host_bins, orc, ndim, geometry, qmax):
+    """getQVectors2 (magnitude shells of the cylinder S(q) estimator): C++ mirror vs the oracle restatement."""
+    N, rho = (16, 0.02198) if ndim == 3 else (128, 0.0432)
+    L = (N / rho) ** (1.0 / ndim)
+    dq = 2.0 * math.pi / L
+    out = subprocess.run([os.path.join(host_bins, f"pimcb_host_selftest{ndim}d"), "--q2", str(N), repr(rho), repr(dq), repr(qmax), geometry],
+                         check=True, capture_output=True, text=True).stdout
+    shells = [l.split("=", 1)[1] for l in out.splitlines() if l.startswith("shell=")]
+    ref = orc.qvectors2(ndim, dq, qmax, geometry)
+    assert len(shells) == len(ref)
+    for line, r in zip(shells, ref):
+        got = np.array([[float(x) for x in v.split()] for v in line.split(";")])
+        assert np.array_equal(got, r)
+    assert f"numq2={sum(len(r) for r in ref)}" in out
 
 
 def test_aziz_table_matches_oracle(host_bins, orc):
@@ -67,6 +85,9 @@ def test_aziz_table_matches_oracle(host_bins, orc):
     assert float(rep["dV1e6"][0]) == pytest.approx(dV[1000000], rel=1e-15)
     cs = float(np.sum(V[::997] * 1e-3 + dV[::997] * 1e-6))
     assert float(rep["checksum"][0]) == pytest.approx(cs, rel=1e-12)
+    _, _, d2V, _ = orc.aziz_table(orc.max_sep(side), second=True)
+    assert float(rep["d2V1e6"][0]) == pytest.approx(d2V[1000000], rel=1e-14)
+    assert float(rep["checksum2"][0]) == pytest.approx(float(np.sum(d2V[::997] * 1e-9)), rel=1e-12)
 
 
 def read_dat(path):
@@ -255,3 +276,87 @@ def test_plugin_api_drop_in_files(host_bins, orc, nthreads, tmp_path):
         assert vals[0] == pytest.approx(U, rel=1e-10)
         np.testing.assert_allclose(vals[1:1 + s.M], cv, rtol=1e-10)
         np.testing.assert_allclose(vals[1 + s.M + 1::2], cf[1::2], rtol=1e-10)      # gsf: odd slices carry |F|^2
+
+
+@pytest.mark.gpu
+def test_virial_and_elastic_estimators_through_the_plugin_api(host_bins, orc, nthreads, tmp_path):
+    """`virial` (VirialEnergyEstimator on LocalActionB200's device sums) and `elastic scattering` created by name
+    through the factory; ce-estimator rows (energy + virial columns in one file, as upstream combines the scalar
+    estimators) and ce-es rows against the oracle chain.  Saved states with permuted world lines exercise the links."""
+    from oracle import statefile
+    s = synth.Shape("vs", 3, 12, 20, 2.0, 0.02198, 0)
+    W, nq, B, window = s.N + 2, 7, 3, 4
+    batch = synth.gen_batch(s, B, first=55, pad=W - s.N)
+    rng = np.random.default_rng(3)
+    files, links = [], []
+    for b in range(B):
+        on = np.zeros((s.M, W), dtype=np.uint32)
+        on[:, :s.N] = 1
+        nxt = np.full((s.M, W, 2), -1, dtype=np.int32)
+        for t in range(s.M):
+            nxt[t, :s.N, 0] = (t + 1) % s.M
+            nxt[t, :s.N, 1] = np.arange(s.N)
+        nxt[s.M - 1, :s.N, 1] = rng.permutation(s.N)
+        f = tmp_path / f"ce-state-{b}.dat"
+        statefile.write_state(f, batch[b], on, next_link=nxt)
+        files.append(str(f))
+        links.append(nxt)
+    text = synth.int_wavevector_text(nq, 3)
+    out = tmp_path / "OUTPUT"
+    subprocess.run([os.path.join(host_bins, "pimcb_measure3d"), "-n", repr(s.rho), "-T", repr(s.T), "--wavevector_type", "int",
+                    "--wavevector", text, "--state", ",".join(files), "--bin_size", "100", "--outdir", str(out), "--id", "v",
+                    "--potential", "--energy", "--virial", "--virial_window", str(window), "--elastic"], check=True)
+    q = orc.qvectors("int", text, s.side)
+    V, dV, d2V, dr = orc.aziz_table(orc.max_sep(s.side), second=True)
+    dSep = 0.5 * math.sqrt(3) * s.side[2] / 50
+    tail = orc.aziz_tail(s.side[2])
+    VF, GF = [2 / 3, 4 / 3], [0.0, 2 / 9]
+    en, ve, es = [], [], []
+    for b in range(B):
+        p = statefile.read_state(files[b], side=s.side)["beads"]
+        cv, cf, _ = orc.pair_sums(s.side, p, s.N, V, dV, dr, dSep, nthreads=nthreads)
+        cf[0::2] = 0.0
+        vir = orc.virial_sums(s.side, p, s.N, window, dV, d2V, dr, t2_parity=1, next_links=links[b], nthreads=nthreads)
+        en.append(orc.energy(s.side, p, s.N, cv, cf, VF, GF, 2, s.tau, synth.LAMBDA_HE4, tail, next_links=links[b]))
+        ve.append(orc.virial_energy(s.side, p, s.N, window, vir, cv, cf, VF, GF, s.tau, synth.LAMBDA_HE4, tail, next_links=links[b]))
+        es.append(orc.elastic(p, s.N, q, nthreads=nthreads))
+    head, rows = read_dat(out / "ce-estimator-v.dat")
+    assert len(rows) == 1 and len(rows[0]) == 16 * (9 + 19)
+    assert head[0].split() == ["#", "K", "V", "V_ext", "V_int", "E", "E_mu", "K/N", "V/N", "E/N"] + list(orc.VIRIAL_COLUMNS) or \
+        head[0].replace("#", " ").split() == ["K", "V", "V_ext", "V_int", "E", "E_mu", "K/N", "V/N", "E/N"] + list(orc.VIRIAL_COLUMNS)
+    got = np.array([float(rows[0][16 * k:16 * k + 16]) for k in range(28)])
+    ref = np.concatenate([np.mean(en, axis=0), np.mean(ve, axis=0)])
+    np.testing.assert_allclose(got, ref, rtol=2e-8, atol=2e-8 * np.max(np.abs(ref)))
+    assert got[9 + 15] == 0.0 and abs(got[9 + 4]) > 1.0                      # CvCov2 column empty (upstream key quirk); E_cv finite
+    head, rows = read_dat(out / "ce-es-v.dat")
+    assert head[0] == "#%15d" % 0 + "".join("%16d" % n for n in range(1, nq))
+    got = np.array([float(rows[0][16 * k:16 * k + 16]) for k in range(nq)])
+    np.testing.assert_allclose(got, 0.5 * np.mean(es, axis=0), rtol=2e-8)       # norm 0.5 (src/estimator.cpp:4161)
+
+
+@pytest.mark.gpu
+def test_cylinder_ssf_estimator_through_the_plugin_api(host_bins, orc, tmp_path):
+    """`cylinder static structure factor` by name: magnitude header, 1/M/shell-size normalisation, division by the number
+    of slice-0 particles inside maxR."""
+    s = synth.Shape("cy", 3, 24, 10, 2.0, 0.02198, 0)
+    B, maxR = 4, 3.5
+    batch = synth.gen_batch(s, B, first=33, pad=0)
+    cfg = tmp_path / "beads.bin"
+    batch.tofile(cfg)
+    out = tmp_path / "OUTPUT"
+    subprocess.run([os.path.join(host_bins, "pimcb_measure3d"), "-N", str(s.N), "-n", repr(s.rho), "-T", repr(s.T), "-P", str(s.M),
+                    "--configs", str(cfg), "--bin_size", "100", "--outdir", str(out), "--id", "c", "--cylinder", repr(maxR)], check=True)
+    shells = orc.qvectors2(3, 2.0 * math.pi / s.side[2], 4.0, "line")
+    q = np.vstack(shells)
+    acc, n_acc = np.zeros(len(q)), 0
+    for b in range(B):
+        raw, n_in = orc.ssf_cyl(s.side, batch[b], s.N, q, maxR)
+        if n_in > 0:
+            acc += raw / n_in
+            n_acc += 1
+    assert n_acc > 0
+    head, rows = read_dat(out / "ce-cyl_ssf-c.dat")
+    mags = [float(head[0][1:16])] + [float(head[0][16 * k:16 * k + 16]) for k in range(1, len(q))]
+    np.testing.assert_allclose(mags, np.linalg.norm(q, axis=1), rtol=1e-6, atol=1e-12)
+    got = np.array([float(rows[0][16 * k:16 * k + 16]) for k in range(len(q))])
+    np.testing.assert_allclose(got, acc / (s.M * n_acc), rtol=2e-8)
