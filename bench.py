@@ -45,6 +45,9 @@ def parse_args():
     ap.add_argument("--shard", default="config", choices=["config", "q"],
                     help="multi-GPU axis: independent walker configurations (weak scaling, one reduce) or q-vectors "
                          "(strong scaling, every rank sees every configuration, one all-gather)")
+    ap.add_argument("--collective", default="torch", choices=["torch", "lib"],
+                    help="who issues the one collective per bin: torch.distributed on the library's device buffer, or the "
+                         "library's own NCCL entry points (pimcb_reduce_bins / pimcb_gather_bins_q)")
     ap.add_argument("--unique", type=int, default=16, help="distinct synthetic configurations generated per slot")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -271,6 +274,11 @@ def run_ours(args, shape, q):
     if args.corr_mode >= 0:
         ctx.set_corr_mode(args.corr_mode)
     nq = len(q)
+    lib_coll = world > 1 and args.collective == "lib"
+    if lib_coll:
+        uid = [api.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)                    # plumbing: ship the 128-byte NCCL id to the ranks
+        ctx.comm_init(world, rank, uid[0])
 
     # synthetic batches: `unique` distinct configurations per slot, cycled to B, different seeds per rank and slot
     nslots = ctx.num_slots()
@@ -298,6 +306,13 @@ def run_ours(args, shape, q):
 
     def bin_collective():
         # the one collective of the path, once per bin (not per step), on the library's own device buffer
+        if lib_coll:
+            if args.shard == "config":
+                ctx.reduce_bins(0)
+            else:
+                g_ssf, _ = ctx.gather_bins_q(multi.shard_sizes(len(q_all), world))
+                assert g_ssf.shape == (len(q_all),)
+            return
         bins = multi.bins_tensor(ctx, torch.device("cuda", local))
         with torch.cuda.stream(ext):
             if args.shard == "config":
@@ -342,7 +357,8 @@ def run_ours(args, shape, q):
     evals_per_step = world * B if args.shard == "config" else B    # q-sharding: all ranks work on the same B walkers
     value = evals_per_step * K / (ms_total * 1e-3)
     _, _, n_acc = ctx.read_bins()
-    assert n_acc == B * K, (n_acc, B, K)
+    expect_acc = B * K * (world if (lib_coll and args.shard == "config" and rank == 0) else 1)   # the library's reduce sums the counts too
+    assert n_acc == expect_acc, (n_acc, expect_acc)
     if args.profile != "all":                      # untimed-region pass with every kernel bracketed: corr / bins durations
         ctx.set_profiling(True)
         for k in range(max(10, min(K, 50))):
@@ -502,6 +518,27 @@ def run_ours(args, shape, q):
                 "bound": "L2/HBM gather: 8-byte table reads move 32-byte sectors; the 106 MB of tables exceed what one L2 "
                          "partition keeps, ncu shows 6.3 GB of DRAM reads per launch (profiles/traffic.json)"}
 
+    # ---- secondary: virial slice sums (rDOTgradU / deltaDOTgradU, gsf: T-matrix terms on odd slices) ---------------
+    if pair is not None:
+        d2Vt = np.gradient(dVt, drt)                   # timing only: central differences of the dV/dr table
+        ctx.set_pair_table_d2(d2Vt)
+        ctx.select_slot(0)
+        delta = 0.01 * pinned[0].array                 # any per-bead vectors in the beads' AoS shape
+        ctx.set_profiling(True)
+        ctx.virial_sums(delta, t2_parity=1)
+        ctx.kernel_times(reset=True)
+        nvir = 3
+        for k in range(nvir):
+            ctx.virial_sums(delta, t2_parity=1)
+        vms, vn = ctx.kernel_times(reset=True)["virial"]
+        ctx.set_profiling(False)
+        v_s = vms * 1e-3 / max(1, vn)
+        vg = B * shape.N * (shape.N - 1) * (shape.M + shape.M // 2)          # dV/dr on every slice, d2V/dr2 on odd ones
+        pair["virial_sums"] = {"metric": "virial slice sums/s (4 sums per slice; gsf action, window deltas from the host)",
+                               "value": B / v_s, "unit": "configurations/s", "avg_launch_ms": v_s * 1e3, "launches_timed": vn,
+                               "gathers_per_launch": vg, "gather_rate_g_per_s": vg / v_s / 1e9,
+                               "bound": "L2/HBM gather (same tables as the pair kernel + d2V/dr2)"}
+
     # ---- secondary: direct minimum-image S(q) for non-commensurate (`float`) wave-vectors --------
     direct = None
     if not args.no_pair:
@@ -541,6 +578,8 @@ def run_ours(args, shape, q):
                                    else f"q-vector sharding x{world} ({nq} of {len(q_all)} q per GPU), one NCCL all-gather of the bin"),
                    "l2": f"{use_slots} resident batches rotated ({footprint_mb:.0f} MB > 126 MB L2)",
                    "rho_mode": args.rho_mode, "corr_mode": args.corr_mode,
+                   "collective": ("none (one GPU)" if world == 1 else
+                                  ("library NCCL (pimcb_reduce_bins / pimcb_gather_bins_q)" if lib_coll else "torch.distributed NCCL on the library's bin")),
                    "host_binding": (f"rank bound to {len(numa_cpus)} GPU-local CPUs (NVML affinity)" if numa_cpus else "none")},
         "clocks": clocks, "e2e": e2e, "latency": latency, "gpu_launches": int(launches), "roofline": roofline, "pair_sums": pair, "ssf_direct": direct,
     }

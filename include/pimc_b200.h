@@ -168,6 +168,27 @@ int pimcb_set_pair_table_d2(pimcb_ctx* ctx, const double* d2Vdr2, int len, const
  * The caller applies VFactor*tau and 2*gradVFactor*tau^3*lambda. */
 int pimcb_virial_sums(pimcb_ctx* ctx, const double* delta_aos, int t2_parity, double* out /*[B][M][4]*/);
 
+/* ---- multi-GPU exchange step ------------------------------------------------------
+ * One process (and one ctx) per GPU.  The path has no collective inside a measurement; per OUTPUT BIN there is one
+ * NCCL reduce over NVLink (walker-configuration sharding: every rank accumulated its own configurations) or one
+ * all-gather (q-vector sharding: every rank owns a contiguous range of output columns).  NCCL is resolved with dlopen
+ * when the first of these is called (PIMCB_NCCL_LIB, else libnccl.so.2), so single-GPU users need no NCCL at all.
+ * The reference has no multi-GPU path; these replace nothing upstream.
+ *   pimcb_comm_unique_id: 128-byte ncclUniqueId created on one rank; the caller ships it to the others (MPI, a file,
+ *     a torch store...).
+ *   pimcb_comm_init / pimcb_comm_destroy: collective over all `nranks` ctxs.
+ *   pimcb_reduce_bins: sums every rank's device bin (S(q) and F(q,tau) accumulators, layout of pimcb_read_bins) and
+ *     its configuration count onto `root`, in place, on the ctx stream; afterwards pimcb_read_bins on the root
+ *     returns the global bin and count (*num_total, may be NULL, gets the count on the root and 0 elsewhere).  The
+ *     other ranks' bins are unchanged: call pimcb_reset_bins on every rank to start the next bin.
+ *   pimcb_gather_bins_q: nq_per_rank[nranks] = wave-vectors held by each rank (rank order = q order); every rank
+ *     receives the concatenated bins ssf[sum nq] and isf[sum nq][M] (host pointers, either may be NULL). */
+int pimcb_comm_unique_id(void* id_out /*[128]*/);
+int pimcb_comm_init(pimcb_ctx* ctx, int nranks, int rank, const void* unique_id /*[128]*/);
+int pimcb_comm_destroy(pimcb_ctx* ctx);
+int pimcb_reduce_bins(pimcb_ctx* ctx, int root, long* num_total);
+int pimcb_gather_bins_q(pimcb_ctx* ctx, const int* nq_per_rank, double* ssf, double* isf);
+
 /* ---- measurement helpers (bench) --------------------------------------------------------------------
  * Sustained FP64 DFMA throughput of the device in TFLOP/s (register-resident FMA chains on every SM,
  * timed with CUDA events).  MEASURED_PEAKS.json carries no FP64 figure. */

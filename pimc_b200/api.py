@@ -27,7 +27,8 @@ SYMBOLS = [
     "pimcb_read_bins", "pimcb_bins_device_ptr", "pimcb_sync", "pimcb_stream", "pimcb_set_pair_table",
     "pimcb_pair_sums", "pimcb_measure_fp64_peak", "pimcb_set_profiling", "pimcb_set_profiling_stride", "pimcb_kernel_times",
     "pimcb_launch_count", "pimcb_rho_plan_info", "pimcb_elastic", "pimcb_ssf_cyl", "pimcb_set_pair_table_d2",
-    "pimcb_virial_sums",
+    "pimcb_virial_sums", "pimcb_comm_unique_id", "pimcb_comm_init", "pimcb_comm_destroy", "pimcb_reduce_bins",
+    "pimcb_gather_bins_q",
 ]
 
 
@@ -90,6 +91,11 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.pimcb_ssf_cyl.argtypes = [vp, C.c_double, _dp, _ip]
     lib.pimcb_set_pair_table_d2.argtypes = [vp, _dp, C.c_int, _dp]
     lib.pimcb_virial_sums.argtypes = [vp, _dp, C.c_int, _dp]
+    lib.pimcb_comm_unique_id.argtypes = [C.c_char_p]
+    lib.pimcb_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+    lib.pimcb_comm_destroy.argtypes = [vp]
+    lib.pimcb_reduce_bins.argtypes = [vp, C.c_int, C.POINTER(C.c_long)]
+    lib.pimcb_gather_bins_q.argtypes = [vp, _ip, _dp, _dp]
     if path == _build.LIB:
         _lib = lib
     return lib
@@ -325,6 +331,36 @@ class Context:
         out = np.zeros((B, M, 4))
         self._chk(self.lib.pimcb_virial_sums(self._h, _ptr(d), t2_parity, _ptr(out)))
         return out
+
+    # -- multi-GPU exchange step (NCCL inside the library) ---------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        rc = lib.pimcb_comm_unique_id(buf)
+        if rc:
+            raise PimcbError(f"pimcb error {rc}: {lib.pimcb_last_error().decode()}")
+        return buf.raw
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        assert len(unique_id) == 128
+        self._chk(self.lib.pimcb_comm_init(self._h, nranks, rank, unique_id))
+
+    def comm_destroy(self):
+        self._chk(self.lib.pimcb_comm_destroy(self._h))
+
+    def reduce_bins(self, root: int = 0) -> int:
+        n = C.c_long(0)
+        self._chk(self.lib.pimcb_reduce_bins(self._h, root, C.byref(n)))
+        return n.value
+
+    def gather_bins_q(self, nq_per_rank):
+        _, M, _ = self.shape
+        sizes = np.ascontiguousarray(nq_per_rank, dtype=np.int32)
+        tot = int(sizes.sum())
+        ssf, isf = np.zeros(tot), np.zeros((tot, M))
+        self._chk(self.lib.pimcb_gather_bins_q(self._h, sizes.ctypes.data_as(_ip), _ptr(ssf), _ptr(isf)))
+        return ssf, isf
 
     # -- measurement helpers ----------------------------------------------------------------------------
     def fp64_peak_tflops(self, seconds=0.5) -> float:

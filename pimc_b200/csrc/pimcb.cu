@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <array>
 #include <cstring>
+#include <dlfcn.h>
 #include <new>
 #include <string>
 #include <vector>
@@ -152,10 +153,61 @@ struct pimcb_ctx {
     DevBuf d_var, d_inside, d_d2V, d_delta_aos, d_delta, d_vir;
     bool have_d2V = false;
     double extd2V[2] = {0, 0};
+    // multi-GPU: NCCL communicator (library resolved with dlopen at pimcb_comm_init; nothing links against NCCL)
+    void* nccl_comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
+    DevBuf d_gather, d_count;
     DevBuf d_sched;                        // ticket counter + retire counter of the persistent-warp rho kernel (self re-arming)
 };
 
 namespace {
+
+// ---- NCCL, resolved at run time ---------------------------------------------------------------------------------------
+// Only the handful of entry points the path's single exchange step needs (one reduce / all-gather per bin).
+// Prototypes follow nccl.h (2.x ABI): ncclUniqueId is 128 opaque bytes passed by value, ncclDouble = 8, ncclSum = 0,
+// ncclInt64 = 4.
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl() {
+    if (g_nccl.handle) return 0;
+    const char* names[] = {std::getenv("PIMCB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names)
+        if (n && *n && (h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!h) return fail(PIMCB_ESTATE, "NCCL library not found (set PIMCB_NCCL_LIB): %s", dlerror());
+    NcclApi a;
+    a.handle = h;
+#define NCCL_SYM(field, name) *reinterpret_cast<void**>(&a.field) = dlsym(h, name); \
+    if (!a.field) return fail(PIMCB_ESTATE, "NCCL symbol %s missing", name)
+    NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+    NCCL_SYM(CommInitRank, "ncclCommInitRank");
+    NCCL_SYM(CommDestroy, "ncclCommDestroy");
+    NCCL_SYM(Reduce, "ncclReduce");
+    NCCL_SYM(AllGather, "ncclAllGather");
+    NCCL_SYM(GroupStart, "ncclGroupStart");
+    NCCL_SYM(GroupEnd, "ncclGroupEnd");
+    NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef NCCL_SYM
+    g_nccl = a;
+    return 0;
+}
+#define NCCLCHK(call)                                                                                   \
+    do {                                                                                                \
+        int r_ = (call);                                                                                \
+        if (r_ != 0) return fail(PIMCB_ECUDA, "%s failed: %s", #call, g_nccl.GetErrorString(r_));       \
+    } while (0)
 
 cudaEvent_t pool_event(pimcb_ctx* c) {
     if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
@@ -699,6 +751,7 @@ int pimcb_destroy(pimcb_ctx* c) {
     for (int k = 0; k < kKernels; ++k) { cudaEventDestroy(c->ev0[k]); cudaEventDestroy(c->ev1[k]); }
     for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
+    if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -1273,6 +1326,104 @@ int pimcb_virial_sums(pimcb_ctx* c, const double* delta_aos, int t2_parity, doub
     CU(cudaEventRecord(s->consumed, c->stream));
     CU(cudaMemcpyAsync(out, c->d_vir.p, sizeof(double) * 4 * nsl, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- multi-GPU exchange step ------------------------------------------------------------------------------------------
+int pimcb_comm_unique_id(void* id_out) {
+    if (!id_out) return fail(PIMCB_EINVAL, "null argument");
+    if (int rc = load_nccl()) return rc;
+    NcclId id;
+    NCCLCHK(g_nccl.GetUniqueId(&id));
+    std::memcpy(id_out, &id, sizeof id);
+    return 0;
+}
+
+int pimcb_comm_init(pimcb_ctx* c, int nranks, int rank, const void* unique_id) {
+    if (!c || !unique_id || nranks < 1 || rank < 0 || rank >= nranks) return fail(PIMCB_EINVAL, "bad communicator arguments");
+    if (c->nccl_comm) return fail(PIMCB_ESTATE, "communicator already initialised");
+    if (int rc = load_nccl()) return rc;
+    CU(cudaSetDevice(c->device));
+    NcclId id;
+    std::memcpy(&id, unique_id, sizeof id);
+    NCCLCHK(g_nccl.CommInitRank(&c->nccl_comm, nranks, id, rank));
+    c->comm_rank = rank;
+    c->comm_size = nranks;
+    return 0;
+}
+
+int pimcb_comm_destroy(pimcb_ctx* c) {
+    if (!c) return fail(PIMCB_EINVAL, "null ctx");
+    if (c->nccl_comm) {
+        CU(cudaStreamSynchronize(c->stream));
+        NCCLCHK(g_nccl.CommDestroy(c->nccl_comm));
+        c->nccl_comm = nullptr;
+    }
+    c->comm_rank = 0;
+    c->comm_size = 1;
+    return 0;
+}
+
+int pimcb_reduce_bins(pimcb_ctx* c, int root, long* num_total) {
+    if (!c) return fail(PIMCB_EINVAL, "null ctx");
+    if (!c->nccl_comm) return fail(PIMCB_ESTATE, "pimcb_comm_init has not been called");
+    if (root < 0 || root >= c->comm_size) return fail(PIMCB_EINVAL, "root %d out of range", root);
+    if (!c->bins_len) return fail(PIMCB_ESTATE, "no measurement accumulated yet");
+    CU(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = fold_binrows(c, c->bins_M))) return rc;
+    if ((rc = c->d_count.ensure(2 * sizeof(long long)))) return rc;
+    long long* cnt = c->d_count.as<long long>();
+    const long long mine = c->n_acc;
+    CU(cudaMemcpyAsync(cnt, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+    // one group: the bin (in place on the root) and the number of configurations in it
+    NCCLCHK(g_nccl.GroupStart());
+    NCCLCHK(g_nccl.Reduce(c->d_bins.p, c->d_bins.p, c->bins_len, /*ncclDouble*/ 8, /*ncclSum*/ 0, root, c->nccl_comm, c->stream));
+    NCCLCHK(g_nccl.Reduce(cnt, cnt + 1, 1, /*ncclInt64*/ 4, /*ncclSum*/ 0, root, c->nccl_comm, c->stream));
+    NCCLCHK(g_nccl.GroupEnd());
+    if (c->comm_rank == root) {
+        long long total = 0;
+        CU(cudaMemcpyAsync(&total, cnt + 1, sizeof total, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->n_acc = static_cast<long>(total);          // the root's bin now holds every rank's configurations
+        if (num_total) *num_total = static_cast<long>(total);
+    } else if (num_total) {
+        *num_total = 0;
+    }
+    return 0;
+}
+
+int pimcb_gather_bins_q(pimcb_ctx* c, const int* nq_per_rank, double* ssf, double* isf) {
+    if (!c || !nq_per_rank) return fail(PIMCB_EINVAL, "null argument");
+    if (!c->nccl_comm) return fail(PIMCB_ESTATE, "pimcb_comm_init has not been called");
+    if (!c->bins_len) return fail(PIMCB_ESTATE, "no measurement accumulated yet");
+    if (nq_per_rank[c->comm_rank] != c->nq) return fail(PIMCB_EINVAL, "nq_per_rank[%d] = %d but this rank holds %d q-vectors",
+                                                       c->comm_rank, nq_per_rank[c->comm_rank], c->nq);
+    CU(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = fold_binrows(c, c->bins_M))) return rc;
+    const int M = c->bins_M;
+    int width = 0, total = 0;
+    for (int r = 0; r < c->comm_size; ++r) { width = std::max(width, nq_per_rank[r]); total += nq_per_rank[r]; }
+    const size_t slot = static_cast<size_t>(width) * (1 + M);           // padded shard: [width] S then [width][M] F
+    if ((rc = c->d_gather.ensure(sizeof(double) * slot * (c->comm_size + 1)))) return rc;
+    double* send = c->d_gather.as<double>() + slot * c->comm_size;
+    CU(cudaMemsetAsync(send, 0, sizeof(double) * slot, c->stream));
+    CU(cudaMemcpyAsync(send, c->d_bins.p, sizeof(double) * c->nq, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(send + width, c->d_bins.as<double>() + c->nq, sizeof(double) * c->nq * M, cudaMemcpyDeviceToDevice, c->stream));
+    NCCLCHK(g_nccl.AllGather(send, c->d_gather.p, slot, /*ncclDouble*/ 8, c->nccl_comm, c->stream));
+    if ((rc = c->h_out.ensure(sizeof(double) * slot * c->comm_size))) return rc;
+    CU(cudaMemcpyAsync(c->h_out.p, c->d_gather.p, sizeof(double) * slot * c->comm_size, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const double* h = static_cast<const double*>(c->h_out.p);
+    int q0 = 0;
+    for (int r = 0; r < c->comm_size; ++r) {                              // rank order = q order
+        const int n = nq_per_rank[r];
+        if (ssf) std::memcpy(ssf + q0, h + slot * r, sizeof(double) * n);
+        if (isf) std::memcpy(isf + static_cast<size_t>(q0) * M, h + slot * r + width, sizeof(double) * n * M);
+        q0 += n;
+    }
+    (void)total;
     return 0;
 }
 

@@ -1,0 +1,97 @@
+"""The multi-GPU exchange step inside the C ABI (pimcb_comm_* / pimcb_reduce_bins / pimcb_gather_bins_q): NCCL resolved
+with dlopen by the library itself.  One-rank communicator on one GPU; two ranks when the box has two GPUs."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from pimc_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_unique_id_needs_no_gpu():
+    """ncclGetUniqueId through the dlopen'd library: 128 bytes, different on every call."""
+    from pimc_b200 import api
+    a, b = api.Context.comm_unique_id(), api.Context.comm_unique_id()
+    assert len(a) == 128 and len(b) == 128 and a != b
+
+
+@pytest.mark.gpu
+def test_single_rank_communicator(orc):
+    from pimc_b200 import api
+    s = synth.Shape("c1", 3, 20, 12, 2.0, 0.02198, 0)
+    q = synth.commensurate_q(9, s.side)
+    batch = synth.gen_batch(s, 6, first=80)
+    with api.Context(0, 3) as ctx:
+        ctx.set_box(s.side)
+        ctx.set_qvecs(q)
+        with pytest.raises(api.PimcbError):
+            ctx.reduce_bins(0)                                   # no communicator yet
+        ctx.comm_init(1, 0, api.Context.comm_unique_id())
+        ctx.stage(batch[:4], s.N).measure()
+        ctx.stage(batch[4:], s.N).measure()
+        ssf0, isf0, n0 = ctx.read_bins()
+        assert ctx.reduce_bins(0) == 6 == n0
+        ssf1, isf1, n1 = ctx.read_bins()
+        assert n1 == 6 and np.array_equal(ssf0, ssf1) and np.array_equal(isf0, isf1)     # sum over one rank
+        g_ssf, g_isf = ctx.gather_bins_q([len(q)])
+        assert np.array_equal(g_ssf, ssf1) and np.array_equal(g_isf, isf1)
+        with pytest.raises(api.PimcbError):
+            ctx.gather_bins_q([len(q) + 1])
+        ctx.comm_destroy()
+    ref = sum(orc.ssf(s.side, b, s.N, q) for b in batch)
+    np.testing.assert_allclose(ssf1, ref, rtol=1e-10)
+
+
+def _rank(rank, world, uid, mode, ret):
+    sys.path.insert(0, ROOT)
+    from pimc_b200 import api, multi
+    s = synth.Shape("c2", 3, 20, 12, 2.0, 0.02198, 0)
+    q = synth.commensurate_q(9, s.side)
+    batch = synth.gen_batch(s, 6, first=80)
+    with api.Context(rank, 3) as ctx:
+        ctx.set_box(s.side)
+        ctx.comm_init(world, rank, uid)
+        if mode == "cfg":
+            ctx.set_qvecs(q)
+            lo, hi = multi.shard_range(len(batch), world, rank)
+            ctx.stage(batch[lo:hi], s.N).measure()
+            n = ctx.reduce_bins(0)
+            ssf, isf, cnt = ctx.read_bins()
+            ret[rank] = (n, cnt, ssf, isf)
+        else:
+            lo, hi = multi.shard_range(len(q), world, rank)
+            ctx.set_qvecs(q[lo:hi])
+            ctx.stage(batch, s.N).measure()
+            ret[rank] = ctx.gather_bins_q(multi.shard_sizes(len(q), world))
+        ctx.comm_destroy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["cfg", "q"])
+def test_two_rank_reduce_and_gather(orc, mode):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from pimc_b200 import api
+    uid = api.Context.comm_unique_id()
+    ret = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_rank, args=(2, uid, mode, ret), nprocs=2, join=True)
+    s = synth.Shape("c2", 3, 20, 12, 2.0, 0.02198, 0)
+    q = synth.commensurate_q(9, s.side)
+    batch = synth.gen_batch(s, 6, first=80)
+    ssf_ref = sum(orc.ssf(s.side, b, s.N, q) for b in batch)
+    isf_ref = sum(orc.isf_factorised(b, s.N, q) for b in batch)
+    if mode == "cfg":
+        n, cnt, ssf, isf = ret[0]
+        assert n == 6 and cnt == 6 and ret[1][0] == 0 and ret[1][1] == 3
+        np.testing.assert_allclose(ssf, ssf_ref, rtol=1e-10)
+        np.testing.assert_allclose(isf, isf_ref, rtol=1e-10, atol=1e-9)
+    else:
+        for r in range(2):
+            np.testing.assert_allclose(ret[r][0], ssf_ref, rtol=1e-10)
+            np.testing.assert_allclose(ret[r][1], isf_ref, rtol=1e-10, atol=1e-9)
+        assert np.array_equal(ret[0][0], ret[1][0]) and np.array_equal(ret[0][1], ret[1][1])
