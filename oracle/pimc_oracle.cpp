@@ -11,7 +11,13 @@
 //    its shipped GPU implementation of the same two estimators, src/estimator_gpu.cu, compiles unmodified from
 //    the upstream tree (oracle/Makefile target `ref` -> oracle/_ref/librefgpu<NDIM>d.so); tests/test_reference_gpu.py
 //    holds this restatement (and the product's CUDA path) to 1e-10 against it on C1, C2, 2-D and ragged inputs.
-//  * pair-potential sums (Vint, gradVSquared, sepHist), q-vector generation, output formatting, energy:
+//  * Aziz tables (parameter sets, valueV / valuedVdr / valued2Vdr2, initLookupTable, direct lookups, tail correction)
+//    and elastic scattering: PINNED against the reference's own code as well -- the upstream AzizPotential /
+//    TabulatedPotential classes are compiled from the upstream tree into oracle/_ref/librefaziz.so
+//    (oracle/ref_aziz_extract.py + ref_aziz_shim.cpp) and this file's tables are array_equal to theirs
+//    (tests/test_reference_aziz.py); the upstream gpu_es kernel pins orc_elastic (tests/test_reference_gpu.py).
+//  * pair LOOPS (Vint, gradVSquared, sepHist, virial sums), q-vector generation, output formatting, energy / virial
+//    estimators, cylinder S(q):
 //    "parity unpinned" by reference outputs -- no fixture exists upstream and those sources need Boost; pinned by
 //    closed-form known-answer tests (tests/test_oracle_kat.py) and by the reference's own batched-vs-scalar 1e-9
 //    rule reproduced on its sampleVector inputs.

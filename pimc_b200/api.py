@@ -36,6 +36,25 @@ class PimcbError(RuntimeError):
     pass
 
 
+def _prefer_bundled_nccl() -> None:
+    """The library dlopens NCCL by soname.  In a Python process that also imports torch, the copy bundled with torch's
+    wheels (nvidia/nccl/lib) must be the one in the process: a system libnccl.so.2 loaded first would satisfy torch's own
+    DT_NEEDED by soname and miss symbols torch was built against.  Point PIMCB_NCCL_LIB at the bundled copy (found
+    without importing torch) unless the caller chose one."""
+    if os.environ.get("PIMCB_NCCL_LIB"):
+        return
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for root in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(root, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            os.environ["PIMCB_NCCL_LIB"] = cand
+            return
+
+
 _lib = None
 
 
@@ -335,6 +354,7 @@ class Context:
     # -- multi-GPU exchange step (NCCL inside the library) ---------------------------------------------------
     @staticmethod
     def comm_unique_id() -> bytes:
+        _prefer_bundled_nccl()
         lib = load_library()
         buf = C.create_string_buffer(128)
         rc = lib.pimcb_comm_unique_id(buf)
@@ -344,6 +364,7 @@ class Context:
 
     def comm_init(self, nranks: int, rank: int, unique_id: bytes):
         assert len(unique_id) == 128
+        _prefer_bundled_nccl()
         self._chk(self.lib.pimcb_comm_init(self._h, nranks, rank, unique_id))
 
     def comm_destroy(self):

@@ -6,7 +6,9 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB = os.path.join(_HERE, "libpimc_b200.so")
+# PIMCB_LIB_PATH selects another build of the same sources (A/B variants compiled with different -D switches by
+# tools/build_variants.sh); the default is the in-tree product library.
+LIB = os.environ.get("PIMCB_LIB_PATH") or os.path.join(_HERE, "libpimc_b200.so")
 SOURCES = [os.path.join(CSRC, "pimcb.cu")]
 HEADERS = [os.path.join(CSRC, "kernels.cuh"), os.path.join(CSRC, "kernels_ext.cuh"), os.path.join(_HERE, "..", "include", "pimc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -21,6 +23,8 @@ def is_stale() -> bool:
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:
+    if os.environ.get("PIMCB_LIB_PATH"):
+        return LIB                      # a prebuilt variant: never rebuilt implicitly
     if force or is_stale():
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
         extra = os.environ.get("PIMCB_NVCC_EXTRA", "").split()

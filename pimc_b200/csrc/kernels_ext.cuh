@@ -135,14 +135,24 @@ __global__ void ssf_cyl_finalize_kernel(const double* __restrict__ partial, doub
 // whose gradVFactor is finite (-1 all, 0 even, 1 odd, -2 none): the T-matrix terms of the others are returned as 0,
 // as upstream skips them (action.cpp:1505, 1680).  External potential "free" (zero gradient and Laplacian).
 // ---------------------------------------------------------------------------------------------
+#ifndef PIMCB_VIRIAL_UNROLL
+#define PIMCB_VIRIAL_UNROLL 2
+#endif
+#ifndef PIMCB_VIRIAL_MINB
+#define PIMCB_VIRIAL_MINB 3
+#endif
+// Measured on 64 C2 configurations, gsf action (tools/virial_ab.py, gpurun_out r01y): U = 1: 8.21 ms; U = 2 / 3 / 4 at two
+// CTAs per SM (98 / 109 / 120 registers): 6.89 / 6.32 / 6.07 ms; U = 2 or 3 held to 80 registers (three CTAs per SM, no
+// spill at U = 2): 5.35 ms.  All variants return bit-identical sums.
 struct VirialParams {
     const double* dVdr; const double* d2V; int len; double dr; double extdV[2]; double extd2V[2]; int t2_parity; int M;
 };
 
 template <int ND>
-__global__ void __launch_bounds__(256, 2) virial_kernel(const double* __restrict__ pos, const double* __restrict__ delta, int nslices,
+__global__ void __launch_bounds__(256, PIMCB_VIRIAL_MINB) virial_kernel(const double* __restrict__ pos, const double* __restrict__ delta, int nslices,
                                                          int N, int Npad, BoxDev box, VirialParams vp, double* __restrict__ out) {
     constexpr int NT = ND * (ND + 1) / 2;
+    constexpr int U = PIMCB_VIRIAL_UNROLL;
     extern __shared__ __align__(16) double sm[];
     double* xs = sm;                                  // [ND][Npad]
     double* ds = sm + ND * Npad;                      // [ND][Npad] (delta)
@@ -161,33 +171,47 @@ __global__ void __launch_bounds__(256, 2) virial_kernel(const double* __restrict
             for (int d = 0; d < ND; ++d) gV[d] = 0.0;
 #pragma unroll
             for (int k = 0; k < NT; ++k) T[k] = 0.0;
-            for (int kk = 1; kk < N; ++kk) {
-                int j = i + kk;
-                if (j >= N) j -= N;
-                double sep[ND];
-                const double r = minimage_norm<ND>(xs, Npad, i, j, box, sep);     // getSeparation(bead1, bead2)
-                const int kidx = __double2int_rz(__ddiv_rn(r, vp.dr));
-                const bool inside = kidx > 0 && kidx < vp.len;
-                const double dv = inside ? __ldg(vp.dVdr + kidx) : (kidx <= 0 ? vp.extdV[0] : vp.extdV[1]);
-                const double g = dv / r;
-                double gi[ND], g2 = 0.0;
+            // U partners in flight per thread, consumed in partner order (sums identical to the one-at-a-time loop): the
+            // gathers are the long pole, exactly as in pair_kernel (52 % of the stall samples of the U = 1 version were a
+            // warp waiting for its single outstanding table read; profiles/r01x_kernels.md)
+            for (int kk0 = 1; kk0 < N; kk0 += U) {
+                double sep[U][ND], r[U], dv[U], d2[U];
 #pragma unroll
-                for (int d = 0; d < ND; ++d) {
-                    gi[d] = __dmul_rn(g, sep[d]);              // gVi as its own rounded value, then gV += gVi (action.cpp:1466, 1556)
-                    gV[d] = __dadd_rn(gV[d], gi[d]);
-                    g2 = fma(gi[d], gi[d], g2);
+                for (int w = 0; w < U; ++w) {
+                    int j = i + min(kk0 + w, N - 1);                              // surplus slots recompute the last partner
+                    if (j >= N) j -= N;
+                    r[w] = minimage_norm<ND>(xs, Npad, i, j, box, sep[w]);        // getSeparation(bead1, bead2)
                 }
-                if (do_t2) {
-                    const double d2 = inside ? __ldg(vp.d2V + kidx) : (kidx <= 0 ? vp.extd2V[0] : vp.extd2V[1]);
-                    const double dV = sqrt(g2);
-                    const double rinv = 1.0 / r;
-                    const double a = d2 * rinv * rinv - dV * rinv * rinv * rinv;
-                    const double diag = dV * rinv;
-                    int k = 0;
 #pragma unroll
-                    for (int p = 0; p < ND; ++p)
+                for (int w = 0; w < U; ++w) {                                     // all gathers of the group are issued here
+                    const int kidx = __double2int_rz(__ddiv_rn(r[w], vp.dr));
+                    const bool inside = kidx > 0 && kidx < vp.len;
+                    dv[w] = inside ? __ldg(vp.dVdr + kidx) : (kidx <= 0 ? vp.extdV[0] : vp.extdV[1]);
+                    d2[w] = 0.0;
+                    if (do_t2) d2[w] = inside ? __ldg(vp.d2V + kidx) : (kidx <= 0 ? vp.extd2V[0] : vp.extd2V[1]);
+                }
 #pragma unroll
-                        for (int q = p; q < ND; ++q, ++k) T[k] = fma(sep[p] * sep[q], a, T[k]) + (p == q ? diag : 0.0);
+                for (int w = 0; w < U; ++w) {
+                    if (kk0 + w >= N) continue;
+                    const double g = dv[w] / r[w];
+                    double gi[ND], g2 = 0.0;
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) {
+                        gi[d] = __dmul_rn(g, sep[w][d]);           // gVi as its own rounded value, then gV += gVi (action.cpp:1466, 1556)
+                        gV[d] = __dadd_rn(gV[d], gi[d]);
+                        g2 = fma(gi[d], gi[d], g2);
+                    }
+                    if (do_t2) {
+                        const double dV = sqrt(g2);
+                        const double rinv = 1.0 / r[w];
+                        const double a = d2[w] * rinv * rinv - dV * rinv * rinv * rinv;
+                        const double diag = dV * rinv;
+                        int k = 0;
+#pragma unroll
+                        for (int p = 0; p < ND; ++p)
+#pragma unroll
+                            for (int q = p; q < ND; ++q, ++k) T[k] = fma(sep[w][p] * sep[w][q], a, T[k]) + (p == q ? diag : 0.0);
+                    }
                 }
             }
             double u[ND];

@@ -182,10 +182,15 @@ NcclApi g_nccl;
 
 int load_nccl() {
     if (g_nccl.handle) return 0;
+    // An NCCL already in the process (e.g. the one a host framework brought along) is used as is: loading a second copy
+    // under the same soname would shadow it for everything loaded later.  Otherwise PIMCB_NCCL_LIB, then the default
+    // sonames.  RTLD_LOCAL: our symbols are taken from the handle, nothing is injected into the global namespace.
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
     const char* names[] = {std::getenv("PIMCB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
-    void* h = nullptr;
-    for (const char* n : names)
-        if (n && *n && (h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    for (const char* n : names) {
+        if (h) break;
+        if (n && *n) h = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+    }
     if (!h) return fail(PIMCB_ESTATE, "NCCL library not found (set PIMCB_NCCL_LIB): %s", dlerror());
     NcclApi a;
     a.handle = h;
