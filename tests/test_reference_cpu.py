@@ -1,0 +1,219 @@
+"""Parity against the REFERENCE'S OWN CPU code for the whole hot path.  The upstream function bodies -- the estimators'
+accumulate() loops, the LocalAction slice sums, getQVectors / getQVectors2, putInBC, getSeparation / getVelocity, the Aziz
+class -- are cut out of the upstream tree at build time and compiled into oracle/_ref/librefcpu<NDIM>d.so
+(oracle/ref_cpu_extract.py + oracle/ref_cpu_shim.cpp, `make -C oracle ref`; built by __graft_entry__.build() wherever
+/root/reference exists, shipped with the snapshot).  The CPU oracle is held against them here (CPU suite), and the CUDA
+path directly (GPU suite) -- to the north-star tolerance of 1e-10, integer outputs exactly."""
+import math
+
+import numpy as np
+import pytest
+
+from parity import assert_parity
+from pimc_b200 import synth
+from refcpu import RefCpu
+
+LAM = synth.LAMBDA_HE4
+GSF = ([2.0 / 3.0, 4.0 / 3.0], [0.0, 2.0 / 9.0], 2)                # src/setup.cpp:1240-1246
+PRIMITIVE = ([1.0, 1.0], [0.0, 0.0], 1)
+LI_BROUGHTON = ([1.0, 1.0], [1.0 / 12.0, 1.0 / 12.0], 2)
+
+
+def permuted_links(M, N, Next, seed):
+    rng = np.random.default_rng(seed)
+    nxt = np.full((M, Next, 2), -1, dtype=np.int32)
+    for s in range(M):
+        nxt[s, :N, 0] = (s + 1) % M
+        nxt[s, :N, 1] = np.arange(N)
+    nxt[M - 1, :N, 1] = rng.permutation(N)
+    return nxt
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU: oracle vs upstream code
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ndim,N,rho,qtype,text", [
+    (3, 16, 0.02198, "int", "1 0 0  0 -2 3  5 5 5"),
+    (3, 16, 0.02198, "float", "0.1 0.25 1.7  -2.2 0.3 0.0"),
+    (3, 16, 0.02198, "max_int", "2 1 2"),
+    (3, 256, 0.02198, "max_float", "0.9 0.0 0.0"),
+    (2, 128, 0.0432, "max_int", "8 8"),
+    (2, 128, 0.0432, "max_float", "1.1 0.0"),
+    (2, 128, 0.0432, "int", "1 0 0 1 -1 1"),
+])
+def test_qvectors_bit_identical_to_upstream(orc, ndim, N, rho, qtype, text):
+    side = np.full(ndim, (N / rho) ** (1.0 / ndim))
+    ref = RefCpu(ndim).qvectors(qtype, text, side)
+    got = orc.qvectors(qtype, text, side)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("ndim,geometry,qmax", [(3, "line", 4.0), (3, "sphere", 0.9), (2, "line", 2.0), (2, "sphere", 1.0)])
+def test_qvectors2_bit_identical_to_upstream(orc, ndim, geometry, qmax):
+    side = np.full(ndim, 20.0)
+    dq = 2.0 * math.pi / side[-1]
+    ref = RefCpu(ndim).qvectors2(dq, qmax, geometry, side)
+    got = orc.qvectors2(ndim, dq, qmax, geometry)
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["C1", "2d", "ragged", "noncommensurate", "slab"])
+def test_ssf_isf_oracle_vs_upstream_loops(orc, nthreads, name):
+    """StaticStructureFactorEstimator::accumulate (minimum image) and IntermediateScatteringFunctionEstimator::accumulate
+    (raw positions): the restatement reproduces the upstream loops bit for bit (same operation order, same flags)."""
+    periodic = None
+    if name == "C1":
+        s, q = synth.C1, synth.commensurate_q(64, synth.C1.side)
+    elif name == "2d":
+        s = synth.Shape("r2", 2, 40, 30, 1.0, 0.0432, 0)
+        q = orc.qvectors("max_int", "3 3", s.side)
+    elif name == "ragged":
+        s = synth.Shape("rr", 3, 37, 10, 2.0, 0.02198, 0)
+        q = synth.commensurate_q(11, s.side, include_zero=True)
+    elif name == "noncommensurate":
+        s = synth.Shape("nc", 3, 20, 8, 2.0, 0.02198, 0)
+        q = synth.float_q(9, 3)
+    else:
+        s = synth.Shape("sl", 3, 20, 8, 2.0, 0.02198, 0)
+        q = np.vstack([synth.commensurate_q(5, s.side), synth.float_q(4, 3)])
+        periodic = [1, 1, 0]
+    beads = synth.gen_config(s.N, s.M, s.ndim, s.rho, s.T, seed=synth.BASE_SEED + 9, pad=3)
+    beads[:, s.N:, :] = 4321.0
+    ref = RefCpu(s.ndim)
+    r_ssf = ref.ssf(s.side, beads, s.N, q, periodic)
+    o_ssf = orc.ssf(s.side, beads, s.N, q, periodic=periodic, nthreads=nthreads)
+    assert np.array_equal(o_ssf, r_ssf)
+    nq_isf = min(len(q), 6)
+    r_isf = ref.isf(s.side, beads, s.N, q[:nq_isf])
+    o_isf = orc.isf(beads, s.N, q[:nq_isf], nthreads=nthreads)
+    assert np.array_equal(o_isf, r_isf)
+    assert_parity(orc.isf_factorised(beads, s.N, q[:nq_isf]), r_isf, f"{name}: factorised CPU variant vs upstream loop")
+
+
+def test_cylinder_ssf_oracle_vs_upstream(orc):
+    from test_variants import cylinder_config
+    N, M, L, R = 37, 12, 11.0, 3.0
+    beads, side, per = cylinder_config(N, M, L, R, seed=3)
+    ref = RefCpu(3)
+    shells = ref.qvectors2(2.0 * math.pi / L, 4.0, "line", side)
+    maxR = 2.0
+    r_out, n1d = ref.ssf_cyl(side, beads, N, shells, maxR, per)
+    raw, n_in = orc.ssf_cyl(side, beads, N, np.vstack(shells), maxR, periodic=per)
+    assert n_in == n1d and 0 < n1d < N
+    assert np.array_equal(raw / n_in, r_out)                       # one vector per shell for "line"
+    # several vectors per shell ("sphere"): shell sums
+    sph = ref.qvectors2(2.0 * math.pi / L, 1.2, "sphere", side)
+    r_out, n1d = ref.ssf_cyl(side, beads, N, sph, maxR, per)
+    raw, _ = orc.ssf_cyl(side, beads, N, np.vstack(sph), maxR, periodic=per)
+    k, sums = 0, []
+    for sh in sph:
+        sums.append(raw[k:k + len(sh)].sum())
+        k += len(sh)
+    np.testing.assert_allclose(np.array(sums) / n1d, r_out, rtol=1e-13)
+
+
+@pytest.mark.parametrize("action", ["gsf", "primitive", "li_broughton"])
+def test_action_sums_oracle_vs_upstream(orc, nthreads, action):
+    """LocalAction::V(slice) + sepHist, gradVSquared, potentialAction and its derivatives, the virial terms, and the
+    energy / virial estimators: oracle restatement vs the upstream bodies running on the upstream Aziz class."""
+    VF, GF, period = {"gsf": GSF, "primitive": PRIMITIVE, "li_broughton": LI_BROUGHTON}[action]
+    s = synth.Shape("ac", 3, 18, 8, 2.0, 0.02198, 0)
+    beads = synth.gen_config(s.N, s.M, 3, s.rho, s.T, seed=77, pad=2)
+    Next = beads.shape[1]
+    links = permuted_links(s.M, s.N, Next, 4)
+    window = 3
+    r = RefCpu(3).action(s.side, beads, s.N, s.tau, LAM, VF, GF, period, window=window, mu=-1.5, next_links=links)
+    V, dV, d2V, dr = orc.aziz_table(orc.max_sep(s.side), second=True)
+    dSep = 0.5 * math.sqrt(3) * s.side[2] / 50
+    vint, f2, hist = orc.pair_sums(s.side, beads, s.N, V, dV, dr, dSep, nthreads=nthreads)
+    assert np.array_equal(hist, r["sephist"])
+    assert np.array_equal(vint, r["vint"])
+    assert np.array_equal(f2, r["f2"])
+    f2m = f2.copy()
+    for eo in (0, 1):
+        if not GF[eo] > 1e-7:
+            f2m[eo::2] = 0.0
+    np.testing.assert_allclose(orc.potential_action(vint, f2m, VF, GF, s.tau, LAM), r["potentialAction"], rtol=1e-14)
+    for t in range(s.M):
+        np.testing.assert_allclose(orc.deriv_potential_action_tau(vint[t], f2m[t], t, VF, GF, s.tau, LAM), r["dtau"][t], rtol=1e-14)
+        np.testing.assert_allclose(orc.deriv_potential_action_lambda(f2m[t], t, GF, s.tau), r["dlam"][t], rtol=1e-14, atol=0)
+    # virial terms: the oracle returns the bare sums, upstream multiplies by VFactor*tau and 2*gradVFactor*tau^3*lambda
+    t2p = -1 if (GF[0] > 1e-7 and GF[1] > 1e-7) else (1 if GF[1] > 1e-7 else (0 if GF[0] > 1e-7 else -2))
+    vir = orc.virial_sums(s.side, beads, s.N, window, dV, d2V, dr, t2_parity=t2p, next_links=links, nthreads=nthreads)
+    eo = np.arange(s.M) % 2
+    c1 = np.array(VF)[eo] * s.tau
+    c2 = 2.0 * np.array(GF)[eo] * s.tau ** 3 * LAM
+    assert_parity(vir[:, 0] * c1, r["vir"][:, 0], "rDOTgradUterm1")
+    assert_parity(vir[:, 2] * c1, r["vir"][:, 2], "deltaDOTgradUterm1")
+    if t2p != -2:
+        assert_parity(vir[:, 1] * c2, r["vir"][:, 1], "rDOTgradUterm2")
+        assert_parity(vir[:, 3] * c2, r["vir"][:, 3], "deltaDOTgradUterm2")
+    else:
+        assert np.all(r["vir"][:, 1] == 0.0) and np.all(r["vir"][:, 3] == 0.0)
+    tail = orc.aziz_tail(s.side[2])
+    en = orc.energy(s.side, beads, s.N, vint, f2m, VF, GF, period, s.tau, LAM, tail, mu=-1.5, next_links=links)
+    np.testing.assert_allclose(en, r["energy"], rtol=1e-12, atol=1e-12 * np.max(np.abs(r["energy"])))
+    ve = orc.virial_energy(s.side, beads, s.N, window, vir, vint, f2m, VF, GF, s.tau, LAM, tail, mu=-1.5, next_links=links)
+    np.testing.assert_allclose(ve, r["virial"], rtol=1e-11, atol=1e-11 * np.max(np.abs(r["virial"])))
+    assert r["virial"][15] == 0.0                                   # the upstream "cVCov2" key typo: the column stays empty
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU: CUDA path vs upstream CPU code, directly
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_cuda_path_against_upstream_cpu_code(orc):
+    from pimc_b200 import api
+    s = synth.C1
+    beads = synth.gen_config(s.N, s.M, 3, s.rho, s.T, seed=synth.BASE_SEED + 31, pad=3)
+    Next = beads.shape[1]
+    ref = RefCpu(3)
+    text = synth.int_wavevector_text(24, 3)
+    q = np.vstack([ref.qvectors("int", text, s.side), ref.qvectors("float", "0.3 -1.1 0.7 2.0 0.1 0.4", s.side)])
+    links = permuted_links(s.M, s.N, Next, 12)
+    VF, GF, period = GSF
+    window = 5
+    r = ref.action(s.side, beads, s.N, s.tau, LAM, VF, GF, period, window=window, next_links=links)
+    V, dV, d2V, dr = orc.aziz_table(orc.max_sep(s.side), second=True)       # array_equal to upstream (test_reference_aziz.py)
+    dSep = 0.5 * math.sqrt(3) * s.side[2] / 50
+    delta = orc.virial_delta(s.side, beads, s.N, window, next_links=links)
+    with api.Context(0, 3) as ctx:
+        ctx.set_box(s.side)
+        ctx.set_qvecs(q)
+        ctx.set_pair_table(V, dV, dr)
+        ctx.set_pair_table_d2(d2V)
+        ssf, isf = ctx.stage(beads, s.N).ssf_isf()
+        vint, f2, hist = ctx.pair_sums(dSep, f2_parity=-1)
+        vir = ctx.virial_sums(delta, t2_parity=1)
+    assert_parity(ssf[0], ref.ssf(s.side, beads, s.N, q), "S(q) vs upstream CPU loop (min-image, incl. non-commensurate q)")
+    k = [0, 7, 23, 25]
+    assert_parity(isf[0][k], ref.isf(s.side, beads, s.N, q[k]), "F(q,tau) vs upstream CPU loop")
+    assert np.array_equal(hist[0], r["sephist"])
+    assert_parity(vint[0], r["vint"], "Vint vs upstream LocalAction::V(slice)")
+    assert_parity(f2[0], r["f2"], "gradVSquared vs upstream")
+    eo = np.arange(s.M) % 2
+    c1 = np.array(VF)[eo] * s.tau
+    c2 = 2.0 * np.array(GF)[eo] * s.tau ** 3 * LAM
+    assert_parity(vir[0][:, 0] * c1, r["vir"][:, 0], "rDOTgradUterm1 vs upstream")
+    assert_parity(vir[0][:, 1] * c2, r["vir"][:, 1], "rDOTgradUterm2 vs upstream")
+    assert_parity(vir[0][:, 2] * c1, r["vir"][:, 2], "deltaDOTgradUterm1 vs upstream")
+    assert_parity(vir[0][:, 3] * c2, r["vir"][:, 3], "deltaDOTgradUterm2 vs upstream")
+
+
+@pytest.mark.gpu
+def test_cuda_cylinder_ssf_against_upstream_cpu_code(orc):
+    from pimc_b200 import api
+    from test_variants import cylinder_config
+    N, M, L, R = 37, 12, 11.0, 3.0
+    beads, side, per = cylinder_config(N, M, L, R, seed=8)
+    ref = RefCpu(3)
+    shells = ref.qvectors2(2.0 * math.pi / L, 4.0, "line", side)
+    r_out, n1d = ref.ssf_cyl(side, beads, N, shells, 2.0, per)
+    with api.Context(0, 3) as ctx:
+        ctx.set_box(side, per)
+        ctx.set_qvecs(np.vstack(shells))
+        out, n_in = ctx.stage(beads, N).ssf_cyl(2.0)
+    assert n_in[0] == n1d
+    assert_parity(out[0] / n_in[0], r_out, "cylinder S(q) vs upstream CPU loop")
