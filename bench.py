@@ -97,43 +97,110 @@ def algorithmic_flops(shape, nq):
 
 
 # --------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's estimators on the host cores (bounded sample, linear extrapolation)
+# CPU arm: the reference's CPU estimators on the host cores (bounded sample, linear extrapolation by term count)
 # --------------------------------------------------------------------------------------------------------------
+class UpstreamCpu:
+    """oracle/_ref/librefcpu<NDIM>d_fast.so: the reference's OWN accumulate() bodies (cut out of the upstream tree at build
+    time, oracle/ref_cpu_extract.py + ref_cpu_shim.cpp) compiled with the reference's optimisation flags."""
+
+    def __init__(self, ndim):
+        import ctypes as C
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle", "_ref", f"librefcpu{ndim}d_fast.so")
+        self.lib = C.CDLL(path)                       # OSError when it was not built: the caller falls back to the port
+        dp, up = C.POINTER(C.c_double), C.POINTER(C.c_uint)
+        self.lib.refcpu_ssf.argtypes = [dp, up, dp, C.c_int, C.c_int, C.c_int, dp, C.c_int, dp]
+        self.lib.refcpu_isf.argtypes = [dp, dp, C.c_int, C.c_int, C.c_int, dp, C.c_int, dp]
+        self.dp, self.up = dp, up
+
+    def ssf(self, side, beads, N, q):
+        M, Next, nd = beads.shape
+        out = np.zeros(len(q))
+        per = np.ones(nd, dtype=np.uint32)
+        self.lib.refcpu_ssf(side.ctypes.data_as(self.dp), per.ctypes.data_as(self.up), beads.ctypes.data_as(self.dp), M, N, Next,
+                            q.ctypes.data_as(self.dp), len(q), out.ctypes.data_as(self.dp))
+        return out
+
+    def isf(self, side, beads, N, q):
+        M, Next, nd = beads.shape
+        out = np.zeros((len(q), M))
+        self.lib.refcpu_isf(beads.ctypes.data_as(self.dp), side.ctypes.data_as(self.dp), M, N, Next, q.ctypes.data_as(self.dp), len(q),
+                            out.ctypes.data_as(self.dp))
+        return out
+
+
 class CpuArm:
+    """Times the reference's CPU S(q) + F(q,tau) on all host threads.  kind = "reference": the upstream accumulate() bodies
+    themselves (UpstreamCpu); the upstream F(q,tau) loop cannot be restricted to a tau range, so its bounded sample is the
+    full (q, t0, tau, i, j) loop nest over the first Ms time slices of the configuration for one q per thread -- every term
+    costs the same cos/sin quadruple -- extrapolated by the term count (nq/threads) * (M/Ms)^2; S(q) runs at full size on
+    a subset of q.  kind = "port" (when the upstream library was not built): the oracle restatement, sampled by output
+    element."""
+
     def __init__(self, shape, q, budget_core_s):
-        from oracle import oracle
-        self.orc = oracle.get(fast=True)
-        self.shape, self.q = shape, q
+        self.shape, self.q = shape, np.ascontiguousarray(q, dtype=np.float64)
         self.cores = host_cores()
         self.beads = synth.gen_config(shape.N, shape.M, shape.ndim, shape.rho, shape.T)
-        # per-element cost estimates (ns per pair term, measured on the container's Xeon) only size the sample
-        isf_elem_s = shape.M * shape.N**2 * 25e-9
-        ssf_q_s = shape.M * shape.N * (shape.N - 1) / 2 * 40e-9
+        self.side = np.ascontiguousarray(shape.side, dtype=np.float64)
         c = self.cores
-        self.n_elem = int(min(len(q) * shape.M, max(1, round(0.6 * budget_core_s / isf_elem_s / c)) * c))   # whole rounds of threads
+        try:
+            self.up = UpstreamCpu(shape.ndim)
+            self.kind = "reference"
+        except OSError:
+            self.up = None
+            self.kind = "port"
+            from oracle import oracle
+            self.orc = oracle.get(fast=True)
+        # per-term cost estimates (measured on the container's Xeon) only size the sample
+        ssf_q_s = shape.M * shape.N * (shape.N - 1) / 2 * 40e-9
         n_ssf = 0.4 * budget_core_s / ssf_q_s
         self.n_ssf = int(min(len(q), max(1, round(n_ssf / c)) * c if n_ssf >= c else max(1, round(n_ssf))))
+        if self.up:
+            per_thread_s = 0.6 * budget_core_s / c
+            ms = int((per_thread_s / (shape.N ** 2 * 25e-9)) ** 0.5)
+            self.Ms = max(2, min(shape.M, ms - ms % 2))
+            self.nq_isf = min(len(q), c)
+            self.sub = np.ascontiguousarray(self.beads[:self.Ms])
+        else:
+            isf_elem_s = shape.M * shape.N**2 * 25e-9
+            self.n_elem = int(min(len(q) * shape.M, max(1, round(0.6 * budget_core_s / isf_elem_s / c)) * c))   # whole rounds of threads
 
     def step(self):
         """One bounded sample; returns (extrapolated seconds per full evaluation, wall seconds of the sample)."""
         s, q = self.shape, self.q
-        t0 = time.perf_counter()
-        self.orc.isf_range(self.beads, s.N, q, 0, self.n_elem, nthreads=self.cores)
-        t1 = time.perf_counter()
-        self.orc.ssf(s.side, self.beads, s.N, q[:self.n_ssf], nthreads=min(self.cores, self.n_ssf))
-        t2 = time.perf_counter()
-        full = (t1 - t0) * (len(q) * s.M / self.n_elem) + (t2 - t1) * (len(q) / self.n_ssf)
+        if not self.up:
+            t0 = time.perf_counter()
+            self.orc.isf_range(self.beads, s.N, q, 0, self.n_elem, nthreads=self.cores)
+            t1 = time.perf_counter()
+            self.orc.ssf(s.side, self.beads, s.N, q[:self.n_ssf], nthreads=min(self.cores, self.n_ssf))
+            t2 = time.perf_counter()
+            full = (t1 - t0) * (len(q) * s.M / self.n_elem) + (t2 - t1) * (len(q) / self.n_ssf)
+            return full, t2 - t0
+        from concurrent.futures import ThreadPoolExecutor          # ctypes calls release the GIL: one upstream loop per host thread
+        with ThreadPoolExecutor(self.cores) as pool:
+            t0 = time.perf_counter()
+            list(pool.map(lambda k: self.up.isf(self.side, self.sub, s.N, np.ascontiguousarray(q[k:k + 1])), range(self.nq_isf)))
+            t1 = time.perf_counter()
+            nt = min(self.cores, self.n_ssf)
+            chunks = [np.ascontiguousarray(q[:self.n_ssf][k::nt]) for k in range(nt)]
+            list(pool.map(lambda qq: self.up.ssf(self.side, self.beads, s.N, qq), chunks))
+            t2 = time.perf_counter()
+        rounds = -(-len(q) // self.cores)                            # q-vectors per thread for the whole q-set
+        full = (t1 - t0) * rounds * (s.M / self.Ms) ** 2 + (t2 - t1) * (len(q) / self.n_ssf)
         return full, t2 - t0
 
     def sample_text(self):
         s = self.shape
+        if self.up:
+            return (f"upstream accumulate() bodies (oracle/_ref/librefcpu{s.ndim}d_fast.so), 1 configuration, {self.cores} threads: F(q,tau) full "
+                    f"loop nest over the first {self.Ms} of {s.M} slices for {self.nq_isf} q (one per thread), S(q) at full size for "
+                    f"{self.n_ssf} of {len(self.q)} q; extrapolated by term count to {len(self.q)} q x {s.M}^2 slice pairs")
         return (f"1 configuration: {self.n_elem} of {len(self.q) * s.M} F(q,tau) elements (direct O(M N^2) loop each) + "
                 f"S(q) for {self.n_ssf} of {len(self.q)} q, {self.cores} threads, extrapolated linearly to the full q-set")
 
 
 def run_reference(args, shape, q):
-    """--impl reference: the reference's CPU algorithm (oracle port; the upstream sources need Boost/<mdspan> and do
-    not compile here) with all host threads.  Under torchrun only rank 0 works."""
+    """--impl reference: the reference's own CPU estimators (the upstream accumulate() bodies compiled into oracle/_ref,
+    else the oracle port) with all host threads.  Under torchrun only rank 0 works."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     total_steps = max(1, args.steps + args.warmup)
@@ -152,9 +219,10 @@ def run_reference(args, shape, q):
         "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(wall)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{shape.name}: N={shape.N} M={shape.M} nq={len(q)} ndim={shape.ndim}, He-4 SVP density, "
-                               f"commensurate q; reference CPU estimators (oracle port) on a bounded sample per step",
+                               f"commensurate q; reference CPU estimators ({'upstream code' if arm.kind == 'reference' else 'oracle port'}) "
+                               f"on a bounded sample per step",
                    "parallelism": f"{arm.cores} host threads, q-vectors / F(q,tau) elements split over threads"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": arm.sample_text()},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.sample_text()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -588,7 +656,7 @@ def run_ours(args, shape, q):
         os.sched_setaffinity(0, all_cpus)             # the CPU arm gets every host core again
         arm = CpuArm(shape, q, args.cpu_seconds)
         full_s, _ = arm.step()
-        line["cpu_baseline"] = {"value": 1.0 / full_s, "unit": UNIT, "cores": arm.cores, "kind": "port",
+        line["cpu_baseline"] = {"value": 1.0 / full_s, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
                                 "sample": arm.sample_text()}
     else:
         line["cpu_baseline"] = None

@@ -16,11 +16,14 @@
 //    TabulatedPotential classes are compiled from the upstream tree into oracle/_ref/librefaziz.so
 //    (oracle/ref_aziz_extract.py + ref_aziz_shim.cpp) and this file's tables are array_equal to theirs
 //    (tests/test_reference_aziz.py); the upstream gpu_es kernel pins orc_elastic (tests/test_reference_gpu.py).
-//  * pair LOOPS (Vint, gradVSquared, sepHist, virial sums), q-vector generation, output formatting, energy / virial
-//    estimators, cylinder S(q):
-//    "parity unpinned" by reference outputs -- no fixture exists upstream and those sources need Boost; pinned by
-//    closed-form known-answer tests (tests/test_oracle_kat.py) and by the reference's own batched-vs-scalar 1e-9
-//    rule reproduced on its sampleVector inputs.
+//  * Every loop in this file -- S(q), F(q,tau), cylinder S(q), Vint / gradVSquared / sepHist, potentialAction and its
+//    derivatives, the virial slice sums, getQVectors / getQVectors2, the energy and virial estimators -- is PINNED
+//    against the reference's own CPU code: the upstream function bodies are cut out of the upstream tree at build time
+//    (oracle/ref_cpu_extract.py) and compiled into oracle/_ref/librefcpu<NDIM>d.so (oracle/ref_cpu_shim.cpp);
+//    tests/test_reference_cpu.py holds this file array_equal to them on q-sets, S(q), F(q,tau), Vint, gradVSquared,
+//    sepHist, and within 1e-11 on the derived quantities.
+//  * Still unpinned by reference code: the %16.8E row formatting (boost::format upstream) and the state-file text
+//    format; closed-form known-answer tests (tests/test_oracle_kat.py, tests/test_variants.py) cover the rest again.
 //
 // Every function cites the reference file:line (relative to the upstream tree) whose
 // arithmetic it follows.  Floating-point semantics: this file is compiled with
