@@ -483,7 +483,9 @@ def run_ours(args, shape, q):
             ctx.ssf_isf_beads(one_locked, shape.N)                        # one ABI call: DMA, transpose, kernels, read-back, one sync
         lat_locked = (time.perf_counter() - t0) / nlat
         latency = {"single_configuration_us": lat_locked * 1e6, "evaluations_per_s": 1.0 / lat_locked, "calls": nlat,
-                   "path": "pimcb_ssf_isf_beads(page-locked host AoS), what B200Session calls: one synchronous ABI call per walker",
+                   "path": "pimcb_ssf_isf_beads(page-locked host AoS), what B200Session calls: one synchronous ABI call per walker"
+                           + ("" if os.environ.get("PIMCB_GRAPH", "1") == "0" else
+                              "; H2D -> transpose -> rho_q -> tau-correlation -> D2H replayed as one CUDA graph"),
                    "pageable_source_us": lat * 1e6}
         for sl, pa in enumerate(pinned):               # the single-walker calls cycled through the slots: restore the batches
             ctx.stage(pa.array, shape.N, slot=sl)

@@ -410,3 +410,53 @@ def test_error_paths(api):
         ctx.stage(np.zeros((4, 2, 3)), 2)
         with pytest.raises(api.PimcbError):
             ctx.pair_sums(1.0)                        # no table
+
+
+def test_fused_single_walker_call_graph_replay(api, orc, nthreads):
+    """pimcb_ssf_isf_beads with a page-locked source: call 1 runs the ordinary path, call 2 captures the CUDA graph,
+    later calls replay it.  Every call must return exactly what the ordinary path returns for the CURRENT contents of the
+    source buffer; a new q-set, a new shape or a pageable source fall back and re-capture."""
+    s = synth.C1
+    q = synth.commensurate_q(24, s.side)
+    cfgs = synth.gen_batch(s, 6, first=300)
+    pa = api.PinnedArray(cfgs.shape[1:])
+    try:
+        with make_ctx(api, s, q) as ctx, make_ctx(api, s, q) as plain:
+            got = []
+            for k in range(6):
+                pa.array[...] = cfgs[k]
+                n0 = ctx.launch_count()
+                got.append(ctx.ssf_isf_beads(pa.array, s.N))
+                if k >= 2:
+                    assert ctx.launch_count() - n0 == 3            # transpose, rho_q, tau-correlation per replay
+                ref_ssf, ref_isf = plain.stage(cfgs[k], s.N).ssf_isf()
+                assert np.array_equal(got[-1][0], ref_ssf) and np.array_equal(got[-1][1], ref_isf), f"call {k}"
+            assert_parity(got[5][0][0], orc.ssf(s.side, cfgs[5], s.N, q, nthreads=nthreads), "graph replay S(q)")
+            assert_parity(got[5][1][0], orc.isf(cfgs[5], s.N, q, nthreads=nthreads), "graph replay F(q,tau)")
+            # the elastic-scattering epilogue finds the replayed results in the cache
+            es = ctx.elastic()
+            np.testing.assert_allclose(es[0], 2.0 / s.M * got[5][1][0][:, :s.M // 2 + 1].sum(axis=1), rtol=1e-12)
+            # new q-set: dropped, primed, captured again
+            q2 = synth.commensurate_q(9, s.side)
+            ctx.set_qvecs(q2)
+            plain.set_qvecs(q2)
+            for k in range(4):
+                pa.array[...] = cfgs[k]
+                a = ctx.ssf_isf_beads(pa.array, s.N)
+                b = plain.stage(cfgs[k], s.N).ssf_isf()
+                assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+            # pageable source and a different shape in between
+            a = ctx.ssf_isf_beads(cfgs[1].copy(), s.N)
+            b = plain.stage(cfgs[1], s.N).ssf_isf()
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+            half = np.ascontiguousarray(cfgs[2][: s.M // 2])
+            a = ctx.ssf_isf_beads(half, s.N)
+            b = plain.stage(half, s.N).ssf_isf()
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+            for k in range(3):
+                pa.array[...] = cfgs[k + 3]
+                a = ctx.ssf_isf_beads(pa.array, s.N)
+                b = plain.stage(cfgs[k + 3], s.N).ssf_isf()
+                assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    finally:
+        pa.free()
