@@ -137,6 +137,11 @@ int pimcb_set_pair_table(pimcb_ctx* ctx, const double* V, const double* dVdr /*o
  * interaction part).  vint[b][M]; f2[b][M] or NULL; sephist[b][M][50] or NULL.
  * `f2_parity`: -1 = every slice, 0/1 = only slices with slice%2 == f2_parity (others get 0). */
 int pimcb_pair_sums(pimcb_ctx* ctx, double* vint, double* f2, int* sephist, double dSep, int f2_parity);
+/* Non-trivial external potentials: LocalAction::gradVSquared adds externalPtr->gradV(r_i) to the pair force of every
+ * bead before squaring (src/action.cpp:1216).  `gext_aos` holds those gradients for the CURRENTLY staged beads, in the
+ * beads' own AoS shape ([B][M][N_ext][ndim]; evaluated by the caller through the reference's PotentialBase, O(N M));
+ * it is used by pimcb_pair_sums until new beads are staged.  NULL clears it ("free" external potential, the default). */
+int pimcb_set_external_gradient(pimcb_ctx* ctx, const double* gext_aos);
 
 /* ---- scattering variants ---------------------------------------------------
  * pimcb_elastic: replaces ElasticScatteringEstimatorGpu::accumulate (src/estimator.cpp:4197-4235; kernel

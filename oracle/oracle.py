@@ -74,6 +74,7 @@ class Oracle:
         L.orc_table_V.argtypes = [C.c_int, _dp, C.c_int, C.c_double, _dp, _dp, _dp, C.c_int]
         L.orc_pair_sums.argtypes = [C.c_int, _dp, _up, _dp, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int,
                                     C.c_double, _dp, _dp, C.c_double, _dp, _dp, _ip, C.c_int]
+        L.orc_grad_v_squared_ext.argtypes = [C.c_int, _dp, _up, _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, C.c_double, _dp, _dp, _dp]
         L.orc_put_in_bc.argtypes = [C.c_int, _dp, _up, _dp, C.c_int]
         L.orc_format_row.argtypes = [_dp, _dp, C.c_int, C.c_uint, C.c_char_p, C.c_int]
         L.orc_dvec_to_string.argtypes = [C.c_int, _dp, C.c_char_p, C.c_int]
@@ -212,6 +213,18 @@ class Oracle:
                                     _iptr(hist), nthreads)
         assert rc == 0
         return vint, f2, hist
+
+    def grad_v_squared_ext(self, side, beads, N, dVdr, dr, gext, periodic=None) -> np.ndarray:
+        """gradVSquared[M] with the external potential's gradient per bead (gext shaped like beads)."""
+        beads, M, Next, nd = self._beads(beads)
+        side, per = self._box(side, periodic)
+        dVdr, gext = _f64(dVdr), _f64(gext)
+        ext = np.zeros(2)
+        f2 = np.zeros(M)
+        rc = self.lib.orc_grad_v_squared_ext(nd, _dptr(side), per.ctypes.data_as(_up), _dptr(beads), M, N, Next, _dptr(dVdr),
+                                             len(dVdr), dr, _dptr(ext), _dptr(gext), _dptr(f2))
+        assert rc == 0
+        return f2
 
     def potential_action(self, vint, f2, VFactor, gradVFactor, tau, lam) -> float:
         vint = _f64(vint)

@@ -340,7 +340,8 @@ double vint_slice(const Box& box, const PairTable& tab, const double* beads, int
 // LocalAction::gradVSquared(slice), interaction part (external "free" potential has zero gradient).
 // src/action.cpp:1188-1223; AzizPotential::gradV include/potential.h:997-1003.
 template <int ND>
-double grad_v_squared_slice(const Box& box, const PairTable& tab, const double* beads, int N, int Next, int slice) {
+double grad_v_squared_slice(const Box& box, const PairTable& tab, const double* beads, int N, int Next, int slice,
+                            const double* gext = nullptr) {
     double totF2 = 0.0;
     for (int i = 0; i < N; ++i) {
         double F[ND];
@@ -353,6 +354,10 @@ double grad_v_squared_slice(const Box& box, const PairTable& tab, const double* 
             const double rnorm = std::sqrt(dot<ND>(sep, sep));
             const double g = table_direct(tab.dVdr, tab.len, tab.dr, tab.extdVdr, rnorm) / rnorm;
             for (int d = 0; d < ND; ++d) F[d] += g * sep[d];
+        }
+        if (gext) {                                             // :1216  F += externalPtr->gradV(path(bead1))
+            const double* ge = bead<ND>(gext, Next, slice, i);
+            for (int d = 0; d < ND; ++d) F[d] += ge[d];
         }
         totF2 += dot<ND>(F, F);                                 // :1219
     }
@@ -804,6 +809,20 @@ int orc_pair_sums(int ndim, const double* side, const unsigned* periodic, const 
         if (s1 > s0) pool.emplace_back(work, s0, s1);
     }
     for (auto& th : pool) th.join();
+    return 0;
+}
+
+// gradVSquared[M] with a non-trivial external potential: gext[M][Next][ndim] = externalPtr->gradV(r) per bead.
+int orc_grad_v_squared_ext(int ndim, const double* side, const unsigned* periodic, const double* beads, int M, int N, int Next,
+                           const double* dVdr, int len, double dr, const double* extdVdr, const double* gext, double* f2) {
+    if (ndim < 1 || ndim > 3) return -100;
+    const Box b = make_box(ndim, side, periodic);
+    PairTable tab{nullptr, dVdr, len, dr, {0.0, 0.0}, {extdVdr ? extdVdr[0] : 0.0, extdVdr ? extdVdr[1] : 0.0}};
+    for (int s = 0; s < M; ++s) {
+        if (ndim == 1) f2[s] = grad_v_squared_slice<1>(b, tab, beads, N, Next, s, gext);
+        else if (ndim == 2) f2[s] = grad_v_squared_slice<2>(b, tab, beads, N, Next, s, gext);
+        else f2[s] = grad_v_squared_slice<3>(b, tab, beads, N, Next, s, gext);
+    }
     return 0;
 }
 

@@ -171,6 +171,15 @@ public:
     double tailV = 0.0;
 };
 class FreePotential : public PotentialBase {};                              // include/potential.h: V = 0, gradV = 0
+// a non-trivial external potential for the tests of the gradient coupling (not an upstream class): V = k r^2 / 2
+class SpringTestPotential : public PotentialBase {
+public:
+    explicit SpringTestPotential(double k_) : k(k_) {}
+    double V(const dVec& r) override { return 0.5 * k * dot(r, r); }
+    dVec gradV(const dVec& r) override { return k * r; }
+private:
+    double k;
+};
 #include "ref_aziz_extract.inc"    // upstream: TabulatedPotential<T>, AzizPotential
 
 // action.cpp's file-local helper (src/action.cpp:119-156) without its timing statistics: V per position
@@ -429,11 +438,13 @@ int refcpu_ssf_cyl(const double* side, const unsigned* periodic, const double* b
 int refcpu_action(int year, const double* side, const double* beads, int M, int N, int Next, const int* next, double tau,
                   double lambda, double mu, int window, const double* VF, const double* GF, int period, double* vint, double* f2,
                   int* sephist, double* vir, double* dtau, double* dlam, double* d2tau, double* vkc, double* scalars,
-                  double* energy, double* virial) {
+                  double* energy, double* virial, double spring_k) {
     const Container box = make_container(side, nullptr);
     set_constants(M, tau, lambda, mu, side[NDIM - 1], box.volume, window);       // rc defaults to side[NDIM-1] (src/setup.cpp:1128-1130)
     Path path(&box, M, N, Next, beads, next);
-    FreePotential external;
+    FreePotential freeExternal;
+    SpringTestPotential spring(spring_k);
+    PotentialBase& external = spring_k != 0.0 ? static_cast<PotentialBase&>(spring) : static_cast<PotentialBase&>(freeExternal);
     AzizPotential aziz(year, &box);
     LocalAction action(path, &external, &aziz, {VF[0], VF[1]}, {GF[0], GF[1]}, period);
     for (int s = 0; s < M; ++s) {

@@ -28,7 +28,7 @@ SYMBOLS = [
     "pimcb_pair_sums", "pimcb_measure_fp64_peak", "pimcb_set_profiling", "pimcb_set_profiling_stride", "pimcb_kernel_times",
     "pimcb_launch_count", "pimcb_rho_plan_info", "pimcb_elastic", "pimcb_ssf_cyl", "pimcb_set_pair_table_d2",
     "pimcb_virial_sums", "pimcb_comm_unique_id", "pimcb_comm_init", "pimcb_comm_destroy", "pimcb_reduce_bins",
-    "pimcb_gather_bins_q",
+    "pimcb_gather_bins_q", "pimcb_set_external_gradient",
 ]
 
 
@@ -110,6 +110,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.pimcb_ssf_cyl.argtypes = [vp, C.c_double, _dp, _ip]
     lib.pimcb_set_pair_table_d2.argtypes = [vp, _dp, C.c_int, _dp]
     lib.pimcb_virial_sums.argtypes = [vp, _dp, C.c_int, _dp]
+    lib.pimcb_set_external_gradient.argtypes = [vp, _dp]
     lib.pimcb_comm_unique_id.argtypes = [C.c_char_p]
     lib.pimcb_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
     lib.pimcb_comm_destroy.argtypes = [vp]
@@ -312,6 +313,11 @@ class Context:
         dV = _f64(dVdr) if dVdr is not None else None
         e0, e1 = _f64(extV), _f64(extdVdr)
         self._chk(self.lib.pimcb_set_pair_table(self._h, _ptr(V), _ptr(dV), len(V), dr, _ptr(e0), _ptr(e1)))
+
+    def set_external_gradient(self, gext):
+        """gext: gradient of the external potential per bead, shaped like the staged beads (or None to clear)."""
+        g = _f64(gext) if gext is not None else None
+        self._chk(self.lib.pimcb_set_external_gradient(self._h, _ptr(g)))
 
     def pair_sums(self, dSep=None, want_f2=True, want_hist=True, f2_parity=-1):
         B, M, _ = self.shape

@@ -1165,6 +1165,7 @@ __device__ __forceinline__ double table_direct(const double* __restrict__ tab, i
 struct PairParams {
     const double* V; const double* dVdr; int len; double dr; double extV[2]; double extdV[2];
     double dSep; int want_hist; int f2_parity; int M;
+    const double* gext;    // gradient of the external potential per bead, slice rows like pos ([sl][d][Npad]), or nullptr ("free")
 };
 
 #ifndef PIMCB_PAIR_UNROLL
@@ -1251,6 +1252,11 @@ __global__ void __launch_bounds__(256, PIMCB_PAIR_MINB) pair_kernel(const double
                 }
             }
             if (do_f2) {
+                if (pp.gext) {                                   // F += externalPtr->gradV(path(bead1)), action.cpp:1216
+                    const double* ge = pp.gext + static_cast<size_t>(sl) * ND * Npad + i;
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) F[d] += __ldg(ge + d * Npad);
+                }
 #pragma unroll
                 for (int d = 0; d < ND; ++d) fsum = fma(F[d], F[d], fsum);
             }

@@ -150,7 +150,8 @@ struct pimcb_ctx {
     unsigned long gen_counter = 0, cfg_gen = 0;
     int cfg_slot = -1;
     // scattering variants (elastic, cylinder S(q)) and virial slice sums
-    DevBuf d_var, d_inside, d_d2V, d_delta_aos, d_delta, d_vir;
+    DevBuf d_var, d_inside, d_d2V, d_delta_aos, d_delta, d_vir, d_gext;
+    unsigned long gext_gen = 0;             // staging generation the uploaded external-potential gradient belongs to (0 = none)
     bool have_d2V = false;
     double extd2V[2] = {0, 0};
     // single-walker fast path: the fixed sequence H2D -> transpose -> rho_q -> tau-correlation -> D2H of
@@ -1294,6 +1295,43 @@ int pimcb_set_pair_table(pimcb_ctx* c, const double* V, const double* dVdr, int 
     return 0;
 }
 
+// Uploads per-bead vectors given in the staged beads' own AoS shape ([B][M][N_ext][ndim]) into slice rows like pos.
+static int upload_bead_vectors(pimcb_ctx* c, Slot* s, const double* aos, DevBuf& dst) {
+    const int nd = c->ndim, nsl = s->B * s->M;
+    const int Next = s->Next > 0 ? s->Next : s->N;
+    const size_t aos_bytes = sizeof(double) * static_cast<size_t>(nsl) * Next * nd;
+    int rc;
+    if ((rc = c->d_delta_aos.ensure(aos_bytes))) return rc;
+    if ((rc = dst.ensure(sizeof(double) * static_cast<size_t>(nsl) * nd * s->Npad))) return rc;
+    CU(cudaMemcpyAsync(c->d_delta_aos.p, aos, aos_bytes, cudaMemcpyHostToDevice, c->stream));
+    const size_t tsmem = sizeof(double) * s->N * nd;
+    const int tgrid = static_cast<int>(std::min<size_t>(nsl, static_cast<size_t>(c->sm_count) * 8));
+#define LAUNCH_TV(ND)                                                                                              \
+    rc = set_smem(aos_to_soa_kernel<ND>, tsmem); if (rc) return rc;                                                 \
+    aos_to_soa_kernel<ND><<<tgrid, 256, tsmem, c->stream>>>(c->d_delta_aos.as<double>(), dst.as<double>(), nsl, s->N, Next, s->Npad)
+    {
+        KTimer kt(c, K_TRANSPOSE);
+        if (nd == 1) { LAUNCH_TV(1); } else if (nd == 2) { LAUNCH_TV(2); } else { LAUNCH_TV(3); }
+    }
+#undef LAUNCH_TV
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int pimcb_set_external_gradient(pimcb_ctx* c, const double* gext_aos) {
+    if (!c) return fail(PIMCB_EINVAL, "null ctx");
+    if (!gext_aos) { c->gext_gen = 0; return 0; }
+    CU(cudaSetDevice(c->device));
+    Slot* s;
+    int rc = need_cur(c, &s);
+    if (rc) return rc;
+    CU(cudaStreamWaitEvent(c->stream, s->ready, 0));
+    if ((rc = upload_bead_vectors(c, s, gext_aos, c->d_gext))) return rc;
+    CU(cudaStreamSynchronize(c->stream));          // the caller's array may go away
+    c->gext_gen = s->gen;
+    return 0;
+}
+
 int pimcb_pair_sums(pimcb_ctx* c, double* vint, double* f2, int* sephist, double dSep, int f2_parity) {
     if (!c || !vint) return fail(PIMCB_EINVAL, "null argument");
     CU(cudaSetDevice(c->device));
@@ -1310,7 +1348,8 @@ int pimcb_pair_sums(pimcb_ctx* c, double* vint, double* f2, int* sephist, double
     if (f2 && (rc = c->d_f2.ensure(sizeof(double) * nsl))) return rc;
     if (sephist && (rc = c->d_hist.ensure(sizeof(int) * static_cast<size_t>(nsl) * kNPCFSEP))) return rc;
     PairParams pp{c->d_V.as<double>(), c->d_dV.as<double>(), c->tab_len, c->dr, {c->extV[0], c->extV[1]}, {c->extdV[0], c->extdV[1]},
-                  sephist ? dSep : 1.0, sephist ? 1 : 0, f2_parity, s->M};
+                  sephist ? dSep : 1.0, sephist ? 1 : 0, f2_parity, s->M,
+                  (c->gext_gen != 0 && c->gext_gen == s->gen) ? c->d_gext.as<double>() : nullptr};
     CU(cudaStreamWaitEvent(c->stream, s->ready, 0));
     if ((rc = materialize(c, *s))) return rc;
     {
@@ -1431,22 +1470,7 @@ int pimcb_virial_sums(pimcb_ctx* c, const double* delta_aos, int t2_parity, doub
     const double* d_delta = nullptr;
     if (delta_aos) {
         // same AoS shape as the staged beads ([B][M][N_ext][ndim]); transposed on the device into the slice-row layout
-        const int Next = s->Next > 0 ? s->Next : s->N;
-        const size_t aos_bytes = sizeof(double) * static_cast<size_t>(nsl) * Next * nd;
-        if ((rc = c->d_delta_aos.ensure(aos_bytes))) return rc;
-        if ((rc = c->d_delta.ensure(sizeof(double) * static_cast<size_t>(nsl) * nd * s->Npad))) return rc;
-        CU(cudaMemcpyAsync(c->d_delta_aos.p, delta_aos, aos_bytes, cudaMemcpyHostToDevice, c->stream));
-        const size_t tsmem = sizeof(double) * s->N * nd;
-        const int tgrid = static_cast<int>(std::min<size_t>(nsl, static_cast<size_t>(c->sm_count) * 8));
-#define LAUNCH_TD(ND)                                                                                              \
-        rc = set_smem(aos_to_soa_kernel<ND>, tsmem); if (rc) return rc;                                             \
-        aos_to_soa_kernel<ND><<<tgrid, 256, tsmem, c->stream>>>(c->d_delta_aos.as<double>(), c->d_delta.as<double>(), nsl, s->N, Next, s->Npad)
-        {
-            KTimer kt(c, K_TRANSPOSE);
-            if (nd == 1) { LAUNCH_TD(1); } else if (nd == 2) { LAUNCH_TD(2); } else { LAUNCH_TD(3); }
-        }
-#undef LAUNCH_TD
-        CU(cudaGetLastError());
+        if ((rc = upload_bead_vectors(c, s, delta_aos, c->d_delta))) return rc;
         d_delta = c->d_delta.as<double>();
     }
     VirialParams vp{c->d_dV.as<double>(), c->d_d2V.as<double>(), c->tab_len, c->dr, {c->extdV[0], c->extdV[1]},

@@ -14,8 +14,31 @@ LocalActionB200::LocalActionB200(const Path& _path, PotentialBase* external, Pot
     if (table.d2Vdr2) B200Session::get(path).setPairTableD2(table.d2Vdr2, table.tableLength, table.extd2Vdr2.data());
 }
 
+// externalPtr->gradV(path(bead)) for every active bead, O(N M) on the host through the reference's own PotentialBase
+// (src/action.cpp:1216: added to the pair force of the bead before squaring).  NULL when all gradients vanish (`free`).
+const std::vector<double>* LocalActionB200::externalGradient() {
+    if (!needF2) return nullptr;
+    const auto ext = path.get_beads_extents();
+    const size_t Next = ext[1];
+    bool any = false;
+    gext.assign(static_cast<size_t>(path.numTimeSlices) * Next * NDIM, 0.0);
+    for (int slice = 0; slice < path.numTimeSlices; ++slice) {
+        const int n = path.numBeadsAtSlice(slice);
+        for (int i = 0; i < n; ++i) {
+            const dVec g = externalPtr->gradV(path(slice, i));
+            for (int d = 0; d < NDIM; ++d) {
+                gext[(static_cast<size_t>(slice) * Next + i) * NDIM + d] = g[d];
+                any = any || g[d] != 0.0;
+            }
+        }
+    }
+    return any ? &gext : nullptr;
+}
+
 const B200Session::PairSums& LocalActionB200::sums() {
-    return B200Session::get(path).pairSums(dSep, needF2, f2Parity);
+    B200Session& session = B200Session::get(path);
+    if (session.havePairSums(needF2)) return session.pairSums(dSep, needF2, f2Parity);      // cached for this configuration
+    return session.pairSums(dSep, needF2, f2Parity, externalGradient());
 }
 
 // Per-slice entry points are called for slice = 0..M-1 in ascending order within one measurement
@@ -40,8 +63,8 @@ std::array<double, 2> LocalActionB200::potential(int slice) {
     return {externalV(slice), s.vint[slice]};
 }
 
-// The interaction part comes from the device; a non-trivial external potential adds gradVext inside |F_i|^2, which
-// couples to the pair forces -- supported only for external potentials with zero gradient (FreePotential).
+// sum_i | sum_j gradV(r_ij) + gradVext(r_i) |^2 on the device; the external gradients are evaluated on the host through the
+// reference's PotentialBase and uploaded with the configuration (pimcb_set_external_gradient).
 double LocalActionB200::gradVSquared(int slice) { return sums().f2[slice]; }
 
 double LocalActionB200::potentialAction() {

@@ -46,7 +46,8 @@ private:
     const B200Session::PairSums& sumsForSlice(int slice, int which);
     const double* virial(int slice);        // the four sums of `slice`
     double externalV(int slice);
-    double externalGradCorrection(int slice);
+    std::vector<double> gext;               // gradVext per bead ([M][N_ext][NDIM]); left empty while every gradient is zero ("free")
+    const std::vector<double>* externalGradient();
 };
 
 #endif

@@ -125,9 +125,10 @@ void B200Session::setPairTable(const double* V, const double* dVdr, int len, dou
     have_pair_ = false;
 }
 
-const B200Session::PairSums& B200Session::pairSums(double dSep, bool wantF2, int f2Parity) {
+const B200Session::PairSums& B200Session::pairSums(double dSep, bool wantF2, int f2Parity, const std::vector<double>* gext) {
     if (!(have_pair_ && (pair_has_f2_ || !wantF2))) {
         stageIfNeeded();
+        if (wantF2) check(pimcb_set_external_gradient(ctx_, gext ? gext->data() : nullptr), "pimcb_set_external_gradient");
         const int M = path_.numTimeSlices;
         pair_.vint.assign(M, 0.0);
         pair_.f2.assign(M, 0.0);

@@ -42,7 +42,9 @@ public:
     // Pair sums of the current configuration: Vint[M], gradVSquared[M], sepHist[M][NPCFSEP].
     void setPairTable(const double* V, const double* dVdr, int len, double dr, const double* extV, const double* extdVdr);
     struct PairSums { std::vector<double> vint, f2; std::vector<int> hist; };
-    const PairSums& pairSums(double dSep, bool wantF2, int f2Parity);
+    // gext (may be NULL = "free"): gradient of the external potential per bead in the beads' own AoS shape, added to the
+    // pair force inside gradVSquared (src/action.cpp:1216)
+    const PairSums& pairSums(double dSep, bool wantF2, int f2Parity, const std::vector<double>* gext = nullptr);
 
     // Scattering variants of the current configuration: the elastic-scattering increment [nq] and the
     // cylinder S(q) raw sums [nq] + the number of slice-0 beads inside maxR.
@@ -54,6 +56,7 @@ public:
     // computed here from the path's links.  t2Parity as pimcb_virial_sums.
     void setPairTableD2(const double* d2Vdr2, int len, const double* extd2Vdr2);
     const std::vector<double>& virialSums(int window, int t2Parity);
+    bool havePairSums(bool wantF2) const { return have_pair_ && (pair_has_f2_ || !wantF2); }
     void invalidate() { staged_ = false; have_sf_ = false; have_pair_ = false; have_es_ = have_cyl_ = have_vir_ = false; }
     void beginIfUnhooked() { if (!hooked_) invalidate(); }
     bool hooked() const { return hooked_; }

@@ -36,7 +36,7 @@ class RefCpu:
         L.refcpu_ssf_cyl.argtypes = [_dp, _up, _dp, C.c_int, C.c_int, C.c_int, _dp, _ip, C.c_int, C.c_double, _dp]
         if ndim == 3:
             L.refcpu_action.argtypes = [C.c_int, _dp, _dp, C.c_int, C.c_int, C.c_int, _ip, C.c_double, C.c_double, C.c_double,
-                                        C.c_int, _dp, _dp, C.c_int, _dp, _dp, _ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
+                                        C.c_int, _dp, _dp, C.c_int, _dp, _dp, _ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double]
 
     def qvectors(self, qtype, text, side):
         side = _f64(side)
@@ -81,7 +81,7 @@ class RefCpu:
         n1d = self.lib.refcpu_ssf_cyl(_p(side), _p(per, _up), _p(beads), M, N, Next, _p(q), _p(sizes, _ip), len(shells), maxR, _p(out))
         return out, n1d
 
-    def action(self, side, beads, N, tau, lam, VF, GF, period, window=5, mu=0.0, next_links=None, year=1979):
+    def action(self, side, beads, N, tau, lam, VF, GF, period, window=5, mu=0.0, next_links=None, year=1979, spring_k=0.0):
         """dict of everything LocalAction / EnergyEstimator / VirialEnergyEstimator return for one configuration."""
         side, beads = _f64(side), _f64(beads)
         M, Next, _ = beads.shape
@@ -92,7 +92,7 @@ class RefCpu:
              "energy": np.zeros(9), "virial": np.zeros(19)}
         rc = self.lib.refcpu_action(year, _p(side), _p(beads), M, N, Next, _p(nl, _ip), tau, lam, mu, window, _p(vf), _p(gf), period,
                                     _p(r["vint"]), _p(r["f2"]), _p(r["sephist"], _ip), _p(r["vir"]), _p(r["dtau"]), _p(r["dlam"]),
-                                    _p(r["d2tau"]), _p(r["vkc"]), _p(r["scalars"]), _p(r["energy"]), _p(r["virial"]))
+                                    _p(r["d2tau"]), _p(r["vkc"]), _p(r["scalars"]), _p(r["energy"]), _p(r["virial"]), spring_k)
         assert rc == 0
         r["potentialAction"] = float(r.pop("scalars")[0])
         return r

@@ -160,6 +160,22 @@ def test_action_sums_oracle_vs_upstream(orc, nthreads, action):
     assert r["virial"][15] == 0.0                                   # the upstream "cVCov2" key typo: the column stays empty
 
 
+def test_external_gradient_coupling_oracle_vs_upstream(orc):
+    """gradVSquared with a non-trivial external potential (F_i += gradVext(r_i) before squaring, src/action.cpp:1216):
+    oracle vs the upstream body running with a spring potential V = k r^2/2."""
+    VF, GF, period = LI_BROUGHTON
+    s = synth.Shape("xg", 3, 14, 6, 2.0, 0.02198, 0)
+    beads = synth.gen_config(s.N, s.M, 3, s.rho, s.T, seed=41, pad=2)
+    k = 40.0
+    r = RefCpu(3).action(s.side, beads, s.N, s.tau, LAM, VF, GF, period, spring_k=k)
+    V, dV, dr = orc.aziz_table(orc.max_sep(s.side))
+    gext = k * beads
+    assert np.array_equal(orc.grad_v_squared_ext(s.side, beads, s.N, dV, dr, gext), r["f2"])
+    free = RefCpu(3).action(s.side, beads, s.N, s.tau, LAM, VF, GF, period)
+    assert not np.allclose(free["f2"], r["f2"], rtol=1e-3)            # the coupling matters
+    np.testing.assert_allclose(orc.grad_v_squared_ext(s.side, beads, s.N, dV, dr, 0.0 * beads), free["f2"], rtol=0, atol=0)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # GPU: CUDA path vs upstream CPU code, directly
 # ------------------------------------------------------------------------------------------------------------------
@@ -217,3 +233,33 @@ def test_cuda_cylinder_ssf_against_upstream_cpu_code(orc):
         out, n_in = ctx.stage(beads, N).ssf_cyl(2.0)
     assert n_in[0] == n1d
     assert_parity(out[0] / n_in[0], r_out, "cylinder S(q) vs upstream CPU loop")
+
+
+@pytest.mark.gpu
+def test_cuda_external_gradient_against_upstream_cpu_code(orc):
+    from pimc_b200 import api
+    VF, GF, period = LI_BROUGHTON
+    s = synth.Shape("xg", 3, 37, 10, 2.0, 0.02198, 0)
+    batch = synth.gen_batch(s, 2, first=44, pad=2)
+    k = 40.0
+    V, dV, dr = orc.aziz_table(orc.max_sep(s.side))
+    dSep = 0.5 * math.sqrt(3) * s.side[2] / 50
+    with api.Context(0, 3) as ctx:
+        ctx.set_box(s.side)
+        ctx.set_pair_table(V, dV, dr)
+        ctx.stage(batch, s.N)
+        _, f2_free, _ = ctx.pair_sums(dSep)
+        ctx.set_external_gradient(k * batch)
+        vint, f2, hist = ctx.pair_sums(dSep)
+        ctx.set_external_gradient(None)
+        _, f2_cleared, _ = ctx.pair_sums(dSep)
+        ctx.set_external_gradient(k * batch)
+        ctx.stage(batch[::-1].copy(), s.N)                      # new beads: the old gradient must not be applied to them
+        _, f2_restaged, _ = ctx.pair_sums(dSep)
+    for b in range(2):
+        r = RefCpu(3).action(s.side, batch[b], s.N, s.tau, LAM, VF, GF, period, spring_k=k)
+        assert_parity(f2[b], r["f2"], "gradVSquared with external gradient vs upstream")
+        assert_parity(vint[b], r["vint"], "Vint")
+        assert np.array_equal(hist[b], r["sephist"])
+    assert np.array_equal(f2_free, f2_cleared) and np.array_equal(f2_restaged, f2_free[::-1])
+    assert not np.allclose(f2_free, f2, rtol=1e-3)
