@@ -188,6 +188,25 @@ class CpuArm:
         full = (t1 - t0) * rounds * (s.M / self.Ms) ** 2 + (t2 - t1) * (len(q) / self.n_ssf)
         return full, t2 - t0
 
+    def one_core(self):
+        """Extrapolated seconds per full evaluation on ONE host core (the reference is single-threaded): the same bounded
+        sample, one q through the F(q,tau) loop nest and a few q through S(q), on the calling thread."""
+        s, q = self.shape, self.q
+        n1 = max(1, self.n_ssf // self.cores)
+        t0 = time.perf_counter()
+        if self.up:
+            self.up.isf(self.side, self.sub, s.N, np.ascontiguousarray(q[:1]))
+            t1 = time.perf_counter()
+            self.up.ssf(self.side, self.beads, s.N, np.ascontiguousarray(q[:n1]))
+            t2 = time.perf_counter()
+            return (t1 - t0) * len(q) * (s.M / self.Ms) ** 2 + (t2 - t1) * (len(q) / n1)
+        ne = max(1, self.n_elem // self.cores)
+        self.orc.isf_range(self.beads, s.N, q, 0, ne, nthreads=1)
+        t1 = time.perf_counter()
+        self.orc.ssf(s.side, self.beads, s.N, q[:n1], nthreads=1)
+        t2 = time.perf_counter()
+        return (t1 - t0) * (len(q) * s.M / ne) + (t2 - t1) * (len(q) / n1)
+
     def sample_text(self):
         s = self.shape
         if self.up:
@@ -659,7 +678,7 @@ def run_ours(args, shape, q):
         arm = CpuArm(shape, q, args.cpu_seconds)
         full_s, _ = arm.step()
         line["cpu_baseline"] = {"value": 1.0 / full_s, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
-                                "sample": arm.sample_text()}
+                                "sample": arm.sample_text(), "one_core_value": 1.0 / arm.one_core()}
     else:
         line["cpu_baseline"] = None
     if rank == 0:
