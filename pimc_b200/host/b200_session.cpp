@@ -219,3 +219,36 @@ const std::vector<double>& B200Session::virialSums(int window, int t2Parity) {
     }
     return vir_;
 }
+
+// ---- batched accumulation and the multi-GPU exchange step ------------------------------------------------------------
+void B200Session::measureBatch(const double* beads, int B, int M, int N, int Next) {
+    check(pimcb_stage_batch(ctx_, beads, B, M, N, Next), "pimcb_stage_batch");
+    check(pimcb_measure(ctx_), "pimcb_measure");
+    invalidate();                              // the staged slot no longer is "the current configuration of the path"
+}
+
+void B200Session::readBins(std::vector<double>& ssf, std::vector<double>& isf, long& count) {
+    const int M = path_.numTimeSlices;
+    ssf.assign(nq_, 0.0);
+    isf.assign(nq_ * M, 0.0);
+    check(pimcb_read_bins(ctx_, ssf.data(), isf.data(), &count), "pimcb_read_bins");
+}
+
+void B200Session::resetBins() { check(pimcb_reset_bins(ctx_), "pimcb_reset_bins"); }
+
+void B200Session::uniqueId(void* id128) {
+    if (pimcb_comm_unique_id(id128) != 0) {
+        std::cerr << "\nERROR: pimc_b200: pimcb_comm_unique_id failed: " << pimcb_last_error() << std::endl;
+        std::exit(EXIT_FAILURE);
+    }
+}
+
+void B200Session::commInit(int nranks, int rank, const void* id128) {
+    check(pimcb_comm_init(ctx_, nranks, rank, id128), "pimcb_comm_init");
+}
+
+long B200Session::reduceBins(int root) {
+    long total = 0;
+    check(pimcb_reduce_bins(ctx_, root, &total), "pimcb_reduce_bins");
+    return total;
+}

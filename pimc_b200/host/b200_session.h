@@ -46,6 +46,17 @@ public:
     // pair force inside gradVSquared (src/action.cpp:1216)
     const PairSums& pairSums(double dSep, bool wantF2, int f2Parity, const std::vector<double>* gext = nullptr);
 
+    // Batched, device-resident accumulation (walker batches): B configurations in the reference bead layout
+    // ([B][M][N_ext][NDIM]) are staged and measured without a read-back; the sums stay in the device bin until readBins.
+    // Multi-GPU: one process per GPU, commInit on every rank (the 128-byte id comes from uniqueId on one of them), one
+    // reduceBins per output bin.
+    void measureBatch(const double* beads, int B, int M, int N, int Next);
+    void readBins(std::vector<double>& ssf, std::vector<double>& isf, long& count);
+    void resetBins();
+    static void uniqueId(void* id128);
+    void commInit(int nranks, int rank, const void* id128);
+    long reduceBins(int root);
+
     // Scattering variants of the current configuration: the elastic-scattering increment [nq] and the
     // cylinder S(q) raw sums [nq] + the number of slice-0 beads inside maxR.
     const std::vector<double>& elastic();

@@ -69,3 +69,19 @@ void IntermediateScatteringFunctionEstimatorB200::accumulate() {
     const int n = static_cast<int>(f.size());
     for (int k = 0; k < n; k++) estimator(k) += f[k];
 }
+
+// ---- bins accumulated elsewhere -------------------------------------------------------------------------------------------
+// A walker batch measured with B200Session::measureBatch (and reduced over GPUs) arrives as the SUM of its accumulate()
+// increments; adding it with its count leaves EstimatorBase::output (estimator * norm / numAccumulated) unchanged.
+void StaticStructureFactorEstimatorB200::addBin(const double* sums, uint32 count) {
+    for (int n = 0; n < numq; n++) estimator(n) += sums[n];
+    numAccumulated += count;
+    totNumAccumulated += count;
+}
+
+void IntermediateScatteringFunctionEstimatorB200::addBin(const double* sums, uint32 count) {
+    const int n = numq * constants()->numTimeSlices();
+    for (int k = 0; k < n; k++) estimator(k) += sums[k];
+    numAccumulated += count;
+    totNumAccumulated += count;
+}

@@ -25,6 +25,8 @@ public:
     ~StaticStructureFactorEstimatorB200();
     static const std::string name;
     std::string getName() const { return name; }
+    // sums of `count` accumulate() increments computed elsewhere (device-resident bins, other GPUs): estimator += sums
+    void addBin(const double* sums, uint32 count);
 private:
     int numq;
     std::vector<dVec> qValues;
@@ -38,6 +40,7 @@ public:
     ~IntermediateScatteringFunctionEstimatorB200();
     static const std::string name;
     std::string getName() const { return name; }
+    void addBin(const double* sums, uint32 count);
 private:
     int numq;
     std::vector<dVec> qValues;

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <iostream>
 
 #include "action_b200.h"
@@ -80,7 +81,9 @@ int main(int argc, char** argv) {
     c->wavevector_ = arg(argc, argv, "--wavevector", "");
     c->wavevectorType_ = arg(argc, argv, "--wavevector_type", "int");
     c->id_ = arg(argc, argv, "--id", "run");
-    communicate()->init(arg(argc, argv, "--outdir", "OUTPUT"), "ce", c->id_);
+    // ranks other than 0 of a multi-GPU run keep their (header-only) files apart: only rank 0 writes results
+    const int myRank = std::atoi(arg(argc, argv, "--rank", "0"));
+    communicate()->init(arg(argc, argv, "--outdir", "OUTPUT"), "ce", myRank > 0 ? c->id_ + "-rank" + std::to_string(myRank) : c->id_);
 
     Prism box(density, N);
     c->V_ = box.volume;
@@ -130,6 +133,71 @@ int main(int argc, char** argv) {
     if (wantPotential) {
         potOut = &communicate()->file("potential")->stream();
         (*potOut) << "# potentialAction, then Vint[0..M-1], then gradVSquared[0..M-1] per configuration" << std::endl;
+    }
+
+    // --batch B [--nranks n --rank r --idfile path]: walker batches accumulated on the device (pimcb_stage_batch +
+    // pimcb_measure, no per-configuration read-back); with several ranks (one process per GPU, PIMCB_DEVICE selects it)
+    // every rank takes a contiguous share of the configurations and the bins are summed onto rank 0 with ONE NCCL reduce
+    // (pimcb_reduce_bins); rank 0 writes ONE row per file: the bin of all configurations.
+    const int batch = std::atoi(arg(argc, argv, "--batch", "0"));
+    if (batch > 0) {
+        if (fromStates || wantPotential || maxR > 0.0) { std::cerr << "--batch works on --configs with the S(q)/F(q,tau) estimators" << std::endl; return 2; }
+        const int nranks = std::atoi(arg(argc, argv, "--nranks", "1")), rank = std::atoi(arg(argc, argv, "--rank", "0"));
+        B200Session& session = B200Session::get(path);
+        if (nranks > 1) {
+            const std::string idfile = arg(argc, argv, "--idfile", "pimcb_nccl_id.bin");
+            char id[128];
+            if (rank == 0) {
+                B200Session::uniqueId(id);
+                FILE* o = std::fopen((idfile + ".tmp").c_str(), "wb");
+                if (!o || std::fwrite(id, 1, 128, o) != 128) { std::cerr << "cannot write " << idfile << std::endl; return 1; }
+                std::fclose(o);
+                std::rename((idfile + ".tmp").c_str(), idfile.c_str());
+            } else {
+                FILE* in = nullptr;
+                for (int tries = 0; tries < 6000 && !(in = std::fopen(idfile.c_str(), "rb")); ++tries) {
+                    struct timespec ts = {0, 10 * 1000 * 1000};
+                    nanosleep(&ts, nullptr);
+                }
+                if (!in || std::fread(id, 1, 128, in) != 128) { std::cerr << "cannot read " << idfile << std::endl; return 1; }
+                std::fclose(in);
+            }
+            session.commInit(nranks, rank, id);
+        }
+        FILE* fb = std::fopen(cfgFile, "rb");
+        if (!fb) { std::cerr << "cannot open " << cfgFile << std::endl; return 1; }
+        const size_t rec = static_cast<size_t>(M) * extent * NDIM;
+        std::fseek(fb, 0, SEEK_END);
+        const long total = std::ftell(fb) / static_cast<long>(rec * sizeof(double));
+        const long base = total / nranks, extra = total % nranks;
+        const long lo = rank * base + std::min<long>(rank, extra), hi = lo + base + (rank < extra ? 1 : 0);
+        std::fseek(fb, static_cast<long>(lo * rec * sizeof(double)), SEEK_SET);
+        std::vector<double> buf(rec * batch);
+        long mine = 0;
+        for (long k = lo; k < hi; k += batch) {
+            const int nb = static_cast<int>(std::min<long>(batch, hi - k));
+            if (std::fread(buf.data(), sizeof(double), rec * nb, fb) != rec * nb) { std::cerr << "short read" << std::endl; return 1; }
+            session.measureBatch(buf.data(), nb, M, N, extent);
+            mine += nb;
+        }
+        std::fclose(fb);
+        long count = mine;
+        if (nranks > 1) count = session.reduceBins(0);
+        if (rank == 0) {
+            std::vector<double> ssf, isf;
+            long n = 0;
+            session.readBins(ssf, isf, n);
+            static_cast<StaticStructureFactorEstimatorB200*>(estimators[0].get())->addBin(ssf.data(), static_cast<uint32>(n));
+            static_cast<IntermediateScatteringFunctionEstimatorB200*>(estimators[1].get())->addBin(isf.data(), static_cast<uint32>(n));
+            estimators[0]->output();
+            estimators[1]->output();
+            count = n;
+        }
+        std::cout << "pimcb_measure: rank " << rank << "/" << nranks << " measured " << mine << " configurations"
+                  << (rank == 0 ? ", bin of " + std::to_string(count) : std::string()) << std::endl;
+        estimators.clear();
+        B200Session::shutdown();
+        return 0;
     }
 
     FILE* f = fromStates ? nullptr : std::fopen(cfgFile, "rb");

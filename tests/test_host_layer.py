@@ -360,3 +360,50 @@ def test_cylinder_ssf_estimator_through_the_plugin_api(host_bins, orc, tmp_path)
     np.testing.assert_allclose(mags, np.linalg.norm(q, axis=1), rtol=1e-6, atol=1e-12)
     got = np.array([float(rows[0][16 * k:16 * k + 16]) for k in range(len(q))])
     np.testing.assert_allclose(got, acc / (s.M * n_acc), rtol=2e-8)
+
+
+def _run_batched(host_bins, tmp_path, s, cfg, text, tag, extra, env=None):
+    out = tmp_path / "OUTPUT"
+    cmd = [os.path.join(host_bins, "pimcb_measure3d"), "-N", str(s.N), "-n", repr(s.rho), "-T", repr(s.T), "-P", str(s.M),
+           "--extent", str(s.N + 3), "--wavevector_type", "int", "--wavevector", text, "--configs", str(cfg), "--bin_size", "1000",
+           "--outdir", str(out), "--id", tag] + extra
+    return subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, text=True), out
+
+
+@pytest.mark.gpu
+def test_batched_device_bins_through_the_cli(host_bins, orc, nthreads, tmp_path):
+    """pimcb_measure --batch: walker batches accumulated in the device-resident bin (no per-configuration read-back) give
+    the same ce-ssfq / ce-isf row as the per-configuration estimator path; with two GPUs, two ranks + one NCCL reduce."""
+    import torch
+    s = synth.Shape("bt", 3, 12, 20, 2.0, 0.02198, 0)
+    B, nq = 7, 9
+    batch = synth.gen_batch(s, B, first=90)
+    cfg = tmp_path / "beads.bin"
+    batch.tofile(cfg)
+    text = synth.int_wavevector_text(nq, 3)
+    q = orc.qvectors("int", text, s.side)
+    ssf = sum(orc.ssf(s.side, b, s.N, q) for b in batch) / (s.M * B)
+    isf = sum(orc.isf(b, s.N, q, nthreads=nthreads).reshape(-1) for b in batch) / (s.M * B)
+
+    def check(out, tag):
+        _, rows = read_dat(out / f"ce-ssfq-{tag}.dat")
+        assert len(rows) == 1
+        np.testing.assert_allclose([float(rows[0][16 * k:16 * k + 16]) for k in range(nq)], ssf, rtol=2e-8)
+        _, rows = read_dat(out / f"ce-isf-{tag}.dat")
+        np.testing.assert_allclose([float(rows[0][16 * k:16 * k + 16]) for k in range(nq * s.M)], isf, rtol=2e-8, atol=1e-8)
+
+    p, out = _run_batched(host_bins, tmp_path, s, cfg, text, "b1", ["--batch", "3"])
+    assert p.wait() == 0 and "bin of 7" in p.stdout.read()
+    check(out, "b1")
+    if torch.cuda.device_count() < 2:
+        return
+    idfile = tmp_path / "nccl.id"
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, PIMCB_DEVICE=str(r))
+        procs.append(_run_batched(host_bins, tmp_path, s, cfg, text, "b2",
+                                  ["--batch", "2", "--nranks", "2", "--rank", str(r), "--idfile", str(idfile)], env)[0])
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "bin of 7" in outs[0] and "measured 4" in outs[0] and "measured 3" in outs[1]
+    check(out, "b2")
