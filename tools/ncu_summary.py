@@ -114,9 +114,22 @@ def main():
         if hot:
             md += ["Hot spots (source page, SASS; `tools/ncu_hot.py`):", "", "```"] + hot + ["```", ""]
     if traffic:
-        traffic["source"] = f"ncu --set full --clock-control none, one launch each, tools/gpu_round.sh {tag} (64 C2 configurations per launch)"
-        with open(os.path.join(out, "traffic.json"), "w") as f:
-            json.dump(traffic, f, indent=1)
+        # kernels captured in this visit replace their entries; entries of kernels captured earlier stay
+        path = os.path.join(out, "traffic.json")
+        merged = {}
+        if os.path.exists(path):
+            try:
+                merged = json.load(open(path))
+            except ValueError:
+                merged = {}
+        src = merged.get("sources", {}) if isinstance(merged.get("sources"), dict) else {}
+        for k, v in traffic.items():
+            merged[k] = v
+            src[k] = tag
+        merged["sources"] = src
+        merged["source"] = "ncu --set full --clock-control none, one launch each (64 C2 configurations per launch); per-kernel visit tag in `sources`"
+        with open(path, "w") as f:
+            json.dump(merged, f, indent=1)
     with open(os.path.join(out, f"{tag}_kernels.md"), "w") as f:
         f.write("\n".join(md) + "\n")
     print("\n".join(md))
