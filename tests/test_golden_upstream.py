@@ -98,3 +98,40 @@ def test_cuda_matches_upstream_vectors(orc, name):
             c1, c2 = np.array(VF)[eo] * tau, 2.0 * np.array(GF)[eo] * tau ** 3 * lam
             for col, c in ((0, c1), (1, c2), (2, c1), (3, c2)):
                 assert_parity(vir[0][:, col] * c, g[f"{a}_vir"][:, col], f"{a} virial term {col} vs upstream vectors")
+
+
+@pytest.mark.gpu
+def test_cuda_full_c2_against_upstream_cpu_record(orc):
+    """The FULL C2 evaluation (N=256, M=170, 64 q; 1.2e11 pair terms on the CPU) as computed once by the upstream CPU code
+    (tests/golden/make_upstream_c2_full.py, ~40 core-minutes) against the CUDA path: every q, every tau."""
+    path = os.path.join(HERE, "golden", "upstream_c2_full.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/upstream_c2_full.npz not generated")
+    from pimc_b200 import api, synth
+    g = np.load(path)
+    s = synth.C2
+    beads = synth.gen_config(s.N, s.M, 3, s.rho, s.T, seed=int(g["seed"]), pad=3)
+    assert float(np.sum(beads[:, :s.N] * np.arange(1, 4))) == float(g["beads_checksum"]), "synthetic generator changed"
+    q = synth.commensurate_q(s.nq, s.side)
+    for mode in (1, 0):
+        with api.Context(0, 3) as ctx:
+            ctx.set_box(s.side)
+            ctx.set_qvecs(q)
+            ctx.set_rho_mode(mode)
+            ssf, isf = ctx.stage(beads, s.N).ssf_isf()
+        assert_parity(ssf[0], g["ssf"], f"full C2 S(q) vs the upstream CPU record (rho mode {mode})")
+        assert_parity(isf[0], g["isf"], f"full C2 F(q,tau) vs the upstream CPU record (rho mode {mode})")
+
+
+def test_oracle_full_c2_factorised_against_upstream_cpu_record(orc):
+    """CPU: the factorised oracle variant (the checker used at sizes where the direct loop takes hours) against the same
+    full-size upstream record."""
+    path = os.path.join(HERE, "golden", "upstream_c2_full.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/upstream_c2_full.npz not generated")
+    from pimc_b200 import synth
+    g = np.load(path)
+    s = synth.C2
+    beads = synth.gen_config(s.N, s.M, 3, s.rho, s.T, seed=int(g["seed"]), pad=3)
+    q = synth.commensurate_q(s.nq, s.side)
+    assert_parity(orc.isf_factorised(beads, s.N, q), g["isf"], "factorised oracle vs the full-size upstream CPU record")
