@@ -1162,6 +1162,23 @@ __device__ __forceinline__ double table_direct(const double* __restrict__ tab, i
     return __ldg(tab + k);
 }
 
+// Order in which a thread walks its ring of partners when it visits ALL of them (force loops: every pair is seen from
+// both ends and both visits read the same table entry).  Zig-zag (A/B switch, off): step 2m-1 -> partner i+m, step 2m ->
+// partner i-m, so the two visits of a pair are one step apart and the second could find the 32-byte sector in L1 instead
+// of going back to L2 / DRAM a whole ring later.  Measured on 64 C2 configurations (gpurun_out r01zz, profiles/
+// r01zz_ring_ab.txt): virial kernel 5.33 -> 5.19 ms, pair kernel 3.39 -> 3.76 ms -- the reuse does not materialise (the
+// sectors of ~10^3 gathers in flight per SM do not survive in L1) and the scattered partner order costs the pair kernel
+// more than it saves; the ascending ring stays.
+#ifndef PIMCB_RING_ZIGZAG
+#define PIMCB_RING_ZIGZAG 0
+#endif
+__device__ __forceinline__ int ring_partner(int step, int N, bool full_ring) {
+#if PIMCB_RING_ZIGZAG
+    if (full_ring) return (step & 1) ? (step + 1) >> 1 : N - (step >> 1);
+#endif
+    return step;
+}
+
 struct PairParams {
     const double* V; const double* dVdr; int len; double dr; double extV[2]; double extdV[2];
     double dSep; int want_hist; int f2_parity; int M;
@@ -1212,7 +1229,7 @@ __global__ void __launch_bounds__(256, PIMCB_PAIR_MINB) pair_kernel(const double
                 double r[U], sep[U][ND], vv[U], dv[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int kk = min(kk0 + u, klast);                      // surplus slots recompute the last partner
+                    const int kk = ring_partner(min(kk0 + u, klast), N, do_f2);   // surplus slots recompute the last partner
                     int j = i + kk;
                     if (j >= N) j -= N;
                     if (do_f2) {
@@ -1227,7 +1244,7 @@ __global__ void __launch_bounds__(256, PIMCB_PAIR_MINB) pair_kernel(const double
                     const int kidx = __double2int_rz(__ddiv_rn(r[u], pp.dr));
                     const bool inside = kidx > 0 && kidx < pp.len;
                     const bool live = kk0 + u <= klast;
-                    const bool vhalf = live && kk0 + u <= kv;
+                    const bool vhalf = live && ring_partner(kk0 + u, N, do_f2) <= kv;
                     vv[u] = 0.0;
                     dv[u] = 0.0;
                     if (vhalf) vv[u] = inside ? __ldg(pp.V + kidx) : (kidx <= 0 ? pp.extV[0] : pp.extV[1]);
@@ -1236,7 +1253,7 @@ __global__ void __launch_bounds__(256, PIMCB_PAIR_MINB) pair_kernel(const double
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const bool live = kk0 + u <= klast;
-                    const bool vhalf = live && kk0 + u <= kv;
+                    const bool vhalf = live && ring_partner(kk0 + u, N, do_f2) <= kv;
                     if (vhalf) {
                         vsum += vv[u];
                         if (pp.want_hist) {

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256, PIMCB_VIRIAL_MINB) virial_kernel(const do
                 double sep[U][ND], r[U], dv[U], d2[U];
 #pragma unroll
                 for (int w = 0; w < U; ++w) {
-                    int j = i + min(kk0 + w, N - 1);                              // surplus slots recompute the last partner
+                    int j = i + ring_partner(min(kk0 + w, N - 1), N, true);       // zig-zag ring (pair_kernel); surplus slots recompute the last partner
                     if (j >= N) j -= N;
                     r[w] = minimage_norm<ND>(xs, Npad, i, j, box, sep[w]);        // getSeparation(bead1, bead2)
                 }
