@@ -256,4 +256,286 @@ __global__ void __launch_bounds__(256, PIMCB_VIRIAL_MINB) virial_kernel(const do
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Symmetric form of the virial slice sums: every pair is visited ONCE.  The table entries of a pair are the same seen
+// from either end (r_ij = r_ji bit for bit), and the per-pair terms are antisymmetric (gV) or symmetric (T), so thread
+// i walks only the half ring k = 1..N/2, keeps its own side in registers and adds the partner's side into
+// shared-memory accumulators acc[component][j].  Within one ring step k all partners j = i + k are distinct, so a plain
+// read-add-write needs no atomics; a CTA barrier separates the steps (~N/2 barriers per slice against ~N^2/2 table
+// gathers).  Half the gathers of virial_kernel -- the gathers are what both kernels wait for.  Summation order is fixed
+// (own side in ring order, partner side in ring order), so results are reproducible; they differ from virial_kernel in
+// the last bits only.  PPT = particles per thread (N <= 256 * PPT).
+// ---------------------------------------------------------------------------------------------
+#ifndef PIMCB_VSYM_U
+#define PIMCB_VSYM_U 2
+#endif
+#ifndef PIMCB_VSYM_MINB
+#define PIMCB_VSYM_MINB 3
+#endif
+template <int ND, int PPT>
+__global__ void __launch_bounds__(256, PPT == 1 ? PIMCB_VSYM_MINB : (PPT == 2 ? 2 : 1))
+virial_sym_kernel(const double* __restrict__ pos, const double* __restrict__ delta, int nslices, int N, int Npad, BoxDev box,
+                  VirialParams vp, double* __restrict__ out) {
+    constexpr int NT = ND * (ND + 1) / 2;
+    constexpr int NC = ND + NT;                       // accumulated components per particle: gV then the upper triangle of T
+    constexpr int U = PIMCB_VSYM_U;
+    extern __shared__ __align__(16) double sm[];
+    double* xs = sm;                                  // [ND][Npad]
+    double* ds = sm + ND * Npad;                      // [ND][Npad] (delta)
+    double* acc = sm + 2 * ND * Npad;                 // [NC][Npad] partner-side accumulators
+    __shared__ double red[4][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int khalf = N / 2;
+    const bool evenN = (N & 1) == 0;
+    for (int sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
+        const int t = sl % vp.M;
+        const bool do_t2 = vp.t2_parity == -1 || (vp.t2_parity >= 0 && (t & 1) == vp.t2_parity);
+        load_slice(xs, pos + static_cast<size_t>(sl) * ND * Npad, ND * Npad);
+        if (delta) load_slice(ds, delta + static_cast<size_t>(sl) * ND * Npad, ND * Npad);
+        for (int k = threadIdx.x; k < NC * Npad; k += blockDim.x) acc[k] = 0.0;
+        __syncthreads();
+        double own[PPT][NC];
+#pragma unroll
+        for (int p = 0; p < PPT; ++p)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) own[p][c] = 0.0;
+        for (int kk0 = 1; kk0 <= khalf; kk0 += U) {
+            double sep[U][PPT][ND], r[U][PPT], dv[U][PPT], d2[U][PPT];
+            int jj[U][PPT];
+#pragma unroll
+            for (int w = 0; w < U; ++w)
+#pragma unroll
+                for (int p = 0; p < PPT; ++p) {
+                    const int i = threadIdx.x + 256 * p, kk = kk0 + w;
+                    // the pair (i, i + N/2) of an even ring belongs to the lower half only
+                    const bool valid = i < N && kk <= khalf && !(evenN && kk == khalf && i >= khalf);
+                    int j = i + kk;
+                    if (j >= N) j -= N;
+                    jj[w][p] = valid ? j : -1;
+                    r[w][p] = 1.0;
+                    if (valid) r[w][p] = minimage_norm<ND>(xs, Npad, i, j, box, sep[w][p]);     // getSeparation(bead1, bead2)
+                }
+#pragma unroll
+            for (int w = 0; w < U; ++w)
+#pragma unroll
+                for (int p = 0; p < PPT; ++p) {                                   // all gathers of the group are issued here
+                    dv[w][p] = 0.0;
+                    d2[w][p] = 0.0;
+                    if (jj[w][p] >= 0) {
+                        const int kidx = __double2int_rz(__ddiv_rn(r[w][p], vp.dr));
+                        const bool inside = kidx > 0 && kidx < vp.len;
+                        dv[w][p] = inside ? __ldg(vp.dVdr + kidx) : (kidx <= 0 ? vp.extdV[0] : vp.extdV[1]);
+                        if (do_t2) d2[w][p] = inside ? __ldg(vp.d2V + kidx) : (kidx <= 0 ? vp.extd2V[0] : vp.extd2V[1]);
+                    }
+                }
+#pragma unroll
+            for (int w = 0; w < U; ++w) {
+#pragma unroll
+                for (int p = 0; p < PPT; ++p) {
+                    const int j = jj[w][p];
+                    if (j < 0) continue;
+                    const double g = dv[w][p] / r[w][p];
+                    double gi[ND], g2 = 0.0;
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) {
+                        gi[d] = __dmul_rn(g, sep[w][p][d]);
+                        g2 = fma(gi[d], gi[d], g2);
+                        own[p][d] = __dadd_rn(own[p][d], gi[d]);
+                        acc[d * Npad + j] = __dsub_rn(acc[d * Npad + j], gi[d]);  // gradV(sep_ji) = -gradV(sep_ij)
+                    }
+                    if (do_t2) {
+                        const double dV = sqrt(g2);
+                        const double rinv = 1.0 / r[w][p];
+                        const double a = d2[w][p] * rinv * rinv - dV * rinv * rinv * rinv;
+                        const double diag = dV * rinv;
+                        int k = ND;
+#pragma unroll
+                        for (int pp = 0; pp < ND; ++pp)
+#pragma unroll
+                            for (int q = pp; q < ND; ++q, ++k) {
+                                const double m = fma(sep[w][p][pp] * sep[w][p][q], a, pp == q ? diag : 0.0);
+                                own[p][k] += m;
+                                acc[k * Npad + j] += m;
+                            }
+                    }
+                }
+                __syncthreads();                      // the next ring step targets other j: order the read-add-writes
+            }
+        }
+        double sums[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+            const int i = threadIdx.x + 256 * p;
+            if (i >= N) continue;
+            double gV[ND], T[NT];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) gV[d] = own[p][d] + acc[d * Npad + i];
+#pragma unroll
+            for (int k = 0; k < NT; ++k) T[k] = own[p][ND + k] + acc[(ND + k) * Npad + i];
+            double uu[ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) uu[d] = 0.0;
+            {
+                int k = 0;
+#pragma unroll
+                for (int pp = 0; pp < ND; ++pp)
+#pragma unroll
+                    for (int q = pp; q < ND; ++q, ++k) {
+                        uu[pp] = fma(T[k], gV[q], uu[pp]);
+                        if (q != pp) uu[q] = fma(T[k], gV[pp], uu[q]);
+                    }
+            }
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                const double x = xs[d * Npad + i];
+                sums[0] = fma(gV[d], x, sums[0]);
+                sums[1] = fma(uu[d], x, sums[1]);
+                if (delta) {
+                    const double dl = ds[d * Npad + i];
+                    sums[2] = fma(gV[d], dl, sums[2]);
+                    sums[3] = fma(uu[d], dl, sums[3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double v = sums[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red[k][warp] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            double v = 0.0;
+            for (int w = 0; w < (blockDim.x >> 5); ++w) v += red[threadIdx.x][w];
+            out[static_cast<size_t>(sl) * 4 + threadIdx.x] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Symmetric form of pair_kernel<ND, true>: on the slices that carry the gradient correction every pair is visited ONCE
+// (half ring); the visiting thread keeps its own side of the force in registers and subtracts the partner's side in a
+// shared-memory accumulator (distinct partners within a ring step, CTA barrier between steps) -- two table gathers per
+// pair (V, dV/dr) instead of three.  Slices without the correction run the same half ring without accumulators or
+// barriers.  Vint, the table indices and sepHist are bit-identical to pair_kernel (same r, same order of the V sum for
+// N <= 256); gradVSquared differs in the last bits (other summation order) and is reproducible.
+// ---------------------------------------------------------------------------------------------
+template <int ND, int PPT>
+__global__ void __launch_bounds__(256, PPT == 1 ? 4 : (PPT == 2 ? 2 : 1))
+pair_sym_kernel(const double* __restrict__ pos, int nslices, int N, int Npad, BoxDev box, PairParams pp, double* __restrict__ vint,
+                double* __restrict__ f2, int* __restrict__ hist) {
+    constexpr int U = 2;
+    extern __shared__ __align__(16) double sm[];
+    double* xs = sm;                                  // [ND][Npad]
+    double* acc = sm + ND * Npad;                     // [ND][Npad] partner-side force accumulators
+    __shared__ double redV[8], redF[8];
+    __shared__ int shist[kNPCFSEP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int khalf = N / 2;
+    const bool evenN = (N & 1) == 0;
+    for (int sl = blockIdx.x; sl < nslices; sl += gridDim.x) {
+        const int t = sl % pp.M;
+        const bool do_f2 = pp.f2_parity < 0 || (t & 1) == pp.f2_parity;
+        load_slice(xs, pos + static_cast<size_t>(sl) * ND * Npad, ND * Npad);
+        if (threadIdx.x < kNPCFSEP) shist[threadIdx.x] = 0;
+        if (do_f2)
+            for (int k = threadIdx.x; k < ND * Npad; k += blockDim.x) acc[k] = 0.0;
+        __syncthreads();
+        double vsum = 0.0, own[PPT][ND];
+#pragma unroll
+        for (int p = 0; p < PPT; ++p)
+#pragma unroll
+            for (int d = 0; d < ND; ++d) own[p][d] = 0.0;
+        for (int kk0 = 1; kk0 <= khalf; kk0 += U) {
+            double sep[U][PPT][ND], r[U][PPT], vv[U][PPT], dv[U][PPT];
+            int jj[U][PPT];
+#pragma unroll
+            for (int w = 0; w < U; ++w)
+#pragma unroll
+                for (int p = 0; p < PPT; ++p) {
+                    const int i = threadIdx.x + 256 * p, kk = kk0 + w;
+                    const bool valid = i < N && kk <= khalf && !(evenN && kk == khalf && i >= khalf);
+                    int j = i + kk;
+                    if (j >= N) j -= N;
+                    jj[w][p] = valid ? j : -1;
+                    r[w][p] = 1.0;
+                    if (valid) {
+                        if (do_f2) {
+                            r[w][p] = minimage_norm<ND>(xs, Npad, i, j, box, sep[w][p]);            // getSeparation(bead1,bead2), action.cpp:1211
+                        } else {
+                            const int lo = min(i, j), hi = max(i, j);
+                            r[w][p] = minimage_norm<ND>(xs, Npad, hi, lo, box, sep[w][p]);          // getSeparation(bead2,bead1), action.cpp:934
+                        }
+                    }
+                }
+#pragma unroll
+            for (int w = 0; w < U; ++w)
+#pragma unroll
+                for (int p = 0; p < PPT; ++p) {                                   // all gathers of the group are issued here
+                    vv[w][p] = 0.0;
+                    dv[w][p] = 0.0;
+                    if (jj[w][p] >= 0) {
+                        const int kidx = __double2int_rz(__ddiv_rn(r[w][p], pp.dr));
+                        const bool inside = kidx > 0 && kidx < pp.len;
+                        vv[w][p] = inside ? __ldg(pp.V + kidx) : (kidx <= 0 ? pp.extV[0] : pp.extV[1]);
+                        if (do_f2) dv[w][p] = inside ? __ldg(pp.dVdr + kidx) : (kidx <= 0 ? pp.extdV[0] : pp.extdV[1]);
+                    }
+                }
+#pragma unroll
+            for (int w = 0; w < U; ++w) {
+#pragma unroll
+                for (int p = 0; p < PPT; ++p) {
+                    const int j = jj[w][p];
+                    if (j < 0) continue;
+                    vsum += vv[w][p];
+                    if (pp.want_hist) {
+                        const int nR = __double2int_rz(__ddiv_rn(r[w][p], pp.dSep));               // action.cpp:221
+                        if (nR >= 0 && nR < kNPCFSEP) atomicAdd(&shist[nR], 1);
+                    }
+                    if (do_f2) {
+                        const double g = __ddiv_rn(dv[w][p], r[w][p]);
+#pragma unroll
+                        for (int d = 0; d < ND; ++d) {
+                            own[p][d] = fma(g, sep[w][p][d], own[p][d]);
+                            acc[d * Npad + j] = fma(-g, sep[w][p][d], acc[d * Npad + j]);          // gradV(sep_ji) = -gradV(sep_ij)
+                        }
+                    }
+                }
+                if (do_f2) __syncthreads();           // the next ring step targets other partners: order the read-add-writes
+            }
+        }
+        double fsum = 0.0;
+        if (do_f2) {
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) {
+                const int i = threadIdx.x + 256 * p;
+                if (i >= N) continue;
+#pragma unroll
+                for (int d = 0; d < ND; ++d) {
+                    double F = own[p][d] + acc[d * Npad + i];
+                    if (pp.gext) F += __ldg(pp.gext + static_cast<size_t>(sl) * ND * Npad + d * Npad + i);   // action.cpp:1216
+                    fsum = fma(F, F, fsum);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+            fsum += __shfl_xor_sync(0xffffffffu, fsum, o);
+        }
+        if (lane == 0) { redV[warp] = vsum; redF[warp] = fsum; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double v = 0.0, f = 0.0;
+            for (int w = 0; w < (blockDim.x >> 5); ++w) { v += redV[w]; f += redF[w]; }
+            vint[sl] = v;
+            if (f2) f2[sl] = f;
+        }
+        if (pp.want_hist && threadIdx.x < kNPCFSEP) hist[static_cast<size_t>(sl) * kNPCFSEP + threadIdx.x] = shist[threadIdx.x];
+        __syncthreads();
+    }
+}
+
 }  // namespace pimcb

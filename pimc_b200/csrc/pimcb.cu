@@ -1361,7 +1361,20 @@ int pimcb_pair_sums(pimcb_ctx* c, double* vint, double* f2, int* sephist, double
         rc = set_smem(pair_kernel<ND, F2>, smem); if (rc) return rc;                                               \
         pair_kernel<ND, F2><<<grid, 256, smem, c->stream>>>(s->pos.as<double>(), nsl, s->N, s->Npad, c->box, pp,  \
                                                             c->d_vint.as<double>(), c->d_f2.as<double>(), c->d_hist.as<int>())
-        if (f2) {
+        // force slices: every pair once (pair_sym_kernel) when the slice fits its particles-per-thread variants;
+        // PIMCB_PAIR_SYM=0 forces the both-ends kernel (A/B)
+        static const bool sym_on = !(std::getenv("PIMCB_PAIR_SYM") && std::atoi(std::getenv("PIMCB_PAIR_SYM")) == 0);
+        const size_t smem_sym = sizeof(double) * 2 * nd * s->Npad;
+        if (f2 && sym_on && s->N <= 1024 && smem_sym <= 200 * 1024) {
+#define LAUNCH_PSYM(ND, PPT)                                                                                       \
+            rc = set_smem(pair_sym_kernel<ND, PPT>, smem_sym); if (rc) return rc;                                   \
+            pair_sym_kernel<ND, PPT><<<grid, 256, smem_sym, c->stream>>>(s->pos.as<double>(), nsl, s->N, s->Npad, c->box, pp, \
+                                                                         c->d_vint.as<double>(), c->d_f2.as<double>(), c->d_hist.as<int>())
+#define LAUNCH_PSYM_P(ND) if (s->N <= 256) { LAUNCH_PSYM(ND, 1); } else if (s->N <= 512) { LAUNCH_PSYM(ND, 2); } else { LAUNCH_PSYM(ND, 4); }
+            if (nd == 1) { LAUNCH_PSYM_P(1) } else if (nd == 2) { LAUNCH_PSYM_P(2) } else { LAUNCH_PSYM_P(3) }
+#undef LAUNCH_PSYM_P
+#undef LAUNCH_PSYM
+        } else if (f2) {
             if (nd == 1) { LAUNCH_PAIR(1, true); } else if (nd == 2) { LAUNCH_PAIR(2, true); } else { LAUNCH_PAIR(3, true); }
         } else {
             if (nd == 1) { LAUNCH_PAIR(1, false); } else if (nd == 2) { LAUNCH_PAIR(2, false); } else { LAUNCH_PAIR(3, false); }
@@ -1478,12 +1491,28 @@ int pimcb_virial_sums(pimcb_ctx* c, const double* delta_aos, int t2_parity, doub
                     {c->extd2V[0], c->extd2V[1]}, t2_parity, s->M};
     {
         KTimer kt(c, K_VIRIAL);
+        // symmetric kernel (every pair once, partner side accumulated in shared memory) when the slice fits its
+        // particles-per-thread variants; PIMCB_VIRIAL_SYM=0 forces the both-ends kernel (A/B)
+        static const bool sym_on = !(std::getenv("PIMCB_VIRIAL_SYM") && std::atoi(std::getenv("PIMCB_VIRIAL_SYM")) == 0);
+        const int nc = nd + nd * (nd + 1) / 2;
+        const size_t smem_sym = sizeof(double) * (2 * nd + nc) * s->Npad;
+        if (sym_on && s->N <= 1024 && smem_sym <= 200 * 1024) {
+#define LAUNCH_VSYM(ND, PPT)                                                                                       \
+            rc = set_smem(virial_sym_kernel<ND, PPT>, smem_sym); if (rc) return rc;                                 \
+            virial_sym_kernel<ND, PPT><<<nsl, 256, smem_sym, c->stream>>>(s->pos.as<double>(), d_delta, nsl, s->N, s->Npad, c->box, vp, \
+                                                                          c->d_vir.as<double>())
+#define LAUNCH_VSYM_P(ND) if (s->N <= 256) { LAUNCH_VSYM(ND, 1); } else if (s->N <= 512) { LAUNCH_VSYM(ND, 2); } else { LAUNCH_VSYM(ND, 4); }
+            if (nd == 1) { LAUNCH_VSYM_P(1) } else if (nd == 2) { LAUNCH_VSYM_P(2) } else { LAUNCH_VSYM_P(3) }
+#undef LAUNCH_VSYM_P
+#undef LAUNCH_VSYM
+        } else {
         const size_t smem = sizeof(double) * 2 * nd * s->Npad;
 #define LAUNCH_VIR(ND)                                                                                             \
         rc = set_smem(virial_kernel<ND>, smem); if (rc) return rc;                                                  \
         virial_kernel<ND><<<nsl, 256, smem, c->stream>>>(s->pos.as<double>(), d_delta, nsl, s->N, s->Npad, c->box, vp, c->d_vir.as<double>())
         if (nd == 1) { LAUNCH_VIR(1); } else if (nd == 2) { LAUNCH_VIR(2); } else { LAUNCH_VIR(3); }
 #undef LAUNCH_VIR
+        }
         CU(cudaGetLastError());
     }
     CU(cudaEventRecord(s->consumed, c->stream));

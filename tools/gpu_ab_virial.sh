@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-for v in zz0 zz1 zz0 zz1; do PIMCB_LIB_PATH=$PWD/pimc_b200/variants/libpimc_b200_$v.so python tools/virial_ab.py 2>&1 | tail -1; done | tee gpurun_out/r01zz_ring_ab.txt
-python -m pytest tests/test_gpu_parity.py tests/test_variants.py tests/test_reference_cpu.py tests/test_golden.py -m gpu -q -k "pair or virial or upstream or golden" 2>&1 | tail -5 | tee gpurun_out/r01zz_pytest.log
+for v in 1 0 1 0; do PIMCB_PAIR_SYM=$v python tools/virial_ab.py 2>&1 | tail -1 | sed "s/^/pair_sym=$v /"; done | tee gpurun_out/r01ps_pair_sym_ab.txt
+python -m pytest tests -m gpu -q -k "pair or golden or upstream or energy or plugin or virial or external or smoke" 2>&1 | tail -5 | tee gpurun_out/r01ps_pytest.log
