@@ -596,10 +596,13 @@ def run_ours(args, shape, q):
         ctx.set_profiling(False)
         p_s = pms * 1e-3 / max(1, pn)
         pairs = shape.N * (shape.N - 1) // 2               # pairs per slice
-        # gsf action: even slices read V once per pair; odd slices walk the full j != i loop (2 visits per pair, each
-        # reads dV/dr, half of them also read V): 3 table reads per pair
-        gathers = B * ((shape.M - shape.M // 2) * pairs + (shape.M // 2) * 3 * pairs)
+        # gsf action: even slices read V once per pair; odd slices read V and dV/dr once per pair in the symmetric kernel
+        # (pair_sym_kernel), or walk the full j != i loop in the both-ends kernel (2 visits per pair, each reads dV/dr,
+        # half of them also read V: 3 table reads per pair)
+        pair_sym = os.environ.get("PIMCB_PAIR_SYM", "1") != "0" and shape.N <= 1024      # every pair once on the force slices
+        gathers = B * ((shape.M - shape.M // 2) * pairs + (shape.M // 2) * (2 if pair_sym else 3) * pairs)
         pair = {"metric": "pair-potential action sums/s (Vint[M] + gradVSquared[odd slices] + sepHist[M][50] per configuration)",
+                "kernel": "pair_sym_kernel (force slices: every pair once)" if pair_sym else "pair_kernel (force slices: both ends)",
                 "value": B / p_s, "unit": "configurations/s", "avg_launch_ms": p_s * 1e3, "launches_timed": pn,
                 "table_entries": len(Vt), "table_mb": 2 * 8 * len(Vt) / 1e6,
                 "gathers_per_launch": gathers, "gather_rate_g_per_s": gathers / p_s / 1e9,
@@ -622,8 +625,10 @@ def run_ours(args, shape, q):
         vms, vn = ctx.kernel_times(reset=True)["virial"]
         ctx.set_profiling(False)
         v_s = vms * 1e-3 / max(1, vn)
-        vg = B * shape.N * (shape.N - 1) * (shape.M + shape.M // 2)          # dV/dr on every slice, d2V/dr2 on odd ones
+        vir_sym = os.environ.get("PIMCB_VIRIAL_SYM", "1") != "0" and shape.N <= 1024
+        vg = B * shape.N * (shape.N - 1) * (shape.M + shape.M // 2) // (2 if vir_sym else 1)   # dV/dr on every slice, d2V/dr2 on odd ones
         pair["virial_sums"] = {"metric": "virial slice sums/s (4 sums per slice; gsf action, window deltas from the host)",
+                               "kernel": "virial_sym_kernel (every pair once)" if vir_sym else "virial_kernel (both ends)",
                                "value": B / v_s, "unit": "configurations/s", "avg_launch_ms": v_s * 1e3, "launches_timed": vn,
                                "gathers_per_launch": vg, "gather_rate_g_per_s": vg / v_s / 1e9,
                                "bound": "L2/HBM gather (same tables as the pair kernel + d2V/dr2)"}
