@@ -16,8 +16,8 @@ ncu --set full --clock-control none --import-source on -k regex:rho_lattice_mma 
 ncu --set full --clock-control none --import-source on -k regex:rho_generic -s 4 -c 1 -f -o $OUT/${TAG}_prof_rho_generic python bench.py $BARGS --no-e2e --rho-mode 0 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:isf_corr -s 4 -c 1 -f -o $OUT/${TAG}_prof_corr python bench.py $BARGS --no-e2e > /dev/null 2>&1
 ls -la $OUT
-ncu --set full --clock-control none --import-source on -k regex:pair_kernel -s 2 -c 1 -f -o $OUT/${TAG}_prof_pair python bench.py --steps 4 --warmup 3 --no-cpu-baseline --peak-seconds 0.02 --no-ab --no-e2e > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:pair_sym_kernel -s 2 -c 1 -f -o $OUT/${TAG}_prof_pair python bench.py --steps 4 --warmup 3 --no-cpu-baseline --peak-seconds 0.02 --no-ab --no-e2e > /dev/null 2>&1
 ls -la $OUT | tail -12
-ncu --set full --clock-control none --import-source on -k regex:virial_kernel -c 1 -f -o $OUT/${TAG}_prof_virial python bench.py --steps 4 --warmup 3 --no-cpu-baseline --peak-seconds 0.02 --no-ab --no-e2e > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:virial_sym_kernel -c 1 -f -o $OUT/${TAG}_prof_virial python bench.py --steps 4 --warmup 3 --no-cpu-baseline --peak-seconds 0.02 --no-ab --no-e2e > /dev/null 2>&1
 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_bench_ref.json 2>> $OUT/${TAG}_bench.err; cat $OUT/${TAG}_bench_ref.json
 ls -la $OUT | tail -14
