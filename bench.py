@@ -608,7 +608,8 @@ def run_ours(args, shape, q):
                 "gathers_per_launch": gathers, "gather_rate_g_per_s": gathers / p_s / 1e9,
                 "sector_traffic_tbs": 32.0 * gathers / p_s / 1e12,
                 "bound": "L2/HBM gather: 8-byte table reads move 32-byte sectors; the 106 MB of tables exceed what one L2 "
-                         "partition keeps, ncu shows 6.3 GB of DRAM reads per launch (profiles/traffic.json)"}
+                         "partition keeps, ncu shows 4.5 GB of DRAM reads per launch for the symmetric kernel, 6.4 GB for the "
+                         "both-ends kernel (profiles/traffic.json)"}
 
     # ---- secondary: virial slice sums (rDOTgradU / deltaDOTgradU, gsf: T-matrix terms on odd slices) ---------------
     if pair is not None:
