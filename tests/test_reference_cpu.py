@@ -263,3 +263,32 @@ def test_cuda_external_gradient_against_upstream_cpu_code(orc):
         assert np.array_equal(hist[b], r["sephist"])
     assert np.array_equal(f2_free, f2_cleared) and np.array_equal(f2_restaged, f2_free[::-1])
     assert not np.allclose(f2_free, f2, rtol=1e-3)
+
+
+def test_extraction_recipe_finds_every_upstream_definition(tmp_path):
+    """The build-time recipes locate each upstream definition by its signature; a silent mismatch would compile the wrong
+    body.  With the upstream tree present: every manifest pattern matches exactly one line, and every cut ends on the brace
+    that closes it (balanced braces in the cut text)."""
+    import importlib.util
+    import os
+    import re
+    ref = "/root/reference"
+    if not os.path.exists(os.path.join(ref, "src", "estimator.cpp")):
+        pytest.skip("upstream tree not present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("ref_cpu_extract", os.path.join(root, "oracle", "ref_cpu_extract.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for name, (path, pats) in mod.MANIFEST.items():
+        lines = open(os.path.join(ref, path)).read().split("\n")
+        for pat in pats:
+            hits = [i for i, l in enumerate(lines) if re.search(pat, l)]
+            assert len(hits) == 1, f"{path}: {pat!r} matches {len(hits)} lines"
+            _, body = mod.body(lines, pat)
+            depth, in_c = 0, False
+            for l in body:
+                text, in_c = mod.strip_code(l, in_c)
+                depth += text.count("{") - text.count("}")
+            assert depth == 0 and len(body) >= 3, f"{path}: {pat!r} cut is unbalanced"
+    mod.main(ref, str(tmp_path))
+    assert sorted(os.listdir(tmp_path)) == sorted(mod.MANIFEST)
