@@ -1137,8 +1137,30 @@ int fused_capture(pimcb_ctx* c, const double* beads, int M, int N, int Next, dou
     const long launches0 = c->launches;
     bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
     if (ok) {
-        ok = cudaMemcpyAsync(s.aos.p, beads, aos_bytes, cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
-        s.needs_transpose = true;
+        // Small configurations: the transpose kernel reads the page-locked source over the host link itself (zero copy)
+        // instead of a DMA into the landing buffer followed by the transpose -- one node and one dependency less.
+        // Measured per call (tools/latency_ab.py, profiles/r01zc_zerocopy.txt): C1 (55 KB) 48 -> 37.5 us, C2 (1.03 MB)
+        // 79.6 -> 74.7 us, C4 (7.7 MB) 320 -> 337 us: SM-issued reads do not reach the DMA engine's link rate on large
+        // arrays, so the zero-copy form is used up to 2 MB.  PIMCB_ZEROCOPY=0 / 1 forces it off / on.
+        static const int zc_env = std::getenv("PIMCB_ZEROCOPY") ? std::atoi(std::getenv("PIMCB_ZEROCOPY")) : -1;
+        const bool zerocopy = zc_env < 0 ? aos_bytes <= (2u << 20) : zc_env != 0;
+        void* mapped = nullptr;
+        if (zerocopy && cudaHostGetDevicePointer(&mapped, const_cast<double*>(beads), 0) == cudaSuccess && mapped) {
+            const size_t tsmem = sizeof(double) * N * nd;
+            const int nslc = M;
+            const int tgrid = std::min(nslc, c->sm_count * 8);
+            const double* src = static_cast<const double*>(mapped);
+            if (nd == 1) { set_smem(aos_to_soa_kernel<1>, tsmem); aos_to_soa_kernel<1><<<tgrid, 256, tsmem, c->stream>>>(src, s.pos.as<double>(), nslc, N, Next, Npad); }
+            else if (nd == 2) { set_smem(aos_to_soa_kernel<2>, tsmem); aos_to_soa_kernel<2><<<tgrid, 256, tsmem, c->stream>>>(src, s.pos.as<double>(), nslc, N, Next, Npad); }
+            else { set_smem(aos_to_soa_kernel<3>, tsmem); aos_to_soa_kernel<3><<<tgrid, 256, tsmem, c->stream>>>(src, s.pos.as<double>(), nslc, N, Next, Npad); }
+            ok = cudaGetLastError() == cudaSuccess;
+            c->launches++;
+            s.needs_transpose = false;
+        } else {
+            cudaGetLastError();
+            ok = cudaMemcpyAsync(s.aos.p, beads, aos_bytes, cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
+            s.needs_transpose = true;
+        }
         ok = ok && materialize(c, s) == 0;
         ok = ok && launch_rho(c, s) == 0;
         ok = ok && launch_corr(c, s) == 0;
