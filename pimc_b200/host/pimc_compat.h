@@ -225,6 +225,17 @@ public:
     double tailV = 0.0;
 };
 class FreePotential : public PotentialBase {};
+// A non-trivial external potential for exercising the gradient coupling in the stand-alone tools: V = k r^2 / 2
+// (upstream's HarmonicPotential has the same form with k = omega^2 / (2 lambda), src/potential.cpp).
+class SpringPotential : public PotentialBase {
+public:
+    explicit SpringPotential(double k_) : k(k_) {}
+    double V(const dVec& r) override { return 0.5 * k * dot(r, r); }
+    dVec gradV(const dVec& r) override { dVec g; for (int i = 0; i < NDIM; ++i) g[i] = k * r[i]; return g; }
+    double grad2V(const dVec&) override { return NDIM * k; }
+private:
+    double k;
+};
 
 // Flat view of a TabulatedPotential (include/potential.h:148-157); upstream the members are protected and a
 // 3-line public accessor returning this struct is the only change the potential classes need.

@@ -91,7 +91,11 @@ int main(int argc, char** argv) {
     MTRand random;
     const bool wantPotential = flag(argc, argv, "--potential");
 
-    FreePotential external;
+    // --spring k: external potential V = k r^2 / 2 instead of `free` (its gradient couples to the pair forces in gradVSquared)
+    FreePotential freeExternal;
+    SpringPotential spring(std::atof(arg(argc, argv, "--spring", "0")));
+    PotentialBase& external = std::atof(arg(argc, argv, "--spring", "0")) != 0.0 ? static_cast<PotentialBase&>(spring)
+                                                                                  : static_cast<PotentialBase&>(freeExternal);
     std::unique_ptr<AzizPotential> aziz;
     std::unique_ptr<LocalActionB200> action;
     if (wantPotential) {

@@ -407,3 +407,34 @@ def test_batched_device_bins_through_the_cli(host_bins, orc, nthreads, tmp_path)
     assert all(p.returncode == 0 for p in procs), outs
     assert "bin of 7" in outs[0] and "measured 4" in outs[0] and "measured 3" in outs[1]
     check(out, "b2")
+
+
+@pytest.mark.gpu
+def test_external_potential_through_the_action_adaptor(host_bins, orc, nthreads, tmp_path):
+    """LocalActionB200 with a non-trivial external potential (pimcb_measure --spring k): Vext summed on the host through the
+    PotentialBase interface, gradVext uploaded per bead and added to the pair forces inside gradVSquared on the device;
+    potentialAction and the per-slice gradVSquared against the oracle."""
+    s = synth.Shape("xp", 3, 16, 12, 2.0, 0.02198, 0)
+    B, k = 2, 35.0
+    batch = synth.gen_batch(s, B, first=61, pad=1)
+    cfg = tmp_path / "beads.bin"
+    batch.tofile(cfg)
+    out = tmp_path / "OUTPUT"
+    subprocess.run([os.path.join(host_bins, "pimcb_measure3d"), "-N", str(s.N), "-n", repr(s.rho), "-T", repr(s.T), "-P", str(s.M),
+                    "--extent", str(s.N + 1), "--wavevector_type", "int", "--wavevector", "1 0 0", "--configs", str(cfg),
+                    "--outdir", str(out), "--id", "x", "--potential", "--action", "li_broughton", "--spring", repr(k)], check=True)
+    V, dV, dr = orc.aziz_table(orc.max_sep(s.side))
+    dSep = 0.5 * math.sqrt(3) * s.side[2] / 50
+    _, prow = read_dat(out / "ce-potential-x.dat")
+    assert len(prow) == B
+    for b in range(B):
+        vals = np.array([float(x) for x in prow[b].split()])
+        cv, _, _ = orc.pair_sums(s.side, batch[b], s.N, V, dV, dr, dSep, nthreads=nthreads)
+        f2 = orc.grad_v_squared_ext(s.side, batch[b], s.N, dV, dr, k * batch[b])
+        vext = 0.5 * k * np.sum(batch[b][:, :s.N] ** 2, axis=(1, 2))
+        U = orc.potential_action(cv + vext, f2, [1.0, 1.0], [1 / 12, 1 / 12], s.tau, synth.LAMBDA_HE4)
+        assert vals[0] == pytest.approx(U, rel=1e-10)
+        np.testing.assert_allclose(vals[1:1 + s.M], cv, rtol=1e-10)
+        np.testing.assert_allclose(vals[1 + s.M:], f2, rtol=1e-10)
+        f2_free = orc.grad_v_squared_ext(s.side, batch[b], s.N, dV, dr, 0.0 * batch[b])
+        assert not np.allclose(f2, f2_free, rtol=1e-3)
