@@ -164,6 +164,31 @@ def test_oracle_virial_energy_thermodynamic_column_matches_energy_estimator(orc,
     np.testing.assert_allclose(cols["Ecv*Beta"], clean[4] * s.M * s.tau, rtol=1e-13)
 
 
+def test_symmetric_half_ring_index_logic():
+    """The every-pair-once force kernels (pair_sym_kernel / virial_sym_kernel) walk the half ring k = 1..N/2 with 256
+    threads, PPT particles per thread and two ring steps per group: mirrored here index for index -- every unordered pair
+    exactly once, and all partners of one ring step distinct (the read-add-write into the shared-memory accumulators needs
+    no atomics)."""
+    for N in (1, 2, 3, 16, 37, 255, 256, 257, 300, 511, 512, 700, 1024):
+        PPT = 1 if N <= 256 else (2 if N <= 512 else 4)
+        khalf, even = N // 2, N % 2 == 0
+        seen = {}
+        for kk0 in range(1, khalf + 1, 2):
+            for w in range(2):
+                targets = []
+                for tid in range(256):
+                    for p in range(PPT):
+                        i, kk = tid + 256 * p, kk0 + w
+                        if not (i < N and kk <= khalf and not (even and kk == khalf and i >= khalf)):
+                            continue
+                        j = i + kk - (N if i + kk >= N else 0)
+                        targets.append(j)
+                        key = (min(i, j), max(i, j))
+                        seen[key] = seen.get(key, 0) + 1
+                assert len(targets) == len(set(targets)), (N, kk0, w)
+        assert len(seen) == N * (N - 1) // 2 and all(v == 1 for v in seen.values()), N
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # GPU: CUDA path vs oracle
 # ------------------------------------------------------------------------------------------------------------------
@@ -291,3 +316,28 @@ def test_virial_energy_from_device_sums(api, orc, nthreads):
     cvir = orc.virial_sums(s.side, beads, s.N, window, dV, d2V, dr, t2_parity=1, next_links=links, nthreads=nthreads)
     ref = orc.virial_energy(s.side, beads, s.N, window, cvir, cv, cf, VF, GF, s.tau, LAM, tail, next_links=links)
     np.testing.assert_allclose(got, ref, rtol=1e-10, atol=1e-10 * np.max(np.abs(ref)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [300, 600])
+def test_force_kernels_with_several_particles_per_thread(api, orc, nthreads, N):
+    """N > 256: the every-pair-once kernels run with 2 / 4 particles per thread (pair sums, sepHist, gradVSquared, virial)."""
+    s = synth.Shape("pp", 3, N, 4, 2.0, 0.02198, 0)
+    beads = synth.gen_config(s.N, s.M, 3, s.rho, s.T, seed=123, pad=1)
+    V, dV, d2V, dr = orc.aziz_table(orc.max_sep(s.side), second=True)
+    dSep = 0.5 * math.sqrt(3) * s.side[2] / 50
+    window = 2
+    delta = orc.virial_delta(s.side, beads, s.N, window)
+    with api.Context(0, 3) as ctx:
+        ctx.set_box(s.side)
+        ctx.set_pair_table(V, dV, dr)
+        ctx.set_pair_table_d2(d2V)
+        vint, f2, hist = ctx.stage(beads, s.N).pair_sums(dSep)
+        vir = ctx.virial_sums(delta, t2_parity=-1)
+    cv, cf, ch = orc.pair_sums(s.side, beads, s.N, V, dV, dr, dSep, nthreads=nthreads)
+    assert np.array_equal(hist[0], ch)
+    assert_parity(vint[0], cv, f"N={N} Vint")
+    assert_parity(f2[0], cf, f"N={N} gradVSquared")
+    ref = orc.virial_sums(s.side, beads, s.N, window, dV, d2V, dr, t2_parity=-1, nthreads=nthreads)
+    for k in range(4):
+        assert_parity(vir[0][:, k], ref[:, k], f"N={N} virial term {k}")
