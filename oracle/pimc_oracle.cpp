@@ -22,8 +22,8 @@
 //    (oracle/ref_cpu_extract.py) and compiled into oracle/_ref/librefcpu<NDIM>d.so (oracle/ref_cpu_shim.cpp);
 //    tests/test_reference_cpu.py holds this file array_equal to them on q-sets, S(q), F(q,tau), Vint, gradVSquared,
 //    sepHist, and within 1e-11 on the derived quantities.
-//  * Still unpinned by reference code: the %16.8E row formatting (boost::format upstream) and the state-file text
-//    format; closed-form known-answer tests (tests/test_oracle_kat.py, tests/test_variants.py) cover the rest again.
+//  * Still unpinned by reference code: the %16.8E row formatting (boost::format upstream); the state-file array text
+//    (oracle/statefile.py) IS pinned against the upstream stream operators.  Closed-form known-answer tests (tests/test_oracle_kat.py, tests/test_variants.py) cover the rest again.
 //
 // Every function cites the reference file:line (relative to the upstream tree) whose
 // arithmetic it follows.  Floating-point semantics: this file is compiled with

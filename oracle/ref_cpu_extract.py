@@ -10,7 +10,8 @@ located by its signature and cut at the brace that closes it (comments and strin
 
     include/container.h   Container::putInBC                                  (member body, pasted inside the stand-in class)
     include/path.h        Path::getSeparation, Path::getVelocity
-    include/common.h      enumerate, all_impl / all (bead comparison), apply_matrix_vector_product
+    include/common.h      enumerate, all_impl / all (bead comparison), apply_matrix_vector_product, the stream operators of
+                          std::array and DynamicArray<T,2> (the text format of the state files)
     src/worm.cpp          Worm::factor(state, bead)
     src/action.cpp        ActionBase::updateSepHist, LocalAction::potentialAction(), derivPotentialActionTau(int),
                           secondderivPotentialActionTau(int), derivPotentialActionLambda(int), V(int slice),
@@ -80,6 +81,12 @@ MANIFEST = {
     "path_inline.inc": ("include/path.h", [r"^inline dVec Path::getSeparation\s*\(", r"^inline dVec Path::getVelocity\s*\("]),
     "common_helpers.inc": ("include/common.h", [r"^constexpr auto enumerate\s*\(T && iterable\)", r"^void apply_matrix_vector_product\s*\(", r"^constexpr bool all_impl\s*\(",
                                                 r"^constexpr bool all\s*\(const std::array<T, N>& a, const std::array<T, N>& b\)"]),
+    "common_stream.inc": ("include/common.h", [
+        r"^std::ostream& operator<<\(std::ostream& os, const std::array<T, N>& arr\)",
+        r"^std::ostream& operator<<\(std::ostream& os, const DynamicArray<T, 2>& arr\)",
+        r"^std::istream& operator>>\(std::istream& is, std::array<T, N>& a\)",
+        r"^std::istream& operator>>\(std::istream& is, DynamicArray<T, 2>& arr\)",
+    ]),
     "worm.inc": ("src/worm.cpp", [r"^double Worm::factor\s*\(const beadState state1, const beadLocator &bead2\)"]),
     "action.inc": ("src/action.cpp", [
         r"^inline void ActionBase::updateSepHist\s*\(",
@@ -108,7 +115,11 @@ MANIFEST = {
     ]),
 }
 # template headers sit on the line above the signature
-TEMPLATE_PREFIX = {r"^constexpr auto enumerate\s*\(T && iterable\)": 3, r"^void apply_matrix_vector_product\s*\(": 1, r"^constexpr bool all_impl\s*\(": 1,
+TEMPLATE_PREFIX = {r"^std::ostream& operator<<\(std::ostream& os, const std::array<T, N>& arr\)": 1,
+                   r"^std::ostream& operator<<\(std::ostream& os, const DynamicArray<T, 2>& arr\)": 1,
+                   r"^std::istream& operator>>\(std::istream& is, std::array<T, N>& a\)": 1,
+                   r"^std::istream& operator>>\(std::istream& is, DynamicArray<T, 2>& arr\)": 1,
+                   r"^constexpr auto enumerate\s*\(T && iterable\)": 3, r"^void apply_matrix_vector_product\s*\(": 1, r"^constexpr bool all_impl\s*\(": 1,
                    r"^constexpr bool all\s*\(const std::array<T, N>& a, const std::array<T, N>& b\)": 1}
 
 

@@ -13,6 +13,7 @@
 #include <cstddef>
 #include <cstdlib>
 #include <cstring>
+#include <iomanip>
 #include <iostream>
 #include <iterator>
 #include <map>
@@ -73,6 +74,23 @@ public:
 private:
     std::vector<T> v_;
 };
+
+// rank 2: what the upstream stream operators touch (extents, resize, operator()(i, j))
+template <class T>
+class DynamicArray<T, 2> {
+public:
+    void resize(size_t r, size_t c) { r_ = r; c_ = c; v_.assign(r * c, T()); }
+    std::array<size_t, 2> extents() const { return {r_, c_}; }
+    T& operator()(size_t i, size_t j) { return v_[i * c_ + j]; }
+    const T& operator()(size_t i, size_t j) const { return v_[i * c_ + j]; }
+    T* data() { return v_.data(); }
+    const T* data() const { return v_.data(); }
+private:
+    size_t r_ = 0, c_ = 0;
+    std::vector<T> v_;
+};
+
+#include "common_stream.inc"       // upstream: operator<< / operator>> of std::array and DynamicArray<T,2> (state-file text)
 
 // ---- Container (include/container.h:24-59, src/container.cpp:84-144): data members + upstream putInBC -------------------
 class Container {
@@ -338,6 +356,33 @@ void set_constants(int M, double tau, double lambda, double mu, double rc, doubl
 
 }  // namespace
 
+template <class T, class S>
+static int write_array_text(const S* src, int R, int C, int width, char* buf, int buflen) {
+    DynamicArray<T, 2> a;
+    a.resize(R, C);
+    for (int i = 0; i < R; ++i)
+        for (int j = 0; j < C; ++j)
+            std::memcpy(&a(i, j), src + (static_cast<size_t>(i) * C + j) * width, sizeof(T));
+    std::stringstream ss;
+    ss << std::setprecision(16) << a << std::endl;
+    const std::string t = ss.str();
+    if (static_cast<int>(t.size()) + 1 <= buflen) std::memcpy(buf, t.c_str(), t.size() + 1);
+    return static_cast<int>(t.size()) + 1;
+}
+template <class T, class S>
+static int read_array_text(const char* text, S* dst, int max_elems, int width, int* R, int* C) {
+    DynamicArray<T, 2> a;
+    std::istringstream is(text);
+    is >> a;
+    if (!is) return -1;
+    const auto e = a.extents();
+    *R = static_cast<int>(e[0]);
+    *C = static_cast<int>(e[1]);
+    if (static_cast<long>(e[0] * e[1]) * width > max_elems) return -2;
+    for (size_t i = 0; i < e[0]; ++i)
+        for (size_t j = 0; j < e[1]; ++j) std::memcpy(dst + (i * e[1] + j) * width, &a(i, j), sizeof(T));
+    return 0;
+}
 extern "C" {
 
 int refcpu_ndim(void) { return NDIM; }
@@ -427,6 +472,20 @@ int refcpu_ssf_cyl(const double* side, const unsigned* periodic, const double* b
     e.accumulate();
     for (int s = 0; s < nshell; ++s) out[s] = e.estimator(s);
     return n1d;
+}
+
+// The text a state file holds for one array (src/pimc.cpp:955-962: `stream << std::setprecision(16) << array << std::endl`),
+// written by the upstream operator<<.  kind 0: DynamicArray<dVec,2> (beads), 1: DynamicArray<beadLocator,2> (links),
+// 2: DynamicArray<unsigned int,2> (worm.beads).  Returns the number of bytes needed (including the terminator).
+int refcpu_write_array(int kind, const void* src, int R, int C, char* buf, int buflen) {
+    if (kind == 0) return write_array_text<dVec>(static_cast<const double*>(src), R, C, NDIM, buf, buflen);
+    if (kind == 1) return write_array_text<beadLocator>(static_cast<const int*>(src), R, C, 2, buf, buflen);
+    return write_array_text<unsigned int>(static_cast<const unsigned int*>(src), R, C, 1, buf, buflen);
+}
+int refcpu_read_array(int kind, const char* text, void* dst, int max_elems, int* R, int* C) {
+    if (kind == 0) return read_array_text<dVec>(text, static_cast<double*>(dst), max_elems, NDIM, R, C);
+    if (kind == 1) return read_array_text<beadLocator>(text, static_cast<int*>(dst), max_elems, 2, R, C);
+    return read_array_text<unsigned int>(text, static_cast<unsigned int*>(dst), max_elems, 1, R, C);
 }
 
 #if NDIM == 3

@@ -34,6 +34,8 @@ class RefCpu:
         L.refcpu_ssf.argtypes = [_dp, _up, _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp]
         L.refcpu_isf.argtypes = [_dp, _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp]
         L.refcpu_ssf_cyl.argtypes = [_dp, _up, _dp, C.c_int, C.c_int, C.c_int, _dp, _ip, C.c_int, C.c_double, _dp]
+        L.refcpu_write_array.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_int]
+        L.refcpu_read_array.argtypes = [C.c_int, C.c_char_p, C.c_void_p, C.c_int, _ip, _ip]
         if ndim == 3:
             L.refcpu_action.argtypes = [C.c_int, _dp, _dp, C.c_int, C.c_int, C.c_int, _ip, C.c_double, C.c_double, C.c_double,
                                         C.c_int, _dp, _dp, C.c_int, _dp, _dp, _ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double]
@@ -80,6 +82,29 @@ class RefCpu:
         out = np.zeros(len(shells))
         n1d = self.lib.refcpu_ssf_cyl(_p(side), _p(per, _up), _p(beads), M, N, Next, _p(q), _p(sizes, _ip), len(shells), maxR, _p(out))
         return out, n1d
+
+    # the text of one state-file array by the upstream operator<< (kind 0 beads, 1 links, 2 worm.beads) and back
+    _KIND = {0: (np.float64, None), 1: (np.int32, 2), 2: (np.uint32, 1)}
+
+    def write_array(self, kind, arr) -> str:
+        dt, _ = self._KIND[kind]
+        a = np.ascontiguousarray(arr, dtype=dt)
+        R, Cc = a.shape[0], a.shape[1]
+        n = self.lib.refcpu_write_array(kind, a.ctypes.data, R, Cc, None, 0)
+        buf = C.create_string_buffer(n)
+        assert self.lib.refcpu_write_array(kind, a.ctypes.data, R, Cc, buf, n) == n
+        return buf.value.decode()
+
+    def read_array(self, kind, text):
+        dt, w = self._KIND[kind]
+        w = self.ndim if kind == 0 else w
+        out = np.zeros(len(text) // 2 + 16, dtype=dt)
+        R, Cc = C.c_int(0), C.c_int(0)
+        rc = self.lib.refcpu_read_array(kind, text.encode(), out.ctypes.data, out.size, C.byref(R), C.byref(Cc))
+        if rc != 0:
+            raise ValueError(f"upstream operator>> failed ({rc})")
+        shape = (R.value, Cc.value) if w == 1 else (R.value, Cc.value, w)
+        return out[:R.value * Cc.value * w].reshape(shape)
 
     def action(self, side, beads, N, tau, lam, VF, GF, period, window=5, mu=0.0, next_links=None, year=1979, spring_k=0.0):
         """dict of everything LocalAction / EnergyEstimator / VirialEnergyEstimator return for one configuration."""

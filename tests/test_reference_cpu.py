@@ -265,6 +265,56 @@ def test_cuda_external_gradient_against_upstream_cpu_code(orc):
     assert not np.allclose(f2_free, f2, rtol=1e-3)
 
 
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_state_file_arrays_against_upstream_stream_operators(ndim, tmp_path):
+    """The text format of the saved state (src/pimc.cpp:955-962) is what the upstream operator<< / operator>> of
+    std::array and DynamicArray<T,2> (include/common.h:244-399) produce and accept.  The Python restatement of the writer
+    (oracle/statefile.py) emits exactly the upstream text for beads, links and worm.beads; the upstream operator>> and
+    both our readers (oracle/statefile.py, pimc_b200/host/state_file.cpp through pimcb_host_selftest) recover the same
+    arrays bit for bit from it."""
+    import os
+    import subprocess
+    from oracle import statefile
+    ref = RefCpu(ndim)
+    rng = np.random.default_rng(ndim)
+    M, W, N = 5, 6, 4
+    beads = rng.uniform(-7.0, 7.0, size=(M, W, ndim))
+    beads[0, 0] = 0.0
+    beads[1, 1, 0] = 1.0e-5                                # short and exponent forms of operator<<(double)
+    beads[2, 2, 0] = -12.3456789125
+    on = np.zeros((M, W), dtype=np.uint32)
+    on[:, :N] = 1
+    nxt = np.full((M, W, 2), -1, dtype=np.int32)
+    for t in range(M):
+        nxt[t, :N, 0] = (t + 1) % M
+        nxt[t, :N, 1] = rng.permutation(N) if t == M - 1 else np.arange(N)
+    f = tmp_path / "ce-state-x.dat"
+    statefile.write_state(f, beads, on, next_link=nxt)
+    text = open(f).read()
+    t_beads, t_next, t_worm = ref.write_array(0, beads), ref.write_array(1, nxt), ref.write_array(2, on)
+    for piece in (t_beads, t_next, t_worm):
+        assert piece in text, "the Python writer must emit the upstream operator<< text verbatim"
+    assert text.index(t_beads) < text.index(t_next) < text.index(t_worm)
+    # upstream operator>> on the upstream text: exact round trip at setprecision(16)? 17 digits are needed in general, so
+    # compare all readers on the SAME text instead
+    up_beads = ref.read_array(0, t_beads)
+    up_next = ref.read_array(1, t_next)
+    up_worm = ref.read_array(2, t_worm)
+    assert np.array_equal(up_next, nxt) and np.array_equal(up_worm, on)
+    np.testing.assert_allclose(up_beads, beads, rtol=2e-16 * 10)
+    mine = statefile.read_state(f)
+    assert np.array_equal(mine["beads"], up_beads)
+    # C++ parser of the host layer
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "pimc_b200", "host", f"pimcb_host_selftest{ndim}d")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.dirname(exe), f"NDIM={ndim}"], check=True, stdout=subprocess.DEVNULL)
+    rho = N / 30.0 ** ndim                                  # a cell of side 30: putInside leaves these positions alone
+    out = subprocess.run([exe, "--state", str(f), str(N), repr(rho)], check=True, capture_output=True, text=True).stdout
+    got = np.array([[float(x) for x in l.split("=", 1)[1].split()] for l in out.splitlines() if l.startswith("bead=")])
+    assert np.array_equal(got.reshape(M, N, ndim), up_beads[:, :N])
+
+
 def test_extraction_recipe_finds_every_upstream_definition(tmp_path):
     """The build-time recipes locate each upstream definition by its signature; a silent mismatch would compile the wrong
     body.  With the upstream tree present: every manifest pattern matches exactly one line, and every cut ends on the brace
