@@ -12,6 +12,7 @@ located by its signature and cut at the brace that closes it (comments and strin
     include/path.h        Path::getSeparation, Path::getVelocity
     include/common.h      enumerate, all_impl / all (bead comparison), apply_matrix_vector_product, the stream operators of
                           std::array and DynamicArray<T,2> (the text format of the state files)
+    src/path.cpp          Path::leftPack (compiled by oracle/ref_pack_shim.cpp)
     src/worm.cpp          Worm::factor(state, bead)
     src/action.cpp        ActionBase::updateSepHist, LocalAction::potentialAction(), derivPotentialActionTau(int),
                           secondderivPotentialActionTau(int), derivPotentialActionLambda(int), V(int slice),
@@ -87,6 +88,7 @@ MANIFEST = {
         r"^std::istream& operator>>\(std::istream& is, std::array<T, N>& a\)",
         r"^std::istream& operator>>\(std::istream& is, DynamicArray<T, 2>& arr\)",
     ]),
+    "path_leftpack.inc": ("src/path.cpp", [r"^void Path::leftPack\(\)"]),
     "worm.inc": ("src/worm.cpp", [r"^double Worm::factor\s*\(const beadState state1, const beadLocator &bead2\)"]),
     "action.inc": ("src/action.cpp", [
         r"^inline void ActionBase::updateSepHist\s*\(",

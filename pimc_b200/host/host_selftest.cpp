@@ -50,6 +50,11 @@ static int stateReport(const char* file, int N, double density) {
               << "diagonal=" << st.isDiagonal() << std::endl << "leftPacked=" << st.isLeftPacked() << std::endl;
     if (!st.isLeftPacked()) st.leftPack();
     st.putInside(box);
+    if (st.nextLink.size() == st.beads.size())
+        for (int s = 0; s < st.numTimeSlices; ++s)
+            for (int p = 0; p < st.numWorldLines; ++p)
+                std::cout << "link=" << s << " " << p << " " << st.nextLink[st.idx(s, p)][0] << " " << st.nextLink[st.idx(s, p)][1] << " "
+                          << st.prevLink[st.idx(s, p)][0] << " " << st.prevLink[st.idx(s, p)][1] << " " << st.wormBeads[st.idx(s, p)] << std::endl;
     std::cout << "perSlice=";
     for (int n : st.numBeadsAtSlice) std::cout << n << " ";
     std::cout << std::endl;

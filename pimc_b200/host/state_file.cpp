@@ -110,17 +110,37 @@ bool PimcState::isLeftPacked() const {
     return true;
 }
 
+// Stable compaction of the active beads of every slice into the leading columns, with the link arrays relabelled to the
+// new columns (what Path::leftPack, src/path.cpp:145-189, arrives at by swapping hole and bead one at a time): the
+// world-line connectivity -- permutation cycles included -- survives, which the kinetic and virial estimators need.
 void PimcState::leftPack() {
+    const bool linked = nextLink.size() == beads.size() && prevLink.size() == beads.size();
+    std::vector<int> newcol(beads.size(), XXX);
     for (int s = 0; s < numTimeSlices; ++s) {
         int w = 0;
         for (int p = 0; p < numWorldLines; ++p)
-            if (wormBeads[idx(s, p)]) {
-                if (w != p) { beads[idx(s, w)] = beads[idx(s, p)]; wormBeads[idx(s, w)] = 1; wormBeads[idx(s, p)] = 0; }
-                ++w;
-            }
+            if (wormBeads[idx(s, p)]) newcol[idx(s, p)] = w++;
     }
-    nextLink.clear();
-    prevLink.clear();
+    auto relabel = [&](const beadLocator& b) {
+        if (b[0] == XXX || b[1] == XXX) return beadLocator{XXX, XXX};
+        return beadLocator{b[0], newcol[idx(b[0], b[1])]};
+    };
+    std::vector<dVec> nb(beads.size());                     // vacated columns: zero positions, no links, flag off
+    for (auto& v : nb) v.fill(0.0);
+    std::vector<beadLocator> nn(beads.size(), beadLocator{XXX, XXX}), np_(beads.size(), beadLocator{XXX, XXX});
+    std::vector<unsigned> on(beads.size(), 0u);
+    for (int s = 0; s < numTimeSlices; ++s)
+        for (int p = 0; p < numWorldLines; ++p) {
+            const size_t from = idx(s, p);
+            if (!wormBeads[from]) continue;
+            const size_t to = idx(s, newcol[from]);
+            nb[to] = beads[from];
+            on[to] = 1u;
+            if (linked) { nn[to] = relabel(nextLink[from]); np_[to] = relabel(prevLink[from]); }
+        }
+    beads.swap(nb);
+    wormBeads.swap(on);
+    if (linked) { nextLink.swap(nn); prevLink.swap(np_); } else { nextLink.clear(); prevLink.clear(); }
 }
 
 void PimcState::putInside(const Container& box) {

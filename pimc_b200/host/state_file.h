@@ -41,7 +41,7 @@ struct PimcState {
     // configuration is diagonal (closed worldlines only), the only kind estimators sample (src/estimator.cpp:228).
     bool isDiagonal() const;
     // Active beads of every slice in columns [0, n): true for files written by the reference; leftPack() restores it
-    // for hand-made files (positions and flags only -- links are not needed for measurement and are dropped).
+    // for hand-made files: stable compaction of positions and flags with the links relabelled accordingly.
     bool isLeftPacked() const;
     void leftPack();
     // Container::putInside on every bead + active count per slice (src/pimc.cpp:1258-1268).

@@ -342,3 +342,60 @@ def test_extraction_recipe_finds_every_upstream_definition(tmp_path):
             assert depth == 0 and len(body) >= 3, f"{path}: {pat!r} cut is unbalanced"
     mod.main(ref, str(tmp_path))
     assert sorted(os.listdir(tmp_path)) == sorted(mod.MANIFEST)
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_left_pack_against_upstream_body(ndim, tmp_path):
+    """Path::leftPack (src/path.cpp:145-189), compiled from the upstream tree (oracle/_ref/librefpack<NDIM>d.so), against
+    PimcState::leftPack of the host layer on a hand-made state with holes in every row and permuted world lines: positions,
+    flags and BOTH link arrays end up identical (the kinetic and virial estimators follow those links)."""
+    import ctypes as C
+    import os
+    import subprocess
+    from oracle import statefile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_path = os.path.join(root, "oracle", "_ref", f"librefpack{ndim}d.so")
+    if not os.path.exists(lib_path):
+        pytest.skip(f"{lib_path} not built (needs the upstream tree: make -C oracle ref)")
+    lib = C.CDLL(lib_path)
+    assert lib.refpack_ndim() == ndim
+    rng = np.random.default_rng(10 + ndim)
+    M, W, N = 6, 9, 5
+    cols = [np.sort(rng.choice(W, size=N, replace=False)) for _ in range(M)]
+    on = np.zeros((M, W), dtype=np.uint32)
+    beads = np.zeros((M, W, ndim))
+    for t in range(M):
+        on[t, cols[t]] = 1
+        beads[t, cols[t]] = rng.uniform(-3.0, 3.0, size=(N, ndim))
+    # closed world lines through the scattered columns, a different permutation on every link
+    nxt = np.full((M, W, 2), -1, dtype=np.int32)
+    prv = np.full((M, W, 2), -1, dtype=np.int32)
+    for t in range(M):
+        perm = rng.permutation(N)
+        for a in range(N):
+            src, dst = (t, cols[t][a]), ((t + 1) % M, cols[(t + 1) % M][perm[a]])
+            nxt[src] = dst
+            prv[dst] = src
+    f = tmp_path / "ce-state-holes.dat"
+    statefile.write_state(f, beads, on, next_link=nxt)
+    # upstream, on the arrays as the loader sees them (positions at the 16 significant digits of the file)
+    parsed = statefile.read_state(f)
+    assert np.array_equal(parsed["next"], nxt) and np.array_equal(parsed["prev"], prv)
+    u_b, u_n, u_p, u_on = np.ascontiguousarray(parsed["beads"]), nxt.copy(), prv.copy(), on.copy()
+    vp = C.c_void_p
+    lib.refpack_left_pack.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int]
+    assert lib.refpack_left_pack(u_b.ctypes.data, u_n.ctypes.data, u_p.ctypes.data, u_on.ctypes.data, M, W) == 0
+    assert np.all(u_on[:, :N] == 1) and np.all(u_on[:, N:] == 0)
+    # host layer
+    exe = os.path.join(root, "pimc_b200", "host", f"pimcb_host_selftest{ndim}d")
+    rho = N / 30.0 ** ndim
+    out = subprocess.run([exe, "--state", str(f), str(N), repr(rho)], check=True, capture_output=True, text=True).stdout
+    rep = [l.split("=", 1) for l in out.splitlines() if "=" in l]
+    assert ["leftPacked", "0"] in rep and ["diagonal", "1"] in rep
+    got = np.array([[float(x) for x in v.split()] for k, v in rep if k == "bead"]).reshape(M, N, ndim)
+    assert np.array_equal(got, u_b[:, :N])
+    links = np.array([[int(x) for x in v.split()] for k, v in rep if k == "link"])
+    assert len(links) == M * W
+    for s_, p_, ns, np_, ps, pp, flag in links:
+        assert flag == u_on[s_, p_]
+        assert (ns, np_) == tuple(u_n[s_, p_]) and (ps, pp) == tuple(u_p[s_, p_]), (s_, p_)
