@@ -932,7 +932,12 @@ int pimcb_set_qvecs(pimcb_ctx* c, const double* q, int nq) {
         plan.insert(plan.end(), best_first.begin(), best_first.end());
         // DMMA formulation: L rows per (leading-key) column, R columns per last-key value; coinciding factors are
         // stored once (see kernels.cuh, MmaPlan) and one all-zero row / column is reserved at the end
-        {
+        // The 3-D kernel indexes lmap with the fixed stride 9 (|n_x|, |n_y| <= 8): q-sets beyond that have no DMMA plan
+        // (mma_nL = mma_nR = 0) and run on the CUDA-core lattice / generic kernels.
+        const bool dmma_plan = !(nd == 3 && (c->nmax[0] > 8 || c->nmax[1] > 8)) && c->nmax[last] <= 16;
+        c->mma_lmap.clear(); c->mma_rmap.clear(); c->mma_gdesc.clear(); c->mma_gout.clear();
+        c->unfold_NR = -1;
+        if (dmma_plan) {
             const int n0 = c->nmax[0] + 1, n1 = nd == 3 ? 9 : 1;   // 3-D lmap has the fixed stride 9 the kernel indexes with
             std::vector<int> lmap(nd == 1 ? 1 : static_cast<size_t>(n0) * n1, -1), rmap(c->nmax[last] + 1, -1);
             int nL = nd == 1 ? 1 : 0, nR = 0;

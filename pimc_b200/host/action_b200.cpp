@@ -1,9 +1,23 @@
 #include "action_b200.h"
 
-LocalActionB200::LocalActionB200(const Path& _path, PotentialBase* external, PotentialBase* interaction,
-                                 const TableView& table, const std::array<double, 2>& _VFactor,
-                                 const std::array<double, 2>& _gradVFactor, int _period)
-    : ActionBase(_path, external, interaction, _period), VFactor(_VFactor), gradVFactor(_gradVFactor) {
+#include <cmath>
+#include <cstdlib>
+#include <iostream>
+
+LocalActionB200::LocalActionB200(const Path& _path, LookupTable& _lookup, PotentialBase* _externalPtr,
+                                 PotentialBase* _interactionPtr, WaveFunctionBase* _waveFunctionPtr,
+                                 const std::array<double, 2>& _VFactor, const std::array<double, 2>& _gradVFactor, bool _local,
+                                 std::string _name, double _endFactor, int _period)
+    : LocalAction(_path, _lookup, _externalPtr, _interactionPtr, _waveFunctionPtr, _VFactor, _gradVFactor, _local, _name,
+                  _endFactor, _period) {
+    const TableView table = interactionPtr->tableView();
+    if (!table.V || !table.dVdr || table.tableLength <= 0) {
+        // reference error convention (src/estimator.cpp:450-455): the B200 action only replaces tabulated pair potentials
+        std::cerr << "\nERROR: pimc_b200: the interaction potential exposes no lookup tables (PotentialBase::tableView())"
+                  << std::endl;
+        std::exit(EXIT_FAILURE);
+    }
+    haveTable = true;
     B200Session::get(path).setPairTable(table.V, table.dVdr, table.tableLength, table.dr, table.extV.data(),
                                         table.extdVdr.data());
     // which slices carry the gradient correction (src/setup.cpp:1232-1253): gsf {0, 2/9} -> odd slices only,
@@ -67,8 +81,10 @@ std::array<double, 2> LocalActionB200::potential(int slice) {
 // reference's PotentialBase and uploaded with the configuration (pimcb_set_external_gradient).
 double LocalActionB200::gradVSquared(int slice) { return sums().f2[slice]; }
 
+// The one whole-path entry point that is also reached from OUTSIDE the measurement loop (DEBUG_MOVE's checkMove calls it
+// before and after a trial move, src/move.cpp:190-243): it never trusts a cached configuration, hooked or not.
 double LocalActionB200::potentialAction() {
-    B200Session::get(path).beginIfUnhooked();
+    B200Session::get(path).invalidate();
     const B200Session::PairSums& s = sums();
     double totU = 0.0;
     for (int slice = 0; slice < path.numTimeSlices; slice++) {

@@ -1,4 +1,10 @@
-// action_b200.h -- B200 replacement of the whole-path pair sums behind the reference's ActionBase interface.
+// action_b200.h -- B200 replacement of the whole-slice pair sums behind the reference's LocalAction interface.
+//
+// LocalActionB200 IS a LocalAction (include/action.h:157-254) with the same constructor parameters, created in its place in
+// Setup::action (src/setup.cpp:1258-1260): pdrive.cpp:141-159 builds ONE action object per path and hands it to the
+// moves and to the estimators alike, so everything bead-level that the moves call -- potentialAction(beadLocator...),
+// barePotentialAction, potentialActionCorrection, the NN-table variants -- stays the inherited upstream host code, and
+// only the whole-slice virtuals the measurement code calls are overridden:
 //
 // LocalActionB200 answers the virtuals the measurement code calls --
 //     potentialAction()                    (src/action.cpp:456-472)
@@ -18,13 +24,22 @@
 #include "pimc_compat.h"
 #else
 #include "action.h"
+#include "lookuptable.h"
+#include "potential.h"          // PotentialBase::tableView() (upstream.patch)
 #endif
 #include "b200_session.h"
 
-class LocalActionB200 : public ActionBase {
+class LocalActionB200 : public LocalAction {
 public:
-    LocalActionB200(const Path& path, PotentialBase* external, PotentialBase* interaction, const TableView& table,
-                    const std::array<double, 2>& VFactor, const std::array<double, 2>& gradVFactor, int period);
+    // parameter list of LocalAction (include/action.h:157-160); the lookup tables come from interaction->tableView()
+    LocalActionB200(const Path& path, LookupTable& lookup, PotentialBase* external, PotentialBase* interaction,
+                    WaveFunctionBase* waveFunction, const std::array<double, 2>& VFactor,
+                    const std::array<double, 2>& gradVFactor, bool local = true, std::string name = "Local",
+                    double endFactor = 1.0, int period = 1);
+    using LocalAction::potentialAction;              // the bead-level overloads stay upstream's
+    using LocalAction::derivPotentialActionTau;      // (int, double) cut-off variants likewise
+    using LocalAction::derivPotentialActionLambda;
+    using LocalAction::potential;
     double potentialAction() override;
     std::array<double, 2> potential(int slice) override;
     double derivPotentialActionTau(int slice) override;
@@ -38,7 +53,7 @@ public:
     double deltaDOTgradUterm2(int slice) override;              // src/action.cpp:1667-1784
     double virKinCorr(int slice) override;                      // src/action.cpp:1786-1803
 private:
-    std::array<double, 2> VFactor, gradVFactor;
+    bool haveTable = false;                 // false: the interaction potential is not tabulated -> upstream host loops
     bool needF2;
     int f2Parity;
     int lastSlice[4] = {1 << 30, 1 << 30, 1 << 30, 1 << 30};   // last slice served per per-slice entry point (unhooked mode)

@@ -16,7 +16,7 @@ public:
     double valuedVdr(double r) const;          // potential.cpp:1849-1875
     double valued2Vdr2(double r) const;        // potential.cpp:1881-1909
     double grad2V(const dVec& r) override;     // potential.h:1010-1016 (direct lookup of d2V/dr2)
-    TableView tableView() const;               // the accessor the B200 action needs (tables are protected upstream)
+    TableView tableView() const override;      // the accessor the B200 action needs (upstream.patch adds it to the reference's class)
 private:
     double rm, A, epsilon, alpha, beta, D, C6, C8, C10;
     double dr = 0.0;

@@ -11,6 +11,13 @@ struct SessionRegistry {
 };
 static SessionRegistry& registry() { static SessionRegistry r; return r; }
 
+// Path::get_beads_data_pointer() returns the dVec (= std::array<double, NDIM>) storage of DynamicArray<dVec,2> beads
+// (include/path.h:208-210, include/dynamic_array.h:209); the C ABI takes the same bytes as flat doubles
+// [M][N_ext][NDIM] -- contiguity is what upstream itself relies on when it hands this pointer to its GPU kernels
+// (src/estimator.cpp:4084-4085).
+static_assert(sizeof(dVec) == NDIM * sizeof(double), "dVec must be NDIM packed doubles");
+static const double* beadsOf(const Path& path) { return reinterpret_cast<const double*>(path.get_beads_data_pointer()); }
+
 // ABI failures follow the reference's error convention: message on std::cerr, then exit(EXIT_FAILURE)
 // (src/estimator.cpp:450-455); nothing is ever wrapped in assert() (cf. GPU_ASSERT, include/common_gpu.h:55).
 void B200Session::check(int rc, const char* what) const {
@@ -74,7 +81,7 @@ void B200Session::stageIfNeeded() {
     // Page-lock Path::beads once (again whenever the array was reallocated, i.e. after particle insertions grew it):
     // staging is then a single DMA of the reference array as it lies, no host-side repacking.  A refused registration
     // only means the bounce-buffer path is used.
-    const void* base = path_.get_beads_data_pointer();
+    const void* base = beadsOf(path_);
     const size_t bytes = sizeof(double) * static_cast<size_t>(M) * ext[1] * NDIM;
     if (base != locked_ptr_ || bytes != locked_bytes_) {
         if (locked_ptr_) pimcb_host_unregister(const_cast<void*>(locked_ptr_));
@@ -86,11 +93,11 @@ void B200Session::stageIfNeeded() {
         }
     }
     if (fused_ssf_out_) {          // ssf()/isf() asked for the staging: one call, one synchronisation
-        check(pimcb_ssf_isf_beads(ctx_, path_.get_beads_data_pointer(), M, N, static_cast<int>(ext[1]), fused_ssf_out_, fused_isf_out_),
+        check(pimcb_ssf_isf_beads(ctx_, beadsOf(path_), M, N, static_cast<int>(ext[1]), fused_ssf_out_, fused_isf_out_),
               "pimcb_ssf_isf_beads");
         fused_done_ = true;
     } else {
-        check(pimcb_stage_beads(ctx_, path_.get_beads_data_pointer(), M, N, static_cast<int>(ext[1])), "pimcb_stage_beads");
+        check(pimcb_stage_beads(ctx_, beadsOf(path_), M, N, static_cast<int>(ext[1])), "pimcb_stage_beads");
     }
     staged_ = true;
     have_sf_ = have_pair_ = false;

@@ -1,4 +1,5 @@
 #include "estimator_b200.h"
+#include "b200_register.h"
 
 #ifdef PIMCB_STANDALONE
 #define PIMCB_FMT_INT(spec, v) pimcb_format(spec, v)
@@ -7,8 +8,8 @@
 #define PIMCB_FMT_INT(spec, v) boost::str(boost::format(spec) % (v))
 #endif
 
-REGISTER_ESTIMATOR("static structure factor", StaticStructureFactorEstimatorB200)
-REGISTER_ESTIMATOR("intermediate scattering function", IntermediateScatteringFunctionEstimatorB200)
+PIMCB_REGISTER_ESTIMATOR("static structure factor", StaticStructureFactorEstimatorB200)
+PIMCB_REGISTER_ESTIMATOR("intermediate scattering function", IntermediateScatteringFunctionEstimatorB200)
 
 // ---- S(q) ----------------------------------------------------------------------------------------------------
 // Constructor contract of src/estimator.cpp:3661-3693: q list from the command line, `numq` columns, a first header

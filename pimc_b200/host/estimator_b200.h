@@ -14,6 +14,7 @@
 #ifdef PIMCB_STANDALONE
 #include "estimator_base.h"
 #else
+#include <complex>                  // estimator.h:805 names std::complex without including it
 #include "estimator.h"
 #endif
 #include "b200_session.h"

@@ -21,6 +21,8 @@
 #include <string>
 #include <vector>
 
+#include "table_view.h"
+
 #ifndef NDIM
 #define NDIM 3                      // CMakeLists.txt:223-226 (compile-time dimension upstream)
 #endif
@@ -192,7 +194,7 @@ public:
         boxPtr->putInBC(sep);
         return sep;
     }
-    const double* get_beads_data_pointer() const { return reinterpret_cast<const double*>(beads_.data()); }   // path.h:208-210
+    const dVec* get_beads_data_pointer() const { return beads_.data(); }                        // path.h:208-210 (typed as upstream)
     double* beads_data() { return reinterpret_cast<double*>(beads_.data()); }
     std::array<size_t, 2> get_beads_extents() const { return {static_cast<size_t>(numTimeSlices), static_cast<size_t>(next_)}; }
 private:
@@ -222,6 +224,7 @@ public:
     }
     virtual dVec gradV(const dVec&) { return dVec{}; }
     virtual double grad2V(const dVec&) { return 0.0; }
+    virtual TableView tableView() const { return TableView{}; }      // upstream.patch adds the same virtual (no table by default)
     double tailV = 0.0;
 };
 class FreePotential : public PotentialBase {};
@@ -237,27 +240,23 @@ private:
     double k;
 };
 
-// Flat view of a TabulatedPotential (include/potential.h:148-157); upstream the members are protected and a
-// 3-line public accessor returning this struct is the only change the potential classes need.
-struct TableView {
-    const double* V = nullptr;
-    const double* dVdr = nullptr;
-    const double* d2Vdr2 = nullptr;
-    int tableLength = 0;
-    double dr = 0.0;
-    std::array<double, 2> extV{}, extdVdr{}, extd2Vdr2{};
-};
-
 // ---- action (include/action.h:30-254; the members the measurement path uses) -----------------------------------
+class LookupTable {};               // include/lookuptable.h: nearest-neighbour grid used by the moves, not by the measurement
+class WaveFunctionBase {};          // include/wavefunction.h: PIGS trial wave functions, unused in PIMC mode
+
 class ActionBase {
 public:
-    ActionBase(const Path& p, PotentialBase* ext, PotentialBase* inter, int period_ = 1)
-        : period(period_), externalPtr(ext), interactionPtr(inter), path(p) {
+    // same parameter list as upstream (include/action.h:33-35)
+    ActionBase(const Path& p, LookupTable& _lookup, PotentialBase* ext, PotentialBase* inter, WaveFunctionBase* wf,
+               bool _local = true, std::string _name = "Base", double _endFactor = 1.0, int _period = 1)
+        : local(_local), period(_period), externalPtr(ext), interactionPtr(inter), name(_name), lookup(_lookup), path(p),
+          waveFunctionPtr(wf), endFactor(_endFactor) {
         sepHist.resize(NPCFSEP);
         sepHist.fill(0);
         dSep = 0.5 * std::sqrt(1.0 * NDIM) * path.boxPtr->side[NDIM - 1] / (1.0 * NPCFSEP);      // src/action.cpp:192
     }
     virtual ~ActionBase() {}
+    std::string getActionName() { return name; }
     virtual double potentialAction() { return 0.0; }
     virtual std::array<double, 2> potential(int) { return {0.0, 0.0}; }
     virtual double derivPotentialActionTau(int) { return 0.0; }
@@ -268,14 +267,33 @@ public:
     virtual double deltaDOTgradUterm1(int) { return 0.0; }
     virtual double deltaDOTgradUterm2(int) { return 0.0; }
     virtual double virKinCorr(int) { return 0.0; }
+    const bool local;
     const int period;
-    DynamicArray<int, 1> sepHist;   // action.h:114
     PotentialBase* externalPtr;     // public upstream as well (include/action.h:108-109)
     PotentialBase* interactionPtr;
-    double tau() const { return constants()->tau(); }
+    DynamicArray<int, 1> sepHist;   // action.h:114
 protected:
+    std::string name;
+    LookupTable& lookup;
     const Path& path;
+    WaveFunctionBase* waveFunctionPtr;
+    double endFactor;
+    int shift = 1;                  // PIMC mode (include/action.h:139-149)
+    double tau() { return shift * constants()->tau(); }
     double dSep;
+};
+
+// include/action.h:157-254: the bead-level members (moves) are upstream code and stay on the host there; the stand-alone
+// measurement tools never call them
+class LocalAction : public ActionBase {
+public:
+    LocalAction(const Path& p, LookupTable& _lookup, PotentialBase* ext, PotentialBase* inter, WaveFunctionBase* wf,
+                const std::array<double, 2>& _VFactor, const std::array<double, 2>& _gradVFactor, bool _local = true,
+                std::string _name = "Local", double _endFactor = 1.0, int _period = 1)
+        : ActionBase(p, _lookup, ext, inter, wf, _local, _name, _endFactor, _period), VFactor(_VFactor), gradVFactor(_gradVFactor) {}
+protected:
+    int eo = 0;
+    std::array<double, 2> VFactor, gradVFactor;
 };
 
 // ---- output files (include/communicator.h; file-name pattern src/communicator.cpp:39-44,160-167) ----------------

@@ -97,6 +97,7 @@ int main(int argc, char** argv) {
     PotentialBase& external = std::atof(arg(argc, argv, "--spring", "0")) != 0.0 ? static_cast<PotentialBase&>(spring)
                                                                                   : static_cast<PotentialBase&>(freeExternal);
     std::unique_ptr<AzizPotential> aziz;
+    LookupTable lookup;
     std::unique_ptr<LocalActionB200> action;
     if (wantPotential) {
         aziz.reset(new AzizPotential(std::atoi(arg(argc, argv, "--aziz_year", "1979")), &box));
@@ -104,7 +105,8 @@ int main(int argc, char** argv) {
         int period = 1;
         if (actionType == "gsf") { VF = {2.0 / 3.0, 4.0 / 3.0}; GF = {0.0, 2.0 / 9.0}; period = 2; }
         else if (actionType == "li_broughton") { GF = {1.0 / 12.0, 1.0 / 12.0}; period = 2; }
-        action.reset(new LocalActionB200(path, &external, aziz.get(), aziz->tableView(), VF, GF, period));
+        // as Setup::action constructs LocalAction (src/setup.cpp:1258-1260)
+        action.reset(new LocalActionB200(path, lookup, &external, aziz.get(), nullptr, VF, GF, true, actionType, 1.0, period));
     }
 
     std::vector<std::unique_ptr<EstimatorBase>> estimators;

@@ -1,4 +1,5 @@
 #include "scattering_b200.h"
+#include "b200_register.h"
 
 #ifdef PIMCB_STANDALONE
 #define PIMCB_FMT(spec, v) pimcb_format(spec, v)
@@ -7,8 +8,8 @@
 #define PIMCB_FMT(spec, v) boost::str(boost::format(spec) % (v))
 #endif
 
-REGISTER_ESTIMATOR("elastic scattering", ElasticScatteringEstimatorB200)
-REGISTER_ESTIMATOR("cylinder static structure factor", CylinderStaticStructureFactorEstimatorB200)
+PIMCB_REGISTER_ESTIMATOR("elastic scattering", ElasticScatteringEstimatorB200)
+PIMCB_REGISTER_ESTIMATOR("cylinder static structure factor", CylinderStaticStructureFactorEstimatorB200)
 
 // ---- elastic scattering ---------------------------------------------------------------------------------------------
 // src/estimator.cpp:4114-4176: q list from the command line, numq columns, header = integer column indices, norm 0.5.

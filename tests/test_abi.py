@@ -51,3 +51,17 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.lower(), f"{f} mentions the oracle"
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/include"), reason="needs the upstream tree (build container only)")
+@pytest.mark.parametrize("ndim", [3, 2])
+def test_adaptor_layer_compiles_against_the_upstream_headers(ndim):
+    """The drop-in claim, compiled: pimc_b200/host/{b200_session,estimator_b200,scattering_b200,action_b200}.cpp WITHOUT
+    PIMCB_STANDALONE against the reference's own estimator.h / action.h / path.h / potential.h (upstream.patch applied
+    to a scratch copy; Boost and <mdspan> declared by upstream_stubs/), plus the patched upstream translation units
+    (setup.cpp with `new LocalActionB200(...)` in Setup::action, estimator.cpp, pimc.cpp, action.cpp, pdrive.cpp)."""
+    import subprocess
+    host = os.path.join(ROOT, "pimc_b200", "host")
+    r = subprocess.run(["make", "-C", host, "upstream-check", f"NDIM={ndim}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert f"upstream-check OK (NDIM={ndim})" in r.stdout

@@ -155,6 +155,11 @@ def test_ragged_sizes(api, orc, ndim, N, M, pad):
     (3, [[1, 2, 3], [1, 2, 3], [-1, -2, -3]]),                      # a repeated q opens a second group
     (2, [[0, 5], [5, 0], [-5, 0], [3, -4], [0, 0]]),
     (1, [[1], [-1], [3], [0]]),
+    # |n_y| >= 9 / |n_x| >= 9 in 3-D: beyond the fixed stride of the DMMA plan's column map -- no DMMA plan is built
+    # (the planner used to index that map out of range, e.g. --wavevector "0 12 0" or max_int "10 10 10")
+    (3, [[0, 12, 0], [1, 9, 2], [-2, 10, 1], [0, 0, 1]]),
+    (3, [[10, 10, 10], [-10, 9, 3], [12, 0, 0], [3, -11, 16]]),
+    (2, [[0, 17], [9, 12], [-12, 3]]),
 ])
 def test_lattice_qsets(api, orc, ndim, nvec):
     """Hand-picked lattice q-sets that exercise every branch of the lattice plans (zero components, anisotropic
