@@ -4,10 +4,12 @@
     python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run)
     python bench.py --impl reference ...                     (the CPU restatement of the reference estimators)
 
-A step = one pass of the hot path (rho_q build, tau-correlation, bin accumulation) over one batch of B synthetic
-walker configurations per GPU.  `value` = configurations evaluated per second over all ranks with beads resident
-in HBM; `e2e` = the same through the C ABI from pinned HOST buffers (H2D of every batch and D2H of the bin inside
-the timed region).  One JSON line on stdout (rank 0).
+A step = ONE OUTPUT BIN of the hot path: `--batches-per-step` (16) batches of B (64) synthetic walker configurations per GPU
+go through rho_q build + tau-correlation + bin accumulation, then the bin is folded and -- on more than one GPU --
+exchanged once (the library's own NCCL reduce / all-gather), exactly what EstimatorBase::output does per bin.
+`value` = configurations evaluated per second over all ranks with beads resident in HBM; `e2e` = the same through the
+C ABI from pinned HOST buffers (H2D of every batch and D2H of every bin inside the timed region), with the bare
+H2D rate of the same buffers measured in the same run as its ceiling.  One JSON line on stdout (rank 0).
 """
 from __future__ import annotations
 
@@ -33,10 +35,11 @@ UNIT = "evaluations/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="walker configurations per GPU per step")
+    ap.add_argument("--batch", type=int, default=64, help="walker configurations per GPU per batch (one launch pair)")
+    ap.add_argument("--batches-per-step", type=int, default=16, help="batches accumulated into one output bin = one step")
     ap.add_argument("--workload", default="C2", choices=sorted(synth.SHAPES))
     ap.add_argument("--rho-mode", type=int, default=-1, help="-1 library default, 0 generic sincos, 1 lattice recurrence")
     ap.add_argument("--corr-mode", type=int, default=-1, help="-1 library default, 0 CUDA-core tau-correlation, 1 DMMA")
@@ -45,7 +48,7 @@ def parse_args():
     ap.add_argument("--shard", default="config", choices=["config", "q"],
                     help="multi-GPU axis: independent walker configurations (weak scaling, one reduce) or q-vectors "
                          "(strong scaling, every rank sees every configuration, one all-gather)")
-    ap.add_argument("--collective", default="torch", choices=["torch", "lib"],
+    ap.add_argument("--collective", default="lib", choices=["torch", "lib"],
                     help="who issues the one collective per bin: torch.distributed on the library's device buffer, or the "
                          "library's own NCCL entry points (pimcb_reduce_bins / pimcb_gather_bins_q)")
     ap.add_argument("--unique", type=int, default=16, help="distinct synthetic configurations generated per slot")
@@ -217,31 +220,53 @@ class CpuArm:
                 f"S(q) for {self.n_ssf} of {len(self.q)} q, {self.cores} threads, extrapolated linearly to the full q-set")
 
 
-def run_reference(args, shape, q):
-    """--impl reference: the reference's own CPU estimators (the upstream accumulate() bodies compiled into oracle/_ref,
-    else the oracle port) with all host threads.  Under torchrun only rank 0 works."""
-    if int(os.environ.get("RANK", "0")) != 0:
-        return
-    total_steps = max(1, args.steps + args.warmup)
-    budget = min(args.cpu_seconds, 150.0 * host_cores() / total_steps)       # keep the whole run within minutes
-    arm = CpuArm(shape, q, budget)
-    for _ in range(args.warmup):
+def workload_text(shape, nq):
+    return (f"{shape.name}: N={shape.N} M={shape.M} nq={nq} ndim={shape.ndim}, He-4 SVP density, commensurate q; one evaluation = "
+            f"S(q)[{nq}] + F(q,tau)[{nq}][{shape.M}] of one walker configuration")
+
+
+def shared_config(shape, nq):
+    """`config` is the WORKLOAD and is identical in both arms (the driver compares it); how each arm runs it is under `run`."""
+    return {"workload": workload_text(shape, nq)}
+
+
+FULL_SIZE_RECORD = {"value": 1.0 / 261.0, "unit": UNIT, "cores": 8,
+                    "what": "ONE complete C2 evaluation through the upstream CPU accumulate() bodies, no sampling: 259.7 s F(q,tau) + "
+                            "1.3 s S(q) on the 8 threads of the build container (tests/golden/make_upstream_c2_full.py -> "
+                            "tests/golden/upstream_c2_full.npz; the CUDA path reproduces all 64 + 10 880 values to 1e-10)"}
+
+
+def time_cpu_arm(arm, steps, warmup):
+    for _ in range(warmup):
         arm.step()
     evals, wall = [], []
-    for _ in range(args.steps):
+    for _ in range(steps):
         f, w = arm.step()
         evals.append(f)
         wall.append(w)
-    value = 1.0 / float(np.mean(evals))
+    return 1.0 / float(np.mean(evals)), float(np.mean(wall))
+
+
+def run_reference(args, shape, q):
+    """--impl reference: the reference's own CPU estimators (the upstream accumulate() bodies compiled into oracle/_ref,
+    else the oracle port) with all host threads, on the same workload and with the same bounded sample per step as the
+    cpu_baseline leg of the GPU arm.  Under torchrun only rank 0 works."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    total_steps = max(1, args.steps + args.warmup)
+    budget = min(args.cpu_seconds, 240.0 * host_cores() / total_steps)       # keep the whole run within minutes
+    arm = CpuArm(shape, q, budget)
+    value, wall = time_cpu_arm(arm, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(wall)), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{shape.name}: N={shape.N} M={shape.M} nq={len(q)} ndim={shape.ndim}, He-4 SVP density, "
-                               f"commensurate q; reference CPU estimators ({'upstream code' if arm.kind == 'reference' else 'oracle port'}) "
-                               f"on a bounded sample per step",
-                   "parallelism": f"{arm.cores} host threads, q-vectors / F(q,tau) elements split over threads"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.sample_text()},
+        "config": shared_config(shape, len(q)),
+        "run": {"what": f"reference CPU estimators ({'upstream code' if arm.kind == 'reference' else 'oracle port'}), a bounded sample of "
+                        "the evaluation per step, extrapolated by term count (see cpu_baseline.sample)",
+                "parallelism": f"{arm.cores} host threads, q-vectors / F(q,tau) elements split over threads"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.sample_text(),
+                         "extrapolated": True, "full_size_record": FULL_SIZE_RECORD},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -325,6 +350,43 @@ def bind_to_gpu_numa(local: int):
 # --------------------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------------------
+def upstream_gpu_ab(shape, q, beads_one):
+    """the reference's shipped GPU kernels (src/estimator_gpu.cu, compiled UNMODIFIED
+    for sm_100a into oracle/_ref/librefgpu3d*.so by `make -C oracle ref`) timed on the same box, same configuration, same q:
+    one gpu_ssf launch + one gpu_isf launch per q per evaluation, with the header's default block size (256) and with
+    the one upstream's CMake passes (1024)."""
+    import ctypes as C
+    if shape.ndim != 3:
+        return None
+    out = {}
+    dp = C.POINTER(C.c_double)
+    beads = np.ascontiguousarray(beads_one, dtype=np.float64)
+    qq = np.ascontiguousarray(q, dtype=np.float64)
+    M, Next, _ = beads.shape
+    for tag, name in (("block256", "librefgpu3d.so"), ("block1024", "librefgpu3d_b1024.so")):
+        path = os.path.join(ROOT, "oracle", "_ref", name)
+        if not os.path.exists(path):
+            continue
+        try:
+            lib = C.CDLL(path)
+            lib.ref_gpu_bench.argtypes = [dp, C.c_int, C.c_int, C.c_int, dp, C.c_int, C.c_int, dp]
+            ms = np.zeros(2)
+            if lib.ref_gpu_bench(beads.ctypes.data_as(dp), M, shape.N, Next, qq.ctypes.data_as(dp), len(qq), 2, ms.ctypes.data_as(dp)) != 0:
+                continue
+            out[tag] = {"kernels_ms_per_evaluation": float(ms[0]), "kernels_evaluations_per_s": 1e3 / float(ms[0]),
+                        "accumulate_pattern_ms_per_evaluation": float(ms[1]), "accumulate_pattern_evaluations_per_s": 1e3 / float(ms[1])}
+        except (OSError, AttributeError):
+            continue
+    if not out:
+        return None
+    best = max(out.values(), key=lambda v: v["kernels_evaluations_per_s"])
+    return {"what": "upstream gpu_ssf + gpu_isf (src/estimator_gpu.cu:66-165, 288-413) compiled unmodified for sm_100a, one configuration, "
+                    "2 evaluations timed after one warm-up; kernels = CUDA events with beads resident, accumulate_pattern = the "
+                    "upstream estimators' own per-measurement H2D + launches + sync + D2H (src/estimator.cpp:3833-3861, 4074-4100)",
+            "variants": out, "best_kernels_evaluations_per_s": best["kernels_evaluations_per_s"],
+            "best_accumulate_evaluations_per_s": max(v["accumulate_pattern_evaluations_per_s"] for v in out.values())}
+
+
 def run_ours(args, shape, q):
     import torch
     import torch.distributed as dist
@@ -347,8 +409,14 @@ def run_ours(args, shape, q):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allreduce(x, op):
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=op)
+        return float(t.item())
+
     from pimc_b200 import multi
-    B, K, W = args.batch, args.steps, args.warmup
+    B, K, W, P = args.batch, args.steps, args.warmup, args.batches_per_step
     q_all = q
     if args.shard == "q" and world > 1:
         lo, hi = multi.shard_range(len(q_all), world, rank)
@@ -370,7 +438,7 @@ def run_ours(args, shape, q):
     # synthetic batches: `unique` distinct configurations per slot, cycled to B, different seeds per rank and slot
     nslots = ctx.num_slots()
     batch_bytes = B * shape.M * (shape.N + 3) * shape.ndim * 8
-    use_slots = nslots if nslots * batch_bytes > 140e6 else nslots        # rotate all slots; total footprint below
+    use_slots = nslots
     pinned = []
     for sl in range(use_slots):
         seed_rank = 0 if args.shard == "q" else rank          # q-sharding: every rank measures the same walkers
@@ -387,12 +455,11 @@ def run_ours(args, shape, q):
     ext = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
     peak_tflops = ctx.fp64_peak_tflops(args.peak_seconds)
 
-    def device_step(k):
-        ctx.select_slot(k % use_slots)
-        ctx.measure()
-
-    def bin_collective():
-        # the one collective of the path, once per bin (not per step), on the library's own device buffer
+    def bin_exchange():
+        """The end of an output bin: fold the accumulators and -- on more than one GPU -- the ONE collective of the path."""
+        if world == 1:
+            ctx.bins_device_ptr()                                 # enqueues the fold of the persistent rows into the bin
+            return
         if lib_coll:
             if args.shard == "config":
                 ctx.reduce_bins(0)
@@ -409,17 +476,29 @@ def run_ours(args, shape, q):
                 gathered = multi.gather_q_shards(loc, len(q_all))         # concatenate the q-shards
                 assert gathered.shape == (len(q_all), 1 + shape.M)
 
+    def device_step(k, exchange=True):
+        for j in range(P):
+            ctx.select_slot((k * P + j) % use_slots)
+            ctx.measure()
+        if exchange:
+            bin_exchange()
+            ctx.reset_bins()
+
     # ---- value: device-resident --------------------------------------------------------------------------
-    # events bracket the dominant kernel (rho_q build) on every launch of the timed region; the two small kernels are
-    # timed in a separate pass below (an event between two kernels breaks their back-to-back staging)
+    # events bracket the dominant kernel (rho_q build) on every `profile_stride`-th launch of the timed region; the small
+    # kernels are timed in a separate pass below (an event between two kernels breaks their back-to-back staging)
     ctx.set_profiling({"all": True, "none": False}.get(args.profile, ["rho"]))
     ctx.set_profiling_stride(args.profile_stride)        # every 8th launch: an event pair costs ~3 us of stream time
     for k in range(W):
         device_step(k)
-    if world > 1:
-        bin_collective()       # warm-up of the collective too: NCCL connects its channels lazily on first use
-    ctx.kernel_times(reset=True)
+    # one bin checked for its bookkeeping before the timed region: every configuration of every rank is in it
+    device_step(0, exchange=False)
+    bin_exchange()
+    _, _, n_acc = ctx.read_bins()
+    expect_acc = B * P * (world if (lib_coll and args.shard == "config" and rank == 0) else 1)
+    assert n_acc == expect_acc, (n_acc, expect_acc)
     ctx.reset_bins()
+    ctx.kernel_times(reset=True)
     launches0 = ctx.launch_count()
     sampler = ClockSampler(local)
     sampler.start()
@@ -428,27 +507,19 @@ def run_ours(args, shape, q):
     e0.record(ext)
     for k in range(K):
         device_step(k)
-    if world > 1:
-        bin_collective()
     e1.record(ext)
     barrier()
     clocks = sampler.stop()
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    ms_total = allreduce(e0.elapsed_time(e1), dist.ReduceOp.MAX if world > 1 else None)
     launches = ctx.launch_count() - launches0
     ktimes = ctx.kernel_times(reset=True)
     ctx.set_profiling(False)
     ctx.set_profiling_stride(1)
-    evals_per_step = world * B if args.shard == "config" else B    # q-sharding: all ranks work on the same B walkers
+    evals_per_step = (world * B if args.shard == "config" else B) * P    # q-sharding: all ranks work on the same walkers
     value = evals_per_step * K / (ms_total * 1e-3)
-    _, _, n_acc = ctx.read_bins()
-    expect_acc = B * K * (world if (lib_coll and args.shard == "config" and rank == 0) else 1)   # the library's reduce sums the counts too
-    assert n_acc == expect_acc, (n_acc, expect_acc)
     if args.profile != "all":                      # untimed-region pass with every kernel bracketed: corr / bins durations
         ctx.set_profiling(True)
-        for k in range(max(10, min(K, 50))):
+        for k in range(max(2, min(K, 4))):
             device_step(k)
         kall = ctx.kernel_times(reset=True)
         for name in ("corr", "bins"):
@@ -458,35 +529,52 @@ def run_ours(args, shape, q):
         ctx.reset_bins()
         ctx.set_profiling(False)
 
-    # ---- e2e: host AoS buffers through the C ABI, H2D + D2H inside the timed region -------------------------
+    # ---- e2e: host AoS buffers through the C ABI, H2D of every batch + D2H of every bin inside the timed region ---------
     e2e = None
     if not args.no_e2e:
-        Ke = max(4, min(K, 60))
+        Ke = max(3, min(K, 8))
         ctx.reset_bins()
         ctx.stage(pinned[0].array, shape.N)
-        for k in range(3):                               # warm-up of the pipelined loop
-            ctx.measure()
-            ctx.stage_async(pinned[(k + 1) % use_slots].array, shape.N)
-            ctx.read_bins()
+
+        def e2e_step(k):
+            for j in range(P):
+                ctx.measure()                                                         # async: kernels on the staged batch
+                ctx.stage_async(pinned[(k * P + j + 1) % use_slots].array, shape.N)   # H2D of the next batch overlaps them
+            if world > 1:
+                bin_exchange()
+            ssf_bin, isf_bin, _ = ctx.read_bins()                                     # D2H of the bin (syncs)
+            ctx.reset_bins()
+
+        e2e_step(0)                                          # warm-up of the pipelined loop
         barrier()
         t0 = time.perf_counter()
         for k in range(Ke):
-            ctx.measure()                                               # async: kernels on batch k
-            ctx.stage_async(pinned[(k + 1) % use_slots].array, shape.N) # H2D of batch k+1 overlaps them, DMAs back to back
-            ssf_bin, isf_bin, _ = ctx.read_bins()                       # D2H of the step's result (syncs)
+            e2e_step(k)
         torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": evals_per_step * Ke / float(dt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(batch_bytes), "d2h_bytes_per_step": int((nq + nq * shape.M) * 8),
-               "steps": Ke, "path": "pimcb_stage_batch_async(pinned host AoS) + pimcb_measure + pimcb_read_bins, double-buffered"}
+        dt = allreduce(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
+        # in-run ceiling: the bare cudaMemcpyAsync rate of the same page-locked buffers, all ranks copying at the same time
+        ctx.sync()
+        barrier()
+        ceil_rank = ctx.h2d_peak_gbs(pinned[0].array, reps=12)
+        barrier()
+        ceil_min = allreduce(ceil_rank, dist.ReduceOp.MIN if world > 1 else None)
+        ceil_sum = allreduce(ceil_rank, dist.ReduceOp.SUM if world > 1 else None)
+        h2d_rate_rank = batch_bytes * P * Ke / dt / 1e9
+        e2e = {"value": evals_per_step * Ke / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(batch_bytes * P), "d2h_bytes_per_step": int((nq + nq * shape.M) * 8),
+               "steps": Ke, "h2d_gbs_per_gpu": h2d_rate_rank,
+               "h2d_ceiling_gbs": ceil_min, "h2d_ceiling_gbs_all_gpus": ceil_sum,
+               "frac_of_ceiling": h2d_rate_rank / ceil_min if ceil_min else None,
+               "ceiling": "bare cudaMemcpyAsync of one batch buffer, 12 back to back, all ranks concurrently, same run "
+                          "(pimcb_measure_h2d_peak); min over ranks",
+               "path": f"per step: {P} x [pimcb_measure + pimcb_stage_batch_async(pinned host AoS)] + "
+                       + ("the bin collective + " if world > 1 else "") + "pimcb_read_bins + pimcb_reset_bins, staging pipelined one batch ahead"}
 
     # ---- latency: ONE configuration through the synchronous ABI calls an estimator's accumulate() makes ----------
     latency = None
     if not args.no_e2e and not args.no_latency:
         one = np.ascontiguousarray(pinned[0].array[0])                   # pageable host copy, like Path::beads
-        ssf1, isf1 = ctx.stage(one, shape.N).ssf_isf()
+        ctx.stage(one, shape.N).ssf_isf()
         for _ in range(5):
             ctx.stage(one, shape.N).ssf_isf()
         nlat = 50
@@ -533,18 +621,25 @@ def run_ours(args, shape, q):
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
+    nominal_tflops = 148 * 64 * 2 * sm_max * 1e6 / 1e12               # 148 SMs x 64 DFMA lanes x 2 flop x clock
     alg_bytes = B * (8 * shape.ndim * shape.N * shape.M + 2 * 8 * nq * shape.M)
+    corr_avg_s = corr_ms * 1e-3 / max(1, corr_n)
     roofline = {
         "kernel": plan["path_name"],
         "bound": "fp64" if plan["path"] != 1 else "fp64 (DFMA phase A + DMMA tensor phase B share the FP64 units)",
         "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
         "frac": (achieved / peak_tflops) if achieved else None, "traffic": traffic,
-        "peak_source": "measured in this run: register-resident DFMA chains on all SMs (pimcb_measure_fp64_peak); "
-                       "MEASURED_PEAKS.json has no FP64 figure (DMMA m8n8k4 measures 37.0 TFLOP/s, tools/micro/dmma_peak.cu)",
+        "peak_source": "measured in this run: register-resident DFMA chains on all SMs (pimcb_measure_fp64_peak; SASS and ncu of that "
+                       "kernel: profiles/r02_fp64_peak.md); MEASURED_PEAKS.json has no FP64 figure",
+        "frac_vs_nominal": (achieved / nominal_tflops) if achieved else None, "nominal_peak": nominal_tflops,
+        "nominal_peak_source": f"148 SMs x 64 FP64 FMA lanes x 2 x {sm_max:.0f} MHz",
+        "frac_vs_dmma_probe": (achieved / 36.9) if achieved else None, "dmma_probe_peak": 36.9,
+        "dmma_probe_source": "tools/micro/dmma_peak.cu (mma.sync.m8n8k4.f64 chains), profiles/r01*_dmma_peak / DESIGN.md section 5",
         "flop_per_launch": B * kernel_flop, "flop_basis": "useful flop of the kernel that ran (DESIGN.md section 5)",
         "avg_launch_ms": rho_avg_s * 1e3, "launches_timed": rho_n,
-        "timing": f"CUDA events around every {args.profile_stride}-th launch of this kernel inside the timed region ({rho_n} of {K} steps)",
-        "share_of_step": rho_avg_s * 1e3 / max(1e-12, rho_avg_s * 1e3 + corr_ms / max(1, corr_n) + bins_ms / max(1, ktimes["bins"][1])),
+        "timing": f"CUDA events around every {args.profile_stride}-th launch of this kernel inside the timed region ({rho_n} of {K * P} launches)",
+        "share_of_step": rho_avg_s / max(1e-12, rho_avg_s + corr_avg_s + bins_ms * 1e-3 / max(1, ktimes["bins"][1])),
         "bins_kernel": {"avg_launch_ms": bins_ms / max(1, ktimes["bins"][1])},
         "plan": plan,
         # the same launch expressed in SURVEY.md section 8d's convention (one 40-flop sincos per (q, bead)): what a
@@ -552,17 +647,15 @@ def run_ours(args, shape, q):
         "survey_convention": {"flop_per_launch": B * rho_flop, "equivalent_tflops": B * rho_flop / rho_avg_s / 1e12 if rho_n else None},
         "hbm": {"achieved_gbs": alg_bytes / rho_avg_s / 1e9 if rho_n else None, "peak_gbs": hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"},
-        "corr_kernel": {"avg_launch_ms": corr_ms / max(1, corr_n), "achieved_tflops": B * corr_flop / (corr_ms * 1e-3 / max(1, corr_n)) / 1e12 if corr_n else None},
+        "corr_kernel": {"avg_launch_ms": corr_avg_s * 1e3, "achieved_tflops": B * corr_flop / corr_avg_s / 1e12 if corr_n else None},
     }
     # ---- A/B: the generic kernel (one sincos per (q, bead)) on the same batches, SURVEY 8d flop convention --------
     if plan["path"] != 0 and not args.no_ab:
         ctx.set_rho_mode(0)
         ctx.set_profiling(True)
-        for k in range(3):
-            device_step(k)
+        device_step(0)
         ctx.kernel_times(reset=True)
-        nab = max(5, min(K, 40))
-        for k in range(nab):
+        for k in range(2):
             device_step(k)
         kt0 = ctx.kernel_times(reset=True)
         ctx.set_profiling(False)
@@ -578,61 +671,7 @@ def run_ours(args, shape, q):
     # ---- secondary metric: per-slice pair-potential sums (Vint, gradVSquared on odd slices, sepHist) -------------
     pair = None
     if shape.ndim == 3 and not args.no_pair:
-        import math
-        max_sep = math.sqrt(sum((L / 2.0) ** 2 for L in shape.side))
-        Vt, dVt, drt = synth.aziz_table_numpy(max_sep)
-        ctx.set_pair_table(Vt, dVt, drt)
-        ctx.select_slot(0)
-        dSep = 0.5 * math.sqrt(3.0) * shape.side[2] / 50.0
-        ctx.set_profiling(True)
-        for _ in range(2):
-            ctx.pair_sums(dSep, want_f2=True, want_hist=True, f2_parity=1)
-        ctx.kernel_times(reset=True)
-        npair = 5
-        for k in range(npair):
-            ctx.select_slot(k % use_slots)
-            ctx.pair_sums(dSep, want_f2=True, want_hist=True, f2_parity=1)
-        pms, pn = ctx.kernel_times(reset=True)["pair"]
-        ctx.set_profiling(False)
-        p_s = pms * 1e-3 / max(1, pn)
-        pairs = shape.N * (shape.N - 1) // 2               # pairs per slice
-        # gsf action: even slices read V once per pair; odd slices read V and dV/dr once per pair in the symmetric kernel
-        # (pair_sym_kernel), or walk the full j != i loop in the both-ends kernel (2 visits per pair, each reads dV/dr,
-        # half of them also read V: 3 table reads per pair)
-        pair_sym = os.environ.get("PIMCB_PAIR_SYM", "1") != "0" and shape.N <= 1024      # every pair once on the force slices
-        gathers = B * ((shape.M - shape.M // 2) * pairs + (shape.M // 2) * (2 if pair_sym else 3) * pairs)
-        pair = {"metric": "pair-potential action sums/s (Vint[M] + gradVSquared[odd slices] + sepHist[M][50] per configuration)",
-                "kernel": "pair_sym_kernel (force slices: every pair once)" if pair_sym else "pair_kernel (force slices: both ends)",
-                "value": B / p_s, "unit": "configurations/s", "avg_launch_ms": p_s * 1e3, "launches_timed": pn,
-                "table_entries": len(Vt), "table_mb": 2 * 8 * len(Vt) / 1e6,
-                "gathers_per_launch": gathers, "gather_rate_g_per_s": gathers / p_s / 1e9,
-                "sector_traffic_tbs": 32.0 * gathers / p_s / 1e12,
-                "bound": "L2/HBM gather: 8-byte table reads move 32-byte sectors; the 106 MB of tables exceed what one L2 "
-                         "partition keeps, ncu shows 4.5 GB of DRAM reads per launch for the symmetric kernel, 6.4 GB for the "
-                         "both-ends kernel (profiles/traffic.json)"}
-
-    # ---- secondary: virial slice sums (rDOTgradU / deltaDOTgradU, gsf: T-matrix terms on odd slices) ---------------
-    if pair is not None:
-        d2Vt = np.gradient(dVt, drt)                   # timing only: central differences of the dV/dr table
-        ctx.set_pair_table_d2(d2Vt)
-        ctx.select_slot(0)
-        delta = 0.01 * pinned[0].array                 # any per-bead vectors in the beads' AoS shape
-        ctx.set_profiling(True)
-        ctx.virial_sums(delta, t2_parity=1)
-        ctx.kernel_times(reset=True)
-        nvir = 3
-        for k in range(nvir):
-            ctx.virial_sums(delta, t2_parity=1)
-        vms, vn = ctx.kernel_times(reset=True)["virial"]
-        ctx.set_profiling(False)
-        v_s = vms * 1e-3 / max(1, vn)
-        vir_sym = os.environ.get("PIMCB_VIRIAL_SYM", "1") != "0" and shape.N <= 1024
-        vg = B * shape.N * (shape.N - 1) * (shape.M + shape.M // 2) // (2 if vir_sym else 1)   # dV/dr on every slice, d2V/dr2 on odd ones
-        pair["virial_sums"] = {"metric": "virial slice sums/s (4 sums per slice; gsf action, window deltas from the host)",
-                               "kernel": "virial_sym_kernel (every pair once)" if vir_sym else "virial_kernel (both ends)",
-                               "value": B / v_s, "unit": "configurations/s", "avg_launch_ms": v_s * 1e3, "launches_timed": vn,
-                               "gathers_per_launch": vg, "gather_rate_g_per_s": vg / v_s / 1e9,
-                               "bound": "L2/HBM gather (same tables as the pair kernel + d2V/dr2)"}
+        pair = pair_legs(args, ctx, shape, pinned, use_slots, B)
 
     # ---- secondary: direct minimum-image S(q) for non-commensurate (`float`) wave-vectors --------
     direct = None
@@ -666,34 +705,107 @@ def run_ours(args, shape, q):
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak" if args.shard == "config" else "strong",
         "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{shape.name}: N={shape.N} M={shape.M} nq={nq} ndim={shape.ndim}, He-4 SVP density, "
-                               f"commensurate q, {B} walker configurations per GPU per step",
-                   "batch_per_gpu": B,
-                   "parallelism": (f"walker-configuration sharding x{world}, one NCCL reduce of the bin" if args.shard == "config"
-                                   else f"q-vector sharding x{world} ({nq} of {len(q_all)} q per GPU), one NCCL all-gather of the bin"),
-                   "l2": f"{use_slots} resident batches rotated ({footprint_mb:.0f} MB > 126 MB L2)",
-                   "rho_mode": args.rho_mode, "corr_mode": args.corr_mode,
-                   "collective": ("none (one GPU)" if world == 1 else
-                                  ("library NCCL (pimcb_reduce_bins / pimcb_gather_bins_q)" if lib_coll else "torch.distributed NCCL on the library's bin")),
-                   "host_binding": (f"rank bound to {len(numa_cpus)} GPU-local CPUs (NVML affinity)" if numa_cpus else "none")},
+        "config": shared_config(shape, len(q_all)),
+        "run": {"step": f"one output bin = {P} batches of {B} walker configurations per GPU ({evals_per_step} evaluations over {world} GPU(s)), "
+                        "bin folded" + (" and exchanged" if world > 1 else "") + " once per step",
+                "batch_per_gpu": B, "batches_per_step": P, "evaluations_per_step": evals_per_step,
+                "parallelism": (f"walker-configuration sharding x{world}, one NCCL reduce of the bin per step" if args.shard == "config"
+                                else f"q-vector sharding x{world} ({nq} of {len(q_all)} q per GPU), one NCCL all-gather of the bin per step"),
+                "l2": f"{use_slots} resident batches rotated ({footprint_mb:.0f} MB > 126 MB L2)",
+                "rho_mode": args.rho_mode, "corr_mode": args.corr_mode,
+                "collective": ("none (one GPU)" if world == 1 else
+                               ("library NCCL (pimcb_reduce_bins / pimcb_gather_bins_q)" if lib_coll else "torch.distributed NCCL on the library's bin")),
+                "host_binding": (f"rank bound to {len(numa_cpus)} GPU-local CPUs (NVML affinity)" if numa_cpus else "none")},
         "clocks": clocks, "e2e": e2e, "latency": latency, "gpu_launches": int(launches), "roofline": roofline, "pair_sums": pair, "ssf_direct": direct,
     }
-
+    beads_one = np.array(pinned[0].array[0])
+    for pa in pinned:
+        pa.free()
+    ctx.close()
+    if rank == 0 and world == 1 and not args.no_ab:
+        roofline["upstream_gpu_ab"] = upstream_gpu_ab(shape, q_all, beads_one)
+        ab = roofline["upstream_gpu_ab"]
+        if ab and latency:
+            ab["ours_single_configuration_evaluations_per_s"] = latency["evaluations_per_s"]
+            ab["ours_device_resident_evaluations_per_s"] = value
+            ab["speedup_single_call_vs_accumulate_pattern"] = latency["evaluations_per_s"] / ab["best_accumulate_evaluations_per_s"]
+            ab["speedup_device_resident_vs_kernels"] = value / ab["best_kernels_evaluations_per_s"]
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        os.sched_setaffinity(0, all_cpus)             # the CPU arm gets every host core again
-        arm = CpuArm(shape, q, args.cpu_seconds)
-        full_s, _ = arm.step()
-        line["cpu_baseline"] = {"value": 1.0 / full_s, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
-                                "sample": arm.sample_text(), "one_core_value": 1.0 / arm.one_core()}
+        # the GPU work is over and its buffers are gone: the CPU arm gets every host core again; same sample and the same
+        # warm-up + averaging as --impl reference
+        os.sched_setaffinity(0, all_cpus)
+        arm = CpuArm(shape, q_all, args.cpu_seconds)
+        cpu_value, _ = time_cpu_arm(arm, 2, 1)
+        line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+                                "sample": arm.sample_text(), "one_core_value": 1.0 / arm.one_core(), "extrapolated": True,
+                                "full_size_record": FULL_SIZE_RECORD,
+                                "note": "the GPU/CPU ratio is ~10^4 algorithm (O(Nq M^2 N^2) pair loop vs the factorised O(Nq N M) form) "
+                                        "and ~10^2 hardware; the roofline fraction, not this ratio, measures the kernels"}
     else:
         line["cpu_baseline"] = None
     if rank == 0:
         emit(line)
-    for pa in pinned:
-        pa.free()
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def pair_legs(args, ctx, shape, pinned, use_slots, B):
+    """Per-slice pair-potential sums (Vint, gradVSquared on the odd slices of the gsf action, sepHist) and the virial slice
+    sums of the same batches, against the measured gather roofline of their access pattern."""
+    import math
+    max_sep = math.sqrt(sum((L / 2.0) ** 2 for L in shape.side))
+    Vt, dVt, drt = synth.aziz_table_numpy(max_sep)
+    ctx.set_pair_table(Vt, dVt, drt)
+    ctx.select_slot(0)
+    dSep = 0.5 * math.sqrt(3.0) * shape.side[2] / 50.0
+    ctx.set_profiling(True)
+    for _ in range(2):
+        ctx.pair_sums(dSep, want_f2=True, want_hist=True, f2_parity=1)
+    ctx.kernel_times(reset=True)
+    npair = 5
+    for k in range(npair):
+        ctx.select_slot(k % use_slots)
+        ctx.pair_sums(dSep, want_f2=True, want_hist=True, f2_parity=1)
+    pms, pn = ctx.kernel_times(reset=True)["pair"]
+    ctx.set_profiling(False)
+    p_s = pms * 1e-3 / max(1, pn)
+    pairs = shape.N * (shape.N - 1) // 2               # pairs per slice
+    # gsf action: even slices read V once per pair, odd slices V and dV/dr once per pair (every pair is visited once)
+    gathers = B * ((shape.M - shape.M // 2) * pairs + (shape.M // 2) * 2 * pairs)
+    gather_peak = 289.0e9                              # profiles/r02a_gather_peak.txt: 32-byte sectors / s out of L2, footprint <= 53 MB
+    tile = os.environ.get("PIMCB_PAIR_TILE", "1") != "0"
+    pair = {"metric": "pair-potential action sums/s (Vint[M] + gradVSquared[odd slices] + sepHist[M][50] per configuration)",
+            "kernel": "pair_tile_kernel (32 x 32 tiles, every pair once)" if tile else "pair_sym_kernel (ring, every pair once)",
+            "value": B / p_s, "unit": "configurations/s", "avg_launch_ms": p_s * 1e3, "launches_timed": pn,
+            "table_entries": len(Vt), "table_mb": 2 * 8 * len(Vt) / 1e6,
+            "pairs_per_launch": B * shape.M * pairs, "pair_rate_g_per_s": B * shape.M * pairs / p_s / 1e9,
+            "gathers_per_launch": gathers, "gather_rate_g_per_s": gathers / p_s / 1e9,
+            "roofline": {"bound": "L2 sector rate of random 8-byte table reads", "achieved": gathers / p_s / 1e9, "peak": gather_peak / 1e9,
+                         "unit": "G reads/s", "frac": gathers / p_s / gather_peak,
+                         "peak_source": "tools/micro/gather_peak.cu on this pool's B200 (profiles/r02a_gather_peak.txt): 289 G reads/s for "
+                                        "footprints <= 53 MB, 140 G/s at 106 MB (V + dV/dr tables of C2), 73 G/s from DRAM",
+                         "hbm_algorithmic": {"bytes": 8 * gathers + B * 8 * shape.ndim * shape.N * shape.M,
+                                             "achieved_gbs": (8 * gathers + B * 8 * shape.ndim * shape.N * shape.M) / p_s / 1e9}}}
+    d2Vt = np.gradient(dVt, drt)                   # timing only: central differences of the dV/dr table
+    ctx.set_pair_table_d2(d2Vt)
+    ctx.select_slot(0)
+    delta = 0.01 * pinned[0].array                 # any per-bead vectors in the beads' AoS shape
+    ctx.set_profiling(True)
+    ctx.virial_sums(delta, t2_parity=1)
+    ctx.kernel_times(reset=True)
+    nvir = 3
+    for k in range(nvir):
+        ctx.virial_sums(delta, t2_parity=1)
+    vms, vn = ctx.kernel_times(reset=True)["virial"]
+    ctx.set_profiling(False)
+    v_s = vms * 1e-3 / max(1, vn)
+    vg = B * pairs * (shape.M + shape.M // 2)      # dV/dr on every slice, d2V/dr2 on the odd ones, every pair once
+    pair["virial_sums"] = {"metric": "virial slice sums/s (4 sums per slice; gsf action, window deltas from the host)",
+                           "value": B / v_s, "unit": "configurations/s", "avg_launch_ms": v_s * 1e3, "launches_timed": vn,
+                           "gathers_per_launch": vg, "gather_rate_g_per_s": vg / v_s / 1e9,
+                           "roofline": {"bound": "L2 sector rate of random 8-byte table reads", "achieved": vg / v_s / 1e9,
+                                        "peak": gather_peak / 1e9, "unit": "G reads/s", "frac": vg / v_s / gather_peak}}
+    return pair
 
 
 _REAL_STDOUT = None

@@ -116,6 +116,9 @@ int pimcb_ssf_isf_beads(pimcb_ctx* ctx, const double* beads_aos, int M, int N, i
  * accumulation of all staged configurations on the ctx stream and returns without synchronising. */
 int pimcb_measure(pimcb_ctx* ctx);
 int pimcb_reset_bins(pimcb_ctx* ctx);
+/* Lays out the zeroed bin for M time slices before any measurement (q-vectors must be set): a rank whose share of a
+ * walker batch is empty can then take part in pimcb_reduce_bins / pimcb_gather_bins_q with a zero contribution. */
+int pimcb_init_bins(pimcb_ctx* ctx, int M);
 /* Copies bins to the host (synchronises): ssf[nq], isf[nq*M] sums over accumulated configurations;
  * *num_accumulated = configurations in the bin. */
 int pimcb_read_bins(pimcb_ctx* ctx, double* ssf /*[nq] or NULL*/, double* isf /*[nq*M] or NULL*/, long* num_accumulated);
@@ -142,6 +145,12 @@ int pimcb_pair_sums(pimcb_ctx* ctx, double* vint, double* f2, int* sephist, doub
  * beads' own AoS shape ([B][M][N_ext][ndim]; evaluated by the caller through the reference's PotentialBase, O(N M));
  * it is used by pimcb_pair_sums until new beads are staged.  NULL clears it ("free" external potential, the default). */
 int pimcb_set_external_gradient(pimcb_ctx* ctx, const double* gext_aos);
+/* The virial terms see the external potential twice (src/action.cpp:1446-1784): gV_i = externalPtr->gradV(r_i) + sum_j
+ * gradV(r_ij) in all four terms (the gradient above), and inside the T-matrix of the second-order terms dV = dVi + |gVe_i|,
+ * d2V = g2Vi + externalPtr->grad2V(r_i) (:1522-1523, 1546-1547, 1721-1722).  `g2ext_aos` holds those Laplacians for the
+ * CURRENTLY staged beads, one double per bead ([B][M][N_ext]); used by pimcb_virial_sums until new beads are staged.
+ * NULL clears it.  With either array set, pimcb_virial_sums runs the both-ends kernel with the external terms. */
+int pimcb_set_external_laplacian(pimcb_ctx* ctx, const double* g2ext_aos);
 
 /* ---- scattering variants ---------------------------------------------------
  * pimcb_elastic: replaces ElasticScatteringEstimatorGpu::accumulate (src/estimator.cpp:4197-4235; kernel
@@ -198,6 +207,9 @@ int pimcb_gather_bins_q(pimcb_ctx* ctx, const int* nq_per_rank, double* ssf, dou
  * Sustained FP64 DFMA throughput of the device in TFLOP/s (register-resident FMA chains on every SM,
  * timed with CUDA events).  MEASURED_PEAKS.json carries no FP64 figure. */
 int pimcb_measure_fp64_peak(pimcb_ctx* ctx, double* tflops, double seconds_target);
+/* Bare host-to-device rate (GB/s) of `reps` back-to-back cudaMemcpyAsync of a page-locked buffer on this context's copy
+ * stream: the in-run ceiling of the host-fed (e2e) path.  Measurement only. */
+int pimcb_measure_h2d_peak(pimcb_ctx* ctx, const void* pinned_src, size_t bytes, int reps, double* gbs);
 /* Per-kernel device time.  With profiling on, every kernel launch is bracketed by CUDA events on the stream it is
  * launched on; pimcb_kernel_times synchronises, folds the pending event pairs into running totals and returns, per
  * kernel id, the summed duration in ms and the number of launches since the last reset:

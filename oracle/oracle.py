@@ -84,6 +84,8 @@ class Oracle:
         L.orc_virial_delta.argtypes = [C.c_int, _dp, _up, _dp, C.c_int, C.c_int, C.c_int, _ip, C.c_int, _dp]
         L.orc_virial_sums.argtypes = [C.c_int, _dp, _up, _dp, C.c_int, C.c_int, C.c_int, _ip, C.c_int, _dp, _dp, C.c_int,
                                       C.c_double, _dp, _dp, C.c_int, _dp, C.c_int]
+        L.orc_virial_sums_ext.argtypes = [C.c_int, _dp, _up, _dp, C.c_int, C.c_int, C.c_int, _ip, C.c_int, _dp, _dp, C.c_int,
+                                          C.c_double, _dp, _dp, C.c_int, _dp, C.c_int, _dp, _dp]
         L.orc_virial_energy.argtypes = [C.c_int, _dp, _up, _dp, C.c_int, C.c_int, C.c_int, _ip, C.c_int, _dp, _dp, _dp, _dp, _dp,
                                         C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, _dp]
 
@@ -314,16 +316,23 @@ class Oracle:
         assert rc == 0
         return out
 
-    def virial_sums(self, side, beads, N, window, dVdr, d2V, dr, t2_parity=-1, next_links=None, periodic=None, nthreads=1):
-        """[M][4] = {sum gV.r, sum (gV T).r, sum gV.delta, sum (gV T).delta} per slice."""
+    def virial_sums(self, side, beads, N, window, dVdr, d2V, dr, t2_parity=-1, next_links=None, periodic=None, nthreads=1,
+                    gext=None, g2ext=None):
+        """[M][4] = {sum gV.r, sum (gV T).r, sum gV.delta, sum (gV T).delta} per slice.  gext [M][Next][nd] / g2ext [M][Next]:
+        gradient and Laplacian of the external potential per bead (None = free)."""
         beads, M, Next, nd = self._beads(beads)
         side, per = self._box(side, periodic)
         nl = self._links(next_links)
         dVdr, d2V = _f64(dVdr), _f64(d2V)
         ext = np.zeros(2)
         out = np.zeros((M, 4))
-        rc = self.lib.orc_virial_sums(nd, _dptr(side), per.ctypes.data_as(_up), _dptr(beads), M, N, Next, _iptr(nl), window,
-                                      _dptr(dVdr), _dptr(d2V), len(dVdr), dr, _dptr(ext), _dptr(ext), t2_parity, _dptr(out), nthreads)
+        ge = _f64(gext) if gext is not None else None
+        g2 = _f64(g2ext) if g2ext is not None else None
+        assert ge is None or ge.shape == beads.shape
+        assert g2 is None or g2.shape == beads.shape[:2]
+        rc = self.lib.orc_virial_sums_ext(nd, _dptr(side), per.ctypes.data_as(_up), _dptr(beads), M, N, Next, _iptr(nl), window,
+                                          _dptr(dVdr), _dptr(d2V), len(dVdr), dr, _dptr(ext), _dptr(ext), t2_parity, _dptr(out), nthreads,
+                                          _dptr(ge) if ge is not None else None, _dptr(g2) if g2 is not None else None)
         assert rc == 0
         return out
 

@@ -500,16 +500,25 @@ struct VirialTables {
 
 // One slice: out[0] = sum_i gV_i.r_i (rDOTgradUterm1 without VFactor*tau, src/action.cpp:1446-1478),
 // out[1] = sum_i (gV_i T_i).r_i (rDOTgradUterm2 without 2*gradVFactor*tau^3*lambda, :1493-1575),
-// out[2], out[3] the same with delta_i in place of r_i (deltadotgradUterm1/2, :1588-1784).  External potential "free".
+// out[2], out[3] the same with delta_i in place of r_i (deltadotgradUterm1/2, :1588-1784).
+// gext [M][Next][ND] = externalPtr->gradV(path(bead)), g2ext [M][Next] = externalPtr->grad2V(path(bead)) (null = "free"):
+// gV = gVe + sum gVi (:1471, :1525), dV = dVi + dVe and d2V = g2Vi + g2Ve inside the T-matrix (:1546-1547).
 template <int ND>
 void virial_slice(const Box& box, const VirialTables& tab, const double* beads, const Links& L, int N, int slice, int window,
-                  bool want_t2, double* out) {
+                  bool want_t2, double* out, const double* gext = nullptr, const double* g2ext = nullptr) {
     const int Next = L.Next;
     out[0] = out[1] = out[2] = out[3] = 0.0;
     for (int i = 0; i < N; ++i) {
         const double* r1 = bead<ND>(beads, Next, slice, i);
-        double gV[ND], tMat[ND][ND];
-        for (int a = 0; a < ND; ++a) { gV[a] = 0.0; for (int b = 0; b < ND; ++b) tMat[a][b] = 0.0; }
+        double gV[ND], gVe[ND], gVsum[ND], tMat[ND][ND];       // gV: term2 order (gVe first, :1525); gVsum: the pair part alone
+        for (int a = 0; a < ND; ++a) {
+            gVe[a] = gext ? gext[(static_cast<size_t>(slice) * Next + i) * ND + a] : 0.0;
+            gV[a] = 0.0 + gVe[a];                                                                   // gV += gVe, :1525
+            gVsum[a] = 0.0;
+            for (int b = 0; b < ND; ++b) tMat[a][b] = 0.0;
+        }
+        const double dVe = std::sqrt(dot<ND>(gVe, gVe));
+        const double g2Ve = g2ext ? g2ext[static_cast<size_t>(slice) * Next + i] : 0.0;
         for (int j = 0; j < N; ++j) {
             double rDiff[ND];
             separation<ND>(box, r1, bead<ND>(beads, Next, slice, j), rDiff);
@@ -521,15 +530,17 @@ void virial_slice(const Box& box, const VirialTables& tab, const double* beads, 
             if (want_t2) {
                 const double dVi = std::sqrt(dot<ND>(gVi, gVi));
                 const double g2Vi = table_direct(tab.d2V, tab.len, tab.dr, tab.extd2V, rmag);      // potential.h:1010-1016
-                const double dV = dVi + 0.0, d2V = g2Vi + 0.0;
+                const double dV = dVi + dVe, d2V = g2Vi + g2Ve;
                 for (int a = 0; a < ND; ++a)
                     for (int b = 0; b < ND; ++b) {
                         tMat[a][b] += rDiff[a] * rDiff[b] * d2V / (rmag * rmag) - rDiff[a] * rDiff[b] * dV / pow(rmag, 3);
                         if (a == b) tMat[a][b] += dV / rmag;
                     }
             }
-            for (int d = 0; d < ND; ++d) gV[d] += gVi[d];
+            for (int d = 0; d < ND; ++d) { gV[d] += gVi[d]; gVsum[d] += gVi[d]; }
         }
+        double gV1[ND];                                            // term1: gV = gVe + gVi (:1471, :1647)
+        for (int d = 0; d < ND; ++d) gV1[d] = gVe[d] + gVsum[d];
         double gVdotT[ND];
         for (int row = 0; row < ND; ++row) {                                                        // common.h:187-199
             double acc = 0.0;
@@ -538,8 +549,8 @@ void virial_slice(const Box& box, const VirialTables& tab, const double* beads, 
         }
         double delta[ND];
         virial_delta<ND>(box, beads, L, slice, i, window, delta);
-        out[0] += dot<ND>(gV, r1);
-        out[2] += dot<ND>(gV, delta);
+        out[0] += dot<ND>(gV1, r1);
+        out[2] += dot<ND>(gV1, delta);
         if (want_t2) {
             out[1] += dot<ND>(gVdotT, r1);
             out[3] += dot<ND>(gVdotT, delta);
@@ -1015,9 +1026,21 @@ int orc_virial_delta(int ndim, const double* side, const unsigned* periodic, con
 }
 
 // out[M][4] per slice (see virial_slice); t2_parity: -1 all slices, 0/1 slices of that parity, -2 none.
+int orc_virial_sums_ext(int ndim, const double* side, const unsigned* periodic, const double* beads, int M, int N, int Next,
+                        const int* next, int window, const double* dVdr, const double* d2V, int len, double dr,
+                        const double* extdVdr, const double* extd2V, int t2_parity, double* out, int nthreads,
+                        const double* gext, const double* g2ext);
 int orc_virial_sums(int ndim, const double* side, const unsigned* periodic, const double* beads, int M, int N, int Next,
                     const int* next, int window, const double* dVdr, const double* d2V, int len, double dr,
                     const double* extdVdr, const double* extd2V, int t2_parity, double* out, int nthreads) {
+    return orc_virial_sums_ext(ndim, side, periodic, beads, M, N, Next, next, window, dVdr, d2V, len, dr, extdVdr, extd2V, t2_parity,
+                               out, nthreads, nullptr, nullptr);
+}
+// the same with a non-trivial external potential: gext [M][Next][ndim], g2ext [M][Next] (either may be null)
+int orc_virial_sums_ext(int ndim, const double* side, const unsigned* periodic, const double* beads, int M, int N, int Next,
+                        const int* next, int window, const double* dVdr, const double* d2V, int len, double dr,
+                        const double* extdVdr, const double* extd2V, int t2_parity, double* out, int nthreads,
+                        const double* gext, const double* g2ext) {
     if (ndim < 1 || ndim > 3) return -100;
     const Box b = make_box(ndim, side, periodic);
     const Links L(next, M, N, Next);
@@ -1027,9 +1050,9 @@ int orc_virial_sums(int ndim, const double* side, const unsigned* periodic, cons
         for (int s = s0; s < s1; ++s) {
             const bool t2 = t2_parity == -1 || (t2_parity >= 0 && (s % 2) == t2_parity);
             double* o = out + static_cast<size_t>(s) * 4;
-            if (ndim == 1) virial_slice<1>(b, tab, beads, L, N, s, window, t2, o);
-            else if (ndim == 2) virial_slice<2>(b, tab, beads, L, N, s, window, t2, o);
-            else virial_slice<3>(b, tab, beads, L, N, s, window, t2, o);
+            if (ndim == 1) virial_slice<1>(b, tab, beads, L, N, s, window, t2, o, gext, g2ext);
+            else if (ndim == 2) virial_slice<2>(b, tab, beads, L, N, s, window, t2, o, gext, g2ext);
+            else virial_slice<3>(b, tab, beads, L, N, s, window, t2, o, gext, g2ext);
         }
     };
     if (nthreads < 1) nthreads = 1;

@@ -195,6 +195,7 @@ public:
     explicit SpringTestPotential(double k_) : k(k_) {}
     double V(const dVec& r) override { return 0.5 * k * dot(r, r); }
     dVec gradV(const dVec& r) override { return k * r; }
+    double grad2V(const dVec&) override { return NDIM * k; }      // Laplacian: enters the T-matrix of the virial terms
 private:
     double k;
 };

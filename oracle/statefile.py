@@ -48,7 +48,8 @@ def write_state(path, beads, on=None, n_moves=7, n_estimators=4, rng_words=8, ne
             for p in range(W):
                 if on[s, p]:
                     a, b = nxt[s][p]
-                    prv[a][b] = (s, p)
+                    if 0 <= a < M and 0 <= b < W:                     # (tests write deliberately broken links too)
+                        prv[a][b] = (s, p)
     with open(path, "w") as f:
         f.write(f"{int(on.sum()) // M}\n")                            # getNumParticles()
         for k in range(1 + n_moves + n_estimators):                  # "%16d\t%16d\n" acceptance / sampling lines

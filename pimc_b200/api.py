@@ -28,7 +28,7 @@ SYMBOLS = [
     "pimcb_pair_sums", "pimcb_measure_fp64_peak", "pimcb_set_profiling", "pimcb_set_profiling_stride", "pimcb_kernel_times",
     "pimcb_launch_count", "pimcb_rho_plan_info", "pimcb_elastic", "pimcb_ssf_cyl", "pimcb_set_pair_table_d2",
     "pimcb_virial_sums", "pimcb_comm_unique_id", "pimcb_comm_init", "pimcb_comm_destroy", "pimcb_reduce_bins",
-    "pimcb_gather_bins_q", "pimcb_set_external_gradient",
+    "pimcb_gather_bins_q", "pimcb_set_external_gradient", "pimcb_set_external_laplacian", "pimcb_init_bins", "pimcb_measure_h2d_peak",
 ]
 
 
@@ -111,6 +111,9 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.pimcb_set_pair_table_d2.argtypes = [vp, _dp, C.c_int, _dp]
     lib.pimcb_virial_sums.argtypes = [vp, _dp, C.c_int, _dp]
     lib.pimcb_set_external_gradient.argtypes = [vp, _dp]
+    lib.pimcb_set_external_laplacian.argtypes = [vp, _dp]
+    lib.pimcb_init_bins.argtypes = [vp, C.c_int]
+    lib.pimcb_measure_h2d_peak.argtypes = [vp, C.c_void_p, C.c_size_t, C.c_int, _dp]
     lib.pimcb_comm_unique_id.argtypes = [C.c_char_p]
     lib.pimcb_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
     lib.pimcb_comm_destroy.argtypes = [vp]
@@ -287,7 +290,7 @@ class Context:
         self._chk(self.lib.pimcb_reset_bins(self._h))
 
     def read_bins(self):
-        _, M, _ = self.shape
+        M = self.shape[1] if getattr(self, "shape", None) else self._bins_M     # nothing staged yet: the init_bins layout
         ssf = np.zeros(self.nq)
         isf = np.zeros((self.nq, M))
         n = C.c_long(0)
@@ -318,6 +321,23 @@ class Context:
         """gext: gradient of the external potential per bead, shaped like the staged beads (or None to clear)."""
         g = _f64(gext) if gext is not None else None
         self._chk(self.lib.pimcb_set_external_gradient(self._h, _ptr(g)))
+
+    def h2d_peak_gbs(self, pinned_array: np.ndarray, reps: int = 8) -> float:
+        """Bare cudaMemcpyAsync rate of a page-locked array on this context's copy stream (GB/s)."""
+        g = C.c_double(0.0)
+        self._chk(self.lib.pimcb_measure_h2d_peak(self._h, pinned_array.ctypes.data_as(C.c_void_p), pinned_array.nbytes, int(reps),
+                                                  C.byref(g)))
+        return g.value
+
+    def init_bins(self, M: int):
+        """Zeroed bin for M slices before any measurement (lets an idle rank join the bin collective)."""
+        self._chk(self.lib.pimcb_init_bins(self._h, int(M)))
+        self._bins_M = int(M)
+
+    def set_external_laplacian(self, g2ext):
+        """g2ext: Laplacian of the external potential per bead, [B][M][N_ext] (or [M][N_ext]; None to clear)."""
+        g = _f64(g2ext) if g2ext is not None else None
+        self._chk(self.lib.pimcb_set_external_laplacian(self._h, _ptr(g)))
 
     def pair_sums(self, dSep=None, want_f2=True, want_hist=True, f2_parity=-1):
         B, M, _ = self.shape

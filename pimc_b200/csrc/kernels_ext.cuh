@@ -133,7 +133,10 @@ __global__ void ssf_cyl_finalize_kernel(const double* __restrict__ partial, doub
 // and out[sl] = { sum_i gV_i.r_i, sum_i (T_i gV_i).r_i, sum_i gV_i.delta_i, sum_i (T_i gV_i).delta_i }.
 // The prefactors (VFactor tau, 2 gradVFactor tau^3 lambda) are applied by the caller.  t2_parity selects the slices
 // whose gradVFactor is finite (-1 all, 0 even, 1 odd, -2 none): the T-matrix terms of the others are returned as 0,
-// as upstream skips them (action.cpp:1505, 1680).  External potential "free" (zero gradient and Laplacian).
+// as upstream skips them (action.cpp:1505, 1680).
+// EXT (non-free external potential; both-ends kernel only): gext[sl][d][Npad] = externalPtr->gradV(r_i), g2ext[sl][Npad] =
+// externalPtr->grad2V(r_i).  gV_i = gVe_i + sum_j gVi (action.cpp:1471, 1525, 1647, 1704) and, inside the T-matrix, dV = dVi +
+// dVe_i with dVe_i = |gVe_i|, d2V = g2Vi + g2Ve_i (action.cpp:1546-1547, 1721-1722).
 // ---------------------------------------------------------------------------------------------
 #ifndef PIMCB_VIRIAL_UNROLL
 #define PIMCB_VIRIAL_UNROLL 2
@@ -148,9 +151,10 @@ struct VirialParams {
     const double* dVdr; const double* d2V; int len; double dr; double extdV[2]; double extd2V[2]; int t2_parity; int M;
 };
 
-template <int ND>
+template <int ND, bool EXT>
 __global__ void __launch_bounds__(256, PIMCB_VIRIAL_MINB) virial_kernel(const double* __restrict__ pos, const double* __restrict__ delta, int nslices,
-                                                         int N, int Npad, BoxDev box, VirialParams vp, double* __restrict__ out) {
+                                                         int N, int Npad, BoxDev box, VirialParams vp, double* __restrict__ out,
+                                                         const double* __restrict__ gext, const double* __restrict__ g2ext) {
     constexpr int NT = ND * (ND + 1) / 2;
     constexpr int U = PIMCB_VIRIAL_UNROLL;
     extern __shared__ __align__(16) double sm[];
@@ -171,6 +175,17 @@ __global__ void __launch_bounds__(256, PIMCB_VIRIAL_MINB) virial_kernel(const do
             for (int d = 0; d < ND; ++d) gV[d] = 0.0;
 #pragma unroll
             for (int k = 0; k < NT; ++k) T[k] = 0.0;
+            double gVe[ND], dVe = 0.0, g2Ve = 0.0;
+            if constexpr (EXT) {
+                double e2 = 0.0;
+#pragma unroll
+                for (int d = 0; d < ND; ++d) {
+                    gVe[d] = gext ? __ldg(gext + static_cast<size_t>(sl) * ND * Npad + d * Npad + i) : 0.0;
+                    e2 = __dadd_rn(e2, __dmul_rn(gVe[d], gVe[d]));
+                }
+                dVe = __dsqrt_rn(e2);                                   // sqrt(dot(gVe,gVe)), action.cpp:1522
+                g2Ve = g2ext ? __ldg(g2ext + static_cast<size_t>(sl) * Npad + i) : 0.0;
+            }
             // U partners in flight per thread, consumed in partner order (sums identical to the one-at-a-time loop): the
             // gathers are the long pole, exactly as in pair_kernel (52 % of the stall samples of the U = 1 version were a
             // warp waiting for its single outstanding table read; profiles/r01x_kernels.md)
@@ -202,9 +217,10 @@ __global__ void __launch_bounds__(256, PIMCB_VIRIAL_MINB) virial_kernel(const do
                         g2 = fma(gi[d], gi[d], g2);
                     }
                     if (do_t2) {
-                        const double dV = sqrt(g2);
+                        const double dV = EXT ? sqrt(g2) + dVe : sqrt(g2);
+                        const double d2V = EXT ? d2[w] + g2Ve : d2[w];
                         const double rinv = 1.0 / r[w];
-                        const double a = d2[w] * rinv * rinv - dV * rinv * rinv * rinv;
+                        const double a = d2V * rinv * rinv - dV * rinv * rinv * rinv;
                         const double diag = dV * rinv;
                         int k = 0;
 #pragma unroll
@@ -213,6 +229,10 @@ __global__ void __launch_bounds__(256, PIMCB_VIRIAL_MINB) virial_kernel(const do
                             for (int q = p; q < ND; ++q, ++k) T[k] = fma(sep[w][p] * sep[w][q], a, T[k]) + (p == q ? diag : 0.0);
                     }
                 }
+            }
+            if constexpr (EXT) {
+#pragma unroll
+                for (int d = 0; d < ND; ++d) gV[d] += gVe[d];
             }
             double u[ND];
 #pragma unroll

@@ -1,0 +1,276 @@
+// kernels_pair.cuh -- pair-potential slice sums, second generation.
+//
+// What the first-generation kernels (pair_kernel / pair_sym_kernel, kernels.cuh / kernels_ext.cuh) taught
+// (profiles/r02b_pair_probe.txt, r02a_gather_peak.txt, r02c_pipe_rates.txt):
+//   * shrinking the tables 16x changes their time by 7 % -- they are bound by instruction issue, not by the gathers:
+//     ~170 warp-instructions per pair, of which three IEEE divisions, one IEEE square root and three floor() go
+//     through multi-instruction sequences on the slow conversion / MUFU pipe, and the force slices add a shared-memory
+//     read-add-write per component plus one CTA barrier per ring step;
+//   * the gathers themselves are bounded by the rate at which L2 hands out 32-byte sectors: 289 G sectors/s while the
+//     footprint stays below ~53 MB, 140 G/s at 106 MB (two 53 MB tables).
+// This kernel attacks the instruction side:
+//   * TILES instead of a ring.  Particles are cut into groups of 32; a warp owns a home group (lane = particle, force in
+//     registers) and meets the other groups one 32 x 32 tile at a time, partner m = (lane + s) & 31 at step s, so every
+//     pair is visited exactly once (half ring over GROUPS, half ring inside the diagonal tile).  The partner's share of
+//     a pair force travels to its lane with one warp shuffle per component and accumulates there in registers: no
+//     shared-memory read-add-writes, no barrier inside a slice (one per round of four group offsets).  Each tile parks
+//     the partner-side sums in its own shared-memory slot and a fixed-order fold adds them: results are reproducible.
+//   * The table index without a division or a correctly rounded square root.  k = int(r/dr) and the histogram bin
+//     int(r/dSep) only need r to a few ulp unless r/dr lies within 2^-20 of an integer: r comes from MUFU.RSQ64H + two
+//     Goldschmidt steps (which also yield 1/r for the force), the quotient is a multiplication by the rounded
+//     reciprocal, and floor() and the fractional part are read from the bits of t + 1.5 * 2^e.  The rare unsafe cases
+//     (|frac - integer| < 2^-20, 2 in 10^6 pairs) and everything outside the fast path's validity re-run the
+//     reference's exact operation sequence (minimage_norm / __ddiv_rn), so k and the histogram stay BIT-IDENTICAL to
+//     the CPU (include/potential.h:249-260, src/action.cpp:216-224) -- the tests hold sepHist to array_equal.
+//   * Minimum image by rint(): sep = s - pSide * rint(s * sideInv) with rint() as an add/subtract of 1.5 * 2^52 (three
+//     FP64 instructions per component instead of five plus an FRND); it differs from Container::putInBC's
+//     floor(x + 0.5) (include/container.h:50-59) only on exact ties, where both images are equally near and r is the
+//     same to rounding -- covered by the same safety margin.
+#pragma once
+
+#include "kernels.cuh"
+
+namespace pimcb {
+
+struct PairTileParams {
+    const double* V; const double* dVdr; int len; double dr, inv_dr; double extV[2]; double extdV[2];
+    double dSep, inv_dSep; int want_hist; int f2_parity; int M;
+    const double* gext;    // gradient of the external potential per bead, slice rows like pos ([sl][d][Npad]), or nullptr
+    double magic;          // 1.5 * 2^e: ulp(magic) = 2^-fb, table indices < 2^(e-1)
+    int fb;                // fraction bits below the integer part in the low word of (t + magic), <= 28
+    int G;                 // particle groups of 32
+    int spc;               // slices per CTA work unit (> 1 when a slice has fewer groups than the CTA has warps)
+};
+
+constexpr int kPairWarps = 8;
+constexpr int kPairRound = 4;        // group offsets per round (partner-side slots in shared memory)
+constexpr double kRintMagic = 6755399441055744.0;   // 1.5 * 2^52
+
+// r ~ sqrt(r2) and rinv ~ 1/sqrt(r2), both to ~2 ulp: MUFU.RSQ64H seed + two Goldschmidt iterations.
+__device__ __forceinline__ void rsqrt_pair(double r2, double& r, double& rinv) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2));
+    double g = r2 * y, h = 0.5 * y;
+    double e = fma(-h, g, 0.5);
+    g = fma(g, e, g);
+    h = fma(h, e, h);
+    e = fma(-h, g, 0.5);
+    r = fma(g, e, g);
+    rinv = 2.0 * fma(h, e, h);
+}
+
+// floor(t) and "t is safely away from an integer", from the bits of t + magic (magic = 1.5 * 2^e, fb = 52 - e fraction bits).
+// Returns false when t is out of the trick's range (negative, too large, NaN) or within 2^-20 of an integer.
+__device__ __forceinline__ bool floor_safe(double t, double magic, int fb, int& k) {
+    const double u = t + magic;
+    const unsigned lo = static_cast<unsigned>(__double2loint(u)), hi = static_cast<unsigned>(__double2hiint(u));
+    const unsigned mhi = static_cast<unsigned>(__double2hiint(magic));
+    // same exponent and the leading mantissa bit of 1.5 still set: u in [magic, magic + 2^(e-1))
+    const bool in_range = (hi >> 19) == (mhi >> 19);
+    k = static_cast<int>(((hi & 0x7ffffu) << (32 - fb)) | (lo >> fb));
+    const unsigned frac = lo & ((1u << fb) - 1u);
+    const unsigned eps = 1u << (fb - 20);
+    return in_range && (frac - eps) < ((1u << fb) - 2u * eps);
+}
+
+// One tile: the 32 particles of the home group (lane = particle i, position xi) against the 32 particles of group b
+// (positions xb[d * NP + m]), steps [s_lo, s_hi), partner m = (lane + s) & 31.  FORCE: own-side force into Fi, partner-side
+// force into Gv (it ends up in the lane that holds the partner: particle 32 b + lane).
+template <int ND, bool FORCE>
+__device__ __forceinline__ void pair_tile(const double* __restrict__ xsl, int NP, const double (&xi)[ND], int i, bool ivalid, int b,
+                                          int lane, int s_lo, int s_hi, bool diag, int N, const BoxDev& box,
+                                          const PairTileParams& pp, int* __restrict__ shist_sl, double& vsum, double (&Fi)[ND],
+                                          double (&Gv)[ND]) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const double* xb = xsl + 32 * b;
+    for (int s = s_lo; s < s_hi; s += 2) {
+        double sep[2][ND], r[2], rinv[2], vv[2], dv[2];
+        int kidx[2], nR[2];
+        bool valid[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int ss = s + u;
+            const int m = (lane + ss) & 31;
+            const int j = 32 * b + m;
+            valid[u] = ivalid && j < N && !(diag && ss == 16 && lane >= 16);
+            double r2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                const double sd = xi[d] - xb[d * NP + m];
+                const double tt = fma(sd, box.sideInv[d], kRintMagic) - kRintMagic;
+                sep[u][d] = fma(-box.pSide[d], tt, sd);
+                r2 = fma(sep[u][d], sep[u][d], r2);
+            }
+            if (!valid[u]) r2 = 1.0;
+            rsqrt_pair(r2, r[u], rinv[u]);
+            bool safe = floor_safe(r[u] * pp.inv_dr, pp.magic, pp.fb, kidx[u]);
+            nR[u] = 0;
+            if (pp.want_hist) {
+                int nr;
+                safe = floor_safe(r[u] * pp.inv_dSep, pp.magic, pp.fb, nr) && safe;
+                nR[u] = nr;
+            }
+            if (!safe && valid[u]) {
+                // the reference's own operation sequence (putInBC -> dot -> sqrt -> r/dr -> int()), bit for bit
+                double sx[ND];
+                const double rx = minimage_norm<ND>(xsl, NP, i, j, box, sx);
+                kidx[u] = __double2int_rz(__ddiv_rn(rx, pp.dr));
+                if (pp.want_hist) nR[u] = __double2int_rz(__ddiv_rn(rx, pp.dSep));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {           // both gathers of the step pair are issued here
+            const bool inside = kidx[u] > 0 && kidx[u] < pp.len;
+            vv[u] = 0.0;
+            dv[u] = 0.0;
+            if (valid[u]) {
+                vv[u] = inside ? __ldg(pp.V + kidx[u]) : (kidx[u] <= 0 ? pp.extV[0] : pp.extV[1]);
+                if (FORCE) dv[u] = inside ? __ldg(pp.dVdr + kidx[u]) : (kidx[u] <= 0 ? pp.extdV[0] : pp.extdV[1]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            vsum += vv[u];
+            if (pp.want_hist && valid[u] && nR[u] >= 0 && nR[u] < kNPCFSEP) atomicAdd(&shist_sl[nR[u]], 1);
+            if constexpr (FORCE) {
+                const double g = dv[u] * rinv[u];      // (dV/dr)/r, potential.h:997-1003
+                const int src = (lane - (s + u)) & 31;  // the lane whose partner this lane is at this step
+#pragma unroll
+                for (int d = 0; d < ND; ++d) {
+                    const double f = g * sep[u][d];    // 0 for invalid pairs (dv = 0)
+                    Fi[d] += f;
+                    Gv[d] -= __shfl_sync(FULL, f, src);          // gradV(sep_ji) = -gradV(sep_ij)
+                }
+            }
+        }
+    }
+}
+
+#ifndef PIMCB_PTILE_MINB
+#define PIMCB_PTILE_MINB 3
+#endif
+template <int ND>
+__global__ void __launch_bounds__(32 * kPairWarps, PIMCB_PTILE_MINB)
+pair_tile_kernel(const double* __restrict__ pos, int nslices, int N, int Npad, BoxDev box, PairTileParams pp,
+                 double* __restrict__ vint, double* __restrict__ f2, int* __restrict__ hist) {
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) double sm[];
+    const int G = pp.G, spc = pp.spc, NP = 32 * G;
+    double* xs = sm;                                            // [spc][ND][NP]
+    double* accF = xs + static_cast<size_t>(spc) * ND * NP;     // [spc][ND][NP]     total force per particle
+    double* part = accF + static_cast<size_t>(spc) * ND * NP;   // [kPairRound][spc][ND][NP] partner-side sums per offset
+    double* redV = part + static_cast<size_t>(kPairRound) * spc * ND * NP;   // [spc * G]  per-home V sums
+    int* shist = reinterpret_cast<int*>(redV + spc * G + (spc * G & 1));     // [spc][kNPCFSEP]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int omax = G / 2;                                     // largest group offset (a half tile when G is even)
+    const bool f2_any = f2 != nullptr;
+    const int nunits = (nslices + spc - 1) / spc;
+
+    for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+        const int sl0 = unit * spc;
+        const int nsl = min(spc, nslices - sl0);
+        // stage the slices of this unit: rows padded to whole groups (the padding is never read as a valid particle)
+        for (int k = threadIdx.x; k < nsl * ND * NP; k += blockDim.x) {
+            const int s = k / (ND * NP), rem = k - s * (ND * NP), d = rem / NP, i = rem - d * NP;
+            xs[k] = i < Npad ? __ldg(pos + (static_cast<size_t>(sl0 + s) * ND + d) * Npad + i) : 0.0;
+            if (f2_any) accF[k] = 0.0;
+        }
+        if (pp.want_hist)
+            for (int k = threadIdx.x; k < nsl * kNPCFSEP; k += blockDim.x) shist[k] = 0;
+        __syncthreads();
+
+        // rounds of kPairRound group offsets (one partner-side slot each); the first round also takes the diagonal tiles
+        for (int o1 = 1; o1 == 1 || o1 <= omax; o1 += kPairRound) {
+            for (int h = warp; h < nsl * G; h += kPairWarps) {
+                const int sloc = h / G, a = h - sloc * G;
+                const int sl = sl0 + sloc, t = sl % pp.M;
+                const bool do_f = f2_any && (pp.f2_parity < 0 || (t & 1) == pp.f2_parity);
+                const double* xsl = xs + static_cast<size_t>(sloc) * ND * NP;
+                int* shist_sl = shist + sloc * kNPCFSEP;
+                const int i = 32 * a + lane;
+                const bool ivalid = i < N;
+                double xi[ND], Fi[ND];
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { xi[d] = xsl[d * NP + i]; Fi[d] = 0.0; }
+                double vsum = 0.0;
+                for (int oi = (o1 == 1 ? -1 : 0); oi < kPairRound; ++oi) {
+                    const int o = oi < 0 ? 0 : o1 + oi;         // oi = -1: the diagonal tile
+                    if (o > omax) break;
+                    int s_lo, s_hi;                             // steps [s_lo, s_hi) of this tile
+                    if (o == 0) { s_lo = 1; s_hi = 17; }        // diagonal: distances 1..15 for every lane, 16 for lanes < 16
+                    else if (2 * o == G) { s_lo = a < o ? 0 : 1; s_hi = s_lo + 16; }   // the offset shared with the opposite group
+                    else { s_lo = 0; s_hi = 32; }
+                    int b = a + o;
+                    if (b >= G) b -= G;
+                    double Gv[ND];
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) Gv[d] = 0.0;
+                    if (do_f) {
+                        pair_tile<ND, true>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, o == 0, N, box, pp, shist_sl, vsum, Fi, Gv);
+                        if (o == 0) {
+#pragma unroll
+                            for (int d = 0; d < ND; ++d) Fi[d] += Gv[d];        // the diagonal tile's partners are the home group itself
+                        } else {
+                            double* slot = part + ((static_cast<size_t>(oi) * spc + sloc) * ND) * NP + 32 * b + lane;
+#pragma unroll
+                            for (int d = 0; d < ND; ++d) slot[d * NP] = Gv[d];
+                        }
+                    } else {
+                        pair_tile<ND, false>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, o == 0, N, box, pp, shist_sl, vsum, Fi, Gv);
+                    }
+                }
+                if (do_f) {
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) accF[(static_cast<size_t>(sloc) * ND + d) * NP + i] += Fi[d];   // this lane is the only writer
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) vsum += __shfl_xor_sync(FULL, vsum, off);
+                if (lane == 0) redV[h] = o1 == 1 ? vsum : redV[h] + vsum;
+            }
+            __syncthreads();
+            if (f2_any) {
+                // fold the partner-side slots of this round, offsets ascending (fixed order)
+                for (int k = threadIdx.x; k < nsl * ND * NP; k += blockDim.x) {
+                    const int sloc = k / (ND * NP);
+                    const int t = (sl0 + sloc) % pp.M;
+                    if (!(pp.f2_parity < 0 || (t & 1) == pp.f2_parity)) continue;
+                    const int rem = k - sloc * (ND * NP);
+                    double acc = accF[k];
+                    for (int oi = 0; oi < kPairRound && o1 + oi <= omax; ++oi)
+                        acc += part[(static_cast<size_t>(oi) * spc + sloc) * ND * NP + rem];
+                    accF[k] = acc;
+                }
+                __syncthreads();
+            }
+        }
+        // per-slice results: Vint = sum of the home sums (home order), sum_i |F_i + gradVext_i|^2
+        for (int sloc = warp; sloc < nsl; sloc += kPairWarps) {
+            const int sl = sl0 + sloc, t = sl % pp.M;
+            const bool do_f = f2_any && (pp.f2_parity < 0 || (t & 1) == pp.f2_parity);
+            double fsum = 0.0;
+            if (do_f) {
+                for (int i = lane; i < N; i += 32) {
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) {
+                        double F = accF[(static_cast<size_t>(sloc) * ND + d) * NP + i];
+                        if (pp.gext) F += __ldg(pp.gext + (static_cast<size_t>(sl) * ND + d) * Npad + i);      // action.cpp:1216
+                        fsum = fma(F, F, fsum);
+                    }
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) fsum += __shfl_xor_sync(FULL, fsum, off);
+            if (lane == 0) {
+                double v = 0.0;
+                for (int a = 0; a < G; ++a) v += redV[sloc * G + a];
+                vint[sl] = v;
+                if (f2) f2[sl] = fsum;
+            }
+            if (pp.want_hist)
+                for (int k = lane; k < kNPCFSEP; k += 32) hist[static_cast<size_t>(sl) * kNPCFSEP + k] = shist[sloc * kNPCFSEP + k];
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace pimcb

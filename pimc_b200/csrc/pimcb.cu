@@ -4,6 +4,7 @@
 #include "../../include/pimc_b200.h"
 #include "kernels.cuh"
 #include "kernels_ext.cuh"
+#include "kernels_pair.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -150,7 +151,8 @@ struct pimcb_ctx {
     unsigned long gen_counter = 0, cfg_gen = 0;
     int cfg_slot = -1;
     // scattering variants (elastic, cylinder S(q)) and virial slice sums
-    DevBuf d_var, d_inside, d_d2V, d_delta_aos, d_delta, d_vir, d_gext;
+    DevBuf d_var, d_inside, d_d2V, d_delta_aos, d_delta, d_vir, d_gext, d_g2ext;
+    unsigned long g2ext_gen = 0;            // staging generation the uploaded external-potential Laplacian belongs to (0 = none)
     unsigned long gext_gen = 0;             // staging generation the uploaded external-potential gradient belongs to (0 = none)
     bool have_d2V = false;
     double extd2V[2] = {0, 0};
@@ -766,7 +768,7 @@ int pimcb_destroy(pimcb_ctx* c) {
     c->h_out.release();
     for (DevBuf* b : {&c->d_q, &c->d_comm, &c->d_qn, &c->d_qidx, &c->d_plan, &c->d_rho, &c->d_cfg, &c->d_bins, &c->d_partial,
                       &c->d_V, &c->d_dV, &c->d_vint, &c->d_f2, &c->d_hist, &c->d_scratch, &c->d_sched, &c->d_binrows, &c->d_unfold,
-                      &c->d_var, &c->d_inside, &c->d_d2V, &c->d_delta_aos, &c->d_delta, &c->d_vir, &c->d_gext, &c->d_gather, &c->d_count})
+                      &c->d_var, &c->d_inside, &c->d_d2V, &c->d_delta_aos, &c->d_delta, &c->d_vir, &c->d_gext, &c->d_g2ext, &c->d_gather, &c->d_count})
         b->release();
     for (int k = 0; k < kKernels; ++k) { cudaEventDestroy(c->ev0[k]); cudaEventDestroy(c->ev1[k]); }
     for (auto& r : c->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -1114,6 +1116,9 @@ int fused_finish(pimcb_ctx* c, Slot& s, int slot, double* ssf_out, double* isf_o
     const double* h = static_cast<const double*>(c->h_out.p);
     if (ssf_out) std::memcpy(ssf_out, h, sizeof(double) * c->nq);
     if (isf_out) std::memcpy(isf_out, h + c->nq, sizeof(double) * (len - c->nq));
+    // the slot now holds exactly the graph's configuration: shape fields included (the rotating stagers may have put
+    // another shape with the same buffers into this slot in between)
+    s.B = 1; s.M = c->fused.M; s.N = c->fused.N; s.Npad = round_up(c->fused.N, 16); s.Next = c->fused.Next;
     s.staged = true;
     s.needs_transpose = false;
     s.gen = ++c->gen_counter;
@@ -1206,6 +1211,8 @@ int pimcb_ssf_isf_beads(pimcb_ctx* c, const double* beads, int M, int N, int Nex
             const void* now[8];
             fused_addresses(c, c->slots[g.slot], now);
             if (std::memcmp(now, g.baked, sizeof now) == 0) {
+                // a pimcb_stage_batch_async into the graph's slot may still be copying on the copy stream
+                CU(cudaStreamWaitEvent(c->stream, c->slots[g.slot].ready, 0));
                 CU(cudaGraphLaunch(g.exec, c->stream));
                 c->launches += g.launches;
                 return fused_finish(c, c->slots[g.slot], g.slot, ssf_out, isf_out);
@@ -1250,6 +1257,26 @@ int pimcb_measure(pimcb_ctx* c) {
         CU(cudaGetLastError());
     }
     c->n_acc += s->B;
+    return 0;
+}
+
+// Creates the (zeroed) bin for M time slices before anything was measured, so that a rank whose share of a walker batch is
+// empty still takes part in pimcb_reduce_bins / pimcb_gather_bins_q with a zero contribution instead of leaving its peers
+// waiting inside the collective.
+int pimcb_init_bins(pimcb_ctx* c, int M) {
+    if (!c || M < 1) return fail(PIMCB_EINVAL, "bad arguments");
+    if (c->nq <= 0) return fail(PIMCB_ESTATE, "no q-vectors set");
+    CU(cudaSetDevice(c->device));
+    const size_t len = static_cast<size_t>(c->nq) * (1 + M);
+    if (c->bins_len == len && c->bins_M == M) return 0;             // already laid out (possibly holding sums)
+    int rc = c->d_bins.ensure(sizeof(double) * len);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(c->d_bins.p, 0, sizeof(double) * len, c->stream));
+    c->bins_len = len;
+    c->bins_M = M;
+    c->n_acc = 0;
+    c->binrows_n = 0;
+    c->binrows_cap = 0;
     return 0;
 }
 
@@ -1360,6 +1387,25 @@ int pimcb_set_external_gradient(pimcb_ctx* c, const double* gext_aos) {
     return 0;
 }
 
+int pimcb_set_external_laplacian(pimcb_ctx* c, const double* g2ext_aos) {
+    if (!c) return fail(PIMCB_EINVAL, "null ctx");
+    if (!g2ext_aos) { c->g2ext_gen = 0; return 0; }
+    CU(cudaSetDevice(c->device));
+    Slot* s;
+    int rc = need_cur(c, &s);
+    if (rc) return rc;
+    const int nsl = s->B * s->M, Next = s->Next > 0 ? s->Next : s->N;
+    // [B][M][N_ext] -> slice rows [sl][Npad] (zero padded); O(N M) values, packed on the host
+    std::vector<double> rows(static_cast<size_t>(nsl) * s->Npad, 0.0);
+    for (int sl = 0; sl < nsl; ++sl)
+        std::memcpy(&rows[static_cast<size_t>(sl) * s->Npad], g2ext_aos + static_cast<size_t>(sl) * Next, sizeof(double) * s->N);
+    if ((rc = c->d_g2ext.ensure(sizeof(double) * rows.size()))) return rc;
+    CU(cudaMemcpyAsync(c->d_g2ext.p, rows.data(), sizeof(double) * rows.size(), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));          // `rows` is a local
+    c->g2ext_gen = s->gen;
+    return 0;
+}
+
 int pimcb_pair_sums(pimcb_ctx* c, double* vint, double* f2, int* sephist, double dSep, int f2_parity) {
     if (!c || !vint) return fail(PIMCB_EINVAL, "null argument");
     CU(cudaSetDevice(c->device));
@@ -1391,8 +1437,29 @@ int pimcb_pair_sums(pimcb_ctx* c, double* vint, double* f2, int* sephist, double
         // force slices: every pair once (pair_sym_kernel) when the slice fits its particles-per-thread variants;
         // PIMCB_PAIR_SYM=0 forces the both-ends kernel (A/B)
         static const bool sym_on = !(std::getenv("PIMCB_PAIR_SYM") && std::atoi(std::getenv("PIMCB_PAIR_SYM")) == 0);
+        // second-generation kernel (kernels_pair.cuh): 32 x 32 tiles, partner forces by warp shuffle, division-free table
+        // index with an exact fallback; PIMCB_PAIR_TILE=0 selects the first-generation kernels (A/B)
+        static const bool tile_on = !(std::getenv("PIMCB_PAIR_TILE") && std::atoi(std::getenv("PIMCB_PAIR_TILE")) == 0);
+        const int G = (s->N + 31) / 32;
+        const int spc = std::max(1, kPairWarps / G);
+        const size_t smem_tile = sizeof(double) * (static_cast<size_t>(spc) * nd * 32 * G * (2 + kPairRound) + spc * G + 1) +
+                                 sizeof(int) * spc * kNPCFSEP;
+        int ebits = 24;
+        while ((1ll << (ebits - 1)) <= static_cast<long long>(c->tab_len) + 2) ++ebits;
         const size_t smem_sym = sizeof(double) * 2 * nd * s->Npad;
-        if (f2 && sym_on && s->N <= 1024 && smem_sym <= 200 * 1024) {
+        if (tile_on && smem_tile <= 200 * 1024 && ebits <= 31) {
+            PairTileParams tp{c->d_V.as<double>(), c->d_dV.as<double>(), c->tab_len, c->dr, 1.0 / c->dr, {c->extV[0], c->extV[1]},
+                              {c->extdV[0], c->extdV[1]}, pp.dSep, 1.0 / pp.dSep, pp.want_hist, f2_parity, s->M, pp.gext,
+                              std::ldexp(1.5, ebits), 52 - ebits, G, spc};
+            const int units = (nsl + spc - 1) / spc;
+#define LAUNCH_PTILE(ND)                                                                                          \
+            rc = set_smem(pair_tile_kernel<ND>, smem_tile); if (rc) return rc;                                      \
+            pair_tile_kernel<ND><<<units, 32 * kPairWarps, smem_tile, c->stream>>>(s->pos.as<double>(), nsl, s->N, s->Npad, c->box, tp, \
+                                                                                  c->d_vint.as<double>(), f2 ? c->d_f2.as<double>() : nullptr, \
+                                                                                  c->d_hist.as<int>())
+            if (nd == 1) { LAUNCH_PTILE(1); } else if (nd == 2) { LAUNCH_PTILE(2); } else { LAUNCH_PTILE(3); }
+#undef LAUNCH_PTILE
+        } else if (f2 && sym_on && s->N <= 1024 && smem_sym <= 200 * 1024) {
 #define LAUNCH_PSYM(ND, PPT)                                                                                       \
             rc = set_smem(pair_sym_kernel<ND, PPT>, smem_sym); if (rc) return rc;                                   \
             pair_sym_kernel<ND, PPT><<<grid, 256, smem_sym, c->stream>>>(s->pos.as<double>(), nsl, s->N, s->Npad, c->box, pp, \
@@ -1523,7 +1590,12 @@ int pimcb_virial_sums(pimcb_ctx* c, const double* delta_aos, int t2_parity, doub
         static const bool sym_on = !(std::getenv("PIMCB_VIRIAL_SYM") && std::atoi(std::getenv("PIMCB_VIRIAL_SYM")) == 0);
         const int nc = nd + nd * (nd + 1) / 2;
         const size_t smem_sym = sizeof(double) * (2 * nd + nc) * s->Npad;
-        if (sym_on && s->N <= 1024 && smem_sym <= 200 * 1024) {
+        // a non-free external potential (gradient / Laplacian uploaded for THIS configuration) couples to every term:
+        // both-ends kernel with the per-bead external arrays
+        const double* d_gext = (c->gext_gen != 0 && c->gext_gen == s->gen) ? c->d_gext.as<double>() : nullptr;
+        const double* d_g2ext = (c->g2ext_gen != 0 && c->g2ext_gen == s->gen) ? c->d_g2ext.as<double>() : nullptr;
+        const bool ext = d_gext != nullptr || d_g2ext != nullptr;
+        if (!ext && sym_on && s->N <= 1024 && smem_sym <= 200 * 1024) {
 #define LAUNCH_VSYM(ND, PPT)                                                                                       \
             rc = set_smem(virial_sym_kernel<ND, PPT>, smem_sym); if (rc) return rc;                                 \
             virial_sym_kernel<ND, PPT><<<nsl, 256, smem_sym, c->stream>>>(s->pos.as<double>(), d_delta, nsl, s->N, s->Npad, c->box, vp, \
@@ -1534,11 +1606,14 @@ int pimcb_virial_sums(pimcb_ctx* c, const double* delta_aos, int t2_parity, doub
 #undef LAUNCH_VSYM
         } else {
         const size_t smem = sizeof(double) * 2 * nd * s->Npad;
-#define LAUNCH_VIR(ND)                                                                                             \
-        rc = set_smem(virial_kernel<ND>, smem); if (rc) return rc;                                                  \
-        virial_kernel<ND><<<nsl, 256, smem, c->stream>>>(s->pos.as<double>(), d_delta, nsl, s->N, s->Npad, c->box, vp, c->d_vir.as<double>())
-        if (nd == 1) { LAUNCH_VIR(1); } else if (nd == 2) { LAUNCH_VIR(2); } else { LAUNCH_VIR(3); }
+#define LAUNCH_VIR2(ND, EXT)                                                                                       \
+        rc = set_smem(virial_kernel<ND, EXT>, smem); if (rc) return rc;                                             \
+        virial_kernel<ND, EXT><<<nsl, 256, smem, c->stream>>>(s->pos.as<double>(), d_delta, nsl, s->N, s->Npad, c->box, vp, \
+                                                              c->d_vir.as<double>(), d_gext, d_g2ext)
+#define LAUNCH_VIR(ND) if (ext) { LAUNCH_VIR2(ND, true); } else { LAUNCH_VIR2(ND, false); }
+        if (nd == 1) { LAUNCH_VIR(1) } else if (nd == 2) { LAUNCH_VIR(2) } else { LAUNCH_VIR(3) }
 #undef LAUNCH_VIR
+#undef LAUNCH_VIR2
         }
         CU(cudaGetLastError());
     }
@@ -1672,6 +1747,27 @@ int pimcb_measure_fp64_peak(pimcb_ctx* c, double* tflops, double seconds_target)
     }
     CU(cudaGetLastError());
     *tflops = best;
+    return 0;
+}
+
+// Bare host-to-device rate of THIS process's link: `reps` back-to-back cudaMemcpyAsync of a page-locked buffer on the copy
+// stream, nothing else in flight -- the ceiling the staged (e2e) path is measured against in the same run.
+int pimcb_measure_h2d_peak(pimcb_ctx* c, const void* pinned_src, size_t bytes, int reps, double* gbs) {
+    if (!c || !pinned_src || !gbs || bytes == 0 || reps < 1) return fail(PIMCB_EINVAL, "bad arguments");
+    CU(cudaSetDevice(c->device));
+    int rc = c->d_scratch.ensure(bytes);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    cudaEvent_t e0 = c->ev0[kKernels - 1], e1 = c->ev1[kKernels - 1];
+    CU(cudaMemcpyAsync(c->d_scratch.p, pinned_src, bytes, cudaMemcpyHostToDevice, c->copy_stream));     // warm-up
+    CU(cudaEventRecord(e0, c->copy_stream));
+    for (int r = 0; r < reps; ++r) CU(cudaMemcpyAsync(c->d_scratch.p, pinned_src, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaEventRecord(e1, c->copy_stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    *gbs = static_cast<double>(bytes) * reps / (ms * 1e-3) / 1e9;
     return 0;
 }
 

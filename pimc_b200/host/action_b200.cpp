@@ -30,8 +30,8 @@ LocalActionB200::LocalActionB200(const Path& _path, LookupTable& _lookup, Potent
 
 // externalPtr->gradV(path(bead)) for every active bead, O(N M) on the host through the reference's own PotentialBase
 // (src/action.cpp:1216: added to the pair force of the bead before squaring).  NULL when all gradients vanish (`free`).
-const std::vector<double>* LocalActionB200::externalGradient() {
-    if (!needF2) return nullptr;
+const std::vector<double>* LocalActionB200::externalGradient(bool always) {
+    if (!needF2 && !always) return nullptr;
     const auto ext = path.get_beads_extents();
     const size_t Next = ext[1];
     bool any = false;
@@ -47,6 +47,23 @@ const std::vector<double>* LocalActionB200::externalGradient() {
         }
     }
     return any ? &gext : nullptr;
+}
+
+// externalPtr->grad2V(path(bead)) for every active bead (src/action.cpp:1523, 1698); NULL when every Laplacian vanishes.
+const std::vector<double>* LocalActionB200::externalLaplacian() {
+    const auto ext = path.get_beads_extents();
+    const size_t Next = ext[1];
+    bool any = false;
+    g2ext.assign(static_cast<size_t>(path.numTimeSlices) * Next, 0.0);
+    for (int slice = 0; slice < path.numTimeSlices; ++slice) {
+        const int n = path.numBeadsAtSlice(slice);
+        for (int i = 0; i < n; ++i) {
+            const double g2 = externalPtr->grad2V(path(slice, i));
+            g2ext[static_cast<size_t>(slice) * Next + i] = g2;
+            any = any || g2 != 0.0;
+        }
+    }
+    return any ? &g2ext : nullptr;
 }
 
 const B200Session::PairSums& LocalActionB200::sums() {
@@ -113,10 +130,16 @@ double LocalActionB200::derivPotentialActionLambda(int slice) {
 // ---- virial / pressure terms ----------------------------------------------------------------------------------------
 // The virial estimator walks slice = 0..M-1 calling all of these per slice (src/estimator.cpp:1160-1172); they share one
 // device pass.  Only the first of them (deltaDOTgradUterm1, the first call of that loop) marks a new configuration in
-// unhooked mode.  External potential: zero gradient / Laplacian only (FreePotential), as for gradVSquared.
+// unhooked mode.  External potential: its gradient and Laplacian per bead are evaluated on the host through the reference's
+// own PotentialBase (O(N M)) and travel with the configuration; `free` uploads nothing.
 const double* LocalActionB200::virial(int slice) {
     const int t2 = needF2 ? f2Parity : -2;
-    return &B200Session::get(path).virialSums(constants()->virialWindow(), t2)[static_cast<size_t>(slice) * 4];
+    B200Session& session = B200Session::get(path);
+    if (session.haveVirialSums(constants()->virialWindow(), t2))
+        return &session.virialSums(constants()->virialWindow(), t2)[static_cast<size_t>(slice) * 4];
+    const std::vector<double>* ge = externalGradient(true);
+    const std::vector<double>* g2 = needF2 ? externalLaplacian() : nullptr;
+    return &session.virialSums(constants()->virialWindow(), t2, ge, g2)[static_cast<size_t>(slice) * 4];
 }
 
 double LocalActionB200::rDOTgradUterm1(int slice) { return VFactor[slice % 2] * tau() * virial(slice)[0]; }

@@ -62,7 +62,9 @@ private:
     const double* virial(int slice);        // the four sums of `slice`
     double externalV(int slice);
     std::vector<double> gext;               // gradVext per bead ([M][N_ext][NDIM]); left empty while every gradient is zero ("free")
-    const std::vector<double>* externalGradient();
+    std::vector<double> g2ext;              // grad2Vext per bead ([M][N_ext]), for the T-matrix of the virial terms
+    const std::vector<double>* externalGradient(bool always = false);
+    const std::vector<double>* externalLaplacian();
 };
 
 #endif

@@ -178,7 +178,8 @@ void B200Session::setPairTableD2(const double* d2Vdr2, int len, const double* ex
     have_vir_ = false;
 }
 
-const std::vector<double>& B200Session::virialSums(int window, int t2Parity) {
+const std::vector<double>& B200Session::virialSums(int window, int t2Parity, const std::vector<double>* gext,
+                                                   const std::vector<double>* g2ext) {
     if (!(have_vir_ && vir_window_ == window && vir_parity_ == t2Parity)) {
         stageIfNeeded();
         const auto ext = path_.get_beads_extents();
@@ -219,6 +220,8 @@ const std::vector<double>& B200Session::virialSums(int window, int t2Parity) {
             }
         }
         vir_.assign(static_cast<size_t>(M) * 4, 0.0);
+        check(pimcb_set_external_gradient(ctx_, gext ? gext->data() : nullptr), "pimcb_set_external_gradient");
+        check(pimcb_set_external_laplacian(ctx_, g2ext ? g2ext->data() : nullptr), "pimcb_set_external_laplacian");
         check(pimcb_virial_sums(ctx_, delta_.data(), have_d2_ ? t2Parity : -2, vir_.data()), "pimcb_virial_sums");
         vir_window_ = window;
         vir_parity_ = t2Parity;
@@ -242,6 +245,8 @@ void B200Session::readBins(std::vector<double>& ssf, std::vector<double>& isf, l
 }
 
 void B200Session::resetBins() { check(pimcb_reset_bins(ctx_), "pimcb_reset_bins"); }
+
+void B200Session::initBins() { check(pimcb_init_bins(ctx_, path_.numTimeSlices), "pimcb_init_bins"); }
 
 void B200Session::uniqueId(void* id128) {
     if (pimcb_comm_unique_id(id128) != 0) {

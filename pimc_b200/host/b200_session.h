@@ -53,6 +53,7 @@ public:
     void measureBatch(const double* beads, int B, int M, int N, int Next);
     void readBins(std::vector<double>& ssf, std::vector<double>& isf, long& count);
     void resetBins();
+    void initBins();                                    // zeroed bin before any measurement (idle ranks join the reduce)
     static void uniqueId(void* id128);
     void commInit(int nranks, int rank, const void* id128);
     long reduceBins(int root);
@@ -66,7 +67,11 @@ public:
     // sum (T gV).delta}; delta (bead minus the centroid of its world-line window, src/action.cpp:1620-1647) is
     // computed here from the path's links.  t2Parity as pimcb_virial_sums.
     void setPairTableD2(const double* d2Vdr2, int len, const double* extd2Vdr2);
-    const std::vector<double>& virialSums(int window, int t2Parity);
+    // gext / g2ext (may be NULL = "free"): gradient ([M][N_ext][NDIM]) and Laplacian ([M][N_ext]) of the external potential
+    // per bead; they enter all four terms (src/action.cpp:1471, 1522-1547)
+    const std::vector<double>& virialSums(int window, int t2Parity, const std::vector<double>* gext = nullptr,
+                                          const std::vector<double>* g2ext = nullptr);
+    bool haveVirialSums(int window, int t2Parity) const { return have_vir_ && vir_window_ == window && vir_parity_ == t2Parity; }
     bool havePairSums(bool wantF2) const { return have_pair_ && (pair_has_f2_ || !wantF2); }
     void invalidate() { staged_ = false; have_sf_ = false; have_pair_ = false; have_es_ = have_cyl_ = have_vir_ = false; }
     void beginIfUnhooked() { if (!hooked_) invalidate(); }

@@ -47,7 +47,8 @@ static int stateReport(const char* file, int N, double density) {
     std::cout.precision(17);
     std::cout << "header=" << st.headerWorldLines << std::endl << "slices=" << st.numTimeSlices << std::endl
               << "worldlines=" << st.numWorldLines << std::endl << "beadsOn=" << st.numBeadsOn() << std::endl
-              << "diagonal=" << st.isDiagonal() << std::endl << "leftPacked=" << st.isLeftPacked() << std::endl;
+              << "diagonal=" << st.isDiagonal() << std::endl << "leftPacked=" << st.isLeftPacked() << std::endl
+              << "linksClosed=" << st.linksClosed() << std::endl;
     if (!st.isLeftPacked()) st.leftPack();
     st.putInside(box);
     if (st.nextLink.size() == st.beads.size())

@@ -180,6 +180,7 @@ int main(int argc, char** argv) {
         std::fseek(fb, static_cast<long>(lo * rec * sizeof(double)), SEEK_SET);
         std::vector<double> buf(rec * batch);
         long mine = 0;
+        session.initBins();                      // a rank with an empty share still joins the reduce with a zero bin
         for (long k = lo; k < hi; k += batch) {
             const int nb = static_cast<int>(std::min<long>(batch, hi - k));
             if (std::fread(buf.data(), sizeof(double), rec * nb, fb) != rec * nb) { std::cerr << "short read" << std::endl; return 1; }
@@ -222,6 +223,10 @@ int main(int argc, char** argv) {
         if (!st.isDiagonal() || st.numTimeSlices != M || st.numBeadsAtSlice[0] != N || st.numWorldLines != extent) {
             std::cerr << name << ": not a diagonal configuration of " << N << " particles x " << M << " slices (extent "
                       << extent << ")" << std::endl;
+            std::exit(EXIT_FAILURE);
+        }
+        if ((wantEnergy || wantVirial) && !st.linksClosed()) {
+            std::cerr << name << ": world-line links are not closed over the active beads (the kinetic / virial estimators walk them)" << std::endl;
             std::exit(EXIT_FAILURE);
         }
         if (!st.isLeftPacked()) st.leftPack();

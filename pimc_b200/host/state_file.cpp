@@ -75,6 +75,19 @@ bool readStateText(std::istream& in, PimcState& st, std::string& err) {
     // empty beads are unlinked (src/pimc.cpp:1228-1239)
     for (size_t k = 0; k < st.wormBeads.size(); ++k)
         if (!st.wormBeads[k]) { st.nextLink[k] = {XXX, XXX}; st.prevLink[k] = {XXX, XXX}; }
+    // links are followed by leftPack and by the kinetic / virial estimators: a target outside the arrays is a damaged file
+    // (memory safety); a target that is inactive is a hand-made file whose links were never maintained -- accepted for the
+    // position-only estimators, reported by linksClosed()
+    auto inRange = [&](const beadLocator& b) {
+        return (b[0] == XXX && b[1] == XXX) || (b[0] >= 0 && b[0] < st.numTimeSlices && b[1] >= 0 && b[1] < st.numWorldLines);
+    };
+    for (size_t k = 0; k < st.wormBeads.size(); ++k)
+        if (st.wormBeads[k] && (!inRange(st.nextLink[k]) || !inRange(st.prevLink[k]))) {
+            std::ostringstream msg;
+            msg << "bead (" << k / st.numWorldLines << "," << k % st.numWorldLines << ") links to a bead outside the arrays";
+            err = msg.str();
+            return false;
+        }
     st.numBeadsAtSlice.assign(st.numTimeSlices, 0);
     for (int s = 0; s < st.numTimeSlices; ++s)
         for (int p = 0; p < st.numWorldLines; ++p) st.numBeadsAtSlice[s] += st.wormBeads[st.idx(s, p)] ? 1 : 0;
@@ -103,6 +116,21 @@ bool PimcState::isDiagonal() const {
     return true;
 }
 
+// Closed world lines: every active bead links to ACTIVE beads and prev(next(b)) == b == next(prev(b)).  What the kinetic and
+// virial estimators walk; files written by the reference always satisfy it.
+bool PimcState::linksClosed() const {
+    if (nextLink.size() != beads.size() || prevLink.size() != beads.size()) return false;
+    for (size_t k = 0; k < wormBeads.size(); ++k) {
+        if (!wormBeads[k]) continue;
+        const beadLocator &n = nextLink[k], &p = prevLink[k];
+        if (n[0] == XXX || n[1] == XXX || p[0] == XXX || p[1] == XXX) return false;
+        if (!wormBeads[idx(n[0], n[1])] || !wormBeads[idx(p[0], p[1])]) return false;
+        const beadLocator me{static_cast<int>(k / numWorldLines), static_cast<int>(k % numWorldLines)};
+        if (prevLink[idx(n[0], n[1])] != me || nextLink[idx(p[0], p[1])] != me) return false;
+    }
+    return true;
+}
+
 bool PimcState::isLeftPacked() const {
     for (int s = 0; s < numTimeSlices; ++s)
         for (int p = 0; p < numWorldLines; ++p)
@@ -122,7 +150,7 @@ void PimcState::leftPack() {
             if (wormBeads[idx(s, p)]) newcol[idx(s, p)] = w++;
     }
     auto relabel = [&](const beadLocator& b) {
-        if (b[0] == XXX || b[1] == XXX) return beadLocator{XXX, XXX};
+        if (b[0] == XXX || b[1] == XXX || newcol[idx(b[0], b[1])] == XXX) return beadLocator{XXX, XXX};   // no link / inactive target
         return beadLocator{b[0], newcol[idx(b[0], b[1])]};
     };
     std::vector<dVec> nb(beads.size());                     // vacated columns: zero positions, no links, flag off

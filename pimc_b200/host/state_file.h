@@ -40,6 +40,7 @@ struct PimcState {
     // All slices hold the same number of active beads and every active bead is linked both ways: the
     // configuration is diagonal (closed worldlines only), the only kind estimators sample (src/estimator.cpp:228).
     bool isDiagonal() const;
+    bool linksClosed() const;              // every world line closed over active beads (needed by the kinetic / virial estimators)
     // Active beads of every slice in columns [0, n): true for files written by the reference; leftPack() restores it
     // for hand-made files: stable compaction of positions and flags with the links relabelled accordingly.
     bool isLeftPacked() const;

@@ -364,6 +364,75 @@ def test_pair_sums(api, orc, nthreads, shape):
     assert abs(Ug - Uc) <= 1e-10 * abs(Uc)
 
 
+def test_pair_table_index_is_exact_at_bin_boundaries(api, orc):
+    """The tile kernel takes k = int(r/dr) and the sepHist bin from a multiplication by the rounded reciprocal plus a
+    safety margin, and re-runs the reference's exact operation sequence inside the margin.  With V[k] = k the slice sum
+    IS the index: two particles per slice at separations (k0 + delta) dr with delta from far inside the margin to far
+    outside it (and the same around the histogram's bin edges); Vint and sepHist must equal the oracle's exactly."""
+    side = np.array([40.0, 40.0, 40.0])
+    dr = 2.9673e-6
+    nk = 3_000_000
+    V = np.arange(nk, dtype=np.float64)
+    dV = -np.arange(nk, dtype=np.float64)
+    dSep = 0.5 * math.sqrt(3) * side[2] / 50
+    rng = np.random.default_rng(7)
+    deltas = np.array([0.0, 1e-13, -1e-13, 1e-11, -1e-11, 1e-9, -1e-9, 1e-7, -1e-7, 5e-7, -5e-7, 1e-6, -1e-6, 2e-6, -2e-6, 1e-4, -1e-4,
+                       0.25, 0.5, 0.999999, 0.9999999999])
+    seps = []
+    for k0 in rng.integers(700_000, nk - 10, size=60):
+        seps += [(k0 + d) * dr for d in deltas]
+    for b in range(1, 14):                                   # histogram edges (bins of dSep), well inside the table
+        seps += [b * dSep * (1.0 + e) for e in (0.0, 1e-16, -1e-16, 1e-15, -1e-15, 1e-12, -1e-12, 1e-9, -1e-9) if b * dSep < (nk - 2) * dr]
+    seps = np.array(seps)
+    M = len(seps)
+    beads = np.zeros((M, 2, 3))
+    beads[:, 0, 0] = -0.3
+    beads[:, 1, 0] = -0.3 + seps                             # along x: r = |dx| up to the rounding of the subtraction
+    half = M // 2                                            # second half: along a diagonal (all components in the norm)
+    beads[half:, 1, 0] = -0.3 + seps[half:] / math.sqrt(3)
+    beads[half:, 1, 1] = seps[half:] / math.sqrt(3)
+    beads[half:, 1, 2] = -seps[half:] / math.sqrt(3)
+    cv, cf, ch = orc.pair_sums(side, beads, 2, V, dV, dr, dSep)
+    with api.Context(0, 3) as ctx:
+        ctx.set_box(side)
+        ctx.set_pair_table(V, dV, dr)
+        ctx.stage(beads, 2)
+        gv, gf, gh = ctx.pair_sums(dSep)
+        gv2, _, gh2 = ctx.pair_sums(dSep, want_f2=False)
+    assert np.array_equal(gv[0], cv) and np.array_equal(gv2[0], cv), np.flatnonzero(gv[0] != cv)[:10]
+    assert np.array_equal(gh[0], ch) and np.array_equal(gh2[0], ch)
+    assert_parity(gf[0], cf, "gradVSquared with V[k] = k tables")
+
+
+@pytest.mark.parametrize("ndim,N,M,pad,per", [(3, 1, 3, 0, None), (3, 2, 5, 1, None), (3, 33, 7, 2, None), (3, 95, 6, 0, None),
+                                              (3, 130, 5, 3, (1, 1, 0)), (2, 128, 9, 1, None), (2, 47, 4, 0, (1, 0)),
+                                              (1, 40, 6, 2, None), (3, 300, 3, 1, None), (3, 700, 2, 0, None)])
+def test_pair_sums_ragged_shapes(api, orc, nthreads, ndim, N, M, pad, per):
+    """Group counts from 1 to 22 (partial last group, odd and even numbers of groups: full tiles, shared half tiles,
+    several rounds of partner slots, several slices per CTA), 1-D / 2-D, slab periodicity, gsf parity and all slices."""
+    rho = {1: 0.2, 2: 0.0432, 3: 0.02198}[ndim]
+    s = synth.Shape("rg", ndim, N, M, 2.0, rho, 0)
+    beads = synth.gen_config(N, M, ndim, rho, 2.0, seed=500 + N, pad=pad)
+    maxsep = math.sqrt(sum((L / 2) ** 2 for L in s.side)) * (2.0 if per is not None else 1.0)
+    V, dV, dr = orc.aziz_table(maxsep)
+    dSep = 0.5 * math.sqrt(ndim) * s.side[-1] / 50
+    periodic = np.array(per, dtype=np.uint32) if per is not None else None
+    cv, cf, ch = orc.pair_sums(s.side, beads, N, V, dV, dr, dSep, periodic=periodic, nthreads=nthreads)
+    with api.Context(0, ndim) as ctx:
+        ctx.set_box(s.side, periodic)
+        ctx.set_pair_table(V, dV, dr)
+        ctx.stage(beads, N)
+        gv, gf, gh = ctx.pair_sums(dSep)
+        gv1, gf1, gh1 = ctx.pair_sums(dSep, f2_parity=1)
+        gv0, _, _ = ctx.pair_sums(dSep, want_f2=False, want_hist=False)
+    assert np.array_equal(gh[0], ch) and np.array_equal(gh1[0], ch)
+    for g in (gv, gv1, gv0):
+        assert_parity(g[0], cv, f"Vint N={N}")
+    assert_parity(gf[0], cf, f"gradVSquared N={N}")
+    assert_parity(gf1[0, 1::2], cf[1::2], "odd slices")
+    assert np.all(gf1[0, 0::2] == 0.0)
+
+
 def test_pair_table_edges(api, orc):
     """Separations below dr (k <= 0 -> extV[0]) and beyond the table (k >= len -> extV[1])."""
     side = np.array([30.0, 30.0, 30.0])

@@ -157,6 +157,27 @@ def test_state_file_parser_matches_format_restatement(host_bins, tmp_path, ndim)
     out = subprocess.run([os.path.join(host_bins, f"pimcb_host_selftest{ndim}d"), "--state", str(f4), "4", "0.02"],
                          capture_output=True, text=True)
     assert out.returncode == 1 and "error=" in out.stdout
+    # links that leave the arrays or point at an inactive bead are refused on load (they used to be followed blindly
+    # by leftPack's relabelling)
+    nxt = np.full((M, W, 2), -1, dtype=np.int32)
+    for t in range(M):
+        nxt[t, :N, 0] = (t + 1) % M
+        nxt[t, :N, 1] = np.arange(N)
+    for k, bad in enumerate(((M + 3, 0), (1, W + 5))):                 # slice out of range, column out of range
+        nb = nxt.copy()
+        nb[0, 2] = bad
+        f5 = tmp_path / f"ce-state-badlink{k}.dat"
+        statefile.write_state(f5, beads, on, next_link=nb)
+        out = subprocess.run([os.path.join(host_bins, f"pimcb_host_selftest{ndim}d"), "--state", str(f5), str(N), repr(rho)],
+                             capture_output=True, text=True)
+        assert out.returncode == 1 and "links to a bead outside the arrays" in out.stdout, out.stdout
+    # a link to an inactive bead loads (positions are still good for S(q) / F(q,tau)) but the world lines are reported open
+    nb = nxt.copy()
+    nb[0, 2] = (1, W - 1)
+    f6 = tmp_path / "ce-state-openlink.dat"
+    statefile.write_state(f6, beads, on, next_link=nb)
+    assert state_report(host_bins, ndim, f6, N, rho)["linksClosed"] == ["0"]
+    assert state_report(host_bins, ndim, f1, N, rho)["linksClosed"] == ["1"]
 
 
 @pytest.mark.gpu

@@ -176,6 +176,45 @@ def test_external_gradient_coupling_oracle_vs_upstream(orc):
     np.testing.assert_allclose(orc.grad_v_squared_ext(s.side, beads, s.N, dV, dr, 0.0 * beads), free["f2"], rtol=0, atol=0)
 
 
+def spring_terms(beads, k):
+    """SpringTestPotential of oracle/ref_cpu_shim.cpp: V = k r^2 / 2 -> gradV = k r, grad2V = NDIM k."""
+    return k * beads, np.full(beads.shape[:2], beads.shape[2] * k)
+
+
+@pytest.mark.parametrize("action", ["gsf", "li_broughton", "primitive"])
+def test_virial_terms_with_external_potential_oracle_vs_upstream(orc, nthreads, action):
+    """The four virial terms with a non-free external potential (src/action.cpp:1446-1784): gV = gVe + sum gVi in the
+    first-order terms, dV = dVi + dVe and d2V = g2Vi + g2Ve inside the T-matrix of the second-order ones.  Oracle
+    restatement vs the upstream bodies running with a spring potential, permuted world lines."""
+    VF, GF, period = {"gsf": GSF, "primitive": PRIMITIVE, "li_broughton": LI_BROUGHTON}[action]
+    s = synth.Shape("xv", 3, 15, 6, 2.0, 0.02198, 0)
+    beads = synth.gen_config(s.N, s.M, 3, s.rho, s.T, seed=91, pad=2)
+    links = permuted_links(s.M, s.N, beads.shape[1], 5)
+    window, k = 2, 40.0
+    r = RefCpu(3).action(s.side, beads, s.N, s.tau, LAM, VF, GF, period, window=window, next_links=links, spring_k=k)
+    free = RefCpu(3).action(s.side, beads, s.N, s.tau, LAM, VF, GF, period, window=window, next_links=links)
+    V, dV, d2V, dr = orc.aziz_table(orc.max_sep(s.side), second=True)
+    t2p = -1 if (GF[0] > 1e-7 and GF[1] > 1e-7) else (1 if GF[1] > 1e-7 else (0 if GF[0] > 1e-7 else -2))
+    gext, g2ext = spring_terms(beads, k)
+    vir = orc.virial_sums(s.side, beads, s.N, window, dV, d2V, dr, t2_parity=t2p, next_links=links, nthreads=nthreads,
+                          gext=gext, g2ext=g2ext)
+    eo = np.arange(s.M) % 2
+    c1 = np.array(VF)[eo] * s.tau
+    c2 = 2.0 * np.array(GF)[eo] * s.tau ** 3 * LAM
+    np.testing.assert_allclose(vir[:, 0] * c1, r["vir"][:, 0], rtol=1e-13)
+    np.testing.assert_allclose(vir[:, 2] * c1, r["vir"][:, 2], rtol=1e-12, atol=1e-13 * np.max(np.abs(r["vir"][:, 2])))
+    assert not np.allclose(free["vir"][:, 0], r["vir"][:, 0], rtol=1e-3)          # the external force matters
+    if t2p != -2:
+        np.testing.assert_allclose(vir[:, 1] * c2, r["vir"][:, 1], rtol=1e-12, atol=1e-13 * np.max(np.abs(r["vir"][:, 1])))
+        np.testing.assert_allclose(vir[:, 3] * c2, r["vir"][:, 3], rtol=1e-12, atol=1e-13 * np.max(np.abs(r["vir"][:, 3])))
+        on = c2 > 0
+        assert not np.allclose(free["vir"][on, 1], r["vir"][on, 1], rtol=1e-5)
+    # and with no external arrays the restatement is unchanged
+    np.testing.assert_array_equal(orc.virial_sums(s.side, beads, s.N, window, dV, d2V, dr, t2_parity=t2p, next_links=links),
+                                  orc.virial_sums(s.side, beads, s.N, window, dV, d2V, dr, t2_parity=t2p, next_links=links,
+                                                  gext=0.0 * beads, g2ext=np.zeros(beads.shape[:2])))
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # GPU: CUDA path vs upstream CPU code, directly
 # ------------------------------------------------------------------------------------------------------------------
@@ -263,6 +302,47 @@ def test_cuda_external_gradient_against_upstream_cpu_code(orc):
         assert np.array_equal(hist[b], r["sephist"])
     assert np.array_equal(f2_free, f2_cleared) and np.array_equal(f2_restaged, f2_free[::-1])
     assert not np.allclose(f2_free, f2, rtol=1e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("action", ["gsf", "li_broughton", "primitive"])
+def test_cuda_virial_terms_with_external_potential_against_upstream_cpu_code(orc, action):
+    """pimcb_virial_sums with the external gradient and Laplacian uploaded (pimcb_set_external_gradient /
+    pimcb_set_external_laplacian) vs the upstream rDOTgradUterm1/2 and deltadotgradUterm1/2 bodies running with a
+    spring potential; permuted world lines; the arrays are bound to the staged configuration."""
+    from pimc_b200 import api
+    VF, GF, period = {"gsf": GSF, "primitive": PRIMITIVE, "li_broughton": LI_BROUGHTON}[action]
+    s = synth.Shape("xv", 3, 37, 8, 2.0, 0.02198, 0)
+    beads = synth.gen_config(s.N, s.M, 3, s.rho, s.T, seed=93, pad=3)
+    links = permuted_links(s.M, s.N, beads.shape[1], 6)
+    window, k = 3, 40.0
+    r = RefCpu(3).action(s.side, beads, s.N, s.tau, LAM, VF, GF, period, window=window, next_links=links, spring_k=k)
+    free = RefCpu(3).action(s.side, beads, s.N, s.tau, LAM, VF, GF, period, window=window, next_links=links)
+    V, dV, d2V, dr = orc.aziz_table(orc.max_sep(s.side), second=True)
+    delta = orc.virial_delta(s.side, beads, s.N, window, next_links=links)
+    t2p = -1 if (GF[0] > 1e-7 and GF[1] > 1e-7) else (1 if GF[1] > 1e-7 else (0 if GF[0] > 1e-7 else -2))
+    gext, g2ext = spring_terms(beads, k)
+    with api.Context(0, 3) as ctx:
+        ctx.set_box(s.side)
+        ctx.set_pair_table(V, dV, dr)
+        ctx.set_pair_table_d2(d2V)
+        ctx.stage(beads, s.N)
+        vir_free = ctx.virial_sums(delta, t2_parity=t2p)[0]
+        ctx.set_external_gradient(gext)
+        ctx.set_external_laplacian(g2ext)
+        vir = ctx.virial_sums(delta, t2_parity=t2p)[0]
+        ctx.stage(beads, s.N)                                   # re-staged: the external arrays are not applied any more
+        vir_restaged = ctx.virial_sums(delta, t2_parity=t2p)[0]
+    eo = np.arange(s.M) % 2
+    c1 = np.array(VF)[eo] * s.tau
+    c2 = 2.0 * np.array(GF)[eo] * s.tau ** 3 * LAM
+    for got, ref in ((vir, r), (vir_free, free), (vir_restaged, free)):
+        assert_parity(got[:, 0] * c1, ref["vir"][:, 0], "rDOTgradUterm1")
+        assert_parity(got[:, 2] * c1, ref["vir"][:, 2], "deltaDOTgradUterm1")
+        if t2p != -2:
+            assert_parity(got[:, 1] * c2, ref["vir"][:, 1], "rDOTgradUterm2")
+            assert_parity(got[:, 3] * c2, ref["vir"][:, 3], "deltaDOTgradUterm2")
+    assert not np.allclose(vir[:, 0], vir_free[:, 0], rtol=1e-3)
 
 
 @pytest.mark.parametrize("ndim", [2, 3])

@@ -25,24 +25,26 @@ dSep = 0.5 * math.sqrt(3.0) * s.side[2] / 50.0
 with api.Context(0, s.ndim) as ctx:
     ctx.set_box(s.side)
     ctx.stage(pa.array, s.N)
-    for sub in (1, 2, 4, 16):
+    for sub in (1, 2, 16):
         ctx.set_pair_table(np.ascontiguousarray(V[::sub]), np.ascontiguousarray(dV[::sub]), dr * sub)
         ctx.set_pair_table_d2(np.ascontiguousarray(d2V[::sub]))
         out = {}
-        for what in ("pair_gsf", "pair_vonly", "virial"):
+        for what in ("pair_gsf", "pair_gsf_nohist", "pair_vonly", "pair_vonly_nohist", "pair_allf", "virial"):
             ctx.set_profiling(True)
             for it in range(4):
                 if it == 1:
                     ctx.kernel_times(reset=True)
-                if what == "pair_gsf":
-                    ctx.pair_sums(dSep, want_f2=True, want_hist=True, f2_parity=1)
-                elif what == "pair_vonly":
-                    ctx.pair_sums(dSep, want_f2=False, want_hist=True)
+                if what.startswith("pair_gsf"):
+                    ctx.pair_sums(dSep, want_f2=True, want_hist="nohist" not in what, f2_parity=1)
+                elif what.startswith("pair_vonly"):
+                    ctx.pair_sums(dSep, want_f2=False, want_hist="nohist" not in what)
+                elif what == "pair_allf":
+                    ctx.pair_sums(dSep, want_f2=True, want_hist=True, f2_parity=-1)
                 else:
                     ctx.virial_sums(0.01 * pa.array, t2_parity=1)
             kt = ctx.kernel_times(reset=True)
             ms, n = kt["pair"] if what != "virial" else kt["virial"]
             out[what] = ms / max(1, n)
             ctx.set_profiling(False)
-        print(f"table/{sub:<2d} ({8 * len(V[::sub]) / 1e6:6.1f} MB per table): " + "  ".join(f"{k} {v:7.3f} ms" for k, v in out.items()), flush=True)
+        print(f"table/{sub:<2d} ({8 * len(V[::sub]) / 1e6:6.1f} MB per table): " + "  ".join(f"{k} {v:6.3f}" for k, v in out.items()) + "  (ms)", flush=True)
 pa.free()
