@@ -209,6 +209,10 @@ int pimcb_gather_bins_q(pimcb_ctx* ctx, const int* nq_per_rank, double* ssf, dou
 int pimcb_measure_fp64_peak(pimcb_ctx* ctx, double* tflops, double seconds_target);
 /* Bare host-to-device rate (GB/s) of `reps` back-to-back cudaMemcpyAsync of a page-locked buffer on this context's copy
  * stream: the in-run ceiling of the host-fed (e2e) path.  Measurement only. */
+/* info[5] = {(V, dV/dr) packed table in use, its verbatim (RAW) sectors, (dV/dr, d2V/dr2) packed table in use, its RAW
+ * sectors, sectors per table}: the one-sector-per-pair encoding of the lookup tables (pimc_b200/csrc/table_codec.h), built
+ * and verified bit for bit against the verbatim tables by pimcb_set_pair_table / pimcb_set_pair_table_d2. */
+int pimcb_table_codec_info(const pimcb_ctx* ctx, long* info);
 int pimcb_measure_h2d_peak(pimcb_ctx* ctx, const void* pinned_src, size_t bytes, int reps, double* gbs);
 /* Per-kernel device time.  With profiling on, every kernel launch is bracketed by CUDA events on the stream it is
  * launched on; pimcb_kernel_times synchronises, folds the pending event pairs into running totals and returns, per

@@ -28,7 +28,7 @@ SYMBOLS = [
     "pimcb_pair_sums", "pimcb_measure_fp64_peak", "pimcb_set_profiling", "pimcb_set_profiling_stride", "pimcb_kernel_times",
     "pimcb_launch_count", "pimcb_rho_plan_info", "pimcb_elastic", "pimcb_ssf_cyl", "pimcb_set_pair_table_d2",
     "pimcb_virial_sums", "pimcb_comm_unique_id", "pimcb_comm_init", "pimcb_comm_destroy", "pimcb_reduce_bins",
-    "pimcb_gather_bins_q", "pimcb_set_external_gradient", "pimcb_set_external_laplacian", "pimcb_init_bins", "pimcb_measure_h2d_peak",
+    "pimcb_gather_bins_q", "pimcb_set_external_gradient", "pimcb_set_external_laplacian", "pimcb_init_bins", "pimcb_measure_h2d_peak", "pimcb_table_codec_info",
 ]
 
 
@@ -113,6 +113,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.pimcb_set_external_gradient.argtypes = [vp, _dp]
     lib.pimcb_set_external_laplacian.argtypes = [vp, _dp]
     lib.pimcb_init_bins.argtypes = [vp, C.c_int]
+    lib.pimcb_table_codec_info.argtypes = [vp, C.POINTER(C.c_long)]
     lib.pimcb_measure_h2d_peak.argtypes = [vp, C.c_void_p, C.c_size_t, C.c_int, _dp]
     lib.pimcb_comm_unique_id.argtypes = [C.c_char_p]
     lib.pimcb_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
@@ -328,6 +329,11 @@ class Context:
         self._chk(self.lib.pimcb_measure_h2d_peak(self._h, pinned_array.ctypes.data_as(C.c_void_p), pinned_array.nbytes, int(reps),
                                                   C.byref(g)))
         return g.value
+
+    def table_codec_info(self) -> dict:
+        v = (C.c_long * 5)()
+        self._chk(self.lib.pimcb_table_codec_info(self._h, v))
+        return {"vd_packed": bool(v[0]), "vd_raw_sectors": v[1], "dd_packed": bool(v[2]), "dd_raw_sectors": v[3], "sectors": v[4]}
 
     def init_bins(self, M: int):
         """Zeroed bin for M slices before any measurement (lets an idle rank join the bin collective)."""

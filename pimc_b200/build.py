@@ -10,7 +10,7 @@ CSRC = os.path.join(_HERE, "csrc")
 # tools/build_variants.sh); the default is the in-tree product library.
 LIB = os.environ.get("PIMCB_LIB_PATH") or os.path.join(_HERE, "libpimc_b200.so")
 SOURCES = [os.path.join(CSRC, "pimcb.cu")]
-HEADERS = [os.path.join(CSRC, "kernels.cuh"), os.path.join(CSRC, "kernels_ext.cuh"), os.path.join(CSRC, "kernels_pair.cuh"), os.path.join(_HERE, "..", "include", "pimc_b200.h")]
+HEADERS = [os.path.join(CSRC, "kernels.cuh"), os.path.join(CSRC, "kernels_ext.cuh"), os.path.join(CSRC, "kernels_pair.cuh"), os.path.join(CSRC, "table_codec.h"), os.path.join(_HERE, "..", "include", "pimc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--fmad=true", "-cudart", "shared"]
 

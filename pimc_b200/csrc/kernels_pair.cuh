@@ -29,6 +29,7 @@
 #pragma once
 
 #include "kernels.cuh"
+#include "table_codec.h"
 
 namespace pimcb {
 
@@ -40,7 +41,15 @@ struct PairTileParams {
     int fb;                // fraction bits below the integer part in the low word of (t + magic), <= 28
     int G;                 // particle groups of 32
     int spc;               // slices per CTA work unit (> 1 when a slice has fewer groups than the CTA has warps)
+    const TableSector* VD; // (V, dV/dr) packed four entries per 32-byte sector (table_codec.h), or nullptr: verbatim tables only
 };
+
+// One whole 32-byte sector per lane in one request (LDG.E.256).
+__device__ __forceinline__ TableSector ldg_sector(const TableSector* p) {
+    TableSector s;
+    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(s.w[0]), "=l"(s.w[1]), "=l"(s.w[2]), "=l"(s.w[3]) : "l"(p));
+    return s;
+}
 
 constexpr int kPairWarps = 8;
 constexpr int kPairRound = 4;        // group offsets per round (partner-side slots in shared memory)
@@ -76,7 +85,7 @@ __device__ __forceinline__ bool floor_safe(double t, double magic, int fb, int& 
 // One tile: the 32 particles of the home group (lane = particle i, position xi) against the 32 particles of group b
 // (positions xb[d * NP + m]), steps [s_lo, s_hi), partner m = (lane + s) & 31.  FORCE: own-side force into Fi, partner-side
 // force into Gv (it ends up in the lane that holds the partner: particle 32 b + lane).
-template <int ND, bool FORCE>
+template <int ND, bool FORCE, bool CODEC>
 __device__ __forceinline__ void pair_tile(const double* __restrict__ xsl, int NP, const double (&xi)[ND], int i, bool ivalid, int b,
                                           int lane, int s_lo, int s_hi, bool diag, int N, const BoxDev& box,
                                           const PairTileParams& pp, int* __restrict__ shist_sl, double& vsum, double (&Fi)[ND],
@@ -118,6 +127,34 @@ __device__ __forceinline__ void pair_tile(const double* __restrict__ xsl, int NP
                 if (pp.want_hist) nR[u] = __double2int_rz(__ddiv_rn(rx, pp.dSep));
             }
         }
+        if constexpr (CODEC) {
+            // one sector request per pair serves V and dV/dr (table_codec.h); RAW sectors fall back to the verbatim tables
+            TableSector sec[2];
+            bool inside[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {       // both sector reads of the step pair are issued here
+                inside[u] = valid[u] && kidx[u] > 0 && kidx[u] < pp.len;
+                sec[u].w[0] = sec[u].w[1] = sec[u].w[2] = 0;
+                sec[u].w[3] = 0;
+                if (inside[u]) sec[u] = ldg_sector(pp.VD + (kidx[u] >> 2));
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                vv[u] = 0.0;
+                dv[u] = 0.0;
+                if (inside[u]) {
+                    if (sector_is_raw(sec[u])) {
+                        vv[u] = __ldg(pp.V + kidx[u]);
+                        if (FORCE) dv[u] = __ldg(pp.dVdr + kidx[u]);
+                    } else {
+                        sector_decode<FORCE>(sec[u], kidx[u] & 3, pp.dr, vv[u], dv[u]);
+                    }
+                } else if (valid[u]) {
+                    vv[u] = kidx[u] <= 0 ? pp.extV[0] : pp.extV[1];
+                    if (FORCE) dv[u] = kidx[u] <= 0 ? pp.extdV[0] : pp.extdV[1];
+                }
+            }
+        } else {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {           // both gathers of the step pair are issued here
             const bool inside = kidx[u] > 0 && kidx[u] < pp.len;
@@ -127,6 +164,7 @@ __device__ __forceinline__ void pair_tile(const double* __restrict__ xsl, int NP
                 vv[u] = inside ? __ldg(pp.V + kidx[u]) : (kidx[u] <= 0 ? pp.extV[0] : pp.extV[1]);
                 if (FORCE) dv[u] = inside ? __ldg(pp.dVdr + kidx[u]) : (kidx[u] <= 0 ? pp.extdV[0] : pp.extdV[1]);
             }
+        }
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -149,7 +187,7 @@ __device__ __forceinline__ void pair_tile(const double* __restrict__ xsl, int NP
 #ifndef PIMCB_PTILE_MINB
 #define PIMCB_PTILE_MINB 3
 #endif
-template <int ND>
+template <int ND, bool CODEC>
 __global__ void __launch_bounds__(32 * kPairWarps, PIMCB_PTILE_MINB)
 pair_tile_kernel(const double* __restrict__ pos, int nslices, int N, int Npad, BoxDev box, PairTileParams pp,
                  double* __restrict__ vint, double* __restrict__ f2, int* __restrict__ hist) {
@@ -206,7 +244,7 @@ pair_tile_kernel(const double* __restrict__ pos, int nslices, int N, int Npad, B
 #pragma unroll
                     for (int d = 0; d < ND; ++d) Gv[d] = 0.0;
                     if (do_f) {
-                        pair_tile<ND, true>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, o == 0, N, box, pp, shist_sl, vsum, Fi, Gv);
+                        pair_tile<ND, true, CODEC>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, o == 0, N, box, pp, shist_sl, vsum, Fi, Gv);
                         if (o == 0) {
 #pragma unroll
                             for (int d = 0; d < ND; ++d) Fi[d] += Gv[d];        // the diagonal tile's partners are the home group itself
@@ -216,7 +254,7 @@ pair_tile_kernel(const double* __restrict__ pos, int nslices, int N, int Npad, B
                             for (int d = 0; d < ND; ++d) slot[d * NP] = Gv[d];
                         }
                     } else {
-                        pair_tile<ND, false>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, o == 0, N, box, pp, shist_sl, vsum, Fi, Gv);
+                        pair_tile<ND, false, CODEC>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, o == 0, N, box, pp, shist_sl, vsum, Fi, Gv);
                     }
                 }
                 if (do_f) {
@@ -268,6 +306,250 @@ pair_tile_kernel(const double* __restrict__ pos, int nslices, int N, int Npad, B
             }
             if (pp.want_hist)
                 for (int k = lane; k < kNPCFSEP; k += 32) hist[static_cast<size_t>(sl) * kNPCFSEP + k] = shist[sloc * kNPCFSEP + k];
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Virial slice sums on the same tiles (see kernels_ext.cuh, virial_kernel, for the definitions and the upstream lines):
+//   gV_i = sum_j (dVdr[k]/r) sep_ij,   T_i = sum_j [ sep sep^T (d2V[k]/r^2 - dV/r^3) + 1 dV/r ],  dV = |dVdr[k]|,
+//   out[sl] = { sum_i gV_i.r_i, sum_i (T_i gV_i).r_i, sum_i gV_i.delta_i, sum_i (T_i gV_i).delta_i }.
+// The pair terms are antisymmetric (gV) / symmetric (T): the partner's share travels to its lane by warp shuffle and
+// accumulates there in registers (ND + ND (ND + 1) / 2 components), exactly as the pair force does in pair_tile_kernel.
+// dV = sqrt(gVi.gVi) upstream (src/action.cpp:1544) is |dVdr[k]| up to rounding ((|dVdr|/r) |sep| with |sep| = r), which is
+// what is used here; external potential "free" (the non-free case runs virial_kernel<ND, true>).
+// ---------------------------------------------------------------------------------------------
+struct VirialTileParams {
+    const double* dVdr; const double* d2V; int len; double dr, inv_dr; double extdV[2]; double extd2V[2];
+    int t2_parity; int M;
+    double magic; int fb; int G; int spc; int rounds;     // rounds = group offsets per round (partner-side slots that fit)
+    const TableSector* DD;  // (dV/dr, d2V/dr2) packed four entries per sector, or nullptr
+};
+
+template <int ND, bool T2, bool CODEC>
+__device__ __forceinline__ void virial_tile(const double* __restrict__ xsl, int NP, const double (&xi)[ND], int i, bool ivalid, int b,
+                                            int lane, int s_lo, int s_hi, bool diag, int N, const BoxDev& box,
+                                            const VirialTileParams& vp, double (&own)[ND + ND * (ND + 1) / 2],
+                                            double (&vis)[ND + ND * (ND + 1) / 2]) {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int NT = ND * (ND + 1) / 2;
+    const double* xb = xsl + 32 * b;
+    for (int s = s_lo; s < s_hi; s += 2) {
+        double sep[2][ND], r[2], rinv[2], dv[2], d2[2];
+        int kidx[2];
+        bool valid[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int ss = s + u;
+            const int m = (lane + ss) & 31;
+            const int j = 32 * b + m;
+            valid[u] = ivalid && j < N && !(diag && ss == 16 && lane >= 16);
+            double r2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                const double sd = xi[d] - xb[d * NP + m];
+                const double tt = fma(sd, box.sideInv[d], kRintMagic) - kRintMagic;
+                sep[u][d] = fma(-box.pSide[d], tt, sd);
+                r2 = fma(sep[u][d], sep[u][d], r2);
+            }
+            if (!valid[u]) r2 = 1.0;
+            rsqrt_pair(r2, r[u], rinv[u]);
+            const bool safe = floor_safe(r[u] * vp.inv_dr, vp.magic, vp.fb, kidx[u]);
+            if (!safe && valid[u]) {
+                double sx[ND];
+                const double rx = minimage_norm<ND>(xsl, NP, i, j, box, sx);
+                kidx[u] = __double2int_rz(__ddiv_rn(rx, vp.dr));
+            }
+        }
+        if constexpr (CODEC) {
+            TableSector sec[2];
+            bool inside[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                inside[u] = valid[u] && kidx[u] > 0 && kidx[u] < vp.len;
+                sec[u].w[0] = sec[u].w[1] = sec[u].w[2] = 0;
+                sec[u].w[3] = 0;
+                if (inside[u]) sec[u] = ldg_sector(vp.DD + (kidx[u] >> 2));
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                dv[u] = 0.0;
+                d2[u] = 0.0;
+                if (inside[u]) {
+                    if (sector_is_raw(sec[u])) {
+                        dv[u] = __ldg(vp.dVdr + kidx[u]);
+                        if (T2) d2[u] = __ldg(vp.d2V + kidx[u]);
+                    } else {
+                        sector_decode<T2>(sec[u], kidx[u] & 3, vp.dr, dv[u], d2[u]);
+                    }
+                } else if (valid[u]) {
+                    dv[u] = kidx[u] <= 0 ? vp.extdV[0] : vp.extdV[1];
+                    if (T2) d2[u] = kidx[u] <= 0 ? vp.extd2V[0] : vp.extd2V[1];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const bool inside = kidx[u] > 0 && kidx[u] < vp.len;
+                dv[u] = 0.0;
+                d2[u] = 0.0;
+                if (valid[u]) {
+                    dv[u] = inside ? __ldg(vp.dVdr + kidx[u]) : (kidx[u] <= 0 ? vp.extdV[0] : vp.extdV[1]);
+                    if (T2) d2[u] = inside ? __ldg(vp.d2V + kidx[u]) : (kidx[u] <= 0 ? vp.extd2V[0] : vp.extd2V[1]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int src = (lane - (s + u)) & 31;
+            const double g = dv[u] * rinv[u];                  // 0 for invalid pairs
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                const double gi = g * sep[u][d];
+                own[d] += gi;
+                vis[d] -= __shfl_sync(FULL, gi, src);          // gradV(sep_ji) = -gradV(sep_ij)
+            }
+            if constexpr (T2) {
+                const double dV = valid[u] ? fabs(dv[u]) : 0.0;
+                const double ri2 = rinv[u] * rinv[u];
+                const double diagv = dV * rinv[u];
+                const double a = valid[u] ? fma(d2[u], ri2, -diagv * ri2) : 0.0;     // d2V/r^2 - dV/r^3
+                int k = ND;
+#pragma unroll
+                for (int p = 0; p < ND; ++p)
+#pragma unroll
+                    for (int q = p; q < ND; ++q, ++k) {
+                        const double mm = fma(sep[u][p] * sep[u][q], a, p == q ? diagv : 0.0);
+                        own[k] += mm;
+                        vis[k] += __shfl_sync(FULL, mm, src);  // the T-matrix term is the same seen from either end
+                    }
+            }
+        }
+    }
+}
+
+#ifndef PIMCB_VTILE_MINB
+#define PIMCB_VTILE_MINB 2
+#endif
+template <int ND, bool CODEC>
+__global__ void __launch_bounds__(32 * kPairWarps, PIMCB_VTILE_MINB)
+virial_tile_kernel(const double* __restrict__ pos, const double* __restrict__ delta, int nslices, int N, int Npad, BoxDev box,
+                   VirialTileParams vp, double* __restrict__ out) {
+    constexpr int NT = ND * (ND + 1) / 2, NC = ND + NT;
+    extern __shared__ __align__(16) double sm[];
+    const int G = vp.G, spc = vp.spc, NP = 32 * G, R = vp.rounds;
+    double* xs = sm;                                            // [spc][ND][NP]
+    double* acc = xs + static_cast<size_t>(spc) * ND * NP;      // [spc][NC][NP]   gV then the upper triangle of T per particle
+    double* part = acc + static_cast<size_t>(spc) * NC * NP;    // [R][spc][NC][NP] partner-side sums per offset
+    double* red = part + static_cast<size_t>(R) * spc * NC * NP;             // [spc][4][kPairWarps]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int omax = G / 2;
+    const int nunits = (nslices + spc - 1) / spc;
+
+    for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+        const int sl0 = unit * spc;
+        const int nsl = min(spc, nslices - sl0);
+        for (int k = threadIdx.x; k < nsl * ND * NP; k += blockDim.x) {
+            const int s = k / (ND * NP), rem = k - s * (ND * NP), d = rem / NP, i = rem - d * NP;
+            xs[k] = i < Npad ? __ldg(pos + (static_cast<size_t>(sl0 + s) * ND + d) * Npad + i) : 0.0;
+        }
+        for (int k = threadIdx.x; k < nsl * NC * NP; k += blockDim.x) acc[k] = 0.0;
+        __syncthreads();
+
+        for (int o1 = 1; o1 == 1 || o1 <= omax; o1 += R) {
+            for (int h = warp; h < nsl * G; h += kPairWarps) {
+                const int sloc = h / G, a = h - sloc * G;
+                const int t = (sl0 + sloc) % vp.M;
+                const bool do_t2 = vp.t2_parity == -1 || (vp.t2_parity >= 0 && (t & 1) == vp.t2_parity);
+                const double* xsl = xs + static_cast<size_t>(sloc) * ND * NP;
+                const int i = 32 * a + lane;
+                const bool ivalid = i < N;
+                double xi[ND], own[NC];
+#pragma unroll
+                for (int d = 0; d < ND; ++d) xi[d] = xsl[d * NP + i];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) own[c] = 0.0;
+                for (int oi = (o1 == 1 ? -1 : 0); oi < R; ++oi) {
+                    const int o = oi < 0 ? 0 : o1 + oi;
+                    if (o > omax) break;
+                    int s_lo, s_hi;
+                    if (o == 0) { s_lo = 1; s_hi = 17; }
+                    else if (2 * o == G) { s_lo = a < o ? 0 : 1; s_hi = s_lo + 16; }
+                    else { s_lo = 0; s_hi = 32; }
+                    int b = a + o;
+                    if (b >= G) b -= G;
+                    double vis[NC];
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) vis[c] = 0.0;
+                    if (do_t2) virial_tile<ND, true, CODEC>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, o == 0, N, box, vp, own, vis);
+                    else virial_tile<ND, false, CODEC>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, o == 0, N, box, vp, own, vis);
+                    if (o == 0) {
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) own[c] += vis[c];
+                    } else {
+                        double* slot = part + ((static_cast<size_t>(oi) * spc + sloc) * NC) * NP + 32 * b + lane;
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) slot[c * NP] = vis[c];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < NC; ++c) acc[(static_cast<size_t>(sloc) * NC + c) * NP + i] += own[c];   // this lane is the only writer
+            }
+            __syncthreads();
+            for (int k = threadIdx.x; k < nsl * NC * NP; k += blockDim.x) {        // fold this round's slots, offsets ascending
+                const int sloc = k / (NC * NP), rem = k - sloc * (NC * NP);
+                double v = acc[k];
+                for (int oi = 0; oi < R && o1 + oi <= omax; ++oi) v += part[(static_cast<size_t>(oi) * spc + sloc) * NC * NP + rem];
+                acc[k] = v;
+            }
+            __syncthreads();
+        }
+        // per slice: sum_i gV.w and (T gV).w for w = r (raw position) and w = delta
+        for (int sloc = 0; sloc < nsl; ++sloc) {
+            const int sl = sl0 + sloc;
+            const double* A = acc + static_cast<size_t>(sloc) * NC * NP;
+            const double* xsl = xs + static_cast<size_t>(sloc) * ND * NP;
+            double sums[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int i = threadIdx.x; i < N; i += blockDim.x) {
+                double gV[ND], T[NT], uu[ND];
+#pragma unroll
+                for (int d = 0; d < ND; ++d) { gV[d] = A[d * NP + i]; uu[d] = 0.0; }
+#pragma unroll
+                for (int k = 0; k < NT; ++k) T[k] = A[(ND + k) * NP + i];
+                int k = 0;
+#pragma unroll
+                for (int p = 0; p < ND; ++p)
+#pragma unroll
+                    for (int q = p; q < ND; ++q, ++k) {
+                        uu[p] = fma(T[k], gV[q], uu[p]);
+                        if (q != p) uu[q] = fma(T[k], gV[p], uu[q]);
+                    }
+#pragma unroll
+                for (int d = 0; d < ND; ++d) {
+                    const double x = xsl[d * NP + i];
+                    sums[0] = fma(gV[d], x, sums[0]);
+                    sums[1] = fma(uu[d], x, sums[1]);
+                    if (delta) {
+                        const double dl = __ldg(delta + (static_cast<size_t>(sl) * ND + d) * Npad + i);
+                        sums[2] = fma(gV[d], dl, sums[2]);
+                        sums[3] = fma(uu[d], dl, sums[3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                double v = sums[k];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                if (lane == 0) red[(sloc * 4 + k) * kPairWarps + warp] = v;
+            }
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < nsl * 4; k += blockDim.x) {
+            double v = 0.0;
+            for (int w = 0; w < kPairWarps; ++w) v += red[k * kPairWarps + w];
+            out[static_cast<size_t>(sl0) * 4 + k] = v;
         }
         __syncthreads();
     }

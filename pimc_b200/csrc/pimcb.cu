@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 #include "kernels_ext.cuh"
 #include "kernels_pair.cuh"
+#include "table_codec.h"
 
 #include <algorithm>
 #include <cmath>
@@ -14,8 +15,10 @@
 #include <array>
 #include <cstring>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges are no-ops unless a profiler injects itself (nsys / ncu --nvtx)
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace pimcb;
@@ -129,6 +132,10 @@ struct pimcb_ctx {
     PinBuf h_out;
     // pair potential
     DevBuf d_V, d_dV, d_vint, d_f2, d_hist;
+    DevBuf d_VD, d_DD;                     // (V, dV/dr) and (dV/dr, d2V/dr2) packed four entries per sector (table_codec.h)
+    bool vd_ok = false, dd_ok = false;     // the packed tables were built AND verified bit for bit on the device
+    long vd_raw = 0, dd_raw = 0;           // sectors left verbatim (zero crossings, core, switch of the damping function)
+    std::vector<double> h_dV;              // host copy of dV/dr for packing (dV/dr, d2V/dr2) when the third table arrives
     int tab_len = 0;
     bool have_dV = false;
     double dr = 0, extV[2] = {0, 0}, extdV[2] = {0, 0};
@@ -236,13 +243,24 @@ cudaEvent_t pool_event(pimcb_ctx* c) {
     return e;
 }
 
+// NVTX range names per kernel id (the reference has no tracing; these make the stage / rho / corr /
+// pair / reduce phases visible on a profiler's timeline).
+const char* const kRangeNames[kKernels] = {"pimcb:rho_q", "pimcb:tau_correlation", "pimcb:ssf_direct", "pimcb:bins", "pimcb:pair_sums",
+                                           "pimcb:aos_to_soa", "pimcb:variant", "pimcb:virial_sums"};
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 // Brackets one kernel launch on `stream` with CUDA events when profiling is on; always counts the launch.
 struct KTimer {
     pimcb_ctx* c; int k; cudaStream_t st; cudaEvent_t a = nullptr;
     KTimer(pimcb_ctx* c_, int k_, cudaStream_t st_ = nullptr) : c(c_), k(k_), st(st_ ? st_ : c_->stream) {
+        nvtxRangePushA(kRangeNames[k]);
         if (((c->profiling >> k) & 1u) && (c->prof_seen[k]++ % c->prof_stride) == 0 && (a = pool_event(c))) cudaEventRecord(a, st);
     }
     ~KTimer() {
+        nvtxRangePop();
         if (a) {
             cudaEvent_t b = pool_event(c);
             if (b) { cudaEventRecord(b, st); c->recs.push_back({k, a, b}); }
@@ -647,6 +665,7 @@ int stage_into(pimcb_ctx* c, int slot, const double* beads, int B, int M, int N,
     if (!beads || B < 1 || M < 1 || N < 1 || Next < N) return fail(PIMCB_EINVAL, "bad staging arguments (B=%d M=%d N=%d N_ext=%d)", B, M, N, Next);
     if (slot < 0 || slot >= kSlots) return fail(PIMCB_EINVAL, "slot %d out of range", slot);
     CU(cudaSetDevice(c->device));
+    NvtxRange range("pimcb:stage");
     const int nd = c->ndim;
     Slot& s = c->slots[slot];
     const int Npad = round_up(N, 16);
@@ -699,6 +718,57 @@ int stage_into(pimcb_ctx* c, int slot, const double* beads, int B, int M, int N,
     s.staged = true;
     s.gen = ++c->gen_counter;
     if (c->cfg_slot == slot) c->cfg_slot = -1;
+    return 0;
+}
+
+// Decodes every entry of a packed table pair and compares it with the verbatim tables, bit for bit; mismatches[0] counts
+// the entries that differ (must be 0), mismatches[1] the RAW sectors.
+__global__ void codec_verify_kernel(const TableSector* __restrict__ sec, const double* __restrict__ F, const double* __restrict__ G,
+                                    int len, double dr, unsigned long long* __restrict__ mismatches) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= len) return;
+    const TableSector s = sec[k >> 2];
+    if (sector_is_raw(s)) {
+        if ((k & 3) == 0) atomicAdd(mismatches + 1, 1ull);
+        return;
+    }
+    double f, g;
+    sector_decode<true>(s, k & 3, dr, f, g);
+    if (__double_as_longlong(f) != __double_as_longlong(F[k]) || __double_as_longlong(g) != __double_as_longlong(G[k]))
+        atomicAdd(mismatches, 1ull);
+}
+
+// Packs (F, G) on the host (several threads), uploads the sectors and verifies them on the device against the verbatim
+// device tables dF / dG.  *ok = the packed table may be used; any mismatch or > 5 % RAW sectors leaves it unused.
+int build_packed_table(pimcb_ctx* c, const double* F, const double* G, int len, double dr, const double* dF, const double* dG,
+                       DevBuf& dst, bool* ok, long* nraw) {
+    *ok = false;
+    *nraw = 0;
+    static const bool codec_on = !(std::getenv("PIMCB_TABLE_CODEC") && std::atoi(std::getenv("PIMCB_TABLE_CODEC")) == 0);
+    if (!codec_on || len < 8) return 0;
+    const int ns = (len + 3) / 4;
+    std::vector<TableSector> sec(ns);
+    const int nth = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    for (int w = 0; w < nth; ++w)
+        pool.emplace_back([&, w]() {
+            const int s0 = static_cast<int>(static_cast<long long>(ns) * w / nth), s1 = static_cast<int>(static_cast<long long>(ns) * (w + 1) / nth);
+            for (int s = s0; s < s1; ++s) sector_encode(F, G, len, 4 * s, dr, sec[s]);
+        });
+    for (auto& t : pool) t.join();
+    int rc = dst.ensure(sizeof(TableSector) * static_cast<size_t>(ns));
+    if (rc) return rc;
+    if ((rc = c->d_count.ensure(2 * sizeof(unsigned long long)))) return rc;
+    CU(cudaMemcpyAsync(dst.p, sec.data(), sizeof(TableSector) * static_cast<size_t>(ns), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->d_count.p, 0, 2 * sizeof(unsigned long long), c->stream));
+    codec_verify_kernel<<<(len + 255) / 256, 256, 0, c->stream>>>(dst.as<TableSector>(), dF, dG, len, dr, c->d_count.as<unsigned long long>());
+    CU(cudaGetLastError());
+    unsigned long long res[2] = {1, 0};
+    CU(cudaMemcpyAsync(res, c->d_count.p, sizeof res, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->launches++;
+    *nraw = static_cast<long>(res[1]);
+    *ok = res[0] == 0 && res[1] * 20 <= static_cast<unsigned long long>(ns);
     return 0;
 }
 
@@ -767,7 +837,7 @@ int pimcb_destroy(pimcb_ctx* c) {
     for (auto& p : c->pin) { p.release(); if (p.done) cudaEventDestroy(p.done); }
     c->h_out.release();
     for (DevBuf* b : {&c->d_q, &c->d_comm, &c->d_qn, &c->d_qidx, &c->d_plan, &c->d_rho, &c->d_cfg, &c->d_bins, &c->d_partial,
-                      &c->d_V, &c->d_dV, &c->d_vint, &c->d_f2, &c->d_hist, &c->d_scratch, &c->d_sched, &c->d_binrows, &c->d_unfold,
+                      &c->d_V, &c->d_dV, &c->d_VD, &c->d_DD, &c->d_vint, &c->d_f2, &c->d_hist, &c->d_scratch, &c->d_sched, &c->d_binrows, &c->d_unfold,
                       &c->d_var, &c->d_inside, &c->d_d2V, &c->d_delta_aos, &c->d_delta, &c->d_vir, &c->d_gext, &c->d_g2ext, &c->d_gather, &c->d_count})
         b->release();
     for (int k = 0; k < kKernels; ++k) { cudaEventDestroy(c->ev0[k]); cudaEventDestroy(c->ev1[k]); }
@@ -1347,6 +1417,21 @@ int pimcb_set_pair_table(pimcb_ctx* c, const double* V, const double* dVdr, int 
     c->dr = dr;
     c->extV[0] = extV ? extV[0] : 0.0; c->extV[1] = extV ? extV[1] : 0.0;
     c->extdV[0] = extdVdr ? extdVdr[0] : 0.0; c->extdV[1] = extdVdr ? extdVdr[1] : 0.0;
+    // one-sector-per-pair form of (V, dV/dr): packed on the host, verified bit for bit on the device (table_codec.h)
+    c->vd_ok = c->dd_ok = false;
+    c->have_d2V = false;
+    c->h_dV.clear();
+    if (dVdr) {
+        c->h_dV.assign(dVdr, dVdr + len);
+        if ((rc = build_packed_table(c, V, dVdr, len, dr, c->d_V.as<double>(), c->d_dV.as<double>(), c->d_VD, &c->vd_ok, &c->vd_raw))) return rc;
+    }
+    return 0;
+}
+
+int pimcb_table_codec_info(const pimcb_ctx* c, long* info) {
+    if (!c || !info) return fail(PIMCB_EINVAL, "null argument");
+    info[0] = c->vd_ok ? 1 : 0; info[1] = c->vd_raw; info[2] = c->dd_ok ? 1 : 0; info[3] = c->dd_raw;
+    info[4] = (c->tab_len + 3) / 4;
     return 0;
 }
 
@@ -1450,15 +1535,17 @@ int pimcb_pair_sums(pimcb_ctx* c, double* vint, double* f2, int* sephist, double
         if (tile_on && smem_tile <= 200 * 1024 && ebits <= 31) {
             PairTileParams tp{c->d_V.as<double>(), c->d_dV.as<double>(), c->tab_len, c->dr, 1.0 / c->dr, {c->extV[0], c->extV[1]},
                               {c->extdV[0], c->extdV[1]}, pp.dSep, 1.0 / pp.dSep, pp.want_hist, f2_parity, s->M, pp.gext,
-                              std::ldexp(1.5, ebits), 52 - ebits, G, spc};
+                              std::ldexp(1.5, ebits), 52 - ebits, G, spc, c->vd_ok ? c->d_VD.as<TableSector>() : nullptr};
             const int units = (nsl + spc - 1) / spc;
-#define LAUNCH_PTILE(ND)                                                                                          \
-            rc = set_smem(pair_tile_kernel<ND>, smem_tile); if (rc) return rc;                                      \
-            pair_tile_kernel<ND><<<units, 32 * kPairWarps, smem_tile, c->stream>>>(s->pos.as<double>(), nsl, s->N, s->Npad, c->box, tp, \
+#define LAUNCH_PTILE2(ND, CODEC)                                                                                   \
+            rc = set_smem(pair_tile_kernel<ND, CODEC>, smem_tile); if (rc) return rc;                               \
+            pair_tile_kernel<ND, CODEC><<<units, 32 * kPairWarps, smem_tile, c->stream>>>(s->pos.as<double>(), nsl, s->N, s->Npad, c->box, tp, \
                                                                                   c->d_vint.as<double>(), f2 ? c->d_f2.as<double>() : nullptr, \
                                                                                   c->d_hist.as<int>())
-            if (nd == 1) { LAUNCH_PTILE(1); } else if (nd == 2) { LAUNCH_PTILE(2); } else { LAUNCH_PTILE(3); }
+#define LAUNCH_PTILE(ND) if (c->vd_ok) { LAUNCH_PTILE2(ND, true); } else { LAUNCH_PTILE2(ND, false); }
+            if (nd == 1) { LAUNCH_PTILE(1) } else if (nd == 2) { LAUNCH_PTILE(2) } else { LAUNCH_PTILE(3) }
 #undef LAUNCH_PTILE
+#undef LAUNCH_PTILE2
         } else if (f2 && sym_on && s->N <= 1024 && smem_sym <= 200 * 1024) {
 #define LAUNCH_PSYM(ND, PPT)                                                                                       \
             rc = set_smem(pair_sym_kernel<ND, PPT>, smem_sym); if (rc) return rc;                                   \
@@ -1558,6 +1645,10 @@ int pimcb_set_pair_table_d2(pimcb_ctx* c, const double* d2Vdr2, int len, const d
     c->extd2V[0] = extd2Vdr2 ? extd2Vdr2[0] : 0.0;
     c->extd2V[1] = extd2Vdr2 ? extd2Vdr2[1] : 0.0;
     c->have_d2V = true;
+    c->dd_ok = false;
+    if (static_cast<int>(c->h_dV.size()) == len &&
+        (rc = build_packed_table(c, c->h_dV.data(), d2Vdr2, len, c->dr, c->d_dV.as<double>(), c->d_d2V.as<double>(), c->d_DD, &c->dd_ok, &c->dd_raw)))
+        return rc;
     return 0;
 }
 
@@ -1595,7 +1686,34 @@ int pimcb_virial_sums(pimcb_ctx* c, const double* delta_aos, int t2_parity, doub
         const double* d_gext = (c->gext_gen != 0 && c->gext_gen == s->gen) ? c->d_gext.as<double>() : nullptr;
         const double* d_g2ext = (c->g2ext_gen != 0 && c->g2ext_gen == s->gen) ? c->d_g2ext.as<double>() : nullptr;
         const bool ext = d_gext != nullptr || d_g2ext != nullptr;
-        if (!ext && sym_on && s->N <= 1024 && smem_sym <= 200 * 1024) {
+        // second-generation kernel: 32 x 32 tiles, partner sums by warp shuffle, packed (dV/dr, d2V/dr2) sectors;
+        // PIMCB_VIRIAL_TILE=0 selects the first-generation kernels (A/B)
+        static const bool vtile_on = !(std::getenv("PIMCB_VIRIAL_TILE") && std::atoi(std::getenv("PIMCB_VIRIAL_TILE")) == 0);
+        const int G = (s->N + 31) / 32;
+        const int spc = std::max(1, kPairWarps / G);
+        int ebits = 24;
+        while ((1ll << (ebits - 1)) <= static_cast<long long>(c->tab_len) + 2) ++ebits;
+        auto vtile_smem = [&](int R) {
+            return sizeof(double) * (static_cast<size_t>(spc) * 32 * G * (nd + nc * (1 + R)) + static_cast<size_t>(spc) * 4 * kPairWarps);
+        };
+        int rounds = kPairRound;
+        while (rounds > 1 && vtile_smem(rounds) > 100 * 1024) --rounds;      // two CTAs per SM when it fits
+        if (!ext && vtile_on && vtile_smem(rounds) <= 200 * 1024 && ebits <= 31) {
+            const bool packed = c->dd_ok && (t2_parity == -2 || c->have_d2V);
+            VirialTileParams tp{c->d_dV.as<double>(), c->d_d2V.as<double>(), c->tab_len, c->dr, 1.0 / c->dr, {c->extdV[0], c->extdV[1]},
+                                {c->extd2V[0], c->extd2V[1]}, t2_parity, s->M, std::ldexp(1.5, ebits), 52 - ebits, G, spc, rounds,
+                                packed ? c->d_DD.as<TableSector>() : nullptr};
+            const size_t smem_t = vtile_smem(rounds);
+            const int units = (nsl + spc - 1) / spc;
+#define LAUNCH_VTILE2(ND, CODEC)                                                                                   \
+            rc = set_smem(virial_tile_kernel<ND, CODEC>, smem_t); if (rc) return rc;                                \
+            virial_tile_kernel<ND, CODEC><<<units, 32 * kPairWarps, smem_t, c->stream>>>(s->pos.as<double>(), d_delta, nsl, s->N, s->Npad, \
+                                                                                         c->box, tp, c->d_vir.as<double>())
+#define LAUNCH_VTILE(ND) if (packed) { LAUNCH_VTILE2(ND, true); } else { LAUNCH_VTILE2(ND, false); }
+            if (nd == 1) { LAUNCH_VTILE(1) } else if (nd == 2) { LAUNCH_VTILE(2) } else { LAUNCH_VTILE(3) }
+#undef LAUNCH_VTILE
+#undef LAUNCH_VTILE2
+        } else if (!ext && sym_on && s->N <= 1024 && smem_sym <= 200 * 1024) {
 #define LAUNCH_VSYM(ND, PPT)                                                                                       \
             rc = set_smem(virial_sym_kernel<ND, PPT>, smem_sym); if (rc) return rc;                                 \
             virial_sym_kernel<ND, PPT><<<nsl, 256, smem_sym, c->stream>>>(s->pos.as<double>(), d_delta, nsl, s->N, s->Npad, c->box, vp, \
@@ -1664,6 +1782,7 @@ int pimcb_reduce_bins(pimcb_ctx* c, int root, long* num_total) {
     if (root < 0 || root >= c->comm_size) return fail(PIMCB_EINVAL, "root %d out of range", root);
     if (!c->bins_len) return fail(PIMCB_ESTATE, "no measurement accumulated yet");
     CU(cudaSetDevice(c->device));
+    NvtxRange range("pimcb:reduce_bins");
     int rc;
     if ((rc = fold_binrows(c, c->bins_M))) return rc;
     if ((rc = c->d_count.ensure(2 * sizeof(long long)))) return rc;
@@ -1694,6 +1813,7 @@ int pimcb_gather_bins_q(pimcb_ctx* c, const int* nq_per_rank, double* ssf, doubl
     if (nq_per_rank[c->comm_rank] != c->nq) return fail(PIMCB_EINVAL, "nq_per_rank[%d] = %d but this rank holds %d q-vectors",
                                                        c->comm_rank, nq_per_rank[c->comm_rank], c->nq);
     CU(cudaSetDevice(c->device));
+    NvtxRange range("pimcb:gather_bins_q");
     int rc;
     if ((rc = fold_binrows(c, c->bins_M))) return rc;
     const int M = c->bins_M;
