@@ -28,7 +28,13 @@ if ROOT not in sys.path:
 
 from pimc_b200 import synth  # noqa: E402
 
-METRIC = "ISF+S(q) evaluations/sec (N=256 He-4, M=170, 64 q)"
+METRIC = "ISF+S(q) evaluations/sec (N=256 He-4, M=170, 64 q)"       # BASELINE.json's metric, quoted on C2
+
+
+def metric_name(shape, nq):
+    if shape.name == "C2":
+        return METRIC
+    return f"ISF+S(q) evaluations/sec ({shape.name}: N={shape.N} He-4, M={shape.M}, {nq} q, {shape.ndim}-D)"
 UNIT = "evaluations/s"
 
 
@@ -51,6 +57,9 @@ def parse_args():
     ap.add_argument("--collective", default="lib", choices=["torch", "lib"],
                     help="who issues the one collective per bin: torch.distributed on the library's device buffer, or the "
                          "library's own NCCL entry points (pimcb_reduce_bins / pimcb_gather_bins_q)")
+    ap.add_argument("--total-batch", type=int, default=0,
+                    help="STRONG scaling over walkers: this many configurations per batch in total, split over the GPUs "
+                         "(overrides --batch; scaling is reported as strong)")
     ap.add_argument("--unique", type=int, default=16, help="distinct synthetic configurations generated per slot")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -258,7 +267,7 @@ def run_reference(args, shape, q):
     arm = CpuArm(shape, q, budget)
     value, wall = time_cpu_arm(arm, args.steps, args.warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(shape, len(q)), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": shared_config(shape, len(q)),
@@ -417,6 +426,10 @@ def run_ours(args, shape, q):
 
     from pimc_b200 import multi
     B, K, W, P = args.batch, args.steps, args.warmup, args.batches_per_step
+    if args.total_batch > 0:
+        if args.total_batch % world:
+            raise SystemExit(f"--total-batch {args.total_batch} is not a multiple of {world} GPUs")
+        B = args.total_batch // world
     q_all = q
     if args.shard == "q" and world > 1:
         lo, hi = multi.shard_range(len(q_all), world, rank)
@@ -701,8 +714,9 @@ def run_ours(args, shape, q):
         dctx.close()
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak" if args.shard == "config" else "strong",
+        "metric": metric_name(shape, len(q_all)), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True,
+        "scaling": "weak" if (args.shard == "config" and args.total_batch <= 0) else "strong",
         "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": shared_config(shape, len(q_all)),

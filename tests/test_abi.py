@@ -65,3 +65,10 @@ def test_adaptor_layer_compiles_against_the_upstream_headers(ndim):
     r = subprocess.run(["make", "-C", host, "upstream-check", f"NDIM={ndim}"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert f"upstream-check OK (NDIM={ndim})" in r.stdout
+
+
+def test_integration_doc_carries_the_literal_patch():
+    """INTEGRATION.md section 2.5 is pimc_b200/host/upstream.patch verbatim (what `make upstream-check` applies)."""
+    patch = open(os.path.join(ROOT, "pimc_b200", "host", "upstream.patch")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert patch in doc
