@@ -768,7 +768,7 @@ def pair_legs(args, ctx, shape, pinned, use_slots, B):
     sums of the same batches, against the measured gather roofline of their access pattern."""
     import math
     max_sep = math.sqrt(sum((L / 2.0) ** 2 for L in shape.side))
-    Vt, dVt, drt = synth.aziz_table_numpy(max_sep)
+    Vt, dVt, d2Vt, drt = synth.aziz_table_numpy(max_sep, second=True)
     ctx.set_pair_table(Vt, dVt, drt)
     ctx.select_slot(0)
     dSep = 0.5 * math.sqrt(3.0) * shape.side[2] / 50.0
@@ -800,7 +800,6 @@ def pair_legs(args, ctx, shape, pinned, use_slots, B):
                                         "footprints <= 53 MB, 140 G/s at 106 MB (V + dV/dr tables of C2), 73 G/s from DRAM",
                          "hbm_algorithmic": {"bytes": 8 * gathers + B * 8 * shape.ndim * shape.N * shape.M,
                                              "achieved_gbs": (8 * gathers + B * 8 * shape.ndim * shape.N * shape.M) / p_s / 1e9}}}
-    d2Vt = np.gradient(dVt, drt)                   # timing only: central differences of the dV/dr table
     ctx.set_pair_table_d2(d2Vt)
     ctx.select_slot(0)
     delta = 0.01 * pinned[0].array                 # any per-bead vectors in the beads' AoS shape

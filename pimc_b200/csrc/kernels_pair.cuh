@@ -22,6 +22,12 @@
 //     (|frac - integer| < 2^-20, 2 in 10^6 pairs) and everything outside the fast path's validity re-run the
 //     reference's exact operation sequence (minimage_norm / __ddiv_rn), so k and the histogram stay BIT-IDENTICAL to
 //     the CPU (include/potential.h:249-260, src/action.cpp:216-224) -- the tests hold sepHist to array_equal.
+//   * The histogram bin from the table index: k = int(r/dr) pins r/dSep to an interval of width dr/dSep = 8e-6 bins, so
+//     int(r/dSep) = (k * round(2^S dr/dSep)) >> S (one integer multiply-add pair) unless that product lies within the
+//     interval's width of a bin edge (3 in 10^5 pairs), which again takes the exact path.
+//   * Table reads without range branches: the device tables carry ext[0] in entry 0 and ext[1] in entry `len`
+//     (TabulatedPotential::direct returns ext[0] for k <= 0 and ext[1] for k >= len and never reads entry 0), so the read
+//     is table[min(max(k, 0), len)].
 //   * Minimum image by rint(): sep = s - pSide * rint(s * sideInv) with rint() as an add/subtract of 1.5 * 2^52 (three
 //     FP64 instructions per component instead of five plus an FRND); it differs from Container::putInBC's
 //     floor(x + 0.5) (include/container.h:50-59) only on exact ties, where both images are equally near and r is the
@@ -33,12 +39,23 @@
 
 namespace pimcb {
 
-struct PairTileParams {
-    const double* V; const double* dVdr; int len; double dr, inv_dr; double extV[2]; double extdV[2];
-    double dSep, inv_dSep; int want_hist; int f2_parity; int M;
-    const double* gext;    // gradient of the external potential per bead, slice rows like pos ([sl][d][Npad]), or nullptr
+// What both tile kernels need to turn a pair of beads into a table index (and a histogram bin).
+struct TileIndexParams {
+    int len; double dr, inv_dr;
+    double dSep; int want_hist;
     double magic;          // 1.5 * 2^e: ulp(magic) = 2^-fb, table indices < 2^(e-1)
-    int fb;                // fraction bits below the integer part in the low word of (t + magic), <= 28
+    int fb;                // fraction bits below the integer part in the low word of (t + magic), 21..28
+    unsigned hmul_lo, hmul_hi;   // round(2^hshift dr/dSep): bin = (k * hmul) >> hshift
+    int hshift;            // 32..56, or 0: no integer shortcut for the bin (every pair takes the exact path for it)
+    unsigned hslop, hspan; // bin safe iff (frac32 - hslop) < hspan  (unsigned), frac32 = fraction of k dr/dSep in 2^-32
+    double x[4], xh[4], x3[4];   // CodecSteps of dr
+};
+
+struct PairTileParams {
+    const double* V; const double* dVdr;   // verbatim tables, len + 1 entries: [0] = ext[0], [len] = ext[1]
+    TileIndexParams ix;
+    int f2_parity; int M;
+    const double* gext;    // gradient of the external potential per bead, slice rows like pos ([sl][d][Npad]), or nullptr
     int G;                 // particle groups of 32
     int spc;               // slices per CTA work unit (> 1 when a slice has fewer groups than the CTA has warps)
     const TableSector* VD; // (V, dV/dr) packed four entries per 32-byte sector (table_codec.h), or nullptr: verbatim tables only
@@ -56,6 +73,7 @@ constexpr int kPairRound = 4;        // group offsets per round (partner-side sl
 constexpr double kRintMagic = 6755399441055744.0;   // 1.5 * 2^52
 
 // r ~ sqrt(r2) and rinv ~ 1/sqrt(r2), both to ~2 ulp: MUFU.RSQ64H seed + two Goldschmidt iterations.
+template <bool WANT_RINV>
 __device__ __forceinline__ void rsqrt_pair(double r2, double& r, double& rinv) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2));
@@ -65,117 +83,155 @@ __device__ __forceinline__ void rsqrt_pair(double r2, double& r, double& rinv) {
     h = fma(h, e, h);
     e = fma(-h, g, 0.5);
     r = fma(g, e, g);
-    rinv = 2.0 * fma(h, e, h);
+    rinv = WANT_RINV ? 2.0 * fma(h, e, h) : 0.0;
 }
 
-// floor(t) and "t is safely away from an integer", from the bits of t + magic (magic = 1.5 * 2^e, fb = 52 - e fraction bits).
-// Returns false when t is out of the trick's range (negative, too large, NaN) or within 2^-20 of an integer.
-__device__ __forceinline__ bool floor_safe(double t, double magic, int fb, int& k) {
-    const double u = t + magic;
+// floor(t) and "t is safely away from an integer", from the bits of u = t + magic (magic = 1.5 * 2^e, fb = 52 - e fraction
+// bits).  Returns false when t is out of the trick's range (negative, too large, NaN) or within 2^-20 of an integer.
+__device__ __forceinline__ bool floor_safe(double u, double magic, int fb, int& k) {
     const unsigned lo = static_cast<unsigned>(__double2loint(u)), hi = static_cast<unsigned>(__double2hiint(u));
     const unsigned mhi = static_cast<unsigned>(__double2hiint(magic));
-    // same exponent and the leading mantissa bit of 1.5 still set: u in [magic, magic + 2^(e-1))
-    const bool in_range = (hi >> 19) == (mhi >> 19);
-    k = static_cast<int>(((hi & 0x7ffffu) << (32 - fb)) | (lo >> fb));
-    const unsigned frac = lo & ((1u << fb) - 1u);
-    const unsigned eps = 1u << (fb - 20);
-    return in_range && (frac - eps) < ((1u << fb) - 2u * eps);
+    k = static_cast<int>(__funnelshift_r(lo, hi & 0x7ffffu, fb));          // (mantissa below the 1.5 bit) >> fb
+    const unsigned frac = lo << (32 - fb);                                  // fraction, left aligned
+    // same exponent and the leading mantissa bit of 1.5 still set: u in [magic, magic + 2^(e-1)); fraction in [2^-20, 1 - 2^-20)
+    return ((hi ^ mhi) < 0x80000u) && (frac - 0x1000u) < 0xffffe000u;
+}
+
+// Geometry of one pair on the fast path: minimum-image separation, r, 1/r, table index and histogram bin.
+// `unsafe` = the index or the bin must be recomputed with the reference's exact operation sequence.
+template <int ND, bool WANT_RINV>
+__device__ __forceinline__ void pair_fast(const double (&xi)[ND], const double* __restrict__ xb, int NP, int m, const BoxDev& box,
+                                          const TileIndexParams& ix, double (&sep)[ND], double& r, double& rinv, int& k, int& nR,
+                                          bool& unsafe) {
+    double r2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        const double sd = xi[d] - xb[d * NP + m];
+        const double tt = fma(sd, box.sideInv[d], kRintMagic) - kRintMagic;
+        sep[d] = fma(-box.pSide[d], tt, sd);
+        r2 = fma(sep[d], sep[d], r2);
+    }
+    rsqrt_pair<WANT_RINV>(r2, r, rinv);
+    unsafe = !floor_safe(fma(r, ix.inv_dr, ix.magic), ix.magic, ix.fb, k);
+    nR = 0;
+    if (ix.want_hist) {
+        // k dr / dSep in fixed point: 64-bit product of k with round(2^hshift dr/dSep)
+        const unsigned long long prod = static_cast<unsigned long long>(static_cast<unsigned>(k)) * ix.hmul_lo +
+                                        (static_cast<unsigned long long>(static_cast<unsigned>(k) * ix.hmul_hi) << 32);
+        const unsigned phi = static_cast<unsigned>(prod >> 32), plo = static_cast<unsigned>(prod);
+        nR = static_cast<int>(phi >> (ix.hshift - 32));
+        const unsigned frac = __funnelshift_r(plo, phi, ix.hshift - 32);   // the 32 bits below the bin number
+        unsafe = unsafe || !((frac - ix.hslop) < ix.hspan);
+    }
+}
+
+// The reference's own operation sequence (putInBC -> dot -> sqrt -> r/dr -> int(); r/dSep -> int()), bit for bit.
+// Out of line and returning BY VALUE: a call that took the index arrays by reference would pin them to local memory and
+// put a store / load pair per pair into the fast path (it did: 2.03 ms instead of 1.7 ms for the V-only pass).
+template <int ND>
+__device__ __noinline__ int2 pair_exact(const double* __restrict__ xsl, int NP, int i, int j, BoxDev box, double dr, double dSep,
+                                        int want_hist) {
+    double sx[ND];
+    const double rx = minimage_norm<ND>(xsl, NP, i, j, box, sx);
+    int2 out;
+    out.x = __double2int_rz(__ddiv_rn(rx, dr));
+    out.y = want_hist ? __double2int_rz(__ddiv_rn(rx, dSep)) : 0;
+    return out;
+}
+
+// Table entries F[k] (and G[k] when WANT_G) with k clamped to [0, len]: one packed sector (CODEC) or the verbatim tables.
+template <bool WANT_G, bool CODEC>
+__device__ __forceinline__ void table_issue(const TableSector* __restrict__ packed, const double* __restrict__ F, const double* __restrict__ G,
+                                            int kc, TableSector& sec, double& f, double& g) {
+    if constexpr (CODEC) {
+        sec = ldg_sector(packed + (kc >> 2));
+    } else {
+        f = __ldg(F + kc);
+        g = WANT_G ? __ldg(G + kc) : 0.0;
+    }
+}
+template <bool WANT_G, bool CODEC>
+__device__ __forceinline__ void table_finish(const TileIndexParams& ix, const double* __restrict__ F, const double* __restrict__ G, int kc,
+                                             const TableSector& sec, double& f, double& g) {
+    if constexpr (CODEC) {
+        const int j = kc & 3;
+        if (sector_is_raw(sec)) {
+            f = __ldg(F + kc);
+            g = WANT_G ? __ldg(G + kc) : 0.0;
+        } else {
+            sector_decode<WANT_G>(sec, j, ix.x[j], ix.xh[j], ix.x3[j], f, g);
+        }
+    }
 }
 
 // One tile: the 32 particles of the home group (lane = particle i, position xi) against the 32 particles of group b
 // (positions xb[d * NP + m]), steps [s_lo, s_hi), partner m = (lane + s) & 31.  FORCE: own-side force into Fi, partner-side
-// force into Gv (it ends up in the lane that holds the partner: particle 32 b + lane).
-template <int ND, bool FORCE, bool CODEC>
+// force into Gv (it ends up in the lane that holds the partner: particle 32 b + lane).  CHECK = false: every pair of the
+// tile exists (both groups full, not the diagonal tile) and no validity logic is compiled.
+#ifndef PIMCB_PTILE_U
+#define PIMCB_PTILE_U 2
+#endif
+template <int ND, bool FORCE, bool CODEC, bool CHECK>
 __device__ __forceinline__ void pair_tile(const double* __restrict__ xsl, int NP, const double (&xi)[ND], int i, bool ivalid, int b,
                                           int lane, int s_lo, int s_hi, bool diag, int N, const BoxDev& box,
                                           const PairTileParams& pp, int* __restrict__ shist_sl, double& vsum, double (&Fi)[ND],
                                           double (&Gv)[ND]) {
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr int U = PIMCB_PTILE_U;         // pairs in flight per lane (tile step counts are multiples of 16)
     const double* xb = xsl + 32 * b;
-    for (int s = s_lo; s < s_hi; s += 2) {
-        double sep[2][ND], r[2], rinv[2], vv[2], dv[2];
-        int kidx[2], nR[2];
-        bool valid[2];
+    const TileIndexParams& ix = pp.ix;
+    for (int s = s_lo; s < s_hi; s += U) {
+        double sep[U][ND], r[U], rinv[U], vv[U], dv[U];
+        int kidx[U], nR[U], kc[U];
+        bool valid[U], unsafe[U];
+        TableSector sec[U];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int ss = s + u;
             const int m = (lane + ss) & 31;
-            const int j = 32 * b + m;
-            valid[u] = ivalid && j < N && !(diag && ss == 16 && lane >= 16);
-            double r2 = 0.0;
-#pragma unroll
-            for (int d = 0; d < ND; ++d) {
-                const double sd = xi[d] - xb[d * NP + m];
-                const double tt = fma(sd, box.sideInv[d], kRintMagic) - kRintMagic;
-                sep[u][d] = fma(-box.pSide[d], tt, sd);
-                r2 = fma(sep[u][d], sep[u][d], r2);
-            }
-            if (!valid[u]) r2 = 1.0;
-            rsqrt_pair(r2, r[u], rinv[u]);
-            bool safe = floor_safe(r[u] * pp.inv_dr, pp.magic, pp.fb, kidx[u]);
-            nR[u] = 0;
-            if (pp.want_hist) {
-                int nr;
-                safe = floor_safe(r[u] * pp.inv_dSep, pp.magic, pp.fb, nr) && safe;
-                nR[u] = nr;
-            }
-            if (!safe && valid[u]) {
-                // the reference's own operation sequence (putInBC -> dot -> sqrt -> r/dr -> int()), bit for bit
-                double sx[ND];
-                const double rx = minimage_norm<ND>(xsl, NP, i, j, box, sx);
-                kidx[u] = __double2int_rz(__ddiv_rn(rx, pp.dr));
-                if (pp.want_hist) nR[u] = __double2int_rz(__ddiv_rn(rx, pp.dSep));
+            pair_fast<ND, FORCE>(xi, xb, NP, m, box, ix, sep[u], r[u], rinv[u], kidx[u], nR[u], unsafe[u]);
+            valid[u] = true;
+            if constexpr (CHECK) {
+                valid[u] = ivalid && 32 * b + m < N && !(diag && ss == 16 && lane >= 16);
+                unsafe[u] = unsafe[u] && valid[u];
             }
         }
-        if constexpr (CODEC) {
-            // one sector request per pair serves V and dV/dr (table_codec.h); RAW sectors fall back to the verbatim tables
-            TableSector sec[2];
-            bool inside[2];
+#ifndef PIMCB_COUNT_FASTPATH         // (static instruction counting of the fast path only: tools/sass_loop.py)
+        bool any_unsafe = false;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {       // both sector reads of the step pair are issued here
-                inside[u] = valid[u] && kidx[u] > 0 && kidx[u] < pp.len;
-                sec[u].w[0] = sec[u].w[1] = sec[u].w[2] = 0;
-                sec[u].w[3] = 0;
-                if (inside[u]) sec[u] = ldg_sector(pp.VD + (kidx[u] >> 2));
-            }
+        for (int u = 0; u < U; ++u) any_unsafe = any_unsafe || unsafe[u];
+        if (any_unsafe) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                vv[u] = 0.0;
-                dv[u] = 0.0;
-                if (inside[u]) {
-                    if (sector_is_raw(sec[u])) {
-                        vv[u] = __ldg(pp.V + kidx[u]);
-                        if (FORCE) dv[u] = __ldg(pp.dVdr + kidx[u]);
-                    } else {
-                        sector_decode<FORCE>(sec[u], kidx[u] & 3, pp.dr, vv[u], dv[u]);
-                    }
-                } else if (valid[u]) {
-                    vv[u] = kidx[u] <= 0 ? pp.extV[0] : pp.extV[1];
-                    if (FORCE) dv[u] = kidx[u] <= 0 ? pp.extdV[0] : pp.extdV[1];
+            for (int u = 0; u < U; ++u)
+                if (unsafe[u]) {
+                    const int2 e = pair_exact<ND>(xsl, NP, i, 32 * b + ((lane + s + u) & 31), box, ix.dr, ix.dSep, ix.want_hist);
+                    kidx[u] = e.x;
+                    nR[u] = e.y;
                 }
-            }
-        } else {
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {           // both gathers of the step pair are issued here
-            const bool inside = kidx[u] > 0 && kidx[u] < pp.len;
-            vv[u] = 0.0;
-            dv[u] = 0.0;
-            if (valid[u]) {
-                vv[u] = inside ? __ldg(pp.V + kidx[u]) : (kidx[u] <= 0 ? pp.extV[0] : pp.extV[1]);
-                if (FORCE) dv[u] = inside ? __ldg(pp.dVdr + kidx[u]) : (kidx[u] <= 0 ? pp.extdV[0] : pp.extdV[1]);
-            }
         }
+#endif
+#pragma unroll
+        for (int u = 0; u < U; ++u) {           // both table reads of the step pair are issued here
+            kc[u] = max(min(kidx[u], ix.len), 0);
+            table_issue<FORCE, CODEC>(pp.VD, pp.V, pp.dVdr, kc[u], sec[u], vv[u], dv[u]);
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            vsum += vv[u];
-            if (pp.want_hist && valid[u] && nR[u] >= 0 && nR[u] < kNPCFSEP) atomicAdd(&shist_sl[nR[u]], 1);
+        for (int u = 0; u < U; ++u) {
+            table_finish<FORCE, CODEC>(ix, pp.V, pp.dVdr, kc[u], sec[u], vv[u], dv[u]);
+            if constexpr (CHECK) {
+                vsum += valid[u] ? vv[u] : 0.0;
+                if (ix.want_hist && valid[u] && static_cast<unsigned>(nR[u]) < static_cast<unsigned>(kNPCFSEP)) atomicAdd(shist_sl + nR[u], 1);
+            } else {
+                vsum += vv[u];
+                if (ix.want_hist && static_cast<unsigned>(nR[u]) < static_cast<unsigned>(kNPCFSEP)) atomicAdd(shist_sl + nR[u], 1);
+            }
             if constexpr (FORCE) {
-                const double g = dv[u] * rinv[u];      // (dV/dr)/r, potential.h:997-1003
+                double g = dv[u] * rinv[u];             // (dV/dr)/r, potential.h:997-1003
+                if constexpr (CHECK) g = valid[u] ? g : 0.0;
                 const int src = (lane - (s + u)) & 31;  // the lane whose partner this lane is at this step
 #pragma unroll
                 for (int d = 0; d < ND; ++d) {
-                    const double f = g * sep[u][d];    // 0 for invalid pairs (dv = 0)
+                    const double f = g * sep[u][d];
                     Fi[d] += f;
                     Gv[d] -= __shfl_sync(FULL, f, src);          // gradV(sep_ji) = -gradV(sep_ij)
                 }
@@ -207,13 +263,13 @@ pair_tile_kernel(const double* __restrict__ pos, int nslices, int N, int Npad, B
     for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
         const int sl0 = unit * spc;
         const int nsl = min(spc, nslices - sl0);
-        // stage the slices of this unit: rows padded to whole groups (the padding is never read as a valid particle)
+        // stage the slices of this unit: rows padded to whole groups (the padding is never counted as a particle)
         for (int k = threadIdx.x; k < nsl * ND * NP; k += blockDim.x) {
             const int s = k / (ND * NP), rem = k - s * (ND * NP), d = rem / NP, i = rem - d * NP;
             xs[k] = i < Npad ? __ldg(pos + (static_cast<size_t>(sl0 + s) * ND + d) * Npad + i) : 0.0;
             if (f2_any) accF[k] = 0.0;
         }
-        if (pp.want_hist)
+        if (pp.ix.want_hist)
             for (int k = threadIdx.x; k < nsl * kNPCFSEP; k += blockDim.x) shist[k] = 0;
         __syncthreads();
 
@@ -240,11 +296,13 @@ pair_tile_kernel(const double* __restrict__ pos, int nslices, int N, int Npad, B
                     else { s_lo = 0; s_hi = 32; }
                     int b = a + o;
                     if (b >= G) b -= G;
+                    const bool full = o != 0 && 32 * (a + 1) <= N && 32 * (b + 1) <= N;   // every pair of the tile exists
                     double Gv[ND];
 #pragma unroll
                     for (int d = 0; d < ND; ++d) Gv[d] = 0.0;
                     if (do_f) {
-                        pair_tile<ND, true, CODEC>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, o == 0, N, box, pp, shist_sl, vsum, Fi, Gv);
+                        if (full) pair_tile<ND, true, CODEC, false>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, false, N, box, pp, shist_sl, vsum, Fi, Gv);
+                        else pair_tile<ND, true, CODEC, true>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, o == 0, N, box, pp, shist_sl, vsum, Fi, Gv);
                         if (o == 0) {
 #pragma unroll
                             for (int d = 0; d < ND; ++d) Fi[d] += Gv[d];        // the diagonal tile's partners are the home group itself
@@ -254,7 +312,8 @@ pair_tile_kernel(const double* __restrict__ pos, int nslices, int N, int Npad, B
                             for (int d = 0; d < ND; ++d) slot[d * NP] = Gv[d];
                         }
                     } else {
-                        pair_tile<ND, false, CODEC>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, o == 0, N, box, pp, shist_sl, vsum, Fi, Gv);
+                        if (full) pair_tile<ND, false, CODEC, false>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, false, N, box, pp, shist_sl, vsum, Fi, Gv);
+                        else pair_tile<ND, false, CODEC, true>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, o == 0, N, box, pp, shist_sl, vsum, Fi, Gv);
                     }
                 }
                 if (do_f) {
@@ -304,7 +363,7 @@ pair_tile_kernel(const double* __restrict__ pos, int nslices, int N, int Npad, B
                 vint[sl] = v;
                 if (f2) f2[sl] = fsum;
             }
-            if (pp.want_hist)
+            if (pp.ix.want_hist)
                 for (int k = lane; k < kNPCFSEP; k += 32) hist[static_cast<size_t>(sl) * kNPCFSEP + k] = shist[sloc * kNPCFSEP + k];
         }
         __syncthreads();
@@ -321,89 +380,64 @@ pair_tile_kernel(const double* __restrict__ pos, int nslices, int N, int Npad, B
 // what is used here; external potential "free" (the non-free case runs virial_kernel<ND, true>).
 // ---------------------------------------------------------------------------------------------
 struct VirialTileParams {
-    const double* dVdr; const double* d2V; int len; double dr, inv_dr; double extdV[2]; double extd2V[2];
+    const double* dVdr; const double* d2V;     // verbatim tables, len + 1 entries: [0] = ext[0], [len] = ext[1]
+    TileIndexParams ix;                          // want_hist = 0
     int t2_parity; int M;
-    double magic; int fb; int G; int spc; int rounds;     // rounds = group offsets per round (partner-side slots that fit)
-    const TableSector* DD;  // (dV/dr, d2V/dr2) packed four entries per sector, or nullptr
+    int G; int spc; int rounds;                  // rounds = group offsets per round (partner-side slots that fit)
+    const TableSector* DD;                       // (dV/dr, d2V/dr2) packed four entries per sector, or nullptr
 };
 
-template <int ND, bool T2, bool CODEC>
+#ifndef PIMCB_VTILE_U
+#define PIMCB_VTILE_U 2
+#endif
+template <int ND, bool T2, bool CODEC, bool CHECK>
 __device__ __forceinline__ void virial_tile(const double* __restrict__ xsl, int NP, const double (&xi)[ND], int i, bool ivalid, int b,
                                             int lane, int s_lo, int s_hi, bool diag, int N, const BoxDev& box,
                                             const VirialTileParams& vp, double (&own)[ND + ND * (ND + 1) / 2],
                                             double (&vis)[ND + ND * (ND + 1) / 2]) {
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int NT = ND * (ND + 1) / 2;
+    constexpr int U = PIMCB_VTILE_U;
     const double* xb = xsl + 32 * b;
-    for (int s = s_lo; s < s_hi; s += 2) {
-        double sep[2][ND], r[2], rinv[2], dv[2], d2[2];
-        int kidx[2];
-        bool valid[2];
+    const TileIndexParams& ix = vp.ix;
+    for (int s = s_lo; s < s_hi; s += U) {
+        double sep[U][ND], r[U], rinv[U], dv[U], d2[U];
+        int kidx[U], nR[U], kc[U];
+        bool valid[U], unsafe[U];
+        TableSector sec[U];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int ss = s + u;
             const int m = (lane + ss) & 31;
-            const int j = 32 * b + m;
-            valid[u] = ivalid && j < N && !(diag && ss == 16 && lane >= 16);
-            double r2 = 0.0;
-#pragma unroll
-            for (int d = 0; d < ND; ++d) {
-                const double sd = xi[d] - xb[d * NP + m];
-                const double tt = fma(sd, box.sideInv[d], kRintMagic) - kRintMagic;
-                sep[u][d] = fma(-box.pSide[d], tt, sd);
-                r2 = fma(sep[u][d], sep[u][d], r2);
-            }
-            if (!valid[u]) r2 = 1.0;
-            rsqrt_pair(r2, r[u], rinv[u]);
-            const bool safe = floor_safe(r[u] * vp.inv_dr, vp.magic, vp.fb, kidx[u]);
-            if (!safe && valid[u]) {
-                double sx[ND];
-                const double rx = minimage_norm<ND>(xsl, NP, i, j, box, sx);
-                kidx[u] = __double2int_rz(__ddiv_rn(rx, vp.dr));
+            pair_fast<ND, true>(xi, xb, NP, m, box, ix, sep[u], r[u], rinv[u], kidx[u], nR[u], unsafe[u]);
+            valid[u] = true;
+            if constexpr (CHECK) {
+                valid[u] = ivalid && 32 * b + m < N && !(diag && ss == 16 && lane >= 16);
+                unsafe[u] = unsafe[u] && valid[u];
             }
         }
-        if constexpr (CODEC) {
-            TableSector sec[2];
-            bool inside[2];
+        bool any_unsafe = false;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                inside[u] = valid[u] && kidx[u] > 0 && kidx[u] < vp.len;
-                sec[u].w[0] = sec[u].w[1] = sec[u].w[2] = 0;
-                sec[u].w[3] = 0;
-                if (inside[u]) sec[u] = ldg_sector(vp.DD + (kidx[u] >> 2));
-            }
+        for (int u = 0; u < U; ++u) any_unsafe = any_unsafe || unsafe[u];
+        if (any_unsafe) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                dv[u] = 0.0;
-                d2[u] = 0.0;
-                if (inside[u]) {
-                    if (sector_is_raw(sec[u])) {
-                        dv[u] = __ldg(vp.dVdr + kidx[u]);
-                        if (T2) d2[u] = __ldg(vp.d2V + kidx[u]);
-                    } else {
-                        sector_decode<T2>(sec[u], kidx[u] & 3, vp.dr, dv[u], d2[u]);
-                    }
-                } else if (valid[u]) {
-                    dv[u] = kidx[u] <= 0 ? vp.extdV[0] : vp.extdV[1];
-                    if (T2) d2[u] = kidx[u] <= 0 ? vp.extd2V[0] : vp.extd2V[1];
-                }
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const bool inside = kidx[u] > 0 && kidx[u] < vp.len;
-                dv[u] = 0.0;
-                d2[u] = 0.0;
-                if (valid[u]) {
-                    dv[u] = inside ? __ldg(vp.dVdr + kidx[u]) : (kidx[u] <= 0 ? vp.extdV[0] : vp.extdV[1]);
-                    if (T2) d2[u] = inside ? __ldg(vp.d2V + kidx[u]) : (kidx[u] <= 0 ? vp.extd2V[0] : vp.extd2V[1]);
-                }
-            }
+            for (int u = 0; u < U; ++u)
+                if (unsafe[u]) kidx[u] = pair_exact<ND>(xsl, NP, i, 32 * b + ((lane + s + u) & 31), box, ix.dr, ix.dSep, 0).x;
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
+            kc[u] = max(min(kidx[u], ix.len), 0);
+            table_issue<T2, CODEC>(vp.DD, vp.dVdr, vp.d2V, kc[u], sec[u], dv[u], d2[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            table_finish<T2, CODEC>(ix, vp.dVdr, vp.d2V, kc[u], sec[u], dv[u], d2[u]);
+            if constexpr (CHECK) {
+                dv[u] = valid[u] ? dv[u] : 0.0;
+                d2[u] = valid[u] ? d2[u] : 0.0;
+                rinv[u] = valid[u] ? rinv[u] : 0.0;
+            }
             const int src = (lane - (s + u)) & 31;
-            const double g = dv[u] * rinv[u];                  // 0 for invalid pairs
+            const double g = dv[u] * rinv[u];
 #pragma unroll
             for (int d = 0; d < ND; ++d) {
                 const double gi = g * sep[u][d];
@@ -411,10 +445,10 @@ __device__ __forceinline__ void virial_tile(const double* __restrict__ xsl, int 
                 vis[d] -= __shfl_sync(FULL, gi, src);          // gradV(sep_ji) = -gradV(sep_ij)
             }
             if constexpr (T2) {
-                const double dV = valid[u] ? fabs(dv[u]) : 0.0;
+                const double dV = fabs(dv[u]);                 // |(dV/dr / r) sep| = |dV/dr| (src/action.cpp:1544)
                 const double ri2 = rinv[u] * rinv[u];
                 const double diagv = dV * rinv[u];
-                const double a = valid[u] ? fma(d2[u], ri2, -diagv * ri2) : 0.0;     // d2V/r^2 - dV/r^3
+                const double a = fma(d2[u], ri2, -diagv * ri2);     // d2V/r^2 - dV/r^3
                 int k = ND;
 #pragma unroll
                 for (int p = 0; p < ND; ++p)
@@ -482,8 +516,14 @@ virial_tile_kernel(const double* __restrict__ pos, const double* __restrict__ de
                     double vis[NC];
 #pragma unroll
                     for (int c = 0; c < NC; ++c) vis[c] = 0.0;
-                    if (do_t2) virial_tile<ND, true, CODEC>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, o == 0, N, box, vp, own, vis);
-                    else virial_tile<ND, false, CODEC>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, o == 0, N, box, vp, own, vis);
+                    const bool full = o != 0 && 32 * (a + 1) <= N && 32 * (b + 1) <= N;   // every pair of the tile exists
+                    if (do_t2) {
+                        if (full) virial_tile<ND, true, CODEC, false>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, false, N, box, vp, own, vis);
+                        else virial_tile<ND, true, CODEC, true>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, o == 0, N, box, vp, own, vis);
+                    } else {
+                        if (full) virial_tile<ND, false, CODEC, false>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, false, N, box, vp, own, vis);
+                        else virial_tile<ND, false, CODEC, true>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, o == 0, N, box, vp, own, vis);
+                    }
                     if (o == 0) {
 #pragma unroll
                         for (int c = 0; c < NC; ++c) own[c] += vis[c];

@@ -724,7 +724,7 @@ int stage_into(pimcb_ctx* c, int slot, const double* beads, int B, int M, int N,
 // Decodes every entry of a packed table pair and compares it with the verbatim tables, bit for bit; mismatches[0] counts
 // the entries that differ (must be 0), mismatches[1] the RAW sectors.
 __global__ void codec_verify_kernel(const TableSector* __restrict__ sec, const double* __restrict__ F, const double* __restrict__ G,
-                                    int len, double dr, unsigned long long* __restrict__ mismatches) {
+                                    int len, CodecSteps st, unsigned long long* __restrict__ mismatches) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= len) return;
     const TableSector s = sec[k >> 2];
@@ -733,7 +733,8 @@ __global__ void codec_verify_kernel(const TableSector* __restrict__ sec, const d
         return;
     }
     double f, g;
-    sector_decode<true>(s, k & 3, dr, f, g);
+    const int j = k & 3;
+    sector_decode<true>(s, j, st.x[j], st.xh[j], st.x3[j], f, g);
     if (__double_as_longlong(f) != __double_as_longlong(F[k]) || __double_as_longlong(g) != __double_as_longlong(G[k]))
         atomicAdd(mismatches, 1ull);
 }
@@ -748,12 +749,13 @@ int build_packed_table(pimcb_ctx* c, const double* F, const double* G, int len, 
     if (!codec_on || len < 8) return 0;
     const int ns = (len + 3) / 4;
     std::vector<TableSector> sec(ns);
+    const CodecSteps st = codec_steps(dr);
     const int nth = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     std::vector<std::thread> pool;
     for (int w = 0; w < nth; ++w)
         pool.emplace_back([&, w]() {
             const int s0 = static_cast<int>(static_cast<long long>(ns) * w / nth), s1 = static_cast<int>(static_cast<long long>(ns) * (w + 1) / nth);
-            for (int s = s0; s < s1; ++s) sector_encode(F, G, len, 4 * s, dr, sec[s]);
+            for (int s = s0; s < s1; ++s) sector_encode(F, G, len, 4 * s, dr, st, sec[s]);
         });
     for (auto& t : pool) t.join();
     int rc = dst.ensure(sizeof(TableSector) * static_cast<size_t>(ns));
@@ -761,7 +763,7 @@ int build_packed_table(pimcb_ctx* c, const double* F, const double* G, int len, 
     if ((rc = c->d_count.ensure(2 * sizeof(unsigned long long)))) return rc;
     CU(cudaMemcpyAsync(dst.p, sec.data(), sizeof(TableSector) * static_cast<size_t>(ns), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemsetAsync(c->d_count.p, 0, 2 * sizeof(unsigned long long), c->stream));
-    codec_verify_kernel<<<(len + 255) / 256, 256, 0, c->stream>>>(dst.as<TableSector>(), dF, dG, len, dr, c->d_count.as<unsigned long long>());
+    codec_verify_kernel<<<(len + 255) / 256, 256, 0, c->stream>>>(dst.as<TableSector>(), dF, dG, len, st, c->d_count.as<unsigned long long>());
     CU(cudaGetLastError());
     unsigned long long res[2] = {1, 0};
     CU(cudaMemcpyAsync(res, c->d_count.p, sizeof res, cudaMemcpyDeviceToHost, c->stream));
@@ -770,6 +772,36 @@ int build_packed_table(pimcb_ctx* c, const double* F, const double* G, int len, 
     *nraw = static_cast<long>(res[1]);
     *ok = res[0] == 0 && res[1] * 20 <= static_cast<unsigned long long>(ns);
     return 0;
+}
+
+// Everything the tile kernels need to turn a separation into a table index and a histogram bin without divisions
+// (kernels_pair.cuh).  Returns false when the table is too long for the bit trick (never for int lengths below 2^30).
+bool make_index_params(const pimcb_ctx* c, double dSep, bool want_hist, TileIndexParams* ix) {
+    int ebits = 24;
+    while ((1ll << (ebits - 1)) <= static_cast<long long>(c->tab_len) + 2) ++ebits;
+    if (ebits > 31) return false;
+    ix->len = c->tab_len; ix->dr = c->dr; ix->inv_dr = 1.0 / c->dr;
+    ix->dSep = dSep; ix->want_hist = want_hist ? 1 : 0;
+    ix->magic = std::ldexp(1.5, ebits); ix->fb = 52 - ebits;
+    // bin = (k * round(2^S dr/dSep)) >> S with the largest S <= 56 that keeps k * mul below 2^64
+    ix->hmul_lo = ix->hmul_hi = 0; ix->hshift = 32; ix->hslop = 0; ix->hspan = 0;      // hspan = 0: never safe (exact path)
+    if (want_hist && dSep > 0.0) {
+        const double cbin = c->dr / dSep;
+        int S = 56;
+        while (S >= 32 && std::ldexp(cbin, S) * std::ldexp(1.0, ebits - 1) >= 1.8e19) --S;
+        const double width = std::ldexp(cbin, 32) * 1.01 + 4096.0;      // width of the interval k pins r/dSep to + rounding slop, in 2^-32 bins
+        if (S >= 32 && width < 1.0e9) {
+            const unsigned long long mul = static_cast<unsigned long long>(std::llround(std::ldexp(cbin, S)));
+            ix->hmul_lo = static_cast<unsigned>(mul & 0xffffffffull);
+            ix->hmul_hi = static_cast<unsigned>(mul >> 32);
+            ix->hshift = S;
+            ix->hslop = 4096u;
+            ix->hspan = static_cast<unsigned>(4294967296.0 - width - 4096.0);
+        }
+    }
+    const CodecSteps st = codec_steps(c->dr);
+    for (int j = 0; j < 4; ++j) { ix->x[j] = st.x[j]; ix->xh[j] = st.xh[j]; ix->x3[j] = st.x3[j]; }
+    return true;
 }
 
 }  // namespace
@@ -1405,33 +1437,42 @@ int pimcb_set_pair_table(pimcb_ctx* c, const double* V, const double* dVdr, int 
     if (!c || !V || len < 1 || !(dr > 0.0)) return fail(PIMCB_EINVAL, "bad pair-table arguments");
     CU(cudaSetDevice(c->device));
     int rc;
-    if ((rc = c->d_V.ensure(sizeof(double) * len))) return rc;
-    CU(cudaMemcpyAsync(c->d_V.p, V, sizeof(double) * len, cudaMemcpyHostToDevice, c->stream));
-    c->have_dV = dVdr != nullptr;
-    if (dVdr) {
-        if ((rc = c->d_dV.ensure(sizeof(double) * len))) return rc;
-        CU(cudaMemcpyAsync(c->d_dV.p, dVdr, sizeof(double) * len, cudaMemcpyHostToDevice, c->stream));
-    }
-    CU(cudaStreamSynchronize(c->stream));
     c->tab_len = len;
     c->dr = dr;
     c->extV[0] = extV ? extV[0] : 0.0; c->extV[1] = extV ? extV[1] : 0.0;
     c->extdV[0] = extdVdr ? extdVdr[0] : 0.0; c->extdV[1] = extdVdr ? extdVdr[1] : 0.0;
-    // one-sector-per-pair form of (V, dV/dr): packed on the host, verified bit for bit on the device (table_codec.h)
-    c->vd_ok = c->dd_ok = false;
-    c->have_d2V = false;
+    // Device tables have len + 1 entries: entry 0 holds ext[0] and entry `len` holds ext[1].  TabulatedPotential::direct
+    // (include/potential.h:249-260) returns ext[0] for k <= 0 and ext[1] for k >= len and never reads entry 0, so
+    // table[min(max(k, 0), len)] is the same function without a branch; entries 1 .. len-1 are the caller's, verbatim.
+    std::vector<double> hV(V, V + len);
+    hV.push_back(c->extV[1]);
+    hV[0] = c->extV[0];
+    const size_t bytes = sizeof(double) * hV.size();
+    if ((rc = c->d_V.ensure(bytes))) return rc;
+    CU(cudaMemcpyAsync(c->d_V.p, hV.data(), bytes, cudaMemcpyHostToDevice, c->stream));
+    c->have_dV = dVdr != nullptr;
     c->h_dV.clear();
     if (dVdr) {
         c->h_dV.assign(dVdr, dVdr + len);
-        if ((rc = build_packed_table(c, V, dVdr, len, dr, c->d_V.as<double>(), c->d_dV.as<double>(), c->d_VD, &c->vd_ok, &c->vd_raw))) return rc;
+        c->h_dV.push_back(c->extdV[1]);
+        c->h_dV[0] = c->extdV[0];
+        if ((rc = c->d_dV.ensure(bytes))) return rc;
+        CU(cudaMemcpyAsync(c->d_dV.p, c->h_dV.data(), bytes, cudaMemcpyHostToDevice, c->stream));
     }
+    CU(cudaStreamSynchronize(c->stream));
+    // one-sector-per-pair form of (V, dV/dr): packed on the host, verified bit for bit on the device (table_codec.h)
+    c->vd_ok = c->dd_ok = false;
+    c->have_d2V = false;
+    if (dVdr && (rc = build_packed_table(c, hV.data(), c->h_dV.data(), len + 1, dr, c->d_V.as<double>(), c->d_dV.as<double>(), c->d_VD,
+                                         &c->vd_ok, &c->vd_raw)))
+        return rc;
     return 0;
 }
 
 int pimcb_table_codec_info(const pimcb_ctx* c, long* info) {
     if (!c || !info) return fail(PIMCB_EINVAL, "null argument");
     info[0] = c->vd_ok ? 1 : 0; info[1] = c->vd_raw; info[2] = c->dd_ok ? 1 : 0; info[3] = c->dd_raw;
-    info[4] = (c->tab_len + 3) / 4;
+    info[4] = (c->tab_len + 1 + 3) / 4;
     return 0;
 }
 
@@ -1529,20 +1570,23 @@ int pimcb_pair_sums(pimcb_ctx* c, double* vint, double* f2, int* sephist, double
         const int spc = std::max(1, kPairWarps / G);
         const size_t smem_tile = sizeof(double) * (static_cast<size_t>(spc) * nd * 32 * G * (2 + kPairRound) + spc * G + 1) +
                                  sizeof(int) * spc * kNPCFSEP;
-        int ebits = 24;
-        while ((1ll << (ebits - 1)) <= static_cast<long long>(c->tab_len) + 2) ++ebits;
         const size_t smem_sym = sizeof(double) * 2 * nd * s->Npad;
-        if (tile_on && smem_tile <= 200 * 1024 && ebits <= 31) {
-            PairTileParams tp{c->d_V.as<double>(), c->d_dV.as<double>(), c->tab_len, c->dr, 1.0 / c->dr, {c->extV[0], c->extV[1]},
-                              {c->extdV[0], c->extdV[1]}, pp.dSep, 1.0 / pp.dSep, pp.want_hist, f2_parity, s->M, pp.gext,
-                              std::ldexp(1.5, ebits), 52 - ebits, G, spc, c->vd_ok ? c->d_VD.as<TableSector>() : nullptr};
+        TileIndexParams ixp{};
+        if (tile_on && smem_tile <= 200 * 1024 && make_index_params(c, pp.dSep, pp.want_hist != 0, &ixp)) {
+            // Packed (V, dV/dr) sectors when the call has force slices (one sector request per pair instead of two reads
+            // from 106 MB of tables); V-only calls read the verbatim V table, which fits L2 on its own (53 MB for C2) and
+            // needs no decoding.  PIMCB_PAIR_PACKED=0 / 1 forces one or the other (A/B).
+            static const int packed_env = std::getenv("PIMCB_PAIR_PACKED") ? std::atoi(std::getenv("PIMCB_PAIR_PACKED")) : -1;
+            const bool use_packed = c->vd_ok && (packed_env < 0 ? f2 != nullptr : packed_env != 0);
+            PairTileParams tp{c->d_V.as<double>(), c->d_dV.as<double>(), ixp, f2_parity, s->M, pp.gext, G, spc,
+                              use_packed ? c->d_VD.as<TableSector>() : nullptr};
             const int units = (nsl + spc - 1) / spc;
 #define LAUNCH_PTILE2(ND, CODEC)                                                                                   \
             rc = set_smem(pair_tile_kernel<ND, CODEC>, smem_tile); if (rc) return rc;                               \
             pair_tile_kernel<ND, CODEC><<<units, 32 * kPairWarps, smem_tile, c->stream>>>(s->pos.as<double>(), nsl, s->N, s->Npad, c->box, tp, \
                                                                                   c->d_vint.as<double>(), f2 ? c->d_f2.as<double>() : nullptr, \
                                                                                   c->d_hist.as<int>())
-#define LAUNCH_PTILE(ND) if (c->vd_ok) { LAUNCH_PTILE2(ND, true); } else { LAUNCH_PTILE2(ND, false); }
+#define LAUNCH_PTILE(ND) if (use_packed) { LAUNCH_PTILE2(ND, true); } else { LAUNCH_PTILE2(ND, false); }
             if (nd == 1) { LAUNCH_PTILE(1) } else if (nd == 2) { LAUNCH_PTILE(2) } else { LAUNCH_PTILE(3) }
 #undef LAUNCH_PTILE
 #undef LAUNCH_PTILE2
@@ -1639,15 +1683,19 @@ int pimcb_set_pair_table_d2(pimcb_ctx* c, const double* d2Vdr2, int len, const d
     if (len != c->tab_len) return fail(PIMCB_EINVAL, "d2V/dr2 table length %d differs from the V table length %d", len, c->tab_len);
     CU(cudaSetDevice(c->device));
     int rc;
-    if ((rc = c->d_d2V.ensure(sizeof(double) * len))) return rc;
-    CU(cudaMemcpyAsync(c->d_d2V.p, d2Vdr2, sizeof(double) * len, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
     c->extd2V[0] = extd2Vdr2 ? extd2Vdr2[0] : 0.0;
     c->extd2V[1] = extd2Vdr2 ? extd2Vdr2[1] : 0.0;
+    std::vector<double> h2(d2Vdr2, d2Vdr2 + len);      // len + 1 entries like the other tables (entry 0 / len = the extremal values)
+    h2.push_back(c->extd2V[1]);
+    h2[0] = c->extd2V[0];
+    if ((rc = c->d_d2V.ensure(sizeof(double) * h2.size()))) return rc;
+    CU(cudaMemcpyAsync(c->d_d2V.p, h2.data(), sizeof(double) * h2.size(), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     c->have_d2V = true;
     c->dd_ok = false;
-    if (static_cast<int>(c->h_dV.size()) == len &&
-        (rc = build_packed_table(c, c->h_dV.data(), d2Vdr2, len, c->dr, c->d_dV.as<double>(), c->d_d2V.as<double>(), c->d_DD, &c->dd_ok, &c->dd_raw)))
+    if (static_cast<int>(c->h_dV.size()) == len + 1 &&
+        (rc = build_packed_table(c, c->h_dV.data(), h2.data(), len + 1, c->dr, c->d_dV.as<double>(), c->d_d2V.as<double>(), c->d_DD,
+                                 &c->dd_ok, &c->dd_raw)))
         return rc;
     return 0;
 }
@@ -1691,17 +1739,15 @@ int pimcb_virial_sums(pimcb_ctx* c, const double* delta_aos, int t2_parity, doub
         static const bool vtile_on = !(std::getenv("PIMCB_VIRIAL_TILE") && std::atoi(std::getenv("PIMCB_VIRIAL_TILE")) == 0);
         const int G = (s->N + 31) / 32;
         const int spc = std::max(1, kPairWarps / G);
-        int ebits = 24;
-        while ((1ll << (ebits - 1)) <= static_cast<long long>(c->tab_len) + 2) ++ebits;
         auto vtile_smem = [&](int R) {
             return sizeof(double) * (static_cast<size_t>(spc) * 32 * G * (nd + nc * (1 + R)) + static_cast<size_t>(spc) * 4 * kPairWarps);
         };
         int rounds = kPairRound;
         while (rounds > 1 && vtile_smem(rounds) > 100 * 1024) --rounds;      // two CTAs per SM when it fits
-        if (!ext && vtile_on && vtile_smem(rounds) <= 200 * 1024 && ebits <= 31) {
+        TileIndexParams ixp{};
+        if (!ext && vtile_on && vtile_smem(rounds) <= 200 * 1024 && make_index_params(c, 1.0, false, &ixp)) {
             const bool packed = c->dd_ok && (t2_parity == -2 || c->have_d2V);
-            VirialTileParams tp{c->d_dV.as<double>(), c->d_d2V.as<double>(), c->tab_len, c->dr, 1.0 / c->dr, {c->extdV[0], c->extdV[1]},
-                                {c->extd2V[0], c->extd2V[1]}, t2_parity, s->M, std::ldexp(1.5, ebits), 52 - ebits, G, spc, rounds,
+            VirialTileParams tp{c->d_dV.as<double>(), c->d_d2V.as<double>(), ixp, t2_parity, s->M, G, spc, rounds,
                                 packed ? c->d_DD.as<TableSector>() : nullptr};
             const size_t smem_t = vtile_smem(rounds);
             const int units = (nsl + spc - 1) / spc;

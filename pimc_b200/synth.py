@@ -103,7 +103,7 @@ def float_q(nq: int, ndim: int, seed: int = 7, qmax: float = 2.5) -> np.ndarray:
     return q.astype(np.float32).astype(np.float64)
 
 
-def aziz_table_numpy(max_sep: float, year: int = 1979):
+def aziz_table_numpy(max_sep: float, year: int = 1979, second: bool = False):
     """Aziz HFDHE2 lookup tables (V, dV/dr, dr) with the reference's construction (include/potential.h:163-183,
     src/potential.cpp:1741-1909): dr = 1e-6 rm, tableLength = int(maxSep/dr), abscissa by repeated addition.
     Vectorised numpy for benchmarks; values agree with the C++ builders to the last few ulp of exp()."""
@@ -136,4 +136,19 @@ def aziz_table_numpy(max_sep: float, year: int = 1979):
     zero = x < 1.0e-7
     V[zero] = 0.0
     dV[zero] = 0.0
-    return V, dV, dr
+    if not second:
+        return V, dV, dr
+    # d2V/dr2 (src/potential.cpp:1881-1909; damping function derivatives include/potential.h:958-975)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        ab = alpha - 2.0 * beta * x
+        S1 = A * (2.0 * beta + ab * ab) * np.exp(-alpha * x + beta * x * x)
+        u = D * ix - 1.0
+        d2F = np.where(x < D, 2.0 * D * ix ** 3 * (2.0 * D ** 3 * ix ** 3 - 4.0 * D * D * ix2 - D * ix + 2.0) * np.exp(-u * u), 0.0)
+        ix12 = ix10 * ix2
+        S2 = -(42.0 * C6 * ix8 + 72.0 * C8 * ix10 + 110.0 * C10 * ix12) * F
+        S3 = 2.0 * (6.0 * C6 * ix6 * ix + 8.0 * C8 * ix8 * ix + 10.0 * C10 * ix10 * ix) * dF
+        S4 = -disp * d2F
+        d2V = (eps / (rm * rm)) * (S1 + S2 + S3 + S4)
+    d2V = np.where(core, (eps / rm) * S1, d2V)
+    d2V[zero] = 0.0
+    return V, dV, d2V, dr

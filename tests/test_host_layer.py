@@ -110,6 +110,20 @@ def state_report(host, ndim, fname, N, rho):
     return d
 
 
+@pytest.mark.parametrize("year", [1979, 1995])
+def test_packed_lookup_tables_are_lossless(host_bins, year):
+    """pimc_b200/csrc/table_codec.h on the real Aziz tables (CPU, the decoder the device compiles): four entries of (V, dV/dr)
+    resp. (dV/dr, d2V/dr2) per 32-byte sector reproduce EVERY table entry bit for bit; under 1 % of the sectors stay verbatim
+    (zero crossings, core, damping switch); tables that are not (function, derivative) pairs come out verbatim, never wrong."""
+    out = subprocess.run([os.path.join(host_bins, "pimcb_codec_selftest3d"), "64", str(year)], check=True, capture_output=True, text=True).stdout
+    d = dict(line.split("=", 1) for line in out.splitlines())
+    for p in ("pass0", "pass1"):
+        assert int(d[p + "_mismatches"]) == 0
+        assert int(d[p + "_raw"]) < 0.01 * int(d[p + "_sectors"])
+        assert int(d[p + "_maxres"]) <= 128
+    assert int(d["unrelated_mismatches"]) == 0 and int(d["unrelated_raw"]) >= 1000
+
+
 @pytest.mark.parametrize("ndim", [2, 3])
 def test_state_file_parser_matches_format_restatement(host_bins, tmp_path, ndim):
     """The C++ reader of the reference's text state files against the Python restatement of the writer/loader

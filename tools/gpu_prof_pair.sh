@@ -7,4 +7,5 @@ ncu --set full --clock-control none --import-source on -k regex:"pair_tile|viria
 tail -5 $OUT/${TAG}_ncu.log
 ncu -i $OUT/${TAG}_pair_tile.ncu-rep --page raw --csv > $OUT/${TAG}_pair_tile_raw.csv 2>/dev/null
 ncu -i $OUT/${TAG}_pair_tile.ncu-rep --page source --csv > $OUT/${TAG}_pair_tile_source.csv 2>/dev/null
+rm -f $OUT/${TAG}_pair_tile.ncu-rep      # gpurun brings back at most 64 MiB: the CSV pages carry what the summaries need
 ls -la $OUT | tail -5

@@ -19,13 +19,12 @@ pa = api.PinnedArray((B,) + uniq.shape[1:])
 for b in range(B):
     pa.array[b] = uniq[b % len(uniq)]
 max_sep = math.sqrt(sum((L / 2.0) ** 2 for L in s.side))
-V, dV, dr = synth.aziz_table_numpy(max_sep)
-d2V = np.gradient(dV, dr)
+V, dV, d2V, dr = synth.aziz_table_numpy(max_sep, second=True)
 dSep = 0.5 * math.sqrt(3.0) * s.side[2] / 50.0
 with api.Context(0, s.ndim) as ctx:
     ctx.set_box(s.side)
     ctx.stage(pa.array, s.N)
-    for sub in (1, 2, 16):
+    for sub in [int(x) for x in os.environ.get("SUBS", "1,2,16").split(",")]:
         ctx.set_pair_table(np.ascontiguousarray(V[::sub]), np.ascontiguousarray(dV[::sub]), dr * sub)
         ctx.set_pair_table_d2(np.ascontiguousarray(d2V[::sub]))
         out = {}

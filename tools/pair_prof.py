@@ -17,8 +17,7 @@ pa = api.PinnedArray((B,) + uniq.shape[1:])
 for b in range(B):
     pa.array[b] = uniq[b % len(uniq)]
 max_sep = math.sqrt(sum((L / 2.0) ** 2 for L in s.side))
-V, dV, dr = synth.aziz_table_numpy(max_sep)
-d2V = np.gradient(dV, dr)
+V, dV, d2V, dr = synth.aziz_table_numpy(max_sep, second=True)
 dSep = 0.5 * math.sqrt(3.0) * s.side[2] / 50.0
 with api.Context(0, s.ndim) as ctx:
     ctx.set_box(s.side)
