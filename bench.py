@@ -784,22 +784,29 @@ def pair_legs(args, ctx, shape, pinned, use_slots, B):
     ctx.set_profiling(False)
     p_s = pms * 1e-3 / max(1, pn)
     pairs = shape.N * (shape.N - 1) // 2               # pairs per slice
-    # gsf action: even slices read V once per pair, odd slices V and dV/dr once per pair (every pair is visited once)
-    gathers = B * ((shape.M - shape.M // 2) * pairs + (shape.M // 2) * 2 * pairs)
-    gather_peak = 289.0e9                              # profiles/r02a_gather_peak.txt: 32-byte sectors / s out of L2, footprint <= 53 MB
+    codec = ctx.table_codec_info()
     tile = os.environ.get("PIMCB_PAIR_TILE", "1") != "0"
+    packed = tile and codec["vd_packed"]
+    # table reads: every pair is visited once.  Packed tables (table_codec.h): ONE 32-byte sector per pair serves V and
+    # dV/dr; verbatim tables: V on every slice + dV/dr on the odd slices of the gsf action
+    reads = B * shape.M * pairs if packed else B * ((shape.M - shape.M // 2) * pairs + (shape.M // 2) * 2 * pairs)
+    gather_peak = 289.0e9                              # profiles/r02a_gather_peak.txt: 32-byte sectors / s out of L2, footprint <= 53 MB
     pair = {"metric": "pair-potential action sums/s (Vint[M] + gradVSquared[odd slices] + sepHist[M][50] per configuration)",
-            "kernel": "pair_tile_kernel (32 x 32 tiles, every pair once)" if tile else "pair_sym_kernel (ring, every pair once)",
+            "kernel": ("pair_tile_kernel (32 x 32 tiles, every pair once, division-free exact index" + (", packed (V, dV/dr) sectors)" if packed else ", verbatim tables)"))
+                      if tile else "pair_sym_kernel (ring, every pair once)",
             "value": B / p_s, "unit": "configurations/s", "avg_launch_ms": p_s * 1e3, "launches_timed": pn,
-            "table_entries": len(Vt), "table_mb": 2 * 8 * len(Vt) / 1e6,
+            "table_entries": len(Vt), "table_mb_verbatim": 2 * 8 * len(Vt) / 1e6, "table_mb_read": (32 * codec["sectors"] / 1e6) if packed else 2 * 8 * len(Vt) / 1e6,
+            "packed_tables": codec,
             "pairs_per_launch": B * shape.M * pairs, "pair_rate_g_per_s": B * shape.M * pairs / p_s / 1e9,
-            "gathers_per_launch": gathers, "gather_rate_g_per_s": gathers / p_s / 1e9,
-            "roofline": {"bound": "L2 sector rate of random 8-byte table reads", "achieved": gathers / p_s / 1e9, "peak": gather_peak / 1e9,
-                         "unit": "G reads/s", "frac": gathers / p_s / gather_peak,
+            "table_reads_per_launch": reads, "table_read_rate_g_per_s": reads / p_s / 1e9,
+            "roofline": {"bound": "L2 sector rate of random table reads (one 32-byte sector per read)", "achieved": reads / p_s / 1e9,
+                         "peak": gather_peak / 1e9, "unit": "G reads/s", "frac": reads / p_s / gather_peak,
                          "peak_source": "tools/micro/gather_peak.cu on this pool's B200 (profiles/r02a_gather_peak.txt): 289 G reads/s for "
-                                        "footprints <= 53 MB, 140 G/s at 106 MB (V + dV/dr tables of C2), 73 G/s from DRAM",
-                         "hbm_algorithmic": {"bytes": 8 * gathers + B * 8 * shape.ndim * shape.N * shape.M,
-                                             "achieved_gbs": (8 * gathers + B * 8 * shape.ndim * shape.N * shape.M) / p_s / 1e9}}}
+                                        "footprints <= 53 MB, 140 G/s at 106 MB (the verbatim V + dV/dr tables of C2), 73 G/s from DRAM",
+                         "note": "ncu (profiles/r02j_*): L2 hit rate 98 %, 0.12 GB DRAM reads per launch, issue slots 61 % busy -- the kernel is "
+                                 "bound by instruction issue / dependent FP64 latency (143 warp-instructions per pair), not by the reads",
+                         "hbm_algorithmic": {"bytes": 32 * reads + B * 8 * shape.ndim * shape.N * shape.M,
+                                             "achieved_gbs": (32 * reads + B * 8 * shape.ndim * shape.N * shape.M) / p_s / 1e9}}}
     ctx.set_pair_table_d2(d2Vt)
     ctx.select_slot(0)
     delta = 0.01 * pinned[0].array                 # any per-bead vectors in the beads' AoS shape
@@ -812,10 +819,12 @@ def pair_legs(args, ctx, shape, pinned, use_slots, B):
     vms, vn = ctx.kernel_times(reset=True)["virial"]
     ctx.set_profiling(False)
     v_s = vms * 1e-3 / max(1, vn)
-    vg = B * pairs * (shape.M + shape.M // 2)      # dV/dr on every slice, d2V/dr2 on the odd ones, every pair once
+    vpacked = os.environ.get("PIMCB_VIRIAL_TILE", "1") != "0" and ctx.table_codec_info()["dd_packed"]
+    vg = B * pairs * (shape.M if vpacked else shape.M + shape.M // 2)      # one sector per pair, or dV/dr everywhere + d2V/dr2 on the odd slices
     pair["virial_sums"] = {"metric": "virial slice sums/s (4 sums per slice; gsf action, window deltas from the host)",
                            "value": B / v_s, "unit": "configurations/s", "avg_launch_ms": v_s * 1e3, "launches_timed": vn,
-                           "gathers_per_launch": vg, "gather_rate_g_per_s": vg / v_s / 1e9,
+                           "kernel": "virial_tile_kernel" + (" (packed (dV/dr, d2V/dr2) sectors)" if vpacked else " (verbatim tables)"),
+                           "table_reads_per_launch": vg, "table_read_rate_g_per_s": vg / v_s / 1e9,
                            "roofline": {"bound": "L2 sector rate of random 8-byte table reads", "achieved": vg / v_s / 1e9,
                                         "peak": gather_peak / 1e9, "unit": "G reads/s", "frac": vg / v_s / gather_peak}}
     return pair

@@ -81,7 +81,9 @@ def kernel_detail(rep):
 
 def main():
     tag = sys.argv[1]
-    out = os.path.join(ROOT, "profiles")
+    # optional second argument: where to write (on the GPU box only gpurun_out/ travels back, so the summaries are written
+    # there next to the captures, the multi-megabyte .ncu-rep files are deleted, and the summaries are copied to profiles/ here)
+    out = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "profiles")
     os.makedirs(out, exist_ok=True)
     md = [f"# ncu summary `{tag}`", "",
           "Source: `tools/gpu_round.sh` on one B200 (`ncu --clock-control none`); numbers printed under ncu are never bench values.", ""]
@@ -117,6 +119,12 @@ def main():
         # kernels captured in this visit replace their entries; entries of kernels captured earlier stay
         path = os.path.join(out, "traffic.json")
         merged = {}
+        seed = os.path.join(ROOT, "profiles", "traffic.json")
+        if not os.path.exists(path) and os.path.exists(seed):
+            try:
+                merged = json.load(open(seed))
+            except ValueError:
+                merged = {}
         if os.path.exists(path):
             try:
                 merged = json.load(open(path))
