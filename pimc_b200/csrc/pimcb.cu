@@ -422,6 +422,11 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
         const int wmax = c->sm_count * std::max(1, occ) * kMmaWarps;          /* resident warps of a full grid */   \
         int split = 1;                                                         /* warps sharing one slice */         \
         while (split < 8 && 2 * split <= nchunk && nsl * split < wmax) split *= 2;                                   \
+        /* few waves of work items: a ragged last wave costs every warp a whole item (C4, 8 walkers per GPU: 2560 slices \
+           on 1776 resident warps = 1.44 waves, 72 % busy); split further while that buys >= 10 % */                     \
+        { auto eff = [&](int sp) { const double w = static_cast<double>(nsl) * sp / wmax; return w / std::ceil(w); };  \
+          while (split < 8 && 2 * split <= nchunk && static_cast<double>(nsl) * split / wmax < 4.0 &&                    \
+                 eff(2 * split) > eff(split) + 0.10) split *= 2; }                                                       \
         if (const char* e = std::getenv("PIMCB_RHO_SPLIT")) split = std::max(1, std::min(nchunk, std::atoi(e)));   \
         if (split > 1) {                                                                                           \
             rc = c->d_partial.ensure(sizeof(double) * static_cast<size_t>(nsl) * split * (MT * NT * 64)); if (rc) return rc; \
