@@ -59,6 +59,7 @@ struct PairTileParams {
     int G;                 // particle groups of 32
     int spc;               // slices per CTA work unit (> 1 when a slice has fewer groups than the CTA has warps)
     const TableSector* VD; // (V, dV/dr) packed four entries per 32-byte sector (table_codec.h), or nullptr: verbatim tables only
+    const struct ExactParams* exact;   // constants of the exact path, in device memory (see pair_exact)
 };
 
 // One whole 32-byte sector per lane in one request (LDG.E.256).
@@ -126,16 +127,20 @@ __device__ __forceinline__ void pair_fast(const double (&xi)[ND], const double* 
 }
 
 // The reference's own operation sequence (putInBC -> dot -> sqrt -> r/dr -> int(); r/dSep -> int()), bit for bit.
-// Out of line and returning BY VALUE: a call that took the index arrays by reference would pin them to local memory and
-// put a store / load pair per pair into the fast path (it did: 2.03 ms instead of 1.7 ms for the V-only pass).
+// Out of line, returning BY VALUE, and taking its constants from a small block in device memory rather than as arguments:
+// a call that took the index arrays by reference pinned them to local memory and put a store / load pair per pair into the
+// fast path (2.03 ms instead of 1.7 ms for the V-only pass), and 20 registers of by-value arguments per call site cost the
+// fast path their set-up moves.
+struct ExactParams { BoxDev box; double dr, dSep; int want_hist; };
+
 template <int ND>
-__device__ __noinline__ int2 pair_exact(const double* __restrict__ xsl, int NP, int i, int j, BoxDev box, double dr, double dSep,
-                                        int want_hist) {
+__device__ __noinline__ int2 pair_exact(const ExactParams* __restrict__ ep, const double* __restrict__ xsl, int NP, int i, int j) {
     double sx[ND];
+    const BoxDev box = ep->box;
     const double rx = minimage_norm<ND>(xsl, NP, i, j, box, sx);
     int2 out;
-    out.x = __double2int_rz(__ddiv_rn(rx, dr));
-    out.y = want_hist ? __double2int_rz(__ddiv_rn(rx, dSep)) : 0;
+    out.x = __double2int_rz(__ddiv_rn(rx, ep->dr));
+    out.y = ep->want_hist ? __double2int_rz(__ddiv_rn(rx, ep->dSep)) : 0;
     return out;
 }
 
@@ -204,7 +209,7 @@ __device__ __forceinline__ void pair_tile(const double* __restrict__ xsl, int NP
 #pragma unroll
             for (int u = 0; u < U; ++u)
                 if (unsafe[u]) {
-                    const int2 e = pair_exact<ND>(xsl, NP, i, 32 * b + ((lane + s + u) & 31), box, ix.dr, ix.dSep, ix.want_hist);
+                    const int2 e = pair_exact<ND>(pp.exact, xsl, NP, i, 32 * b + ((lane + s + u) & 31));
                     kidx[u] = e.x;
                     nR[u] = e.y;
                 }
@@ -385,6 +390,7 @@ struct VirialTileParams {
     int t2_parity; int M;
     int G; int spc; int rounds;                  // rounds = group offsets per round (partner-side slots that fit)
     const TableSector* DD;                       // (dV/dr, d2V/dr2) packed four entries per sector, or nullptr
+    const struct ExactParams* exact;             // constants of the exact path, in device memory (want_hist = 0)
 };
 
 #ifndef PIMCB_VTILE_U
@@ -421,7 +427,7 @@ __device__ __forceinline__ void virial_tile(const double* __restrict__ xsl, int 
         if (any_unsafe) {
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (unsafe[u]) kidx[u] = pair_exact<ND>(xsl, NP, i, 32 * b + ((lane + s + u) & 31), box, ix.dr, ix.dSep, 0).x;
+                if (unsafe[u]) kidx[u] = pair_exact<ND>(vp.exact, xsl, NP, i, 32 * b + ((lane + s + u) & 31)).x;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {

@@ -45,6 +45,29 @@ def test_single_rank_communicator(orc):
     np.testing.assert_allclose(ssf1, ref, rtol=1e-10)
 
 
+@pytest.mark.gpu
+def test_idle_rank_joins_the_reduce_with_a_zero_bin():
+    """pimcb_init_bins: a rank whose share of a walker batch is empty (nothing measured) still takes part in
+    pimcb_reduce_bins -- with zeros -- instead of failing and leaving its peers inside the collective."""
+    from pimc_b200 import api
+    s = synth.Shape("c0", 3, 20, 12, 2.0, 0.02198, 0)
+    q = synth.commensurate_q(5, s.side)
+    with api.Context(0, 3) as ctx:
+        ctx.set_box(s.side)
+        ctx.set_qvecs(q)
+        ctx.comm_init(1, 0, api.Context.comm_unique_id())
+        with pytest.raises(api.PimcbError):
+            ctx.reduce_bins(0)                                   # no bin laid out yet
+        ctx.init_bins(s.M)
+        assert ctx.reduce_bins(0) == 0
+        ssf, isf, n = ctx.read_bins()
+        assert n == 0 and not ssf.any() and not isf.any() and isf.shape == (len(q), s.M)
+        ctx.stage(synth.gen_batch(s, 3, first=5), s.N).measure()  # the same layout keeps accumulating afterwards
+        ctx.init_bins(s.M)                                       # a second call must not clear what is there
+        assert ctx.reduce_bins(0) == 3
+        ctx.comm_destroy()
+
+
 def _rank(rank, world, uid, mode, ret):
     sys.path.insert(0, ROOT)
     from pimc_b200 import api, multi
