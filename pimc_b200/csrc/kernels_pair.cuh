@@ -19,9 +19,10 @@
 //     int(r/dSep) only need r to a few ulp unless r/dr lies within 2^-20 of an integer: r comes from MUFU.RSQ64H + two
 //     Goldschmidt steps (which also yield 1/r for the force), the quotient is a multiplication by the rounded
 //     reciprocal, and floor() and the fractional part are read from the bits of t + 1.5 * 2^e.  The rare unsafe cases
-//     (|frac - integer| < 2^-20, 2 in 10^6 pairs) and everything outside the fast path's validity re-run the
-//     reference's exact operation sequence (minimage_norm / __ddiv_rn), so k and the histogram stay BIT-IDENTICAL to
-//     the CPU (include/potential.h:249-260, src/action.cpp:216-224) -- the tests hold sepHist to array_equal.
+//     (|frac - integer| < 2^-20, 2 in 10^6 pairs) and everything outside the fast path's validity are left out of the
+//     fast loop and redone after it with the reference's exact operation sequence (minimage_norm / __ddiv_rn; see
+//     pair_tile_redo), so k and the histogram stay BIT-IDENTICAL to the CPU (include/potential.h:249-260,
+//     src/action.cpp:216-224) -- the tests hold sepHist to array_equal.
 //   * The histogram bin from the table index: k = int(r/dr) pins r/dSep to an interval of width dr/dSep = 8e-6 bins, so
 //     int(r/dSep) = (k * round(2^S dr/dSep)) >> S (one integer multiply-add pair) unless that product lies within the
 //     interval's width of a bin edge (3 in 10^5 pairs), which again takes the exact path.
@@ -59,7 +60,6 @@ struct PairTileParams {
     int G;                 // particle groups of 32
     int spc;               // slices per CTA work unit (> 1 when a slice has fewer groups than the CTA has warps)
     const TableSector* VD; // (V, dV/dr) packed four entries per 32-byte sector (table_codec.h), or nullptr: verbatim tables only
-    const struct ExactParams* exact;   // constants of the exact path, in device memory (see pair_exact)
 };
 
 // One whole 32-byte sector per lane in one request (LDG.E.256).
@@ -126,24 +126,6 @@ __device__ __forceinline__ void pair_fast(const double (&xi)[ND], const double* 
     }
 }
 
-// The reference's own operation sequence (putInBC -> dot -> sqrt -> r/dr -> int(); r/dSep -> int()), bit for bit.
-// Out of line, returning BY VALUE, and taking its constants from a small block in device memory rather than as arguments:
-// a call that took the index arrays by reference pinned them to local memory and put a store / load pair per pair into the
-// fast path (2.03 ms instead of 1.7 ms for the V-only pass), and 20 registers of by-value arguments per call site cost the
-// fast path their set-up moves.
-struct ExactParams { BoxDev box; double dr, dSep; int want_hist; };
-
-template <int ND>
-__device__ __noinline__ int2 pair_exact(const ExactParams* __restrict__ ep, const double* __restrict__ xsl, int NP, int i, int j) {
-    double sx[ND];
-    const BoxDev box = ep->box;
-    const double rx = minimage_norm<ND>(xsl, NP, i, j, box, sx);
-    int2 out;
-    out.x = __double2int_rz(__ddiv_rn(rx, ep->dr));
-    out.y = ep->want_hist ? __double2int_rz(__ddiv_rn(rx, ep->dSep)) : 0;
-    return out;
-}
-
 // Table entries F[k] (and G[k] when WANT_G) with k clamped to [0, len]: one packed sector (CODEC) or the verbatim tables.
 template <bool WANT_G, bool CODEC>
 __device__ __forceinline__ void table_issue(const TableSector* __restrict__ packed, const double* __restrict__ F, const double* __restrict__ G,
@@ -173,9 +155,57 @@ __device__ __forceinline__ void table_finish(const TileIndexParams& ix, const do
 // (positions xb[d * NP + m]), steps [s_lo, s_hi), partner m = (lane + s) & 31.  FORCE: own-side force into Fi, partner-side
 // force into Gv (it ends up in the lane that holds the partner: particle 32 b + lane).  CHECK = false: every pair of the
 // tile exists (both groups full, not the diagonal tile) and no validity logic is compiled.
+//
+// Two passes.  The loop runs the fast path only; a pair whose index or bin is not provably the reference's ("unsafe":
+// 1.5 in 10^5 pairs) contributes NOTHING there and sets the bit of its step in the lane's `redo` mask.  After the loop --
+// in 1.5 % of the tiles -- pair_tile_redo walks the set bits in a fixed order (lane ascending, step ascending), all lanes
+// recomputing the pair with the reference's exact operation sequence so that both the owning lane and the partner's lane
+// can add their share: no call, no exact-path registers and no reconvergence bookkeeping inside the loop (the first cut
+// called the exact path from inside the loop: +45 instructions per two pairs of call plumbing on the FAST path).
 #ifndef PIMCB_PTILE_U
 #define PIMCB_PTILE_U 2
 #endif
+template <int ND, bool FORCE>
+__device__ __forceinline__ void pair_tile_redo(unsigned redo, const double* __restrict__ xsl, int NP, int ibase, int b, int lane,
+                                               const BoxDev& box, const PairTileParams& pp, int* __restrict__ shist_sl, double& vsum,
+                                               double (&Fi)[ND], double (&Gv)[ND]) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const TileIndexParams& ix = pp.ix;
+    unsigned lanes = __ballot_sync(FULL, redo != 0u);
+    while (lanes) {
+        const int l = __ffs(lanes) - 1;
+        lanes &= lanes - 1;
+        unsigned steps = __shfl_sync(FULL, redo, l);
+        while (steps) {
+            const int ss = __ffs(steps) - 1;
+            steps &= steps - 1;
+            const int m = (l + ss) & 31;
+            // the reference's own operation sequence (putInBC -> dot -> sqrt -> r/dr -> int(); r/dSep -> int()), bit for bit
+            double sx[ND];
+            const double rx = minimage_norm<ND>(xsl, NP, ibase + l, 32 * b + m, box, sx);
+            const int k = __double2int_rz(__ddiv_rn(rx, ix.dr));
+            const int kc = max(min(k, ix.len), 0);
+            const double v = __ldg(pp.V + kc);
+            if (lane == l) {
+                vsum += v;
+                if (ix.want_hist) {
+                    const int nR = __double2int_rz(__ddiv_rn(rx, ix.dSep));
+                    if (static_cast<unsigned>(nR) < static_cast<unsigned>(kNPCFSEP)) atomicAdd(shist_sl + nR, 1);
+                }
+            }
+            if constexpr (FORCE) {
+                const double g = __ddiv_rn(__ldg(pp.dVdr + kc), rx);      // (dV/dr)/r, potential.h:997-1003
+#pragma unroll
+                for (int d = 0; d < ND; ++d) {
+                    const double f = g * sx[d];
+                    if (lane == l) Fi[d] += f;
+                    if (lane == m) Gv[d] -= f;
+                }
+            }
+        }
+    }
+}
+
 template <int ND, bool FORCE, bool CODEC, bool CHECK>
 __device__ __forceinline__ void pair_tile(const double* __restrict__ xsl, int NP, const double (&xi)[ND], int i, bool ivalid, int b,
                                           int lane, int s_lo, int s_hi, bool diag, int N, const BoxDev& box,
@@ -185,36 +215,29 @@ __device__ __forceinline__ void pair_tile(const double* __restrict__ xsl, int NP
     constexpr int U = PIMCB_PTILE_U;         // pairs in flight per lane (tile step counts are multiples of 16)
     const double* xb = xsl + 32 * b;
     const TileIndexParams& ix = pp.ix;
+    unsigned redo = 0u;                      // bit ss: the pair of step ss is left to pair_tile_redo
     for (int s = s_lo; s < s_hi; s += U) {
         double sep[U][ND], r[U], rinv[U], vv[U], dv[U];
         int kidx[U], nR[U], kc[U];
-        bool valid[U], unsafe[U];
+        bool ok[U];
         TableSector sec[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int ss = s + u;
             const int m = (lane + ss) & 31;
-            pair_fast<ND, FORCE>(xi, xb, NP, m, box, ix, sep[u], r[u], rinv[u], kidx[u], nR[u], unsafe[u]);
-            valid[u] = true;
+            bool unsafe;
+            pair_fast<ND, FORCE>(xi, xb, NP, m, box, ix, sep[u], r[u], rinv[u], kidx[u], nR[u], unsafe);
             if constexpr (CHECK) {
-                valid[u] = ivalid && 32 * b + m < N && !(diag && ss == 16 && lane >= 16);
-                unsafe[u] = unsafe[u] && valid[u];
+                const bool valid = ivalid && 32 * b + m < N && !(diag && ss == 16 && lane >= 16);
+                unsafe = unsafe && valid;
+                ok[u] = valid && !unsafe;
+            } else {
+                ok[u] = !unsafe;
             }
-        }
 #ifndef PIMCB_COUNT_FASTPATH         // (static instruction counting of the fast path only: tools/sass_loop.py)
-        bool any_unsafe = false;
-#pragma unroll
-        for (int u = 0; u < U; ++u) any_unsafe = any_unsafe || unsafe[u];
-        if (any_unsafe) {
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (unsafe[u]) {
-                    const int2 e = pair_exact<ND>(pp.exact, xsl, NP, i, 32 * b + ((lane + s + u) & 31));
-                    kidx[u] = e.x;
-                    nR[u] = e.y;
-                }
-        }
+            if (unsafe) redo |= 1u << ss;
 #endif
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {           // both table reads of the step pair are issued here
             kc[u] = max(min(kidx[u], ix.len), 0);
@@ -223,16 +246,10 @@ __device__ __forceinline__ void pair_tile(const double* __restrict__ xsl, int NP
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             table_finish<FORCE, CODEC>(ix, pp.V, pp.dVdr, kc[u], sec[u], vv[u], dv[u]);
-            if constexpr (CHECK) {
-                vsum += valid[u] ? vv[u] : 0.0;
-                if (ix.want_hist && valid[u] && static_cast<unsigned>(nR[u]) < static_cast<unsigned>(kNPCFSEP)) atomicAdd(shist_sl + nR[u], 1);
-            } else {
-                vsum += vv[u];
-                if (ix.want_hist && static_cast<unsigned>(nR[u]) < static_cast<unsigned>(kNPCFSEP)) atomicAdd(shist_sl + nR[u], 1);
-            }
+            vsum += ok[u] ? vv[u] : 0.0;
+            if (ix.want_hist && ok[u] && static_cast<unsigned>(nR[u]) < static_cast<unsigned>(kNPCFSEP)) atomicAdd(shist_sl + nR[u], 1);
             if constexpr (FORCE) {
-                double g = dv[u] * rinv[u];             // (dV/dr)/r, potential.h:997-1003
-                if constexpr (CHECK) g = valid[u] ? g : 0.0;
+                const double g = ok[u] ? dv[u] * rinv[u] : 0.0;      // (dV/dr)/r, potential.h:997-1003
                 const int src = (lane - (s + u)) & 31;  // the lane whose partner this lane is at this step
 #pragma unroll
                 for (int d = 0; d < ND; ++d) {
@@ -243,6 +260,9 @@ __device__ __forceinline__ void pair_tile(const double* __restrict__ xsl, int NP
             }
         }
     }
+#ifndef PIMCB_COUNT_FASTPATH
+    if (__any_sync(FULL, redo != 0u)) pair_tile_redo<ND, FORCE>(redo, xsl, NP, i - lane, b, lane, box, pp, shist_sl, vsum, Fi, Gv);
+#endif
 }
 
 #ifndef PIMCB_PTILE_MINB
@@ -390,44 +410,98 @@ struct VirialTileParams {
     int t2_parity; int M;
     int G; int spc; int rounds;                  // rounds = group offsets per round (partner-side slots that fit)
     const TableSector* DD;                       // (dV/dr, d2V/dr2) packed four entries per sector, or nullptr
-    const struct ExactParams* exact;             // constants of the exact path, in device memory (want_hist = 0)
 };
 
 #ifndef PIMCB_VTILE_U
 #define PIMCB_VTILE_U 2
 #endif
+// own / vis += the gV and T-matrix terms of one pair with separation sep, r, 1/r, table values dv, d2
+template <int ND, bool T2>
+__device__ __forceinline__ void virial_pair_terms(const double (&sep)[ND], double rinv, double dv, double d2, double (&gi)[ND],
+                                                  double (&mm)[ND * (ND + 1) / 2]) {
+    const double g = dv * rinv;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) gi[d] = g * sep[d];
+    if constexpr (T2) {
+        const double dV = fabs(dv);                    // |(dV/dr / r) sep| = |dV/dr| (src/action.cpp:1544)
+        const double ri2 = rinv * rinv;
+        const double diagv = dV * rinv;
+        const double a = fma(d2, ri2, -diagv * ri2);   // d2V/r^2 - dV/r^3
+        int k = 0;
+#pragma unroll
+        for (int p = 0; p < ND; ++p)
+#pragma unroll
+            for (int q = p; q < ND; ++q, ++k) mm[k] = fma(sep[p] * sep[q], a, p == q ? diagv : 0.0);
+    }
+}
+
+template <int ND, bool T2>
+__device__ __forceinline__ void virial_tile_redo(unsigned redo, const double* __restrict__ xsl, int NP, int ibase, int b, int lane,
+                                                 const BoxDev& box, const VirialTileParams& vp,
+                                                 double (&own)[ND + ND * (ND + 1) / 2], double (&vis)[ND + ND * (ND + 1) / 2]) {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int NT = ND * (ND + 1) / 2;
+    const TileIndexParams& ix = vp.ix;
+    unsigned lanes = __ballot_sync(FULL, redo != 0u);
+    while (lanes) {
+        const int l = __ffs(lanes) - 1;
+        lanes &= lanes - 1;
+        unsigned steps = __shfl_sync(FULL, redo, l);
+        while (steps) {
+            const int ss = __ffs(steps) - 1;
+            steps &= steps - 1;
+            const int m = (l + ss) & 31;
+            double sx[ND], gi[ND], mm[NT];
+            const double rx = minimage_norm<ND>(xsl, NP, ibase + l, 32 * b + m, box, sx);     // the reference's exact sequence
+            const int kc = max(min(__double2int_rz(__ddiv_rn(rx, ix.dr)), ix.len), 0);
+            const double dv = __ldg(vp.dVdr + kc), d2 = T2 ? __ldg(vp.d2V + kc) : 0.0;
+            virial_pair_terms<ND, T2>(sx, 1.0 / rx, dv, d2, gi, mm);
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                if (lane == l) own[d] += gi[d];
+                if (lane == m) vis[d] -= gi[d];
+            }
+            if constexpr (T2) {
+#pragma unroll
+                for (int k = 0; k < NT; ++k) {
+                    if (lane == l) own[ND + k] += mm[k];
+                    if (lane == m) vis[ND + k] += mm[k];
+                }
+            }
+        }
+    }
+}
+
 template <int ND, bool T2, bool CODEC, bool CHECK>
 __device__ __forceinline__ void virial_tile(const double* __restrict__ xsl, int NP, const double (&xi)[ND], int i, bool ivalid, int b,
                                             int lane, int s_lo, int s_hi, bool diag, int N, const BoxDev& box,
                                             const VirialTileParams& vp, double (&own)[ND + ND * (ND + 1) / 2],
                                             double (&vis)[ND + ND * (ND + 1) / 2]) {
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr int NT = ND * (ND + 1) / 2;
     constexpr int U = PIMCB_VTILE_U;
     const double* xb = xsl + 32 * b;
     const TileIndexParams& ix = vp.ix;
+    unsigned redo = 0u;                      // see pair_tile
     for (int s = s_lo; s < s_hi; s += U) {
         double sep[U][ND], r[U], rinv[U], dv[U], d2[U];
         int kidx[U], nR[U], kc[U];
-        bool valid[U], unsafe[U];
+        bool ok[U];
         TableSector sec[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int ss = s + u;
             const int m = (lane + ss) & 31;
-            pair_fast<ND, true>(xi, xb, NP, m, box, ix, sep[u], r[u], rinv[u], kidx[u], nR[u], unsafe[u]);
-            valid[u] = true;
+            bool unsafe;
+            pair_fast<ND, true>(xi, xb, NP, m, box, ix, sep[u], r[u], rinv[u], kidx[u], nR[u], unsafe);
             if constexpr (CHECK) {
-                valid[u] = ivalid && 32 * b + m < N && !(diag && ss == 16 && lane >= 16);
-                unsafe[u] = unsafe[u] && valid[u];
+                const bool valid = ivalid && 32 * b + m < N && !(diag && ss == 16 && lane >= 16);
+                unsafe = unsafe && valid;
+                ok[u] = valid && !unsafe;
+            } else {
+                ok[u] = !unsafe;
             }
-        }
-        bool any_unsafe = false;
-#pragma unroll
-        for (int u = 0; u < U; ++u) any_unsafe = any_unsafe || unsafe[u];
-        if (any_unsafe) {
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (unsafe[u]) kidx[u] = pair_exact<ND>(vp.exact, xsl, NP, i, 32 * b + ((lane + s + u) & 31)).x;
+            if (unsafe) redo |= 1u << ss;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -437,36 +511,27 @@ __device__ __forceinline__ void virial_tile(const double* __restrict__ xsl, int 
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             table_finish<T2, CODEC>(ix, vp.dVdr, vp.d2V, kc[u], sec[u], dv[u], d2[u]);
-            if constexpr (CHECK) {
-                dv[u] = valid[u] ? dv[u] : 0.0;
-                d2[u] = valid[u] ? d2[u] : 0.0;
-                rinv[u] = valid[u] ? rinv[u] : 0.0;
-            }
+            dv[u] = ok[u] ? dv[u] : 0.0;     // pairs that do not exist, or are left to virial_tile_redo, add exact zeros
+            d2[u] = ok[u] ? d2[u] : 0.0;
+            rinv[u] = ok[u] ? rinv[u] : 0.0;
             const int src = (lane - (s + u)) & 31;
-            const double g = dv[u] * rinv[u];
+            double gi[ND], mm[NT];
+            virial_pair_terms<ND, T2>(sep[u], rinv[u], dv[u], d2[u], gi, mm);
 #pragma unroll
             for (int d = 0; d < ND; ++d) {
-                const double gi = g * sep[u][d];
-                own[d] += gi;
-                vis[d] -= __shfl_sync(FULL, gi, src);          // gradV(sep_ji) = -gradV(sep_ij)
+                own[d] += gi[d];
+                vis[d] -= __shfl_sync(FULL, gi[d], src);       // gradV(sep_ji) = -gradV(sep_ij)
             }
             if constexpr (T2) {
-                const double dV = fabs(dv[u]);                 // |(dV/dr / r) sep| = |dV/dr| (src/action.cpp:1544)
-                const double ri2 = rinv[u] * rinv[u];
-                const double diagv = dV * rinv[u];
-                const double a = fma(d2[u], ri2, -diagv * ri2);     // d2V/r^2 - dV/r^3
-                int k = ND;
 #pragma unroll
-                for (int p = 0; p < ND; ++p)
-#pragma unroll
-                    for (int q = p; q < ND; ++q, ++k) {
-                        const double mm = fma(sep[u][p] * sep[u][q], a, p == q ? diagv : 0.0);
-                        own[k] += mm;
-                        vis[k] += __shfl_sync(FULL, mm, src);  // the T-matrix term is the same seen from either end
-                    }
+                for (int k = 0; k < NT; ++k) {
+                    own[ND + k] += mm[k];
+                    vis[ND + k] += __shfl_sync(FULL, mm[k], src);   // the T-matrix term is the same seen from either end
+                }
             }
         }
     }
+    if (__any_sync(FULL, redo != 0u)) virial_tile_redo<ND, T2>(redo, xsl, NP, i - lane, b, lane, box, vp, own, vis);
 }
 
 #ifndef PIMCB_VTILE_MINB

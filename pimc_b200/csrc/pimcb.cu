@@ -132,7 +132,6 @@ struct pimcb_ctx {
     PinBuf h_out;
     // pair potential
     DevBuf d_V, d_dV, d_vint, d_f2, d_hist;
-    DevBuf d_exact;                        // ExactParams blocks of the tile kernels' exact path: [0] pair sums, [1] virial sums
     DevBuf d_VD, d_DD;                     // (V, dV/dr) and (dV/dr, d2V/dr2) packed four entries per sector (table_codec.h)
     bool vd_ok = false, dd_ok = false;     // the packed tables were built AND verified bit for bit on the device
     long vd_raw = 0, dd_raw = 0;           // sectors left verbatim (zero crossings, core, switch of the damping function)
@@ -810,18 +809,6 @@ bool make_index_params(const pimcb_ctx* c, double dSep, bool want_hist, TileInde
     return true;
 }
 
-// Constants of the tile kernels' exact path, in device memory (slot 0: pair sums, slot 1: virial sums); enqueued on the
-// compute stream in front of the launch that reads them.
-int upload_exact_params(pimcb_ctx* c, int slot, double dSep, int want_hist, const ExactParams** out) {
-    int rc = c->d_exact.ensure(2 * sizeof(ExactParams));
-    if (rc) return rc;
-    ExactParams ep{c->box, c->dr, dSep, want_hist};
-    ExactParams* dst = c->d_exact.as<ExactParams>() + slot;
-    CU(cudaMemcpyAsync(dst, &ep, sizeof ep, cudaMemcpyHostToDevice, c->stream));     // pageable source: staged by the runtime before returning
-    *out = dst;
-    return 0;
-}
-
 }  // namespace
 
 // =============================================================================================
@@ -887,7 +874,7 @@ int pimcb_destroy(pimcb_ctx* c) {
     for (auto& p : c->pin) { p.release(); if (p.done) cudaEventDestroy(p.done); }
     c->h_out.release();
     for (DevBuf* b : {&c->d_q, &c->d_comm, &c->d_qn, &c->d_qidx, &c->d_plan, &c->d_rho, &c->d_cfg, &c->d_bins, &c->d_partial,
-                      &c->d_V, &c->d_dV, &c->d_VD, &c->d_DD, &c->d_exact, &c->d_vint, &c->d_f2, &c->d_hist, &c->d_scratch, &c->d_sched, &c->d_binrows, &c->d_unfold,
+                      &c->d_V, &c->d_dV, &c->d_VD, &c->d_DD, &c->d_vint, &c->d_f2, &c->d_hist, &c->d_scratch, &c->d_sched, &c->d_binrows, &c->d_unfold,
                       &c->d_var, &c->d_inside, &c->d_d2V, &c->d_delta_aos, &c->d_delta, &c->d_vir, &c->d_gext, &c->d_g2ext, &c->d_gather, &c->d_count})
         b->release();
     for (int k = 0; k < kKernels; ++k) { cudaEventDestroy(c->ev0[k]); cudaEventDestroy(c->ev1[k]); }
@@ -1596,10 +1583,8 @@ int pimcb_pair_sums(pimcb_ctx* c, double* vint, double* f2, int* sephist, double
             // needs no decoding.  PIMCB_PAIR_PACKED=0 / 1 forces one or the other (A/B).
             static const int packed_env = std::getenv("PIMCB_PAIR_PACKED") ? std::atoi(std::getenv("PIMCB_PAIR_PACKED")) : -1;
             const bool use_packed = c->vd_ok && (packed_env < 0 ? f2 != nullptr : packed_env != 0);
-            const ExactParams* exact = nullptr;
-            if ((rc = upload_exact_params(c, 0, pp.dSep, pp.want_hist, &exact))) return rc;
             PairTileParams tp{c->d_V.as<double>(), c->d_dV.as<double>(), ixp, f2_parity, s->M, pp.gext, G, spc,
-                              use_packed ? c->d_VD.as<TableSector>() : nullptr, exact};
+                              use_packed ? c->d_VD.as<TableSector>() : nullptr};
             const int units = (nsl + spc - 1) / spc;
 #define LAUNCH_PTILE2(ND, CODEC)                                                                                   \
             rc = set_smem(pair_tile_kernel<ND, CODEC>, smem_tile); if (rc) return rc;                               \
@@ -1767,10 +1752,8 @@ int pimcb_virial_sums(pimcb_ctx* c, const double* delta_aos, int t2_parity, doub
         TileIndexParams ixp{};
         if (!ext && vtile_on && vtile_smem(rounds) <= 200 * 1024 && make_index_params(c, 1.0, false, &ixp)) {
             const bool packed = c->dd_ok && (t2_parity == -2 || c->have_d2V);
-            const ExactParams* exact = nullptr;
-            if ((rc = upload_exact_params(c, 1, 1.0, 0, &exact))) return rc;
             VirialTileParams tp{c->d_dV.as<double>(), c->d_d2V.as<double>(), ixp, t2_parity, s->M, G, spc, rounds,
-                                packed ? c->d_DD.as<TableSector>() : nullptr, exact};
+                                packed ? c->d_DD.as<TableSector>() : nullptr};
             const size_t smem_t = vtile_smem(rounds);
             const int units = (nsl + spc - 1) / spc;
 #define LAUNCH_VTILE2(ND, CODEC)                                                                                   \
