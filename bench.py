@@ -4,7 +4,7 @@
     python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run)
     python bench.py --impl reference ...                     (the CPU restatement of the reference estimators)
 
-A step = ONE OUTPUT BIN of the hot path: `--batches-per-step` (16) batches of B (64) synthetic walker configurations per GPU
+A step = ONE OUTPUT BIN of the hot path: `--batches-per-step` (4) batches of B (256) synthetic walker configurations per GPU
 go through rho_q build + tau-correlation + bin accumulation, then the bin is folded and -- on more than one GPU --
 exchanged once (the library's own NCCL reduce / all-gather), exactly what EstimatorBase::output does per bin.
 `value` = configurations evaluated per second over all ranks with beads resident in HBM; `e2e` = the same through the
@@ -44,8 +44,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="walker configurations per GPU per batch (one launch pair)")
-    ap.add_argument("--batches-per-step", type=int, default=16, help="batches accumulated into one output bin = one step")
+    ap.add_argument("--batch", type=int, default=256,
+                    help="walker configurations per GPU per batch (one launch pair); 64 -> 256 per launch is worth 16 %% "
+                         "(profiles/r02p_corr_occ_and_batch_sweep.txt: fewer ragged last waves of the persistent rho kernel)")
+    ap.add_argument("--batches-per-step", type=int, default=4, help="batches accumulated into one output bin = one step (1024 evaluations)")
     ap.add_argument("--workload", default="C2", choices=sorted(synth.SHAPES))
     ap.add_argument("--rho-mode", type=int, default=-1, help="-1 library default, 0 generic sincos, 1 lattice recurrence")
     ap.add_argument("--corr-mode", type=int, default=-1, help="-1 library default, 0 CUDA-core tau-correlation, 1 DMMA")

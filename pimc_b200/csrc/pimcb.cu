@@ -519,7 +519,10 @@ int launch_corr(pimcb_ctx* c, const Slot& s, int* partial_rows = nullptr) {
     if (c->corr_mode == 1 && mtc <= 4) {
         const int off = 64 * mtc, mpad = (s.M + 3) & ~3, ext = off + mpad + 8;
         const int plen = ext + 4 * (ext >> 3) + 4;
-        const size_t smem = sizeof(double) * 2 * static_cast<size_t>(plen) * 4;
+        size_t smem = sizeof(double) * 2 * static_cast<size_t>(plen) * 4;
+        // PIMCB_CORR_OCC=n: pad the shared-memory request so that at most n CTAs are resident per SM (occupancy A/B)
+        static const int corr_occ = std::getenv("PIMCB_CORR_OCC") ? std::atoi(std::getenv("PIMCB_CORR_OCC")) : 0;
+        if (corr_occ > 0) smem = std::max(smem, static_cast<size_t>(226 * 1024) / corr_occ - 1024);
         const int quads = (s.B + 3) / 4;
         const bool partial = partial_rows != nullptr;
         int rc = 0;
