@@ -44,10 +44,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256,
-                    help="walker configurations per GPU per batch (one launch pair); 64 -> 256 per launch is worth 16 %% "
+    ap.add_argument("--batch", type=int, default=0,
+                    help="0 = 256 (64 for C4, whose configurations are 7.5x larger); walker configurations per GPU per batch (one launch pair); 64 -> 256 per launch is worth 16 %% "
                          "(profiles/r02p_corr_occ_and_batch_sweep.txt: fewer ragged last waves of the persistent rho kernel)")
-    ap.add_argument("--batches-per-step", type=int, default=4, help="batches accumulated into one output bin = one step (1024 evaluations)")
+    ap.add_argument("--batches-per-step", type=int, default=0,
+                    help="batches accumulated into one output bin = one step; 0 = 4 for batches of >= 256 (1024 evaluations), else 16")
     ap.add_argument("--workload", default="C2", choices=sorted(synth.SHAPES))
     ap.add_argument("--rho-mode", type=int, default=-1, help="-1 library default, 0 generic sincos, 1 lattice recurrence")
     ap.add_argument("--corr-mode", type=int, default=-1, help="-1 library default, 0 CUDA-core tau-correlation, 1 DMMA")
@@ -428,10 +429,14 @@ def run_ours(args, shape, q):
 
     from pimc_b200 import multi
     B, K, W, P = args.batch, args.steps, args.warmup, args.batches_per_step
+    if B <= 0:
+        B = 64 if shape.name == "C4" else 256
     if args.total_batch > 0:
         if args.total_batch % world:
             raise SystemExit(f"--total-batch {args.total_batch} is not a multiple of {world} GPUs")
         B = args.total_batch // world
+    if P <= 0:
+        P = 4 if B >= 256 else 16
     q_all = q
     if args.shard == "q" and world > 1:
         lo, hi = multi.shard_range(len(q_all), world, rank)
@@ -653,6 +658,7 @@ def run_ours(args, shape, q):
         "dmma_probe_source": "tools/micro/dmma_peak.cu (mma.sync.m8n8k4.f64 chains), profiles/r01*_dmma_peak / DESIGN.md section 5",
         "flop_per_launch": B * kernel_flop, "flop_basis": "useful flop of the kernel that ran (DESIGN.md section 5)",
         "avg_launch_ms": rho_avg_s * 1e3, "launches_timed": rho_n,
+        "configurations_per_launch": B, "us_per_64_configurations": rho_avg_s * 1e6 * 64.0 / B,
         "timing": f"CUDA events around every {args.profile_stride}-th launch of this kernel inside the timed region ({rho_n} of {K * P} launches)",
         "share_of_step": rho_avg_s / max(1e-12, rho_avg_s + corr_avg_s + bins_ms * 1e-3 / max(1, ktimes["bins"][1])),
         "bins_kernel": {"avg_launch_ms": bins_ms / max(1, ktimes["bins"][1])},
@@ -662,7 +668,7 @@ def run_ours(args, shape, q):
         "survey_convention": {"flop_per_launch": B * rho_flop, "equivalent_tflops": B * rho_flop / rho_avg_s / 1e12 if rho_n else None},
         "hbm": {"achieved_gbs": alg_bytes / rho_avg_s / 1e9 if rho_n else None, "peak_gbs": hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"},
-        "corr_kernel": {"avg_launch_ms": corr_avg_s * 1e3, "achieved_tflops": B * corr_flop / corr_avg_s / 1e12 if corr_n else None},
+        "corr_kernel": {"avg_launch_ms": corr_avg_s * 1e3, "us_per_64_configurations": corr_avg_s * 1e6 * 64.0 / B, "achieved_tflops": B * corr_flop / corr_avg_s / 1e12 if corr_n else None},
     }
     # ---- A/B: the generic kernel (one sincos per (q, bead)) on the same batches, SURVEY 8d flop convention --------
     if plan["path"] != 0 and not args.no_ab:
@@ -797,6 +803,7 @@ def pair_legs(args, ctx, shape, pinned, use_slots, B):
             "kernel": ("pair_tile_kernel (32 x 32 tiles, every pair once, division-free exact index" + (", packed (V, dV/dr) sectors)" if packed else ", verbatim tables)"))
                       if tile else "pair_sym_kernel (ring, every pair once)",
             "value": B / p_s, "unit": "configurations/s", "avg_launch_ms": p_s * 1e3, "launches_timed": pn,
+            "configurations_per_launch": B, "ms_per_64_configurations": p_s * 1e3 * 64.0 / B,
             "table_entries": len(Vt), "table_mb_verbatim": 2 * 8 * len(Vt) / 1e6, "table_mb_read": (32 * codec["sectors"] / 1e6) if packed else 2 * 8 * len(Vt) / 1e6,
             "packed_tables": codec,
             "pairs_per_launch": B * shape.M * pairs, "pair_rate_g_per_s": B * shape.M * pairs / p_s / 1e9,
@@ -805,8 +812,8 @@ def pair_legs(args, ctx, shape, pinned, use_slots, B):
                          "peak": gather_peak / 1e9, "unit": "G reads/s", "frac": reads / p_s / gather_peak,
                          "peak_source": "tools/micro/gather_peak.cu on this pool's B200 (profiles/r02a_gather_peak.txt): 289 G reads/s for "
                                         "footprints <= 53 MB, 140 G/s at 106 MB (the verbatim V + dV/dr tables of C2), 73 G/s from DRAM",
-                         "note": "ncu (profiles/r02j_*): L2 hit rate 98 %, 0.12 GB DRAM reads per launch, issue slots 61 % busy -- the kernel is "
-                                 "bound by instruction issue / dependent FP64 latency (143 warp-instructions per pair), not by the reads",
+                         "note": "ncu (profiles/r02*_kernels.md, 64 configurations per launch): L2 hit rate 98 %, 0.12 GB DRAM reads per launch, issue "
+                                 "slots 61 % busy -- bound by instruction issue / dependent FP64 latency, not by the reads",
                          "hbm_algorithmic": {"bytes": 32 * reads + B * 8 * shape.ndim * shape.N * shape.M,
                                              "achieved_gbs": (32 * reads + B * 8 * shape.ndim * shape.N * shape.M) / p_s / 1e9}}}
     ctx.set_pair_table_d2(d2Vt)
@@ -825,6 +832,7 @@ def pair_legs(args, ctx, shape, pinned, use_slots, B):
     vg = B * pairs * (shape.M if vpacked else shape.M + shape.M // 2)      # one sector per pair, or dV/dr everywhere + d2V/dr2 on the odd slices
     pair["virial_sums"] = {"metric": "virial slice sums/s (4 sums per slice; gsf action, window deltas from the host)",
                            "value": B / v_s, "unit": "configurations/s", "avg_launch_ms": v_s * 1e3, "launches_timed": vn,
+                           "configurations_per_launch": B, "ms_per_64_configurations": v_s * 1e3 * 64.0 / B,
                            "kernel": "virial_tile_kernel" + (" (packed (dV/dr, d2V/dr2) sectors)" if vpacked else " (verbatim tables)"),
                            "table_reads_per_launch": vg, "table_read_rate_g_per_s": vg / v_s / 1e9,
                            "roofline": {"bound": "L2 sector rate of random 8-byte table reads", "achieved": vg / v_s / 1e9,
