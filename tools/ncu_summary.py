@@ -96,6 +96,15 @@ def main():
         for k, a in agg.items():
             md.append(f"| `{k}` | {a[0]} | {a[1] / a[0] / 1e3:.1f} | {100 * a[1] / total:.1f}% |")
         md.append("")
+        # the timed step of bench.py is rho + tau-correlation (one pair per batch) + one bin fold: the share inside THAT
+        # is what bench.py's roofline.share_of_step claims (the list above also holds the secondary legs' kernels)
+        step = {k: a for k, a in agg.items() if k.startswith(("rho_lattice", "isf_corr_mma_kernel<2, 1>", "bins_fold"))}
+        rho = [a for k, a in step.items() if k.startswith("rho_lattice")]
+        cor = [a for k, a in step.items() if k.startswith("isf_corr")]
+        if rho and cor:
+            r_us, c_us = rho[0][1] / rho[0][0] / 1e3, cor[0][1] / cor[0][0] / 1e3
+            md += [f"Inside the timed step (one rho + one tau-correlation launch per batch): rho {r_us:.1f} us of {r_us + c_us:.1f} us = "
+                   f"**{100 * r_us / (r_us + c_us):.1f} %** -- compare `roofline.share_of_step` of the bench line.", ""]
     for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"{tag}_prof_*.ncu-rep"))):
         d = kernel_detail(rep)
         if not d:
@@ -135,7 +144,7 @@ def main():
             merged[k] = v
             src[k] = tag
         merged["sources"] = src
-        merged["source"] = "ncu --set full --clock-control none, one launch each (64 C2 configurations per launch); per-kernel visit tag in `sources`"
+        merged["source"] = "ncu --set full --clock-control none, one launch each (the bench's default batch per launch: 256 C2 configurations from r02q on, 64 before); per-kernel visit tag in `sources`"
         with open(path, "w") as f:
             json.dump(merged, f, indent=1)
     with open(os.path.join(out, f"{tag}_kernels.md"), "w") as f:
