@@ -227,9 +227,9 @@ class CpuArm:
         if self.up:
             return (f"upstream accumulate() bodies (oracle/_ref/librefcpu{s.ndim}d_fast.so), 1 configuration, {self.cores} threads: F(q,tau) full "
                     f"loop nest over the first {self.Ms} of {s.M} slices for {self.nq_isf} q (one per thread), S(q) at full size for "
-                    f"{self.n_ssf} of {len(self.q)} q; extrapolated by term count to {len(self.q)} q x {s.M}^2 slice pairs")
+                    f"{self.n_ssf} of {len(self.q)} q; extrapolated by term count to {len(self.q)} q x {s.M}^2 slice pairs; median over the timed steps")
         return (f"1 configuration: {self.n_elem} of {len(self.q) * s.M} F(q,tau) elements (direct O(M N^2) loop each) + "
-                f"S(q) for {self.n_ssf} of {len(self.q)} q, {self.cores} threads, extrapolated linearly to the full q-set")
+                f"S(q) for {self.n_ssf} of {len(self.q)} q, {self.cores} threads, extrapolated linearly to the full q-set; median over the timed steps")
 
 
 def workload_text(shape, nq):
@@ -256,7 +256,9 @@ def time_cpu_arm(arm, steps, warmup):
         f, w = arm.step()
         evals.append(f)
         wall.append(w)
-    return 1.0 / float(np.mean(evals)), float(np.mean(wall))
+    # median over the steps: the sample is statically partitioned (one q per thread), so one descheduled thread stretches
+    # a whole step -- the mean of a handful of steps moved by 10-20 % between two processes on the same box
+    return 1.0 / float(np.median(evals)), float(np.median(wall))
 
 
 def run_reference(args, shape, q):
@@ -757,7 +759,7 @@ def run_ours(args, shape, q):
         # warm-up + averaging as --impl reference
         os.sched_setaffinity(0, all_cpus)
         arm = CpuArm(shape, q_all, args.cpu_seconds)
-        cpu_value, _ = time_cpu_arm(arm, 2, 1)
+        cpu_value, _ = time_cpu_arm(arm, 5, 1)
         line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
                                 "sample": arm.sample_text(), "one_core_value": 1.0 / arm.one_core(), "extrapolated": True,
                                 "full_size_record": FULL_SIZE_RECORD,
