@@ -49,6 +49,9 @@ def parse_args():
                          "(profiles/r02p_corr_occ_and_batch_sweep.txt: fewer ragged last waves of the persistent rho kernel)")
     ap.add_argument("--batches-per-step", type=int, default=0,
                     help="batches accumulated into one output bin = one step; 0 = 4 for batches of >= 256 (1024 evaluations), else 16")
+    ap.add_argument("--exchange", default="pipelined", choices=["pipelined", "inline"],
+                    help="walker sharding on > 1 GPU with --collective lib: pimcb_reduce_bins_begin/_end (the bin's snapshot is reduced "
+                         "on the library's communication stream while the next bin is measured) or pimcb_reduce_bins on the compute stream")
     ap.add_argument("--workload", default="C2", choices=sorted(synth.SHAPES))
     ap.add_argument("--rho-mode", type=int, default=-1, help="-1 library default, 0 generic sincos, 1 lattice recurrence")
     ap.add_argument("--corr-mode", type=int, default=-1, help="-1 library default, 0 CUDA-core tau-correlation, 1 DMMA")
@@ -477,14 +480,30 @@ def run_ours(args, shape, q):
     ext = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
     peak_tflops = ctx.fp64_peak_tflops(args.peak_seconds)
 
+    pipelined = lib_coll and args.shard == "config" and args.exchange == "pipelined"
+    xchg = {"pending": False, "last": None}
+
+    def exchange_collect():
+        """Wait for the exchange started one bin ago (root: the global bin lands in host memory)."""
+        if xchg["pending"]:
+            xchg["last"] = ctx.reduce_bins_end()
+            xchg["pending"] = False
+        return xchg["last"]
+
     def bin_exchange():
         """The end of an output bin: fold the accumulators and -- on more than one GPU -- the ONE collective of the path."""
         if world == 1:
             ctx.bins_device_ptr()                                 # enqueues the fold of the persistent rows into the bin
             return
         if lib_coll:
-            if args.shard == "config":
-                ctx.reduce_bins(0)
+            if pipelined:
+                # pimcb_reduce_bins_begin / _end: the previous bin's row is collected, then this bin's snapshot starts its
+                # reduce on the library's communication stream while the next bin is measured
+                exchange_collect()
+                ctx.reduce_bins_begin(0)
+                xchg["pending"] = True
+            elif args.shard == "config":
+                ctx.reduce_bins(0, want_total=False)          # no host synchronisation: the count comes with read_bins
             else:
                 g_ssf, _ = ctx.gather_bins_q(multi.shard_sizes(len(q_all), world))
                 assert g_ssf.shape == (len(q_all),)
@@ -516,7 +535,12 @@ def run_ours(args, shape, q):
     # one bin checked for its bookkeeping before the timed region: every configuration of every rank is in it
     device_step(0, exchange=False)
     bin_exchange()
-    _, _, n_acc = ctx.read_bins()
+    if pipelined:
+        _, _, n_acc = exchange_collect()
+        if rank != 0:
+            n_acc = ctx.read_bins()[2]
+    else:
+        _, _, n_acc = ctx.read_bins()
     expect_acc = B * P * (world if (lib_coll and args.shard == "config" and rank == 0) else 1)
     assert n_acc == expect_acc, (n_acc, expect_acc)
     ctx.reset_bins()
@@ -529,6 +553,7 @@ def run_ours(args, shape, q):
     e0.record(ext)
     for k in range(K):
         device_step(k)
+    exchange_collect()                      # the last bin's row: inside the timed region
     e1.record(ext)
     barrier()
     clocks = sampler.stop()
@@ -564,7 +589,9 @@ def run_ours(args, shape, q):
                 ctx.stage_async(pinned[(k * P + j + 1) % use_slots].array, shape.N)   # H2D of the next batch overlaps them
             if world > 1:
                 bin_exchange()
-            ssf_bin, isf_bin, _ = ctx.read_bins()                                     # D2H of the bin (syncs)
+            if not pipelined:
+                ssf_bin, isf_bin, _ = ctx.read_bins()                                 # D2H of the bin (syncs)
+            # (pipelined exchange: the root's D2H of the GLOBAL bin is part of pimcb_reduce_bins_end, one bin later)
             ctx.reset_bins()
 
         e2e_step(0)                                          # warm-up of the pipelined loop
@@ -572,6 +599,7 @@ def run_ours(args, shape, q):
         t0 = time.perf_counter()
         for k in range(Ke):
             e2e_step(k)
+        exchange_collect()
         torch.cuda.synchronize()
         dt = allreduce(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
         # in-run ceiling: the bare cudaMemcpyAsync rate of the same page-locked buffers, all ranks copying at the same time
@@ -590,7 +618,9 @@ def run_ours(args, shape, q):
                "ceiling": "bare cudaMemcpyAsync of one batch buffer, 12 back to back, all ranks concurrently, same run "
                           "(pimcb_measure_h2d_peak); min over ranks",
                "path": f"per step: {P} x [pimcb_measure + pimcb_stage_batch_async(pinned host AoS)] + "
-                       + ("the bin collective + " if world > 1 else "") + "pimcb_read_bins + pimcb_reset_bins, staging pipelined one batch ahead"}
+                       + (("pimcb_reduce_bins_end(previous bin: root's D2H) + pimcb_reduce_bins_begin + pimcb_reset_bins" if pipelined else
+                           "the bin collective + pimcb_read_bins + pimcb_reset_bins") if world > 1 else "pimcb_read_bins + pimcb_reset_bins")
+                       + ", staging pipelined one batch ahead"}
 
     # ---- latency: ONE configuration through the synchronous ABI calls an estimator's accumulate() makes ----------
     latency = None
@@ -738,10 +768,13 @@ def run_ours(args, shape, q):
                 "l2": f"{use_slots} resident batches rotated ({footprint_mb:.0f} MB > 126 MB L2)",
                 "rho_mode": args.rho_mode, "corr_mode": args.corr_mode,
                 "collective": ("none (one GPU)" if world == 1 else
-                               ("library NCCL (pimcb_reduce_bins / pimcb_gather_bins_q)" if lib_coll else "torch.distributed NCCL on the library's bin")),
+                               (("library NCCL, pipelined: pimcb_reduce_bins_begin / _end, the snapshot of bin k is reduced on the library's "
+                                 "communication stream while bin k+1 is measured" if pipelined else
+                                 "library NCCL (pimcb_reduce_bins / pimcb_gather_bins_q) on the compute stream") if lib_coll else "torch.distributed NCCL on the library's bin")),
                 "host_binding": (f"rank bound to {len(numa_cpus)} GPU-local CPUs (NVML affinity)" if numa_cpus else "none")},
         "clocks": clocks, "e2e": e2e, "latency": latency, "gpu_launches": int(launches), "roofline": roofline, "pair_sums": pair, "ssf_direct": direct,
     }
+    exchange_collect()
     beads_one = np.array(pinned[0].array[0])
     for pa in pinned:
         pa.free()

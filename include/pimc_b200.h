@@ -193,14 +193,22 @@ int pimcb_virial_sums(pimcb_ctx* ctx, const double* delta_aos, int t2_parity, do
  *   pimcb_comm_init / pimcb_comm_destroy: collective over all `nranks` ctxs.
  *   pimcb_reduce_bins: sums every rank's device bin (S(q) and F(q,tau) accumulators, layout of pimcb_read_bins) and
  *     its configuration count onto `root`, in place, on the ctx stream; afterwards pimcb_read_bins on the root
- *     returns the global bin and count (*num_total, may be NULL, gets the count on the root and 0 elsewhere).  The
- *     other ranks' bins are unchanged: call pimcb_reset_bins on every rank to start the next bin.
+ *     returns the global bin and count (*num_total gets the count on the root and 0 elsewhere; with num_total == NULL
+ *     the call does not synchronise with the device at all -- the count reaches the host with the next
+ *     pimcb_read_bins).  The other ranks' bins are unchanged: call pimcb_reset_bins on every rank to start the next bin.
+ *   pimcb_reduce_bins_begin / pimcb_reduce_bins_end: the same reduce, pipelined.  _begin snapshots the bin (and its
+ *     count) and starts the reduce of the snapshot on the library's own communication stream, without waiting for
+ *     anything; the caller resets the bin (pimcb_reset_bins) and measures the next one while the snapshot travels.  _end
+ *     waits for that reduce and, on the root, copies the global bin out (ssf[nq], isf[nq][M], either may be NULL;
+ *     *num_total = configurations in it, 0 on the other ranks).  One exchange in flight per ctx; every rank calls both.
  *   pimcb_gather_bins_q: nq_per_rank[nranks] = wave-vectors held by each rank (rank order = q order); every rank
  *     receives the concatenated bins ssf[sum nq] and isf[sum nq][M] (host pointers, either may be NULL). */
 int pimcb_comm_unique_id(void* id_out /*[128]*/);
 int pimcb_comm_init(pimcb_ctx* ctx, int nranks, int rank, const void* unique_id /*[128]*/);
 int pimcb_comm_destroy(pimcb_ctx* ctx);
 int pimcb_reduce_bins(pimcb_ctx* ctx, int root, long* num_total);
+int pimcb_reduce_bins_begin(pimcb_ctx* ctx, int root);
+int pimcb_reduce_bins_end(pimcb_ctx* ctx, double* ssf /*[nq] or NULL*/, double* isf /*[nq*M] or NULL*/, long* num_total /*or NULL*/);
 int pimcb_gather_bins_q(pimcb_ctx* ctx, const int* nq_per_rank, double* ssf, double* isf);
 
 /* ---- measurement helpers (bench) --------------------------------------------------------------------

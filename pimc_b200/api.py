@@ -28,6 +28,7 @@ SYMBOLS = [
     "pimcb_pair_sums", "pimcb_measure_fp64_peak", "pimcb_set_profiling", "pimcb_set_profiling_stride", "pimcb_kernel_times",
     "pimcb_launch_count", "pimcb_rho_plan_info", "pimcb_elastic", "pimcb_ssf_cyl", "pimcb_set_pair_table_d2",
     "pimcb_virial_sums", "pimcb_comm_unique_id", "pimcb_comm_init", "pimcb_comm_destroy", "pimcb_reduce_bins",
+    "pimcb_reduce_bins_begin", "pimcb_reduce_bins_end",
     "pimcb_gather_bins_q", "pimcb_set_external_gradient", "pimcb_set_external_laplacian", "pimcb_init_bins", "pimcb_measure_h2d_peak", "pimcb_table_codec_info",
 ]
 
@@ -119,6 +120,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.pimcb_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
     lib.pimcb_comm_destroy.argtypes = [vp]
     lib.pimcb_reduce_bins.argtypes = [vp, C.c_int, C.POINTER(C.c_long)]
+    lib.pimcb_reduce_bins_begin.argtypes = [vp, C.c_int]
+    lib.pimcb_reduce_bins_end.argtypes = [vp, _dp, _dp, C.POINTER(C.c_long)]
     lib.pimcb_gather_bins_q.argtypes = [vp, _ip, _dp, _dp]
     if path == _build.LIB:
         _lib = lib
@@ -402,10 +405,29 @@ class Context:
     def comm_destroy(self):
         self._chk(self.lib.pimcb_comm_destroy(self._h))
 
-    def reduce_bins(self, root: int = 0) -> int:
+    def reduce_bins(self, root: int = 0, want_total: bool = True) -> int:
+        """want_total=False: everything is enqueued, nothing waited for; read_bins() returns the global count later."""
+        if not want_total:
+            self._chk(self.lib.pimcb_reduce_bins(self._h, root, None))
+            return 0
         n = C.c_long(0)
         self._chk(self.lib.pimcb_reduce_bins(self._h, root, C.byref(n)))
         return n.value
+
+    def reduce_bins_begin(self, root: int = 0):
+        """Snapshot the bin and start its reduce on the library's communication stream; reset_bins() and the next bin's
+        measurements may follow at once."""
+        M = self.shape[1] if getattr(self, "shape", None) else self._bins_M     # nothing staged yet: the init_bins layout
+        self._xchg = (self.nq, M)
+        self._chk(self.lib.pimcb_reduce_bins_begin(self._h, root))
+        return self
+
+    def reduce_bins_end(self):
+        """Wait for the exchange started by reduce_bins_begin; (ssf[nq], isf[nq][M], configurations) -- zeros off the root."""
+        nq, M = getattr(self, "_xchg", None) or (self.nq, self.shape[1] if getattr(self, "shape", None) else self._bins_M)
+        ssf, isf, n = np.zeros(nq), np.zeros((nq, M)), C.c_long(0)
+        self._chk(self.lib.pimcb_reduce_bins_end(self._h, _ptr(ssf), _ptr(isf), C.byref(n)))
+        return ssf, isf, n.value
 
     def gather_bins_q(self, nq_per_rank):
         _, M, _ = self.shape

@@ -127,6 +127,17 @@ struct pimcb_ctx {
     // work buffers
     DevBuf d_rho, d_cfg, d_bins, d_partial;
     long n_acc = 0;
+    PinBuf h_cnt;                          // pimcb_reduce_bins without num_total: the global count lands here, read at the next sync
+    bool n_acc_pending = false;
+    // pipelined exchange (pimcb_reduce_bins_begin / _end): a snapshot of the bin travels on its own stream while the next
+    // bin accumulates
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t xchg_ready = nullptr, xchg_done = nullptr;
+    DevBuf d_xchg;                         // [bins_len] doubles + {my count, total count}
+    PinBuf h_xchg;                         // root: the reduced bin; every rank: {my count, total count} behind it
+    bool xchg_inflight = false;
+    int xchg_root = 0, xchg_nq = 0, xchg_M = 0;
+    size_t xchg_len = 0;
     size_t bins_len = 0;
     int bins_M = 0;                        // time slices of the current bin layout
     PinBuf h_out;
@@ -876,6 +887,13 @@ int pimcb_destroy(pimcb_ctx* c) {
     }
     for (auto& p : c->pin) { p.release(); if (p.done) cudaEventDestroy(p.done); }
     c->h_out.release();
+    c->h_cnt.release();
+    if (c->comm_stream) { cudaStreamSynchronize(c->comm_stream); cudaStreamDestroy(c->comm_stream); c->comm_stream = nullptr; }
+    if (c->xchg_ready) cudaEventDestroy(c->xchg_ready);
+    if (c->xchg_done) cudaEventDestroy(c->xchg_done);
+    c->xchg_ready = c->xchg_done = nullptr;
+    c->d_xchg.release();
+    c->h_xchg.release();
     for (DevBuf* b : {&c->d_q, &c->d_comm, &c->d_qn, &c->d_qidx, &c->d_plan, &c->d_rho, &c->d_cfg, &c->d_bins, &c->d_partial,
                       &c->d_V, &c->d_dV, &c->d_VD, &c->d_DD, &c->d_vint, &c->d_f2, &c->d_hist, &c->d_scratch, &c->d_sched, &c->d_binrows, &c->d_unfold,
                       &c->d_var, &c->d_inside, &c->d_d2V, &c->d_delta_aos, &c->d_delta, &c->d_vir, &c->d_gext, &c->d_g2ext, &c->d_gather, &c->d_count})
@@ -1353,12 +1371,24 @@ int pimcb_ssf_isf_beads(pimcb_ctx* c, const double* beads, int M, int N, int Nex
 int pimcb_ssf(pimcb_ctx* c, double* out) { return pimcb_ssf_isf(c, out, nullptr); }
 int pimcb_isf(pimcb_ctx* c, double* out) { return pimcb_ssf_isf(c, nullptr, out); }
 
+// The global configuration count of a pimcb_reduce_bins that did not wait for it: valid once the ctx stream has passed the
+// copy.  `synced` = the caller has just synchronised the stream.
+static int settle_count(pimcb_ctx* c, bool synced) {
+    if (!c->n_acc_pending) return 0;
+    if (!synced) CU(cudaStreamSynchronize(c->stream));
+    c->n_acc = static_cast<long>(*static_cast<const long long*>(c->h_cnt.p));
+    c->n_acc_pending = false;
+    return 0;
+}
+
 int pimcb_measure(pimcb_ctx* c) {
     if (!c) return fail(PIMCB_EINVAL, "null ctx");
     CU(cudaSetDevice(c->device));
     Slot* s;
     int rows = 0;
-    int rc = run_estimators(c, &s, &rows);
+    int rc = settle_count(c, false);        // accumulating on top of a reduced bin: its count first
+    if (rc) return rc;
+    rc = run_estimators(c, &s, &rows);
     if (rc) return rc;
     if (rows > 0) {
         KTimer kt(c, K_BINS);
@@ -1398,6 +1428,7 @@ int pimcb_reset_bins(pimcb_ctx* c) {
         c->binrows_n = 0;
     }
     c->n_acc = 0;
+    c->n_acc_pending = false;
     return 0;
 }
 
@@ -1414,6 +1445,7 @@ int pimcb_read_bins(pimcb_ctx* c, double* ssf, double* isf, long* num_acc) {
     const double* h = static_cast<const double*>(c->h_out.p);
     if (ssf) std::memcpy(ssf, h, sizeof(double) * c->nq);
     if (isf) std::memcpy(isf, h + c->nq, bytes - sizeof(double) * c->nq);
+    if ((rc = settle_count(c, true))) return rc;
     if (num_acc) *num_acc = c->n_acc;
     return 0;
 }
@@ -1822,6 +1854,8 @@ int pimcb_comm_destroy(pimcb_ctx* c) {
     if (!c) return fail(PIMCB_EINVAL, "null ctx");
     if (c->nccl_comm) {
         CU(cudaStreamSynchronize(c->stream));
+        if (c->comm_stream) CU(cudaStreamSynchronize(c->comm_stream));
+        c->xchg_inflight = false;
         NCCLCHK(g_nccl.CommDestroy(c->nccl_comm));
         c->nccl_comm = nullptr;
     }
@@ -1849,11 +1883,83 @@ int pimcb_reduce_bins(pimcb_ctx* c, int root, long* num_total) {
     NCCLCHK(g_nccl.Reduce(cnt, cnt + 1, 1, /*ncclInt64*/ 4, /*ncclSum*/ 0, root, c->nccl_comm, c->stream));
     NCCLCHK(g_nccl.GroupEnd());
     if (c->comm_rank == root) {
-        long long total = 0;
-        CU(cudaMemcpyAsync(&total, cnt + 1, sizeof total, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        c->n_acc = static_cast<long>(total);          // the root's bin now holds every rank's configurations
-        if (num_total) *num_total = static_cast<long>(total);
+        // the root's bin now holds every rank's configurations.  With num_total the call waits for the count; without, it
+        // returns with everything enqueued and the count is picked up by the next pimcb_read_bins (which synchronises
+        // anyway): no host synchronisation per bin, so the next bin's launches queue up behind the collective.
+        if ((rc = c->h_cnt.ensure(sizeof(long long)))) return rc;
+        CU(cudaMemcpyAsync(c->h_cnt.p, cnt + 1, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+        c->n_acc_pending = true;
+        if (num_total) {
+            if ((rc = settle_count(c, false))) return rc;
+            *num_total = c->n_acc;
+        }
+    } else if (num_total) {
+        *num_total = 0;
+    }
+    return 0;
+}
+
+// The same exchange, pipelined: _begin snapshots the folded bin and its count and starts the reduce on the library's
+// communication stream; the caller resets the bin and goes on measuring; _end (one bin later, or whenever the row is
+// written) waits for the snapshot's reduce and hands the global bin to the root.  One exchange in flight per ctx.
+int pimcb_reduce_bins_begin(pimcb_ctx* c, int root) {
+    if (!c) return fail(PIMCB_EINVAL, "null ctx");
+    if (!c->nccl_comm) return fail(PIMCB_ESTATE, "pimcb_comm_init has not been called");
+    if (root < 0 || root >= c->comm_size) return fail(PIMCB_EINVAL, "root %d out of range", root);
+    if (!c->bins_len) return fail(PIMCB_ESTATE, "no measurement accumulated yet");
+    if (c->xchg_inflight) return fail(PIMCB_ESTATE, "the previous exchange has not been collected (pimcb_reduce_bins_end)");
+    CU(cudaSetDevice(c->device));
+    NvtxRange range("pimcb:reduce_bins_begin");
+    int rc;
+    if ((rc = settle_count(c, false))) return rc;
+    if (!c->comm_stream) {
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));          // hi = numerically lowest = highest priority
+        CU(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
+        CU(cudaEventCreateWithFlags(&c->xchg_ready, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->xchg_done, cudaEventDisableTiming));
+    }
+    if ((rc = fold_binrows(c, c->bins_M))) return rc;
+    const size_t len = c->bins_len, bytes = sizeof(double) * len;
+    if ((rc = c->d_xchg.ensure(bytes + 2 * sizeof(long long)))) return rc;
+    if ((rc = c->h_xchg.ensure(bytes + 2 * sizeof(long long)))) return rc;
+    long long* hcnt = reinterpret_cast<long long*>(static_cast<char*>(c->h_xchg.p) + bytes);
+    long long* dcnt = reinterpret_cast<long long*>(static_cast<char*>(c->d_xchg.p) + bytes);
+    hcnt[0] = c->n_acc;
+    hcnt[1] = 0;
+    CU(cudaMemcpyAsync(c->d_xchg.p, c->d_bins.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaEventRecord(c->xchg_ready, c->stream));
+    CU(cudaStreamWaitEvent(c->comm_stream, c->xchg_ready, 0));
+    CU(cudaMemcpyAsync(dcnt, hcnt, sizeof(long long), cudaMemcpyHostToDevice, c->comm_stream));
+    NCCLCHK(g_nccl.GroupStart());
+    NCCLCHK(g_nccl.Reduce(c->d_xchg.p, c->d_xchg.p, len, /*ncclDouble*/ 8, /*ncclSum*/ 0, root, c->nccl_comm, c->comm_stream));
+    NCCLCHK(g_nccl.Reduce(dcnt, dcnt + 1, 1, /*ncclInt64*/ 4, /*ncclSum*/ 0, root, c->nccl_comm, c->comm_stream));
+    NCCLCHK(g_nccl.GroupEnd());
+    if (c->comm_rank == root) {
+        CU(cudaMemcpyAsync(c->h_xchg.p, c->d_xchg.p, bytes, cudaMemcpyDeviceToHost, c->comm_stream));
+        CU(cudaMemcpyAsync(hcnt + 1, dcnt + 1, sizeof(long long), cudaMemcpyDeviceToHost, c->comm_stream));
+    }
+    CU(cudaEventRecord(c->xchg_done, c->comm_stream));
+    c->xchg_inflight = true;
+    c->xchg_root = root;
+    c->xchg_nq = c->nq;
+    c->xchg_M = c->bins_M;
+    c->xchg_len = len;
+    return 0;
+}
+
+int pimcb_reduce_bins_end(pimcb_ctx* c, double* ssf, double* isf, long* num_total) {
+    if (!c) return fail(PIMCB_EINVAL, "null ctx");
+    if (!c->xchg_inflight) return fail(PIMCB_ESTATE, "no exchange in flight (pimcb_reduce_bins_begin)");
+    CU(cudaSetDevice(c->device));
+    NvtxRange range("pimcb:reduce_bins_end");
+    CU(cudaEventSynchronize(c->xchg_done));
+    c->xchg_inflight = false;
+    if (c->comm_rank == c->xchg_root) {
+        const double* h = static_cast<const double*>(c->h_xchg.p);
+        if (ssf) std::memcpy(ssf, h, sizeof(double) * c->xchg_nq);
+        if (isf) std::memcpy(isf, h + c->xchg_nq, sizeof(double) * (c->xchg_len - c->xchg_nq));
+        if (num_total) *num_total = static_cast<long>(reinterpret_cast<const long long*>(h + c->xchg_len)[1]);
     } else if (num_total) {
         *num_total = 0;
     }

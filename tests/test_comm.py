@@ -40,6 +40,32 @@ def test_single_rank_communicator(orc):
         assert np.array_equal(g_ssf, ssf1) and np.array_equal(g_isf, isf1)
         with pytest.raises(api.PimcbError):
             ctx.gather_bins_q([len(q) + 1])
+        # the reduce that waits for nothing: the count arrives with the next read, and measuring on top of the reduced bin
+        # picks it up first
+        assert ctx.reduce_bins(0, want_total=False) == 0
+        assert ctx.read_bins()[2] == 6
+        ctx.reduce_bins(0, want_total=False)
+        ctx.stage(batch[:2], s.N).measure()
+        ssf2, _, n2 = ctx.read_bins()
+        assert n2 == 8
+        ctx.reduce_bins(0, want_total=False)
+        ctx.reset_bins()
+        ctx.stage(batch[:1], s.N).measure()
+        assert ctx.read_bins()[2] == 1
+        # the pipelined exchange: the snapshot of a bin is reduced while the next bin accumulates
+        ctx.reset_bins()
+        with pytest.raises(api.PimcbError):
+            ctx.reduce_bins_end()                                # nothing in flight
+        ctx.stage(batch, s.N).measure()
+        ctx.reduce_bins_begin(0)
+        with pytest.raises(api.PimcbError):
+            ctx.reduce_bins_begin(0)                             # one exchange at a time
+        ctx.reset_bins()
+        ctx.stage(batch[:2], s.N).measure()                      # the next bin, while the first one travels
+        ssf3, isf3, n3 = ctx.reduce_bins_end()
+        assert n3 == 6 and np.array_equal(ssf3, ssf1) and np.array_equal(isf3, isf1)
+        ssf4, _, n4 = ctx.read_bins()
+        assert n4 == 2 and not np.array_equal(ssf4, ssf1)
         ctx.comm_destroy()
     ref = sum(orc.ssf(s.side, b, s.N, q) for b in batch)
     np.testing.assert_allclose(ssf1, ref, rtol=1e-10)
@@ -77,12 +103,25 @@ def _rank(rank, world, uid, mode, ret):
     with api.Context(rank, 3) as ctx:
         ctx.set_box(s.side)
         ctx.comm_init(world, rank, uid)
-        if mode == "cfg":
+        if mode == "cfg_pipe":
             ctx.set_qvecs(q)
             lo, hi = multi.shard_range(len(batch), world, rank)
             ctx.stage(batch[lo:hi], s.N).measure()
-            n = ctx.reduce_bins(0)
+            ctx.reduce_bins_begin(0)
+            ctx.reset_bins()
+            ctx.stage(batch[lo:lo + 1], s.N).measure()               # next bin: one configuration per rank
+            ssf, isf, n = ctx.reduce_bins_end()
+            ctx.reduce_bins_begin(0)
+            ssf_b, _, n_b = ctx.reduce_bins_end()
+            ret[rank] = (n, 6 if rank == 0 else 3, ssf, isf, n_b, ssf_b)
+        elif mode in ("cfg", "cfg_async"):
+            ctx.set_qvecs(q)
+            lo, hi = multi.shard_range(len(batch), world, rank)
+            ctx.stage(batch[lo:hi], s.N).measure()
+            n = ctx.reduce_bins(0, want_total=(mode == "cfg"))       # cfg_async: nothing waited for, count with read_bins
             ssf, isf, cnt = ctx.read_bins()
+            if mode == "cfg_async":
+                n = cnt if rank == 0 else 0
             ret[rank] = (n, cnt, ssf, isf)
         else:
             lo, hi = multi.shard_range(len(q), world, rank)
@@ -93,7 +132,7 @@ def _rank(rank, world, uid, mode, ret):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["cfg", "q"])
+@pytest.mark.parametrize("mode", ["cfg", "cfg_async", "cfg_pipe", "q"])
 def test_two_rank_reduce_and_gather(orc, mode):
     import torch
     import torch.multiprocessing as mp
@@ -108,9 +147,12 @@ def test_two_rank_reduce_and_gather(orc, mode):
     batch = synth.gen_batch(s, 6, first=80)
     ssf_ref = sum(orc.ssf(s.side, b, s.N, q) for b in batch)
     isf_ref = sum(orc.isf_factorised(b, s.N, q) for b in batch)
-    if mode == "cfg":
-        n, cnt, ssf, isf = ret[0]
+    if mode in ("cfg", "cfg_async", "cfg_pipe"):
+        n, cnt, ssf, isf = ret[0][:4]
         assert n == 6 and cnt == 6 and ret[1][0] == 0 and ret[1][1] == 3
+        if mode == "cfg_pipe":                                   # the second bin: configurations 0 and 3
+            assert ret[0][4] == 2 and ret[1][4] == 0
+            np.testing.assert_allclose(ret[0][5], orc.ssf(s.side, batch[0], s.N, q) + orc.ssf(s.side, batch[3], s.N, q), rtol=1e-10)
         np.testing.assert_allclose(ssf, ssf_ref, rtol=1e-10)
         np.testing.assert_allclose(isf, isf_ref, rtol=1e-10, atol=1e-9)
     else:
