@@ -264,3 +264,16 @@ long B200Session::reduceBins(int root) {
     check(pimcb_reduce_bins(ctx_, root, &total), "pimcb_reduce_bins");
     return total;
 }
+
+void B200Session::reduceBinsBegin(int root) {
+    check(pimcb_reduce_bins_begin(ctx_, root), "pimcb_reduce_bins_begin");
+}
+
+long B200Session::reduceBinsEnd(std::vector<double>& ssf, std::vector<double>& isf) {
+    const int M = path_.numTimeSlices;
+    long total = 0;
+    ssf.assign(nq_, 0.0);
+    isf.assign(nq_ * M, 0.0);
+    check(pimcb_reduce_bins_end(ctx_, ssf.data(), isf.data(), &total), "pimcb_reduce_bins_end");
+    return total;
+}

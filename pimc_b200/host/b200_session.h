@@ -57,6 +57,11 @@ public:
     static void uniqueId(void* id128);
     void commInit(int nranks, int rank, const void* id128);
     long reduceBins(int root);
+    // the same exchange pipelined over output bins: reduceBinsBegin snapshots the bin and starts its reduce on the
+    // library's communication stream (resetBins and the next bin's measureBatch may follow at once); reduceBinsEnd waits
+    // for it and fills the global bin on the root (returns its configuration count, 0 elsewhere)
+    void reduceBinsBegin(int root);
+    long reduceBinsEnd(std::vector<double>& ssf, std::vector<double>& isf);
 
     // Scattering variants of the current configuration: the elastic-scattering increment [nq] and the
     // cylinder S(q) raw sums [nq] + the number of slice-0 beads inside maxR.
