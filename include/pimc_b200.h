@@ -61,8 +61,9 @@ int pimcb_num_commensurate(const pimcb_ctx* ctx);
  * (DMMA), falling back to the CUDA-core lattice kernel and then to the generic one when the q-set does not fit;
  * 2 = force the CUDA-core lattice kernel.  Results agree to rounding; the switch exists for A/B measurement. */
 int pimcb_set_rho_mode(pimcb_ctx* ctx, int mode);
-/* tau-correlation kernel: 1 = FP64 tensor cores (DMMA) when M <= 510 (default), 0 = CUDA-core register-tiled kernel
- * (any M).  Results agree to rounding; A/B switch. */
+/* tau-correlation kernel: FP64 tensor cores (DMMA) when M <= 510 -- 1 = one CTA per (four configurations, q), 2 =
+ * persistent CTAs that stage the next pair while the current one is multiplied (bit-identical to 1) -- or 0 = CUDA-core
+ * register-tiled kernel (any M).  Results agree to rounding; A/B switch. */
 int pimcb_set_corr_mode(pimcb_ctx* ctx, int mode);
 
 /* ---- bead staging ------------------------------------------------------------------------------

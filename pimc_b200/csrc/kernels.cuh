@@ -1008,6 +1008,175 @@ __global__ void __launch_bounds__(128) isf_corr_mma_kernel(const double* __restr
     }
 }
 
+// The same correlation with PERSISTENT CTAs and the staging of the next work item overlapped with the tensor work of the
+// current one.  isf_corr_mma_kernel launches one CTA per (four configurations, q) and spends 40 % of its instructions
+// outside the DMMA loops: index arithmetic of the staging (modulo M, padded index, one global address per element and
+// image), which every warp repeats for every pair although none of it depends on the pair; the FP64 datapath is 2/3 busy
+// (profiles/r02q_kernels.md) although a DMMA loop fed from shared memory keeps it 93 % busy (tools/micro/dmma_lds.cu).
+// Here a CTA walks the items blockIdx.x, blockIdx.x + gridDim.x, ... and
+//   1. per item, each warp writes the pair it holds in REGISTERS (M unique values of C and of S, slice t = lane + 32 u)
+//      to its staging area: both periodic images of a value from the one register copy, a dozen integer instructions
+//      per value,
+//   2. issues the loads of its NEXT pair into those registers (not waited for) and, on the bin path, of the row segment
+//      the item will be added to,
+//   3. runs the DMMA loops of the current pair, 4. parks / stores the result.
+// PARTIAL: the four configurations' F(tau) meet in a small double-buffered parking area, ONE CTA barrier per item.
+// Same arithmetic and the same summation order as isf_corr_mma_kernel: results are bit-identical.
+// Requires M >= 64 MTC + 11 (at most two images per value); the host falls back to isf_corr_mma_kernel otherwise.
+// MEASURED (C2, profiles/r02u_corr_experiments.md): 17.6 us per 64 configurations against 16.7 us for
+// isf_corr_mma_kernel -- not faster, so corr mode 1 stays the default and this kernel is the A/B leg (corr mode 2).
+template <int MTC, bool PARTIAL>
+__global__ void __launch_bounds__(128, (MTC == 1 ? 7 : (MTC == 2 ? 6 : (MTC == 3 ? 4 : 3)))) isf_corr_mma_pipe_kernel(
+    const double* __restrict__ rho, double* __restrict__ out, int M, int nq, int B, double invN,
+    const unsigned char* __restrict__ commensurate, int nitems) {
+    extern __shared__ __align__(16) double sm[];
+    constexpr int OFF = 64 * MTC;
+    constexpr int U = 4 * MTC;                               // values per lane and array: M <= 128 MTC - 2
+    const int Mpad = (M + 3) & ~3;
+    const int ext = OFF + Mpad + 8;                          // extended length in elements
+    const int plen = corrm_idx(ext) + 4;                     // padded doubles per array
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int half = M / 2;
+    double* dc = sm + (2 * warp) * plen;
+    double* ds = dc + plen;
+    double* park = sm + 8 * plen;                            // [2][4][half + 1] (PARTIAL; 0 doubles otherwise)
+    const int fi = lane >> 2, fk = lane & 3;                 // fragment row / k index of this lane
+    const int nfull = M >> 2;                                // k-steps with all four s < M
+    const int nks = Mpad >> 2;
+
+    // 0. the item-independent part of the staging, per lane: value u is slice t = lane + 32 u; its first periodic image is
+    //    element e0 = (t + OFF) mod M = first + 32 u (- M), its second e0 + M when that is inside the extended array.
+    const int first = (lane + OFF) % M;
+    const int tstep = 8 * nq * 8;                            // rho_slice_off(t + 32) - rho_slice_off(t)
+    const int toff0 = static_cast<int>(rho_slice_off(lane, nq));
+    double pc[U], ps[U];                                     // the pair held for the next staging step
+    auto prefetch = [&](int item) {
+        const bool ok = item < nitems;
+        const int bq = ok ? item / nq : 0, iq = ok ? item - bq * nq : 0;
+        const int b = min(4 * bq + warp, B - 1);             // dead warps read a valid pair and never use it
+        const double* rc = rho + rho_pair_base(b, iq, 0, nq, rho_tblocks(M));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int o = lane + 32 * u < M ? toff0 + u * tstep : 0;      // lanes past the end read slice 0 and park it
+            pc[u] = __ldg(rc + o);
+            ps[u] = __ldg(rc + 4 + o);
+        }
+    };
+    prefetch(blockIdx.x);
+    int parity = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, parity ^= 1) {
+        const int bq = item / nq, iq = item - bq * nq;
+        const int b = 4 * bq + warp;
+        const bool live = b < B;
+        // 1. registers -> staging area
+        // (the staging indices do not depend on the item; ptxas hoists all 4 U of them out of the loop and spills them to
+        // local memory -- an opaque copy of `first` per item keeps them a dozen integer instructions instead)
+        int first_i = first;
+        asm volatile("" : "+r"(first_i));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            int e0 = first_i + 32 * u;
+            if (e0 >= M) e0 -= M;                            // first < M and 32 u <= t < M: one wrap at most
+            const int e1 = e0 + M;
+            int k0 = corrm_idx(e0), k1 = e1 < ext ? corrm_idx(e1) : k0;     // a missing second image repeats the first
+            if (lane + 32 * u >= M) k0 = k1 = 8;             // index 8 of the padded layout is a slot nothing reads
+            dc[k0] = pc[u]; ds[k0] = ps[u];
+            dc[k1] = pc[u]; ds[k1] = ps[u];
+        }
+        __syncwarp();
+        // 2. the next item's pair on its way while this one is multiplied -- and, on the bin path, this item's row segment
+        //    (read-add-write below): fetched now, so that its latency is not paid behind the barrier
+        prefetch(item + gridDim.x);
+        constexpr int RV = (64 * MTC + 127) / 128;           // row values per thread: half + 1 <= 64 MTC
+        double rowv[RV];
+        if constexpr (PARTIAL) {
+            const double* row = out + (static_cast<size_t>(bq) * nq + iq) * (half + 1);
+#pragma unroll
+            for (int r = 0; r < RV; ++r) {
+                const int tau = threadIdx.x + 128 * r;
+                rowv[r] = tau <= half ? __ldcg(row + tau) : 0.0;
+            }
+        }
+        // 3. tensor work (identical to isf_corr_mma_kernel)
+        double acc[2][MTC][2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int m = 0; m < MTC; ++m) acc[e][m][0] = acc[e][m][1] = 0.0;
+        if (live) {
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                const double* E = part ? ds : dc;
+                const double* pa = E + corrm_idx(fk - 8 * fi + OFF);
+                const double* pb0 = E + corrm_idx(fk + fi + OFF);
+                const double* pb1 = E + corrm_idx(4 + fk + fi + OFF);
+                const int hmax = nfull >> 1;
+#pragma unroll 2
+                for (int h = 0; h < hmax; ++h) {
+                    const double bv0 = pb0[12 * h], bv1 = pb1[12 * h];
+                    double av0[MTC], av1[MTC];
+#pragma unroll
+                    for (int m = 0; m < MTC; ++m) { av0[m] = pa[12 * h - 96 * m]; av1[m] = pa[12 * h + 4 - 96 * m]; }
+#pragma unroll
+                    for (int m = 0; m < MTC; ++m) dmma8x8x4(acc[0][m], av0[m], bv0);
+#pragma unroll
+                    for (int m = 0; m < MTC; ++m) dmma8x8x4(acc[1][m], av1[m], bv1);
+                }
+                for (int ks = 2 * hmax; ks < nks; ++ks) {    // at most two: a full even k-step and / or the masked tail
+                    const int h = ks >> 1, sidx = 4 * ks + fk;
+                    const double bv = (ks & 1) ? pb1[12 * h] : pb0[12 * h];
+#pragma unroll
+                    for (int m = 0; m < MTC; ++m) {
+                        const double v = pa[12 * h + 4 * (ks & 1) - 96 * m];
+                        const double vm = sidx < M ? v : 0.0;
+                        if (ks & 1) dmma8x8x4(acc[1][m], vm, bv); else dmma8x8x4(acc[0][m], vm, bv);
+                    }
+                }
+            }
+        }
+        __syncwarp();                                        // every lane is done reading the staging area
+        // 4. results
+        if constexpr (!PARTIAL) {
+            if (live) {
+                const size_t row_len = static_cast<size_t>(nq) + static_cast<size_t>(nq) * M;
+                double* row = out + static_cast<size_t>(b) * row_len;
+                double* dst = row + nq + static_cast<size_t>(iq) * M;
+#pragma unroll
+                for (int m = 0; m < MTC; ++m)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int tau = 64 * m + 8 * fi + 2 * fk + e;
+                        if (tau > half) continue;
+                        const double val = (acc[0][m][e] + acc[1][m][e]) * invN;
+                        dst[tau] = val;
+                        if (tau > 0 && tau < M - tau) dst[M - tau] = val;
+                        if (tau == 0 && commensurate[iq]) row[iq] = val;
+                    }
+            }
+        } else {
+            // the four configurations in fixed order (b0 .. b0+3; dead warps contribute exact zeros).  The parking area is
+            // double buffered by item parity: the barrier of item n + 1 orders the adds of item n before the parking of n + 2
+            double* pk = park + (parity * 4 + warp) * (half + 1);
+#pragma unroll
+            for (int m = 0; m < MTC; ++m)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int tau = 64 * m + 8 * fi + 2 * fk + e;
+                    if (tau <= half) pk[tau] = (acc[0][m][e] + acc[1][m][e]) * invN;
+                }
+            __syncthreads();
+            const double* p0 = park + (parity * 4) * (half + 1);
+            double* row = out + (static_cast<size_t>(bq) * nq + iq) * (half + 1);
+#pragma unroll
+            for (int r = 0; r < RV; ++r) {
+                const int tau = threadIdx.x + 128 * r;
+                if (tau <= half)
+                    row[tau] = rowv[r] + (((p0[tau] + p0[(half + 1) + tau]) + p0[2 * (half + 1) + tau]) + p0[3 * (half + 1) + tau]);
+            }
+        }
+    }
+}
+
 // Folds the persistent quad rows into the bin (fixed row order), mirrors tau -> M - tau, S(q) = F(q,0) for commensurate
 // q, and clears the rows.  Runs once per bin read-out, not per measurement.
 __global__ void __launch_bounds__(128) bins_fold_kernel(double* __restrict__ rows, double* __restrict__ bins, int nrows, int nq, int M,

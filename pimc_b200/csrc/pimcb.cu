@@ -118,7 +118,8 @@ struct pimcb_ctx {
     int lattice_J = 0;                     // 0 = choose from N; else forced (PIMCB_LATTICE_J)
     int lattice_warps = kLatticeWarps;     // warps per CTA of the lattice kernel (PIMCB_LATTICE_WARPS may lower it to 2)
     int rho_mode = 1;
-    int corr_mode = 1;                     // 1 = DMMA tau-correlation when M <= 510, 0 = CUDA-core kernel (PIMCB_CORR_MODE)
+    int corr_mode = 1;                     // DMMA tau-correlation when M <= 510: 1 = one CTA per item, 2 = persistent CTAs with the
+                                           // next pair prefetched behind the tensor work; 0 = CUDA-core kernel (PIMCB_CORR_MODE)
     // beads
     Slot slots[kSlots];
     int cur = -1;
@@ -527,10 +528,16 @@ int launch_corr(pimcb_ctx* c, const Slot& s, int* partial_rows = nullptr) {
     KTimer kt(c, K_CORR);
     if (partial_rows) *partial_rows = s.B;
     const int mtc = (s.M / 2 + 1 + 63) / 64;                      // 64-tau accumulator tiles of the DMMA formulation
-    if (c->corr_mode == 1 && mtc <= 4) {
+    if (c->corr_mode >= 1 && mtc <= 4) {
+        // 2: persistent CTAs, next pair prefetched behind the DMMAs (at most two periodic images per value: M >= 64 mtc + 11)
+        const bool pipe = c->corr_mode == 2 && s.M >= 64 * mtc + 11;
         const int off = 64 * mtc, mpad = (s.M + 3) & ~3, ext = off + mpad + 8;
         const int plen = ext + 4 * (ext >> 3) + 4;
         size_t smem = sizeof(double) * 2 * static_cast<size_t>(plen) * 4;
+        if (pipe) {
+            size_t park = partial_rows ? 8 * static_cast<size_t>(s.M / 2 + 1) : 0;   // double-buffered parking area (doubles)
+            smem += sizeof(double) * park;
+        }
         // PIMCB_CORR_OCC=n: pad the shared-memory request so that at most n CTAs are resident per SM (occupancy A/B)
         static const int corr_occ = std::getenv("PIMCB_CORR_OCC") ? std::atoi(std::getenv("PIMCB_CORR_OCC")) : 0;
         if (corr_occ > 0) smem = std::max(smem, static_cast<size_t>(226 * 1024) / corr_occ - 1024);
@@ -552,10 +559,21 @@ int launch_corr(pimcb_ctx* c, const Slot& s, int* partial_rows = nullptr) {
         isf_corr_mma_kernel<MTC, PART><<<quads * c->nq, 128, smem, c->stream>>>(c->d_rho.as<double>(),                          \
                                                                                 PART ? c->d_binrows.as<double>() : c->d_cfg.as<double>(), \
                                                                                 s.M, c->nq, s.B, 1.0 / s.N, c->d_comm.as<unsigned char>())
-#define LAUNCH_CORR_MMA(MTC) if (partial) { LAUNCH_CORR_MMA2(MTC, true); } else { LAUNCH_CORR_MMA2(MTC, false); }
+#define LAUNCH_CORR_PIPE2(MTC, PART)                                                                               \
+        { rc = set_smem(isf_corr_mma_pipe_kernel<MTC, PART>, smem); if (rc) return rc;                             \
+          int occ = 1;                                                                                             \
+          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, isf_corr_mma_pipe_kernel<MTC, PART>, 128, smem)); \
+          const int nitems = quads * c->nq;                                                                        \
+          const int pgrid = std::max(1, std::min(nitems, c->sm_count * std::max(1, occ)));                         \
+          isf_corr_mma_pipe_kernel<MTC, PART><<<pgrid, 128, smem, c->stream>>>(c->d_rho.as<double>(),              \
+                                                                                PART ? c->d_binrows.as<double>() : c->d_cfg.as<double>(), \
+                                                                                s.M, c->nq, s.B, 1.0 / s.N, c->d_comm.as<unsigned char>(), nitems); }
+#define LAUNCH_CORR_MMA(MTC) if (pipe) { if (partial) LAUNCH_CORR_PIPE2(MTC, true) else LAUNCH_CORR_PIPE2(MTC, false) }       \
+                             else if (partial) { LAUNCH_CORR_MMA2(MTC, true); } else { LAUNCH_CORR_MMA2(MTC, false); }
         if (mtc == 1) { LAUNCH_CORR_MMA(1) } else if (mtc == 2) { LAUNCH_CORR_MMA(2) } else if (mtc == 3) { LAUNCH_CORR_MMA(3) } else { LAUNCH_CORR_MMA(4) }
 #undef LAUNCH_CORR_MMA
 #undef LAUNCH_CORR_MMA2
+#undef LAUNCH_CORR_PIPE2
         CU(cudaGetLastError());
         if (partial) *partial_rows = 0;         // accumulated into the persistent quad rows by the kernel
         return 0;
@@ -846,7 +864,7 @@ int pimcb_create(pimcb_ctx** out, int device, int ndim) {
     c->device = device;
     c->ndim = ndim;
     if (const char* e = std::getenv("PIMCB_LATTICE_J")) c->lattice_J = std::atoi(e);
-    if (const char* e = std::getenv("PIMCB_CORR_MODE")) c->corr_mode = std::atoi(e) ? 1 : 0;
+    if (const char* e = std::getenv("PIMCB_CORR_MODE")) c->corr_mode = std::max(0, std::min(2, std::atoi(e)));
     if (const char* e = std::getenv("PIMCB_GRAPH")) c->use_graph = std::atoi(e) ? 1 : 0;
     if (const char* e = std::getenv("PIMCB_LATTICE_WARPS")) {
         const int w = std::atoi(e);
@@ -1148,7 +1166,7 @@ int pimcb_set_rho_mode(pimcb_ctx* c, int mode) {
 }
 
 int pimcb_set_corr_mode(pimcb_ctx* c, int mode) {
-    if (!c || mode < 0 || mode > 1) return fail(PIMCB_EINVAL, "corr mode must be 0 or 1");
+    if (!c || mode < 0 || mode > 2) return fail(PIMCB_EINVAL, "corr mode must be 0, 1 or 2");
     c->corr_mode = mode;
     c->cfg_slot = -1;
     return 0;

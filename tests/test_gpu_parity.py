@@ -218,7 +218,7 @@ def test_odd_slice_counts(api, orc, M):
     batch = np.stack([synth.gen_config(N, M, 3, s.rho, 2.0, seed=71 + b) for b in range(3)])
     q = synth.commensurate_q(7, s.side, include_zero=True)
     ref = np.array([orc.isf(batch[b], N, q, nthreads=2) for b in range(3)])
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         with make_ctx(api, s, q) as ctx:
             ctx.set_corr_mode(mode)
             ssf, isf = ctx.stage(batch, N).ssf_isf()
@@ -234,25 +234,54 @@ def test_odd_slice_counts(api, orc, M):
 
 @pytest.mark.parametrize("M", [2, 4, 6, 14, 62, 126, 128, 130, 254, 258, 382, 386, 510, 512, 640])
 def test_tau_correlation_kernels(api, orc, M):
-    """Both tau-correlation kernels (1 = DMMA, up to M = 510 then falls back; 0 = CUDA cores) over time-slice counts
-    that straddle every 64-tau accumulator tile boundary of the DMMA formulation, two configurations per batch."""
+    """The tau-correlation kernels (1 = DMMA, 2 = DMMA with persistent CTAs and the next pair prefetched, both up to
+    M = 510 then falling back; 0 = CUDA cores) over time-slice counts that straddle every 64-tau accumulator tile boundary
+    of the DMMA formulation, two configurations per batch."""
     N = 5
     s = synth.Shape("corr", 3, N, M, 2.0, 0.02198, 0)
     batch = np.stack([synth.gen_config(N, M, 3, s.rho, 2.0, seed=31 + b) for b in range(2)])
     q = np.vstack([synth.commensurate_q(5, s.side, include_zero=True), synth.float_q(2, 3)])
     out = {}
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         with make_ctx(api, s, q) as ctx:
             ctx.set_corr_mode(mode)
             out[mode] = ctx.stage(batch, N).ssf_isf()
+    assert np.array_equal(out[1][1], out[2][1]) and np.array_equal(out[1][0], out[2][0]), "modes 1 and 2: same arithmetic"
     for b in range(2):
         ref_f = orc.isf_factorised(batch[b], N, q)
         ref_s = orc.ssf(s.side, batch[b], N, q)
-        for mode in (0, 1):
+        for mode in (0, 1, 2):
             assert_parity(out[mode][1][b], ref_f, f"isf corr mode {mode} M={M}")
             assert_parity(out[mode][0][b], ref_s, f"ssf corr mode {mode} M={M}")
     if M <= 62:
         assert_parity(out[1][1][0], orc.isf(batch[0], N, q, nthreads=4), f"isf direct M={M}")
+
+
+def test_tau_correlation_persistent_ctas_walk_many_items(api, orc):
+    """corr mode 2 with more work items than resident CTAs (1776 quads x q on 148 x <= 7 CTAs): every CTA loops, the
+    prefetched pair of item n + 1 must not leak into item n, the double-buffered parking area of the bin path must hold.
+    Per-configuration results and the bin are bit-identical to mode 1; a sample of configurations against the oracle."""
+    N, M = 6, 76                                        # M >= 64 + 11: the persistent kernel's two-image staging table applies
+    s = synth.Shape("pipe", 3, N, M, 2.0, 0.02198, 0)
+    uniq = synth.gen_batch(s, 37, first=500)
+    B = 1481                                            # not a multiple of 4: the last quad has dead warps
+    batch = np.ascontiguousarray(uniq[np.arange(B) % len(uniq)])
+    q = synth.commensurate_q(5, s.side, include_zero=True)
+    res = {}
+    for mode in (1, 2):
+        with make_ctx(api, s, q) as ctx:
+            ctx.set_corr_mode(mode)
+            ssf, isf = ctx.stage(batch, N).ssf_isf()
+            ctx.reset_bins()
+            ctx.measure()
+            ctx.measure()                               # accumulates on top of the persistent rows
+            res[mode] = (ssf, isf) + ctx.read_bins()
+    for a, b in zip(res[1], res[2]):
+        assert np.array_equal(a, b)
+    assert res[2][4] == 2 * B
+    for b in (0, 36, 1480):
+        assert_parity(res[2][1][b], orc.isf_factorised(batch[b], N, q), f"persistent corr, configuration {b}")
+    assert_parity(res[2][3], 2.0 * res[2][1].sum(axis=0), "bin = sum of the per-configuration rows, twice")
 
 
 @pytest.mark.parametrize("split", [1, 2, 3, 5])
