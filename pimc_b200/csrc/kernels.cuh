@@ -443,12 +443,17 @@ __device__ __forceinline__ void dmma8x8x4(double (&c)[2], double a, double b) {
 // scoreboard, and the "prefetch" waits for itself (21 % of all stall samples in profiles/r01j).
 // NM > 0 (3-D only): every |n_d| <= NM, the power recurrences and the (a,b) column loop are fully unrolled with the
 // powers held in registers; NM = 0: run-time loop bounds.
-template <int ND, int MT, int NT, int NM>
+template <int ND, int MT, int NT, int NM, bool DIRECT = false>
 __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __restrict__ pos, const MmaPlan plan,
                                                                double* __restrict__ rho, int nslices, int N, int Npad, int nq,
                                                                int3 nmax, double3 kphase, unsigned* __restrict__ sched,
                                                                int zero_mask, int split, double* __restrict__ partial, int M,
-                                                               unsigned ticket_wrap) {
+                                                               unsigned ticket_wrap, int3 stride, double* __restrict__ soa_out) {
+    // DIRECT = false: `pos` is the library's own pos[slice][d][Npad] layout; stride and soa_out are ignored (and this
+    //   instantiation compiles exactly as it did before they existed -- as run-time values they cost the batched path 5 %).
+    // DIRECT = true (single-walker graph): `pos` is the reference's beads array itself, double[slice][N_ext][ND], read over
+    //   the host link from inside this kernel; stride = (N_ext ND, ND, 1) doubles per (slice, particle, dimension); the
+    //   transposed copy that the other kernels expect is written to soa_out on the way.
     constexpr int ML = MT, NR = NT;                         // every tile is computed; unused rows / cols are zero planes
     constexpr int ntile = ML * NR;
     constexpr unsigned FULL = 0xffffffffu;
@@ -499,10 +504,17 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
         const int i = ch * kMmaChunk + il;
         x[0] = x[1] = x[2] = 0.0;
         if (sl < nslices && i < N) {
-            const double* ps = pos + static_cast<size_t>(sl) * ND * Npad + (i + dep);
-            x[0] = __ldg(ps);
-            if constexpr (ND > 1) x[1] = __ldg(ps + Npad);
-            if constexpr (ND > 2) x[2] = __ldg(ps + 2 * Npad);
+            if constexpr (DIRECT) {
+                const double* ps = pos + static_cast<size_t>(sl) * stride.x + static_cast<size_t>(i + dep) * stride.y;
+                x[0] = __ldg(ps);
+                if constexpr (ND > 1) x[1] = __ldg(ps + stride.z);
+                if constexpr (ND > 2) x[2] = __ldg(ps + 2 * stride.z);
+            } else {
+                const double* ps = pos + static_cast<size_t>(sl) * ND * Npad + (i + dep);
+                x[0] = __ldg(ps);
+                if constexpr (ND > 1) x[1] = __ldg(ps + Npad);
+                if constexpr (ND > 2) x[2] = __ldg(ps + 2 * Npad);
+            }
         }
     };
     // Work item = (slice, part): `split` warps (anywhere on the GPU) share the particle blocks of a slice when there
@@ -527,6 +539,12 @@ __global__ void __launch_bounds__(128) rho_lattice_mma_kernel(const double* __re
             // ---- phase A: thread = particle of the chunk -------------------------------------------------
             {
                 const bool live = ch * kMmaChunk + il < N;
+                if (DIRECT && ch * kMmaChunk + il < Npad) {                  // the transposed copy (zeros beyond N)
+                    double* dst = soa_out + static_cast<size_t>(sl) * ND * Npad + ch * kMmaChunk + il;
+                    dst[0] = xc[0];
+                    if constexpr (ND > 1) dst[Npad] = xc[1];
+                    if constexpr (ND > 2) dst[2 * Npad] = xc[2];
+                }
                 // Particles beyond N (ragged last block) must add nothing: their R entries (the powers of the last
                 // dimension's phase, incl. the column of ones) are zeroed with selects, so every product L x R vanishes
                 // and the L side needs no mask -- FP64 instructions are the scarce resource here, selects are not.

@@ -382,7 +382,28 @@ int build_unfold(pimcb_ctx* c, int NR) {
 }
 
 // ---- rho_q build + correlation + direct S(q) into d_cfg (per configuration results) ------------
-int launch_rho(pimcb_ctx* c, const Slot& s) {
+// Tile shape and shared memory of the DMMA formulation for the current q-set; false when it does not apply.
+static bool rho_mma_shape(const pimcb_ctx* c, int* ML_out, int* NR_out, size_t* smem_out) {
+    const int nd = c->ndim;
+    auto up = [](int v) { return v <= 1 ? 1 : (v <= 2 ? 2 : (v <= 4 ? 4 : (v <= 8 ? 8 : 16))); };
+    const int mlx = (c->mma_nL + 7) / 8, nrx = (c->mma_nR + 7) / 8;        // exact tile counts
+    const int NR = c->mma_nR > 0 ? up(nrx) : 0;
+    const int ML = c->mma_nL > 0 ? ((NR <= 2 && mlx <= 8) ? mlx : up(mlx)) : 0;   // MT = 1..8 compiled exactly for NT <= 2
+    const bool mma_fits = ML > 0 && NR > 0 && c->mma_nL <= 128 && NR <= 4 && ML * NR <= 16 &&
+                          c->mma_lmap.size() <= 81 && c->mma_rmap.size() <= 17 && (nd < 3 || c->nmax[1] <= 8);
+    const size_t mma_smem = sizeof(double) * kMmaWarps * (8 * static_cast<size_t>(ML + NR) * kMmaStride + static_cast<size_t>(ML) * NR * 64) +
+                            sizeof(unsigned) * 2 * static_cast<size_t>(c->nq);
+                            // per-warp operand planes + C staging, CTA copy of the unfold table
+    if (ML_out) *ML_out = ML;
+    if (NR_out) *NR_out = NR;
+    if (smem_out) *smem_out = mma_smem;
+    return c->rho_mode == 1 && c->ngroups > 0 && mma_fits && mma_smem <= 160 * 1024;
+}
+
+// aos_src != nullptr (single-walker graph, DMMA formulation only -- check rho_mma_shape first): the kernel reads the
+// reference's beads array double[M][Next][nd] at aos_src (device-visible: the page-locked host array itself) instead of
+// s.pos, and writes s.pos on the way.
+int launch_rho(pimcb_ctx* c, const Slot& s, const double* aos_src = nullptr) {
     const int nd = c->ndim, nq = c->nq;
     const int nsl = s.B * s.M;
     const size_t limit = 200 * 1024;
@@ -399,16 +420,11 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
     KTimer kt(c, K_RHO);
     const int grid = grid_for(c, nsl, 8);
     // DMMA formulation: tile counts rounded up to a compiled accumulator shape MT x NT (MT*NT <= 16)
-    auto up = [](int v) { return v <= 1 ? 1 : (v <= 2 ? 2 : (v <= 4 ? 4 : (v <= 8 ? 8 : 16))); };
-    const int mlx = (c->mma_nL + 7) / 8, nrx = (c->mma_nR + 7) / 8;        // exact tile counts
-    const int NR = c->mma_nR > 0 ? up(nrx) : 0;
-    const int ML = c->mma_nL > 0 ? ((NR <= 2 && mlx <= 8) ? mlx : up(mlx)) : 0;   // MT = 1..8 compiled exactly for NT <= 2
-    const bool mma_fits = ML > 0 && NR > 0 && c->mma_nL <= 128 && NR <= 4 && ML * NR <= 16 &&
-                          c->mma_lmap.size() <= 81 && c->mma_rmap.size() <= 17 && (nd < 3 || c->nmax[1] <= 8);
-    const size_t mma_smem = sizeof(double) * kMmaWarps * (8 * static_cast<size_t>(ML + NR) * kMmaStride + static_cast<size_t>(ML) * NR * 64) +
-                            sizeof(unsigned) * 2 * static_cast<size_t>(nq);
-                            // per-warp operand planes + C staging, CTA copy of the unfold table
-    if (c->rho_mode == 1 && c->ngroups > 0 && mma_fits && mma_smem <= 160 * 1024) {
+    int ML = 0, NR = 0;
+    size_t mma_smem = 0;
+    const bool use_mma = rho_mma_shape(c, &ML, &NR, &mma_smem);
+    if (aos_src && !use_mma) return fail(PIMCB_ESTATE, "the direct beads-array form needs the DMMA rho_q kernel");
+    if (use_mma) {
         const int3 nmax = make_int3(c->nmax[0], c->nmax[1], c->nmax[2]);
         const double twopi = 2.0 * M_PI;
         const double3 kph = make_double3(twopi / c->side[0], nd > 1 ? twopi / c->side[1] : 0.0, nd > 2 ? twopi / c->side[2] : 0.0);
@@ -426,10 +442,10 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
         int pgrid = 0;
         const int nchunk = (s.N + kMmaChunk - 1) / kMmaChunk;      // 32-particle blocks per slice
         const int nm3 = std::max(c->nmax[0], std::max(c->nmax[1], c->nmax[2]));
-#define LAUNCH_MMA_NM(ND, MT, NT, NM)                                                                             \
-        { rc = set_smem(rho_lattice_mma_kernel<ND, MT, NT, NM>, mma_smem); if (rc) return rc;                      \
+#define LAUNCH_MMA_NM2(ND, MT, NT, NM, DIRECT)                                                                             \
+        { rc = set_smem(rho_lattice_mma_kernel<ND, MT, NT, NM, DIRECT>, mma_smem); if (rc) return rc;                      \
         int occ = 1;                                                                                               \
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rho_lattice_mma_kernel<ND, MT, NT, NM>, 128, mma_smem)); \
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rho_lattice_mma_kernel<ND, MT, NT, NM, DIRECT>, 128, mma_smem)); \
         if (const char* e = std::getenv("PIMCB_RHO_OCC")) occ = std::max(1, std::min(occ, std::atoi(e)));          \
         const int wmax = c->sm_count * std::max(1, occ) * kMmaWarps;          /* resident warps of a full grid */   \
         int split = 1;                                                         /* warps sharing one slice */         \
@@ -446,10 +462,14 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
         }                                                                                                          \
         const int items = nsl * split;                                                                             \
         pgrid = std::max(1, std::min((items + kMmaWarps - 1) / kMmaWarps, c->sm_count * std::max(1, occ)));        \
-        rho_lattice_mma_kernel<ND, MT, NT, NM><<<pgrid, 128, mma_smem, c->stream>>>(s.pos.as<double>(), plan, c->d_rho.as<double>(), \
+        rho_lattice_mma_kernel<ND, MT, NT, NM, DIRECT><<<pgrid, 128, mma_smem, c->stream>>>(DIRECT ? aos_src : s.pos.as<double>(), plan,         \
+                                                                                    c->d_rho.as<double>(),                   \
                                                                                     nsl, s.N, s.Npad, nq, nmax, kph,         \
                                                                                     c->d_sched.as<unsigned>(), 0, split,     \
-                                                                                    c->d_partial.as<double>(), s.M, 0xffffffffu); }
+                                                                                    c->d_partial.as<double>(), s.M, 0xffffffffu, \
+                                                                                    make_int3(s.Next * ND, ND, 1),           \
+                                                                                    DIRECT ? s.pos.as<double>() : nullptr); }
+#define LAUNCH_MMA_NM(ND, MT, NT, NM) { if (aos_src) LAUNCH_MMA_NM2(ND, MT, NT, NM, true) else LAUNCH_MMA_NM2(ND, MT, NT, NM, false) }
         // 3-D with every |n_d| <= 2 (or 3): phase A fully unrolled; the R columns then fit one N tile
 #define LAUNCH_MMA(ND, MT, NT)                                                                                    \
         if (ND == 3 && NT == 1 && nm3 <= 2) LAUNCH_MMA_NM(ND, MT, NT, (ND == 3 && NT == 1 ? 2 : 0))                \
@@ -467,6 +487,7 @@ int launch_rho(pimcb_ctx* c, const Slot& s) {
                              default: LAUNCH_MMA(ND, 4, 4) break; } }
         if (nd == 1) { LAUNCH_MMA_SHAPE(1) } else if (nd == 2) { LAUNCH_MMA_SHAPE(2) } else { LAUNCH_MMA_SHAPE(3) }
 #undef LAUNCH_MMA_SHAPE
+#undef LAUNCH_MMA_NM2
 #undef LAUNCH_MMA_M8
 #undef LAUNCH_MMA
 #undef LAUNCH_MMA_NM
@@ -1300,8 +1321,17 @@ int fused_capture(pimcb_ctx* c, const double* beads, int M, int N, int Next, dou
         // arrays, so the zero-copy form is used up to 2 MB.  PIMCB_ZEROCOPY=0 / 1 forces it off / on.
         static const int zc_env = std::getenv("PIMCB_ZEROCOPY") ? std::atoi(std::getenv("PIMCB_ZEROCOPY")) : -1;
         const bool zerocopy = zc_env < 0 ? aos_bytes <= (2u << 20) : zc_env != 0;
+        // ... and with the DMMA rho_q kernel not even the transpose kernel is needed: the rho kernel reads the beads array
+        // where it lies and writes the transposed copy (for the pair / virial kernels that may follow) on the way.
+        // PIMCB_RHO_DIRECT=0 keeps the transpose node (A/B).
+        static const int direct_env = std::getenv("PIMCB_RHO_DIRECT") ? std::atoi(std::getenv("PIMCB_RHO_DIRECT")) : 1;
         void* mapped = nullptr;
-        if (zerocopy && cudaHostGetDevicePointer(&mapped, const_cast<double*>(beads), 0) == cudaSuccess && mapped) {
+        const double* rho_src = nullptr;
+        if (zerocopy && direct_env != 0 && rho_mma_shape(c, nullptr, nullptr, nullptr) &&
+            cudaHostGetDevicePointer(&mapped, const_cast<double*>(beads), 0) == cudaSuccess && mapped) {
+            rho_src = static_cast<const double*>(mapped);
+            s.needs_transpose = false;
+        } else if (zerocopy && cudaHostGetDevicePointer(&mapped, const_cast<double*>(beads), 0) == cudaSuccess && mapped) {
             const size_t tsmem = sizeof(double) * N * nd;
             const int nslc = M;
             const int tgrid = std::min(nslc, c->sm_count * 8);
@@ -1318,7 +1348,7 @@ int fused_capture(pimcb_ctx* c, const double* beads, int M, int N, int Next, dou
             s.needs_transpose = true;
         }
         ok = ok && materialize(c, s) == 0;
-        ok = ok && launch_rho(c, s) == 0;
+        ok = ok && launch_rho(c, s, rho_src) == 0;
         ok = ok && launch_corr(c, s) == 0;
         ok = ok && cudaMemcpyAsync(c->h_out.p, c->d_cfg.p, sizeof(double) * len, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess;
         cudaGraph_t graph = nullptr;
@@ -1337,7 +1367,7 @@ int fused_capture(pimcb_ctx* c, const double* beads, int M, int N, int Next, dou
     }
     pimcb_ctx::FusedGraph& g = c->fused;
     g.src = beads; g.M = M; g.N = N; g.Next = Next; g.slot = slot; g.qgen = c->qgen; g.rho_mode = c->rho_mode; g.corr_mode = c->corr_mode;
-    g.launches = c->launches - launches0;           // kernels per replay (transpose, rho_q, tau-correlation)
+    g.launches = c->launches - launches0;           // kernels per replay ([transpose,] rho_q, tau-correlation)
     fused_addresses(c, s, g.baked);
     CU(cudaGraphLaunch(g.exec, c->stream));
     return fused_finish(c, s, slot, ssf_out, isf_out);

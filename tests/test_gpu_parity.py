@@ -1,6 +1,8 @@
 """GPU parity: CUDA path (through the C ABI) vs the CPU oracle on identical seeded inputs."""
 import math
 
+import os
+
 import numpy as np
 import pytest
 
@@ -515,6 +517,41 @@ def test_error_paths(api):
             ctx.pair_sums(1.0)                        # no table
 
 
+@pytest.mark.parametrize("N,pad", [(45, 3), (64, 0), (150, 5)])
+def test_graph_replay_leaves_the_transposed_beads_for_the_pair_kernels(api, orc, nthreads, N, pad):
+    """In the captured single-walker call the rho_q kernel reads the page-locked beads array itself and writes the
+    transposed copy on the way (no transpose kernel).  Whatever runs next on the same ctx -- pimcb_pair_sums here, what
+    LocalActionB200 does after an estimator's accumulate() -- must find exactly the staged layout: ragged last particle
+    block, padded source rows (N_ext > N), zero padding up to Npad."""
+    M = 10
+    s = synth.Shape("direct", 3, N, M, 2.0, 0.02198, 0)
+    q = synth.commensurate_q(12, s.side)
+    cfgs = np.stack([synth.gen_config(N, M, 3, s.rho, 2.0, seed=900 + k, pad=pad) for k in range(4)])
+    V, dV, dr = orc.aziz_table(orc.max_sep(s.side))
+    dSep = 0.5 * math.sqrt(3.0) * s.side[2] / 50.0
+    pa = api.PinnedArray(cfgs.shape[1:])
+    try:
+        with make_ctx(api, s, q) as ctx, make_ctx(api, s, q) as plain:
+            ctx.set_pair_table(V, dV, dr)
+            plain.set_pair_table(V, dV, dr)
+            for k in range(4):
+                pa.array[...] = cfgs[k]
+                n0 = ctx.launch_count()
+                a = ctx.ssf_isf_beads(pa.array, N)
+                if k >= 2 and os.environ.get("PIMCB_RHO_DIRECT") != "0":
+                    assert ctx.launch_count() - n0 == 2                      # replay: rho_q + tau-correlation
+                b = plain.stage(cfgs[k], N).ssf_isf()
+                assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+                gv, gf, gh = ctx.pair_sums(dSep)                             # on the copy the rho kernel left behind
+                pv, pf, ph = plain.pair_sums(dSep)
+                assert np.array_equal(gv, pv) and np.array_equal(gf, pf) and np.array_equal(gh, ph), f"call {k}"
+            cv, cf, ch = orc.pair_sums(s.side, cfgs[3], N, V, dV, dr, dSep, nthreads=nthreads)
+            assert_parity(gv[0], cv, "Vint after a graph replay")
+            assert np.array_equal(gh[0], ch)
+    finally:
+        pa.free()
+
+
 def test_fused_single_walker_call_graph_replay(api, orc, nthreads):
     """pimcb_ssf_isf_beads with a page-locked source: call 1 runs the ordinary path, call 2 captures the CUDA graph,
     later calls replay it.  Every call must return exactly what the ordinary path returns for the CURRENT contents of the
@@ -531,7 +568,9 @@ def test_fused_single_walker_call_graph_replay(api, orc, nthreads):
                 n0 = ctx.launch_count()
                 got.append(ctx.ssf_isf_beads(pa.array, s.N))
                 if k >= 2:
-                    assert ctx.launch_count() - n0 == 3            # transpose, rho_q, tau-correlation per replay
+                    # rho_q (reading the page-locked beads array itself, leaving the transposed copy behind) and the
+                    # tau-correlation per replay; PIMCB_RHO_DIRECT=0 puts the transpose kernel back in front
+                    assert ctx.launch_count() - n0 == (3 if os.environ.get("PIMCB_RHO_DIRECT") == "0" else 2)
                 ref_ssf, ref_isf = plain.stage(cfgs[k], s.N).ssf_isf()
                 assert np.array_equal(got[-1][0], ref_ssf) and np.array_equal(got[-1][1], ref_isf), f"call {k}"
             assert_parity(got[5][0][0], orc.ssf(s.side, cfgs[5], s.N, q, nthreads=nthreads), "graph replay S(q)")
