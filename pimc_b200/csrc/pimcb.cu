@@ -1257,7 +1257,8 @@ int pimcb_ssf_isf(pimcb_ctx* c, double* ssf_out, double* isf_out) {
 //
 // Graph path.  An estimator's accumulate() calls this once per measurement with the same page-locked source
 // (Path::beads), the same shape and the same q-set, so after one ordinary call (which sizes every buffer) the fixed
-// sequence  H2D(AoS) -> aos_to_soa -> rho_q build -> tau-correlation -> D2H  is captured from the compute stream into
+// sequence  [H2D(AoS) -> aos_to_soa ->] rho_q build -> tau-correlation -> D2H  (the bracketed nodes disappear when the rho
+// kernel can read the page-locked array in place, see fused_capture)  is captured from the compute stream into
 // a CUDA graph and replayed: one cudaGraphLaunch + one synchronisation per measurement instead of five enqueues on two
 // streams with an event between them.  Every address baked into the graph is re-checked before a replay; anything that
 // changes (source pointer, shape, q-set, kernel mode, a buffer that had to grow) drops the graph and the ordinary path
