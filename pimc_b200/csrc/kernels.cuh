@@ -1069,8 +1069,8 @@ __global__ void __launch_bounds__(128, (MTC == 1 ? 7 : (MTC == 2 ? 6 : (MTC == 3
     const int toff0 = static_cast<int>(rho_slice_off(lane, nq));
     double pc[U], ps[U];                                     // the pair held for the next staging step
     auto prefetch = [&](int item) {
-        const bool ok = item < nitems;
-        const int bq = ok ? item / nq : 0, iq = ok ? item - bq * nq : 0;
+        if (item >= nitems) return;                          // no next item: the registers are never read again
+        const int bq = item / nq, iq = item - bq * nq;
         const int b = min(4 * bq + warp, B - 1);             // dead warps read a valid pair and never use it
         const double* rc = rho + rho_pair_base(b, iq, 0, nq, rho_tblocks(M));
 #pragma unroll
