@@ -60,7 +60,16 @@ struct PairTileParams {
     int G;                 // particle groups of 32
     int spc;               // slices per CTA work unit (> 1 when a slice has fewer groups than the CTA has warps)
     const TableSector* VD; // (V, dV/dr) packed four entries per 32-byte sector (table_codec.h), or nullptr: verbatim tables only
+    // slice selection: sel_p < 0: the launch covers every slice; sel_p = 0 / 1: only the slices with (t mod 2) == sel_p,
+    // sel_cnt of them per configuration; the kernel's `nslices` then counts SELECTED slices.  A gsf call is two launches:
+    // the force kernel on the slices that carry gradVSquared, the V-only kernel (fewer registers, more warps) on the rest.
+    int sel_p, sel_cnt;
 };
+__device__ __forceinline__ int pair_slice_of(const PairTileParams& pp, int u) {
+    if (pp.sel_p < 0) return u;
+    const int b = u / pp.sel_cnt;
+    return b * pp.M + 2 * (u - b * pp.sel_cnt) + pp.sel_p;
+}
 
 // One whole 32-byte sector per lane in one request (LDG.E.256).
 __device__ __forceinline__ TableSector ldg_sector(const TableSector* p) {
@@ -268,21 +277,26 @@ __device__ __forceinline__ void pair_tile(const double* __restrict__ xsl, int NP
 #ifndef PIMCB_PTILE_MINB
 #define PIMCB_PTILE_MINB 3
 #endif
-template <int ND, bool CODEC>
-__global__ void __launch_bounds__(32 * kPairWarps, PIMCB_PTILE_MINB)
+#ifndef PIMCB_PTILE_MINB_V
+#define PIMCB_PTILE_MINB_V 4
+#endif
+// FK = true: the force-capable kernel (slices selected by pp.f2_parity get gradVSquared).  FK = false: V-only -- no force
+// code, no force accumulators in shared memory, 64 registers: four CTAs (32 warps) per SM instead of three.
+template <int ND, bool CODEC, bool FK = true>
+__global__ void __launch_bounds__(32 * kPairWarps, (FK ? PIMCB_PTILE_MINB : PIMCB_PTILE_MINB_V))
 pair_tile_kernel(const double* __restrict__ pos, int nslices, int N, int Npad, BoxDev box, PairTileParams pp,
                  double* __restrict__ vint, double* __restrict__ f2, int* __restrict__ hist) {
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) double sm[];
     const int G = pp.G, spc = pp.spc, NP = 32 * G;
     double* xs = sm;                                            // [spc][ND][NP]
-    double* accF = xs + static_cast<size_t>(spc) * ND * NP;     // [spc][ND][NP]     total force per particle
-    double* part = accF + static_cast<size_t>(spc) * ND * NP;   // [kPairRound][spc][ND][NP] partner-side sums per offset
-    double* redV = part + static_cast<size_t>(kPairRound) * spc * ND * NP;   // [spc * G]  per-home V sums
+    double* accF = xs + static_cast<size_t>(spc) * ND * NP;     // [spc][ND][NP]     total force per particle (FK only)
+    double* part = accF + (FK ? static_cast<size_t>(spc) * ND * NP : 0);   // [kPairRound][spc][ND][NP] partner-side sums per offset (FK only)
+    double* redV = part + (FK ? static_cast<size_t>(kPairRound) * spc * ND * NP : 0);   // [spc * G]  per-home V sums
     int* shist = reinterpret_cast<int*>(redV + spc * G + (spc * G & 1));     // [spc][kNPCFSEP]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int omax = G / 2;                                     // largest group offset (a half tile when G is even)
-    const bool f2_any = f2 != nullptr;
+    const bool f2_any = FK && f2 != nullptr;
     const int nunits = (nslices + spc - 1) / spc;
 
     for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
@@ -291,7 +305,7 @@ pair_tile_kernel(const double* __restrict__ pos, int nslices, int N, int Npad, B
         // stage the slices of this unit: rows padded to whole groups (the padding is never counted as a particle)
         for (int k = threadIdx.x; k < nsl * ND * NP; k += blockDim.x) {
             const int s = k / (ND * NP), rem = k - s * (ND * NP), d = rem / NP, i = rem - d * NP;
-            xs[k] = i < Npad ? __ldg(pos + (static_cast<size_t>(sl0 + s) * ND + d) * Npad + i) : 0.0;
+            xs[k] = i < Npad ? __ldg(pos + (static_cast<size_t>(pair_slice_of(pp, sl0 + s)) * ND + d) * Npad + i) : 0.0;
             if (f2_any) accF[k] = 0.0;
         }
         if (pp.ix.want_hist)
@@ -302,7 +316,7 @@ pair_tile_kernel(const double* __restrict__ pos, int nslices, int N, int Npad, B
         for (int o1 = 1; o1 == 1 || o1 <= omax; o1 += kPairRound) {
             for (int h = warp; h < nsl * G; h += kPairWarps) {
                 const int sloc = h / G, a = h - sloc * G;
-                const int sl = sl0 + sloc, t = sl % pp.M;
+                const int sl = pair_slice_of(pp, sl0 + sloc), t = sl % pp.M;
                 const bool do_f = f2_any && (pp.f2_parity < 0 || (t & 1) == pp.f2_parity);
                 const double* xsl = xs + static_cast<size_t>(sloc) * ND * NP;
                 int* shist_sl = shist + sloc * kNPCFSEP;
@@ -325,7 +339,7 @@ pair_tile_kernel(const double* __restrict__ pos, int nslices, int N, int Npad, B
                     double Gv[ND];
 #pragma unroll
                     for (int d = 0; d < ND; ++d) Gv[d] = 0.0;
-                    if (do_f) {
+                    if (FK && do_f) {
                         if (full) pair_tile<ND, true, CODEC, false>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, false, N, box, pp, shist_sl, vsum, Fi, Gv);
                         else pair_tile<ND, true, CODEC, true>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, o == 0, N, box, pp, shist_sl, vsum, Fi, Gv);
                         if (o == 0) {
@@ -341,7 +355,7 @@ pair_tile_kernel(const double* __restrict__ pos, int nslices, int N, int Npad, B
                         else pair_tile<ND, false, CODEC, true>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, o == 0, N, box, pp, shist_sl, vsum, Fi, Gv);
                     }
                 }
-                if (do_f) {
+                if (FK && do_f) {
 #pragma unroll
                     for (int d = 0; d < ND; ++d) accF[(static_cast<size_t>(sloc) * ND + d) * NP + i] += Fi[d];   // this lane is the only writer
                 }
@@ -354,7 +368,7 @@ pair_tile_kernel(const double* __restrict__ pos, int nslices, int N, int Npad, B
                 // fold the partner-side slots of this round, offsets ascending (fixed order)
                 for (int k = threadIdx.x; k < nsl * ND * NP; k += blockDim.x) {
                     const int sloc = k / (ND * NP);
-                    const int t = (sl0 + sloc) % pp.M;
+                    const int t = pair_slice_of(pp, sl0 + sloc) % pp.M;
                     if (!(pp.f2_parity < 0 || (t & 1) == pp.f2_parity)) continue;
                     const int rem = k - sloc * (ND * NP);
                     double acc = accF[k];
@@ -367,10 +381,10 @@ pair_tile_kernel(const double* __restrict__ pos, int nslices, int N, int Npad, B
         }
         // per-slice results: Vint = sum of the home sums (home order), sum_i |F_i + gradVext_i|^2
         for (int sloc = warp; sloc < nsl; sloc += kPairWarps) {
-            const int sl = sl0 + sloc, t = sl % pp.M;
+            const int sl = pair_slice_of(pp, sl0 + sloc), t = sl % pp.M;
             const bool do_f = f2_any && (pp.f2_parity < 0 || (t & 1) == pp.f2_parity);
             double fsum = 0.0;
-            if (do_f) {
+            if (FK && do_f) {
                 for (int i = lane; i < N; i += 32) {
 #pragma unroll
                     for (int d = 0; d < ND; ++d) {

@@ -1674,15 +1674,35 @@ int pimcb_pair_sums(pimcb_ctx* c, double* vint, double* f2, int* sephist, double
             static const int packed_env = std::getenv("PIMCB_PAIR_PACKED") ? std::atoi(std::getenv("PIMCB_PAIR_PACKED")) : -1;
             const bool use_packed = c->vd_ok && (packed_env < 0 ? f2 != nullptr : packed_env != 0);
             PairTileParams tp{c->d_V.as<double>(), c->d_dV.as<double>(), ixp, f2_parity, s->M, pp.gext, G, spc,
-                              use_packed ? c->d_VD.as<TableSector>() : nullptr};
-            const int units = (nsl + spc - 1) / spc;
-#define LAUNCH_PTILE2(ND, CODEC)                                                                                   \
-            rc = set_smem(pair_tile_kernel<ND, CODEC>, smem_tile); if (rc) return rc;                               \
-            pair_tile_kernel<ND, CODEC><<<units, 32 * kPairWarps, smem_tile, c->stream>>>(s->pos.as<double>(), nsl, s->N, s->Npad, c->box, tp, \
+                              use_packed ? c->d_VD.as<TableSector>() : nullptr, -1, 0};
+            // the V-only kernel needs neither force accumulators nor partner slots
+            const size_t smem_v = sizeof(double) * (static_cast<size_t>(spc) * nd * 32 * G + spc * G + 1) + sizeof(int) * spc * kNPCFSEP;
+#define LAUNCH_PTILE2(ND, CODEC, FK, NSEL, SMEM)                                                                   \
+            { rc = set_smem(pair_tile_kernel<ND, CODEC, FK>, SMEM); if (rc) return rc;                              \
+            pair_tile_kernel<ND, CODEC, FK><<<((NSEL) + spc - 1) / spc, 32 * kPairWarps, SMEM, c->stream>>>(s->pos.as<double>(), NSEL, s->N, s->Npad, c->box, tp, \
                                                                                   c->d_vint.as<double>(), f2 ? c->d_f2.as<double>() : nullptr, \
-                                                                                  c->d_hist.as<int>())
-#define LAUNCH_PTILE(ND) if (use_packed) { LAUNCH_PTILE2(ND, true); } else { LAUNCH_PTILE2(ND, false); }
-            if (nd == 1) { LAUNCH_PTILE(1) } else if (nd == 2) { LAUNCH_PTILE(2) } else { LAUNCH_PTILE(3) }
+                                                                                  c->d_hist.as<int>()); }
+#define LAUNCH_PTILE(ND, FK, NSEL, SMEM) if (tp.VD) LAUNCH_PTILE2(ND, true, FK, NSEL, SMEM) else LAUNCH_PTILE2(ND, false, FK, NSEL, SMEM)
+#define LAUNCH_PTILE_ND(FK, NSEL, SMEM) { if (nd == 1) { LAUNCH_PTILE(1, FK, NSEL, SMEM) } else if (nd == 2) { LAUNCH_PTILE(2, FK, NSEL, SMEM) } else { LAUNCH_PTILE(3, FK, NSEL, SMEM) } }
+            // PIMCB_PAIR_SPLIT=0: one launch of the force-capable kernel over all slices, as before (A/B)
+            static const bool split_on = !(std::getenv("PIMCB_PAIR_SPLIT") && std::atoi(std::getenv("PIMCB_PAIR_SPLIT")) == 0);
+            if (!f2) {
+                LAUNCH_PTILE_ND(false, nsl, smem_v)                        // V-only call
+            } else if (split_on && (f2_parity == 0 || f2_parity == 1) && s->M >= 2) {
+                // gsf-type call: the slices that carry gradVSquared go through the force kernel, the others through the
+                // V-only kernel (64 registers, four CTAs per SM; verbatim V table unless PIMCB_PAIR_PACKED=1) -- two launches
+                // over disjoint slices and disjoint outputs
+                const int cnt_f = (s->M - f2_parity + 1) / 2, cnt_v = s->M - cnt_f;
+                tp.sel_p = f2_parity; tp.sel_cnt = cnt_f;
+                LAUNCH_PTILE_ND(true, s->B * cnt_f, smem_tile)
+                c->launches++;
+                tp.sel_p = 1 - f2_parity; tp.sel_cnt = cnt_v;
+                if (packed_env <= 0) tp.VD = nullptr;
+                if (cnt_v > 0) LAUNCH_PTILE_ND(false, s->B * cnt_v, smem_v)
+            } else {
+                LAUNCH_PTILE_ND(true, nsl, smem_tile)                      // forces on every slice (or none selected)
+            }
+#undef LAUNCH_PTILE_ND
 #undef LAUNCH_PTILE
 #undef LAUNCH_PTILE2
         } else if (f2 && sym_on && s->N <= 1024 && smem_sym <= 200 * 1024) {

@@ -464,6 +464,32 @@ def test_pair_sums_ragged_shapes(api, orc, nthreads, ndim, N, M, pad, per):
     assert np.all(gf1[0, 0::2] == 0.0)
 
 
+@pytest.mark.parametrize("M", [1, 5, 6])
+@pytest.mark.parametrize("parity", [0, 1])
+def test_pair_sums_parity_split_over_a_batch(api, orc, nthreads, M, parity):
+    """A gsf-type call (gradVSquared on the slices of one parity) is two launches over disjoint slices: the force kernel on
+    the selected parity, the V-only kernel on the rest.  Batches of several configurations with odd and even slice counts:
+    the slice selection must follow (t mod 2) inside every configuration, every output row must be written exactly once,
+    and the histogram of every slice must be there whichever launch produced it."""
+    N, B = 70, 3
+    s = synth.Shape("split", 3, N, M, 2.0, 0.02198, 0)
+    batch = np.stack([synth.gen_config(N, M, 3, s.rho, 2.0, seed=640 + b) for b in range(B)])
+    V, dV, dr = orc.aziz_table(orc.max_sep(s.side))
+    dSep = 0.5 * math.sqrt(3) * s.side[2] / 50
+    with api.Context(0, 3) as ctx:
+        ctx.set_box(s.side)
+        ctx.set_pair_table(V, dV, dr)
+        ctx.stage(batch, N)
+        gv, gf, gh = ctx.pair_sums(dSep, f2_parity=parity)
+    for b in range(B):
+        cv, cf, ch = orc.pair_sums(s.side, batch[b], N, V, dV, dr, dSep, nthreads=nthreads)
+        assert np.array_equal(gh[b], ch), f"sepHist, configuration {b}"
+        assert_parity(gv[b], cv, f"Vint, configuration {b}")
+        if len(cf[parity::2]):
+            assert_parity(gf[b, parity::2], cf[parity::2], f"gradVSquared on parity {parity}, configuration {b}")
+        assert np.all(gf[b, 1 - parity::2] == 0.0)
+
+
 def test_pair_table_edges(api, orc):
     """Separations below dr (k <= 0 -> extV[0]) and beyond the table (k >= len -> extV[1])."""
     side = np.array([30.0, 30.0, 30.0])
