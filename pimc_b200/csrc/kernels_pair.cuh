@@ -424,7 +424,13 @@ struct VirialTileParams {
     int t2_parity; int M;
     int G; int spc; int rounds;                  // rounds = group offsets per round (partner-side slots that fit)
     const TableSector* DD;                       // (dV/dr, d2V/dr2) packed four entries per sector, or nullptr
+    int sel_p, sel_cnt;                          // slice selection, as in PairTileParams: a gsf call is two launches
 };
+__device__ __forceinline__ int virial_slice_of(const VirialTileParams& vp, int u) {
+    if (vp.sel_p < 0) return u;
+    const int b = u / vp.sel_cnt;
+    return b * vp.M + 2 * (u - b * vp.sel_cnt) + vp.sel_p;
+}
 
 #ifndef PIMCB_VTILE_U
 #define PIMCB_VTILE_U 2
@@ -551,17 +557,23 @@ __device__ __forceinline__ void virial_tile(const double* __restrict__ xsl, int 
 #ifndef PIMCB_VTILE_MINB
 #define PIMCB_VTILE_MINB 2
 #endif
-template <int ND, bool CODEC>
-__global__ void __launch_bounds__(32 * kPairWarps, PIMCB_VTILE_MINB)
+#ifndef PIMCB_VTILE_MINB_G
+#define PIMCB_VTILE_MINB_G 3
+#endif
+// T2K = true: the kernel that can carry the T-matrix terms (slices selected by vp.t2_parity).  T2K = false: gV terms only --
+// ND components per particle instead of ND + ND (ND + 1) / 2 in registers, shared memory and shuffles, no d2V/dr2.
+// NCK = components actually kept; the per-pair code keeps its full-size arrays, whose unused tail the compiler drops.
+template <int ND, bool CODEC, bool T2K = true>
+__global__ void __launch_bounds__(32 * kPairWarps, (T2K ? PIMCB_VTILE_MINB : PIMCB_VTILE_MINB_G))
 virial_tile_kernel(const double* __restrict__ pos, const double* __restrict__ delta, int nslices, int N, int Npad, BoxDev box,
                    VirialTileParams vp, double* __restrict__ out) {
-    constexpr int NT = ND * (ND + 1) / 2, NC = ND + NT;
+    constexpr int NT = ND * (ND + 1) / 2, NC = ND + NT, NCK = T2K ? NC : ND;
     extern __shared__ __align__(16) double sm[];
     const int G = vp.G, spc = vp.spc, NP = 32 * G, R = vp.rounds;
     double* xs = sm;                                            // [spc][ND][NP]
-    double* acc = xs + static_cast<size_t>(spc) * ND * NP;      // [spc][NC][NP]   gV then the upper triangle of T per particle
-    double* part = acc + static_cast<size_t>(spc) * NC * NP;    // [R][spc][NC][NP] partner-side sums per offset
-    double* red = part + static_cast<size_t>(R) * spc * NC * NP;             // [spc][4][kPairWarps]
+    double* acc = xs + static_cast<size_t>(spc) * ND * NP;      // [spc][NCK][NP]  gV then the upper triangle of T per particle
+    double* part = acc + static_cast<size_t>(spc) * NCK * NP;   // [R][spc][NCK][NP] partner-side sums per offset
+    double* red = part + static_cast<size_t>(R) * spc * NCK * NP;            // [spc][4][kPairWarps]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int omax = G / 2;
     const int nunits = (nslices + spc - 1) / spc;
@@ -571,16 +583,16 @@ virial_tile_kernel(const double* __restrict__ pos, const double* __restrict__ de
         const int nsl = min(spc, nslices - sl0);
         for (int k = threadIdx.x; k < nsl * ND * NP; k += blockDim.x) {
             const int s = k / (ND * NP), rem = k - s * (ND * NP), d = rem / NP, i = rem - d * NP;
-            xs[k] = i < Npad ? __ldg(pos + (static_cast<size_t>(sl0 + s) * ND + d) * Npad + i) : 0.0;
+            xs[k] = i < Npad ? __ldg(pos + (static_cast<size_t>(virial_slice_of(vp, sl0 + s)) * ND + d) * Npad + i) : 0.0;
         }
-        for (int k = threadIdx.x; k < nsl * NC * NP; k += blockDim.x) acc[k] = 0.0;
+        for (int k = threadIdx.x; k < nsl * NCK * NP; k += blockDim.x) acc[k] = 0.0;
         __syncthreads();
 
         for (int o1 = 1; o1 == 1 || o1 <= omax; o1 += R) {
             for (int h = warp; h < nsl * G; h += kPairWarps) {
                 const int sloc = h / G, a = h - sloc * G;
-                const int t = (sl0 + sloc) % vp.M;
-                const bool do_t2 = vp.t2_parity == -1 || (vp.t2_parity >= 0 && (t & 1) == vp.t2_parity);
+                const int t = virial_slice_of(vp, sl0 + sloc) % vp.M;
+                const bool do_t2 = T2K && (vp.t2_parity == -1 || (vp.t2_parity >= 0 && (t & 1) == vp.t2_parity));
                 const double* xsl = xs + static_cast<size_t>(sloc) * ND * NP;
                 const int i = 32 * a + lane;
                 const bool ivalid = i < N;
@@ -602,7 +614,7 @@ virial_tile_kernel(const double* __restrict__ pos, const double* __restrict__ de
 #pragma unroll
                     for (int c = 0; c < NC; ++c) vis[c] = 0.0;
                     const bool full = o != 0 && 32 * (a + 1) <= N && 32 * (b + 1) <= N;   // every pair of the tile exists
-                    if (do_t2) {
+                    if (T2K && do_t2) {
                         if (full) virial_tile<ND, true, CODEC, false>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, false, N, box, vp, own, vis);
                         else virial_tile<ND, true, CODEC, true>(xsl, NP, xi, i, ivalid, b, lane, s_lo, s_hi, o == 0, N, box, vp, own, vis);
                     } else {
@@ -611,29 +623,29 @@ virial_tile_kernel(const double* __restrict__ pos, const double* __restrict__ de
                     }
                     if (o == 0) {
 #pragma unroll
-                        for (int c = 0; c < NC; ++c) own[c] += vis[c];
+                        for (int c = 0; c < NCK; ++c) own[c] += vis[c];
                     } else {
-                        double* slot = part + ((static_cast<size_t>(oi) * spc + sloc) * NC) * NP + 32 * b + lane;
+                        double* slot = part + ((static_cast<size_t>(oi) * spc + sloc) * NCK) * NP + 32 * b + lane;
 #pragma unroll
-                        for (int c = 0; c < NC; ++c) slot[c * NP] = vis[c];
+                        for (int c = 0; c < NCK; ++c) slot[c * NP] = vis[c];
                     }
                 }
 #pragma unroll
-                for (int c = 0; c < NC; ++c) acc[(static_cast<size_t>(sloc) * NC + c) * NP + i] += own[c];   // this lane is the only writer
+                for (int c = 0; c < NCK; ++c) acc[(static_cast<size_t>(sloc) * NCK + c) * NP + i] += own[c];   // this lane is the only writer
             }
             __syncthreads();
-            for (int k = threadIdx.x; k < nsl * NC * NP; k += blockDim.x) {        // fold this round's slots, offsets ascending
-                const int sloc = k / (NC * NP), rem = k - sloc * (NC * NP);
+            for (int k = threadIdx.x; k < nsl * NCK * NP; k += blockDim.x) {       // fold this round's slots, offsets ascending
+                const int sloc = k / (NCK * NP), rem = k - sloc * (NCK * NP);
                 double v = acc[k];
-                for (int oi = 0; oi < R && o1 + oi <= omax; ++oi) v += part[(static_cast<size_t>(oi) * spc + sloc) * NC * NP + rem];
+                for (int oi = 0; oi < R && o1 + oi <= omax; ++oi) v += part[(static_cast<size_t>(oi) * spc + sloc) * NCK * NP + rem];
                 acc[k] = v;
             }
             __syncthreads();
         }
         // per slice: sum_i gV.w and (T gV).w for w = r (raw position) and w = delta
         for (int sloc = 0; sloc < nsl; ++sloc) {
-            const int sl = sl0 + sloc;
-            const double* A = acc + static_cast<size_t>(sloc) * NC * NP;
+            const int sl = virial_slice_of(vp, sl0 + sloc);
+            const double* A = acc + static_cast<size_t>(sloc) * NCK * NP;
             const double* xsl = xs + static_cast<size_t>(sloc) * ND * NP;
             double sums[4] = {0.0, 0.0, 0.0, 0.0};
             for (int i = threadIdx.x; i < N; i += blockDim.x) {
@@ -641,7 +653,7 @@ virial_tile_kernel(const double* __restrict__ pos, const double* __restrict__ de
 #pragma unroll
                 for (int d = 0; d < ND; ++d) { gV[d] = A[d * NP + i]; uu[d] = 0.0; }
 #pragma unroll
-                for (int k = 0; k < NT; ++k) T[k] = A[(ND + k) * NP + i];
+                for (int k = 0; k < NT; ++k) T[k] = T2K ? A[(ND + k) * NP + i] : 0.0;
                 int k = 0;
 #pragma unroll
                 for (int p = 0; p < ND; ++p)
@@ -674,7 +686,7 @@ virial_tile_kernel(const double* __restrict__ pos, const double* __restrict__ de
         for (int k = threadIdx.x; k < nsl * 4; k += blockDim.x) {
             double v = 0.0;
             for (int w = 0; w < kPairWarps; ++w) v += red[k * kPairWarps + w];
-            out[static_cast<size_t>(sl0) * 4 + k] = v;
+            out[static_cast<size_t>(virial_slice_of(vp, sl0 + k / 4)) * 4 + (k & 3)] = v;
         }
         __syncthreads();
     }

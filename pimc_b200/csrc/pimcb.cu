@@ -1863,15 +1863,32 @@ int pimcb_virial_sums(pimcb_ctx* c, const double* delta_aos, int t2_parity, doub
         if (!ext && vtile_on && vtile_smem(rounds) <= 200 * 1024 && make_index_params(c, 1.0, false, &ixp)) {
             const bool packed = c->dd_ok && (t2_parity == -2 || c->have_d2V);
             VirialTileParams tp{c->d_dV.as<double>(), c->d_d2V.as<double>(), ixp, t2_parity, s->M, G, spc, rounds,
-                                packed ? c->d_DD.as<TableSector>() : nullptr};
+                                packed ? c->d_DD.as<TableSector>() : nullptr, -1, 0};
             const size_t smem_t = vtile_smem(rounds);
-            const int units = (nsl + spc - 1) / spc;
-#define LAUNCH_VTILE2(ND, CODEC)                                                                                   \
-            rc = set_smem(virial_tile_kernel<ND, CODEC>, smem_t); if (rc) return rc;                                \
-            virial_tile_kernel<ND, CODEC><<<units, 32 * kPairWarps, smem_t, c->stream>>>(s->pos.as<double>(), d_delta, nsl, s->N, s->Npad, \
-                                                                                         c->box, tp, c->d_vir.as<double>())
-#define LAUNCH_VTILE(ND) if (packed) { LAUNCH_VTILE2(ND, true); } else { LAUNCH_VTILE2(ND, false); }
-            if (nd == 1) { LAUNCH_VTILE(1) } else if (nd == 2) { LAUNCH_VTILE(2) } else { LAUNCH_VTILE(3) }
+            // the gV-only kernel keeps nd instead of nc components per particle
+            const size_t smem_g = sizeof(double) * (static_cast<size_t>(spc) * 32 * G * (nd + nd * (1 + rounds)) + static_cast<size_t>(spc) * 4 * kPairWarps);
+#define LAUNCH_VTILE2(ND, CODEC, T2K, NSEL, SMEM)                                                                  \
+            { rc = set_smem(virial_tile_kernel<ND, CODEC, T2K>, SMEM); if (rc) return rc;                           \
+            virial_tile_kernel<ND, CODEC, T2K><<<((NSEL) + spc - 1) / spc, 32 * kPairWarps, SMEM, c->stream>>>(s->pos.as<double>(), d_delta, NSEL, s->N, s->Npad, \
+                                                                                         c->box, tp, c->d_vir.as<double>()); }
+#define LAUNCH_VTILE(ND, T2K, NSEL, SMEM) if (packed) LAUNCH_VTILE2(ND, true, T2K, NSEL, SMEM) else LAUNCH_VTILE2(ND, false, T2K, NSEL, SMEM)
+#define LAUNCH_VTILE_ND(T2K, NSEL, SMEM) { if (nd == 1) { LAUNCH_VTILE(1, T2K, NSEL, SMEM) } else if (nd == 2) { LAUNCH_VTILE(2, T2K, NSEL, SMEM) } else { LAUNCH_VTILE(3, T2K, NSEL, SMEM) } }
+            // PIMCB_VIRIAL_SPLIT=0: one launch of the T-matrix-capable kernel over all slices, as before (A/B)
+            static const bool vsplit_on = !(std::getenv("PIMCB_VIRIAL_SPLIT") && std::atoi(std::getenv("PIMCB_VIRIAL_SPLIT")) == 0);
+            if (t2_parity == -2) {
+                LAUNCH_VTILE_ND(false, nsl, smem_g)                        // no slice carries the T-matrix terms
+            } else if (vsplit_on && (t2_parity == 0 || t2_parity == 1) && s->M >= 2) {
+                // gsf-type call: two launches over disjoint slices and disjoint output rows
+                const int cnt_t = (s->M - t2_parity + 1) / 2, cnt_g = s->M - cnt_t;
+                tp.sel_p = t2_parity; tp.sel_cnt = cnt_t;
+                LAUNCH_VTILE_ND(true, s->B * cnt_t, smem_t)
+                c->launches++;
+                tp.sel_p = 1 - t2_parity; tp.sel_cnt = cnt_g;
+                if (cnt_g > 0) LAUNCH_VTILE_ND(false, s->B * cnt_g, smem_g)
+            } else {
+                LAUNCH_VTILE_ND(true, nsl, smem_t)
+            }
+#undef LAUNCH_VTILE_ND
 #undef LAUNCH_VTILE
 #undef LAUNCH_VTILE2
         } else if (!ext && sym_on && s->N <= 1024 && smem_sym <= 200 * 1024) {

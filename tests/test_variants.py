@@ -264,7 +264,7 @@ def test_virial_sums_vs_oracle(api, orc, nthreads, name):
     if name == "small3d":
         s, window, B = synth.Shape("v3", 3, 37, 10, 2.0, 0.02198, 0), 5, 2
     elif name == "2d":
-        s, window, B = synth.Shape("v2", 2, 40, 9, 1.0, 0.0432, 0), 3, 1
+        s, window, B = synth.Shape("v2", 2, 40, 9, 1.0, 0.0432, 0), 3, 3          # odd M, several configurations
     else:
         s, window, B = synth.C2, 5, 1
     beads = synth.gen_batch(s, B, first=70)
@@ -281,6 +281,7 @@ def test_virial_sums_vs_oracle(api, orc, nthreads, name):
         ctx.set_pair_table_d2(d2V)
         full = ctx.virial_sums(delta, t2_parity=-1)
         odd = ctx.virial_sums(delta, t2_parity=1)
+        even = ctx.virial_sums(delta, t2_parity=0)                    # (two launches each: T-matrix kernel + gV-only kernel)
     for b in range(B):
         ref = orc.virial_sums(s.side, beads[b], s.N, window, dV, d2V, dr, t2_parity=-1, next_links=links, nthreads=nthreads)
         for k, what in enumerate(("sum gV.r", "sum (T gV).r", "sum gV.delta", "sum (T gV).delta")):
@@ -289,6 +290,9 @@ def test_virial_sums_vs_oracle(api, orc, nthreads, name):
         assert np.array_equal(odd[b, 1::2], full[b, 1::2])
         assert np.all(odd[b, 0::2, 1] == 0.0) and np.all(odd[b, 0::2, 3] == 0.0)
         assert np.array_equal(odd[b, 0::2, 0], full[b, 0::2, 0]) and np.array_equal(odd[b, 0::2, 2], full[b, 0::2, 2])
+        assert np.array_equal(even[b, 0::2], full[b, 0::2])
+        assert np.all(even[b, 1::2, 1] == 0.0) and np.all(even[b, 1::2, 3] == 0.0)
+        assert np.array_equal(even[b, 1::2, 0], full[b, 1::2, 0]) and np.array_equal(even[b, 1::2, 2], full[b, 1::2, 2])
 
 
 @pytest.mark.gpu
