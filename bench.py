@@ -835,7 +835,8 @@ def pair_legs(args, ctx, shape, pinned, use_slots, B):
     reads = B * shape.M * pairs if packed else B * ((shape.M - shape.M // 2) * pairs + (shape.M // 2) * 2 * pairs)
     gather_peak = 289.0e9                              # profiles/r02a_gather_peak.txt: 32-byte sectors / s out of L2, footprint <= 53 MB
     pair = {"metric": "pair-potential action sums/s (Vint[M] + gradVSquared[odd slices] + sepHist[M][50] per configuration)",
-            "kernel": ("pair_tile_kernel (32 x 32 tiles, every pair once, division-free exact index" + (", packed (V, dV/dr) sectors)" if packed else ", verbatim tables)"))
+            "kernel": ("pair_tile_kernel (32 x 32 tiles, every pair once, division-free exact index; two launches: force kernel on the "
+                       "gradVSquared slices" + (" reading packed (V, dV/dr) sectors" if packed else "") + ", 64-register V-only kernel on the rest)")
                       if tile else "pair_sym_kernel (ring, every pair once)",
             "value": B / p_s, "unit": "configurations/s", "avg_launch_ms": p_s * 1e3, "launches_timed": pn,
             "configurations_per_launch": B, "ms_per_64_configurations": p_s * 1e3 * 64.0 / B,
@@ -868,7 +869,8 @@ def pair_legs(args, ctx, shape, pinned, use_slots, B):
     pair["virial_sums"] = {"metric": "virial slice sums/s (4 sums per slice; gsf action, window deltas from the host)",
                            "value": B / v_s, "unit": "configurations/s", "avg_launch_ms": v_s * 1e3, "launches_timed": vn,
                            "configurations_per_launch": B, "ms_per_64_configurations": v_s * 1e3 * 64.0 / B,
-                           "kernel": "virial_tile_kernel" + (" (packed (dV/dr, d2V/dr2) sectors)" if vpacked else " (verbatim tables)"),
+                           "kernel": "virial_tile_kernel" + (" (packed (dV/dr, d2V/dr2) sectors" if vpacked else " (verbatim tables")
+                                     + "; two launches: T-matrix kernel on its slices, gV-only kernel on the rest)",
                            "table_reads_per_launch": vg, "table_read_rate_g_per_s": vg / v_s / 1e9,
                            "roofline": {"bound": "L2 sector rate of random 8-byte table reads", "achieved": vg / v_s / 1e9,
                                         "peak": gather_peak / 1e9, "unit": "G reads/s", "frac": vg / v_s / gather_peak}}
