@@ -206,9 +206,13 @@ class CpuArm:
         full = (t1 - t0) * rounds * (s.M / self.Ms) ** 2 + (t2 - t1) * (len(q) / self.n_ssf)
         return full, t2 - t0
 
-    def one_core(self):
+    def one_core(self, repeats=3):
         """Extrapolated seconds per full evaluation on ONE host core (the reference is single-threaded): the same bounded
-        sample, one q through the F(q,tau) loop nest and a few q through S(q), on the calling thread."""
+        sample, one q through the F(q,tau) loop nest and a few q through S(q), on the calling thread; median of `repeats`
+        (a single shot came out 3x slow once on a shared host: r02y)."""
+        return float(np.median([self._one_core_once() for _ in range(max(1, repeats))]))
+
+    def _one_core_once(self):
         s, q = self.shape, self.q
         n1 = max(1, self.n_ssf // self.cores)
         t0 = time.perf_counter()
