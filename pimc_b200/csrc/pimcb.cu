@@ -387,8 +387,10 @@ static bool rho_mma_shape(const pimcb_ctx* c, int* ML_out, int* NR_out, size_t* 
     const int nd = c->ndim;
     auto up = [](int v) { return v <= 1 ? 1 : (v <= 2 ? 2 : (v <= 4 ? 4 : (v <= 8 ? 8 : 16))); };
     const int mlx = (c->mma_nL + 7) / 8, nrx = (c->mma_nR + 7) / 8;        // exact tile counts
-    const int NR = c->mma_nR > 0 ? up(nrx) : 0;
-    const int ML = c->mma_nL > 0 ? ((NR <= 2 && mlx <= 8) ? mlx : up(mlx)) : 0;   // MT = 1..8 compiled exactly for NT <= 2
+    const int NR = c->mma_nR > 0 ? (nrx <= 4 ? nrx : up(nrx)) : 0;         // NT = 1..4 compiled exactly
+    // MT = 1..8 compiled exactly for NT <= 2, MT = 1..4 for NT = 3, 4 (C3's 2-D grid of 17 x 17 q: 3 x 3 tiles; rounded up
+    // to the 4 x 4 shape it ran 16 DMMAs per k-step instead of 9)
+    const int ML = c->mma_nL > 0 ? ((NR <= 2 && mlx <= 8) || (NR > 2 && mlx <= 4) ? mlx : up(mlx)) : 0;
     const bool mma_fits = ML > 0 && NR > 0 && c->mma_nL <= 128 && NR <= 4 && ML * NR <= 16 &&
                           c->mma_lmap.size() <= 81 && c->mma_rmap.size() <= 17 && (nd < 3 || c->nmax[1] <= 8);
     const size_t mma_smem = sizeof(double) * kMmaWarps * (8 * static_cast<size_t>(ML + NR) * kMmaStride + static_cast<size_t>(ML) * NR * 64) +
@@ -483,8 +485,10 @@ int launch_rho(pimcb_ctx* c, const Slot& s, const double* aos_src = nullptr) {
 #define LAUNCH_MMA_SHAPE(ND)                                                                                      \
         if (NR == 1) { if (ML == 16) LAUNCH_MMA(ND, 16, 1) else LAUNCH_MMA_M8(ND, 1) }                             \
         else if (NR == 2) { LAUNCH_MMA_M8(ND, 2) }                                                                 \
+        else if (NR == 3) { switch (ML) { case 1: LAUNCH_MMA(ND, 1, 3) break; case 2: LAUNCH_MMA(ND, 2, 3) break;  \
+                                          case 3: LAUNCH_MMA(ND, 3, 3) break; default: LAUNCH_MMA(ND, 4, 3) break; } } \
         else { switch (ML) { case 1: LAUNCH_MMA(ND, 1, 4) break; case 2: LAUNCH_MMA(ND, 2, 4) break;               \
-                             default: LAUNCH_MMA(ND, 4, 4) break; } }
+                             case 3: LAUNCH_MMA(ND, 3, 4) break; default: LAUNCH_MMA(ND, 4, 4) break; } }
         if (nd == 1) { LAUNCH_MMA_SHAPE(1) } else if (nd == 2) { LAUNCH_MMA_SHAPE(2) } else { LAUNCH_MMA_SHAPE(3) }
 #undef LAUNCH_MMA_SHAPE
 #undef LAUNCH_MMA_NM2
