@@ -1107,7 +1107,13 @@ int pimcb_set_qvecs(pimcb_ctx* c, const double* q, int nq) {
         // stored once (see kernels.cuh, MmaPlan) and one all-zero row / column is reserved at the end
         // The 3-D kernel indexes lmap with the fixed stride 9 (|n_x|, |n_y| <= 8): q-sets beyond that have no DMMA plan
         // (mma_nL = mma_nR = 0) and run on the CUDA-core lattice / generic kernels.
-        const bool dmma_plan = !(nd == 3 && (c->nmax[0] > 8 || c->nmax[1] > 8)) && c->nmax[last] <= 16;
+        bool dmma_plan = !(nd == 3 && (c->nmax[0] > 8 || c->nmax[1] > 8)) && c->nmax[last] <= 16;
+        // ... and every group key is checked against the tables it will index (3-D: lmap[|n_x| * 9 + |n_y|] of (nmax_x + 1) * 9
+        // entries, rmap[|n_last|] of nmax_last + 1): a key outside them drops the DMMA plan instead of writing past a vector
+        // (round-1 advisor finding: |n_y| >= 9 used to corrupt the heap here)
+        for (const Grp& g : groups) {
+            if (g.key[last] > c->nmax[last] || (nd > 1 && g.key[0] > c->nmax[0]) || (nd == 3 && g.key[1] > 8)) dmma_plan = false;
+        }
         c->mma_lmap.clear(); c->mma_rmap.clear(); c->mma_gdesc.clear(); c->mma_gout.clear();
         c->unfold_NR = -1;
         if (dmma_plan) {
@@ -1116,10 +1122,12 @@ int pimcb_set_qvecs(pimcb_ctx* c, const double* q, int nq) {
             int nL = nd == 1 ? 1 : 0, nR = 0;
             if (nd == 1) lmap[0] = 0;
             for (const Grp& g : groups) {
-                int& r = rmap[g.key[last]];
+                const size_t ri = static_cast<size_t>(g.key[last]);
+                const size_t li = nd == 3 ? static_cast<size_t>(g.key[0]) * n1 + g.key[1] : static_cast<size_t>(nd > 1 ? g.key[0] : 0);
+                int& r = rmap[ri];
                 if (r < 0) { r = nR; nR += (g.key[last] > 0 || nd == 1) ? 2 : 1; }
                 if (nd > 1) {
-                    int& l = lmap[nd == 3 ? g.key[0] * n1 + g.key[1] : g.key[0]];
+                    int& l = lmap[li];
                     if (l < 0) {
                         l = nL;
                         if (nd == 3) nL += (g.key[0] > 0 && g.key[1] > 0) ? 4 : ((g.key[0] > 0 || g.key[1] > 0) ? 2 : 1);
