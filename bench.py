@@ -4,7 +4,7 @@
     python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run)
     python bench.py --impl reference ...                     (the CPU restatement of the reference estimators)
 
-A step = ONE OUTPUT BIN of the hot path: `--batches-per-step` (4) batches of B (256) synthetic walker configurations per GPU
+A step = ONE OUTPUT BIN of the hot path: `--batches-per-step` (16) batches of B (512) synthetic walker configurations per GPU
 go through rho_q build + tau-correlation + bin accumulation, then the bin is folded and -- on more than one GPU --
 exchanged once (the library's own NCCL reduce / all-gather), exactly what EstimatorBase::output does per bin.
 `value` = configurations evaluated per second over all ranks with beads resident in HBM; `e2e` = the same through the
@@ -45,10 +45,11 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0,
-                    help="0 = 256 (64 for C4, whose configurations are 7.5x larger); walker configurations per GPU per batch (one launch pair); 64 -> 256 per launch is worth 16 %% "
-                         "(profiles/r02p_corr_occ_and_batch_sweep.txt: fewer ragged last waves of the persistent rho kernel)")
-    ap.add_argument("--batches-per-step", type=int, default=0,
-                    help="batches accumulated into one output bin = one step; 0 = 4 for batches of >= 256 (1024 evaluations), else 16")
+                    help="0 = 512 (64 for C4, whose configurations are 7.5x larger); walker configurations per GPU per batch (one launch pair); "
+                         "64 -> 256 -> 512 per launch is worth 16 %% + 4 %% (profiles/r02p_corr_occ_and_batch_sweep.txt: fewer ragged last "
+                         "waves of the persistent rho kernel, more waves of the tau-correlation)")
+    ap.add_argument("--batches-per-step", type=int, default=16,
+                    help="batches accumulated into one output bin = one step (16 x 512 = 8192 evaluations per GPU)")
     ap.add_argument("--exchange", default="pipelined", choices=["pipelined", "inline"],
                     help="walker sharding on > 1 GPU with --collective lib: pimcb_reduce_bins_begin/_end (the bin's snapshot is reduced "
                          "on the library's communication stream while the next bin is measured) or pimcb_reduce_bins on the compute stream")
@@ -439,13 +440,13 @@ def run_ours(args, shape, q):
     from pimc_b200 import multi
     B, K, W, P = args.batch, args.steps, args.warmup, args.batches_per_step
     if B <= 0:
-        B = 64 if shape.name == "C4" else 256
+        B = 64 if shape.name == "C4" else 512
     if args.total_batch > 0:
         if args.total_batch % world:
             raise SystemExit(f"--total-batch {args.total_batch} is not a multiple of {world} GPUs")
         B = args.total_batch // world
     if P <= 0:
-        P = 4 if B >= 256 else 16
+        P = 16
     q_all = q
     if args.shard == "q" and world > 1:
         lo, hi = multi.shard_range(len(q_all), world, rank)
@@ -668,7 +669,12 @@ def run_ours(args, shape, q):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(plan["path_name"] + "_dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            key = plan["path_name"] + "_dram_bytes_per_launch"
+            traffic = tj.get(key)
+            per = (tj.get("configurations_per_launch") or {}).get(key)
+            if traffic is not None and per and shape.name == "C2":
+                traffic = traffic * B / per            # the capture's launch held `per` configurations, this run's holds B
         except Exception:
             traffic = None
     peaks = {}

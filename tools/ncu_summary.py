@@ -140,11 +140,16 @@ def main():
             except ValueError:
                 merged = {}
         src = merged.get("sources", {}) if isinstance(merged.get("sources"), dict) else {}
+        per = merged.get("configurations_per_launch", {}) if isinstance(merged.get("configurations_per_launch"), dict) else {}
+        batch = int(os.environ.get("PIMCB_PROFILE_BATCH", "512"))      # configurations per launch of the profiled bench run
         for k, v in traffic.items():
             merged[k] = v
             src[k] = tag
+            per[k] = batch
         merged["sources"] = src
-        merged["source"] = "ncu --set full --clock-control none, one launch each (the bench's default batch per launch: 256 C2 configurations from r02q on, 64 before); per-kernel visit tag in `sources`"
+        merged["configurations_per_launch"] = per
+        merged["source"] = ("ncu --set full --clock-control none, one launch each; per-kernel visit tag in `sources`, C2 configurations in that "
+                            "launch in `configurations_per_launch` (bench.py scales the figure to its own batch)")
         with open(path, "w") as f:
             json.dump(merged, f, indent=1)
     with open(os.path.join(out, f"{tag}_kernels.md"), "w") as f:
